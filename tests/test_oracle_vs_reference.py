@@ -1,0 +1,84 @@
+"""Oracle restatement vs the reference's own numpy modules, executed verbatim.
+Runs only where /root/reference is mounted (this container, not the GPU box)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import mpc_oracle as O
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "controllers.py")),
+                                reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, REF)
+    try:
+        import controllers
+        import cost_functions
+    finally:
+        sys.path.remove(REF)
+    return controllers, cost_functions
+
+
+class _Space:
+    def __init__(self, n):
+        self.low, self.high, self.shape = -np.ones(n), np.ones(n), (n,)
+
+
+class _Env:
+    action_space, observation_space = _Space(6), _Space(20)
+
+
+def test_cost_matches_reference_random(ref):
+    _, cf = ref
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        S = rng.standard_normal((257, 20)) * 0.3
+        S[rng.integers(0, 257, 10), rng.integers(5, 8, 10)] = rng.choice([0.0, -0.0, 0.2], 10)
+        N = S + rng.standard_normal((257, 20)) * 0.1
+        assert np.array_equal(cf.cheetah_cost_fn(S, None, N), O.cheetah_cost_fn(S, None, N))
+        assert cf.cheetah_cost_fn(S[3], None, N[3]) == O.cheetah_cost_fn(S[3], None, N[3])
+
+
+@pytest.mark.parametrize("seed,K,H", [(0, 1000, 15), (1, 129, 7), (2, 1, 1)])
+def test_get_action_matches_reference(ref, seed, K, H):
+    ctl, cf = ref
+    rng, norm, weights, state = O.synthetic_problem(seed, (48, 48))
+    dyn = O.OracleDynamics(weights, norm)
+    actions = rng.uniform(-1, 1, (H, K, 6))
+    c = ctl.MPCcontroller(_Env(), dyn, horizon=H, cost_fn=cf.cheetah_cost_fn, num_simulated_paths=K)
+    c.sample_random_actions = lambda: actions
+    want = c.get_action(state)
+    got = O.OracleMPC(dyn, H, K).get_action(state, actions)
+    assert np.array_equal(want, got)
+
+
+def test_policy_controller_matches_reference(ref):
+    ctl, cf = ref
+    rng, norm, weights, state = O.synthetic_problem(4, (48, 48))
+    dyn = O.OracleDynamics(weights, norm)
+    pol = O.OraclePolicy(*O.synthetic_policy(rng, hidden=(16, 16), norm=norm))
+    H, K = 5, 77
+    uni = rng.uniform(-1, 1, (H, K, 6))
+
+    class P:
+        def act(self, ob, stochastic=True):
+            return pol.act(ob, False)
+
+    c = ctl.MPCcontrollerPolicyNet(_Env(), dyn, P(), explore=0.3, self_exp=False, horizon=H,
+                                   cost_fn=cf.cheetah_cost_fn, num_simulated_paths=K)
+    c.sample_random_actions = lambda: uni
+    want = c.get_action(state)
+    got = O.OracleMPC(dyn, H, K, proposal="policy_mix", policy=pol, explore=0.3).get_action(state, uni)
+    assert np.array_equal(want, got)
+
+
+def test_sample_random_actions_layout(ref):
+    ctl, cf = ref
+    c = ctl.MPCcontroller(_Env(), None, horizon=3, cost_fn=None, num_simulated_paths=5)
+    a = c.sample_random_actions()
+    assert a.shape == (3, 5, 6) and a.dtype == np.float64 and (a >= -1).all() and (a < 1).all()
