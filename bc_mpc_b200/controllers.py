@@ -1,0 +1,144 @@
+"""Drop-in for the reference controllers.py planners, backed by the fused GPU rollout.
+
+Same constructors and get_action / sample_random_actions signatures as controllers.py:26-88
+(MPCcontroller), :160-237 (MPCcontrollerPolicyNet) and the legacy MPCcontroller_BC recovered from
+controllers.pyc.  Differences that follow from fusing the loop:
+  * randomness is drawn on the device (Philox, seeded from np.random so np.random.seed still makes runs
+    reproducible) unless sample_random_actions is overridden, in which case the returned [H,K,A] tensor
+    is injected exactly like controllers.py:60 does;
+  * cost_fn must be cheetah_cost_fn (the cost is fused into the kernel epilogue).
+"""
+import copy
+
+import numpy as np
+
+from . import cost_functions
+from .planner import Planner
+
+
+class Controller:
+    def __init__(self):
+        pass
+
+    def get_action(self, state):
+        pass
+
+
+class RandomController(Controller):
+    def __init__(self, env):
+        self.env = env
+
+    def get_action(self, state):
+        return self.env.action_space.sample()  # controllers.py:24
+
+
+def _check_cost(cost_fn):
+    if cost_fn is None or getattr(cost_fn, "__name__", "") != "cheetah_cost_fn":
+        raise ValueError("the fused planner implements cheetah_cost_fn only (cost_functions.py:9-30); "
+                         f"got {cost_fn!r}")
+
+
+class _GpuShootingController(Controller):
+    proposal = "uniform"
+
+    def _init_common(self, env, dyn_model, horizon, cost_fn, num_simulated_paths, precision, device):
+        _check_cost(cost_fn)
+        self.env, self.dyn_model, self.horizon, self.cost_fn = env, dyn_model, horizon, cost_fn
+        self.num_simulated_paths = num_simulated_paths
+        self.precision, self.device = precision, device
+        self._planner = None
+        self._dyn_version = None
+        self._pol_version = None
+        self.last_record = None
+
+    def sample_random_actions(self):
+        """controllers.py:43-55 / :181-187: float64 [H,K,A], U[low,high).  Kept for API parity; the
+        default planning path samples on the device instead of calling this."""
+        a = self.env.action_space
+        return np.random.uniform(low=a.low, high=a.high, size=[self.horizon, self.num_simulated_paths, len(a.high)])
+
+    def _sampling_overridden(self):
+        return ("sample_random_actions" in self.__dict__ or
+                type(self).sample_random_actions is not _GpuShootingController.sample_random_actions)
+
+    def _policy(self):
+        return None
+
+    def _explore(self):
+        return 1.0
+
+    def _ensure_planner(self):
+        dm = self.dyn_model
+        if self._planner is None:
+            self._planner = Planner(dm.obs_dim, dm.act_dim, dm.n_layers, dm.size, dm.activation,
+                                    num_paths=self.num_simulated_paths, horizon=self.horizon, max_states=1,
+                                    precision=self.precision, proposal=self.proposal, explore=self._explore(),
+                                    device=self.device)
+            self._planner.set_action_bounds(self.env.action_space.low, self.env.action_space.high)
+            self._dyn_version = None
+        if self._dyn_version != dm.version:     # weights change after every dyn_model.fit (train_mpc_ppo.py:279)
+            self._planner.set_dynamics(dm.weights)
+            self._planner.set_normalization(*dm.normalization6())
+            self._dyn_version = dm.version
+        pol = self._policy()
+        if pol is not None and self._pol_version != pol.version:
+            pol.upload(self._planner)
+            self._pol_version = pol.version
+        return self._planner
+
+    def _plan(self, state, inj):
+        p = self._ensure_planner()
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
+        rec = p.plan(np.asarray(state, np.float64), inj=inj, seed=seed)[0]
+        self.last_record = rec
+        return copy.copy(rec["action"][: self.dyn_model.act_dim])   # float64 [A] (controllers.py:85)
+
+
+class MPCcontroller(_GpuShootingController):
+    """Random-shooting MPC (controllers.py:26-88)."""
+
+    def __init__(self, env, dyn_model, horizon=5, cost_fn=None, num_simulated_paths=10, gamma=1.,
+                 precision="fp32", device=0):
+        self._init_common(env, dyn_model, horizon, cost_fn, num_simulated_paths, precision, device)
+        self.gamma = gamma
+
+    def get_action(self, state):
+        inj = self.sample_random_actions() if self._sampling_overridden() else None
+        return self._plan(state, inj)
+
+
+class MPCcontrollerPolicyNet(_GpuShootingController):
+    """Policy-proposal shooting (controllers.py:160-237)."""
+
+    def __init__(self, env, dyn_model, policy_net, explore=1., self_exp=True, horizon=5, cost_fn=None,
+                 num_simulated_paths=10, precision="fp32", device=0):
+        self.policy_net, self.self_exp, self.explore = policy_net, self_exp, explore
+        self.proposal = "policy_gaussian" if self_exp else "policy_mix"
+        self._init_common(env, dyn_model, horizon, cost_fn, num_simulated_paths, precision, device)
+
+    def _policy(self):
+        return self.policy_net
+
+    def _explore(self):
+        return self.explore
+
+    def get_action(self, state):
+        # controllers.py:192 always draws `exploration`, but uses it only when not self_exp (:208)
+        inj = self.sample_random_actions() if (not self.self_exp and self._sampling_overridden()) else None
+        return self._plan(state, inj)
+
+
+class MPCcontroller_BC(_GpuShootingController):
+    """Legacy BC-guided shooting (controllers.pyc src 90-163): a = bc_network.predict(s) + U[-1,1)."""
+    proposal = "bc_uniform"
+
+    def __init__(self, env, dyn_model, bc_network, horizon=5, cost_fn=None, num_simulated_paths=10,
+                 precision="fp32", device=0):
+        self.bc_network = bc_network
+        self._init_common(env, dyn_model, horizon, cost_fn, num_simulated_paths, precision, device)
+
+    def _policy(self):
+        return self.bc_network
+
+    def get_action(self, state):
+        return self._plan(state, None)

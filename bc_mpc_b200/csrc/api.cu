@@ -1,0 +1,640 @@
+// C ABI of the planner (include/bcmpc.h): handle, weight upload, launch logic.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bcmpc.h"
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "rollout_tc.cuh"
+#include "rollout_verify.cuh"
+
+using namespace bcmpc;
+
+namespace {
+thread_local std::string g_err;
+
+struct DeviceMlp {
+  MlpDesc desc{};
+  std::vector<float*> bufs;
+  bool set = false;
+  void release() {
+    for (float* p : bufs) cudaFree(p);
+    bufs.clear();
+    set = false;
+  }
+};
+}  // namespace
+
+struct bcmpc_handle {
+  bcmpc_config cfg{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  DeviceMlp dyn, pol;
+  NormArgs norm{};
+  bool have_norm = false, have_bounds = false;
+  // proposal network meta
+  bool has_filter = false, has_logstd = false;
+  float filt_mean[kMaxObs]{}, filt_std[kMaxObs]{}, pol_std[kMaxAct]{}, clip = 0.f;
+  // verify-kernel geometry
+  int vM = 32, vld = 0;
+  // scratch
+  Candidate* d_cand = nullptr;
+  size_t cand_cap = 0;
+  double* d_states = nullptr;
+  bcmpc_record* d_records = nullptr;
+  double* h_states = nullptr;        // pinned
+  bcmpc_record* h_records = nullptr; // pinned
+  double* d_inj = nullptr;
+  size_t inj_cap = 0;
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  // tcgen05 path
+  tc::TcHostPlan tcp;
+  uint8_t* d_tape = nullptr;
+  tc::TcOp* d_ops = nullptr;
+  float *d_b1 = nullptr, *d_b2 = nullptr;
+  bool tc_ready = false;
+  int tc_schedule = 1;
+};
+
+namespace {
+
+int fail(bcmpc_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CK(h, expr)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess) return fail(h, BCMPC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+int round4(int x) { return (x + 3) / 4 * 4; }
+
+// Uploads an MLP as zero-padded [in_pad][out_pad] float32 kernels + [out_pad] biases.
+int upload_mlp(bcmpc_handle* h, DeviceMlp& m, int n_layers, const int* sizes, const float* const* W,
+               const float* const* b) {
+  m.release();
+  m.desc = MlpDesc{};
+  m.desc.n_layers = n_layers;
+  for (int l = 0; l < n_layers; ++l) {
+    const int in = sizes[l], out = sizes[l + 1];
+    const int ip = round4(in), op = round4(out);
+    m.desc.in_dim[l] = in; m.desc.out_dim[l] = out; m.desc.in_pad[l] = ip; m.desc.out_pad[l] = op;
+    std::vector<float> w((size_t)ip * op, 0.f), bb(op, 0.f);
+    for (int i = 0; i < in; ++i) memcpy(&w[(size_t)i * op], W[l] + (size_t)i * out, sizeof(float) * out);
+    memcpy(bb.data(), b[l], sizeof(float) * out);
+    float *dw = nullptr, *db = nullptr;
+    CK(h, cudaMalloc(&dw, w.size() * sizeof(float)));
+    m.bufs.push_back(dw);
+    CK(h, cudaMalloc(&db, bb.size() * sizeof(float)));
+    m.bufs.push_back(db);
+    CK(h, cudaMemcpy(dw, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(db, bb.data(), bb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    m.desc.W[l] = dw;
+    m.desc.b[l] = db;
+  }
+  m.set = true;
+  return BCMPC_OK;
+}
+
+void update_verify_geometry(bcmpc_handle* h) {
+  int ld = 4;
+  auto scan = [&](const DeviceMlp& m) {
+    if (!m.set) return;
+    for (int l = 0; l < m.desc.n_layers; ++l) { ld = std::max(ld, m.desc.in_pad[l]); ld = std::max(ld, m.desc.out_pad[l]); }
+  };
+  scan(h->dyn);
+  scan(h->pol);
+  h->vld = ld;
+  h->vM = ld <= 512 ? 32 : 16;
+}
+
+int inj_kind_of(int proposal) {
+  switch (proposal) {
+    case BCMPC_PROP_POLICY_GAUSSIAN: return kInjNormal;
+    case BCMPC_PROP_NET_PLUS_UNIFORM: return kInjUniformPm1;
+    default: return kInjUniformBox;
+  }
+}
+
+int check_ready(bcmpc_handle* h, bool need_policy) {
+  if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics)");
+  if (!h->have_norm) return fail(h, BCMPC_ERR_STATE, "normalisation not set (bcmpc_set_normalization)");
+  if (need_policy) {
+    if (!h->pol.set) return fail(h, BCMPC_ERR_STATE, "proposal network not set (bcmpc_set_policy)");
+    if (h->cfg.proposal == BCMPC_PROP_POLICY_GAUSSIAN && !h->has_logstd)
+      return fail(h, BCMPC_ERR_STATE, "POLICY_GAUSSIAN needs logstd in bcmpc_set_policy");
+  }
+  return BCMPC_OK;
+}
+
+void fill_verify_args(bcmpc_handle* h, VerifyArgs* a) {
+  memset(a, 0, sizeof *a);
+  a->n = h->norm;
+  a->dyn = h->dyn.desc;
+  if (h->pol.set) a->pol = h->pol.desc;
+  a->dyn_act = h->cfg.activation;
+  a->ld = h->vld;
+  a->has_filter = h->has_filter;
+  memcpy(a->filt_mean, h->filt_mean, sizeof a->filt_mean);
+  memcpy(a->filt_std, h->filt_std, sizeof a->filt_std);
+  a->clip = h->clip;
+  memcpy(a->pol_std, h->pol_std, sizeof a->pol_std);
+  a->one_minus_explore = (float)(1.0 - h->cfg.explore);
+  a->explore = h->cfg.explore;
+}
+
+template <int M>
+int launch_verify_t(bcmpc_handle* h, const VerifyArgs& a, dim3 grid, cudaStream_t st) {
+  const size_t smem = verify_smem_bytes(M, a.ld);
+  CK(h, cudaFuncSetAttribute(rollout_verify_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rollout_verify_kernel<M><<<grid, kVerifyThreads, smem, st>>>(a);
+  CK(h, cudaGetLastError());
+  h->launches++;
+  return BCMPC_OK;
+}
+
+int ensure_cand(bcmpc_handle* h, size_t n) {
+  if (n <= h->cand_cap) return BCMPC_OK;
+  if (h->d_cand) cudaFree(h->d_cand);
+  h->d_cand = nullptr;
+  h->cand_cap = 0;
+  CK(h, cudaMalloc(&h->d_cand, n * sizeof(Candidate)));
+  h->cand_cap = n;
+  return BCMPC_OK;
+}
+
+int tc_prepare(bcmpc_handle* h, const float* const* W, const float* const* b) {
+  const int S = h->cfg.hidden_size;
+  tc::tc_build(W[0], b[0], W[1], b[1], W[2], b[2], S, h->tc_schedule, &h->tcp);
+  const tc::TcHostPlan& P = h->tcp;
+  if ((int)P.ops.size() > tc::kMaxOps) return fail(h, BCMPC_ERR_UNSUPPORTED, "op table too long (%zu)", P.ops.size());
+  if (h->d_tape) cudaFree(h->d_tape);
+  if (h->d_ops) cudaFree(h->d_ops);
+  if (h->d_b1) cudaFree(h->d_b1);
+  if (h->d_b2) cudaFree(h->d_b2);
+  h->d_tape = nullptr; h->d_ops = nullptr; h->d_b1 = h->d_b2 = nullptr;
+  CK(h, cudaMalloc(&h->d_tape, P.tape.size() * 2));
+  CK(h, cudaMalloc(&h->d_ops, P.ops.size() * sizeof(tc::TcOp)));
+  CK(h, cudaMalloc(&h->d_b1, P.b1.size() * sizeof(float)));
+  CK(h, cudaMalloc(&h->d_b2, P.b2.size() * sizeof(float)));
+  CK(h, cudaMemcpy(h->d_tape, P.tape.data(), P.tape.size() * 2, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(h->d_ops, P.ops.data(), P.ops.size() * sizeof(tc::TcOp), cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(h->d_b1, P.b1.data(), P.b1.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(h->d_b2, P.b2.data(), P.b2.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(h, cudaFuncSetAttribute(tc::rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+  h->tc_ready = true;
+  return BCMPC_OK;
+}
+
+int launch_tc(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
+  if (!h->tc_ready) return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared (bcmpc_set_dynamics)");
+  const tc::TcHostPlan& P = h->tcp;
+  tc::TcArgs a;
+  memset(&a, 0, sizeof a);
+  a.p = p;
+  a.tape = h->d_tape; a.ops = h->d_ops; a.n_ops = (int)P.ops.size();
+  a.nkb = P.nkb; a.nc = P.nc; a.nst = P.nst;
+  a.off_a1 = P.off_a1; a.off_ring2 = P.off_ring2; a.off_wring = P.off_wring; a.off_misc = P.off_misc;
+  a.b1 = h->d_b1; a.b2 = h->d_b2;
+  for (int d = 0; d < h->cfg.obs_dim; ++d) {
+    a.mean_obs[d] = (float)h->norm.mean_obs[d];
+    a.inv_den_obs[d] = (float)(1.0 / h->norm.den_obs[d]);
+    a.mean_delta[d] = (float)h->norm.mean_delta[d];
+    a.std_delta[d] = (float)h->norm.std_delta[d];
+    a.b3[d] = P.b3[d];
+  }
+  for (int j = 0; j < h->cfg.act_dim; ++j) {
+    a.mean_act[j] = (float)h->norm.mean_act[j];
+    a.inv_den_act[j] = (float)(1.0 / h->norm.den_act[j]);
+    a.low[j] = h->norm.low[j];
+    a.span[j] = h->norm.span[j];
+  }
+  dim3 grid(p.tiles_per_state, p.B);
+  tc::rollout_tc_kernel<<<grid, tc::kThreads, P.smem_bytes, st>>>(a);
+  CK(h, cudaGetLastError());
+  h->launches++;
+  return BCMPC_OK;
+}
+
+// rollout (either precision) + per-state reduction of the tile candidates into d_out[B]
+int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, int force_verify) {
+  const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST && !force_verify;
+  const int M = fast ? tc::kRows : h->vM;
+  p.tiles_per_state = (p.K + M - 1) / M;
+  if (d_out) {
+    int rc = ensure_cand(h, (size_t)p.B * p.tiles_per_state);
+    if (rc) return rc;
+    p.cand = h->d_cand;
+  } else {
+    p.cand = nullptr;
+  }
+  if (h->timing) { CK(h, cudaEventRecord(h->ev0, st)); }
+  int rc;
+  if (fast) {
+    rc = launch_tc(h, p, st);
+  } else {
+    VerifyArgs a;
+    fill_verify_args(h, &a);
+    a.p = p;
+    dim3 grid(p.tiles_per_state, p.B);
+    rc = h->vM == 32 ? launch_verify_t<32>(h, a, grid, st) : launch_verify_t<16>(h, a, grid, st);
+  }
+  if (rc) return rc;
+  if (h->timing) { CK(h, cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
+  if (d_out) {
+    reduce_candidates_kernel<<<p.B, 256, 0, st>>>(h->d_cand, p.tiles_per_state, p.B, 0, d_out);
+    CK(h, cudaGetLastError());
+    h->launches++;
+  }
+  return BCMPC_OK;
+}
+
+PlanArgs base_plan_args(bcmpc_handle* h, int B, uint64_t seed) {
+  PlanArgs p;
+  memset(&p, 0, sizeof p);
+  p.D = h->cfg.obs_dim; p.A = h->cfg.act_dim; p.K = h->cfg.num_paths; p.H = h->cfg.horizon; p.B = B;
+  p.proposal = h->cfg.proposal;
+  p.inj_kind = inj_kind_of(h->cfg.proposal);
+  p.path_offset = h->cfg.path_offset;
+  p.seed = seed;
+  return p;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int bcmpc_abi_version(void) { return BCMPC_ABI_VERSION; }
+
+const char* bcmpc_last_error(const bcmpc_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
+  if (!cfg || !out) return fail(nullptr, BCMPC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const bcmpc_config& c = *cfg;
+  if (c.obs_dim < 1 || c.obs_dim > kMaxObs) return fail(nullptr, BCMPC_ERR_INVALID, "obs_dim %d out of [1,%d]", c.obs_dim, kMaxObs);
+  if (c.act_dim < 1 || c.act_dim > kMaxAct) return fail(nullptr, BCMPC_ERR_INVALID, "act_dim %d out of [1,%d]", c.act_dim, kMaxAct);
+  if (c.n_hidden < 1 || c.n_hidden + 1 > kMaxLayers) return fail(nullptr, BCMPC_ERR_INVALID, "n_hidden %d out of [1,%d]", c.n_hidden, kMaxLayers - 1);
+  if (c.hidden_size < 1 || c.hidden_size > 1536) return fail(nullptr, BCMPC_ERR_INVALID, "hidden_size %d out of [1,1536]", c.hidden_size);
+  if (c.num_paths < 1) return fail(nullptr, BCMPC_ERR_INVALID, "num_paths must be >= 1");
+  if (c.horizon < 1) return fail(nullptr, BCMPC_ERR_INVALID, "horizon must be >= 1");
+  if (c.max_states < 1) return fail(nullptr, BCMPC_ERR_INVALID, "max_states must be >= 1");
+  if (c.activation != BCMPC_ACT_RELU && c.activation != BCMPC_ACT_TANH) return fail(nullptr, BCMPC_ERR_INVALID, "unknown activation %d", c.activation);
+  if (c.precision != BCMPC_PREC_FP32_VERIFY && c.precision != BCMPC_PREC_BF16_FAST) return fail(nullptr, BCMPC_ERR_INVALID, "unknown precision %d", c.precision);
+  if (c.proposal < BCMPC_PROP_UNIFORM || c.proposal > BCMPC_PROP_NET_PLUS_UNIFORM) return fail(nullptr, BCMPC_ERR_INVALID, "unknown proposal %d", c.proposal);
+  if (c.path_offset < 0 || c.path_offset + c.num_paths > 0xFFFFFFFFLL) return fail(nullptr, BCMPC_ERR_INVALID, "path_offset out of range");
+  if (c.precision == BCMPC_PREC_BF16_FAST) {
+    std::string why;
+    if (!tc::tc_supported(c, &why)) return fail(nullptr, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(nullptr, BCMPC_ERR_CUDA, "no CUDA device: the planner has no CPU fallback");
+  if (c.device < 0 || c.device >= ndev) return fail(nullptr, BCMPC_ERR_INVALID, "device %d out of [0,%d)", c.device, ndev);
+  bcmpc_handle* h = new bcmpc_handle();
+  h->cfg = c;
+  if (h->cfg.total_paths <= 0) h->cfg.total_paths = c.path_offset + c.num_paths;
+  if (const char* s = getenv("BCMPC_TC_SCHEDULE")) h->tc_schedule = atoi(s);
+  cudaError_t e = cudaSetDevice(c.device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_states, sizeof(double) * c.max_states * c.obs_dim);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_records, sizeof(bcmpc_record) * c.max_states);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_states, sizeof(double) * c.max_states * c.obs_dim);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_records, sizeof(bcmpc_record) * c.max_states);
+  if (e != cudaSuccess) {
+    int rc = fail(nullptr, BCMPC_ERR_CUDA, "bcmpc_create: %s", cudaGetErrorString(e));
+    bcmpc_destroy(h);
+    return rc;
+  }
+  // default action box [-1, 1) (HalfCheetah, controllers.py:53); std_act etc. must be set explicitly
+  for (int j = 0; j < kMaxAct; ++j) { h->norm.low[j] = -1.f; h->norm.span[j] = 2.f; }
+  *out = h;
+  return BCMPC_OK;
+}
+
+int bcmpc_destroy(bcmpc_handle* h) {
+  if (!h) return BCMPC_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->dyn.release();
+  h->pol.release();
+  cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
+  cudaFree(h->d_tape); cudaFree(h->d_ops); cudaFree(h->d_b1); cudaFree(h->d_b2);
+  if (h->h_states) cudaFreeHost(h->h_states);
+  if (h->h_records) cudaFreeHost(h->h_records);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return BCMPC_OK;
+}
+
+int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int32_t n_layers) {
+  if (!h || !W || !b) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n_layers != h->cfg.n_hidden + 1) return fail(h, BCMPC_ERR_INVALID, "n_layers %d != n_hidden+1 = %d", n_layers, h->cfg.n_hidden + 1);
+  for (int l = 0; l < n_layers; ++l)
+    if (!W[l] || !b[l]) return fail(h, BCMPC_ERR_INVALID, "null weight pointer for layer %d", l);
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  int sizes[kMaxLayers + 1];
+  sizes[0] = h->cfg.obs_dim + h->cfg.act_dim;
+  for (int l = 1; l <= h->cfg.n_hidden; ++l) sizes[l] = h->cfg.hidden_size;
+  sizes[n_layers] = h->cfg.obs_dim;
+  int rc = upload_mlp(h, h->dyn, n_layers, sizes, W, b);
+  if (rc) return rc;
+  update_verify_geometry(h);
+  if (h->cfg.precision == BCMPC_PREC_BF16_FAST) {
+    rc = tc_prepare(h, W, b);
+    if (rc) return rc;
+  }
+  return BCMPC_OK;
+}
+
+int bcmpc_set_normalization(bcmpc_handle* h, const double* mean_obs, const double* std_obs, const double* mean_act,
+                            const double* std_act, const double* mean_delta, const double* std_delta) {
+  if (!h || !mean_obs || !std_obs || !mean_act || !std_act || !mean_delta || !std_delta)
+    return fail(h, BCMPC_ERR_INVALID, "null argument");
+  for (int d = 0; d < h->cfg.obs_dim; ++d) {
+    h->norm.mean_obs[d] = mean_obs[d];
+    h->norm.den_obs[d] = std_obs[d] + 1e-10;     // dynamics.py:109
+    h->norm.mean_delta[d] = mean_delta[d];
+    h->norm.std_delta[d] = std_delta[d];         // dynamics.py:113 (no epsilon)
+  }
+  for (int j = 0; j < h->cfg.act_dim; ++j) {
+    h->norm.mean_act[j] = mean_act[j];
+    h->norm.den_act[j] = std_act[j] + 1e-10;     // dynamics.py:110
+  }
+  h->have_norm = true;
+  return BCMPC_OK;
+}
+
+int bcmpc_set_action_bounds(bcmpc_handle* h, const double* low, const double* high) {
+  if (!h || !low || !high) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  for (int j = 0; j < h->cfg.act_dim; ++j) {
+    if (!(high[j] >= low[j])) return fail(h, BCMPC_ERR_INVALID, "action bound %d: high < low", j);
+    h->norm.low[j] = (float)low[j];
+    h->norm.span[j] = (float)(high[j] - low[j]);
+  }
+  h->have_bounds = true;
+  return BCMPC_OK;
+}
+
+int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* W,
+                     const float* const* b, const float* logstd, const float* filt_mean, const float* filt_std,
+                     float clip) {
+  if (!h || !sizes || !W || !b) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n_layers < 1 || n_layers > kMaxLayers) return fail(h, BCMPC_ERR_INVALID, "n_layers %d out of [1,%d]", n_layers, kMaxLayers);
+  if (sizes[0] != h->cfg.obs_dim || sizes[n_layers] != h->cfg.act_dim)
+    return fail(h, BCMPC_ERR_INVALID, "policy sizes must start with obs_dim and end with act_dim");
+  for (int l = 0; l <= n_layers; ++l)
+    if (sizes[l] < 1 || sizes[l] > 1536) return fail(h, BCMPC_ERR_INVALID, "policy layer size %d out of range", sizes[l]);
+  if ((filt_mean == nullptr) != (filt_std == nullptr)) return fail(h, BCMPC_ERR_INVALID, "filt_mean and filt_std must be given together");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  int rc = upload_mlp(h, h->pol, n_layers, sizes, W, b);
+  if (rc) return rc;
+  h->has_filter = filt_mean != nullptr;
+  for (int d = 0; d < h->cfg.obs_dim; ++d) {
+    h->filt_mean[d] = filt_mean ? filt_mean[d] : 0.f;
+    h->filt_std[d] = filt_std ? filt_std[d] : 1.f;
+  }
+  h->clip = clip;
+  h->has_logstd = logstd != nullptr;
+  for (int j = 0; j < h->cfg.act_dim; ++j) h->pol_std[j] = logstd ? expf(logstd[j]) : 0.f;   // distributions.py:65
+  update_verify_geometry(h);
+  return BCMPC_OK;
+}
+
+int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj, uint64_t seed,
+                      bcmpc_record* d_out, void* stream) {
+  if (!h || !d_states || !d_out) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n_states < 1 || n_states > h->cfg.max_states) return fail(h, BCMPC_ERR_INVALID, "n_states %d out of [1,%d]", n_states, h->cfg.max_states);
+  int rc = check_ready(h, h->cfg.proposal != BCMPC_PROP_UNIFORM);
+  if (rc) return rc;
+  CK(h, cudaSetDevice(h->cfg.device));
+  PlanArgs p = base_plan_args(h, n_states, seed);
+  p.states = d_states;
+  p.inj = d_inj;
+  return run_plan(h, p, d_out, stream ? (cudaStream_t)stream : h->stream, 0);
+}
+
+int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const double* inj, uint64_t seed,
+               bcmpc_record* out) {
+  if (!h || !states || !out) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n_states < 1 || n_states > h->cfg.max_states) return fail(h, BCMPC_ERR_INVALID, "n_states %d out of [1,%d]", n_states, h->cfg.max_states);
+  CK(h, cudaSetDevice(h->cfg.device));
+  const size_t sbytes = sizeof(double) * n_states * h->cfg.obs_dim;
+  memcpy(h->h_states, states, sbytes);
+  CK(h, cudaMemcpyAsync(h->d_states, h->h_states, sbytes, cudaMemcpyHostToDevice, h->stream));
+  const double* d_inj = nullptr;
+  if (inj) {
+    const size_t n = (size_t)n_states * h->cfg.horizon * h->cfg.num_paths * h->cfg.act_dim;
+    if (n > h->inj_cap) {
+      if (h->d_inj) cudaFree(h->d_inj);
+      h->d_inj = nullptr; h->inj_cap = 0;
+      CK(h, cudaMalloc(&h->d_inj, n * sizeof(double)));
+      h->inj_cap = n;
+    }
+    CK(h, cudaMemcpyAsync(h->d_inj, inj, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    d_inj = h->d_inj;
+  }
+  int rc = bcmpc_plan_device(h, h->d_states, n_states, d_inj, seed, h->d_records, h->stream);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(h->h_records, h->d_records, sizeof(bcmpc_record) * n_states, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  memcpy(out, h->h_records, sizeof(bcmpc_record) * n_states);
+  return BCMPC_OK;
+}
+
+int bcmpc_rollout_debug(bcmpc_handle* h, const double* state, const double* inj, uint64_t seed, double* states_out,
+                        double* actions_out, double* costs_out) {
+  if (!h || !state) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  int rc = check_ready(h, h->cfg.proposal != BCMPC_PROP_UNIFORM);
+  if (rc) return rc;
+  CK(h, cudaSetDevice(h->cfg.device));
+  const int D = h->cfg.obs_dim, A = h->cfg.act_dim, K = h->cfg.num_paths, H = h->cfg.horizon;
+  double *d_state = nullptr, *d_inj = nullptr, *d_so = nullptr, *d_ao = nullptr, *d_co = nullptr;
+  auto cleanup = [&]() { cudaFree(d_state); cudaFree(d_inj); cudaFree(d_so); cudaFree(d_ao); cudaFree(d_co); };
+#define CKC(expr)                                                                                      \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess) { cleanup(); return fail(h, BCMPC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); } \
+  } while (0)
+  CKC(cudaMalloc(&d_state, sizeof(double) * D));
+  CKC(cudaMemcpy(d_state, state, sizeof(double) * D, cudaMemcpyHostToDevice));
+  if (inj) {
+    CKC(cudaMalloc(&d_inj, sizeof(double) * H * K * A));
+    CKC(cudaMemcpy(d_inj, inj, sizeof(double) * H * K * A, cudaMemcpyHostToDevice));
+  }
+  if (states_out) CKC(cudaMalloc(&d_so, sizeof(double) * (H + 1) * K * D));
+  if (actions_out) CKC(cudaMalloc(&d_ao, sizeof(double) * H * K * A));
+  if (costs_out) CKC(cudaMalloc(&d_co, sizeof(double) * K));
+  PlanArgs p = base_plan_args(h, 1, seed);
+  p.states = d_state; p.inj = d_inj; p.states_out = d_so; p.actions_out = d_ao; p.costs_out = d_co;
+  rc = run_plan(h, p, nullptr, h->stream, 0);
+  if (rc) { cleanup(); return rc; }
+  CKC(cudaStreamSynchronize(h->stream));
+  if (states_out) CKC(cudaMemcpy(states_out, d_so, sizeof(double) * (H + 1) * K * D, cudaMemcpyDeviceToHost));
+  if (actions_out) CKC(cudaMemcpy(actions_out, d_ao, sizeof(double) * H * K * A, cudaMemcpyDeviceToHost));
+  if (costs_out) CKC(cudaMemcpy(costs_out, d_co, sizeof(double) * K, cudaMemcpyDeviceToHost));
+  cleanup();
+  return BCMPC_OK;
+}
+
+int bcmpc_predict(bcmpc_handle* h, const double* states, const double* actions, int64_t n, double* next_states) {
+  if (!h || !states || !actions || !next_states) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n < 1 || n > 0x7FFFFFFF) return fail(h, BCMPC_ERR_INVALID, "row count out of range");
+  int rc = check_ready(h, false);
+  if (rc) return rc;
+  CK(h, cudaSetDevice(h->cfg.device));
+  const int D = h->cfg.obs_dim, A = h->cfg.act_dim;
+  double *d_s = nullptr, *d_a = nullptr, *d_o = nullptr;
+  auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_a); cudaFree(d_o); };
+  CKC(cudaMalloc(&d_s, sizeof(double) * n * D));
+  CKC(cudaMalloc(&d_a, sizeof(double) * n * A));
+  CKC(cudaMalloc(&d_o, sizeof(double) * 2 * n * D));
+  CKC(cudaMemcpy(d_s, states, sizeof(double) * n * D, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(d_a, actions, sizeof(double) * n * A, cudaMemcpyHostToDevice));
+  // one step, every row from its own state with its own action: the predict of dynamics.py:106-119
+  PlanArgs p = base_plan_args(h, 1, 0);
+  p.K = (int)n; p.H = 1; p.proposal = BCMPC_PROP_UNIFORM; p.inj_kind = kInjUniformBox;
+  p.states = d_s; p.inj = d_a; p.states_out = d_o; p.per_row_states = 1;
+  rc = run_plan(h, p, nullptr, h->stream, /*force_verify=*/h->cfg.precision != BCMPC_PREC_BF16_FAST);
+  if (rc) { cleanup(); return rc; }
+  CKC(cudaStreamSynchronize(h->stream));
+  CKC(cudaMemcpy(next_states, d_o + n * D, sizeof(double) * n * D, cudaMemcpyDeviceToHost));
+  cleanup();
+  return BCMPC_OK;
+}
+
+int bcmpc_policy_act(bcmpc_handle* h, const double* obs, const float* noise, int64_t n, float* out) {
+  if (!h || !obs || !out) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n < 1 || n > 0x7FFFFFFF) return fail(h, BCMPC_ERR_INVALID, "row count out of range");
+  if (!h->pol.set) return fail(h, BCMPC_ERR_STATE, "proposal network not set (bcmpc_set_policy)");
+  if (noise && !h->has_logstd) return fail(h, BCMPC_ERR_STATE, "stochastic act needs logstd in bcmpc_set_policy");
+  CK(h, cudaSetDevice(h->cfg.device));
+  const int D = h->cfg.obs_dim, A = h->cfg.act_dim;
+  double* d_obs = nullptr;
+  float *d_noise = nullptr, *d_out = nullptr;
+  auto cleanup = [&]() { cudaFree(d_obs); cudaFree(d_noise); cudaFree(d_out); };
+  CKC(cudaMalloc(&d_obs, sizeof(double) * n * D));
+  CKC(cudaMalloc(&d_out, sizeof(float) * n * A));
+  CKC(cudaMemcpy(d_obs, obs, sizeof(double) * n * D, cudaMemcpyHostToDevice));
+  if (noise) {
+    CKC(cudaMalloc(&d_noise, sizeof(float) * n * A));
+    CKC(cudaMemcpy(d_noise, noise, sizeof(float) * n * A, cudaMemcpyHostToDevice));
+  }
+  VerifyArgs a;
+  fill_verify_args(h, &a);
+  a.p = base_plan_args(h, 1, 0);
+  const int M = h->vM;
+  const size_t smem = 2 * (size_t)M * a.ld * sizeof(float);
+  const unsigned grid = (unsigned)((n + M - 1) / M);
+  if (M == 32) {
+    CKC(cudaFuncSetAttribute(policy_act_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    policy_act_kernel<32><<<grid, kVerifyThreads, smem, h->stream>>>(a, d_obs, d_noise, n, d_out);
+  } else {
+    CKC(cudaFuncSetAttribute(policy_act_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    policy_act_kernel<16><<<grid, kVerifyThreads, smem, h->stream>>>(a, d_obs, d_noise, n, d_out);
+  }
+  CKC(cudaGetLastError());
+  h->launches++;
+  CKC(cudaStreamSynchronize(h->stream));
+  CKC(cudaMemcpy(out, d_out, sizeof(float) * n * A, cudaMemcpyDeviceToHost));
+  cleanup();
+  return BCMPC_OK;
+}
+
+int bcmpc_cheetah_cost(bcmpc_handle* h, const double* states, const double* next_states, int64_t n, double* out) {
+  if (!h || !states || !next_states || !out) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n < 1) return fail(h, BCMPC_ERR_INVALID, "row count out of range");
+  if (h->cfg.obs_dim < 18) return fail(h, BCMPC_ERR_INVALID, "cheetah_cost_fn indexes obs[17]; obs_dim = %d", h->cfg.obs_dim);
+  CK(h, cudaSetDevice(h->cfg.device));
+  const int D = h->cfg.obs_dim;
+  double *d_s = nullptr, *d_n = nullptr, *d_o = nullptr;
+  auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_n); cudaFree(d_o); };
+  CKC(cudaMalloc(&d_s, sizeof(double) * n * D));
+  CKC(cudaMalloc(&d_n, sizeof(double) * n * D));
+  CKC(cudaMalloc(&d_o, sizeof(double) * n));
+  CKC(cudaMemcpy(d_s, states, sizeof(double) * n * D, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(d_n, next_states, sizeof(double) * n * D, cudaMemcpyHostToDevice));
+  cheetah_cost_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_s, d_n, n, D, d_o);
+  CKC(cudaGetLastError());
+  h->launches++;
+  CKC(cudaStreamSynchronize(h->stream));
+  CKC(cudaMemcpy(out, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cleanup();
+  return BCMPC_OK;
+}
+
+int bcmpc_sample_injection(bcmpc_handle* h, uint64_t seed, int32_t n_states, double* out) {
+  if (!h || !out) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n_states < 1) return fail(h, BCMPC_ERR_INVALID, "n_states must be >= 1");
+  CK(h, cudaSetDevice(h->cfg.device));
+  const int A = h->cfg.act_dim, K = h->cfg.num_paths, H = h->cfg.horizon;
+  const int64_t rows = (int64_t)n_states * H * K;
+  double* d_o = nullptr;
+  auto cleanup = [&]() { cudaFree(d_o); };
+  CKC(cudaMalloc(&d_o, sizeof(double) * rows * A));
+  sample_injection_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(
+      h->norm, A, K, H, n_states, inj_kind_of(h->cfg.proposal), seed, h->cfg.path_offset, d_o);
+  CKC(cudaGetLastError());
+  h->launches++;
+  CKC(cudaStreamSynchronize(h->stream));
+  CKC(cudaMemcpy(out, d_o, sizeof(double) * rows * A, cudaMemcpyDeviceToHost));
+  cleanup();
+  return BCMPC_OK;
+}
+#undef CKC
+
+int bcmpc_reduce_records(bcmpc_handle* h, const bcmpc_record* d_gathered, int32_t n_ranks, int32_t n_states,
+                         bcmpc_record* d_out, void* stream) {
+  if (!h || !d_gathered || !d_out) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n_ranks < 1 || n_states < 1) return fail(h, BCMPC_ERR_INVALID, "n_ranks and n_states must be >= 1");
+  CK(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  reduce_candidates_kernel<<<n_states, 256, 0, st>>>(d_gathered, n_ranks, n_states, 1, d_out);
+  CK(h, cudaGetLastError());
+  h->launches++;
+  return BCMPC_OK;
+}
+
+int64_t bcmpc_kernel_launches(const bcmpc_handle* h) { return h ? h->launches : 0; }
+
+int bcmpc_enable_timing(bcmpc_handle* h, int32_t on) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  h->timing = on != 0;
+  h->ev_valid = false;
+  return BCMPC_OK;
+}
+
+int bcmpc_last_kernel_ms(bcmpc_handle* h, float* ms) {
+  if (!h || !ms) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (!h->ev_valid) return fail(h, BCMPC_ERR_STATE, "no timed rollout kernel yet (bcmpc_enable_timing)");
+  CK(h, cudaEventSynchronize(h->ev1));
+  CK(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return BCMPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// Small HBM-bound helper kernels: candidate reduction (argmin), stand-alone cost, injection dump.
+#pragma once
+#include "common.cuh"
+
+namespace bcmpc {
+
+// Reduces rows of candidates to one record each: in [n_out][n_in] -> out[n_out]
+// (np.argmin order, controllers.py:82).  One CTA per output record.  With `strided` the input is
+// [n_in][n_out] (gathered per-rank records, rank-major) instead.
+__global__ void __launch_bounds__(256) reduce_candidates_kernel(const Candidate* __restrict__ in, int n_in, int n_out,
+                                                                int strided, bcmpc_record* __restrict__ out) {
+  const int o = blockIdx.x;
+  __shared__ double s_cost[256];
+  __shared__ int64_t s_idx[256];
+  __shared__ int s_src[256];
+  double c = 0.0;
+  int64_t idx = -1;
+  int src = -1;
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
+    const Candidate& cd = strided ? in[(size_t)i * n_out + o] : in[(size_t)o * n_in + i];
+    if (cd.index < 0) continue;
+    if (idx < 0 || cand_better(cd.cost, cd.index, c, idx)) { c = cd.cost; idx = cd.index; src = i; }
+  }
+  s_cost[threadIdx.x] = c; s_idx[threadIdx.x] = idx; s_src[threadIdx.x] = src;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      const int t = threadIdx.x + off;
+      if (s_idx[t] >= 0 && (s_idx[threadIdx.x] < 0 || cand_better(s_cost[t], s_idx[t], s_cost[threadIdx.x], s_idx[threadIdx.x]))) {
+        s_cost[threadIdx.x] = s_cost[t]; s_idx[threadIdx.x] = s_idx[t]; s_src[threadIdx.x] = s_src[t];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    bcmpc_record r;
+    r.cost = s_cost[0];
+    r.index = s_idx[0];
+    for (int j = 0; j < kMaxAct; ++j) r.action[j] = 0.0;
+    if (s_src[0] >= 0) {
+      const Candidate& cd = strided ? in[(size_t)s_src[0] * n_out + o] : in[(size_t)o * n_in + s_src[0]];
+      for (int j = 0; j < kMaxAct; ++j) r.action[j] = cd.action[j];
+    }
+    out[o] = r;
+  }
+}
+
+// cheetah_cost_fn batched branch (cost_functions.py:10-30), float64.
+__global__ void cheetah_cost_kernel(const double* __restrict__ s, const double* __restrict__ ns, int64_t n, int D,
+                                    double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* a = s + i * D;
+  double c = 0.0;
+  if (a[5] >= 0.2) c += 10.0;
+  if (a[6] >= 0.0) c += 10.0;
+  if (a[7] >= 0.0) c += 10.0;
+  c -= (ns[i * D + 17] - a[17]) / 0.01;
+  out[i] = c;
+}
+
+// Writes the injection tensor [B,H,K,A] exactly as the rollout kernels draw it.
+__global__ void sample_injection_kernel(NormArgs n, int A, int K, int H, int B, int kind, uint64_t seed,
+                                        int64_t path_offset, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*H*K
+  if (i >= (int64_t)B * H * K) return;
+  const int k = (int)(i % K);
+  const int h = (int)((i / K) % H);
+  const int b = (int)(i / ((int64_t)K * H));
+  float v[kMaxAct];
+  draw_injection(v, A, kind, seed, (uint32_t)(path_offset + k), (uint32_t)b, (uint32_t)h, n.low, n.span);
+  for (int j = 0; j < A; ++j) out[i * A + j] = (double)v[j];
+}
+
+}  // namespace bcmpc

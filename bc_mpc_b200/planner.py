@@ -1,0 +1,175 @@
+"""Planner: Python owner of one bcmpc handle (one GPU).  Thin: argument checking, numpy <-> pointers."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+_PROPOSALS = {"uniform": L.PROP_UNIFORM, "policy_gaussian": L.PROP_POLICY_GAUSSIAN,
+              "policy_mix": L.PROP_POLICY_MIX, "bc_uniform": L.PROP_NET_PLUS_UNIFORM}
+_PRECISIONS = {"fp32": L.PREC_FP32_VERIFY, "fp32_verify": L.PREC_FP32_VERIFY,
+               "bf16": L.PREC_BF16_FAST, "bf16_fast": L.PREC_BF16_FAST}
+_ACTS = {"relu": L.ACT_RELU, "tanh": L.ACT_TANH}
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return a
+
+
+class Planner:
+    """One random-shooting planner instance on one device.
+
+    Mirrors what MPCcontroller / MPCcontrollerPolicyNet hold (controllers.py:28-41,162-181):
+    K = num_paths, H = horizon, the dynamics net and the optional proposal net."""
+
+    def __init__(self, obs_dim=20, act_dim=6, n_hidden=2, hidden_size=500, activation="relu", num_paths=1000,
+                 horizon=15, max_states=1, precision="fp32", proposal="uniform", explore=1.0, device=0,
+                 path_offset=0, total_paths=0):
+        self._h = C.c_void_p()
+        self._lib = L.lib()
+        cfg = L.Config(obs_dim=obs_dim, act_dim=act_dim, n_hidden=n_hidden, hidden_size=hidden_size,
+                       activation=_ACTS[activation] if isinstance(activation, str) else int(activation),
+                       num_paths=num_paths, horizon=horizon, max_states=max_states,
+                       precision=_PRECISIONS[precision] if isinstance(precision, str) else int(precision),
+                       proposal=_PROPOSALS[proposal] if isinstance(proposal, str) else int(proposal),
+                       device=device, reserved0=0, path_offset=path_offset, total_paths=total_paths,
+                       explore=float(explore))
+        L.check(self._lib.bcmpc_create(C.byref(cfg), C.byref(self._h)))
+        self.cfg = cfg
+        self.D, self.A, self.K, self.H = obs_dim, act_dim, num_paths, horizon
+        self.max_states = max_states
+        self.precision = precision
+        self.proposal = proposal
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.bcmpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        L.check(rc, self._h)
+
+    # -- weights ----------------------------------------------------------------------------------
+    def set_dynamics(self, weights):
+        """weights: [(kernel[in,out], bias[out]), ...] hidden layers first (dynamics.py:54-71)."""
+        Ws = [np.ascontiguousarray(w, np.float32) for w, _ in weights]
+        bs = [np.ascontiguousarray(b, np.float32).reshape(-1) for _, b in weights]
+        sizes = [self.D + self.A] + [self.cfg.hidden_size] * self.cfg.n_hidden + [self.D]
+        if len(Ws) != len(sizes) - 1:
+            raise ValueError(f"expected {len(sizes) - 1} layers, got {len(Ws)}")
+        for i, (w, b) in enumerate(zip(Ws, bs)):
+            if w.shape != (sizes[i], sizes[i + 1]) or b.shape != (sizes[i + 1],):
+                raise ValueError(f"layer {i}: expected kernel {(sizes[i], sizes[i + 1])}, got {w.shape} / {b.shape}")
+        self._ck(self._lib.bcmpc_set_dynamics(self._h, L.ptr_array(Ws), L.ptr_array(bs), len(Ws)))
+
+    def set_normalization(self, mean_obs, std_obs, mean_action, std_action, mean_deltas, std_deltas):
+        a = [_f64(mean_obs, (self.D,)), _f64(std_obs, (self.D,)), _f64(mean_action, (self.A,)),
+             _f64(std_action, (self.A,)), _f64(mean_deltas, (self.D,)), _f64(std_deltas, (self.D,))]
+        self._ck(self._lib.bcmpc_set_normalization(self._h, *[L.ptr(x) for x in a]))
+
+    def set_action_bounds(self, low, high):
+        low = _f64(np.broadcast_to(low, (self.A,)))
+        high = _f64(np.broadcast_to(high, (self.A,)))
+        self._ck(self._lib.bcmpc_set_action_bounds(self._h, L.ptr(low), L.ptr(high)))
+
+    def set_policy(self, weights, logstd=None, filt_mean=None, filt_std=None, clip=0.0):
+        Ws = [np.ascontiguousarray(w, np.float32) for w, _ in weights]
+        bs = [np.ascontiguousarray(b, np.float32).reshape(-1) for _, b in weights]
+        sizes = np.array([Ws[0].shape[0]] + [w.shape[1] for w in Ws], np.int32)
+        for i, (w, b) in enumerate(zip(Ws, bs)):
+            if w.shape != (sizes[i], sizes[i + 1]) or b.shape != (sizes[i + 1],):
+                raise ValueError(f"policy layer {i}: inconsistent shapes {w.shape} / {b.shape}")
+        ls = None if logstd is None else np.ascontiguousarray(logstd, np.float32).reshape(-1)
+        fm = None if filt_mean is None else np.ascontiguousarray(filt_mean, np.float32).reshape(-1)
+        fs = None if filt_std is None else np.ascontiguousarray(filt_std, np.float32).reshape(-1)
+        self._ck(self._lib.bcmpc_set_policy(self._h, len(Ws), L.ptr(sizes), L.ptr_array(Ws), L.ptr_array(bs),
+                                            L.ptr(ls), L.ptr(fm), L.ptr(fs), float(clip or 0.0)))
+
+    # -- the hot path -----------------------------------------------------------------------------
+    def plan(self, states, inj=None, seed=0):
+        """get_action for B root states (host buffers).  Returns a structured array [B] of
+        (cost, index, action[8]).  inj: [B,H,K,A] (or [H,K,A] for B = 1) injected randomness."""
+        states = _f64(states)
+        if states.ndim == 1:
+            states = states[None]
+        B = states.shape[0]
+        if states.shape[1] != self.D:
+            raise ValueError(f"states must be [B,{self.D}]")
+        if inj is not None:
+            inj = _f64(inj).reshape(B, self.H, self.K, self.A)
+        out = np.zeros(B, L.RECORD_DTYPE)
+        self._ck(self._lib.bcmpc_plan(self._h, L.ptr(states), B, L.ptr(inj), C.c_uint64(seed), L.ptr(out)))
+        return out
+
+    def plan_device(self, d_states_ptr, n_states, d_out_ptr, seed=0, d_inj_ptr=None, stream_ptr=None):
+        """Asynchronous launch on device buffers (raw pointers, e.g. torch.Tensor.data_ptr())."""
+        self._ck(self._lib.bcmpc_plan_device(self._h, C.c_void_p(d_states_ptr), n_states,
+                                             C.c_void_p(d_inj_ptr) if d_inj_ptr else None, C.c_uint64(seed),
+                                             C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def rollout_debug(self, state, inj=None, seed=0, want_states=True, want_actions=True):
+        state = _f64(state, (self.D,))
+        if inj is not None:
+            inj = _f64(inj, (self.H, self.K, self.A))
+        so = np.empty((self.H + 1, self.K, self.D)) if want_states else None
+        ao = np.empty((self.H, self.K, self.A)) if want_actions else None
+        co = np.empty(self.K)
+        self._ck(self._lib.bcmpc_rollout_debug(self._h, L.ptr(state), L.ptr(inj), C.c_uint64(seed), L.ptr(so),
+                                               L.ptr(ao), L.ptr(co)))
+        return so, ao, co
+
+    def predict(self, states, actions):
+        states = _f64(states)
+        actions = _f64(actions)
+        n = states.shape[0]
+        if states.shape != (n, self.D) or actions.shape != (n, self.A):
+            raise ValueError(f"predict expects states [n,{self.D}] and actions [n,{self.A}]")
+        out = np.empty_like(states)
+        self._ck(self._lib.bcmpc_predict(self._h, L.ptr(states), L.ptr(actions), n, L.ptr(out)))
+        return out
+
+    def policy_act(self, obs, noise=None):
+        obs = _f64(obs)
+        n = obs.shape[0]
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(n, self.A)
+        out = np.empty((n, self.A), np.float32)
+        self._ck(self._lib.bcmpc_policy_act(self._h, L.ptr(obs), L.ptr(nz), n, L.ptr(out)))
+        return out
+
+    def cheetah_cost(self, states, next_states):
+        states, next_states = _f64(states), _f64(next_states)
+        out = np.empty(states.shape[0])
+        self._ck(self._lib.bcmpc_cheetah_cost(self._h, L.ptr(states), L.ptr(next_states), states.shape[0], L.ptr(out)))
+        return out
+
+    def sample_injection(self, seed, n_states=1):
+        out = np.empty((n_states, self.H, self.K, self.A))
+        self._ck(self._lib.bcmpc_sample_injection(self._h, C.c_uint64(seed), n_states, L.ptr(out)))
+        return out
+
+    def reduce_records_device(self, d_gathered_ptr, n_ranks, n_states, d_out_ptr, stream_ptr=None):
+        self._ck(self._lib.bcmpc_reduce_records(self._h, C.c_void_p(d_gathered_ptr), n_ranks, n_states,
+                                                C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    # -- bookkeeping ------------------------------------------------------------------------------
+    @property
+    def kernel_launches(self):
+        return int(self._lib.bcmpc_kernel_launches(self._h))
+
+    def enable_timing(self, on=True):
+        self._ck(self._lib.bcmpc_enable_timing(self._h, int(on)))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._ck(self._lib.bcmpc_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)

@@ -1,0 +1,84 @@
+"""Inference side of the proposal networks: MlpPolicy.act (ppo_bc_policy.py:56-88,174-185) and
+BCnetwork.predict (behavioral_cloning.py:21-26,44-47).  Weight containers + GPU forward."""
+import numpy as np
+
+from .planner import Planner
+
+
+def rms_from_sums(runningsum, runningsumsq, count):
+    """baselines RunningMeanStd mean / std (float32 casts; std = sqrt(max(E[x^2]-mean^2, 1e-2)))."""
+    mean = (np.asarray(runningsum, np.float64) / count).astype(np.float32)
+    msq = (np.asarray(runningsumsq, np.float64) / count).astype(np.float32)
+    return mean, np.sqrt(np.maximum(msq - mean * mean, np.float32(1e-2))).astype(np.float32)
+
+
+class _ProposalNet:
+    logstd = None
+    filt_mean = None
+    filt_std = None
+    clip = 0.0
+
+    def __init__(self, env):
+        self.ob_dim = env.observation_space.shape[0]
+        self.ac_dim = env.action_space.shape[0]
+        self.weights = None
+        self.version = 0
+        self._fwd = None
+
+    def set_weights(self, weights, logstd=None, filt_mean=None, filt_std=None):
+        self.weights = [(np.asarray(w, np.float32), np.asarray(b, np.float32)) for w, b in weights]
+        if logstd is not None:
+            self.logstd = np.asarray(logstd, np.float32).reshape(-1)
+        if filt_mean is not None:
+            self.filt_mean, self.filt_std = np.asarray(filt_mean, np.float32), np.asarray(filt_std, np.float32)
+        self.version += 1
+        self._fwd = None
+
+    def upload(self, planner):
+        planner.set_policy(self.weights, self.logstd, self.filt_mean, self.filt_std, self.clip)
+
+    def _forward(self, ob, noise=None):
+        if self.weights is None:
+            raise RuntimeError("proposal network has no weights (set_weights / load_vars)")
+        if self._fwd is None:
+            p = Planner(self.ob_dim, self.ac_dim, 1, 4, num_paths=1, horizon=1)
+            self.upload(p)
+            self._fwd = p
+        return self._fwd.policy_act(ob, noise)
+
+
+class MlpPolicy(_ProposalNet):
+    """ppo_bc_policy.MlpPolicy, forward 'pol' branch only."""
+    recurrent = False
+    clip = 5.0
+
+    def __init__(self, sess=None, env=None, hid_size=128, num_hid_layers=2, clip_param=None, entcoeff=None):
+        super().__init__(env)
+        self.hid_size, self.num_hid_layers = hid_size, num_hid_layers
+
+    def load_vars(self, var_dict, scope="pi/pi"):
+        names = [f"fc{i + 1}" for i in range(self.num_hid_layers)] + ["final"]
+        ws = [(var_dict[f"{scope}/pol/{n}/kernel:0"], var_dict[f"{scope}/pol/{n}/bias:0"]) for n in names]
+        mean, std = rms_from_sums(var_dict[f"{scope}/obfilter/runningsum:0"],
+                                  var_dict[f"{scope}/obfilter/runningsumsq:0"],
+                                  float(var_dict[f"{scope}/obfilter/count:0"]))
+        self.set_weights(ws, var_dict[f"{scope}/pol/logstd:0"], mean, std)
+
+    def act(self, ob, stochastic=True):
+        """ppo_bc_policy.py:174-185.  Returns (ac, vpred); the value head is not on the planning
+        path (controllers.py:203 discards it) so vpred is None."""
+        ob = np.asarray(ob, np.float64)
+        if ob.ndim == 1:
+            ob = ob[None]
+        noise = np.random.standard_normal((ob.shape[0], self.ac_dim)).astype(np.float32) if stochastic else None
+        return self._forward(ob, noise), None
+
+
+class BCnetwork(_ProposalNet):
+    """behavioral_cloning.BCnetwork: 20 -> 128 tanh -> 64 tanh -> A linear, no observation filter."""
+
+    def __init__(self, sess=None, env=None, batch_size=None, learning_rate=None):
+        super().__init__(env)
+
+    def predict(self, obs):
+        return self._forward(np.asarray(obs, np.float64))

@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the MPC planning hot path (BASELINE.json metric: dynamics transitions/s and
+plans/s, HalfCheetah).
+
+Workload (config.workload): the per-GPU share of BASELINE.json configs[2] - 32*N concurrent synthetic root
+states x K=4096 paths x H=20, MLP 26->500->500->20 ReLU, cheetah cost, uniform shooting sampled on the
+device, bf16 fast mode; the K paths of every state are sharded over the N ranks (512*8/N ... K/N per rank)
+and each plan ends with one NCCL all-gather of 80-byte records + a min-loc kernel.  N=8 is configs[2] itself.
+A "step" is one batched plan.  `value` = transitions/s with inputs resident in HBM; `e2e` = the same
+through the host-buffer C-ABI call (pinned-host -> device copy of the states and device -> host read of the
+winning records inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN = (500, 500)
+K_PATHS, HORIZON, STATES_PER_GPU = 4096, 20, 32
+FLOP_PER_TRANSITION = 2 * (26 * 500 + 500 * 500 + 500 * 20)   # 546 000; padding not credited
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def problem():
+    from oracle import mpc_oracle as O   # synthetic inputs only (shared generator); never on the timed path
+    rng, norm, weights, state = O.synthetic_problem(0, HIDDEN)
+    return O, rng, norm, weights
+
+
+def cpu_baseline(budget_s=12.0):
+    """The oracle port (reference controllers/cost restated + numpy float32 predict) on the host cores:
+    BASELINE.json configs[0] (1 state, K=1000, H=15) repeated for about `budget_s` seconds."""
+    O, rng, norm, weights = problem()
+    dyn = O.OracleDynamics(weights, norm)
+    K, H = 1000, 15
+    mpc = O.OracleMPC(dyn, H, K)
+    state = O.synthetic_state(rng, norm)
+    mpc.get_action(state, rng.uniform(-1, 1, (H, K, 6)))
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s or n < 3:
+        mpc.get_action(state, rng.uniform(-1, 1, (H, K, 6)))   # controllers.py:53 sampling included
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * K * H / dt, "unit": "transitions/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} plans of configs[0] (1 state x K=1000 x H=15, numpy float32 BLAS predict, all host threads), "
+                      f"{dt:.1f} s; plans/s = {n / dt:.2f}; TF-less restatement = optimistic stand-in for the TF CPU path"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; TensorFlow is not installable here) on
+    this arm's config, each step a bounded sample: 1 root state x K=4096 x H=20."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O, rng, norm, weights = problem()
+    dyn = O.OracleDynamics(weights, norm)
+    mpc = O.OracleMPC(dyn, HORIZON, K_PATHS)
+    state = O.synthetic_state(rng, norm)
+    for _ in range(args.warmup):
+        mpc.get_action(state, rng.uniform(-1, 1, (HORIZON, K_PATHS, 6)))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mpc.get_action(state, rng.uniform(-1, 1, (HORIZON, K_PATHS, 6)))
+    dt = time.perf_counter() - t0
+    val = args.steps * K_PATHS * HORIZON / dt
+    sample = "each step = 1 root state x K=4096 x H=20 of the workload (81 920 transitions), oracle port, all host threads"
+    line = {"impl": "reference", "metric": "dynamics transitions/s (HalfCheetah random-shooting MPC)", "value": val,
+            "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "plans_per_s": args.steps / dt,
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": "transitions/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": f"BASELINE.json configs[2] per-GPU share: {STATES_PER_GPU * n} root states x K={K_PATHS} x H={HORIZON}, "
+                        f"MLP 26-500-500-20 ReLU, cheetah_cost_fn, uniform shooting (device Philox), K sharded over {n} GPU(s)",
+            "states": STATES_PER_GPU * n, "num_paths": K_PATHS, "horizon": HORIZON, "hidden": list(HIDDEN),
+            "precision": "bf16 operands / fp32 accumulate, state and cost",
+            "parallelism": f"paths sharded x{n}, NCCL all-gather of 80 B records + min-loc per plan" if n > 1 else "1 GPU",
+            "l2": "flushed between steps (256 MiB memset outside the per-step event pairs); weights (608 KB) are re-read from HBM once per step"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bc_mpc_b200 import _lib as L
+    from bc_mpc_b200.distributed import ShardedPlanner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = STATES_PER_GPU * world
+    O, rng, norm, weights = problem()
+    sp = ShardedPlanner(K_PATHS, HORIZON, rank=rank, world_size=world, device=local, obs_dim=20, act_dim=6, n_hidden=2,
+                        hidden_size=HIDDEN[0], activation="relu", max_states=B, precision="bf16", proposal="uniform")
+    pl = sp.planner
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"],
+                         norm["mean_deltas"], norm["std_deltas"])
+    pl.set_action_bounds(-np.ones(6), np.ones(6))
+    states = norm["mean_obs"] + norm["std_obs"] * np.random.default_rng(1).standard_normal((B, 20))
+    states[:, 18] = 0.0
+    d_states = torch.from_numpy(states).cuda()
+    h_states = torch.from_numpy(states).pin_memory()
+    h_out = torch.zeros(B * 80, dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        return sp.plan_device(d_states, B, seed=1000 + i)
+
+    def step_e2e(i):
+        d_states.copy_(h_states, non_blocking=True)                      # pinned host -> device, every step
+        out = sp.plan_device(d_states, B, seed=2000 + i)
+        h_out.copy_(out, non_blocking=True)                               # device -> host read of the winners
+        stream.synchronize()
+        return h_out
+
+    def timed(step_fn, steps, per_step_events):
+        evs = []
+        barrier()
+        t_wall = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn(i)
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        wall = time.perf_counter() - t_wall
+        ms = [a.elapsed_time(b) for a, b in evs]
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)                    # max over ranks, on the device
+        return float(tot.item()), ms, wall
+
+    for i in range(args.warmup):
+        step_resident(i)
+        step_e2e(i)
+    barrier()
+    # ---- resident-input throughput (value) + kernel-only duration for the roofline ----
+    pl.enable_timing(True)
+    launches0 = pl.kernel_launches
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    kernel_ms = []
+    evs_tot, ms_list, wall = 0.0, [], 0.0
+    barrier()
+    t_wall = time.perf_counter()
+    pairs = []
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_resident(i)
+        e1.record(stream)
+        pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        kernel_ms.append(pl.last_kernel_ms())
+    barrier()
+    wall = time.perf_counter() - t_wall
+    clk = clocks.stop() if rank == 0 else None
+    launches = pl.kernel_launches - launches0
+    ms_list = [a.elapsed_time(b) for a, b in pairs]
+    tot = torch.tensor([sum(ms_list)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms = float(tot.item())
+    pl.enable_timing(False)
+    # ---- end-to-end through the host-buffer path ----
+    e2e_ms, _, _ = timed(step_e2e, args.steps, True)
+
+    transitions_per_step = B * K_PATHS * HORIZON                          # all ranks together
+    value = transitions_per_step * args.steps / (total_ms * 1e-3)
+    e2e_value = transitions_per_step * args.steps / (e2e_ms * 1e-3)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        k_ms = float(np.mean(kernel_ms))
+        per_gpu_transitions = transitions_per_step / world
+        achieved = per_gpu_transitions * FLOP_PER_TRANSITION / (k_ms * 1e-3) / 1e12
+        line = {"metric": "dynamics transitions/s (HalfCheetah random-shooting MPC)", "value": value, "unit": "transitions/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "plans_per_s": B * args.steps / (total_ms * 1e-3),
+                "config": workload_config(world),
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "bcmpc::tc::rollout_tc_kernel", "kernel_ms": k_ms,
+                             "flop_per_transition": FLOP_PER_TRANSITION, "peak_source": peak_src,
+                             "note": "algorithmic FLOPs only (26-500-500-20); padded tiles (32/512/512/32) are not credited"},
+                "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": B * 20 * 8,
+                        "d2h_bytes_per_step": B * 80, "plans_per_s": B * args.steps / (e2e_ms * 1e-3)},
+                "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

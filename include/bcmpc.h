@@ -1,0 +1,163 @@
+/*
+ * bcmpc.h - C ABI of the B200-native random-shooting MPC planner.
+ *
+ * This is the drop-in boundary for the planning hot path of Bonnieccc/bc-mpc.  The
+ * reference has no FFI of its own (the path sits behind duck-typed Python objects), so
+ * each entry point cites the reference interface it replaces.  Plain pointers and sizes
+ * only; no torch / numpy types.  Every function returns 0 on success or a negative
+ * bcmpc_status; none throws across the ABI; bcmpc_last_error() returns the message.
+ *
+ * Threading: a handle is not re-entrant (one in-flight call per handle); use one handle per
+ * device / rank.  Ownership: the caller owns every buffer it passes; set_* calls COPY their
+ * inputs to the device (weights change after each dyn_model.fit, train_mpc_ppo.py:279, and
+ * each PPO update, :355-364, so call them again after training steps).
+ *
+ * Tensor layouts follow the reference: weights are TF "kernel" layout [in, out] row-major
+ * float32 with bias [out] (names NNDynamicsModel/dense{,_1,_2}/{kernel,bias}); action paths /
+ * injected randomness are [H, K, A] row-major (controllers.py:53), per root state
+ * ([B, H, K, A] when batched); states are float64 [*, D] (controllers.py:63).
+ */
+#ifndef BCMPC_H_
+#define BCMPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCMPC_ABI_VERSION 1
+#define BCMPC_MAX_ACT 8      /* action dims carried in a record (HalfCheetah: 6) */
+#define BCMPC_MAX_OBS 32     /* observation dims supported (HalfCheetah: 20)      */
+#define BCMPC_MAX_LAYERS 5   /* dense layers per MLP, output layer included        */
+
+typedef struct bcmpc_handle bcmpc_handle;
+
+typedef enum {
+  BCMPC_OK = 0,
+  BCMPC_ERR_INVALID = -1,     /* bad argument / configuration               */
+  BCMPC_ERR_CUDA = -2,        /* CUDA runtime error (message has the detail) */
+  BCMPC_ERR_STATE = -3,       /* weights / normalisation not set yet          */
+  BCMPC_ERR_UNSUPPORTED = -4  /* valid request the selected kernel cannot run */
+} bcmpc_status;
+
+/* hidden activation of the dynamics MLP (dynamics.py:66-67; all call sites use relu) */
+enum { BCMPC_ACT_RELU = 0, BCMPC_ACT_TANH = 1 };
+
+/* precision mode (BASELINE.json north_star): FP32_VERIFY follows the reference precision map
+ * of dynamics.py:106-119 (float64 normalise / state carry / cost, float32 MLP on FFMA);
+ * BF16_FAST is the tcgen05 path (bf16 operands, fp32 accumulate, fp32 state and cost). */
+enum { BCMPC_PREC_FP32_VERIFY = 0, BCMPC_PREC_BF16_FAST = 1 };
+
+/* action proposal mode:
+ *  P0 UNIFORM           controllers.py:43-55,70     a = inj,               inj ~ U[low,high)
+ *  P1 POLICY_GAUSSIAN   controllers.py:203          a = mean(s)+exp(logstd)*inj,  inj ~ N(0,1)
+ *  P2 POLICY_MIX        controllers.py:205-208      a = (1-e)*mean(s)+e*inj,      inj ~ U[low,high)
+ *  P3 NET_PLUS_UNIFORM  controllers.pyc src 120-163 a = net(s)+inj,               inj ~ U[-1,1)
+ */
+enum {
+  BCMPC_PROP_UNIFORM = 0,
+  BCMPC_PROP_POLICY_GAUSSIAN = 1,
+  BCMPC_PROP_POLICY_MIX = 2,
+  BCMPC_PROP_NET_PLUS_UNIFORM = 3
+};
+
+/* Replaces the constructor arguments of MPCcontroller / MPCcontrollerPolicyNet
+ * (controllers.py:28-41,162-181) and NNDynamicsModel (dynamics.py:8-52). */
+typedef struct {
+  int32_t obs_dim;      /* D  = env.observation_space.shape[0]                     */
+  int32_t act_dim;      /* A  = env.action_space.shape[0]                          */
+  int32_t n_hidden;     /* n_layers of NNDynamicsModel (hidden layers)              */
+  int32_t hidden_size;  /* size                                                     */
+  int32_t activation;   /* BCMPC_ACT_*                                              */
+  int32_t num_paths;    /* K paths THIS handle rolls per root state                 */
+  int32_t horizon;      /* H                                                        */
+  int32_t max_states;   /* B_max concurrent root states per plan call (>=1)         */
+  int32_t precision;    /* BCMPC_PREC_*                                             */
+  int32_t proposal;     /* BCMPC_PROP_*                                             */
+  int32_t device;       /* CUDA device ordinal                                      */
+  int32_t reserved0;
+  int64_t path_offset;  /* global index of this handle's first path (GPU sharding)  */
+  int64_t total_paths;  /* global K over all shards (0 -> num_paths)                */
+  double explore;       /* e of P2 (MPCcontrollerPolicyNet.explore)                 */
+} bcmpc_config;
+
+/* One winning candidate per root state: what controllers.py:82-85 extracts. */
+typedef struct {
+  double cost;                    /* costs[argmin]          (controllers.py:83)     */
+  int64_t index;                  /* global argmin index j  (controllers.py:82)     */
+  double action[BCMPC_MAX_ACT];   /* action_paths[0, j, :]  (controllers.py:84-85)  */
+} bcmpc_record;
+
+int bcmpc_abi_version(void);
+
+/* message of the last failing call on this handle (or on this thread when h == NULL) */
+const char* bcmpc_last_error(const bcmpc_handle* h);
+
+int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out);
+int bcmpc_destroy(bcmpc_handle* h);
+
+/* NNDynamicsModel weights (dynamics.py:54-71).  n_layers = n_hidden + 1; W[i] is [in_i,out_i]. */
+int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int32_t n_layers);
+
+/* The six members of the normalisation 10-tuple that predict uses (dynamics.py:41,109-113). */
+int bcmpc_set_normalization(bcmpc_handle* h, const double* mean_obs, const double* std_obs,
+                            const double* mean_act, const double* std_act,
+                            const double* mean_delta, const double* std_delta);
+
+/* env.action_space.low / high (controllers.py:53). */
+int bcmpc_set_action_bounds(bcmpc_handle* h, const double* low, const double* high);
+
+/* Proposal network: MlpPolicy 'pol' branch (ppo_bc_policy.py:60,70-72,79) or BCnetwork
+ * (behavioral_cloning.py:21-26).  sizes has n_layers+1 entries (sizes[0] = D, last = A); hidden
+ * layers are tanh, the last is linear.  logstd [A] may be NULL (P2/P3).  filt_mean/filt_std [D]
+ * (RunningMeanStd mean/std as float32) may be NULL = no filter; clip <= 0 = no clipping. */
+int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* W,
+                     const float* const* b, const float* logstd, const float* filt_mean,
+                     const float* filt_std, float clip);
+
+/* MPCcontroller.get_action / MPCcontrollerPolicyNet.get_action (controllers.py:57-88,189-237)
+ * for B root states at once, HOST buffers.  states [B,D]; inj [B,H,K,A] or NULL (NULL = sample
+ * on the device with Philox4x32-10 keyed by seed and the global path index).  out [B]. */
+int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const double* inj,
+               uint64_t seed, bcmpc_record* out);
+
+/* Same, DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = the handle's own). */
+int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj,
+                      uint64_t seed, bcmpc_record* d_out, void* stream);
+
+/* Verification only: one root state, every path's states [H+1,K,D] (controllers.py:74), actions
+ * [H,K,A] and trajectory costs [K] (controllers.py:80).  Any output may be NULL.  HOST buffers. */
+int bcmpc_rollout_debug(bcmpc_handle* h, const double* state, const double* inj, uint64_t seed,
+                        double* states_out, double* actions_out, double* costs_out);
+
+/* NNDynamicsModel.predict (dynamics.py:106-119): n independent (state, action) rows. HOST buffers. */
+int bcmpc_predict(bcmpc_handle* h, const double* states, const double* actions, int64_t n, double* next_states);
+
+/* policy_net.act(ob, stochastic) (ppo_bc_policy.py:174-185) / BCnetwork.predict: noise [n,A] N(0,1)
+ * draws for the stochastic sample, NULL = mode (mean).  out float32 [n,A].  HOST buffers. */
+int bcmpc_policy_act(bcmpc_handle* h, const double* obs, const float* noise, int64_t n, float* out);
+
+/* cheetah_cost_fn batched branch (cost_functions.py:10-30) on the device.  HOST buffers. */
+int bcmpc_cheetah_cost(bcmpc_handle* h, const double* states, const double* next_states, int64_t n, double* out);
+
+/* The injection tensor [B,H,K,A] the planner would draw on the device for (seed, proposal). */
+int bcmpc_sample_injection(bcmpc_handle* h, uint64_t seed, int32_t n_states, double* out);
+
+/* Cross-GPU min-loc: gathered [n_ranks, n_states] records -> [n_states] winners, lowest global
+ * index on ties, NaN wins (np.argmin, controllers.py:82).  DEVICE buffers, asynchronous. */
+int bcmpc_reduce_records(bcmpc_handle* h, const bcmpc_record* d_gathered, int32_t n_ranks,
+                         int32_t n_states, bcmpc_record* d_out, void* stream);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t bcmpc_kernel_launches(const bcmpc_handle* h);
+
+/* device time (ms, CUDA events on the launch stream) of the last bcmpc_plan* rollout kernel; the
+ * events are recorded around the kernel only when timing was enabled. */
+int bcmpc_enable_timing(bcmpc_handle* h, int32_t on);
+int bcmpc_last_kernel_ms(bcmpc_handle* h, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCMPC_H_ */

@@ -253,7 +253,7 @@ class OracleMPC:
                 actions = (1 - self.explore) * actions + self.explore * inj[i, :, :]  # :208
             elif self.proposal == "bc_uniform":
                 actions = self.policy.predict(states)  # controllers.pyc src 120-163
-                actions = actions + inj[i, :, :]
+                actions += inj[i, :, :]  # in place: float32 array += float64 draw stays float32
             else:
                 raise ValueError(self.proposal)
             states = self.dyn_model.predict(states, actions)  # :70 / :210

@@ -1,0 +1,220 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libbcmpc.so), against
+the oracle on the same seeded inputs and against the golden fixtures made by the reference's own
+controllers.py / cost_functions.py.  FP32 verification mode: per-step states within 1e-4 relative,
+identical argmin and first action (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mpc_oracle as O
+from tests._util import f32_uniform, make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # north_star: predicted states within 1e-4 relative per step
+
+
+def _planner_for(weights, norm, K, H, **kw):
+    from bc_mpc_b200 import Planner
+    hidden = weights[0][0].shape[1]
+    pl = Planner(20, 6, len(weights) - 1, hidden, "relu", num_paths=K, horizon=H, **kw)
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"],
+                         norm["mean_deltas"], norm["std_deltas"])
+    return pl
+
+
+def test_golden_uniform_plans(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mpc_uniform.npz"))
+    for tag in "abc":
+        hidden = tuple(int(x) for x in g[f"{tag}_hidden"])
+        rng, norm, weights, state = O.synthetic_problem(int(g[f"{tag}_seed"]), hidden)
+        actions = g[f"{tag}_actions"]
+        H, K = actions.shape[:2]
+        pl = _planner_for(weights, norm, K, H)
+        so, ao, co = pl.rollout_debug(state, actions)
+        assert np.array_equal(ao, actions)
+        assert rel_err(so, g[f"{tag}_states"]).max() < TOL
+        assert np.abs(co - g[f"{tag}_costs"]).max() < 1e-3
+        rec = pl.plan(state, inj=actions)[0]
+        assert rec["index"] == int(g[f"{tag}_argmin"])
+        assert np.array_equal(rec["action"][:6], g[f"{tag}_first_action"])
+
+
+def test_golden_trained_weights(golden_dir):
+    g = np.load(os.path.join(golden_dir, "vars_ppo_mpc.npz"))
+    weights = [(g[f"dyn_w{i}"], g[f"dyn_b{i}"]) for i in range(3)]
+    norm = O.synthetic_normalization()
+    H, K = g["plan_actions"].shape[:2]
+    pl = _planner_for(weights, norm, K, H)
+    so, _, co = pl.rollout_debug(g["plan_state"], g["plan_actions"])
+    assert rel_err(so, g["plan_states"]).max() < TOL
+    rec = pl.plan(g["plan_state"], inj=g["plan_actions"])[0]
+    assert rec["index"] == int(np.argmin(g["plan_costs"]))
+    assert np.array_equal(rec["action"][:6], g["plan_first_action"])
+
+
+def test_golden_policy_plans(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mpc_policy.npz"))
+    hidden = tuple(int(x) for x in g["hidden"])
+    H, K = g["eps"].shape[:2]
+    for proposal, inj, want in (("policy_gaussian", g["eps"], g["selfexp_first_action"]),
+                                ("policy_mix", g["uni"], g["mix_first_action"])):
+        rng, norm, state, pl, mpc = make_pair(int(g["seed"]), hidden, K, H, proposal=proposal, policy_hidden=(32, 32),
+                                              explore=float(g["explore"]), bias_scale=0.1)
+        rec = pl.plan(state, inj=inj)[0]
+        assert np.allclose(rec["action"][:6], want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("K,H", [(1000, 15), (4096, 15)])   # BASELINE.json configs[0], configs[1]
+def test_config_1_2_verify_mode(seed, K, H):
+    rng, norm, state, pl, mpc = make_pair(seed, (500, 500), K, H)
+    actions = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    err = rel_err(so, dbg["states"])
+    assert err.max() < TOL, err.max()
+    rec = pl.plan(state, inj=actions)[0]
+    order = np.sort(dbg["costs"])
+    assert rec["index"] == dbg["argmin"], (rec["index"], dbg["argmin"], order[:2])
+    assert np.array_equal(rec["action"][:6], act)
+    assert abs(rec["cost"] - dbg["costs"][dbg["argmin"]]) < 1e-3
+
+
+def test_threshold_and_tie_cases():
+    K, H = 256, 4
+    rng, norm, state, pl, mpc = make_pair(11, (64, 64), K, H)
+    state[5], state[6], state[7] = 0.2, -0.0, -1e-12   # exactly on / next to the >= thresholds
+    actions = f32_uniform(rng, (H, K, 6))
+    actions[:, 200] = actions[:, 17]                      # identical sequences -> lowest index must win
+    actions[:, 5] = actions[:, 17]
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    assert co[5] == co[17] == co[200]
+    assert np.array_equal(np.round(co[:8] - dbg["costs"][:8], 3), np.zeros(8))
+    rec = pl.plan(state, inj=actions)[0]
+    assert rec["index"] == dbg["argmin"]
+
+
+@pytest.mark.parametrize("proposal,bc", [("policy_gaussian", False), ("policy_mix", False), ("bc_uniform", True)])
+def test_policy_proposals_vs_oracle(proposal, bc):
+    K, H = 8192 if proposal == "policy_gaussian" else 512, 15   # BASELINE.json configs[3] shape for P1
+    rng, norm, state, pl, mpc = make_pair(21, (500, 500), K, H, proposal=proposal, bc=bc)
+    inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64) if proposal == "policy_gaussian" \
+        else f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, inj, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, inj)
+    assert rel_err(ao, dbg["actions"]).max() < TOL
+    assert rel_err(so, dbg["states"]).max() < TOL
+    rec = pl.plan(state, inj=inj)[0]
+    assert rec["index"] == dbg["argmin"]
+    assert np.allclose(rec["action"][:6], act, rtol=1e-5, atol=1e-6)
+
+
+def test_predict_policy_cost_entry_points(golden_dir):
+    rng, norm, state, pl, mpc = make_pair(5, (500, 500), 8, 2, proposal="policy_gaussian")
+    n = 333
+    S = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((n, 20))
+    A = f32_uniform(rng, (n, 6))
+    assert rel_err(pl.predict(S, A), mpc.dyn_model.predict(S, A)).max() < 1e-5
+    eps = rng.standard_normal((n, 6)).astype(np.float32)
+    assert np.allclose(pl.policy_act(S), mpc.policy.act(S, False)[0], rtol=1e-5, atol=1e-6)
+    assert np.allclose(pl.policy_act(S, eps), mpc.policy.act(S, True, noise=eps)[0], rtol=1e-5, atol=1e-6)
+    g = np.load(os.path.join(golden_dir, "cost_kat.npz"))
+    assert np.array_equal(pl.cheetah_cost(g["S"], g["N"]), g["batched"])     # bit-exact: float64 compare/sub/div
+
+
+def test_device_sampling_replays_through_oracle():
+    K, H = 1000, 15
+    rng, norm, state, pl, mpc = make_pair(31, (500, 500), K, H)
+    rec = pl.plan(state, seed=1234)[0]
+    inj = pl.sample_injection(1234)[0]
+    assert inj.shape == (H, K, 6) and (inj >= -1).all() and (inj < 1).all()
+    act, dbg = mpc.get_action(state, inj, return_debug=True)
+    assert rec["index"] == dbg["argmin"] and np.array_equal(rec["action"][:6], act)
+    rec2 = pl.plan(state, seed=1235)[0]
+    assert not np.array_equal(rec2["action"], rec["action"])
+    # statistics of U[-1,1): mean 0, var 1/3
+    assert abs(inj.mean()) < 0.01 and abs(inj.var() - 1 / 3) < 0.01
+    cols = inj.reshape(-1, 6)
+    assert np.abs(np.corrcoef(cols.T) - np.eye(6)).max() < 0.02
+
+
+def test_normal_sampling_statistics():
+    rng, norm, state, pl, mpc = make_pair(32, (64, 64), 4096, 8, proposal="policy_gaussian")
+    z = pl.sample_injection(7)[0].reshape(-1)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs((z ** 3).mean()) < 0.03 and abs((z ** 4).mean() - 3) < 0.1
+
+
+def test_batched_states_equal_single_plans():
+    K, H, B = 300, 6, 5
+    rng, norm, state, pl, mpc = make_pair(41, (64, 64), K, H, max_states=B)
+    states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((B, 20))
+    inj = f32_uniform(rng, (B, H, K, 6))
+    recs = pl.plan(states, inj=inj)
+    for b in range(B):
+        act, dbg = mpc.get_action(states[b], inj[b], return_debug=True)
+        assert recs[b]["index"] == dbg["argmin"] and np.array_equal(recs[b]["action"][:6], act)
+    # device sampling: root-state index is part of the Philox counter, so states do not share draws
+    recs = pl.plan(np.tile(states[0], [B, 1]), seed=3)
+    assert len({int(r["index"]) for r in recs}) > 1
+
+
+def test_sharded_paths_match_single_gpu_result():
+    import torch
+    from bc_mpc_b200 import _lib as L
+    K, H, G = 1000, 8, 4
+    rng, norm, state, pl, mpc = make_pair(51, (64, 64), K, H)
+    want = pl.plan(state, seed=99)[0]
+    bounds = [0, 250, 500, 777, 1000]     # ragged shards
+    gathered = torch.zeros(G * 80, dtype=torch.uint8, device="cuda")
+    d_state = torch.tensor(state, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()    # the handles launch on their own streams
+    shards = []
+    for g in range(G):
+        _, _, _, sp, _ = make_pair(51, (64, 64), bounds[g + 1] - bounds[g], H, path_offset=bounds[g], total_paths=K)
+        sp.plan_device(d_state.data_ptr(), 1, gathered.data_ptr() + g * 80, seed=99)
+        shards.append(sp)
+    torch.cuda.synchronize()
+    out = torch.zeros(80, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    pl.reduce_records_device(gathered.data_ptr(), G, 1, out.data_ptr())
+    torch.cuda.synchronize()
+    got = np.frombuffer(out.cpu().numpy().tobytes(), L.RECORD_DTYPE)[0]
+    assert got["index"] == want["index"] and got["cost"] == want["cost"]
+    assert np.array_equal(got["action"], want["action"])
+
+
+def test_edge_shapes_and_errors():
+    from bc_mpc_b200 import Planner
+    for K, H in [(1, 1), (33, 2), (129, 3)]:
+        rng, norm, state, pl, mpc = make_pair(61, (40, 40), K, H)
+        actions = f32_uniform(rng, (H, K, 6))
+        act, dbg = mpc.get_action(state, actions, return_debug=True)
+        rec = pl.plan(state, inj=actions)[0]
+        assert rec["index"] == dbg["argmin"] and np.array_equal(rec["action"][:6], act)
+    pl = Planner(num_paths=4, horizon=2, hidden_size=8)
+    with pytest.raises(RuntimeError, match="dynamics weights not set"):
+        pl.plan(np.zeros(20))
+    with pytest.raises(ValueError):
+        pl.set_dynamics([(np.zeros((26, 9), np.float32), np.zeros(9, np.float32))] * 3)
+    with pytest.raises(RuntimeError, match="obs_dim"):
+        Planner(obs_dim=64)
+    with pytest.raises(RuntimeError, match="n_states"):
+        rng, norm, state, pl, mpc = make_pair(61, (40, 40), 4, 2)
+        pl.plan(np.zeros((2, 20)))
+
+
+def test_nan_cost_wins_like_numpy():
+    K, H = 64, 2
+    rng, norm, state, pl, mpc = make_pair(71, (32, 32), K, H)
+    actions = f32_uniform(rng, (H, K, 6))
+    actions[1, 40, 2] = np.nan          # a NaN action poisons path 40's last step
+    with np.errstate(invalid="ignore"):
+        act, dbg = mpc.get_action(state, actions, return_debug=True)
+    assert dbg["argmin"] == 40
+    rec = pl.plan(state, inj=actions)[0]
+    assert rec["index"] == 40 and np.isnan(rec["cost"])
