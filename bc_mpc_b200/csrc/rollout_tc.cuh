@@ -345,10 +345,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc_kernel(const __grid_co
             ptx::mbar_wait(bars + 8u * op.wait_bar, (uint32_t)((pbits >> op.wait_bar) & 1ull));
             pbits ^= 1ull << op.wait_bar;
           }
-          if (op.flags & kOpFirst) {
+          if (!(op.flags & kOpL3)) {
             const uint32_t seq = (uint32_t)(h * 2 * NC + op.chunk_id);
-            buf = seq % kNumDBuf;
-            ptx::mbar_wait(bars + 8u * (kBarDEmpty + buf), ((seq / kNumDBuf) & 1u) ^ 1u);
+            buf = seq % kNumDBuf;     // ops of different chunks may interleave (schedule 1)
+            if (op.flags & kOpFirst) ptx::mbar_wait(bars + 8u * (kBarDEmpty + buf), ((seq / kNumDBuf) & 1u) ^ 1u);
           }
           ptx::mbar_wait(bars + 8u * (kBarWFull + stage), phase);
           ptx::tc_fence_after();

@@ -78,8 +78,8 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
     for (int r = 0; r < 8; ++r) {
       float4 o;
       o.x = acc[r][0] + bv.x; o.y = acc[r][1] + bv.y; o.z = acc[r][2] + bv.z; o.w = acc[r][3] + bv.w;
-      if (act == BCMPC_ACT_RELU) {
-        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+      if (act == BCMPC_ACT_RELU) {   // (x < 0) ? 0 : x propagates NaN like Eigen's / numpy's max (fmaxf would drop it)
+        o.x = o.x < 0.f ? 0.f : o.x; o.y = o.y < 0.f ? 0.f : o.y; o.z = o.z < 0.f ? 0.f : o.z; o.w = o.w < 0.f ? 0.f : o.w;
       } else if (act == BCMPC_ACT_TANH) {
         o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
       }

@@ -12,6 +12,15 @@ _PRECISIONS = {"fp32": L.PREC_FP32_VERIFY, "fp32_verify": L.PREC_FP32_VERIFY,
 _ACTS = {"relu": L.ACT_RELU, "tanh": L.ACT_TANH}
 
 
+_CUDA_STREAM_LEGACY = 1   # cudaStreamLegacy: the explicit handle of the legacy default stream (stream 0)
+
+
+def _stream(stream_ptr):
+    if stream_ptr is None:
+        return None
+    return C.c_void_p(int(stream_ptr) or _CUDA_STREAM_LEGACY)
+
+
 def _f64(a, shape=None):
     a = np.ascontiguousarray(a, dtype=np.float64)
     if shape is not None and tuple(a.shape) != tuple(shape):
@@ -112,10 +121,12 @@ class Planner:
         return out
 
     def plan_device(self, d_states_ptr, n_states, d_out_ptr, seed=0, d_inj_ptr=None, stream_ptr=None):
-        """Asynchronous launch on device buffers (raw pointers, e.g. torch.Tensor.data_ptr())."""
+        """Asynchronous launch on device buffers (raw pointers, e.g. torch.Tensor.data_ptr()).
+        stream_ptr: None = the handle's own stream; an integer cudaStream_t otherwise (0, torch's default
+        stream, is passed as cudaStreamLegacy so that it is not mistaken for "none")."""
         self._ck(self._lib.bcmpc_plan_device(self._h, C.c_void_p(d_states_ptr), n_states,
                                              C.c_void_p(d_inj_ptr) if d_inj_ptr else None, C.c_uint64(seed),
-                                             C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr) if stream_ptr else None))
+                                             C.c_void_p(d_out_ptr), _stream(stream_ptr)))
 
     def rollout_debug(self, state, inj=None, seed=0, want_states=True, want_actions=True):
         state = _f64(state, (self.D,))
@@ -159,7 +170,7 @@ class Planner:
 
     def reduce_records_device(self, d_gathered_ptr, n_ranks, n_states, d_out_ptr, stream_ptr=None):
         self._ck(self._lib.bcmpc_reduce_records(self._h, C.c_void_p(d_gathered_ptr), n_ranks, n_states,
-                                                C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr) if stream_ptr else None))
+                                                C.c_void_p(d_out_ptr), _stream(stream_ptr)))
 
     # -- bookkeeping ------------------------------------------------------------------------------
     @property

@@ -37,6 +37,19 @@ def rel_err(got, ref):
     return np.abs(got - ref) / (np.abs(ref) + 1e-3)
 
 
+def state_scale(norm):
+    """natural magnitude of every observation dimension: |mean_obs| + std_obs (idx 18 is identically 0)"""
+    return np.abs(norm["mean_obs"]) + norm["std_obs"]
+
+
+def scaled_rel_err(got, ref, scale):
+    """per-entry error relative to max-ish(|entry|, magnitude of its dimension): |got-ref| / (|ref| + scale + 1e-3).
+    Two float32 GEMMs that sum in different orders (numpy/OpenBLAS vs FFMA k-ascending vs TF/Eigen) differ by
+    ~1e-6 of the DIMENSION's magnitude, so an entry that happens to pass near zero has an unbounded
+    entry-relative error in any float32 implementation; the dimension scale is the meaningful denominator."""
+    return np.abs(got - ref) / (np.abs(ref) + scale + 1e-3)
+
+
 def f32_uniform(rng, shape):
     """U[-1,1) draws that are exactly representable in float32 (so every precision mode sees the same numbers)"""
     return rng.uniform(-1, 1, shape).astype(np.float32).astype(np.float64)

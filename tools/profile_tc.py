@@ -1,0 +1,20 @@
+"""One batched plan of the bench workload (32 states x K=4096 x H=20, bf16) for ncu."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bc_mpc_b200 import Planner  # noqa: E402
+from oracle import mpc_oracle as O  # noqa: E402
+
+B = int(os.environ.get("PROF_B", "32"))
+H = int(os.environ.get("PROF_H", "20"))
+rng, norm, weights, state = O.synthetic_problem(0, (500, 500))
+pl = Planner(20, 6, 2, 500, "relu", num_paths=4096, horizon=H, precision="bf16", max_states=B)
+pl.set_dynamics(weights)
+pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((B, 20))
+for i in range(3):
+    rec = pl.plan(states, seed=i)
+print("ok", rec[0]["index"], rec[0]["cost"])
