@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libbcmpc.so")
 SRC = os.path.join(HERE, "csrc", "api.cu")
 DEPS = [os.path.join(HERE, "csrc", f) for f in
-        ("api.cu", "common.cuh", "ptx.cuh", "rollout_verify.cuh", "rollout_tc.cuh", "aux_kernels.cuh")]
+        ("api.cu", "common.cuh", "ptx.cuh", "rollout_verify.cuh", "rollout_tmem.cuh", "aux_kernels.cuh")]
 DEPS.append(os.path.join(HERE, "..", "include", "bcmpc.h"))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

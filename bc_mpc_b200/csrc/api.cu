@@ -12,7 +12,7 @@
 #include "../../include/bcmpc.h"
 #include "aux_kernels.cuh"
 #include "common.cuh"
-#include "rollout_tc.cuh"
+#include "rollout_tmem.cuh"
 #include "rollout_verify.cuh"
 
 using namespace bcmpc;
@@ -57,13 +57,13 @@ struct bcmpc_handle {
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
-  // tcgen05 path
-  tc::TcHostPlan tcp;
-  uint8_t* d_tape = nullptr;
-  tc::TcOp* d_ops = nullptr;
-  float *d_b1 = nullptr, *d_b2 = nullptr;
-  bool tc_ready = false;
-  int tc_schedule = 1;
+  // tcgen05 path (rollout_tmem.cuh)
+  tmx::TmHostPlan tmp;
+  uint8_t *d_res = nullptr, *d_stream = nullptr;
+  unsigned long long* d_trace = nullptr;
+  bool tm_ready = false;
+  int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
+  std::string trace_path; // BCMPC_TC_TRACE: dump the pipeline trace of CTA (0,0) after every launch
 };
 
 namespace {
@@ -181,45 +181,37 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
   return BCMPC_OK;
 }
 
-int tc_prepare(bcmpc_handle* h, const float* const* W, const float* const* b) {
+int tm_prepare(bcmpc_handle* h, const float* const* W, const float* const* b) {
   const int S = h->cfg.hidden_size;
-  tc::tc_build(W[0], b[0], W[1], b[1], W[2], b[2], S, h->tc_schedule, &h->tcp);
-  const tc::TcHostPlan& P = h->tcp;
-  if ((int)P.ops.size() > tc::kMaxOps) return fail(h, BCMPC_ERR_UNSUPPORTED, "op table too long (%zu)", P.ops.size());
-  if (h->d_tape) cudaFree(h->d_tape);
-  if (h->d_ops) cudaFree(h->d_ops);
-  if (h->d_b1) cudaFree(h->d_b1);
-  if (h->d_b2) cudaFree(h->d_b2);
-  h->d_tape = nullptr; h->d_ops = nullptr; h->d_b1 = h->d_b2 = nullptr;
-  CK(h, cudaMalloc(&h->d_tape, P.tape.size() * 2));
-  CK(h, cudaMalloc(&h->d_ops, P.ops.size() * sizeof(tc::TcOp)));
-  CK(h, cudaMalloc(&h->d_b1, P.b1.size() * sizeof(float)));
-  CK(h, cudaMalloc(&h->d_b2, P.b2.size() * sizeof(float)));
-  CK(h, cudaMemcpy(h->d_tape, P.tape.data(), P.tape.size() * 2, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(h->d_ops, P.ops.data(), P.ops.size() * sizeof(tc::TcOp), cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(h->d_b1, P.b1.data(), P.b1.size() * sizeof(float), cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(h->d_b2, P.b2.data(), P.b2.size() * sizeof(float), cudaMemcpyHostToDevice));
-  CK(h, cudaFuncSetAttribute(tc::rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-  h->tc_ready = true;
+  tmx::tm_build(W[0], b[0], W[1], b[1], W[2], b[2], S, h->tm_cg, &h->tmp);
+  const tmx::TmHostPlan& P = h->tmp;
+  if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
+  if (P.lay.nst < 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "weight ring does not fit in shared memory");
+  if (h->d_res) cudaFree(h->d_res);
+  if (h->d_stream) cudaFree(h->d_stream);
+  h->d_res = h->d_stream = nullptr;
+  CK(h, cudaMalloc(&h->d_res, P.res.size() * 2));
+  CK(h, cudaMalloc(&h->d_stream, P.stream.size() * 2));
+  CK(h, cudaMemcpy(h->d_res, P.res.data(), P.res.size() * 2, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(h->d_stream, P.stream.data(), P.stream.size() * 2, cudaMemcpyHostToDevice));
+  if (!h->trace_path.empty() && !h->d_trace)
+    CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots));
+  h->tm_ready = true;
   return BCMPC_OK;
 }
 
-int launch_tc(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
-  if (!h->tc_ready) return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared (bcmpc_set_dynamics)");
-  const tc::TcHostPlan& P = h->tcp;
-  tc::TcArgs a;
+int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
+  if (!h->tm_ready) return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared (bcmpc_set_dynamics)");
+  const tmx::TmHostPlan& P = h->tmp;
+  tmx::TmArgs a;
   memset(&a, 0, sizeof a);
   a.p = p;
-  a.tape = h->d_tape; a.ops = h->d_ops; a.n_ops = (int)P.ops.size();
-  a.nkb = P.nkb; a.nc = P.nc; a.nst = P.nst;
-  a.off_a1 = P.off_a1; a.off_ring2 = P.off_ring2; a.off_wring = P.off_wring; a.off_misc = P.off_misc;
-  a.b1 = h->d_b1; a.b2 = h->d_b2;
+  a.res = h->d_res; a.stream = h->d_stream; a.trace = h->d_trace;
   for (int d = 0; d < h->cfg.obs_dim; ++d) {
     a.mean_obs[d] = (float)h->norm.mean_obs[d];
     a.inv_den_obs[d] = (float)(1.0 / h->norm.den_obs[d]);
     a.mean_delta[d] = (float)h->norm.mean_delta[d];
     a.std_delta[d] = (float)h->norm.std_delta[d];
-    a.b3[d] = P.b3[d];
   }
   for (int j = 0; j < h->cfg.act_dim; ++j) {
     a.mean_act[j] = (float)h->norm.mean_act[j];
@@ -227,18 +219,37 @@ int launch_tc(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.low[j] = h->norm.low[j];
     a.span[j] = h->norm.span[j];
   }
-  dim3 grid(p.tiles_per_state, p.B);
-  tc::rollout_tc_kernel<<<grid, tc::kThreads, P.smem_bytes, st>>>(a);
+  if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
+  // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
+  CK(h, tmx::tm_launch(h->tm_cg, P.nc, a, dim3(p.tiles_per_state, p.B), st));
   CK(h, cudaGetLastError());
   h->launches++;
+  if (h->d_trace) {
+    CK(h, cudaStreamSynchronize(st));
+    std::vector<unsigned long long> t((size_t)tmx::kTraceSteps * tmx::kTraceSlots);
+    CK(h, cudaMemcpy(t.data(), h->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(h->trace_path.c_str(), "wb")) {
+      const tmx::Schedule sch = tmx::make_schedule(P.nc, P.lay.kbs);
+      const int hdr[10] = {tmx::kTraceSteps, tmx::kTraceSlots, sch.n, P.nc, tmx::kTrMma, tmx::kTrL3, tmx::kTrEpi, tmx::kTrFinal,
+                           tmx::kTrProd, P.nc * P.lay.nstg};
+      fwrite(hdr, sizeof hdr, 1, f);
+      fwrite(t.data(), sizeof(unsigned long long), t.size(), f);
+      for (int i = 0; i < sch.n; ++i) {
+        const int rec[6] = {sch.ops[i].kind, sch.ops[i].c, sch.ops[i].kb0, sch.ops[i].nblk, sch.ops[i].buf, sch.ops[i].sfirst};
+        fwrite(rec, sizeof rec, 1, f);
+      }
+      fclose(f);
+    }
+  }
   return BCMPC_OK;
 }
 
 // rollout (either precision) + per-state reduction of the tile candidates into d_out[B]
 int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, int force_verify) {
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST && !force_verify;
-  const int M = fast ? tc::kRows : h->vM;
+  const int M = fast ? tmx::kRows : h->vM;
   p.tiles_per_state = (p.K + M - 1) / M;
+  if (fast && h->tm_cg == 2) p.tiles_per_state = (p.tiles_per_state + 1) / 2 * 2;   // CTA pairs; a padding tile has no valid row
   if (d_out) {
     int rc = ensure_cand(h, (size_t)p.B * p.tiles_per_state);
     if (rc) return rc;
@@ -249,7 +260,7 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   if (h->timing) { CK(h, cudaEventRecord(h->ev0, st)); }
   int rc;
   if (fast) {
-    rc = launch_tc(h, p, st);
+    rc = launch_tm(h, p, st);
   } else {
     VerifyArgs a;
     fill_verify_args(h, &a);
@@ -304,7 +315,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   if (c.path_offset < 0 || c.path_offset + c.num_paths > 0xFFFFFFFFLL) return fail(nullptr, BCMPC_ERR_INVALID, "path_offset out of range");
   if (c.precision == BCMPC_PREC_BF16_FAST) {
     std::string why;
-    if (!tc::tc_supported(c, &why)) return fail(nullptr, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
+    if (!tmx::tm_supported(c, &why)) return fail(nullptr, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -313,7 +324,8 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   bcmpc_handle* h = new bcmpc_handle();
   h->cfg = c;
   if (h->cfg.total_paths <= 0) h->cfg.total_paths = c.path_offset + c.num_paths;
-  if (const char* s = getenv("BCMPC_TC_SCHEDULE")) h->tc_schedule = atoi(s);
+  if (const char* s = getenv("BCMPC_TC_CG")) h->tm_cg = atoi(s) == 2 ? 2 : 1;
+  if (const char* s = getenv("BCMPC_TC_TRACE")) h->trace_path = s;
   cudaError_t e = cudaSetDevice(c.device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
@@ -340,7 +352,7 @@ int bcmpc_destroy(bcmpc_handle* h) {
   h->dyn.release();
   h->pol.release();
   cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
-  cudaFree(h->d_tape); cudaFree(h->d_ops); cudaFree(h->d_b1); cudaFree(h->d_b2);
+  cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_trace);
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_records) cudaFreeHost(h->h_records);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -365,7 +377,7 @@ int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* cons
   if (rc) return rc;
   update_verify_geometry(h);
   if (h->cfg.precision == BCMPC_PREC_BF16_FAST) {
-    rc = tc_prepare(h, W, b);
+    rc = tm_prepare(h, W, b);
     if (rc) return rc;
   }
   return BCMPC_OK;

@@ -1,0 +1,728 @@
+// BF16 fast-mode fused rollout kernel (BCMPC_PREC_BF16_FAST): tcgen05.mma with TMEM-resident activations.
+//
+// One CTA owns 128 paths (one TMEM lane per path) for all H steps.  With CG = 2 two CTAs of a cluster form a
+// cta_group::2 pair: 256 paths per UMMA (M = 256), every weight tile is fetched once per pair (each CTA loads
+// half of its rows) and read by both tensor cores, which halves the L2 -> SM weight stream per path.
+//
+// Where the data lives (per CTA):
+//   registers   state s[20] (fp32), running cost, first action of the path that owns the TMEM lane
+//   TMEM (512 columns x 128 lanes)
+//     [  0,256)  A1   hidden-1 activations, bf16 pairs, the A operand of layer 2  (tcgen05.mma A-from-TMEM)
+//     [256,448)  D    3 x 64-column fp32 accumulators (layer 1 / layer 2 output chunks)
+//     [448,480)  A2   one 64-unit chunk of hidden-2 activations (bf16 pairs), the A operand of layer 3
+//     [480,512)  D3   output-layer accumulator (20 of 32 columns used)
+//   shared memory
+//     A0   [128 x 64] bf16 K-major SWIZZLE_128B: normalised (state, action, 1, 1) rows = A operand of layer 1
+//     W1, W3 resident for the whole kernel (UMMA smem images, loaded once)
+//     ring of W2 tiles streamed from L2 with cp.async.bulk + mbarriers
+//   no activation or state ever touches HBM.
+//
+// Per step (hidden width S padded to a multiple of 64, NC = chunks of 64 hidden units):
+//   L1  D[c]  = A0 x W1[c]                 (2 k-steps, A from smem)      -> epilogue ReLU, bf16 -> A1[:, 64c..]
+//   L2  D[c]  = A1 x W2[:, c]              (S/16 k-steps, A from TMEM)   -> epilogue ReLU, bf16 -> A2
+//   L3  D3   += A2 x W3[64c.., :]          (4 k-steps per chunk)
+//   final epilogue: denormalise, cheetah cost on the pre-step state, s += delta, next action (Philox), normalise
+//                   -> A0 of the next step.
+// Biases ride in the GEMMs (two constant-1 input columns / hidden units x a hi+lo bf16 split of the bias), so the
+// hidden epilogues are ReLU + convert only.
+//
+// Roles: warp 0 = weight producer; warps 1 and 3 = MMA issuers of the leader CTA (warp 1: the even layer-2 chunks,
+// warp 3: layer 1 and the odd layer-2 chunks - two issuers so that one can wait on barriers while the other keeps the
+// tensor pipe fed; every accumulator is written by one issuer only, so results do not depend on the interleaving);
+// warp 2 = TMEM allocation + layer-3 issuer; in the peer CTA warp 1 forwards "weights landed" to the leader;
+// warps 4-11 = epilogue: two groups of four warps (one warp per TMEM lane quadrant) that take alternate accumulator
+// chunks, 64 columns per warp.
+// The step's schedule - which accumulator a chunk uses, what each MMA group waits for and signals - is computed by a
+// constexpr function and unrolled at compile time, so every TMEM column, barrier and descriptor offset is an immediate.
+//
+// Replaces dynamics.py:106-119 + cost_functions.py:10-30,59-63 + controllers.py:53,63-85 for HalfCheetah shapes
+// (D = 20, A = 6), two hidden ReLU layers, S <= 510, uniform shooting (P0).
+#pragma once
+#include <cuda_bf16.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace bcmpc {
+namespace tmx {
+
+constexpr int kRows = 128;
+constexpr int kThreads = 384;
+constexpr int kChunk = 64;             // hidden units per accumulator chunk (UMMA N)
+constexpr int kOutN = 32;              // output layer padded to UMMA N = 32
+constexpr int kColA1 = 0, kColD = 256, kColA2 = 448, kColD3 = 480, kTmemCols = 512;
+constexpr int kNumDBuf = 3;
+constexpr int kD = 20, kA = 6;
+constexpr int kMaxStages = 16, kMaxOps = 40, kMaxChunks = 16;
+constexpr int kSmemLimit = 232448;     // 227 KB
+constexpr int kA0Bytes = 128 * 128;
+
+// Event barriers.  Every one of them completes exactly ONCE per step, so every wait in the kernel is "parity = step & 1"
+// and a waiter can never confuse two phases, however far the MMA issuers and the epilogue groups drift apart inside a
+// step (they re-join at every step boundary through D3 / A0).  e = chunk index in epilogue order: layer-1 chunk c -> c,
+// layer-2 chunk c -> NC + c.
+enum : int {
+  kEvA0Ready = 0,      // A0 rows of the step are in shared memory                     (epilogue -> L1 issuer)
+  kEvD3Full = 1,       // output accumulator complete                                  (L3 issuer -> epilogue)
+  kEvA1Ready = 2,      // [8]  hidden-1 k-block c is in TMEM                           (epilogue -> L2 issuers)
+  kEvDFull = 10,       // [16] accumulator of chunk e complete                         (issuer -> epilogue)
+  kEvDEmpty = 26,      // [16] accumulator of chunk e drained into registers           (epilogue -> issuer of the next user)
+  kEvA2Ready = 42,     // [8]  hidden-2 chunk c is in TMEM                             (epilogue -> L3 issuer)
+  kEvA2Empty = 50,     // [8]  layer 3 has consumed hidden-2 chunk c                   (L3 issuer -> epilogue)
+  kNumEv = 58
+};
+// misc smem: [w_full 16][w_empty 16][res_full][events 58] x 8 B, tmem ptr, argmin scratch
+constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, kOffTmemPtr = 736, kOffRed = 752, kMiscBytes = 1024;
+
+// ---------------------------------------------------------------------------------------------------------
+// The per-step schedule of the layer-1/2 issuer, computed by ONE constexpr function that both sides use: the host
+// walks it to lay the streamed weight image out in consumption order, the kernel (template <NC, KBS>) unrolls it at
+// compile time.  (A table walked at run time costs ~100 cycles per register-indexed constant load - measured:
+// 1300 cycles per MMA group, 5x its tensor time.)
+// ---------------------------------------------------------------------------------------------------------
+enum : int { kKindL1 = 0, kKindL2 = 1 };
+struct SOp {
+  int kind, c;         // layer, hidden chunk
+  int e;               // chunk index in epilogue order (L1: c, L2: nc + c)
+  int buf;             // accumulator buffer
+  int prev;            // chunk (epilogue index) that used `buf` before within this step, -1 = none
+  int kb0, nblk;       // L2: 64-wide k-blocks [kb0, kb0 + nblk) of the chunk
+  int sblk;            // L2: index of k-block kb0 inside its weight stage
+  bool first, last;    // first / last MMA group of the chunk
+  bool sfirst, slast;  // L2: first / last MMA group that reads its weight stage
+};
+struct Schedule {
+  SOp ops[kMaxOps] = {};
+  int n = 0;
+  int nc = 0, kbs = 0, nstg = 0;
+  int buf[kMaxChunks] = {};      // accumulator buffer of chunk e
+};
+// Accumulator buffers are handed out round-robin: the layer-1 chunks run three deep (MMA of chunk n+3 waits for the
+// epilogue of chunk n to drain the buffer), then the layer-2 chunks, one MMA group per weight stage (kbs k-blocks).
+// The hand-out restarts every step (all buffers are drained at a step boundary).
+constexpr Schedule make_schedule(int nc, int kbs) {
+  Schedule S;
+  S.nc = nc; S.kbs = kbs; S.nstg = (nc + kbs - 1) / kbs;
+  int next_buf = 0;
+  int last_user[kNumDBuf] = {-1, -1, -1};
+  for (int c = 0; c < nc; ++c) {
+    const int b = next_buf; next_buf = (next_buf + 1) % kNumDBuf;
+    SOp o{}; o.kind = kKindL1; o.c = c; o.e = c; o.buf = b; o.prev = last_user[b]; o.nblk = 1; o.first = o.last = true;
+    S.buf[o.e] = b; last_user[b] = o.e;
+    S.ops[S.n++] = o;
+  }
+  for (int c = 0; c < nc; ++c) {
+    const int b = next_buf; next_buf = (next_buf + 1) % kNumDBuf;
+    const int prev = last_user[b];
+    last_user[b] = nc + c; S.buf[nc + c] = b;
+    for (int j = 0; j < S.nstg; ++j) {
+      SOp o{}; o.kind = kKindL2; o.c = c; o.e = nc + c; o.buf = b; o.prev = prev;
+      o.kb0 = j * kbs; o.nblk = (nc - o.kb0 < kbs) ? nc - o.kb0 : kbs; o.sblk = 0;
+      o.first = j == 0; o.last = j == S.nstg - 1;
+      o.sfirst = o.slast = true;
+      S.ops[S.n++] = o;
+    }
+  }
+  return S;
+}
+template <int NC, int KBS>
+struct Sched {
+  static constexpr Schedule value = make_schedule(NC, KBS);
+};
+
+// k-blocks per streamed weight stage: a whole chunk of W2 per stage for a CTA pair (32 KB per CTA at NC = 8), a
+// quarter chunk for a single CTA (16 KB; the ring must hold several stages next to the resident W1 / W3)
+constexpr int stage_kblocks(int cg, int nc) { return cg == 2 ? nc : (nc + 3) / 4; }
+
+// shared-memory map, a function of (CTA-group size, hidden chunks) only: the kernel uses it as compile-time constants
+struct Layout {
+  int kbs = 0, nstg = 0, nst = 0;
+  int nst_r[2] = {0, 0}, first_r[2] = {0, 0};     // the ring is split in two: even layer-2 chunks / odd layer-2 chunks, one per MMA issuer
+  uint32_t blk_h = 0, blk_o = 0, w1_bytes = 0, res_bytes = 0, stage_bytes = 0;
+  uint32_t off_a0 = 0, off_res = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
+};
+constexpr Layout make_layout(int cg, int nc) {
+  Layout L;
+  L.kbs = stage_kblocks(cg, nc);
+  L.nstg = (nc + L.kbs - 1) / L.kbs;
+  L.blk_h = (kChunk / cg) * 128u;                  // bytes of one 64-wide k-block image of a hidden tile, per CTA
+  L.blk_o = (kOutN / cg) * 128u;                   // ... of an output tile
+  L.w1_bytes = nc * L.blk_h;
+  L.res_bytes = L.w1_bytes + nc * L.blk_o;         // resident: W1 chunks then W3 k-blocks
+  L.off_a0 = 0;
+  L.off_res = kA0Bytes;
+  L.off_ring = (L.off_res + L.res_bytes + 1023u) / 1024u * 1024u;
+  L.stage_bytes = L.kbs * L.blk_h;
+  L.nst = (int)((kSmemLimit - kMiscBytes - L.off_ring) / L.stage_bytes);
+  if (L.nst > kMaxStages) L.nst = kMaxStages;
+  L.nst_r[0] = (L.nst + 1) / 2; L.nst_r[1] = L.nst / 2;   // each sub-ring has ONE consumer, which sees every phase of its barriers
+  L.first_r[0] = 0; L.first_r[1] = L.nst_r[0];
+  L.off_misc = L.off_ring + L.nst * L.stage_bytes;
+  L.smem_bytes = L.off_misc + kMiscBytes;
+  return L;
+}
+
+template <int CG, int NC>
+struct Lay {
+  static constexpr Layout value = make_layout(CG, NC);
+};
+
+struct TmArgs {
+  PlanArgs p;
+  const uint8_t* res;            // resident image   [CG][res_bytes]
+  const uint8_t* stream;         // streamed image: per weight stage, in consumption order, [CG][stage_bytes]
+  unsigned long long* trace;     // optional pipeline trace (tools/tc_trace.py), nullptr = off
+  float mean_obs[kMaxObs], inv_den_obs[kMaxObs], mean_delta[kMaxObs], std_delta[kMaxObs];
+  float mean_act[kMaxAct], inv_den_act[kMaxAct], low[kMaxAct], span[kMaxAct];
+};
+// pipeline trace of CTA (0,0), steps 0..3: [2 per L1/L2 group][2 per L3 group][2 per epilogue chunk][final 2][2 per stage]
+constexpr int kTraceSteps = 4, kTrMma = 0, kTrL3 = 2 * kMaxOps, kTrEpi = kTrL3 + 16, kTrFinal = kTrEpi + 32, kTrProd = kTrFinal + 4,
+              kTraceSlots = kTrProd + 2 * 64;
+
+// ---------------------------------------------------------------------------------------------------------
+// host: weight images
+// ---------------------------------------------------------------------------------------------------------
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// byte offset of element (row n, k-column kk < 64) in a K-major SWIZZLE_128B image (8-row groups of 1024 B)
+inline size_t sw128_offset(int n, int kk) {
+  return (size_t)(n / 8) * 1024 + (size_t)(n % 8) * 128 + (size_t)(((kk / 8) ^ (n % 8)) * 16) + (size_t)(kk % 8) * 2;
+}
+
+struct TmHostPlan {
+  std::vector<uint16_t> res, stream;
+  int cg = 1, s_pad = 0, nc = 0;
+  Layout lay;
+};
+
+inline bool tm_supported(const bcmpc_config& c, std::string* why) {
+  if (c.obs_dim != kD || c.act_dim != kA) { *why = "bf16 fast path is specialised for obs_dim=20, act_dim=6 (HalfCheetah)"; return false; }
+  if (c.n_hidden != 2) { *why = "bf16 fast path supports n_hidden == 2 this round"; return false; }
+  if (c.hidden_size < 1 || c.hidden_size > 510) { *why = "bf16 fast path supports hidden_size <= 510 this round (TMEM holds the 512-wide padded activations)"; return false; }
+  if (c.activation != BCMPC_ACT_RELU) { *why = "bf16 fast path supports relu only"; return false; }
+  if (c.proposal != BCMPC_PROP_UNIFORM) { *why = "bf16 fast path supports uniform shooting (P0) this round; use BCMPC_PREC_FP32_VERIFY for policy proposals"; return false; }
+  return true;
+}
+
+// W[l] are TF kernels [in,out] row-major: W1 [26,S], W2 [S,S], W3 [S,20].
+// Bias-in-GEMM: input columns 26,27 of A0 are 1.0; hidden units S and S+1 of both hidden layers are wired to be
+// exactly 1.0 after ReLU; row S / S+1 of the next layer's kernel hold bf16(b) and bf16(b - bf16(b)).
+inline void tm_build(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
+                     int S, int cg, TmHostPlan* out) {
+  TmHostPlan& P = *out;
+  P = TmHostPlan{};
+  const int in_dim = kD + kA;
+  P.cg = cg;
+  P.s_pad = (S + 2 + 63) / 64 * 64;
+  P.nc = P.s_pad / 64;
+  P.lay = make_layout(cg, P.nc);
+  const int NC = P.nc, NKB = P.nc, kbs = P.lay.kbs;
+  const int rows_h = kChunk / cg, rows_o = kOutN / cg;                 // B rows per CTA (hidden / output tiles)
+  const uint32_t blk_h = P.lay.blk_h, blk_o = P.lay.blk_o, w1_bytes = P.lay.w1_bytes;
+  const uint32_t res_bytes = P.lay.res_bytes, stage_bytes = P.lay.stage_bytes;
+
+  auto hi = [](float v) { return f32_to_bf16(v); };
+  auto lo = [](float v) { return f32_to_bf16(v - bf16_to_f32(f32_to_bf16(v))); };
+  const uint16_t one = f32_to_bf16(1.0f);
+  // effective (bias-augmented, zero-padded) kernels as functions
+  auto w1 = [&](int k, int n) -> uint16_t {        // k < 64 (input column), n < s_pad (hidden unit)
+    if (n < S) return k < in_dim ? f32_to_bf16(W1[(size_t)k * S + n]) : k == in_dim ? hi(b1[n]) : k == in_dim + 1 ? lo(b1[n]) : 0;
+    if (n == S || n == S + 1) return k == in_dim ? one : 0;          // the hidden "ones" units: relu(1 * 1) = 1
+    return 0;
+  };
+  auto w2 = [&](int k, int n) -> uint16_t {
+    if (n < S) return k < S ? f32_to_bf16(W2[(size_t)k * S + n]) : k == S ? hi(b2[n]) : k == S + 1 ? lo(b2[n]) : 0;
+    if (n == S || n == S + 1) return k == S ? one : 0;
+    return 0;
+  };
+  auto w3 = [&](int k, int n) -> uint16_t {        // n < 32 (output column)
+    if (n >= kD) return 0;
+    return k < S ? f32_to_bf16(W3[(size_t)k * kD + n]) : k == S ? hi(b3[n]) : k == S + 1 ? lo(b3[n]) : 0;
+  };
+
+  // ---- resident image: per rank [W1 chunk 0..NC-1][W3 k-block 0..NKB-1] ----
+  P.res.assign((size_t)cg * res_bytes / 2, 0);
+  for (int r = 0; r < cg; ++r) {
+    const size_t rb = (size_t)r * res_bytes;
+    for (int c = 0; c < NC; ++c)
+      for (int i = 0; i < rows_h; ++i)
+        for (int k = 0; k < 64; ++k)
+          P.res[(rb + (size_t)c * blk_h + sw128_offset(i, k)) / 2] = w1(k, c * kChunk + r * rows_h + i);
+    for (int kb = 0; kb < NKB; ++kb)
+      for (int i = 0; i < rows_o; ++i)
+        for (int kk = 0; kk < 64; ++kk)
+          P.res[(rb + w1_bytes + (size_t)kb * blk_o + sw128_offset(i, kk)) / 2] = w3(kb * 64 + kk, r * rows_o + i);
+  }
+  // ---- streamed image: one slot [CG][stage_bytes] per (chunk, stage), chunk-major = consumption order ----
+  const int nstg = (NC + kbs - 1) / kbs;
+  P.stream.assign((size_t)NC * nstg * cg * stage_bytes / 2, 0);
+  for (int c = 0; c < NC; ++c)
+    for (int j = 0; j < nstg; ++j) {
+      const size_t off = (size_t)(c * nstg + j) * cg * stage_bytes;
+      for (int r = 0; r < cg; ++r)
+        for (int t = 0; t < kbs && j * kbs + t < NKB; ++t)
+          for (int ii = 0; ii < rows_h; ++ii)
+            for (int kk = 0; kk < 64; ++kk)
+              P.stream[(off + (size_t)r * stage_bytes + (size_t)t * blk_h + sw128_offset(ii, kk)) / 2] =
+                  w2((j * kbs + t) * 64 + kk, c * kChunk + r * rows_h + ii);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------------------------------------
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// ReLU + round-to-nearest bf16 of two accumulators in one instruction (negative -> +0, NaN stays NaN)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// normalise (dynamics.py:109-110) -> bf16 -> the first four 16-byte chunks of this row of A0; columns 26, 27 = 1
+__device__ __forceinline__ void build_input(const TmArgs& a, uint32_t a0_row_addr, int row, const float (&s)[kD],
+                                            const float (&act)[kA]) {
+  float x[32];
+#pragma unroll
+  for (int c = 0; c < kD; ++c) x[c] = (s[c] - a.mean_obs[c]) * a.inv_den_obs[c];   // subtract first: a zero-variance dim has inv_den = 1e10
+#pragma unroll
+  for (int j = 0; j < kA; ++j) x[kD + j] = (act[j] - a.mean_act[j]) * a.inv_den_act[j];
+  x[kD + kA] = 1.f;
+  x[kD + kA + 1] = 1.f;
+#pragma unroll
+  for (int c = kD + kA + 2; c < 32; ++c) x[c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t addr = a0_row_addr + (uint32_t)(((c ^ (row & 7)) << 4));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(x[8 * c + 0], x[8 * c + 1])),
+                 "r"(pack_bf16(x[8 * c + 2], x[8 * c + 3])), "r"(pack_bf16(x[8 * c + 4], x[8 * c + 5])),
+                 "r"(pack_bf16(x[8 * c + 6], x[8 * c + 7]))
+                 : "memory");
+  }
+}
+
+// the action of (path, step): injected tensor or Philox draw (controllers.py:53)
+__device__ __forceinline__ void get_action(const TmArgs& a, int b, int h, int k, float (&act)[kA]) {
+  const PlanArgs& p = a.p;
+  if (p.inj) {
+    const double* src = p.inj + (((size_t)b * p.H + h) * p.K + k) * kA;
+#pragma unroll
+    for (int j = 0; j < kA; ++j) act[j] = (float)src[j];
+  } else {
+    float v[kMaxAct];
+    draw_injection(v, kA, kInjUniformBox, p.seed, (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
+#pragma unroll
+    for (int j = 0; j < kA; ++j) act[j] = v[j];
+  }
+}
+
+// Barrier waits are executed by all 32 lanes of the role warp (measured: ~100 cycles when the phase is already
+// complete; a single elected lane polling while the others park at the reconvergence barrier costs > 1000).
+template <int CG, int NC>
+__global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
+  constexpr Layout L = Lay<CG, NC>::value;
+  using SC = Sched<NC, L.kbs>;
+  constexpr int kNumOps = SC::value.n;
+  constexpr int kNstg = L.nstg;                               // weight stages per layer-2 chunk
+  constexpr int kNumStream = NC * kNstg;                      // weight stages per step
+  constexpr int kStagesPerStepR[2] = {((NC + 1) / 2) * kNstg, (NC / 2) * kNstg};   // ... per sub-ring (even / odd chunks)
+  constexpr uint32_t kIdescH = ptx::umma_idesc_bf16(kRows * CG, kChunk), kIdescO = ptx::umma_idesc_bf16(kRows * CG, kOutN);
+  static_assert(L.nst_r[0] >= 1 && L.nst_r[1] >= 1, "weight ring too small");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const PlanArgs& p = a.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, b = blockIdx.y;
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const uint32_t base = ptx::smem_u32(smem);
+  const uint32_t misc = base + L.off_misc;
+  const uint32_t ev = misc + kOffEv;                                  // event barriers of THIS CTA
+  const uint32_t ev_leader = CG == 2 ? ptx::mapa(ev, 0) : ev;        // ... of the leader CTA (shared::cluster address)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.off_misc + kOffTmemPtr);
+  unsigned char* s_red = smem + L.off_misc + kOffRed;
+  const int H = p.H;
+
+  if (tid == 0) {
+    if (base & 1023u) { printf("bcmpc: dynamic smem base not 1024-byte aligned\n"); __trap(); }
+    for (int i = 0; i < kMaxStages; ++i) {
+      // leader: its own producer's expect_tx arrive + the peer's "my half has landed" arrive
+      ptx::mbar_init(misc + kOffWFull + 8u * i, (CG == 2 && leader) ? 2 : 1);
+      ptx::mbar_init(misc + kOffWEmpty + 8u * i, 1);
+    }
+    ptx::mbar_init(misc + kOffResFull, (CG == 2 && leader) ? 2 : 1);
+    ptx::mbar_init(ev + 8u * kEvA0Ready, 4 * CG);
+    ptx::mbar_init(ev + 8u * kEvD3Full, 1);
+    for (int i = 0; i < 8; ++i) {
+      ptx::mbar_init(ev + 8u * (kEvA1Ready + i), 4 * CG);
+      ptx::mbar_init(ev + 8u * (kEvA2Ready + i), 4 * CG);
+      ptx::mbar_init(ev + 8u * (kEvA2Empty + i), 1);
+    }
+    for (int i = 0; i < kMaxChunks; ++i) { ptx::mbar_init(ev + 8u * (kEvDFull + i), 1); ptx::mbar_init(ev + 8u * (kEvDEmpty + i), 4 * CG); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_cg<CG>(ptx::smem_u32(s_tmem), kTmemCols);
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  ptx::tc_fence_after();
+  // The allocation is the whole TMEM (512 columns), so it starts at lane 0 / column 0; using the literal keeps every
+  // TMEM address a compile-time value.
+  if (*s_tmem != 0u) { if (tid == 0) printf("bcmpc: unexpected TMEM base 0x%x\n", *s_tmem); __trap(); }
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+
+  // Warps 0-3 run their loops warp-uniformly and elect one lane only for the instructions themselves: every
+  // descriptor / address is then a uniform-register value (an `if (lane == 0)` role costs a divergent-value waterfall
+  // loop around every UTCHMMA).
+  if (warp == 0) {
+    // ===================== weight producer (every CTA loads its own half) =====================
+    if (ptx::elect_one()) {
+      const uint8_t* src = a.res + (size_t)rank * L.res_bytes;
+      ptx::mbar_arrive_expect_tx(misc + kOffResFull, L.res_bytes);
+      for (uint32_t o = 0; o < L.res_bytes; o += 16384u)
+        ptx::bulk_g2s(base + L.off_res + o, src + o, min(16384u, L.res_bytes - o), misc + kOffResFull);
+    }
+    __syncwarp();
+    uint32_t stage[2] = {0, 0}, phase[2] = {0, 0};
+    for (int h = 0; h < H; ++h) {
+      const uint8_t* src = a.stream + (size_t)rank * L.stage_bytes;
+      const bool trp = tracing && h < kTraceSteps;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int r = c & 1;                     // sub-ring: even chunks feed issuer warp 1, odd chunks issuer warp 3
+        for (int j = 0; j < kNstg; ++j) {
+          const int i = c * kNstg + j;
+          const uint32_t st = (uint32_t)L.first_r[r] + stage[r];
+          if (trp && lane == 0) a.trace[h * kTraceSlots + kTrProd + 2 * i] = clock64();
+          ptx::mbar_wait(misc + kOffWEmpty + 8u * st, phase[r] ^ 1u);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(misc + kOffWFull + 8u * st, L.stage_bytes);
+#pragma unroll
+            for (uint32_t o = 0; o < L.stage_bytes; o += 16384u)
+              ptx::bulk_g2s(base + L.off_ring + st * L.stage_bytes + o, src + o, min(16384u, L.stage_bytes - o), misc + kOffWFull + 8u * st);
+            if (trp) a.trace[h * kTraceSlots + kTrProd + 2 * i + 1] = clock64();
+          }
+          __syncwarp();
+          src += (size_t)CG * L.stage_bytes;
+          if (++stage[r] == (uint32_t)L.nst_r[r]) { stage[r] = 0; phase[r] ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    if (leader) {
+      // ===================== layer-1 / layer-2 MMA issuers: the step's schedule unrolled at compile time =====================
+      // warp 1 takes the even layer-2 chunks (chunk 0 in k-block groups that follow the layer-1 epilogues), warp 3 takes
+      // layer 1 and the odd layer-2 chunks.
+      const int mine = warp == 1 ? 0 : 1;
+      ptx::mbar_wait(misc + kOffResFull, 0);
+      const uint64_t a0desc = ptx::umma_desc_sw128(base + L.off_a0);
+      const uint64_t w1desc = ptx::umma_desc_sw128(base + L.off_res);
+      for (int h = 0; h < H; ++h) {
+        const uint32_t uh = (uint32_t)h, par = uh & 1u;
+        const bool trw = tracing && h < kTraceSteps;
+        static_for<kNumOps>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          constexpr SOp op = SC::value.ops[i];
+          constexpr int owner = (op.kind == kKindL2) ? (op.c & 1) : 1;
+          if (owner != mine) return;
+          // ---- operands ready?  (every event completes once per step: parity = step & 1) ----
+          if constexpr (op.first && op.prev >= 0) ptx::mbar_wait(ev + 8u * (kEvDEmpty + op.prev), par);   // previous user of the accumulator drained
+          if constexpr (op.kind == kKindL1 && op.c == 0) {
+            ptx::mbar_wait(ev + 8u * kEvA0Ready, par);
+          }
+          if constexpr (op.kind == kKindL2 && op.c < 2 && op.first) {
+            // first layer-2 chunk of this issuer in the step: all of A1 must be in TMEM.  Each epilogue group signals its
+            // chunks in order (group 0 the even ones, group 1 the odd ones), so the last two barriers imply the rest.
+            ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 1), par);
+            if constexpr (NC >= 2) ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 2), par);
+          }
+          // weight stage of this group: sub-ring r = chunk parity, stages consumed in (chunk, stage-of-chunk) order
+          constexpr int r = op.c & 1;
+          constexpr int sidx = (op.c / 2) * kNstg + op.kb0 / L.kbs;
+          const uint32_t gs = uh * kStagesPerStepR[r] + sidx;
+          const uint32_t stage = (uint32_t)L.first_r[r] + gs % (uint32_t)L.nst_r[r], phase = (gs / (uint32_t)L.nst_r[r]) & 1u;
+          if constexpr (op.kind == kKindL2 && op.sfirst) ptx::mbar_wait(misc + kOffWFull + 8u * stage, phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            if (trw) a.trace[h * kTraceSlots + kTrMma + 2 * i] = clock64();
+            constexpr uint32_t d = kColD + kChunk * op.buf;
+            if constexpr (op.kind == kKindL1) {
+              constexpr int nks = (kD + kA + 2 + 15) / 16;
+#pragma unroll
+              for (int ks = 0; ks < nks; ++ks)
+                ptx::umma_ss<CG>(d, a0desc + 2u * ks, w1desc + (uint64_t)(op.c * (L.blk_h >> 4) + 2u * ks), kIdescH, ks > 0 ? 1u : 0u);
+              ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + op.e));
+            } else {
+              const uint64_t bdesc = ptx::umma_desc_sw128(base + L.off_ring + stage * L.stage_bytes);
+#pragma unroll
+              for (int t = 0; t < op.nblk; ++t) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  ptx::umma_ts<CG>(d, kColA1 + (op.kb0 + t) * 32 + ks * 8, bdesc + (uint64_t)((op.sblk + t) * (L.blk_h >> 4) + 2u * ks),
+                                   kIdescH, (op.first && t == 0 && ks == 0) ? 0u : 1u);
+              }
+              if constexpr (op.slast) ptx::umma_commit_cg<CG>(misc + kOffWEmpty + 8u * stage);
+              if constexpr (op.last) ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + op.e));
+            }
+            if (trw) a.trace[h * kTraceSlots + kTrMma + 2 * i + 1] = clock64();
+          }
+          __syncwarp();
+        });
+      }
+    } else if (warp == 1) {
+      // ===================== peer CTA: tell the leader when this CTA's weight halves have landed =====================
+      const uint32_t misc_leader = ptx::mapa(misc, 0);
+      ptx::mbar_wait(misc + kOffResFull, 0);
+      if (ptx::elect_one()) ptx::mbar_arrive_remote(misc_leader + kOffResFull);
+      __syncwarp();
+      uint32_t stage[2] = {0, 0}, phase[2] = {0, 0};
+      for (int h = 0; h < H; ++h) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int r = c & 1;
+          for (int j = 0; j < kNstg; ++j) {
+            const uint32_t st = (uint32_t)L.first_r[r] + stage[r];
+            ptx::mbar_wait(misc + kOffWFull + 8u * st, phase[r]);
+            if (ptx::elect_one()) ptx::mbar_arrive_remote(misc_leader + kOffWFull + 8u * st);
+            __syncwarp();
+            if (++stage[r] == (uint32_t)L.nst_r[r]) { stage[r] = 0; phase[r] ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (leader) {
+      // ===================== layer-3 MMA issuer: D3 (+)= A2 x W3[chunk] as the hidden-2 chunks appear =====================
+      ptx::mbar_wait(misc + kOffResFull, 0);
+      const uint64_t w3desc = ptx::umma_desc_sw128(base + L.off_res + L.w1_bytes);
+      for (int h = 0; h < H; ++h) {
+        const uint32_t uh = (uint32_t)h;
+        const bool trw = tracing && h < kTraceSteps;
+        static_for<NC>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
+          ptx::mbar_wait(ev + 8u * (kEvA2Ready + c), uh & 1u);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c] = clock64();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::umma_ts<CG>(kColD3, kColA2 + ks * 8, w3desc + (uint64_t)(c * (L.blk_o >> 4) + 2u * ks), kIdescO, (c == 0 && ks == 0) ? 0u : 1u);
+            if constexpr (c == NC - 1) ptx::umma_commit_cg<CG>(ev + 8u * kEvD3Full);
+            else ptx::umma_commit_cg<CG>(ev + 8u * (kEvA2Empty + c));
+            if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c + 1] = clock64();
+          }
+          __syncwarp();
+        });
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: group g (4 warps, one per lane quadrant) takes the chunks with (index & 1) == g =====================
+    const int q = warp & 3, g = (warp - 4) >> 2, row = q * 32 + lane;
+    const bool is_final = g == 0;
+    const bool tr = tracing && q == 0 && lane == 0;
+    const int k = tile * kRows + row;
+    const bool valid = k < p.K;
+    const int kc = valid ? k : p.K - 1;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t a0_row = base + L.off_a0 + (uint32_t)row * 128u;
+    // hand-offs that concern TMEM contents / tensor-core reads: default (CTA-scope release) arrive, like CUTLASS' 2-SM kernels
+    auto arrive_leader = [&](uint32_t id) {
+      if constexpr (CG == 1) ptx::mbar_arrive(ev + 8u * id);
+      else ptx::mbar_arrive_remote(ev_leader + 8u * id);
+    };
+    // A0 rows are generic-proxy shared-memory writes read by THIS CTA's tensor core (A is split by rows across the
+    // pair); the proxy fence makes them visible to the async proxy, the arrive tells the leader's issuer to go
+    auto publish_a0 = [&]() {
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) arrive_leader(kEvA0Ready);
+    };
+    float s[kD], act[kA], act0[kA], cost = 0.f;
+    if (is_final) {
+#pragma unroll
+      for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)(p.per_row_states ? kc : b) * kD + d];
+      get_action(a, b, 0, kc, act);
+#pragma unroll
+      for (int j = 0; j < kA; ++j) act0[j] = act[j];
+      if (p.states_out && valid)
+        for (int d = 0; d < kD; ++d) p.states_out[(size_t)k * kD + d] = (double)s[d];
+      if (p.actions_out && valid)
+        for (int j = 0; j < kA; ++j) p.actions_out[(size_t)k * kA + j] = (double)act[j];
+      build_input(a, a0_row, row, s, act);
+      publish_a0();
+    }
+    for (int h = 0; h < H; ++h) {
+      const uint32_t uh = (uint32_t)h;
+      const bool trh = tr && h < kTraceSteps;
+      // the next step's action is drawn now, while layer 1 of this step is in the tensor pipe (not at the step's tail)
+      if (is_final && h + 1 < H) get_action(a, b, h + 1, kc, act);
+      static_for<2 * NC>([&](auto ec) {
+        constexpr int e = decltype(ec)::value;
+        constexpr bool l2 = e >= NC;
+        constexpr int c = l2 ? e - NC : e;
+        constexpr int buf = SC::value.buf[e];
+        constexpr uint32_t dst = l2 ? kColA2 : kColA1 + 32 * c;
+        if ((e & 1) == g) {
+          ptx::mbar_wait(ev + 8u * (kEvDFull + e), uh & 1u);
+          ptx::tc_fence_after();
+          if (trh) a.trace[h * kTraceSlots + kTrEpi + 2 * e] = clock64();
+          uint32_t v0[32], v1[32], w0[16], w1[16];
+          ptx::tmem_ld32(lane_off + (uint32_t)(kColD + kChunk * buf), v0);
+          ptx::tmem_ld32(lane_off + (uint32_t)(kColD + kChunk * buf + 32), v1);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader(kEvDEmpty + e);             // accumulator is in registers: release the TMEM buffer
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w0[i] = pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w1[i] = pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          if constexpr (l2 && c > 0) {
+            ptx::mbar_wait(ev + 8u * (kEvA2Empty + c - 1), uh & 1u);   // layer 3 has consumed the previous chunk
+            ptx::tc_fence_after();
+          }
+          ptx::tmem_st16(lane_off + dst, w0);
+          ptx::tmem_st16(lane_off + dst + 16u, w1);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader((l2 ? kEvA2Ready : kEvA1Ready) + c);
+          if (trh) a.trace[h * kTraceSlots + kTrEpi + 2 * e + 1] = clock64();
+        }
+      });
+      if (is_final) {
+        ptx::mbar_wait(ev + 8u * kEvD3Full, uh & 1u);
+        ptx::tc_fence_after();
+        if (trh) a.trace[h * kTraceSlots + kTrFinal] = clock64();
+        uint32_t v[32];
+        ptx::tmem_ld32(lane_off + (uint32_t)kColD3, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        float delta[kD];
+#pragma unroll
+        for (int d = 0; d < kD; ++d) delta[d] = fmaf(__uint_as_float(v[d]), a.std_delta[d], a.mean_delta[d]);   // dynamics.py:113
+        if (s[5] >= 0.2f) cost += 10.f;                                      // cost_functions.py:16-26 (pre-step state)
+        if (s[6] >= 0.f) cost += 10.f;
+        if (s[7] >= 0.f) cost += 10.f;
+        cost -= delta[17] * 100.f;                                           // cost_functions.py:28 (/ 0.01)
+#pragma unroll
+        for (int d = 0; d < kD; ++d) s[d] += delta[d];                       // dynamics.py:116
+        if (h + 1 < H) {
+          build_input(a, a0_row, row, s, act);
+          publish_a0();
+          if (trh) a.trace[h * kTraceSlots + kTrFinal + 1] = clock64();
+          if (p.actions_out && valid)
+            for (int j = 0; j < kA; ++j) p.actions_out[((size_t)(h + 1) * p.K + k) * kA + j] = (double)act[j];
+        }
+        if (p.states_out && valid)
+          for (int d = 0; d < kD; ++d) p.states_out[((size_t)(h + 1) * p.K + k) * kD + d] = (double)s[d];
+      }
+    }
+    if (is_final) {
+      // ---- per-tile argmin over the 128 rows (np.argmin order) ----
+      if (p.costs_out && valid) p.costs_out[(size_t)b * p.K + k] = (double)cost;
+      double c = (double)cost;
+      int64_t idx = valid ? p.path_offset + k : INT64_MAX;
+      int src = row;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double oc = __shfl_xor_sync(0xffffffffu, c, off);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        const int os = __shfl_xor_sync(0xffffffffu, src, off);
+        if (oi != INT64_MAX && (idx == INT64_MAX || cand_better(oc, oi, c, idx))) { c = oc; idx = oi; src = os; }
+      }
+      double* r_cost = reinterpret_cast<double*>(s_red);
+      int64_t* r_idx = reinterpret_cast<int64_t*>(s_red + 32);
+      int* r_src = reinterpret_cast<int*>(s_red + 64);
+      if (lane == 0) { r_cost[q] = c; r_idx[q] = idx; r_src[q] = src; }
+      ptx::named_bar_sync(1, 128);
+      c = r_cost[0]; idx = r_idx[0]; src = r_src[0];
+#pragma unroll
+      for (int i = 1; i < 4; ++i)
+        if (r_idx[i] != INT64_MAX && (idx == INT64_MAX || cand_better(r_cost[i], r_idx[i], c, idx))) { c = r_cost[i]; idx = r_idx[i]; src = r_src[i]; }
+      if (row == src && p.cand) {
+        Candidate& o = p.cand[(size_t)b * p.tiles_per_state + tile];
+        o.cost = c;
+        o.index = idx == INT64_MAX ? -1 : idx;
+#pragma unroll
+        for (int j = 0; j < kA; ++j) o.action[j] = (double)act0[j];
+        for (int j = kA; j < kMaxAct; ++j) o.action[j] = 0.0;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc_cg<CG>(0u, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch: picks the instantiation for (CTA-group size, hidden chunks)
+// ---------------------------------------------------------------------------------------------------------
+template <int CG, int NC>
+inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
+  auto kern = rollout_tmem_kernel<CG, NC>;
+  constexpr Layout L = Lay<CG, NC>::value;
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+template <int CG>
+inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  switch (nc) {
+    case 1: return tm_launch_t<CG, 1>(a, grid, st);
+    case 2: return tm_launch_t<CG, 2>(a, grid, st);
+    case 3: return tm_launch_t<CG, 3>(a, grid, st);
+    case 4: return tm_launch_t<CG, 4>(a, grid, st);
+    case 5: return tm_launch_t<CG, 5>(a, grid, st);
+    case 6: return tm_launch_t<CG, 6>(a, grid, st);
+    case 7: return tm_launch_t<CG, 7>(a, grid, st);
+    case 8: return tm_launch_t<CG, 8>(a, grid, st);
+  }
+  return cudaErrorInvalidValue;
+}
+inline cudaError_t tm_launch(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  return cg == 2 ? tm_launch_cg<2>(nc, a, grid, st) : tm_launch_cg<1>(nc, a, grid, st);
+}
+
+}  // namespace tmx
+}  // namespace bcmpc

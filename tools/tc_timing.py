@@ -26,5 +26,5 @@ for tiles in (1, 8, 37, 74, 148, 296, 1024):
     m = float(np.median(ms[2:]))
     waves = -(-tiles // 148)
     print(f"S={S} tiles={tiles:5d} H={H} kernel {m * 1e3:9.1f} us  per tile-step {m * 1e3 / (waves * H):7.2f} us  "
-          f"{K * H / m / 1e6:8.1f} Mtr/s  {K * H * flop / m / 1e9:7.1f} TFLOP/s (sched {os.environ.get('BCMPC_TC_SCHEDULE', '1')})")
+          f"{K * H / m / 1e6:8.1f} Mtr/s  {K * H * flop / m / 1e9:7.1f} TFLOP/s (cg {os.environ.get('BCMPC_TC_CG', '2')})")
     pl.close()
