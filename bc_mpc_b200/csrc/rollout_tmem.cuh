@@ -31,7 +31,7 @@
 // tensor pipe fed; every accumulator is written by one issuer only, so results do not depend on the interleaving);
 // warp 2 = TMEM allocation + layer-3 issuer; in the peer CTA warp 1 forwards "weights landed" to the leader;
 // warps 4-11 = epilogue: two groups of four warps (one warp per TMEM lane quadrant) that take alternate accumulator
-// chunks, 64 columns per warp.
+// chunks (layer 1: alternate pairs of chunks), 64 columns per warp and chunk.
 // The step's schedule - which accumulator a chunk uses, what each MMA group waits for and signals - is computed by a
 // constexpr function and unrolled at compile time, so every TMEM column, barrier and descriptor offset is an immediate.
 //
@@ -55,7 +55,9 @@ constexpr int kThreads = 384;
 constexpr int kChunk = 64;             // hidden units per accumulator chunk (UMMA N)
 constexpr int kOutN = 32;              // output layer padded to UMMA N = 32
 constexpr int kColA1 = 0, kColD = 256, kColA2 = 448, kColD3 = 480, kTmemCols = 512;
-constexpr int kNumDBuf = 3;
+constexpr int kNumDBuf = 3;            // accumulators of the layer-2 chunks
+constexpr int kNumDBufL1 = 4;          // layer 1 also borrows [448,512): A2 and D3 are idle while layer 1 runs
+__host__ __device__ constexpr int buf_col(int b) { return b < kNumDBuf ? kColD + kChunk * b : kColA2; }
 constexpr int kD = 20, kA = 6;
 constexpr int kMaxStages = 16, kMaxOps = 40, kMaxChunks = 16;
 constexpr int kSmemLimit = 232448;     // 227 KB
@@ -101,26 +103,24 @@ struct Schedule {
   int nc = 0, kbs = 0, nstg = 0;
   int buf[kMaxChunks] = {};      // accumulator buffer of chunk e
 };
-// Accumulator buffers are handed out round-robin: the layer-1 chunks run three deep (MMA of chunk n+3 waits for the
-// epilogue of chunk n to drain the buffer), then the layer-2 chunks, one MMA group per weight stage (kbs k-blocks).
-// The hand-out restarts every step (all buffers are drained at a step boundary).
+// Layer 1 runs in PAIRS of chunks over four accumulators (two pairs in flight; the MMA group of pair n+2 waits for the
+// epilogues of pair n to drain their buffers - one combined wait); layer 2 follows, one MMA group per weight stage (kbs
+// k-blocks), round-robin over three accumulators.  Both layer-2 issuers wait for the last two "hidden-1 ready"
+// barriers before their first chunk, which also tells them that every layer-1 accumulator has been drained.
 constexpr Schedule make_schedule(int nc, int kbs) {
   Schedule S;
   S.nc = nc; S.kbs = kbs; S.nstg = (nc + kbs - 1) / kbs;
-  int next_buf = 0;
-  int last_user[kNumDBuf] = {-1, -1, -1};
-  for (int c = 0; c < nc; ++c) {
-    const int b = next_buf; next_buf = (next_buf + 1) % kNumDBuf;
-    SOp o{}; o.kind = kKindL1; o.c = c; o.e = c; o.buf = b; o.prev = last_user[b]; o.nblk = 1; o.first = o.last = true;
-    S.buf[o.e] = b; last_user[b] = o.e;
+  for (int c = 0; c < nc; c += 2) {
+    SOp o{}; o.kind = kKindL1; o.c = c; o.e = c; o.nblk = (c + 1 < nc) ? 2 : 1;      // nblk = chunks in this group
+    o.buf = c % kNumDBufL1; o.prev = c >= kNumDBufL1 ? c - kNumDBufL1 : -1; o.first = o.last = true;
     S.ops[S.n++] = o;
   }
+  for (int c = 0; c < nc; ++c) S.buf[c] = c % kNumDBufL1;
   for (int c = 0; c < nc; ++c) {
-    const int b = next_buf; next_buf = (next_buf + 1) % kNumDBuf;
-    const int prev = last_user[b];
-    last_user[b] = nc + c; S.buf[nc + c] = b;
+    const int b = c % kNumDBuf;
+    S.buf[nc + c] = b;
     for (int j = 0; j < S.nstg; ++j) {
-      SOp o{}; o.kind = kKindL2; o.c = c; o.e = nc + c; o.buf = b; o.prev = prev;
+      SOp o{}; o.kind = kKindL2; o.c = c; o.e = nc + c; o.buf = b; o.prev = c >= kNumDBuf ? nc + c - kNumDBuf : -1;
       o.kb0 = j * kbs; o.nblk = (nc - o.kb0 < kbs) ? nc - o.kb0 : kbs; o.sblk = 0;
       o.first = j == 0; o.last = j == S.nstg - 1;
       o.sfirst = o.slast = true;
@@ -179,8 +179,8 @@ struct TmArgs {
   float mean_obs[kMaxObs], inv_den_obs[kMaxObs], mean_delta[kMaxObs], std_delta[kMaxObs];
   float mean_act[kMaxAct], inv_den_act[kMaxAct], low[kMaxAct], span[kMaxAct];
 };
-// pipeline trace of CTA (0,0), steps 0..3: [2 per L1/L2 group][2 per L3 group][2 per epilogue chunk][final 2][2 per stage]
-constexpr int kTraceSteps = 4, kTrMma = 0, kTrL3 = 2 * kMaxOps, kTrEpi = kTrL3 + 16, kTrFinal = kTrEpi + 32, kTrProd = kTrFinal + 4,
+// pipeline trace of CTA (0,0), steps 0..3: [2 per L1/L2 group][2 per L3 group][4 per epilogue chunk][final 2][2 per stage]
+constexpr int kTraceSteps = 4, kTrMma = 0, kTrL3 = 2 * kMaxOps, kTrEpi = kTrL3 + 16, kTrFinal = kTrEpi + 64, kTrProd = kTrFinal + 4,
               kTraceSlots = kTrProd + 2 * 64;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -453,15 +453,20 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           constexpr int owner = (op.kind == kKindL2) ? (op.c & 1) : 1;
           if (owner != mine) return;
           // ---- operands ready?  (every event completes once per step: parity = step & 1) ----
-          if constexpr (op.first && op.prev >= 0) ptx::mbar_wait(ev + 8u * (kEvDEmpty + op.prev), par);   // previous user of the accumulator drained
-          if constexpr (op.kind == kKindL1 && op.c == 0) {
-            ptx::mbar_wait(ev + 8u * kEvA0Ready, par);
-          }
-          if constexpr (op.kind == kKindL2 && op.c < 2 && op.first) {
-            // first layer-2 chunk of this issuer in the step: all of A1 must be in TMEM.  Each epilogue group signals its
-            // chunks in order (group 0 the even ones, group 1 the odd ones), so the last two barriers imply the rest.
-            ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 1), par);
-            if constexpr (NC >= 2) ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 2), par);
+          if constexpr (op.kind == kKindL1) {
+            if constexpr (op.c == 0) ptx::mbar_wait(ev + 8u * kEvA0Ready, par);
+            if constexpr (op.prev >= 0) {     // the previous users of this pair of accumulators have been drained
+              if constexpr (op.nblk == 2) ptx::mbar_wait2(ev + 8u * (kEvDEmpty + op.prev), ev + 8u * (kEvDEmpty + op.prev + 1), par);
+              else ptx::mbar_wait(ev + 8u * (kEvDEmpty + op.prev), par);
+            }
+          } else {
+            if constexpr (op.first && op.prev >= 0) ptx::mbar_wait(ev + 8u * (kEvDEmpty + op.prev), par);   // previous user of the accumulator drained
+            if constexpr (op.c < 2 && op.first) {
+              // first layer-2 chunk of this issuer in the step: all of A1 must be in TMEM.  Each epilogue group signals its
+              // chunks in order (group 0 the even ones, group 1 the odd ones), so the last two barriers imply the rest.
+              if constexpr (NC >= 2) ptx::mbar_wait2(ev + 8u * (kEvA1Ready + NC - 1), ev + 8u * (kEvA1Ready + NC - 2), par);
+              else ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 1), par);
+            }
           }
           // weight stage of this group: sub-ring r = chunk parity, stages consumed in (chunk, stage-of-chunk) order
           constexpr int r = op.c & 1;
@@ -472,14 +477,18 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             if (trw) a.trace[h * kTraceSlots + kTrMma + 2 * i] = clock64();
-            constexpr uint32_t d = kColD + kChunk * op.buf;
             if constexpr (op.kind == kKindL1) {
               constexpr int nks = (kD + kA + 2 + 15) / 16;
 #pragma unroll
-              for (int ks = 0; ks < nks; ++ks)
-                ptx::umma_ss<CG>(d, a0desc + 2u * ks, w1desc + (uint64_t)(op.c * (L.blk_h >> 4) + 2u * ks), kIdescH, ks > 0 ? 1u : 0u);
-              ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + op.e));
+              for (int t = 0; t < op.nblk; ++t) {
+                const uint32_t d = (uint32_t)buf_col((op.c + t) % kNumDBufL1);
+#pragma unroll
+                for (int ks = 0; ks < nks; ++ks)
+                  ptx::umma_ss<CG>(d, a0desc + 2u * ks, w1desc + (uint64_t)((op.c + t) * (L.blk_h >> 4) + 2u * ks), kIdescH, ks > 0 ? 1u : 0u);
+                ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + op.c + t));
+              }
             } else {
+              constexpr uint32_t d = buf_col(op.buf);
               const uint64_t bdesc = ptx::umma_desc_sw128(base + L.off_ring + stage * L.stage_bytes);
 #pragma unroll
               for (int t = 0; t < op.nblk; ++t) {
@@ -581,40 +590,60 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     for (int h = 0; h < H; ++h) {
       const uint32_t uh = (uint32_t)h;
       const bool trh = tr && h < kTraceSteps;
-      // the next step's action is drawn now, while layer 1 of this step is in the tensor pipe (not at the step's tail)
-      if (is_final && h + 1 < H) get_action(a, b, h + 1, kc, act);
-      static_for<2 * NC>([&](auto ec) {
+      // one accumulator chunk: TMEM -> registers, ReLU + bf16, -> TMEM operand of the next layer
+      auto chunk = [&](auto ec) {
         constexpr int e = decltype(ec)::value;
         constexpr bool l2 = e >= NC;
         constexpr int c = l2 ? e - NC : e;
         constexpr int buf = SC::value.buf[e];
         constexpr uint32_t dst = l2 ? kColA2 : kColA1 + 32 * c;
-        if ((e & 1) == g) {
-          ptx::mbar_wait(ev + 8u * (kEvDFull + e), uh & 1u);
+        if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e] = clock64();
+        uint32_t v0[32], v1[32], w0[16], w1[16];
+        ptx::tmem_ld32(lane_off + (uint32_t)buf_col(buf), v0);
+        ptx::tmem_ld32(lane_off + (uint32_t)(buf_col(buf) + 32), v1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(kEvDEmpty + e);             // accumulator is in registers: release the TMEM buffer
+        if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e + 1] = clock64();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w0[i] = pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w1[i] = pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+        if constexpr (l2 && c > 0) {
+          ptx::mbar_wait(ev + 8u * (kEvA2Empty + c - 1), uh & 1u);   // layer 3 has consumed the previous chunk
           ptx::tc_fence_after();
-          if (trh) a.trace[h * kTraceSlots + kTrEpi + 2 * e] = clock64();
-          uint32_t v0[32], v1[32], w0[16], w1[16];
-          ptx::tmem_ld32(lane_off + (uint32_t)(kColD + kChunk * buf), v0);
-          ptx::tmem_ld32(lane_off + (uint32_t)(kColD + kChunk * buf + 32), v1);
-          ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) arrive_leader(kEvDEmpty + e);             // accumulator is in registers: release the TMEM buffer
-#pragma unroll
-          for (int i = 0; i < 16; ++i) w0[i] = pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-#pragma unroll
-          for (int i = 0; i < 16; ++i) w1[i] = pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-          if constexpr (l2 && c > 0) {
-            ptx::mbar_wait(ev + 8u * (kEvA2Empty + c - 1), uh & 1u);   // layer 3 has consumed the previous chunk
-            ptx::tc_fence_after();
-          }
-          ptx::tmem_st16(lane_off + dst, w0);
-          ptx::tmem_st16(lane_off + dst + 16u, w1);
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) arrive_leader((l2 ? kEvA2Ready : kEvA1Ready) + c);
-          if (trh) a.trace[h * kTraceSlots + kTrEpi + 2 * e + 1] = clock64();
+        }
+        if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e + 2] = clock64();
+        ptx::tmem_st16(lane_off + dst, w0);
+        ptx::tmem_st16(lane_off + dst + 16u, w1);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader((l2 ? kEvA2Ready : kEvA1Ready) + c);
+        if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e + 3] = clock64();
+      };
+      // layer 1: the groups take alternate PAIRS of chunks (the pairs the issuer commits together): one combined wait
+      static_for<(NC + 1) / 2>([&](auto pc) {
+        constexpr int pr = decltype(pc)::value, c0 = 2 * pr;
+        if ((pr & 1) == g) {
+          if constexpr (c0 + 1 < NC) ptx::mbar_wait2(ev + 8u * (kEvDFull + c0), ev + 8u * (kEvDFull + c0 + 1), uh & 1u);
+          else ptx::mbar_wait(ev + 8u * (kEvDFull + c0), uh & 1u);
+          ptx::tc_fence_after();
+          chunk(std::integral_constant<int, c0>{});
+          if constexpr (c0 + 1 < NC) chunk(std::integral_constant<int, c0 + 1>{});
+        }
+      });
+      // the next step's action is drawn between the layer-1 and layer-2 chunks, where these warps have slack (at the top
+      // of the step it delays the first layer-1 epilogue, at the bottom the state update)
+      if (is_final && h + 1 < H) get_action(a, b, h + 1, kc, act);
+      // layer 2: alternate chunks
+      static_for<NC>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        if ((c & 1) == g) {
+          ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u);
+          ptx::tc_fence_after();
+          chunk(std::integral_constant<int, NC + c>{});
         }
       });
       if (is_final) {

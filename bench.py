@@ -28,6 +28,10 @@ sys.path.insert(0, ROOT)
 HIDDEN = (500, 500)
 K_PATHS, HORIZON, STATES_PER_GPU = 4096, 20, 32
 FLOP_PER_TRANSITION = 2 * (26 * 500 + 500 * 500 + 500 * 20)   # 546 000; padding not credited
+# dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload, from the committed ncu --set full
+# capture (the kernel streams its 0.6 MB of weights from L2; states in, 80-byte records out)
+NCU_DRAM_BYTES_PER_LAUNCH = 829952
+NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_full_rollout_tmem.csv"
 
 
 def measured_peaks():
@@ -131,7 +135,7 @@ def workload_config(n):
             "states": STATES_PER_GPU * n, "num_paths": K_PATHS, "horizon": HORIZON, "hidden": list(HIDDEN),
             "precision": "bf16 operands / fp32 accumulate, state and cost",
             "parallelism": f"paths sharded x{n}, NCCL all-gather of 80 B records + min-loc per plan" if n > 1 else "1 GPU",
-            "l2": "flushed between steps (256 MiB memset outside the per-step event pairs); weights (608 KB) are re-read from HBM once per step"}
+            "l2": "flushed between steps (256 MiB memset outside the per-step event pairs); the 0.6 MB weight images are re-read from HBM once per step"}
 
 
 def run_ours(args):
@@ -248,7 +252,9 @@ def run_ours(args):
                 "plans_per_s": B * args.steps / (total_ms * 1e-3),
                 "config": workload_config(world),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "bcmpc::tc::rollout_tc_kernel", "kernel_ms": k_ms,
+                             "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (dram read+write)",
+                             "traffic_source": NCU_TRAFFIC_SOURCE,
+                             "kernel": "bcmpc::tmx::rollout_tmem_kernel<2, 8>", "kernel_ms": k_ms,
                              "flop_per_transition": FLOP_PER_TRANSITION, "peak_source": peak_src,
                              "note": "algorithmic FLOPs only (26-500-500-20); padded tiles (32/512/512/32) are not credited"},
                 "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": B * 20 * 8,

@@ -34,17 +34,17 @@ def main():
         prev = t0
         for i in range(n_ops):
             kd, ch, kb0, nblk, bf, sf = ops[i]
-            name = f"L1 c{ch} b{bf}" if kd == 0 else f"L2 c{ch} kb{kb0}+{nblk} b{bf}{' W' if sf else ''}"
+            name = f"L1 c{ch}+{nblk} b{bf}" if kd == 0 else f"L2 c{ch} kb{kb0}+{nblk} b{bf}{' W' if sf else ''}"
             a, b = t[h, o_mma + 2 * i], t[h, o_mma + 2 * i + 1]
             print(f"    {i:2d} {name:18s} | {a - t0:7d} {b - t0:7d} ({b - a:4d})  gap {a - prev:5d}")
             prev = b
         print("  layer-3 issuer: chunk | issue-start issue-end")
         for c in range(nc):
             print(f"    {c} | {t[h, o_l3 + 2 * c] - t0:7d} {t[h, o_l3 + 2 * c + 1] - t0:7d}")
-        print("  epilogue (quadrant-0 warp of the group): chunk | accumulator seen   chunk done (dur)")
+        print("  epilogue (quadrant-0 warp of the group): chunk | accumulator seen  +drained  +dest free  +stored (total)")
         for e in range(2 * nc):
-            a, b = t[h, o_epi + 2 * e], t[h, o_epi + 2 * e + 1]
-            print(f"    {'L2' if e >= nc else 'L1'} c{e % nc} g{e & 1} | {a - t0:7d} {b - t0:7d} ({b - a:4d})")
+            a, b, c, d = (t[h, o_epi + 4 * e + j] for j in range(4))
+            print(f"    {'L2' if e >= nc else 'L1'} c{e % nc} g{e & 1} | {a - t0:7d}  +{b - a:4d}  +{c - b:4d}  +{d - c:4d} ({d - a:4d})")
         f0, f1 = t[h, o_fin], t[h, o_fin + 1]
         print(f"  final: output accumulator seen {f0 - t0}, next input ready {f1 - t0} ({f1 - f0})")
         print("  producer: stage | slot-wait-start copy-issued")
