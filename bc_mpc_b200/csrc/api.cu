@@ -59,7 +59,7 @@ struct bcmpc_handle {
   bool ev_valid = false;
   // tcgen05 path (rollout_tmem.cuh)
   tmx::TmHostPlan tmp;
-  uint8_t *d_res = nullptr, *d_stream = nullptr;
+  uint8_t *d_res = nullptr, *d_stream = nullptr, *d_pol = nullptr;
   unsigned long long* d_trace = nullptr;
   bool tm_ready = false;
   int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
@@ -183,7 +183,13 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 
 int tm_prepare(bcmpc_handle* h, const float* const* W, const float* const* b) {
   const int S = h->cfg.hidden_size;
-  tmx::tm_build(W[0], b[0], W[1], b[1], W[2], b[2], S, h->tm_cg, &h->tmp);
+  const bool keep_policy = h->tmp.with_policy;
+  const tmx::TmHostPlan old = h->tmp;
+  tmx::tm_build(W[0], b[0], W[1], b[1], W[2], b[2], S, h->tm_cg, h->cfg.proposal != BCMPC_PROP_UNIFORM, &h->tmp);
+  if (keep_policy) {   // the proposal network survives a dynamics refresh
+    h->tmp.with_policy = true; h->tmp.np1 = old.np1; h->tmp.np2 = old.np2; h->tmp.pol = old.pol;
+    memcpy(h->tmp.bp1, old.bp1, sizeof old.bp1); memcpy(h->tmp.bp2, old.bp2, sizeof old.bp2); memcpy(h->tmp.bp3, old.bp3, sizeof old.bp3);
+  }
   const tmx::TmHostPlan& P = h->tmp;
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
   if (P.lay.nst < 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "weight ring does not fit in shared memory");
@@ -219,9 +225,20 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.low[j] = h->norm.low[j];
     a.span[j] = h->norm.span[j];
   }
+  const bool pol = p.proposal != BCMPC_PROP_UNIFORM;
+  a.proposal = p.proposal; a.inj_kind = p.inj_kind;
+  if (pol) {
+    if (!P.with_policy || !h->d_pol) return fail(h, BCMPC_ERR_STATE, "proposal network not set (bcmpc_set_policy)");
+    a.pol = h->d_pol; a.np1 = P.np1; a.np2 = P.np2;
+    a.has_filter = h->has_filter ? 1 : 0; a.clip = h->clip;
+    a.explore = (float)h->cfg.explore; a.one_minus_explore = (float)(1.0 - h->cfg.explore);
+    for (int d = 0; d < h->cfg.obs_dim; ++d) { a.filt_mean[d] = h->filt_mean[d]; a.filt_inv_std[d] = 1.0f / h->filt_std[d]; }
+    for (int j = 0; j < h->cfg.act_dim; ++j) a.pol_std[j] = h->pol_std[j];
+    memcpy(a.bp1, P.bp1, sizeof a.bp1); memcpy(a.bp2, P.bp2, sizeof a.bp2); memcpy(a.bp3, P.bp3, sizeof a.bp3);
+  }
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
-  CK(h, tmx::tm_launch(h->tm_cg, P.nc, a, dim3(p.tiles_per_state, p.B), st));
+  CK(h, tmx::tm_launch(h->tm_cg, P.nc, pol, a, dim3(p.tiles_per_state, p.B), st));
   CK(h, cudaGetLastError());
   h->launches++;
   if (h->d_trace) {
@@ -352,7 +369,7 @@ int bcmpc_destroy(bcmpc_handle* h) {
   h->dyn.release();
   h->pol.release();
   cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
-  cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_trace);
+  cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_trace);
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_records) cudaFreeHost(h->h_records);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -435,6 +452,20 @@ int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, co
   h->has_logstd = logstd != nullptr;
   for (int j = 0; j < h->cfg.act_dim; ++j) h->pol_std[j] = logstd ? expf(logstd[j]) : 0.f;   // distributions.py:65
   update_verify_geometry(h);
+  if (h->cfg.precision == BCMPC_PREC_BF16_FAST && h->cfg.proposal != BCMPC_PROP_UNIFORM) {
+    std::string why;
+    if (!tmx::tm_policy_supported(n_layers, sizes, &why)) return fail(h, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
+    if (h->tmp.cg == 0 || h->tmp.lay.blk_h == 0) {   // layout depends only on (pair mode, hidden chunks): fix it now if the dynamics come later
+      h->tmp.cg = h->tm_cg;
+      h->tmp.nc = (h->cfg.hidden_size + 2 + 63) / 64;
+      h->tmp.lay = tmx::make_layout(h->tm_cg, h->tmp.nc, true);
+    }
+    tmx::tm_build_policy(sizes, W, b, &h->tmp);
+    if (h->d_pol) cudaFree(h->d_pol);
+    h->d_pol = nullptr;
+    CK(h, cudaMalloc(&h->d_pol, h->tmp.pol.size() * 2));
+    CK(h, cudaMemcpy(h->d_pol, h->tmp.pol.data(), h->tmp.pol.size() * 2, cudaMemcpyHostToDevice));
+  }
   return BCMPC_OK;
 }
 

@@ -75,10 +75,17 @@ enum : int {
   kEvDEmpty = 26,      // [16] accumulator of chunk e drained into registers           (epilogue -> issuer of the next user)
   kEvA2Ready = 42,     // [8]  hidden-2 chunk c is in TMEM                             (epilogue -> L3 issuer)
   kEvA2Empty = 50,     // [8]  layer 3 has consumed hidden-2 chunk c                   (L3 issuer -> epilogue)
-  kNumEv = 58
+  // proposal network (policy-guided shooting), also once per step each
+  kEvAp0Ready = 58,    // policy input rows are in shared memory                        (epilogue -> issuer)
+  kEvPdFull = 59,      // [4]  policy accumulators: layer-1 chunks 0,1, layer-2 chunks 0,1   (issuer -> epilogue)
+  kEvAp1Ready = 63,    // [2]  policy hidden-1 chunk in TMEM                            (epilogue -> issuer)
+  kEvAp2Ready = 65,    // [2]  policy hidden-2 chunk in TMEM
+  kEvPolFull = 67,     // policy output accumulator complete                            (issuer -> epilogue)
+  kNumEv = 68
 };
-// misc smem: [w_full 16][w_empty 16][res_full][events 58] x 8 B, tmem ptr, argmin scratch
-constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, kOffTmemPtr = 736, kOffRed = 752, kMiscBytes = 1024;
+// misc smem: [w_full 16][w_empty 16][res_full][events 68] x 8 B, tmem ptr, argmin scratch
+constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, kOffTmemPtr = 816, kOffRed = 832, kMiscBytes = 1024;
+constexpr int kPolMaxHidden = 128;     // proposal network: two tanh layers of at most 128 units (MlpPolicy hid_size=128, BCnetwork 128/64)
 
 // ---------------------------------------------------------------------------------------------------------
 // The per-step schedule of the layer-1/2 issuer, computed by ONE constexpr function that both sides use: the host
@@ -143,9 +150,9 @@ struct Layout {
   int kbs = 0, nstg = 0, nst = 0;
   int nst_r[2] = {0, 0}, first_r[2] = {0, 0};     // the ring is split in two: even layer-2 chunks / odd layer-2 chunks, one per MMA issuer
   uint32_t blk_h = 0, blk_o = 0, w1_bytes = 0, res_bytes = 0, stage_bytes = 0;
-  uint32_t off_a0 = 0, off_res = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
+  uint32_t off_a0 = 0, off_res = 0, off_pol = 0, pol_bytes = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
 };
-constexpr Layout make_layout(int cg, int nc) {
+constexpr Layout make_layout(int cg, int nc, bool pol) {
   Layout L;
   L.kbs = stage_kblocks(cg, nc);
   L.nstg = (nc + L.kbs - 1) / L.kbs;
@@ -155,7 +162,10 @@ constexpr Layout make_layout(int cg, int nc) {
   L.res_bytes = L.w1_bytes + nc * L.blk_o;         // resident: W1 chunks then W3 k-blocks
   L.off_a0 = 0;
   L.off_res = kA0Bytes;
-  L.off_ring = (L.off_res + L.res_bytes + 1023u) / 1024u * 1024u;
+  L.off_pol = (L.off_res + L.res_bytes + 1023u) / 1024u * 1024u;
+  // resident proposal network (sized for 128/128 hidden units): [Wp1: 2 chunks][Wp2: 2 chunks x 2 k-blocks][Wp3: 2 k-blocks]
+  L.pol_bytes = pol ? 6u * L.blk_h + 2u * L.blk_o : 0u;
+  L.off_ring = (L.off_pol + L.pol_bytes + 1023u) / 1024u * 1024u;
   L.stage_bytes = L.kbs * L.blk_h;
   L.nst = (int)((kSmemLimit - kMiscBytes - L.off_ring) / L.stage_bytes);
   if (L.nst > kMaxStages) L.nst = kMaxStages;
@@ -166,9 +176,9 @@ constexpr Layout make_layout(int cg, int nc) {
   return L;
 }
 
-template <int CG, int NC>
+template <int CG, int NC, bool POL>
 struct Lay {
-  static constexpr Layout value = make_layout(CG, NC);
+  static constexpr Layout value = make_layout(CG, NC, POL);
 };
 
 struct TmArgs {
@@ -178,6 +188,13 @@ struct TmArgs {
   unsigned long long* trace;     // optional pipeline trace (tools/tc_trace.py), nullptr = off
   float mean_obs[kMaxObs], inv_den_obs[kMaxObs], mean_delta[kMaxObs], std_delta[kMaxObs];
   float mean_act[kMaxAct], inv_den_act[kMaxAct], low[kMaxAct], span[kMaxAct];
+  // proposal network (policy-guided shooting); unused with uniform shooting
+  const uint8_t* pol;            // resident image [CG][pol_bytes]
+  int np1, np2;                  // 64-unit chunks of the two hidden layers
+  int proposal, inj_kind, has_filter;
+  float clip, explore, one_minus_explore;
+  float filt_mean[kMaxObs], filt_inv_std[kMaxObs], pol_std[kMaxAct];
+  float bp1[kPolMaxHidden], bp2[kPolMaxHidden], bp3[kMaxAct];
 };
 // pipeline trace of CTA (0,0), steps 0..3: [2 per L1/L2 group][2 per L3 group][4 per epilogue chunk][final 2][2 per stage]
 constexpr int kTraceSteps = 4, kTrMma = 0, kTrL3 = 2 * kMaxOps, kTrEpi = kTrL3 + 16, kTrFinal = kTrEpi + 64, kTrProd = kTrFinal + 4,
@@ -206,8 +223,11 @@ inline size_t sw128_offset(int n, int kk) {
 }
 
 struct TmHostPlan {
-  std::vector<uint16_t> res, stream;
+  std::vector<uint16_t> res, stream, pol;
   int cg = 1, s_pad = 0, nc = 0;
+  bool with_policy = false;
+  int np1 = 0, np2 = 0;
+  float bp1[kPolMaxHidden] = {}, bp2[kPolMaxHidden] = {}, bp3[kMaxAct] = {};
   Layout lay;
 };
 
@@ -216,22 +236,68 @@ inline bool tm_supported(const bcmpc_config& c, std::string* why) {
   if (c.n_hidden != 2) { *why = "bf16 fast path supports n_hidden == 2 this round"; return false; }
   if (c.hidden_size < 1 || c.hidden_size > 510) { *why = "bf16 fast path supports hidden_size <= 510 this round (TMEM holds the 512-wide padded activations)"; return false; }
   if (c.activation != BCMPC_ACT_RELU) { *why = "bf16 fast path supports relu only"; return false; }
-  if (c.proposal != BCMPC_PROP_UNIFORM) { *why = "bf16 fast path supports uniform shooting (P0) this round; use BCMPC_PREC_FP32_VERIFY for policy proposals"; return false; }
   return true;
+}
+
+// Proposal network for the fast path: sizes = {20, h1, h2, 6}, tanh hidden layers, h1, h2 <= 128.  W[l] are [in,out].
+inline bool tm_policy_supported(int n_layers, const int* sizes, std::string* why) {
+  if (n_layers != 3) { *why = "bf16 fast path supports proposal networks with two hidden layers"; return false; }
+  if (sizes[0] != kD || sizes[3] != kA) { *why = "bf16 fast path: proposal network must map 20 observations to 6 actions"; return false; }
+  if (sizes[1] < 1 || sizes[1] > kPolMaxHidden || sizes[2] < 1 || sizes[2] > kPolMaxHidden) { *why = "bf16 fast path: proposal network hidden sizes must be <= 128"; return false; }
+  return true;
+}
+inline void tm_build_policy(const int* sizes, const float* const* W, const float* const* b, TmHostPlan* plan) {
+  TmHostPlan& P = *plan;
+  const int cg = P.cg, h1 = sizes[1], h2 = sizes[2];
+  P.np1 = (h1 + 63) / 64; P.np2 = (h2 + 63) / 64;
+  const int rows_h = kChunk / cg, rows_o = kOutN / cg;
+  const uint32_t blk_h = P.lay.blk_h, blk_o = P.lay.blk_o, pol_bytes = 6u * blk_h + 2u * blk_o;
+  P.pol.assign((size_t)cg * pol_bytes / 2, 0);
+  for (int r = 0; r < cg; ++r) {
+    const size_t rb = (size_t)r * pol_bytes;
+    for (int j = 0; j < P.np1; ++j)                                  // Wp1 chunk j: [64 units x 64 k (20 used)]
+      for (int i = 0; i < rows_h; ++i) {
+        const int n = j * kChunk + r * rows_h + i;
+        if (n >= h1) continue;
+        for (int k = 0; k < kD; ++k) P.pol[(rb + (size_t)j * blk_h + sw128_offset(i, k)) / 2] = f32_to_bf16(W[0][(size_t)k * h1 + n]);
+      }
+    for (int j = 0; j < P.np2; ++j)                                  // Wp2 chunk j, k-block kb
+      for (int kb = 0; kb < P.np1; ++kb)
+        for (int i = 0; i < rows_h; ++i) {
+          const int n = j * kChunk + r * rows_h + i;
+          if (n >= h2) continue;
+          for (int kk = 0; kk < 64; ++kk) {
+            const int k = kb * 64 + kk;
+            if (k < h1) P.pol[(rb + (size_t)(2 + j * 2 + kb) * blk_h + sw128_offset(i, kk)) / 2] = f32_to_bf16(W[1][(size_t)k * h2 + n]);
+          }
+        }
+    for (int kb = 0; kb < P.np2; ++kb)                               // Wp3 k-block kb: [32 outputs (6 used) x 64 k]
+      for (int i = 0; i < rows_o; ++i) {
+        const int n = r * rows_o + i;
+        if (n >= kA) continue;
+        for (int kk = 0; kk < 64; ++kk) {
+          const int k = kb * 64 + kk;
+          if (k < h2) P.pol[(rb + 6u * blk_h + (size_t)kb * blk_o + sw128_offset(i, kk)) / 2] = f32_to_bf16(W[2][(size_t)k * kA + n]);
+        }
+      }
+  }
+  for (int i = 0; i < kPolMaxHidden; ++i) { P.bp1[i] = i < h1 ? b[0][i] : 0.f; P.bp2[i] = i < h2 ? b[1][i] : 0.f; }
+  for (int i = 0; i < kMaxAct; ++i) P.bp3[i] = i < kA ? b[2][i] : 0.f;
+  P.with_policy = true;
 }
 
 // W[l] are TF kernels [in,out] row-major: W1 [26,S], W2 [S,S], W3 [S,20].
 // Bias-in-GEMM: input columns 26,27 of A0 are 1.0; hidden units S and S+1 of both hidden layers are wired to be
 // exactly 1.0 after ReLU; row S / S+1 of the next layer's kernel hold bf16(b) and bf16(b - bf16(b)).
 inline void tm_build(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
-                     int S, int cg, TmHostPlan* out) {
+                     int S, int cg, bool pol, TmHostPlan* out) {
   TmHostPlan& P = *out;
   P = TmHostPlan{};
   const int in_dim = kD + kA;
   P.cg = cg;
   P.s_pad = (S + 2 + 63) / 64 * 64;
   P.nc = P.s_pad / 64;
-  P.lay = make_layout(cg, P.nc);
+  P.lay = make_layout(cg, P.nc, pol);
   const int NC = P.nc, NKB = P.nc, kbs = P.lay.kbs;
   const int rows_h = kChunk / cg, rows_o = kOutN / cg;                 // B rows per CTA (hidden / output tiles)
   const uint32_t blk_h = P.lay.blk_h, blk_o = P.lay.blk_o, w1_bytes = P.lay.w1_bytes;
@@ -329,26 +395,50 @@ __device__ __forceinline__ void build_input(const TmArgs& a, uint32_t a0_row_add
   }
 }
 
-// the action of (path, step): injected tensor or Philox draw (controllers.py:53)
-__device__ __forceinline__ void get_action(const TmArgs& a, int b, int h, int k, float (&act)[kA]) {
+// the injected randomness of (path, step): the given tensor or a Philox draw.  Uniform shooting: the action itself
+// (controllers.py:53); policy-guided: N(0,1) / U[low,high) / U[-1,1) noise.
+__device__ __forceinline__ void get_noise(const TmArgs& a, int b, int h, int k, float (&z)[kA]) {
   const PlanArgs& p = a.p;
   if (p.inj) {
     const double* src = p.inj + (((size_t)b * p.H + h) * p.K + k) * kA;
 #pragma unroll
-    for (int j = 0; j < kA; ++j) act[j] = (float)src[j];
+    for (int j = 0; j < kA; ++j) z[j] = (float)src[j];
   } else {
     float v[kMaxAct];
-    draw_injection(v, kA, kInjUniformBox, p.seed, (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
+    draw_injection(v, kA, a.inj_kind, p.seed, (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
 #pragma unroll
-    for (int j = 0; j < kA; ++j) act[j] = v[j];
+    for (int j = 0; j < kA; ++j) z[j] = v[j];
+  }
+}
+
+// observation filter of MlpPolicy (ppo_bc_policy.py:60) -> bf16 -> the first four 16-byte chunks of this row of the
+// input tile (the proposal network reuses the A0 buffer; its biases are added in the epilogues)
+__device__ __forceinline__ void build_policy_input(const TmArgs& a, uint32_t a0_row_addr, int row, const float (&s)[kD]) {
+  float x[32];
+#pragma unroll
+  for (int c = 0; c < kD; ++c) {
+    float v = s[c];
+    if (a.has_filter) v = (v - a.filt_mean[c]) * a.filt_inv_std[c];
+    if (a.clip > 0.f) v = fminf(fmaxf(v, -a.clip), a.clip);
+    x[c] = v;
+  }
+#pragma unroll
+  for (int c = kD; c < 32; ++c) x[c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t addr = a0_row_addr + (uint32_t)(((c ^ (row & 7)) << 4));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(x[8 * c + 0], x[8 * c + 1])),
+                 "r"(pack_bf16(x[8 * c + 2], x[8 * c + 3])), "r"(pack_bf16(x[8 * c + 4], x[8 * c + 5])),
+                 "r"(pack_bf16(x[8 * c + 6], x[8 * c + 7]))
+                 : "memory");
   }
 }
 
 // Barrier waits are executed by all 32 lanes of the role warp (measured: ~100 cycles when the phase is already
 // complete; a single elected lane polling while the others park at the reconvergence barrier costs > 1000).
-template <int CG, int NC>
+template <int CG, int NC, bool POL>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
-  constexpr Layout L = Lay<CG, NC>::value;
+  constexpr Layout L = Lay<CG, NC, POL>::value;
   using SC = Sched<NC, L.kbs>;
   constexpr int kNumOps = SC::value.n;
   constexpr int kNstg = L.nstg;                               // weight stages per layer-2 chunk
@@ -387,6 +477,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       ptx::mbar_init(ev + 8u * (kEvA2Empty + i), 1);
     }
     for (int i = 0; i < kMaxChunks; ++i) { ptx::mbar_init(ev + 8u * (kEvDFull + i), 1); ptx::mbar_init(ev + 8u * (kEvDEmpty + i), 4 * CG); }
+    ptx::mbar_init(ev + 8u * kEvAp0Ready, 4 * CG);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(ev + 8u * (kEvPdFull + i), 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(ev + 8u * (kEvAp1Ready + i), 4 * CG); ptx::mbar_init(ev + 8u * (kEvAp2Ready + i), 4 * CG); }
+    ptx::mbar_init(ev + 8u * kEvPolFull, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc_cg<CG>(ptx::smem_u32(s_tmem), kTmemCols);
@@ -405,9 +499,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     // ===================== weight producer (every CTA loads its own half) =====================
     if (ptx::elect_one()) {
       const uint8_t* src = a.res + (size_t)rank * L.res_bytes;
-      ptx::mbar_arrive_expect_tx(misc + kOffResFull, L.res_bytes);
+      ptx::mbar_arrive_expect_tx(misc + kOffResFull, L.res_bytes + L.pol_bytes);
       for (uint32_t o = 0; o < L.res_bytes; o += 16384u)
         ptx::bulk_g2s(base + L.off_res + o, src + o, min(16384u, L.res_bytes - o), misc + kOffResFull);
+      if constexpr (POL) {
+        const uint8_t* psrc = a.pol + (size_t)rank * L.pol_bytes;
+        for (uint32_t o = 0; o < L.pol_bytes; o += 16384u)
+          ptx::bulk_g2s(base + L.off_pol + o, psrc + o, min(16384u, L.pol_bytes - o), misc + kOffResFull);
+      }
     }
     __syncwarp();
     uint32_t stage[2] = {0, 0}, phase[2] = {0, 0};
@@ -447,6 +546,54 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       for (int h = 0; h < H; ++h) {
         const uint32_t uh = (uint32_t)h, par = uh & 1u;
         const bool trw = tracing && h < kTraceSteps;
+        if constexpr (POL) {
+          if (mine == 1) {
+            // ---- proposal network: policy input (smem) -> tanh layer -> tanh layer -> action means (D3 columns 0..5) ----
+            // Accumulators: layer-1 chunks in buffers 0,1; layer-2 chunks in buffers 2,0 (every policy accumulator has
+            // been drained before the barrier that lets its buffer's next user start completes).
+            const uint64_t wpdesc = ptx::umma_desc_sw128(base + L.off_pol);
+            const uint32_t np1 = (uint32_t)a.np1, np2 = (uint32_t)a.np2;
+            ptx::mbar_wait(ev + 8u * kEvAp0Ready, par);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              for (uint32_t j = 0; j < np1; ++j) {
+                const uint32_t d = j ? (uint32_t)buf_col(1) : (uint32_t)buf_col(0);
+#pragma unroll
+                for (uint32_t ks = 0; ks < 2; ++ks)
+                  ptx::umma_ss<CG>(d, a0desc + 2u * ks, wpdesc + (uint64_t)(j * (L.blk_h >> 4) + 2u * ks), kIdescH, ks);
+                ptx::umma_commit_cg<CG>(ev + 8u * (kEvPdFull + j));
+              }
+            }
+            __syncwarp();
+            if (np1 > 1) ptx::mbar_wait2(ev + 8u * kEvAp1Ready, ev + 8u * (kEvAp1Ready + 1), par);
+            else ptx::mbar_wait(ev + 8u * kEvAp1Ready, par);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              for (uint32_t j = 0; j < np2; ++j) {
+                const uint32_t d = j ? (uint32_t)buf_col(0) : (uint32_t)buf_col(2);
+                for (uint32_t kb = 0; kb < np1; ++kb)
+#pragma unroll
+                  for (uint32_t ks = 0; ks < 4; ++ks)
+                    ptx::umma_ts<CG>(d, kColA1 + kb * 32u + ks * 8u, wpdesc + (uint64_t)((2u + j * 2u + kb) * (L.blk_h >> 4) + 2u * ks), kIdescH,
+                                     (kb | ks) ? 1u : 0u);
+                ptx::umma_commit_cg<CG>(ev + 8u * (kEvPdFull + 2 + j));
+              }
+            }
+            __syncwarp();
+            if (np2 > 1) ptx::mbar_wait2(ev + 8u * kEvAp2Ready, ev + 8u * (kEvAp2Ready + 1), par);
+            else ptx::mbar_wait(ev + 8u * kEvAp2Ready, par);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              for (uint32_t kb = 0; kb < np2; ++kb)
+#pragma unroll
+                for (uint32_t ks = 0; ks < 4; ++ks)
+                  ptx::umma_ts<CG>(kColD3, kColA1 + 64u + kb * 32u + ks * 8u,
+                                   wpdesc + (uint64_t)(6u * (L.blk_h >> 4) + kb * (L.blk_o >> 4) + 2u * ks), kIdescO, (kb | ks) ? 1u : 0u);
+              ptx::umma_commit_cg<CG>(ev + 8u * kEvPolFull);
+            }
+            __syncwarp();
+          }
+        }
         static_for<kNumOps>([&](auto ic) {
           constexpr int i = decltype(ic)::value;
           constexpr SOp op = SC::value.ops[i];
@@ -568,28 +715,93 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     };
     // A0 rows are generic-proxy shared-memory writes read by THIS CTA's tensor core (A is split by rows across the
     // pair); the proxy fence makes them visible to the async proxy, the arrive tells the leader's issuer to go
-    auto publish_a0 = [&]() {
+    auto publish = [&](uint32_t id) {
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) arrive_leader(kEvA0Ready);
+      if (lane == 0) arrive_leader(id);
     };
-    float s[kD], act[kA], act0[kA], cost = 0.f;
+    float s[kD], z[kA], act[kA], act0[kA], cost = 0.f;
     if (is_final) {
 #pragma unroll
       for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)(p.per_row_states ? kc : b) * kD + d];
-      get_action(a, b, 0, kc, act);
-#pragma unroll
-      for (int j = 0; j < kA; ++j) act0[j] = act[j];
+      get_noise(a, b, 0, kc, z);
       if (p.states_out && valid)
         for (int d = 0; d < kD; ++d) p.states_out[(size_t)k * kD + d] = (double)s[d];
-      if (p.actions_out && valid)
-        for (int j = 0; j < kA; ++j) p.actions_out[(size_t)k * kA + j] = (double)act[j];
-      build_input(a, a0_row, row, s, act);
-      publish_a0();
     }
     for (int h = 0; h < H; ++h) {
       const uint32_t uh = (uint32_t)h;
       const bool trh = tr && h < kTraceSteps;
+      // ---- the action of this step ----
+      if constexpr (POL) {
+        // proposal network (ppo_bc_policy.py:60,70-72 / behavioral_cloning.py:21-26) on the tensor cores
+        if (is_final) {
+          build_policy_input(a, a0_row, row, s);
+          publish(kEvAp0Ready);
+        }
+        // one 64-unit chunk of a tanh layer: accumulator + bias -> tanh -> bf16 -> TMEM operand of the next policy layer
+        auto pol_chunk = [&](auto lc, auto jc) {
+          constexpr int layer = decltype(lc)::value, j = decltype(jc)::value;
+          constexpr uint32_t col = layer == 1 ? (uint32_t)buf_col(j) : (j == 0 ? (uint32_t)buf_col(2) : (uint32_t)buf_col(0));
+          constexpr uint32_t dst = kColA1 + (layer == 1 ? 0u : 64u) + 32u * j;
+          ptx::mbar_wait(ev + 8u * (kEvPdFull + (layer - 1) * 2 + j), uh & 1u);
+          ptx::tc_fence_after();
+          uint32_t v0[32], v1[32], w0[16], w1[16];
+          ptx::tmem_ld32(lane_off + col, v0);
+          ptx::tmem_ld32(lane_off + col + 32u, v1);
+          ptx::tmem_ld_wait();
+          auto bias_at = [&](int idx) { if constexpr (layer == 1) return a.bp1[idx]; else return a.bp2[idx]; };
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            w0[i] = pack_bf16(ptx::tanh_approx(__uint_as_float(v0[2 * i]) + bias_at(64 * j + 2 * i)),
+                              ptx::tanh_approx(__uint_as_float(v0[2 * i + 1]) + bias_at(64 * j + 2 * i + 1)));
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            w1[i] = pack_bf16(ptx::tanh_approx(__uint_as_float(v1[2 * i]) + bias_at(64 * j + 32 + 2 * i)),
+                              ptx::tanh_approx(__uint_as_float(v1[2 * i + 1]) + bias_at(64 * j + 32 + 2 * i + 1)));
+          ptx::tmem_st16(lane_off + dst, w0);
+          ptx::tmem_st16(lane_off + dst + 16u, w1);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader((layer == 1 ? kEvAp1Ready : kEvAp2Ready) + j);
+        };
+        // group g takes chunk g of both hidden layers
+        if (g == 0) pol_chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
+        else if (a.np1 > 1) pol_chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+        if (g == 0) pol_chunk(std::integral_constant<int, 2>{}, std::integral_constant<int, 0>{});
+        else if (a.np2 > 1) pol_chunk(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{});
+        if (is_final) {
+          ptx::mbar_wait(ev + 8u * kEvPolFull, uh & 1u);
+          ptx::tc_fence_after();
+          uint32_t v[32];
+          ptx::tmem_ld32(lane_off + (uint32_t)kColD3, v);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+#pragma unroll
+          for (int j = 0; j < kA; ++j) {
+            const float mean = __uint_as_float(v[j]) + a.bp3[j];
+            if (a.proposal == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
+            else if (a.proposal == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
+            else act[j] = mean + z[j];                                                                                   // controllers.pyc (BC + U[-1,1))
+          }
+        }
+      } else {
+        if (is_final) {
+#pragma unroll
+          for (int j = 0; j < kA; ++j) act[j] = z[j];                        // controllers.py:70: the sampled action itself
+        }
+      }
+      if (is_final) {
+        if (h == 0) {
+#pragma unroll
+          for (int j = 0; j < kA; ++j) act0[j] = act[j];
+        }
+        if (p.actions_out && valid)
+          for (int j = 0; j < kA; ++j) p.actions_out[((size_t)h * p.K + k) * kA + j] = (double)act[j];
+        build_input(a, a0_row, row, s, act);
+        publish(kEvA0Ready);
+        if (trh) a.trace[h * kTraceSlots + kTrFinal + 1] = clock64();
+      }
       // one accumulator chunk: TMEM -> registers, ReLU + bf16, -> TMEM operand of the next layer
       auto chunk = [&](auto ec) {
         constexpr int e = decltype(ec)::value;
@@ -634,9 +846,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           if constexpr (c0 + 1 < NC) chunk(std::integral_constant<int, c0 + 1>{});
         }
       });
-      // the next step's action is drawn between the layer-1 and layer-2 chunks, where these warps have slack (at the top
-      // of the step it delays the first layer-1 epilogue, at the bottom the state update)
-      if (is_final && h + 1 < H) get_action(a, b, h + 1, kc, act);
+      // the next step's randomness is drawn between the layer-1 and layer-2 chunks, where these warps have slack (at the
+      // top of the step it delays the first layer-1 epilogue, at the bottom the state update)
+      if (is_final && h + 1 < H) get_noise(a, b, h + 1, kc, z);
       // layer 2: alternate chunks
       static_for<NC>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
@@ -663,13 +875,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         cost -= delta[17] * 100.f;                                           // cost_functions.py:28 (/ 0.01)
 #pragma unroll
         for (int d = 0; d < kD; ++d) s[d] += delta[d];                       // dynamics.py:116
-        if (h + 1 < H) {
-          build_input(a, a0_row, row, s, act);
-          publish_a0();
-          if (trh) a.trace[h * kTraceSlots + kTrFinal + 1] = clock64();
-          if (p.actions_out && valid)
-            for (int j = 0; j < kA; ++j) p.actions_out[((size_t)(h + 1) * p.K + k) * kA + j] = (double)act[j];
-        }
         if (p.states_out && valid)
           for (int d = 0; d < kD; ++d) p.states_out[((size_t)(h + 1) * p.K + k) * kD + d] = (double)s[d];
       }
@@ -714,10 +919,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------
 // launch: picks the instantiation for (CTA-group size, hidden chunks)
 // ---------------------------------------------------------------------------------------------------------
-template <int CG, int NC>
+template <int CG, int NC, bool POL>
 inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = rollout_tmem_kernel<CG, NC>;
-  constexpr Layout L = Lay<CG, NC>::value;
+  auto kern = rollout_tmem_kernel<CG, NC, POL>;
+  constexpr Layout L = Lay<CG, NC, POL>::value;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes);
@@ -735,22 +940,23 @@ inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
-template <int CG>
+template <int CG, bool POL>
 inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
   switch (nc) {
-    case 1: return tm_launch_t<CG, 1>(a, grid, st);
-    case 2: return tm_launch_t<CG, 2>(a, grid, st);
-    case 3: return tm_launch_t<CG, 3>(a, grid, st);
-    case 4: return tm_launch_t<CG, 4>(a, grid, st);
-    case 5: return tm_launch_t<CG, 5>(a, grid, st);
-    case 6: return tm_launch_t<CG, 6>(a, grid, st);
-    case 7: return tm_launch_t<CG, 7>(a, grid, st);
-    case 8: return tm_launch_t<CG, 8>(a, grid, st);
+    case 1: return tm_launch_t<CG, 1, POL>(a, grid, st);
+    case 2: return tm_launch_t<CG, 2, POL>(a, grid, st);
+    case 3: return tm_launch_t<CG, 3, POL>(a, grid, st);
+    case 4: return tm_launch_t<CG, 4, POL>(a, grid, st);
+    case 5: return tm_launch_t<CG, 5, POL>(a, grid, st);
+    case 6: return tm_launch_t<CG, 6, POL>(a, grid, st);
+    case 7: return tm_launch_t<CG, 7, POL>(a, grid, st);
+    case 8: return tm_launch_t<CG, 8, POL>(a, grid, st);
   }
   return cudaErrorInvalidValue;
 }
-inline cudaError_t tm_launch(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
-  return cg == 2 ? tm_launch_cg<2>(nc, a, grid, st) : tm_launch_cg<1>(nc, a, grid, st);
+inline cudaError_t tm_launch(int cg, int nc, bool pol, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  if (pol) return cg == 2 ? tm_launch_cg<2, true>(nc, a, grid, st) : tm_launch_cg<1, true>(nc, a, grid, st);
+  return cg == 2 ? tm_launch_cg<2, false>(nc, a, grid, st) : tm_launch_cg<1, false>(nc, a, grid, st);
 }
 
 }  // namespace tmx

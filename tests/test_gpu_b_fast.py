@@ -57,6 +57,34 @@ def test_rollout_tracks_oracle_and_argmin_agreement(K, H):
     assert max(regrets) < 0.5       # the bf16 winner is within half a cost-std of the exact winner
 
 
+@pytest.mark.parametrize("proposal,bc,K", [("policy_gaussian", False, 8192), ("policy_mix", False, 1000), ("bc_uniform", True, 1000)])
+def test_policy_guided_fast_mode_tracks_oracle(proposal, bc, K):
+    """BASELINE.json configs[3] (BC/policy-guided MPC, K=8192 x H=15) on the tcgen05 path: proposal network, noise
+    mixing, rollout and cost fused; compared with the float32/float64 oracle on injected noise."""
+    H = 15
+    rng, norm, state, pl, mpc = make_pair(21, (500, 500), K, H, precision="bf16", proposal=proposal, bc=bc)
+    inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64) if proposal == "policy_gaussian" \
+        else f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, inj, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, inj)
+    assert np.abs(ao[0] - dbg["actions"][0]).max() < 0.03           # first proposals: same state, bf16 policy net
+    assert np.abs(ao - dbg["actions"]).max() < 0.25                 # later ones drift with the bf16 rollout
+    e = _norm_err(so, dbg["states"], norm)
+    assert np.abs(e).max() < 0.25, np.abs(e).max()
+    assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
+    rec = pl.plan(state, inj=inj)[0]
+    assert rec["index"] == int(np.argmin(co))
+    assert np.allclose(rec["action"][:6], ao[0, rec["index"]])
+    regret = (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std()
+    print(dict(proposal=proposal, K=K, argmin_match=bool(rec["index"] == dbg["argmin"]), regret_in_cost_std=float(regret),
+               max_action_err=float(np.abs(ao - dbg["actions"]).max()), max_state_err_in_delta_std=float(np.abs(e).max())))
+    assert regret < 0.5
+    # device-side sampling: runs, is reproducible, and differs across seeds
+    r1, r2, r3 = pl.plan(state, seed=5)[0], pl.plan(state, seed=5)[0], pl.plan(state, seed=6)[0]
+    assert r1["index"] == r2["index"] and r1["cost"] == r2["cost"]
+    assert not np.array_equal(r1["action"], r3["action"])
+
+
 def test_fast_mode_sampling_batching_sharding_are_bit_consistent():
     import torch
     from bc_mpc_b200 import _lib as L
@@ -104,6 +132,6 @@ def test_fast_mode_large_k_properties():
     assert np.array_equal(inj1[0, 0], rec["action"][:6])
     _, _, c = mpc1.rollout(state, inj1)
     assert abs(c[0] - rec["cost"]) < 0.25 * abs(c[0]) + 5.0
-    unsupported = dict(hidden=(500, 500, 500))
+    unsupported = dict(hidden=(500, 500, 500))   # three hidden layers: verification mode only
     with pytest.raises(RuntimeError, match="n_hidden"):
         make_pair(1, unsupported["hidden"], 128, 2, precision="bf16")
