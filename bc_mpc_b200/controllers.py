@@ -78,6 +78,8 @@ class _GpuShootingController(Controller):
             self._dyn_version = None
         if self._dyn_version != dm.version:     # weights change after every dyn_model.fit (train_mpc_ppo.py:279)
             self._planner.set_dynamics(dm.weights)
+            if getattr(dm, "layer_norm", False):
+                self._planner.set_layer_norm(dm.layer_norm_params)
             self._planner.set_normalization(*dm.normalization6())
             self._dyn_version = dm.version
         pol = self._policy()

@@ -37,6 +37,7 @@ struct bcmpc_handle {
   std::string err;
   cudaStream_t stream = nullptr;
   DeviceMlp dyn, pol;
+  std::vector<float*> ln_bufs;   // LayerNorm gamma/beta of the dynamics net (bcmpc_set_layer_norm)
   NormArgs norm{};
   bool have_norm = false, have_bounds = false;
   // proposal network meta
@@ -246,15 +247,10 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     std::vector<unsigned long long> t((size_t)tmx::kTraceSteps * tmx::kTraceSlots);
     CK(h, cudaMemcpy(t.data(), h->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (FILE* f = fopen(h->trace_path.c_str(), "wb")) {
-      const tmx::Schedule sch = tmx::make_schedule(P.nc, P.lay.kbs);
-      const int hdr[10] = {tmx::kTraceSteps, tmx::kTraceSlots, sch.n, P.nc, tmx::kTrMma, tmx::kTrL3, tmx::kTrEpi, tmx::kTrFinal,
-                           tmx::kTrProd, P.nc * P.lay.nstg};
+      const int hdr[10] = {tmx::kTraceSteps, tmx::kTraceSlots, P.nc, P.lay.nstg, tmx::kTrL1, tmx::kTrL2, tmx::kTrL3, tmx::kTrEpi,
+                           tmx::kTrFinal, tmx::kTrProd};
       fwrite(hdr, sizeof hdr, 1, f);
       fwrite(t.data(), sizeof(unsigned long long), t.size(), f);
-      for (int i = 0; i < sch.n; ++i) {
-        const int rec[6] = {sch.ops[i].kind, sch.ops[i].c, sch.ops[i].kb0, sch.ops[i].nblk, sch.ops[i].buf, sch.ops[i].sfirst};
-        fwrite(rec, sizeof rec, 1, f);
-      }
       fclose(f);
     }
   }
@@ -368,6 +364,7 @@ int bcmpc_destroy(bcmpc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->dyn.release();
   h->pol.release();
+  for (float* p : h->ln_bufs) cudaFree(p);
   cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
   cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_trace);
   if (h->h_states) cudaFreeHost(h->h_states);
@@ -397,6 +394,33 @@ int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* cons
     rc = tm_prepare(h, W, b);
     if (rc) return rc;
   }
+  return BCMPC_OK;
+}
+
+int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (h->cfg.precision == BCMPC_PREC_BF16_FAST)
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "LayerNorm dynamics run in BCMPC_PREC_FP32_VERIFY only this round");
+  if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  for (float* p : h->ln_bufs) cudaFree(p);
+  h->ln_bufs.clear();
+  for (int l = 0; l < kMaxLayers; ++l) h->dyn.desc.ln_gamma[l] = h->dyn.desc.ln_beta[l] = nullptr;
+  if (!gamma) return BCMPC_OK;
+  if (!beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
+  if (n_hidden != h->cfg.n_hidden) return fail(h, BCMPC_ERR_INVALID, "n_hidden %d != %d", n_hidden, h->cfg.n_hidden);
+  for (int l = 0; l < n_hidden; ++l) {
+    if (!gamma[l] || !beta[l]) return fail(h, BCMPC_ERR_INVALID, "null LayerNorm pointer for layer %d", l);
+    float *dg = nullptr, *db = nullptr;
+    CK(h, cudaMalloc(&dg, sizeof(float) * h->cfg.hidden_size)); h->ln_bufs.push_back(dg);
+    CK(h, cudaMalloc(&db, sizeof(float) * h->cfg.hidden_size)); h->ln_bufs.push_back(db);
+    CK(h, cudaMemcpy(dg, gamma[l], sizeof(float) * h->cfg.hidden_size, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(db, beta[l], sizeof(float) * h->cfg.hidden_size, cudaMemcpyHostToDevice));
+    h->dyn.desc.ln_gamma[l] = dg;
+    h->dyn.desc.ln_beta[l] = db;
+  }
+  h->dyn.desc.ln_eps = eps;
   return BCMPC_OK;
 }
 

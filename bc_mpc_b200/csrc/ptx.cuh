@@ -33,9 +33,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded wait: a protocol bug traps (kills the context) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug traps (kills the context) instead of hanging the GPU.  The slow path is out of line so
+// that the dozens of wait sites stay a few instructions each (the rollout kernel is instruction-cache sensitive).
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 6000000000LL) {
@@ -44,6 +44,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // Two barriers at once: both try_waits are in flight together, so two already-complete phases cost one wait latency
@@ -59,8 +62,8 @@ __device__ __forceinline__ void mbar_wait2(uint32_t bar0, uint32_t bar1, uint32_
       : "=r"(d0), "=r"(d1)
       : "r"(bar0), "r"(bar1), "r"(parity), "r"(0x989680u)
       : "memory");
-  if (!d0) mbar_wait(bar0, parity);
-  if (!d1) mbar_wait(bar1, parity);
+  if (!d0) mbar_wait_slow(bar0, parity);
+  if (!d1) mbar_wait_slow(bar1, parity);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads, bulk copies)
@@ -133,6 +136,12 @@ __device__ __forceinline__ float tanh_approx(float x) {   // MUFU.TANH
   return y;
 }
 
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {   // two bf16 lanes per MUFU op
+  uint32_t y;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -189,7 +198,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   return done != 0;
 }
 // wait on a local mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {

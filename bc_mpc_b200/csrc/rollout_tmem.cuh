@@ -59,7 +59,7 @@ constexpr int kNumDBuf = 3;            // accumulators of the layer-2 chunks
 constexpr int kNumDBufL1 = 4;          // layer 1 also borrows [448,512): A2 and D3 are idle while layer 1 runs
 __host__ __device__ constexpr int buf_col(int b) { return b < kNumDBuf ? kColD + kChunk * b : kColA2; }
 constexpr int kD = 20, kA = 6;
-constexpr int kMaxStages = 16, kMaxOps = 40, kMaxChunks = 16;
+constexpr int kMaxStages = 16, kMaxChunks = 16;
 constexpr int kSmemLimit = 232448;     // 227 KB
 constexpr int kA0Bytes = 128 * 128;
 
@@ -88,59 +88,15 @@ constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, 
 constexpr int kPolMaxHidden = 128;     // proposal network: two tanh layers of at most 128 units (MlpPolicy hid_size=128, BCnetwork 128/64)
 
 // ---------------------------------------------------------------------------------------------------------
-// The per-step schedule of the layer-1/2 issuer, computed by ONE constexpr function that both sides use: the host
-// walks it to lay the streamed weight image out in consumption order, the kernel (template <NC, KBS>) unrolls it at
-// compile time.  (A table walked at run time costs ~100 cycles per register-indexed constant load - measured:
-// 1300 cycles per MMA group, 5x its tensor time.)
+// The per-step schedule is fixed arithmetic, the same for every step (all accumulators are drained at a step boundary):
+//   layer 1 : chunk c accumulates in buffer c % 4, issued in pairs (c, c+1); pair n+2 waits for the drains of pair n
+//   layer 2 : chunk c accumulates in buffer c % 3 (waits for the drain of chunk c-3), one MMA group per weight stage;
+//             even chunks are issued by warp 1 from sub-ring 0, odd chunks by warp 3 from sub-ring 1
+//   layer 3 : chunk c as soon as the epilogue has stored hidden-2 chunk c
+// Chunk loops run at run time with compile-time inner unrolling: every tcgen05 operand is then a uniform-register
+// value computed from the loop counter.  (A schedule TABLE walked at run time cost ~100 cycles per register-indexed
+// constant load; a fully unrolled schedule made the kernel 160-200 KB of code and instruction-fetch bound.)
 // ---------------------------------------------------------------------------------------------------------
-enum : int { kKindL1 = 0, kKindL2 = 1 };
-struct SOp {
-  int kind, c;         // layer, hidden chunk
-  int e;               // chunk index in epilogue order (L1: c, L2: nc + c)
-  int buf;             // accumulator buffer
-  int prev;            // chunk (epilogue index) that used `buf` before within this step, -1 = none
-  int kb0, nblk;       // L2: 64-wide k-blocks [kb0, kb0 + nblk) of the chunk
-  int sblk;            // L2: index of k-block kb0 inside its weight stage
-  bool first, last;    // first / last MMA group of the chunk
-  bool sfirst, slast;  // L2: first / last MMA group that reads its weight stage
-};
-struct Schedule {
-  SOp ops[kMaxOps] = {};
-  int n = 0;
-  int nc = 0, kbs = 0, nstg = 0;
-  int buf[kMaxChunks] = {};      // accumulator buffer of chunk e
-};
-// Layer 1 runs in PAIRS of chunks over four accumulators (two pairs in flight; the MMA group of pair n+2 waits for the
-// epilogues of pair n to drain their buffers - one combined wait); layer 2 follows, one MMA group per weight stage (kbs
-// k-blocks), round-robin over three accumulators.  Both layer-2 issuers wait for the last two "hidden-1 ready"
-// barriers before their first chunk, which also tells them that every layer-1 accumulator has been drained.
-constexpr Schedule make_schedule(int nc, int kbs) {
-  Schedule S;
-  S.nc = nc; S.kbs = kbs; S.nstg = (nc + kbs - 1) / kbs;
-  for (int c = 0; c < nc; c += 2) {
-    SOp o{}; o.kind = kKindL1; o.c = c; o.e = c; o.nblk = (c + 1 < nc) ? 2 : 1;      // nblk = chunks in this group
-    o.buf = c % kNumDBufL1; o.prev = c >= kNumDBufL1 ? c - kNumDBufL1 : -1; o.first = o.last = true;
-    S.ops[S.n++] = o;
-  }
-  for (int c = 0; c < nc; ++c) S.buf[c] = c % kNumDBufL1;
-  for (int c = 0; c < nc; ++c) {
-    const int b = c % kNumDBuf;
-    S.buf[nc + c] = b;
-    for (int j = 0; j < S.nstg; ++j) {
-      SOp o{}; o.kind = kKindL2; o.c = c; o.e = nc + c; o.buf = b; o.prev = c >= kNumDBuf ? nc + c - kNumDBuf : -1;
-      o.kb0 = j * kbs; o.nblk = (nc - o.kb0 < kbs) ? nc - o.kb0 : kbs; o.sblk = 0;
-      o.first = j == 0; o.last = j == S.nstg - 1;
-      o.sfirst = o.slast = true;
-      S.ops[S.n++] = o;
-    }
-  }
-  return S;
-}
-template <int NC, int KBS>
-struct Sched {
-  static constexpr Schedule value = make_schedule(NC, KBS);
-};
-
 // k-blocks per streamed weight stage: a whole chunk of W2 per stage for a CTA pair (32 KB per CTA at NC = 8), a
 // quarter chunk for a single CTA (16 KB; the ring must hold several stages next to the resident W1 / W3)
 constexpr int stage_kblocks(int cg, int nc) { return cg == 2 ? nc : (nc + 3) / 4; }
@@ -196,9 +152,8 @@ struct TmArgs {
   float filt_mean[kMaxObs], filt_inv_std[kMaxObs], pol_std[kMaxAct];
   float bp1[kPolMaxHidden], bp2[kPolMaxHidden], bp3[kMaxAct];
 };
-// pipeline trace of CTA (0,0), steps 0..3: [2 per L1/L2 group][2 per L3 group][4 per epilogue chunk][final 2][2 per stage]
-constexpr int kTraceSteps = 4, kTrMma = 0, kTrL3 = 2 * kMaxOps, kTrEpi = kTrL3 + 16, kTrFinal = kTrEpi + 64, kTrProd = kTrFinal + 4,
-              kTraceSlots = kTrProd + 2 * 64;
+// pipeline trace of CTA (0,0), steps 0..3: [2 per L1 pair][2 per L2 chunk][2 per L3 chunk][4 per epilogue chunk][final 8][2 per stage]
+constexpr int kTraceSteps = 4, kTrL1 = 0, kTrL2 = 8, kTrL3 = 24, kTrEpi = 40, kTrFinal = 104, kTrProd = 112, kTraceSlots = kTrProd + 2 * 64;
 
 // ---------------------------------------------------------------------------------------------------------
 // host: weight images
@@ -439,8 +394,6 @@ __device__ __forceinline__ void build_policy_input(const TmArgs& a, uint32_t a0_
 template <int CG, int NC, bool POL>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
   constexpr Layout L = Lay<CG, NC, POL>::value;
-  using SC = Sched<NC, L.kbs>;
-  constexpr int kNumOps = SC::value.n;
   constexpr int kNstg = L.nstg;                               // weight stages per layer-2 chunk
   constexpr int kNumStream = NC * kNstg;                      // weight stages per step
   constexpr int kStagesPerStepR[2] = {((NC + 1) / 2) * kNstg, (NC / 2) * kNstg};   // ... per sub-ring (even / odd chunks)
@@ -513,7 +466,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     for (int h = 0; h < H; ++h) {
       const uint8_t* src = a.stream + (size_t)rank * L.stage_bytes;
       const bool trp = tracing && h < kTraceSteps;
-#pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int r = c & 1;                     // sub-ring: even chunks feed issuer warp 1, odd chunks issuer warp 3
         for (int j = 0; j < kNstg; ++j) {
@@ -536,18 +488,19 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     }
   } else if (warp == 1 || warp == 3) {
     if (leader) {
-      // ===================== layer-1 / layer-2 MMA issuers: the step's schedule unrolled at compile time =====================
-      // warp 1 takes the even layer-2 chunks (chunk 0 in k-block groups that follow the layer-1 epilogues), warp 3 takes
-      // layer 1 and the odd layer-2 chunks.
+      // ===================== MMA issuers =====================
+      // warp 1: the even layer-2 chunks (sub-ring 0); warp 3: proposal network, layer 1, the odd layer-2 chunks (sub-ring 1)
       const int mine = warp == 1 ? 0 : 1;
       ptx::mbar_wait(misc + kOffResFull, 0);
       const uint64_t a0desc = ptx::umma_desc_sw128(base + L.off_a0);
       const uint64_t w1desc = ptx::umma_desc_sw128(base + L.off_res);
+      const uint32_t nst_mine = (uint32_t)L.nst_r[mine], first_mine = (uint32_t)L.first_r[mine];
+      const uint32_t stages_per_step = (uint32_t)kStagesPerStepR[mine];
       for (int h = 0; h < H; ++h) {
         const uint32_t uh = (uint32_t)h, par = uh & 1u;
         const bool trw = tracing && h < kTraceSteps;
-        if constexpr (POL) {
-          if (mine == 1) {
+        if (mine == 1) {
+          if constexpr (POL) {
             // ---- proposal network: policy input (smem) -> tanh layer -> tanh layer -> action means (D3 columns 0..5) ----
             // Accumulators: layer-1 chunks in buffers 0,1; layer-2 chunks in buffers 2,0 (every policy accumulator has
             // been drained before the barrier that lets its buffer's next user start completes).
@@ -593,64 +546,73 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
             }
             __syncwarp();
           }
-        }
-        static_for<kNumOps>([&](auto ic) {
-          constexpr int i = decltype(ic)::value;
-          constexpr SOp op = SC::value.ops[i];
-          constexpr int owner = (op.kind == kKindL2) ? (op.c & 1) : 1;
-          if (owner != mine) return;
-          // ---- operands ready?  (every event completes once per step: parity = step & 1) ----
-          if constexpr (op.kind == kKindL1) {
-            if constexpr (op.c == 0) ptx::mbar_wait(ev + 8u * kEvA0Ready, par);
-            if constexpr (op.prev >= 0) {     // the previous users of this pair of accumulators have been drained
-              if constexpr (op.nblk == 2) ptx::mbar_wait2(ev + 8u * (kEvDEmpty + op.prev), ev + 8u * (kEvDEmpty + op.prev + 1), par);
-              else ptx::mbar_wait(ev + 8u * (kEvDEmpty + op.prev), par);
+          // ---- layer 1: pairs of chunks over four accumulators ----
+          ptx::mbar_wait(ev + 8u * kEvA0Ready, par);
+          for (uint32_t c0 = 0; c0 < (uint32_t)NC; c0 += 2) {
+            const bool two = c0 + 1 < (uint32_t)NC;
+            if (c0 >= (uint32_t)kNumDBufL1) {      // the previous users of this pair of accumulators have been drained
+              if (two) ptx::mbar_wait2(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), ev + 8u * (kEvDEmpty + c0 - kNumDBufL1 + 1), par);
+              else ptx::mbar_wait(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), par);
             }
-          } else {
-            if constexpr (op.first && op.prev >= 0) ptx::mbar_wait(ev + 8u * (kEvDEmpty + op.prev), par);   // previous user of the accumulator drained
-            if constexpr (op.c < 2 && op.first) {
-              // first layer-2 chunk of this issuer in the step: all of A1 must be in TMEM.  Each epilogue group signals its
-              // chunks in order (group 0 the even ones, group 1 the odd ones), so the last two barriers imply the rest.
-              if constexpr (NC >= 2) ptx::mbar_wait2(ev + 8u * (kEvA1Ready + NC - 1), ev + 8u * (kEvA1Ready + NC - 2), par);
-              else ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 1), par);
-            }
-          }
-          // weight stage of this group: sub-ring r = chunk parity, stages consumed in (chunk, stage-of-chunk) order
-          constexpr int r = op.c & 1;
-          constexpr int sidx = (op.c / 2) * kNstg + op.kb0 / L.kbs;
-          const uint32_t gs = uh * kStagesPerStepR[r] + sidx;
-          const uint32_t stage = (uint32_t)L.first_r[r] + gs % (uint32_t)L.nst_r[r], phase = (gs / (uint32_t)L.nst_r[r]) & 1u;
-          if constexpr (op.kind == kKindL2 && op.sfirst) ptx::mbar_wait(misc + kOffWFull + 8u * stage, phase);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            if (trw) a.trace[h * kTraceSlots + kTrMma + 2 * i] = clock64();
-            if constexpr (op.kind == kKindL1) {
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              if (trw) a.trace[h * kTraceSlots + kTrL1 + c0] = clock64();
               constexpr int nks = (kD + kA + 2 + 15) / 16;
 #pragma unroll
-              for (int t = 0; t < op.nblk; ++t) {
-                const uint32_t d = (uint32_t)buf_col((op.c + t) % kNumDBufL1);
+              for (uint32_t t = 0; t < 2; ++t) {
+                if (t == 0 || two) {
+                  const uint32_t c = c0 + t, bsel = c % (uint32_t)kNumDBufL1;
+                  const uint32_t d = bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2;
 #pragma unroll
-                for (int ks = 0; ks < nks; ++ks)
-                  ptx::umma_ss<CG>(d, a0desc + 2u * ks, w1desc + (uint64_t)((op.c + t) * (L.blk_h >> 4) + 2u * ks), kIdescH, ks > 0 ? 1u : 0u);
-                ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + op.c + t));
+                  for (int ks = 0; ks < nks; ++ks)
+                    ptx::umma_ss<CG>(d, a0desc + 2u * ks, w1desc + (uint64_t)(c * (L.blk_h >> 4) + 2u * ks), kIdescH, ks > 0 ? 1u : 0u);
+                  ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + c));
+                }
               }
-            } else {
-              constexpr uint32_t d = buf_col(op.buf);
-              const uint64_t bdesc = ptx::umma_desc_sw128(base + L.off_ring + stage * L.stage_bytes);
-#pragma unroll
-              for (int t = 0; t < op.nblk; ++t) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  ptx::umma_ts<CG>(d, kColA1 + (op.kb0 + t) * 32 + ks * 8, bdesc + (uint64_t)((op.sblk + t) * (L.blk_h >> 4) + 2u * ks),
-                                   kIdescH, (op.first && t == 0 && ks == 0) ? 0u : 1u);
-              }
-              if constexpr (op.slast) ptx::umma_commit_cg<CG>(misc + kOffWEmpty + 8u * stage);
-              if constexpr (op.last) ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + op.e));
+              if (trw) a.trace[h * kTraceSlots + kTrL1 + c0 + 1] = clock64();
             }
-            if (trw) a.trace[h * kTraceSlots + kTrMma + 2 * i + 1] = clock64();
+            __syncwarp();
           }
-          __syncwarp();
-        });
+        }
+        // ---- layer 2: this issuer's chunks, one MMA group per weight stage ----
+        for (uint32_t c = (uint32_t)mine; c < (uint32_t)NC; c += 2) {
+          if (c < 2) {
+            // first layer-2 chunk of this issuer in the step: all of A1 must be in TMEM (which also means that every
+            // layer-1 accumulator has been drained).  Each epilogue group signals its chunks in order, so the last two
+            // barriers imply the rest.
+            if constexpr (NC >= 2) ptx::mbar_wait2(ev + 8u * (kEvA1Ready + NC - 1), ev + 8u * (kEvA1Ready + NC - 2), par);
+            else ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 1), par);
+          }
+          if (c >= (uint32_t)kNumDBuf) ptx::mbar_wait(ev + 8u * (kEvDEmpty + NC + c - kNumDBuf), par);   // previous user of the accumulator drained
+          const uint32_t d = (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf);
+          const uint32_t gs0 = uh * stages_per_step + (c >> 1) * (uint32_t)kNstg;
+#pragma unroll
+          for (int j = 0; j < kNstg; ++j) {
+            const uint32_t gs = gs0 + (uint32_t)j, stage = first_mine + gs % nst_mine, phase = (gs / nst_mine) & 1u;
+            ptx::mbar_wait(misc + kOffWFull + 8u * stage, phase);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              if (trw && j == 0) a.trace[h * kTraceSlots + kTrL2 + 2 * c] = clock64();
+              const uint64_t bdesc = ptx::umma_desc_sw128(base + L.off_ring + stage * L.stage_bytes);
+              const int nblk = (NC - j * L.kbs < L.kbs) ? NC - j * L.kbs : L.kbs;
+#pragma unroll
+              for (int t = 0; t < L.kbs; ++t) {
+                if (t < nblk) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    ptx::umma_ts<CG>(d, kColA1 + (j * L.kbs + t) * 32 + ks * 8, bdesc + (uint64_t)(t * (L.blk_h >> 4) + 2u * ks), kIdescH,
+                                     (j == 0 && t == 0 && ks == 0) ? 0u : 1u);
+                }
+              }
+              ptx::umma_commit_cg<CG>(misc + kOffWEmpty + 8u * stage);
+              if (j == kNstg - 1) {
+                ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + NC + c));
+                if (trw) a.trace[h * kTraceSlots + kTrL2 + 2 * c + 1] = clock64();
+              }
+            }
+            __syncwarp();
+          }
+        }
       }
     } else if (warp == 1) {
       // ===================== peer CTA: tell the leader when this CTA's weight halves have landed =====================
@@ -660,7 +622,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       __syncwarp();
       uint32_t stage[2] = {0, 0}, phase[2] = {0, 0};
       for (int h = 0; h < H; ++h) {
-#pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int r = c & 1;
           for (int j = 0; j < kNstg; ++j) {
@@ -681,8 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       for (int h = 0; h < H; ++h) {
         const uint32_t uh = (uint32_t)h;
         const bool trw = tracing && h < kTraceSteps;
-        static_for<NC>([&](auto cc) {
-          constexpr int c = decltype(cc)::value;
+        for (uint32_t c = 0; c < (uint32_t)NC; ++c) {
           ptx::mbar_wait(ev + 8u * (kEvA2Ready + c), uh & 1u);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
@@ -690,12 +650,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               ptx::umma_ts<CG>(kColD3, kColA2 + ks * 8, w3desc + (uint64_t)(c * (L.blk_o >> 4) + 2u * ks), kIdescO, (c == 0 && ks == 0) ? 0u : 1u);
-            if constexpr (c == NC - 1) ptx::umma_commit_cg<CG>(ev + 8u * kEvD3Full);
+            if (c == (uint32_t)NC - 1) ptx::umma_commit_cg<CG>(ev + 8u * kEvD3Full);
             else ptx::umma_commit_cg<CG>(ev + 8u * (kEvA2Empty + c));
             if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c + 1] = clock64();
           }
           __syncwarp();
-        });
+        }
       }
     }
   } else if (warp >= 4) {
@@ -737,6 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (is_final) {
           build_policy_input(a, a0_row, row, s);
           publish(kEvAp0Ready);
+          if (trh) a.trace[h * kTraceSlots + kTrFinal + 2] = clock64();
         }
         // one 64-unit chunk of a tanh layer: accumulator + bias -> tanh -> bf16 -> TMEM operand of the next policy layer
         auto pol_chunk = [&](auto lc, auto jc) {
@@ -745,25 +706,28 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           constexpr uint32_t dst = kColA1 + (layer == 1 ? 0u : 64u) + 32u * j;
           ptx::mbar_wait(ev + 8u * (kEvPdFull + (layer - 1) * 2 + j), uh & 1u);
           ptx::tc_fence_after();
+          if (trh) a.trace[h * kTraceSlots + kTrFinal + 1 + 2 * layer] = clock64();
           uint32_t v0[32], v1[32], w0[16], w1[16];
           ptx::tmem_ld32(lane_off + col, v0);
           ptx::tmem_ld32(lane_off + col + 32u, v1);
           ptx::tmem_ld_wait();
           auto bias_at = [&](int idx) { if constexpr (layer == 1) return a.bp1[idx]; else return a.bp2[idx]; };
+          // bias, round to bf16, then one MUFU.TANH per two units (tanh.approx.bf16x2): the layer is MUFU-bound otherwise
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            w0[i] = pack_bf16(ptx::tanh_approx(__uint_as_float(v0[2 * i]) + bias_at(64 * j + 2 * i)),
-                              ptx::tanh_approx(__uint_as_float(v0[2 * i + 1]) + bias_at(64 * j + 2 * i + 1)));
+            w0[i] = ptx::tanh_bf16x2(pack_bf16(__uint_as_float(v0[2 * i]) + bias_at(64 * j + 2 * i),
+                                               __uint_as_float(v0[2 * i + 1]) + bias_at(64 * j + 2 * i + 1)));
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            w1[i] = pack_bf16(ptx::tanh_approx(__uint_as_float(v1[2 * i]) + bias_at(64 * j + 32 + 2 * i)),
-                              ptx::tanh_approx(__uint_as_float(v1[2 * i + 1]) + bias_at(64 * j + 32 + 2 * i + 1)));
+            w1[i] = ptx::tanh_bf16x2(pack_bf16(__uint_as_float(v1[2 * i]) + bias_at(64 * j + 32 + 2 * i),
+                                               __uint_as_float(v1[2 * i + 1]) + bias_at(64 * j + 32 + 2 * i + 1)));
           ptx::tmem_st16(lane_off + dst, w0);
           ptx::tmem_st16(lane_off + dst + 16u, w1);
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) arrive_leader((layer == 1 ? kEvAp1Ready : kEvAp2Ready) + j);
+          if (trh) a.trace[h * kTraceSlots + kTrFinal + 2 + 2 * layer] = clock64();
         };
         // group g takes chunk g of both hidden layers
         if (g == 0) pol_chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
@@ -773,6 +737,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (is_final) {
           ptx::mbar_wait(ev + 8u * kEvPolFull, uh & 1u);
           ptx::tc_fence_after();
+          if (trh) a.trace[h * kTraceSlots + kTrFinal + 7] = clock64();
           uint32_t v[32];
           ptx::tmem_ld32(lane_off + (uint32_t)kColD3, v);
           ptx::tmem_ld_wait();
@@ -803,16 +768,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (trh) a.trace[h * kTraceSlots + kTrFinal + 1] = clock64();
       }
       // one accumulator chunk: TMEM -> registers, ReLU + bf16, -> TMEM operand of the next layer
-      auto chunk = [&](auto ec) {
-        constexpr int e = decltype(ec)::value;
-        constexpr bool l2 = e >= NC;
-        constexpr int c = l2 ? e - NC : e;
-        constexpr int buf = SC::value.buf[e];
-        constexpr uint32_t dst = l2 ? kColA2 : kColA1 + 32 * c;
+      auto chunk = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, bool l2, uint32_t c) {
         if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e] = clock64();
         uint32_t v0[32], v1[32], w0[16], w1[16];
-        ptx::tmem_ld32(lane_off + (uint32_t)buf_col(buf), v0);
-        ptx::tmem_ld32(lane_off + (uint32_t)(buf_col(buf) + 32), v1);
+        ptx::tmem_ld32(lane_off + col, v0);
+        ptx::tmem_ld32(lane_off + col + 32u, v1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -822,7 +782,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         for (int i = 0; i < 16; ++i) w0[i] = pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
 #pragma unroll
         for (int i = 0; i < 16; ++i) w1[i] = pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-        if constexpr (l2 && c > 0) {
+        if (l2 && c > 0) {
           ptx::mbar_wait(ev + 8u * (kEvA2Empty + c - 1), uh & 1u);   // layer 3 has consumed the previous chunk
           ptx::tc_fence_after();
         }
@@ -832,32 +792,32 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) arrive_leader((l2 ? kEvA2Ready : kEvA1Ready) + c);
+        if (lane == 0) arrive_leader(ready_id);
         if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e + 3] = clock64();
       };
       // layer 1: the groups take alternate PAIRS of chunks (the pairs the issuer commits together): one combined wait
-      static_for<(NC + 1) / 2>([&](auto pc) {
-        constexpr int pr = decltype(pc)::value, c0 = 2 * pr;
-        if ((pr & 1) == g) {
-          if constexpr (c0 + 1 < NC) ptx::mbar_wait2(ev + 8u * (kEvDFull + c0), ev + 8u * (kEvDFull + c0 + 1), uh & 1u);
-          else ptx::mbar_wait(ev + 8u * (kEvDFull + c0), uh & 1u);
-          ptx::tc_fence_after();
-          chunk(std::integral_constant<int, c0>{});
-          if constexpr (c0 + 1 < NC) chunk(std::integral_constant<int, c0 + 1>{});
+      for (uint32_t c0 = 2u * (uint32_t)g; c0 < (uint32_t)NC; c0 += 4) {
+        const bool two = c0 + 1 < (uint32_t)NC;
+        if (two) ptx::mbar_wait2(ev + 8u * (kEvDFull + c0), ev + 8u * (kEvDFull + c0 + 1), uh & 1u);
+        else ptx::mbar_wait(ev + 8u * (kEvDFull + c0), uh & 1u);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (uint32_t c = c0; c < c0 + (two ? 2u : 1u); ++c) {
+          const uint32_t bsel = c % (uint32_t)kNumDBufL1;
+          chunk(c, bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2, (uint32_t)kColA1 + 32u * c,
+                (uint32_t)kEvA1Ready + c, false, c);
         }
-      });
+      }
       // the next step's randomness is drawn between the layer-1 and layer-2 chunks, where these warps have slack (at the
       // top of the step it delays the first layer-1 epilogue, at the bottom the state update)
       if (is_final && h + 1 < H) get_noise(a, b, h + 1, kc, z);
       // layer 2: alternate chunks
-      static_for<NC>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        if ((c & 1) == g) {
-          ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u);
-          ptx::tc_fence_after();
-          chunk(std::integral_constant<int, NC + c>{});
-        }
-      });
+#pragma unroll 1
+      for (uint32_t c = (uint32_t)g; c < (uint32_t)NC; c += 2) {
+        ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u);
+        ptx::tc_fence_after();
+        chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), (uint32_t)kColA2, (uint32_t)kEvA2Ready + c, true, c);
+      }
       if (is_final) {
         ptx::mbar_wait(ev + 8u * kEvD3Full, uh & 1u);
         ptx::tc_fence_after();

@@ -17,6 +17,9 @@ struct MlpDesc {
   int in_pad[kMaxLayers], out_pad[kMaxLayers];   // padded to multiples of 4 (zero filled)
   const float* W[kMaxLayers];                    // [in_pad][out_pad] row-major (TF kernel layout)
   const float* b[kMaxLayers];                    // [out_pad]
+  const float* ln_gamma[kMaxLayers];             // LayerNorm after the activation of hidden layer l (nullptr = none)
+  const float* ln_beta[kMaxLayers];
+  float ln_eps;
 };
 
 struct VerifyArgs {
@@ -88,6 +91,28 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
   }
 }
 
+// tf.contrib.layers.layer_norm over the last axis (dynamics.py:68-69), float32: one warp per row,
+// mean, then mean of squared deviations, then (x - mean) * rsqrt(var + eps) * gamma + beta.  Padding columns stay 0.
+template <int M>
+__device__ __forceinline__ void layer_norm_rows(float* buf, int n, int n_pad, int ld, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < M; r += kVerifyThreads / 32) {
+    float* x = buf + r * ld;
+    float sum = 0.f;
+    for (int i = lane; i < n; i += 32) sum += x[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float mean = sum / (float)n;
+    float sq = 0.f;
+    for (int i = lane; i < n; i += 32) { const float d = x[i] - mean; sq = fmaf(d, d, sq); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    const float inv = 1.0f / sqrtf(sq / (float)n + eps);
+    for (int i = lane; i < n_pad; i += 32) x[i] = i < n ? (x[i] - mean) * inv * gamma[i] + beta[i] : 0.f;
+  }
+}
+
 // Runs an MLP whose input already sits in bufA (zero padded to in_pad[0]); hidden layers use
 // `hidden_act`, the last layer is linear.  Returns the buffer holding the output.
 template <int M>
@@ -98,6 +123,10 @@ __device__ __forceinline__ float* run_mlp(const MlpDesc& m, int hidden_act, floa
     const int act = (l + 1 < m.n_layers) ? hidden_act : -1;
     dense_layer<M>(m.W[l], m.b[l], m.in_pad[l], m.out_pad[l], in, out, ld, act);
     __syncthreads();
+    if (l + 1 < m.n_layers && m.ln_gamma[l] != nullptr) {
+      layer_norm_rows<M>(out, m.out_dim[l], m.out_pad[l], ld, m.ln_gamma[l], m.ln_beta[l], m.ln_eps);
+      __syncthreads();
+    }
     float* t = in; in = out; out = t;
   }
   return in;

@@ -10,7 +10,7 @@ from .planner import Planner
 
 class NNDynamicsModel:
     def __init__(self, env, n_layers, size, activation="relu", output_activation=None, normalization=None,
-                 batch_size=None, iterations=None, learning_rate=None, sess=None, precision="fp32"):
+                 batch_size=None, iterations=None, learning_rate=None, sess=None, precision="fp32", layer_norm=False):
         if output_activation is not None:
             raise NotImplementedError("output_activation must be None (train_mpc_ppo.py:540)")
         self.env = env
@@ -24,21 +24,31 @@ class NNDynamicsModel:
             (self.mean_obs, self.std_obs, self.mean_action, self.std_action, self.mean_reward, self.std_reward,
              self.mean_nxt_state, self.std_nxt_state, self.mean_deltas, self.std_deltas) = normalization  # dynamics.py:41
         self.weights = None
+        self.layer_norm = layer_norm           # FLAGS.LAYER_NORM of the reference (dynamics.py:68-69)
+        self.layer_norm_params = None          # [(gamma, beta)] per hidden layer
         self.version = 0           # bumped on every weight change; controllers re-upload lazily
         self.precision = precision
         self._predictor = None
 
     # -- weight hand-off (replaces tf variables / fit) ------------------------------------------------
-    def set_weights(self, weights):
+    def set_weights(self, weights, layer_norm_params=None):
         self.weights = [(np.asarray(w, np.float32), np.asarray(b, np.float32)) for w, b in weights]
+        if self.layer_norm:
+            if layer_norm_params is None:
+                raise ValueError("this model was built with layer_norm=True: pass [(gamma, beta), ...] per hidden layer")
+            self.layer_norm_params = [(np.asarray(g, np.float32), np.asarray(b, np.float32)) for g, b in layer_norm_params]
         self.version += 1
         self._predictor = None
 
     def load_vars(self, var_dict):
         """var_dict: {tf variable name: ndarray} as written by logz.pickle_tf_vars (logz.py:78-85)."""
         names = ["dense"] + [f"dense_{i}" for i in range(1, self.n_layers + 1)]
+        ln = None
+        if self.layer_norm:   # tf.contrib.layers.layer_norm variable names [from memory - not in the reference tree]
+            lnn = ["LayerNorm"] + [f"LayerNorm_{i}" for i in range(1, self.n_layers)]
+            ln = [(var_dict[f"{self.scope}/{n}/gamma:0"], var_dict[f"{self.scope}/{n}/beta:0"]) for n in lnn]
         self.set_weights([(var_dict[f"{self.scope}/{n}/kernel:0"], var_dict[f"{self.scope}/{n}/bias:0"])
-                          for n in names])
+                          for n in names], ln)
 
     def normalization6(self):
         return (self.mean_obs, self.std_obs, self.mean_action, self.std_action, self.mean_deltas, self.std_deltas)
@@ -56,6 +66,8 @@ class NNDynamicsModel:
             p = Planner(self.obs_dim, self.act_dim, self.n_layers, self.size, self.activation, num_paths=1,
                         horizon=1, precision="fp32")
             p.set_dynamics(self.weights)
+            if self.layer_norm:
+                p.set_layer_norm(self.layer_norm_params)
             p.set_normalization(*self.normalization6())
             self._predictor = p
         return self._predictor.predict(s, a)

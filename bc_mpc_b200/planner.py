@@ -81,6 +81,19 @@ class Planner:
                 raise ValueError(f"layer {i}: expected kernel {(sizes[i], sizes[i + 1])}, got {w.shape} / {b.shape}")
         self._ck(self._lib.bcmpc_set_dynamics(self._h, L.ptr_array(Ws), L.ptr_array(bs), len(Ws)))
 
+    def set_layer_norm(self, params, eps=1e-12):
+        """LayerNorm after every hidden activation (dynamics.py:68-69): params = [(gamma[size], beta[size]), ...] per
+        hidden layer, or None to switch it off.  Call after set_dynamics (new weights reset it)."""
+        if params is None:
+            self._ck(self._lib.bcmpc_set_layer_norm(self._h, None, None, 0, C.c_float(eps)))
+            return
+        gs = [np.ascontiguousarray(g, np.float32).reshape(-1) for g, _ in params]
+        bs = [np.ascontiguousarray(b, np.float32).reshape(-1) for _, b in params]
+        for g, b in zip(gs, bs):
+            if g.shape != (self.cfg.hidden_size,) or b.shape != (self.cfg.hidden_size,):
+                raise ValueError(f"LayerNorm gamma/beta must be [{self.cfg.hidden_size}]")
+        self._ck(self._lib.bcmpc_set_layer_norm(self._h, L.ptr_array(gs), L.ptr_array(bs), len(gs), C.c_float(eps)))
+
     def set_normalization(self, mean_obs, std_obs, mean_action, std_action, mean_deltas, std_deltas):
         a = [_f64(mean_obs, (self.D,)), _f64(std_obs, (self.D,)), _f64(mean_action, (self.A,)),
              _f64(std_action, (self.A,)), _f64(mean_deltas, (self.D,)), _f64(std_deltas, (self.D,))]

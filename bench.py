@@ -101,6 +101,54 @@ def cpu_baseline(budget_s=12.0):
                       f"{dt:.1f} s; plans/s = {n / dt:.2f}; TF-less restatement = optimistic stand-in for the TF CPU path"}
 
 
+def extras():
+    """Not part of the contract line's headline: the other BASELINE.json configs on 1 GPU, a few calls each.
+    configs[0]/[1] are single-plan latency cases (host-buffer C-ABI call, copies included); configs[3] is the
+    policy-guided variant (proposal network + Gaussian noise fused with the rollout), 16 states per call."""
+    from bc_mpc_b200 import Planner
+    O, rng, norm, weights = problem()
+    pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
+    state = O.synthetic_state(rng, norm)
+    out = {}
+
+    def make(K, H, precision, proposal="uniform", B=1):
+        pl = Planner(20, 6, 2, HIDDEN[0], "relu", num_paths=K, horizon=H, max_states=B, precision=precision, proposal=proposal)
+        pl.set_dynamics(weights)
+        pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"],
+                             norm["mean_deltas"], norm["std_deltas"])
+        if proposal != "uniform":
+            pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+        return pl
+
+    def time_plans(pl, states, n=20):
+        for i in range(3):
+            pl.plan(states, seed=i)
+        t0 = time.perf_counter()
+        for i in range(n):
+            pl.plan(states, seed=100 + i)
+        return (time.perf_counter() - t0) / n
+
+    for tag, K, H, prec in (("configs0_K1000_H15_bf16", 1000, 15, "bf16"), ("configs0_K1000_H15_fp32_verify", 1000, 15, "fp32"),
+                            ("configs1_K4096_H15_fp32_verify", 4096, 15, "fp32"), ("configs1_K4096_H15_bf16", 4096, 15, "bf16")):
+        pl = make(K, H, prec)
+        dt = time_plans(pl, state)
+        out[tag] = {"plan_latency_ms": 1e3 * dt, "plans_per_s": 1 / dt, "transitions_per_s": K * H / dt}
+        pl.close()
+    B, K, H = 16, 8192, 15
+    pl = make(K, H, "bf16", "policy_gaussian", B)
+    states = norm["mean_obs"] + norm["std_obs"] * np.random.default_rng(2).standard_normal((B, 20))
+    states[:, 18] = 0.0
+    pl.enable_timing(True)
+    dt = time_plans(pl, states, 10)
+    k_ms = pl.last_kernel_ms()
+    flop = FLOP_PER_TRANSITION + 2 * (20 * 128 + 128 * 128 + 128 * 6)
+    out["configs3_policy_gaussian_K8192_H15_bf16_x16states"] = {
+        "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
+        "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
+    pl.close()
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; TensorFlow is not installable here) on
     this arm's config, each step a bounded sample: 1 root state x K=4096 x H=20."""
@@ -262,6 +310,11 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_extras:
+            try:
+                line["extras"] = extras()
+            except Exception as e:  # extras never break the contract line
+                line["extras"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -275,6 +328,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

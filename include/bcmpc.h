@@ -100,6 +100,13 @@ int bcmpc_destroy(bcmpc_handle* h);
 /* NNDynamicsModel weights (dynamics.py:54-71).  n_layers = n_hidden + 1; W[i] is [in_i,out_i]. */
 int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int32_t n_layers);
 
+/* LayerNorm variant of NNDynamicsModel (dynamics.py:68-69, FLAGS.LAYER_NORM, the default of train_mpc_ppo.py:52):
+ * tf.contrib.layers.layer_norm AFTER the activation of every hidden layer - moments over the last axis, centre and
+ * scale.  gamma[l], beta[l] are [hidden_size] for hidden layer l (n_hidden of them); eps is the variance epsilon
+ * (1e-12 in tf.contrib).  gamma == NULL switches LayerNorm off.  Verification mode only: with BCMPC_PREC_BF16_FAST
+ * the call returns BCMPC_ERR_UNSUPPORTED. */
+int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps);
+
 /* The six members of the normalisation 10-tuple that predict uses (dynamics.py:41,109-113). */
 int bcmpc_set_normalization(bcmpc_handle* h, const double* mean_obs, const double* std_obs,
                             const double* mean_act, const double* std_act,

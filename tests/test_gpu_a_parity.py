@@ -87,6 +87,28 @@ def test_config_1_2_verify_mode(seed, K, H):
     assert abs(rec["cost"] - dbg["costs"][dbg["argmin"]]) < 1e-3
 
 
+def test_layer_norm_dynamics_variant():
+    """FLAGS.LAYER_NORM = True, the default of train_mpc_ppo.py:52: LayerNorm after every hidden ReLU (dynamics.py:68-69)."""
+    K, H, S = 1000, 15, 256
+    rng, norm, state, pl, mpc = make_pair(17, (S, S), K, H)
+    ln = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(2)]
+    pl.set_layer_norm(ln)
+    mpc.dyn_model.layer_norm = ln
+    actions = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    assert scaled_rel_err(so, dbg["states"], state_scale(norm)).max() < TOL
+    rec = pl.plan(state, inj=actions)[0]
+    assert rec["index"] == dbg["argmin"] and np.array_equal(rec["action"][:6], act)
+    pl.set_layer_norm(None)                      # switching it off gives the plain network again
+    mpc.dyn_model.layer_norm = None
+    so2, _, _ = pl.rollout_debug(state, actions)
+    assert scaled_rel_err(so2, mpc.rollout(state, actions)[0], state_scale(norm)).max() < TOL
+    assert np.abs(so2 - so).max() > 1e-3
+    with pytest.raises(RuntimeError, match="LayerNorm"):
+        make_pair(17, (S, S), 128, 2, precision="bf16")[3].set_layer_norm(ln)
+
+
 def test_threshold_and_tie_cases():
     K, H = 256, 4
     rng, norm, state, pl, mpc = make_pair(11, (64, 64), K, H)
