@@ -64,6 +64,7 @@ struct bcmpc_handle {
   unsigned long long* d_trace = nullptr;
   bool tm_ready = false;
   int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
+  uint32_t tm_hint_chain = 0x989680u;   // BCMPC_TC_HINT_CHAIN: mbarrier try_wait suspend hint (ns) on the per-step dependency chain
   std::string trace_path; // BCMPC_TC_TRACE: dump the pipeline trace of CTA (0,0) after every launch
 };
 
@@ -214,6 +215,7 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   memset(&a, 0, sizeof a);
   a.p = p;
   a.res = h->d_res; a.stream = h->d_stream; a.trace = h->d_trace;
+  a.hint_chain = h->tm_hint_chain;
   for (int d = 0; d < h->cfg.obs_dim; ++d) {
     a.mean_obs[d] = (float)h->norm.mean_obs[d];
     a.inv_den_obs[d] = (float)(1.0 / h->norm.den_obs[d]);
@@ -339,6 +341,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   if (h->cfg.total_paths <= 0) h->cfg.total_paths = c.path_offset + c.num_paths;
   if (const char* s = getenv("BCMPC_TC_CG")) h->tm_cg = atoi(s) == 2 ? 2 : 1;
   if (const char* s = getenv("BCMPC_TC_TRACE")) h->trace_path = s;
+  if (const char* s = getenv("BCMPC_TC_HINT_CHAIN")) h->tm_hint_chain = (uint32_t)strtoul(s, nullptr, 0);
   cudaError_t e = cudaSetDevice(c.device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);

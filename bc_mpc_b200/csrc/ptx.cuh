@@ -22,22 +22,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (wake-up ~60 cycles
 // after the arrive) or the hint expires, instead of burning issue slots that the epilogue warps on the same SM
 // sub-partition need (measured: the per-step state update ran 2.5x slower next to spinning waiters).
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+constexpr uint32_t kSleepHint = 0x989680u;
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uint32_t hint = kSleepHint) {
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done)
-      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "r"(bar), "r"(parity), "r"(hint)
       : "memory");
   return done != 0;
 }
 // Bounded wait: a protocol bug traps (kills the context) instead of hanging the GPU.  The slow path is out of line so
 // that the dozens of wait sites stay a few instructions each (the rollout kernel is instruction-cache sensitive).
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t hint) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait(bar, parity, hint)) {
     if (clock64() - t0 > 6000000000LL) {
       printf("bcmpc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);
@@ -45,13 +46,13 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint = kSleepHint) {
+  if (!mbar_try_wait(bar, parity, hint)) mbar_wait_slow(bar, parity, hint);
 }
 
 // Two barriers at once: both try_waits are in flight together, so two already-complete phases cost one wait latency
 // (~100 cycles) instead of two.
-__device__ __forceinline__ void mbar_wait2(uint32_t bar0, uint32_t bar1, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait2(uint32_t bar0, uint32_t bar1, uint32_t parity, uint32_t hint = kSleepHint) {
   uint32_t d0, d1;
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
@@ -60,10 +61,10 @@ __device__ __forceinline__ void mbar_wait2(uint32_t bar0, uint32_t bar1, uint32_
       "selp.u32 %0, 1, 0, p;\n\t"
       "selp.u32 %1, 1, 0, q;\n\t}"
       : "=r"(d0), "=r"(d1)
-      : "r"(bar0), "r"(bar1), "r"(parity), "r"(0x989680u)
+      : "r"(bar0), "r"(bar1), "r"(parity), "r"(hint)
       : "memory");
-  if (!d0) mbar_wait_slow(bar0, parity);
-  if (!d1) mbar_wait_slow(bar1, parity);
+  if (!d0) mbar_wait_slow(bar0, parity, hint);
+  if (!d1) mbar_wait_slow(bar1, parity, hint);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads, bulk copies)

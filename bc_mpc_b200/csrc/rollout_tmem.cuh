@@ -142,6 +142,7 @@ struct TmArgs {
   const uint8_t* res;            // resident image   [CG][res_bytes]
   const uint8_t* stream;         // streamed image: per weight stage, in consumption order, [CG][stage_bytes]
   unsigned long long* trace;     // optional pipeline trace (tools/tc_trace.py), nullptr = off
+  uint32_t hint_chain;           // try_wait suspend hint (ns) of the waits on the per-step dependency chain
   float mean_obs[kMaxObs], inv_den_obs[kMaxObs], mean_delta[kMaxObs], std_delta[kMaxObs];
   float mean_act[kMaxAct], inv_den_act[kMaxAct], low[kMaxAct], span[kMaxAct];
   // proposal network (policy-guided shooting); unused with uniform shooting
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   // TMEM address a compile-time value.
   if (*s_tmem != 0u) { if (tid == 0) printf("bcmpc: unexpected TMEM base 0x%x\n", *s_tmem); __trap(); }
   const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  const uint32_t hc = a.hint_chain;
 
   // Warps 0-3 run their loops warp-uniformly and elect one lane only for the instructions themselves: every
   // descriptor / address is then a uniform-register value (an `if (lane == 0)` role costs a divergent-value waterfall
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
             // been drained before the barrier that lets its buffer's next user start completes).
             const uint64_t wpdesc = ptx::umma_desc_sw128(base + L.off_pol);
             const uint32_t np1 = (uint32_t)a.np1, np2 = (uint32_t)a.np2;
-            ptx::mbar_wait(ev + 8u * kEvAp0Ready, par);
+            ptx::mbar_wait(ev + 8u * kEvAp0Ready, par, hc);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               for (uint32_t j = 0; j < np1; ++j) {
@@ -518,8 +520,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
               }
             }
             __syncwarp();
-            if (np1 > 1) ptx::mbar_wait2(ev + 8u * kEvAp1Ready, ev + 8u * (kEvAp1Ready + 1), par);
-            else ptx::mbar_wait(ev + 8u * kEvAp1Ready, par);
+            if (np1 > 1) ptx::mbar_wait2(ev + 8u * kEvAp1Ready, ev + 8u * (kEvAp1Ready + 1), par, hc);
+            else ptx::mbar_wait(ev + 8u * kEvAp1Ready, par, hc);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               for (uint32_t j = 0; j < np2; ++j) {
@@ -533,8 +535,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
               }
             }
             __syncwarp();
-            if (np2 > 1) ptx::mbar_wait2(ev + 8u * kEvAp2Ready, ev + 8u * (kEvAp2Ready + 1), par);
-            else ptx::mbar_wait(ev + 8u * kEvAp2Ready, par);
+            if (np2 > 1) ptx::mbar_wait2(ev + 8u * kEvAp2Ready, ev + 8u * (kEvAp2Ready + 1), par, hc);
+            else ptx::mbar_wait(ev + 8u * kEvAp2Ready, par, hc);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               for (uint32_t kb = 0; kb < np2; ++kb)
@@ -547,12 +549,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
             __syncwarp();
           }
           // ---- layer 1: pairs of chunks over four accumulators ----
-          ptx::mbar_wait(ev + 8u * kEvA0Ready, par);
+          ptx::mbar_wait(ev + 8u * kEvA0Ready, par, hc);
           for (uint32_t c0 = 0; c0 < (uint32_t)NC; c0 += 2) {
             const bool two = c0 + 1 < (uint32_t)NC;
             if (c0 >= (uint32_t)kNumDBufL1) {      // the previous users of this pair of accumulators have been drained
-              if (two) ptx::mbar_wait2(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), ev + 8u * (kEvDEmpty + c0 - kNumDBufL1 + 1), par);
-              else ptx::mbar_wait(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), par);
+              if (two) ptx::mbar_wait2(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), ev + 8u * (kEvDEmpty + c0 - kNumDBufL1 + 1), par, hc);
+              else ptx::mbar_wait(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), par, hc);
             }
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
@@ -580,10 +582,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
             // first layer-2 chunk of this issuer in the step: all of A1 must be in TMEM (which also means that every
             // layer-1 accumulator has been drained).  Each epilogue group signals its chunks in order, so the last two
             // barriers imply the rest.
-            if constexpr (NC >= 2) ptx::mbar_wait2(ev + 8u * (kEvA1Ready + NC - 1), ev + 8u * (kEvA1Ready + NC - 2), par);
-            else ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 1), par);
+            if constexpr (NC >= 2) ptx::mbar_wait2(ev + 8u * (kEvA1Ready + NC - 1), ev + 8u * (kEvA1Ready + NC - 2), par, hc);
+            else ptx::mbar_wait(ev + 8u * (kEvA1Ready + NC - 1), par, hc);
           }
-          if (c >= (uint32_t)kNumDBuf) ptx::mbar_wait(ev + 8u * (kEvDEmpty + NC + c - kNumDBuf), par);   // previous user of the accumulator drained
+          if (c >= (uint32_t)kNumDBuf) ptx::mbar_wait(ev + 8u * (kEvDEmpty + NC + c - kNumDBuf), par, hc);   // previous user of the accumulator drained
           const uint32_t d = (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf);
           const uint32_t gs0 = uh * stages_per_step + (c >> 1) * (uint32_t)kNstg;
 #pragma unroll
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         const uint32_t uh = (uint32_t)h;
         const bool trw = tracing && h < kTraceSteps;
         for (uint32_t c = 0; c < (uint32_t)NC; ++c) {
-          ptx::mbar_wait(ev + 8u * (kEvA2Ready + c), uh & 1u);
+          ptx::mbar_wait(ev + 8u * (kEvA2Ready + c), uh & 1u, hc);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c] = clock64();
@@ -704,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           constexpr int layer = decltype(lc)::value, j = decltype(jc)::value;
           constexpr uint32_t col = layer == 1 ? (uint32_t)buf_col(j) : (j == 0 ? (uint32_t)buf_col(2) : (uint32_t)buf_col(0));
           constexpr uint32_t dst = kColA1 + (layer == 1 ? 0u : 64u) + 32u * j;
-          ptx::mbar_wait(ev + 8u * (kEvPdFull + (layer - 1) * 2 + j), uh & 1u);
+          ptx::mbar_wait(ev + 8u * (kEvPdFull + (layer - 1) * 2 + j), uh & 1u, hc);
           ptx::tc_fence_after();
           if (trh) a.trace[h * kTraceSlots + kTrFinal + 1 + 2 * layer] = clock64();
           uint32_t v0[32], v1[32], w0[16], w1[16];
@@ -735,7 +737,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (g == 0) pol_chunk(std::integral_constant<int, 2>{}, std::integral_constant<int, 0>{});
         else if (a.np2 > 1) pol_chunk(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{});
         if (is_final) {
-          ptx::mbar_wait(ev + 8u * kEvPolFull, uh & 1u);
+          ptx::mbar_wait(ev + 8u * kEvPolFull, uh & 1u, hc);
           ptx::tc_fence_after();
           if (trh) a.trace[h * kTraceSlots + kTrFinal + 7] = clock64();
           uint32_t v[32];
@@ -783,7 +785,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < 16; ++i) w1[i] = pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
         if (l2 && c > 0) {
-          ptx::mbar_wait(ev + 8u * (kEvA2Empty + c - 1), uh & 1u);   // layer 3 has consumed the previous chunk
+          ptx::mbar_wait(ev + 8u * (kEvA2Empty + c - 1), uh & 1u, hc);   // layer 3 has consumed the previous chunk
           ptx::tc_fence_after();
         }
         if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e + 2] = clock64();
@@ -798,8 +800,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       // layer 1: the groups take alternate PAIRS of chunks (the pairs the issuer commits together): one combined wait
       for (uint32_t c0 = 2u * (uint32_t)g; c0 < (uint32_t)NC; c0 += 4) {
         const bool two = c0 + 1 < (uint32_t)NC;
-        if (two) ptx::mbar_wait2(ev + 8u * (kEvDFull + c0), ev + 8u * (kEvDFull + c0 + 1), uh & 1u);
-        else ptx::mbar_wait(ev + 8u * (kEvDFull + c0), uh & 1u);
+        if (two) ptx::mbar_wait2(ev + 8u * (kEvDFull + c0), ev + 8u * (kEvDFull + c0 + 1), uh & 1u, hc);
+        else ptx::mbar_wait(ev + 8u * (kEvDFull + c0), uh & 1u, hc);
         ptx::tc_fence_after();
 #pragma unroll 1
         for (uint32_t c = c0; c < c0 + (two ? 2u : 1u); ++c) {
@@ -814,12 +816,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       // layer 2: alternate chunks
 #pragma unroll 1
       for (uint32_t c = (uint32_t)g; c < (uint32_t)NC; c += 2) {
-        ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u);
+        ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u, hc);
         ptx::tc_fence_after();
         chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), (uint32_t)kColA2, (uint32_t)kEvA2Ready + c, true, c);
       }
       if (is_final) {
-        ptx::mbar_wait(ev + 8u * kEvD3Full, uh & 1u);
+        ptx::mbar_wait(ev + 8u * kEvD3Full, uh & 1u, hc);
         ptx::tc_fence_after();
         if (trh) a.trace[h * kTraceSlots + kTrFinal] = clock64();
         uint32_t v[32];

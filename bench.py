@@ -30,8 +30,8 @@ K_PATHS, HORIZON, STATES_PER_GPU = 4096, 20, 32
 FLOP_PER_TRANSITION = 2 * (26 * 500 + 500 * 500 + 500 * 20)   # 546 000; padding not credited
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload, from the committed ncu --set full
 # capture (the kernel streams its 0.6 MB of weights from L2; states in, 80-byte records out)
-NCU_DRAM_BYTES_PER_LAUNCH = 829952
-NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_full_rollout_tmem.csv"
+NCU_DRAM_BYTES_PER_LAUNCH = 697088
+NCU_TRAFFIC_SOURCE = "profiles/r1e_ncu_full_rollout_tmem.csv"
 
 
 def measured_peaks():
@@ -43,17 +43,18 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  The sampler runs from
+    before the warm-up (nvidia-smi needs a few hundred ms to start); only rows that arrive inside a marked region count."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.regions, self._t0 = index, [], None, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -61,19 +62,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self._t0 = time.perf_counter()
+
+    def end(self):
+        self.regions.append((self._t0, time.perf_counter()))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if any(a - 0.02 <= t <= b + 0.02 for a, b in self.regions)]
+        rows = inside if inside else [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "samples_inside_timed_regions": len(inside)}
 
 
 def problem():
@@ -249,6 +258,9 @@ def run_ours(args):
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)                    # max over ranks, on the device
         return float(tot.item()), ms, wall
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         step_resident(i)
         step_e2e(i)
@@ -256,12 +268,10 @@ def run_ours(args):
     # ---- resident-input throughput (value) + kernel-only duration for the roofline ----
     pl.enable_timing(True)
     launches0 = pl.kernel_launches
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     kernel_ms = []
     evs_tot, ms_list, wall = 0.0, [], 0.0
     barrier()
+    clocks.begin()
     t_wall = time.perf_counter()
     pairs = []
     for i in range(args.steps):
@@ -275,7 +285,7 @@ def run_ours(args):
         kernel_ms.append(pl.last_kernel_ms())
     barrier()
     wall = time.perf_counter() - t_wall
-    clk = clocks.stop() if rank == 0 else None
+    clocks.end()
     launches = pl.kernel_launches - launches0
     ms_list = [a.elapsed_time(b) for a, b in pairs]
     tot = torch.tensor([sum(ms_list)], dtype=torch.float64, device="cuda")
@@ -284,7 +294,10 @@ def run_ours(args):
     total_ms = float(tot.item())
     pl.enable_timing(False)
     # ---- end-to-end through the host-buffer path ----
+    clocks.begin()
     e2e_ms, _, _ = timed(step_e2e, args.steps, True)
+    clocks.end()
+    clk = clocks.stop() if rank == 0 else None
 
     transitions_per_step = B * K_PATHS * HORIZON                          # all ranks together
     value = transitions_per_step * args.steps / (total_ms * 1e-3)
@@ -302,7 +315,7 @@ def run_ours(args):
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                              "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (dram read+write)",
                              "traffic_source": NCU_TRAFFIC_SOURCE,
-                             "kernel": "bcmpc::tmx::rollout_tmem_kernel<2, 8>", "kernel_ms": k_ms,
+                             "kernel": "bcmpc::tmx::rollout_tmem_kernel<2, 8, 0>", "kernel_ms": k_ms,
                              "flop_per_transition": FLOP_PER_TRANSITION, "peak_source": peak_src,
                              "note": "algorithmic FLOPs only (26-500-500-20); padded tiles (32/512/512/32) are not credited"},
                 "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": B * 20 * 8,
