@@ -58,6 +58,10 @@ constexpr int kColA1 = 0, kColD = 256, kColA2 = 448, kColD3 = 480, kTmemCols = 5
 constexpr int kNumDBuf = 3;            // accumulators of the layer-2 chunks
 constexpr int kNumDBufL1 = 4;          // layer 1 also borrows [448,512): A2 and D3 are idle while layer 1 runs
 __host__ __device__ constexpr int buf_col(int b) { return b < kNumDBuf ? kColD + kChunk * b : kColA2; }
+// TMEM columns of hidden-2 chunk c (bf16 pairs, A operand of layer 3).  Chunks share the single A2 buffer, except the
+// LAST one: it goes to the accumulator buffer of chunk nc-3, which has been drained and has no further user in the
+// step - so the step's tail does not wait for layer 3 to consume chunk nc-2 first.
+__host__ __device__ constexpr int a2_col(int c, int nc) { return (nc >= 3 && c == nc - 1) ? kColD + kChunk * ((nc - 3) % kNumDBuf) : kColA2; }
 constexpr int kD = 20, kA = 6;
 constexpr int kMaxStages = 16, kMaxChunks = 16;
 constexpr int kSmemLimit = 232448;     // 227 KB
@@ -649,9 +653,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c] = clock64();
+            const uint32_t acol = c == (uint32_t)NC - 1 ? (uint32_t)a2_col(NC - 1, NC) : (uint32_t)kColA2;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              ptx::umma_ts<CG>(kColD3, kColA2 + ks * 8, w3desc + (uint64_t)(c * (L.blk_o >> 4) + 2u * ks), kIdescO, (c == 0 && ks == 0) ? 0u : 1u);
+              ptx::umma_ts<CG>(kColD3, acol + ks * 8, w3desc + (uint64_t)(c * (L.blk_o >> 4) + 2u * ks), kIdescO, (c == 0 && ks == 0) ? 0u : 1u);
             if (c == (uint32_t)NC - 1) ptx::umma_commit_cg<CG>(ev + 8u * kEvD3Full);
             else ptx::umma_commit_cg<CG>(ev + 8u * (kEvA2Empty + c));
             if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c + 1] = clock64();
@@ -784,7 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         for (int i = 0; i < 16; ++i) w0[i] = pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
 #pragma unroll
         for (int i = 0; i < 16; ++i) w1[i] = pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-        if (l2 && c > 0) {
+        if (l2 && c > 0 && dst == (uint32_t)kColA2) {
           ptx::mbar_wait(ev + 8u * (kEvA2Empty + c - 1), uh & 1u, hc);   // layer 3 has consumed the previous chunk
           ptx::tc_fence_after();
         }
@@ -818,7 +823,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       for (uint32_t c = (uint32_t)g; c < (uint32_t)NC; c += 2) {
         ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u, hc);
         ptx::tc_fence_after();
-        chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), (uint32_t)kColA2, (uint32_t)kEvA2Ready + c, true, c);
+        chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf),
+              c == (uint32_t)NC - 1 ? (uint32_t)a2_col(NC - 1, NC) : (uint32_t)kColA2, (uint32_t)kEvA2Ready + c, true, c);
       }
       if (is_final) {
         ptx::mbar_wait(ev + 8u * kEvD3Full, uh & 1u, hc);
