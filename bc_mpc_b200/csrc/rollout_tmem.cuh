@@ -552,36 +552,43 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
             }
             __syncwarp();
           }
-          // ---- layer 1: pairs of chunks over four accumulators ----
-          ptx::mbar_wait(ev + 8u * kEvA0Ready, par, hc);
-          for (uint32_t c0 = 0; c0 < (uint32_t)NC; c0 += 2) {
-            const bool two = c0 + 1 < (uint32_t)NC;
-            if (c0 >= (uint32_t)kNumDBufL1) {      // the previous users of this pair of accumulators have been drained
-              if (two) ptx::mbar_wait2(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), ev + 8u * (kEvDEmpty + c0 - kNumDBufL1 + 1), par, hc);
-              else ptx::mbar_wait(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), par, hc);
-            }
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              if (trw) a.trace[h * kTraceSlots + kTrL1 + c0] = clock64();
-              constexpr int nks = (kD + kA + 2 + 15) / 16;
-#pragma unroll
-              for (uint32_t t = 0; t < 2; ++t) {
-                if (t == 0 || two) {
-                  const uint32_t c = c0 + t, bsel = c % (uint32_t)kNumDBufL1;
-                  const uint32_t d = bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2;
-#pragma unroll
-                  for (int ks = 0; ks < nks; ++ks)
-                    ptx::umma_ss<CG>(d, a0desc + 2u * ks, w1desc + (uint64_t)(c * (L.blk_h >> 4) + 2u * ks), kIdescH, ks > 0 ? 1u : 0u);
-                  ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + c));
-                }
-              }
-              if (trw) a.trace[h * kTraceSlots + kTrL1 + c0 + 1] = clock64();
-            }
-            __syncwarp();
+        }
+        // ---- layer 1: pairs of chunks over four accumulators.  Warp 3 issues pairs 0, 1 and the later even pairs,
+        // warp 1 the later odd pairs: the second wave starts as soon as its own accumulators are drained. ----
+        if (mine == 1) ptx::mbar_wait(ev + 8u * kEvA0Ready, par, hc);
+        for (uint32_t c0 = 0; c0 < (uint32_t)NC; c0 += 2) {
+          const uint32_t pr = c0 >> 1;
+          const int owner = (pr >= 2 && (pr & 1u)) ? 0 : 1;
+          if (owner != mine) continue;
+          const bool two = c0 + 1 < (uint32_t)NC;
+          if (c0 >= (uint32_t)kNumDBufL1) {      // the previous users of this pair of accumulators have been drained
+            if (two) ptx::mbar_wait2(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), ev + 8u * (kEvDEmpty + c0 - kNumDBufL1 + 1), par, hc);
+            else ptx::mbar_wait(ev + 8u * (kEvDEmpty + c0 - kNumDBufL1), par, hc);
           }
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            if (trw) a.trace[h * kTraceSlots + kTrL1 + c0] = clock64();
+            constexpr int nks = (kD + kA + 2 + 15) / 16;
+#pragma unroll
+            for (uint32_t t = 0; t < 2; ++t) {
+              if (t == 0 || two) {
+                const uint32_t c = c0 + t, bsel = c % (uint32_t)kNumDBufL1;
+                const uint32_t d = bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2;
+#pragma unroll
+                for (int ks = 0; ks < nks; ++ks)
+                  ptx::umma_ss<CG>(d, a0desc + 2u * ks, w1desc + (uint64_t)(c * (L.blk_h >> 4) + 2u * ks), kIdescH, ks > 0 ? 1u : 0u);
+                ptx::umma_commit_cg<CG>(ev + 8u * (kEvDFull + c));
+              }
+            }
+            if (trw) a.trace[h * kTraceSlots + kTrL1 + c0 + 1] = clock64();
+          }
+          __syncwarp();
         }
         // ---- layer 2: this issuer's chunks, one MMA group per weight stage ----
         for (uint32_t c = (uint32_t)mine; c < (uint32_t)NC; c += 2) {
+          const uint32_t gs0 = uh * stages_per_step + (c >> 1) * (uint32_t)kNstg;
+          // the chunk's first weight stage landed long ago: take that wait before the ones on the dependency chain
+          ptx::mbar_wait(misc + kOffWFull + 8u * (first_mine + gs0 % nst_mine), (gs0 / nst_mine) & 1u);
           if (c < 2) {
             // first layer-2 chunk of this issuer in the step: all of A1 must be in TMEM (which also means that every
             // layer-1 accumulator has been drained).  Each epilogue group signals its chunks in order, so the last two
@@ -591,11 +598,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           }
           if (c >= (uint32_t)kNumDBuf) ptx::mbar_wait(ev + 8u * (kEvDEmpty + NC + c - kNumDBuf), par, hc);   // previous user of the accumulator drained
           const uint32_t d = (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf);
-          const uint32_t gs0 = uh * stages_per_step + (c >> 1) * (uint32_t)kNstg;
 #pragma unroll
           for (int j = 0; j < kNstg; ++j) {
             const uint32_t gs = gs0 + (uint32_t)j, stage = first_mine + gs % nst_mine, phase = (gs / nst_mine) & 1u;
-            ptx::mbar_wait(misc + kOffWFull + 8u * stage, phase);
+            if (j > 0) ptx::mbar_wait(misc + kOffWFull + 8u * stage, phase);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               if (trw && j == 0) a.trace[h * kTraceSlots + kTrL2 + 2 * c] = clock64();
