@@ -58,10 +58,23 @@ constexpr int kColA1 = 0, kColD = 256, kColA2 = 448, kColD3 = 480, kTmemCols = 5
 constexpr int kNumDBuf = 3;            // accumulators of the layer-2 chunks
 constexpr int kNumDBufL1 = 4;          // layer 1 also borrows [448,512): A2 and D3 are idle while layer 1 runs
 __host__ __device__ constexpr int buf_col(int b) { return b < kNumDBuf ? kColD + kChunk * b : kColA2; }
-// TMEM columns of hidden-2 chunk c (bf16 pairs, A operand of layer 3).  Chunks share the single A2 buffer, except the
-// LAST one: it goes to the accumulator buffer of chunk nc-3, which has been drained and has no further user in the
-// step - so the step's tail does not wait for layer 3 to consume chunk nc-2 first.
-__host__ __device__ constexpr int a2_col(int c, int nc) { return (nc >= 3 && c == nc - 1) ? kColD + kChunk * ((nc - 3) % kNumDBuf) : kColA2; }
+// TMEM columns of hidden-2 chunk c (bf16 pairs, A operand of layer 3).  Layer 3 queues behind ~1000 cycles of layer-2
+// MMAs in the in-order tensor pipe, so with ONE buffer the epilogue of chunk c+1 waits that long for layer 3 to consume
+// chunk c.  Networks narrower than 512 leave part of the A1 region unused: those columns become extra buffers
+// (2x256 net: 4 buffers).  With a single buffer (hidden = 512) at least the LAST chunk goes elsewhere - to the
+// accumulator buffer of chunk nc-3, drained and without further user in the step - so the step's tail does not wait.
+__host__ __device__ constexpr int a2_buffers(int nc) { return 1 + (256 - 32 * nc) / 32 > 4 ? 4 : 1 + (256 - 32 * nc) / 32; }
+__host__ __device__ constexpr int a2_col(int c, int nc) {
+  const int nb = a2_buffers(nc), b = c % nb;
+  if (nb == 1) return (nc >= 3 && c == nc - 1) ? kColD + kChunk * ((nc - 3) % kNumDBuf) : kColA2;
+  return b == 0 ? kColA2 : kColA1 + 32 * nc + 32 * (b - 1);
+}
+// does the epilogue of chunk c have to wait for layer 3 to consume an earlier chunk (and which)?
+__host__ __device__ constexpr int a2_wait_chunk(int c, int nc) {
+  const int nb = a2_buffers(nc);
+  if (nb == 1) return (c == 0 || (nc >= 3 && c == nc - 1)) ? -1 : c - 1;
+  return c >= nb ? c - nb : -1;
+}
 constexpr int kD = 20, kA = 6;
 constexpr int kMaxStages = 16, kMaxChunks = 16;
 constexpr int kSmemLimit = 232448;     // 227 KB
@@ -659,7 +672,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c] = clock64();
-            const uint32_t acol = c == (uint32_t)NC - 1 ? (uint32_t)a2_col(NC - 1, NC) : (uint32_t)kColA2;
+            uint32_t acol;
+            if constexpr (a2_buffers(NC) == 1) {
+              acol = c == (uint32_t)NC - 1 ? (uint32_t)a2_col(NC - 1, NC) : (uint32_t)kColA2;
+            } else {
+              const uint32_t bsel = c % (uint32_t)a2_buffers(NC);
+              acol = bsel == 0 ? (uint32_t)kColA2 : (uint32_t)(kColA1 + 32 * NC) + 32u * (bsel - 1u);
+            }
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               ptx::umma_ts<CG>(kColD3, acol + ks * 8, w3desc + (uint64_t)(c * (L.blk_o >> 4) + 2u * ks), kIdescO, (c == 0 && ks == 0) ? 0u : 1u);
@@ -781,7 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (trh) a.trace[h * kTraceSlots + kTrFinal + 1] = clock64();
       }
       // one accumulator chunk: TMEM -> registers, ReLU + bf16, -> TMEM operand of the next layer
-      auto chunk = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, bool l2, uint32_t c) {
+      auto chunk = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, int wait_a2) {
         if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e] = clock64();
         uint32_t v0[32], v1[32], w0[16], w1[16];
         ptx::tmem_ld32(lane_off + col, v0);
@@ -795,8 +814,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         for (int i = 0; i < 16; ++i) w0[i] = pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
 #pragma unroll
         for (int i = 0; i < 16; ++i) w1[i] = pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-        if (l2 && c > 0 && dst == (uint32_t)kColA2) {
-          ptx::mbar_wait(ev + 8u * (kEvA2Empty + c - 1), uh & 1u, hc);   // layer 3 has consumed the previous chunk
+        if (wait_a2 >= 0) {
+          ptx::mbar_wait(ev + 8u * (kEvA2Empty + wait_a2), uh & 1u, hc);   // layer 3 has consumed the buffer's previous chunk
           ptx::tc_fence_after();
         }
         if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e + 2] = clock64();
@@ -818,7 +837,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         for (uint32_t c = c0; c < c0 + (two ? 2u : 1u); ++c) {
           const uint32_t bsel = c % (uint32_t)kNumDBufL1;
           chunk(c, bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2, (uint32_t)kColA1 + 32u * c,
-                (uint32_t)kEvA1Ready + c, false, c);
+                (uint32_t)kEvA1Ready + c, -1);
         }
       }
       // the next step's randomness is drawn between the layer-1 and layer-2 chunks, where these warps have slack (at the
@@ -829,8 +848,18 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       for (uint32_t c = (uint32_t)g; c < (uint32_t)NC; c += 2) {
         ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u, hc);
         ptx::tc_fence_after();
-        chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf),
-              c == (uint32_t)NC - 1 ? (uint32_t)a2_col(NC - 1, NC) : (uint32_t)kColA2, (uint32_t)kEvA2Ready + c, true, c);
+        uint32_t dst;
+        int wait_a2;
+        if constexpr (a2_buffers(NC) == 1) {
+          const bool last = NC >= 3 && c == (uint32_t)NC - 1;
+          dst = last ? (uint32_t)a2_col(NC - 1, NC) : (uint32_t)kColA2;
+          wait_a2 = (c == 0 || last) ? -1 : (int)c - 1;
+        } else {
+          const uint32_t bsel = c % (uint32_t)a2_buffers(NC);
+          dst = bsel == 0 ? (uint32_t)kColA2 : (uint32_t)(kColA1 + 32 * NC) + 32u * (bsel - 1u);
+          wait_a2 = c >= (uint32_t)a2_buffers(NC) ? (int)c - a2_buffers(NC) : -1;
+        }
+        chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2);
       }
       if (is_final) {
         ptx::mbar_wait(ev + 8u * kEvD3Full, uh & 1u, hc);
