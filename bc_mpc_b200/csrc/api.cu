@@ -61,6 +61,11 @@ struct bcmpc_handle {
   // tcgen05 path (rollout_tmem.cuh)
   tmx::TmHostPlan tmp;
   uint8_t *d_res = nullptr, *d_stream = nullptr, *d_pol = nullptr;
+  float* d_lnvec = nullptr;
+  std::vector<float> hW[3], hb[3];            // host copies of the dynamics weights (the fast images are rebuilt when LayerNorm is switched)
+  std::vector<float> ln_gamma[2], ln_beta[2]; // LayerNorm parameters (fast mode)
+  bool ln_on = false;
+  float ln_eps = 1e-12f;
   unsigned long long* d_trace = nullptr;
   bool tm_ready = false;
   int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
@@ -183,11 +188,20 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
   return BCMPC_OK;
 }
 
-int tm_prepare(bcmpc_handle* h, const float* const* W, const float* const* b) {
+int tm_variant(const bcmpc_handle* h) {
+  if (h->cfg.proposal != BCMPC_PROP_UNIFORM) return tmx::kVarPolicy;
+  return h->ln_on ? tmx::kVarLayerNorm : tmx::kVarUniform;
+}
+
+// (re)builds the fast-mode weight images from the host copies of the dynamics weights
+int tm_prepare(bcmpc_handle* h) {
   const int S = h->cfg.hidden_size;
   const bool keep_policy = h->tmp.with_policy;
   const tmx::TmHostPlan old = h->tmp;
-  tmx::tm_build(W[0], b[0], W[1], b[1], W[2], b[2], S, h->tm_cg, h->cfg.proposal != BCMPC_PROP_UNIFORM, &h->tmp);
+  const float* g[2] = {h->ln_gamma[0].data(), h->ln_gamma[1].data()};
+  const float* be[2] = {h->ln_beta[0].data(), h->ln_beta[1].data()};
+  tmx::tm_build(h->hW[0].data(), h->hb[0].data(), h->hW[1].data(), h->hb[1].data(), h->hW[2].data(), h->hb[2].data(), S, h->tm_cg,
+                tm_variant(h), h->ln_on ? g : nullptr, h->ln_on ? be : nullptr, &h->tmp);
   if (keep_policy) {   // the proposal network survives a dynamics refresh
     h->tmp.with_policy = true; h->tmp.np1 = old.np1; h->tmp.np2 = old.np2; h->tmp.pol = old.pol;
     memcpy(h->tmp.bp1, old.bp1, sizeof old.bp1); memcpy(h->tmp.bp2, old.bp2, sizeof old.bp2); memcpy(h->tmp.bp3, old.bp3, sizeof old.bp3);
@@ -197,11 +211,16 @@ int tm_prepare(bcmpc_handle* h, const float* const* W, const float* const* b) {
   if (P.lay.nst < 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "weight ring does not fit in shared memory");
   if (h->d_res) cudaFree(h->d_res);
   if (h->d_stream) cudaFree(h->d_stream);
-  h->d_res = h->d_stream = nullptr;
+  if (h->d_lnvec) cudaFree(h->d_lnvec);
+  h->d_res = h->d_stream = nullptr; h->d_lnvec = nullptr;
   CK(h, cudaMalloc(&h->d_res, P.res.size() * 2));
   CK(h, cudaMalloc(&h->d_stream, P.stream.size() * 2));
   CK(h, cudaMemcpy(h->d_res, P.res.data(), P.res.size() * 2, cudaMemcpyHostToDevice));
   CK(h, cudaMemcpy(h->d_stream, P.stream.data(), P.stream.size() * 2, cudaMemcpyHostToDevice));
+  if (P.layer_norm) {
+    CK(h, cudaMalloc(&h->d_lnvec, P.lnvec.size() * sizeof(float)));
+    CK(h, cudaMemcpy(h->d_lnvec, P.lnvec.data(), P.lnvec.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if (!h->trace_path.empty() && !h->d_trace)
     CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots));
   h->tm_ready = true;
@@ -229,7 +248,14 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.span[j] = h->norm.span[j];
   }
   const bool pol = p.proposal != BCMPC_PROP_UNIFORM;
+  const int var = pol ? tmx::kVarPolicy : (P.layer_norm ? tmx::kVarLayerNorm : tmx::kVarUniform);
   a.proposal = p.proposal; a.inj_kind = p.inj_kind;
+  if (P.layer_norm) {
+    if (pol) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm dynamics with a proposal network run in BCMPC_PREC_FP32_VERIFY only");
+    a.lnvec = h->d_lnvec;
+    memcpy(a.u3, P.u3, sizeof a.u3); memcpy(a.c3, P.c3, sizeof a.c3);
+    a.ln_inv_n = 1.0f / (float)h->cfg.hidden_size; a.ln_eps = h->ln_eps;
+  }
   if (pol) {
     if (!P.with_policy || !h->d_pol) return fail(h, BCMPC_ERR_STATE, "proposal network not set (bcmpc_set_policy)");
     a.pol = h->d_pol; a.np1 = P.np1; a.np2 = P.np2;
@@ -241,7 +267,7 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   }
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
-  CK(h, tmx::tm_launch(h->tm_cg, P.nc, pol, a, dim3(p.tiles_per_state, p.B), st));
+  CK(h, tmx::tm_launch(h->tm_cg, P.nc, var, a, dim3(p.tiles_per_state, p.B), st));
   CK(h, cudaGetLastError());
   h->launches++;
   if (h->d_trace) {
@@ -369,7 +395,7 @@ int bcmpc_destroy(bcmpc_handle* h) {
   h->pol.release();
   for (float* p : h->ln_bufs) cudaFree(p);
   cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
-  cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_trace);
+  cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_lnvec); cudaFree(h->d_trace);
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_records) cudaFreeHost(h->h_records);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -394,7 +420,12 @@ int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* cons
   if (rc) return rc;
   update_verify_geometry(h);
   if (h->cfg.precision == BCMPC_PREC_BF16_FAST) {
-    rc = tm_prepare(h, W, b);
+    for (int l = 0; l < 3; ++l) {
+      h->hW[l].assign(W[l], W[l] + (size_t)sizes[l] * sizes[l + 1]);
+      h->hb[l].assign(b[l], b[l] + sizes[l + 1]);
+    }
+    h->ln_on = false;      // new weights reset LayerNorm (same rule as the verification path): call bcmpc_set_layer_norm again
+    rc = tm_prepare(h);
     if (rc) return rc;
   }
   return BCMPC_OK;
@@ -402,9 +433,22 @@ int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* cons
 
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps) {
   if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
-  if (h->cfg.precision == BCMPC_PREC_BF16_FAST)
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "LayerNorm dynamics run in BCMPC_PREC_FP32_VERIFY only this round");
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
+  if (h->cfg.precision == BCMPC_PREC_BF16_FAST) {
+    if (gamma && h->cfg.proposal != BCMPC_PROP_UNIFORM)
+      return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm dynamics with a proposal network run in BCMPC_PREC_FP32_VERIFY only");
+    if (gamma && (!beta || n_hidden != 2)) return fail(h, BCMPC_ERR_INVALID, "fast mode expects gamma and beta for the two hidden layers");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->ln_on = gamma != nullptr;
+    h->ln_eps = eps;
+    for (int l = 0; l < 2 && gamma; ++l) {
+      if (!gamma[l] || !beta[l]) return fail(h, BCMPC_ERR_INVALID, "null LayerNorm pointer for layer %d", l);
+      h->ln_gamma[l].assign(gamma[l], gamma[l] + h->cfg.hidden_size);
+      h->ln_beta[l].assign(beta[l], beta[l] + h->cfg.hidden_size);
+    }
+    return tm_prepare(h);
+  }
   CK(h, cudaSetDevice(h->cfg.device));
   CK(h, cudaStreamSynchronize(h->stream));
   for (float* p : h->ln_bufs) cudaFree(p);
@@ -485,7 +529,7 @@ int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, co
     if (h->tmp.cg == 0 || h->tmp.lay.blk_h == 0) {   // layout depends only on (pair mode, hidden chunks): fix it now if the dynamics come later
       h->tmp.cg = h->tm_cg;
       h->tmp.nc = (h->cfg.hidden_size + 2 + 63) / 64;
-      h->tmp.lay = tmx::make_layout(h->tm_cg, h->tmp.nc, true);
+      h->tmp.lay = tmx::make_layout(h->tm_cg, h->tmp.nc, tmx::kVarPolicy);
     }
     tmx::tm_build_policy(sizes, W, b, &h->tmp);
     if (h->d_pol) cudaFree(h->d_pol);

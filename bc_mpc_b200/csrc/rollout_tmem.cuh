@@ -123,9 +123,13 @@ struct Layout {
   int kbs = 0, nstg = 0, nst = 0;
   int nst_r[2] = {0, 0}, first_r[2] = {0, 0};     // the ring is split in two: even layer-2 chunks / odd layer-2 chunks, one per MMA issuer
   uint32_t blk_h = 0, blk_o = 0, w1_bytes = 0, res_bytes = 0, stage_bytes = 0;
-  uint32_t off_a0 = 0, off_res = 0, off_pol = 0, pol_bytes = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
+  uint32_t off_a0 = 0, off_res = 0, off_pol = 0, pol_bytes = 0, off_ln = 0, ln_bytes = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
 };
-constexpr Layout make_layout(int cg, int nc, bool pol) {
+// kernel variants: uniform shooting, policy-guided shooting, uniform shooting with the LayerNorm dynamics net
+enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2 };
+constexpr uint32_t kLnStatsBytes = 2 * 2 * kRows * 8;      // [layer][epilogue group][row] (sum, sum of squares)
+constexpr Layout make_layout(int cg, int nc, int var) {
+  const bool pol = var == kVarPolicy, ln = var == kVarLayerNorm;
   Layout L;
   L.kbs = stage_kblocks(cg, nc);
   L.nstg = (nc + L.kbs - 1) / L.kbs;
@@ -138,7 +142,10 @@ constexpr Layout make_layout(int cg, int nc, bool pol) {
   L.off_pol = (L.off_res + L.res_bytes + 1023u) / 1024u * 1024u;
   // resident proposal network (sized for 128/128 hidden units): [Wp1: 2 chunks][Wp2: 2 chunks x 2 k-blocks][Wp3: 2 k-blocks]
   L.pol_bytes = pol ? 6u * L.blk_h + 2u * L.blk_o : 0u;
-  L.off_ring = (L.off_pol + L.pol_bytes + 1023u) / 1024u * 1024u;
+  // LayerNorm variant: per-column correction vectors of layer 2 (u2, c2: 2 x 64*nc floats) + per-row statistics
+  L.off_ln = (L.off_pol + L.pol_bytes + 1023u) / 1024u * 1024u;
+  L.ln_bytes = ln ? 2u * 64u * nc * 4u + kLnStatsBytes : 0u;
+  L.off_ring = (L.off_ln + L.ln_bytes + 1023u) / 1024u * 1024u;
   L.stage_bytes = L.kbs * L.blk_h;
   L.nst = (int)((kSmemLimit - kMiscBytes - L.off_ring) / L.stage_bytes);
   if (L.nst > kMaxStages) L.nst = kMaxStages;
@@ -149,9 +156,9 @@ constexpr Layout make_layout(int cg, int nc, bool pol) {
   return L;
 }
 
-template <int CG, int NC, bool POL>
+template <int CG, int NC, int VAR>
 struct Lay {
-  static constexpr Layout value = make_layout(CG, NC, POL);
+  static constexpr Layout value = make_layout(CG, NC, VAR);
 };
 
 struct TmArgs {
@@ -169,6 +176,10 @@ struct TmArgs {
   float clip, explore, one_minus_explore;
   float filt_mean[kMaxObs], filt_inv_std[kMaxObs], pol_std[kMaxAct];
   float bp1[kPolMaxHidden], bp2[kPolMaxHidden], bp3[kMaxAct];
+  // LayerNorm variant (dynamics.py:68-69): z = rho * acc - rho * mu * u + c per column, rho / mu per row
+  const float* lnvec;            // [u2 (64*nc)][c2 (64*nc)] correction vectors of layer 2
+  float u3[kMaxObs], c3[kMaxObs];   // ... of the output layer
+  float ln_inv_n, ln_eps;        // 1 / hidden_size, variance epsilon
 };
 // pipeline trace of CTA (0,0), steps 0..3: [2 per L1 pair][2 per L2 chunk][2 per L3 chunk][4 per epilogue chunk][final 8][2 per stage]
 constexpr int kTraceSteps = 4, kTrL1 = 0, kTrL2 = 8, kTrL3 = 24, kTrEpi = 40, kTrFinal = 104, kTrProd = 112, kTraceSlots = kTrProd + 2 * 64;
@@ -197,7 +208,10 @@ inline size_t sw128_offset(int n, int kk) {
 
 struct TmHostPlan {
   std::vector<uint16_t> res, stream, pol;
-  int cg = 1, s_pad = 0, nc = 0;
+  std::vector<float> lnvec;      // LayerNorm variant: [u2][c2]
+  float u3[kMaxObs] = {}, c3[kMaxObs] = {};
+  bool layer_norm = false;
+  int cg = 1, s_pad = 0, nc = 0, hidden = 0;
   bool with_policy = false;
   int np1 = 0, np2 = 0;
   float bp1[kPolMaxHidden] = {}, bp2[kPolMaxHidden] = {}, bp3[kMaxAct] = {};
@@ -262,15 +276,22 @@ inline void tm_build_policy(const int* sizes, const float* const* W, const float
 // W[l] are TF kernels [in,out] row-major: W1 [26,S], W2 [S,S], W3 [S,20].
 // Bias-in-GEMM: input columns 26,27 of A0 are 1.0; hidden units S and S+1 of both hidden layers are wired to be
 // exactly 1.0 after ReLU; row S / S+1 of the next layer's kernel hold bf16(b) and bf16(b - bf16(b)).
+// ln_gamma / ln_beta: [2][S] LayerNorm parameters of the two hidden layers, or nullptr.  With LayerNorm the kernel
+// multiplies UN-normalised ReLU outputs r by W' = diag(gamma) W and corrects in the next epilogue:
+//   LN(r) W + b = rho * (r W') - rho * mu * u + c,   u = gamma^T W (column sums of the bf16 W'),  c = beta^T W + b,
+// rho = 1 / sqrt(var(r) + eps) and mu = mean(r) per path.  Biases of layers 2 / 3 live in c, so no "ones" units.
 inline void tm_build(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
-                     int S, int cg, bool pol, TmHostPlan* out) {
+                     int S, int cg, int var, const float* const* ln_gamma, const float* const* ln_beta, TmHostPlan* out) {
   TmHostPlan& P = *out;
   P = TmHostPlan{};
   const int in_dim = kD + kA;
+  const bool ln = var == kVarLayerNorm;
   P.cg = cg;
-  P.s_pad = (S + 2 + 63) / 64 * 64;
+  P.hidden = S;
+  P.layer_norm = ln;
+  P.s_pad = ((ln ? S : S + 2) + 63) / 64 * 64;
   P.nc = P.s_pad / 64;
-  P.lay = make_layout(cg, P.nc, pol);
+  P.lay = make_layout(cg, P.nc, var);
   const int NC = P.nc, NKB = P.nc, kbs = P.lay.kbs;
   const int rows_h = kChunk / cg, rows_o = kOutN / cg;                 // B rows per CTA (hidden / output tiles)
   const uint32_t blk_h = P.lay.blk_h, blk_o = P.lay.blk_o, w1_bytes = P.lay.w1_bytes;
@@ -282,18 +303,33 @@ inline void tm_build(const float* W1, const float* b1, const float* W2, const fl
   // effective (bias-augmented, zero-padded) kernels as functions
   auto w1 = [&](int k, int n) -> uint16_t {        // k < 64 (input column), n < s_pad (hidden unit)
     if (n < S) return k < in_dim ? f32_to_bf16(W1[(size_t)k * S + n]) : k == in_dim ? hi(b1[n]) : k == in_dim + 1 ? lo(b1[n]) : 0;
-    if (n == S || n == S + 1) return k == in_dim ? one : 0;          // the hidden "ones" units: relu(1 * 1) = 1
+    if (!ln && (n == S || n == S + 1)) return k == in_dim ? one : 0;          // the hidden "ones" units: relu(1 * 1) = 1
     return 0;
   };
   auto w2 = [&](int k, int n) -> uint16_t {
+    if (ln) return (n < S && k < S) ? f32_to_bf16(ln_gamma[0][k] * W2[(size_t)k * S + n]) : 0;
     if (n < S) return k < S ? f32_to_bf16(W2[(size_t)k * S + n]) : k == S ? hi(b2[n]) : k == S + 1 ? lo(b2[n]) : 0;
     if (n == S || n == S + 1) return k == S ? one : 0;
     return 0;
   };
   auto w3 = [&](int k, int n) -> uint16_t {        // n < 32 (output column)
     if (n >= kD) return 0;
+    if (ln) return k < S ? f32_to_bf16(ln_gamma[1][k] * W3[(size_t)k * kD + n]) : 0;
     return k < S ? f32_to_bf16(W3[(size_t)k * kD + n]) : k == S ? hi(b3[n]) : k == S + 1 ? lo(b3[n]) : 0;
   };
+  if (ln) {
+    P.lnvec.assign((size_t)2 * P.s_pad, 0.f);
+    for (int n = 0; n < S; ++n) {
+      double u = 0.0, c = b2[n];
+      for (int k = 0; k < S; ++k) { u += bf16_to_f32(w2(k, n)); c += (double)ln_beta[0][k] * W2[(size_t)k * S + n]; }
+      P.lnvec[n] = (float)u; P.lnvec[P.s_pad + n] = (float)c;
+    }
+    for (int d = 0; d < kD; ++d) {
+      double u = 0.0, c = b3[d];
+      for (int k = 0; k < S; ++k) { u += bf16_to_f32(w3(k, d)); c += (double)ln_beta[1][k] * W3[(size_t)k * kD + d]; }
+      P.u3[d] = (float)u; P.c3[d] = (float)c;
+    }
+  }
 
   // ---- resident image: per rank [W1 chunk 0..NC-1][W3 k-block 0..NKB-1] ----
   P.res.assign((size_t)cg * res_bytes / 2, 0);
@@ -409,9 +445,10 @@ __device__ __forceinline__ void build_policy_input(const TmArgs& a, uint32_t a0_
 
 // Barrier waits are executed by all 32 lanes of the role warp (measured: ~100 cycles when the phase is already
 // complete; a single elected lane polling while the others park at the reconvergence barrier costs > 1000).
-template <int CG, int NC, bool POL>
+template <int CG, int NC, int VAR>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
-  constexpr Layout L = Lay<CG, NC, POL>::value;
+  constexpr bool POL = VAR == kVarPolicy, LN = VAR == kVarLayerNorm;
+  constexpr Layout L = Lay<CG, NC, VAR>::value;
   constexpr int kNstg = L.nstg;                               // weight stages per layer-2 chunk
   constexpr int kNumStream = NC * kNstg;                      // weight stages per step
   constexpr int kStagesPerStepR[2] = {((NC + 1) / 2) * kNstg, (NC / 2) * kNstg};   // ... per sub-ring (even / odd chunks)
@@ -453,6 +490,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(ev + 8u * (kEvAp1Ready + i), 4 * CG); ptx::mbar_init(ev + 8u * (kEvAp2Ready + i), 4 * CG); }
     ptx::mbar_init(ev + 8u * kEvPolFull, 1);
     ptx::fence_mbar_init();
+  }
+  if constexpr (LN) {
+    float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
+    for (int i = tid; i < 2 * 64 * NC; i += kThreads) s_vec[i] = a.lnvec[i];
+    // per-row statistics start at zero: a group without a chunk in some layer never writes its partial
+    for (int i = tid; i < (int)(kLnStatsBytes / 4); i += kThreads) s_vec[2 * 64 * NC + i] = 0.f;
   }
   if (warp == 2) ptx::tmem_alloc_cg<CG>(ptx::smem_u32(s_tmem), kTmemCols);
   ptx::tc_fence_before();
@@ -799,6 +842,65 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         publish(kEvA0Ready);
         if (trh) a.trace[h * kTraceSlots + kTrFinal + 1] = clock64();
       }
+      // ---- LayerNorm variant: statistics of this row's ReLU outputs, correction of the previous layer's statistics ----
+      // (each row's chunks are split between the two epilogue groups: partial sums meet in shared memory)
+      float ln_sum = 0.f, ln_sq = 0.f, rho = 1.f, rmu = 0.f;
+      [[maybe_unused]] float2* s_stats = reinterpret_cast<float2*>(smem + L.off_ln + 2u * 64u * NC * 4u);   // [layer][group][row]
+      [[maybe_unused]] const float* s_u2 = reinterpret_cast<const float*>(smem + L.off_ln);
+      [[maybe_unused]] const float* s_c2 = s_u2 + 64 * NC;
+      // rho = 1 / sqrt(var + eps), rmu = rho * mean of the layer whose partial sums are in s_stats[layer]
+      auto ln_row_stats = [&](int layer) {
+        const float2 p0 = s_stats[(layer * 2 + 0) * kRows + row], p1 = s_stats[(layer * 2 + 1) * kRows + row];
+        const float mean = (p0.x + p1.x) * a.ln_inv_n;
+        const float var = fmaxf((p0.y + p1.y) * a.ln_inv_n - mean * mean, 0.f);
+        rho = rsqrtf(var + a.ln_eps);
+        rmu = rho * mean;
+      };
+      // one chunk with LayerNorm: layer 0 = hidden 1 (plain ReLU of the accumulator), layer 1 = hidden 2 (corrected)
+      auto chunk_ln = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, int wait_a2, int layer, uint32_t c) {
+        uint32_t v0[32], v1[32], w0[16], w1[16];
+        ptx::tmem_ld32(lane_off + col, v0);
+        ptx::tmem_ld32(lane_off + col + 32u, v1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(kEvDEmpty + e);
+        const float4* u4 = reinterpret_cast<const float4*>(s_u2 + 64u * c);
+        const float4* c4 = reinterpret_cast<const float4*>(s_c2 + 64u * c);
+        auto relu_stat = [&](float acc, float u, float cc) {
+          float zv = layer == 0 ? acc : fmaf(rho, acc, fmaf(-rmu, u, cc));
+          zv = zv < 0.f ? 0.f : zv;
+          ln_sum += zv;
+          ln_sq = fmaf(zv, zv, ln_sq);
+          return zv;
+        };
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), cc = uu;
+          if (layer == 1) { uu = u4[i]; cc = c4[i]; }
+          w0[2 * i] = pack_bf16(relu_stat(__uint_as_float(v0[4 * i]), uu.x, cc.x), relu_stat(__uint_as_float(v0[4 * i + 1]), uu.y, cc.y));
+          w0[2 * i + 1] = pack_bf16(relu_stat(__uint_as_float(v0[4 * i + 2]), uu.z, cc.z), relu_stat(__uint_as_float(v0[4 * i + 3]), uu.w, cc.w));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), cc = uu;
+          if (layer == 1) { uu = u4[8 + i]; cc = c4[8 + i]; }
+          w1[2 * i] = pack_bf16(relu_stat(__uint_as_float(v1[4 * i]), uu.x, cc.x), relu_stat(__uint_as_float(v1[4 * i + 1]), uu.y, cc.y));
+          w1[2 * i + 1] = pack_bf16(relu_stat(__uint_as_float(v1[4 * i + 2]), uu.z, cc.z), relu_stat(__uint_as_float(v1[4 * i + 3]), uu.w, cc.w));
+        }
+        s_stats[(layer * 2 + g) * kRows + row] = make_float2(ln_sum, ln_sq);     // running partial of this group
+        __threadfence_block();
+        if (wait_a2 >= 0) {
+          ptx::mbar_wait(ev + 8u * (kEvA2Empty + wait_a2), uh & 1u, hc);
+          ptx::tc_fence_after();
+        }
+        ptx::tmem_st16(lane_off + dst, w0);
+        ptx::tmem_st16(lane_off + dst + 16u, w1);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(ready_id);
+      };
       // one accumulator chunk: TMEM -> registers, ReLU + bf16, -> TMEM operand of the next layer
       auto chunk = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, int wait_a2) {
         if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e] = clock64();
@@ -836,18 +938,27 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 #pragma unroll 1
         for (uint32_t c = c0; c < c0 + (two ? 2u : 1u); ++c) {
           const uint32_t bsel = c % (uint32_t)kNumDBufL1;
-          chunk(c, bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2, (uint32_t)kColA1 + 32u * c,
-                (uint32_t)kEvA1Ready + c, -1);
+          const uint32_t col = bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2;
+          if constexpr (LN) chunk_ln(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, 0, c);
+          else chunk(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1);
         }
       }
       // the next step's randomness is drawn between the layer-1 and layer-2 chunks, where these warps have slack (at the
       // top of the step it delays the first layer-1 epilogue, at the bottom the state update)
       if (is_final && h + 1 < H) get_noise(a, b, h + 1, kc, z);
       // layer 2: alternate chunks
+      bool first_l2 = true;
 #pragma unroll 1
       for (uint32_t c = (uint32_t)g; c < (uint32_t)NC; c += 2) {
         ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u, hc);
         ptx::tc_fence_after();
+        if constexpr (LN) {
+          if (first_l2) {      // all hidden-1 chunks of both groups are stored (layer 2 has run): their statistics are complete
+            ln_row_stats(0);
+            ln_sum = 0.f; ln_sq = 0.f;
+            first_l2 = false;
+          }
+        }
         uint32_t dst;
         int wait_a2;
         if constexpr (a2_buffers(NC) == 1) {
@@ -859,8 +970,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           dst = bsel == 0 ? (uint32_t)kColA2 : (uint32_t)(kColA1 + 32 * NC) + 32u * (bsel - 1u);
           wait_a2 = c >= (uint32_t)a2_buffers(NC) ? (int)c - a2_buffers(NC) : -1;
         }
-        chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2);
+        if constexpr (LN) chunk_ln((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, 1, c);
+        else chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2);
       }
+
       if (is_final) {
         ptx::mbar_wait(ev + 8u * kEvD3Full, uh & 1u, hc);
         ptx::tc_fence_after();
@@ -870,6 +983,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         float delta[kD];
+        if constexpr (LN) {
+          ln_row_stats(1);
+#pragma unroll
+          for (int d = 0; d < kD; ++d) v[d] = __float_as_uint(fmaf(rho, __uint_as_float(v[d]), fmaf(-rmu, a.u3[d], a.c3[d])));
+          ln_sum = 0.f; ln_sq = 0.f;
+        }
 #pragma unroll
         for (int d = 0; d < kD; ++d) delta[d] = fmaf(__uint_as_float(v[d]), a.std_delta[d], a.mean_delta[d]);   // dynamics.py:113
         if (s[5] >= 0.2f) cost += 10.f;                                      // cost_functions.py:16-26 (pre-step state)
@@ -922,10 +1041,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------
 // launch: picks the instantiation for (CTA-group size, hidden chunks)
 // ---------------------------------------------------------------------------------------------------------
-template <int CG, int NC, bool POL>
+template <int CG, int NC, int VAR>
 inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = rollout_tmem_kernel<CG, NC, POL>;
-  constexpr Layout L = Lay<CG, NC, POL>::value;
+  auto kern = rollout_tmem_kernel<CG, NC, VAR>;
+  constexpr Layout L = Lay<CG, NC, VAR>::value;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes);
@@ -943,23 +1062,24 @@ inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
-template <int CG, bool POL>
+template <int CG, int VAR>
 inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
   switch (nc) {
-    case 1: return tm_launch_t<CG, 1, POL>(a, grid, st);
-    case 2: return tm_launch_t<CG, 2, POL>(a, grid, st);
-    case 3: return tm_launch_t<CG, 3, POL>(a, grid, st);
-    case 4: return tm_launch_t<CG, 4, POL>(a, grid, st);
-    case 5: return tm_launch_t<CG, 5, POL>(a, grid, st);
-    case 6: return tm_launch_t<CG, 6, POL>(a, grid, st);
-    case 7: return tm_launch_t<CG, 7, POL>(a, grid, st);
-    case 8: return tm_launch_t<CG, 8, POL>(a, grid, st);
+    case 1: return tm_launch_t<CG, 1, VAR>(a, grid, st);
+    case 2: return tm_launch_t<CG, 2, VAR>(a, grid, st);
+    case 3: return tm_launch_t<CG, 3, VAR>(a, grid, st);
+    case 4: return tm_launch_t<CG, 4, VAR>(a, grid, st);
+    case 5: return tm_launch_t<CG, 5, VAR>(a, grid, st);
+    case 6: return tm_launch_t<CG, 6, VAR>(a, grid, st);
+    case 7: return tm_launch_t<CG, 7, VAR>(a, grid, st);
+    case 8: return tm_launch_t<CG, 8, VAR>(a, grid, st);
   }
   return cudaErrorInvalidValue;
 }
-inline cudaError_t tm_launch(int cg, int nc, bool pol, const TmArgs& a, dim3 grid, cudaStream_t st) {
-  if (pol) return cg == 2 ? tm_launch_cg<2, true>(nc, a, grid, st) : tm_launch_cg<1, true>(nc, a, grid, st);
-  return cg == 2 ? tm_launch_cg<2, false>(nc, a, grid, st) : tm_launch_cg<1, false>(nc, a, grid, st);
+inline cudaError_t tm_launch(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  if (var == kVarPolicy) return cg == 2 ? tm_launch_cg<2, kVarPolicy>(nc, a, grid, st) : tm_launch_cg<1, kVarPolicy>(nc, a, grid, st);
+  if (var == kVarLayerNorm) return cg == 2 ? tm_launch_cg<2, kVarLayerNorm>(nc, a, grid, st) : tm_launch_cg<1, kVarLayerNorm>(nc, a, grid, st);
+  return cg == 2 ? tm_launch_cg<2, kVarUniform>(nc, a, grid, st) : tm_launch_cg<1, kVarUniform>(nc, a, grid, st);
 }
 
 }  // namespace tmx

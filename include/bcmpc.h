@@ -103,8 +103,9 @@ int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* cons
 /* LayerNorm variant of NNDynamicsModel (dynamics.py:68-69, FLAGS.LAYER_NORM, the default of train_mpc_ppo.py:52):
  * tf.contrib.layers.layer_norm AFTER the activation of every hidden layer - moments over the last axis, centre and
  * scale.  gamma[l], beta[l] are [hidden_size] for hidden layer l (n_hidden of them); eps is the variance epsilon
- * (1e-12 in tf.contrib).  gamma == NULL switches LayerNorm off.  Verification mode only: with BCMPC_PREC_BF16_FAST
- * the call returns BCMPC_ERR_UNSUPPORTED. */
+ * (1e-12 in tf.contrib).  gamma == NULL switches LayerNorm off.  Call it after bcmpc_set_dynamics (new weights reset
+ * it).  Both precision modes; BCMPC_PREC_BF16_FAST supports it with uniform shooting only (BCMPC_ERR_UNSUPPORTED with a
+ * proposal network). */
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps);
 
 /* The six members of the normalisation 10-tuple that predict uses (dynamics.py:41,109-113). */

@@ -85,6 +85,33 @@ def test_policy_guided_fast_mode_tracks_oracle(proposal, bc, K):
     assert not np.array_equal(r1["action"], r3["action"])
 
 
+@pytest.mark.parametrize("S", [500, 256, 64])
+def test_layer_norm_fast_mode_tracks_oracle(S):
+    """FLAGS.LAYER_NORM dynamics (dynamics.py:68-69) on the tcgen05 path: un-normalised activations through the MMAs,
+    the per-row mean / variance correction applied in the next layer's epilogue."""
+    K, H = 1000, 15
+    rng, norm, state, pl, mpc = make_pair(23, (S, S), K, H, precision="bf16")
+    ln = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(2)]
+    pl.set_layer_norm(ln)
+    mpc.dyn_model.layer_norm = ln
+    actions = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    e = _norm_err(so, dbg["states"], norm)
+    print(dict(S=S, max_state_err_in_delta_std=float(np.abs(e).max()), one_step=float(np.abs(e[1]).max())))
+    assert np.abs(e[1]).max() < 0.1
+    assert np.abs(e).max() < 0.5
+    assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
+    rec = pl.plan(state, inj=actions)[0]
+    assert rec["index"] == int(np.argmin(co))
+    regret = (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std()
+    assert regret < 0.5
+    pl.set_layer_norm(None)                          # back to the plain network
+    mpc.dyn_model.layer_norm = None
+    so2, _, _ = pl.rollout_debug(state, actions)
+    assert np.abs(_norm_err(so2, mpc.rollout(state, actions)[0], norm)).max() < 0.25
+
+
 def test_fast_mode_sampling_batching_sharding_are_bit_consistent():
     import torch
     from bc_mpc_b200 import _lib as L
