@@ -41,8 +41,12 @@ def _check_cost(cost_fn):
 class _GpuShootingController(Controller):
     proposal = "uniform"
 
+    learned_reward = False      # True: maximise the model's predicted reward instead of minimising cheetah_cost_fn
+    gamma = 1.0
+
     def _init_common(self, env, dyn_model, horizon, cost_fn, num_simulated_paths, precision, device):
-        _check_cost(cost_fn)
+        if not self.learned_reward:
+            _check_cost(cost_fn)
         self.env, self.dyn_model, self.horizon, self.cost_fn = env, dyn_model, horizon, cost_fn
         self.num_simulated_paths = num_simulated_paths
         self.precision, self.device = precision, device
@@ -81,6 +85,8 @@ class _GpuShootingController(Controller):
             if getattr(dm, "layer_norm", False):
                 self._planner.set_layer_norm(dm.layer_norm_params)
             self._planner.set_normalization(*dm.normalization6())
+            if self.learned_reward:
+                dm.upload_reward_head(self._planner, self.gamma)
             self._dyn_version = dm.version
         pol = self._policy()
         if pol is not None and self._pol_version != pol.version:
@@ -144,3 +150,30 @@ class MPCcontroller_BC(_GpuShootingController):
 
     def get_action(self, state):
         return self._plan(state, None)
+
+
+class MPCcontrollerReward(_GpuShootingController):
+    """Random shooting on the learned reward (controllers.py:90-158): argmax over paths of sum_i gamma**i * reward_i
+    predicted by an NNDynamicsRewardModel.  cost_fn is accepted and ignored, like in the reference."""
+    learned_reward = True
+
+    def __init__(self, env, dyn_model, horizon=5, cost_fn=None, num_simulated_paths=10, gamma=1., precision="fp32", device=0):
+        self.gamma = gamma
+        self._init_common(env, dyn_model, horizon, cost_fn, num_simulated_paths, precision, device)
+
+    def get_action(self, state):
+        inj = self.sample_random_actions() if self._sampling_overridden() else None
+        return self._plan(state, inj)
+
+
+class MPCcontrollerPolicyNetReward(MPCcontrollerPolicyNet):
+    """Policy-proposal shooting on the learned reward (controllers.py:289-363): plain sum of predicted rewards (the
+    reference stores gamma but does not apply it, :345-352), argmax."""
+    learned_reward = True
+
+    def __init__(self, env, dyn_model, policy_net, explore=1., self_exp=True, horizon=5, cost_fn=None,
+                 num_simulated_paths=10, gamma=1., precision="fp32", device=0):
+        super().__init__(env, dyn_model, policy_net, explore=explore, self_exp=self_exp, horizon=horizon, cost_fn=cost_fn,
+                         num_simulated_paths=num_simulated_paths, precision=precision, device=device)
+        self.gamma = 1.0      # not applied by the reference
+        self.stored_gamma = gamma

@@ -36,7 +36,8 @@ struct bcmpc_handle {
   bcmpc_config cfg{};
   std::string err;
   cudaStream_t stream = nullptr;
-  DeviceMlp dyn, pol;
+  DeviceMlp dyn, pol, rew;       // rew: reward head of NNDynamicsRewardModel (bcmpc_set_reward_head)
+  double mean_reward = 0.0, std_reward = 1.0, gamma = 1.0;
   std::vector<float*> ln_bufs;   // LayerNorm gamma/beta of the dynamics net (bcmpc_set_layer_norm)
   NormArgs norm{};
   bool have_norm = false, have_bounds = false;
@@ -129,6 +130,7 @@ void update_verify_geometry(bcmpc_handle* h) {
   };
   scan(h->dyn);
   scan(h->pol);
+  scan(h->rew);
   h->vld = ld;
   h->vM = ld <= 512 ? 32 : 16;
 }
@@ -157,6 +159,7 @@ void fill_verify_args(bcmpc_handle* h, VerifyArgs* a) {
   a->n = h->norm;
   a->dyn = h->dyn.desc;
   if (h->pol.set) a->pol = h->pol.desc;
+  if (h->rew.set) { a->rew = h->rew.desc; a->mean_reward = h->mean_reward; a->std_reward = h->std_reward; a->gamma = h->gamma; }
   a->dyn_act = h->cfg.activation;
   a->ld = h->vld;
   a->has_filter = h->has_filter;
@@ -393,6 +396,7 @@ int bcmpc_destroy(bcmpc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->dyn.release();
   h->pol.release();
+  h->rew.release();
   for (float* p : h->ln_bufs) cudaFree(p);
   cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
   cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_lnvec); cudaFree(h->d_trace);
@@ -468,6 +472,24 @@ int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float
     h->dyn.desc.ln_beta[l] = db;
   }
   h->dyn.desc.ln_eps = eps;
+  return BCMPC_OK;
+}
+
+int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward,
+                          double std_reward, double gamma) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (h->cfg.precision == BCMPC_PREC_BF16_FAST)
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "learned-reward planners run in BCMPC_PREC_FP32_VERIFY only this round");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (!W) { h->rew.release(); update_verify_geometry(h); return BCMPC_OK; }
+  if (!b || !W[0] || !W[1] || !b[0] || !b[1]) return fail(h, BCMPC_ERR_INVALID, "null reward-head pointer");
+  if (h->cfg.n_hidden != 2) return fail(h, BCMPC_ERR_INVALID, "NNDynamicsRewardModel has a shared layer and one hidden layer per head: n_hidden must be 2");
+  const int sizes[3] = {h->cfg.hidden_size, h->cfg.hidden_size, 1};
+  int rc = upload_mlp(h, h->rew, 2, sizes, W, b);
+  if (rc) return rc;
+  h->mean_reward = mean_reward; h->std_reward = std_reward; h->gamma = gamma;
+  update_verify_geometry(h);
   return BCMPC_OK;
 }
 
@@ -638,6 +660,37 @@ int bcmpc_predict(bcmpc_handle* h, const double* states, const double* actions, 
   if (rc) { cleanup(); return rc; }
   CKC(cudaStreamSynchronize(h->stream));
   CKC(cudaMemcpy(next_states, d_o + n * D, sizeof(double) * n * D, cudaMemcpyDeviceToHost));
+  cleanup();
+  return BCMPC_OK;
+}
+
+int bcmpc_predict_reward(bcmpc_handle* h, const double* states, const double* actions, int64_t n, double* next_states,
+                         double* rewards) {
+  if (!h || !states || !actions || !next_states || !rewards) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (n < 1 || n > 0x7FFFFFFF) return fail(h, BCMPC_ERR_INVALID, "row count out of range");
+  if (!h->rew.set) return fail(h, BCMPC_ERR_STATE, "reward head not set (bcmpc_set_reward_head)");
+  int rc = check_ready(h, false);
+  if (rc) return rc;
+  CK(h, cudaSetDevice(h->cfg.device));
+  const int D = h->cfg.obs_dim, A = h->cfg.act_dim;
+  double *d_s = nullptr, *d_a = nullptr, *d_o = nullptr, *d_c = nullptr;
+  auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_a); cudaFree(d_o); cudaFree(d_c); };
+  CKC(cudaMalloc(&d_s, sizeof(double) * n * D));
+  CKC(cudaMalloc(&d_a, sizeof(double) * n * A));
+  CKC(cudaMalloc(&d_o, sizeof(double) * 2 * n * D));
+  CKC(cudaMalloc(&d_c, sizeof(double) * n));
+  CKC(cudaMemcpy(d_s, states, sizeof(double) * n * D, cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(d_a, actions, sizeof(double) * n * A, cudaMemcpyHostToDevice));
+  // one step, every row from its own state with its own action; the step objective is -reward * gamma^0
+  PlanArgs p = base_plan_args(h, 1, 0);
+  p.K = (int)n; p.H = 1; p.proposal = BCMPC_PROP_UNIFORM; p.inj_kind = kInjUniformBox;
+  p.states = d_s; p.inj = d_a; p.states_out = d_o; p.costs_out = d_c; p.per_row_states = 1;
+  rc = run_plan(h, p, nullptr, h->stream, /*force_verify=*/1);
+  if (rc) { cleanup(); return rc; }
+  CKC(cudaStreamSynchronize(h->stream));
+  CKC(cudaMemcpy(next_states, d_o + n * D, sizeof(double) * n * D, cudaMemcpyDeviceToHost));
+  CKC(cudaMemcpy(rewards, d_c, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) rewards[i] = -rewards[i];
   cleanup();
   return BCMPC_OK;
 }

@@ -35,6 +35,10 @@ struct VerifyArgs {
   float pol_std[kMaxAct];      // exp(logstd), float32 (distributions.py:65)
   float one_minus_explore;     // float32(1 - e): python scalar * float32 array (controllers.py:208)
   double explore;
+  // learned-reward planners (NNDynamicsRewardModel, dynamics.py:121-238; controllers.py:90-158,289-363): the reward head
+  // branches off the first hidden layer of `dyn`; the objective is minus the (discounted) sum of predicted rewards
+  MlpDesc rew;                 // 2 layers: hidden (dyn activation) and linear [hidden -> 1]; n_layers == 0: off
+  double mean_reward, std_reward, gamma;
 };
 
 constexpr int kVerifyThreads = 256;
@@ -44,7 +48,8 @@ constexpr int kVerifyThreads = 256;
 // coalesced LDG.128 that the M/8 row-group warps share through L1.
 template <int M>
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias, int in_pad,
-                                            int out_pad, const float* in_s, float* out_s, int ld, int act) {
+                                            int out_pad, const float* in_s, float* out_s, int ld, int act, int ld_out = 0) {
+  if (ld_out == 0) ld_out = ld;
   constexpr int MG = M / 8;
   constexpr int NS = (kVerifyThreads / 32) / MG;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,7 +91,7 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
       } else if (act == BCMPC_ACT_TANH) {
         o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
       }
-      *reinterpret_cast<float4*>(out_s + (mg * 8 + r) * ld + n) = o;
+      *reinterpret_cast<float4*>(out_s + (mg * 8 + r) * ld_out + n) = o;
     }
   }
 }
@@ -148,7 +153,8 @@ __global__ void __launch_bounds__(kVerifyThreads) rollout_verify_kernel(const __
   double* s_act0 = s_action + M * kMaxAct;                      // [M][kMaxAct] action of step 0
   double* s_inj = s_act0 + M * kMaxAct;                         // [M][kMaxAct]
   double* s_cost = s_inj + M * kMaxAct;                         // [M]
-  float* bufA = reinterpret_cast<float*>(s_cost + M);
+  float* s_rew = reinterpret_cast<float*>(s_cost + M);          // [M][4] reward-head output (column 0)
+  float* bufA = s_rew + M * 4;
   float* bufB = bufA + M * a.ld;
 
   const PlanArgs& p = a.p;
@@ -223,12 +229,35 @@ __global__ void __launch_bounds__(kVerifyThreads) rollout_verify_kernel(const __
       }
     }
     __syncthreads();
-    const float* y = run_mlp<M>(a.dyn, a.dyn_act, bufA, bufB, ld);   // dynamics.py:112
+    const float* y;
+    if (a.rew.n_layers == 0) {
+      y = run_mlp<M>(a.dyn, a.dyn_act, bufA, bufB, ld);   // dynamics.py:112
+    } else {
+      // NNDynamicsRewardModel.build_network (dynamics.py:162-193): shared layer, then the reward head (bufB must survive
+      // it), then the state-delta head
+      dense_layer<M>(a.dyn.W[0], a.dyn.b[0], a.dyn.in_pad[0], a.dyn.out_pad[0], bufA, bufB, ld, a.dyn_act);
+      __syncthreads();
+      if (a.dyn.ln_gamma[0]) { layer_norm_rows<M>(bufB, a.dyn.out_dim[0], a.dyn.out_pad[0], ld, a.dyn.ln_gamma[0], a.dyn.ln_beta[0], a.dyn.ln_eps); __syncthreads(); }
+      dense_layer<M>(a.rew.W[0], a.rew.b[0], a.rew.in_pad[0], a.rew.out_pad[0], bufB, bufA, ld, a.dyn_act);
+      __syncthreads();
+      if (a.rew.ln_gamma[0]) { layer_norm_rows<M>(bufA, a.rew.out_dim[0], a.rew.out_pad[0], ld, a.rew.ln_gamma[0], a.rew.ln_beta[0], a.rew.ln_eps); __syncthreads(); }
+      dense_layer<M>(a.rew.W[1], a.rew.b[1], a.rew.in_pad[1], a.rew.out_pad[1], bufA, s_rew, ld, -1, 4);
+      __syncthreads();
+      dense_layer<M>(a.dyn.W[1], a.dyn.b[1], a.dyn.in_pad[1], a.dyn.out_pad[1], bufB, bufA, ld, a.dyn_act);
+      __syncthreads();
+      if (a.dyn.ln_gamma[1]) { layer_norm_rows<M>(bufA, a.dyn.out_dim[1], a.dyn.out_pad[1], ld, a.dyn.ln_gamma[1], a.dyn.ln_beta[1], a.dyn.ln_eps); __syncthreads(); }
+      dense_layer<M>(a.dyn.W[2], a.dyn.b[2], a.dyn.in_pad[2], a.dyn.out_pad[2], bufA, bufB, ld, -1);
+      __syncthreads();
+      y = bufB;
+    }
     // ---- cost on the pre-step state (cost_functions.py:16-28), then s' = s + delta ----
     if (tid < M) {
       const double* s = s_state + tid * kMaxObs;
       double c = 0.0;
-      if (D > 17) {
+      if (a.rew.n_layers != 0) {
+        // controllers.py:137-139: rewards_all.append(reward * gamma ** i), reward = y * std_reward + mean_reward (dynamics.py:236)
+        c = -(((double)s_rew[tid * 4] * a.std_reward + a.mean_reward) * pow(a.gamma, (double)h));
+      } else if (D > 17) {
         if (s[5] >= 0.2) c += 10.0;
         if (s[6] >= 0.0) c += 10.0;
         if (s[7] >= 0.0) c += 10.0;
@@ -277,7 +306,7 @@ __global__ void __launch_bounds__(kVerifyThreads) rollout_verify_kernel(const __
 }
 
 inline size_t verify_smem_bytes(int M, int ld) {
-  return (size_t)M * (kMaxObs + 3 * kMaxAct + 1) * sizeof(double) + 2 * (size_t)M * ld * sizeof(float);
+  return (size_t)M * (kMaxObs + 3 * kMaxAct + 1) * sizeof(double) + (size_t)M * 4 * sizeof(float) + 2 * (size_t)M * ld * sizeof(float);
 }
 
 // Stand-alone forward of the proposal network: policy_net.act / BCnetwork.predict.

@@ -71,3 +71,44 @@ class NNDynamicsModel:
             p.set_normalization(*self.normalization6())
             self._predictor = p
         return self._predictor.predict(s, a)
+
+
+class NNDynamicsRewardModel(NNDynamicsModel):
+    """Drop-in for the inference side of NNDynamicsRewardModel (dynamics.py:121-238): a shared tanh layer of 500 units, a
+    tanh + linear head for the normalised state delta and a tanh + linear head for the normalised reward.  ``predict``
+    returns ``(next_states, rewards[n,1])`` (dynamics.py:221-238).  The reference hard-codes size 500 and tanh
+    (build_network, :162); both are parameters here with those defaults."""
+
+    def __init__(self, env, normalization, batch_size=None, iterations=None, learning_rate=None, sess=None, size=500,
+                 activation="tanh", layer_norm=False):
+        super().__init__(env, n_layers=2, size=size, activation=activation, normalization=normalization,
+                         batch_size=batch_size, iterations=iterations, learning_rate=learning_rate, sess=sess,
+                         layer_norm=layer_norm)
+        self.reward_weights = None
+
+    def set_weights(self, weights, reward_weights, layer_norm_params=None):
+        """weights: share, delta-hidden, delta-out; reward_weights: reward-hidden, reward-out (TF creation order:
+        dense, dense_1, dense_2, dense_3, dense_4 under scope NNDynamicsModel)."""
+        self.reward_weights = [(np.asarray(w, np.float32), np.asarray(b, np.float32)) for w, b in reward_weights]
+        super().set_weights(weights, layer_norm_params)
+
+    def load_vars(self, var_dict):
+        names = ["dense", "dense_1", "dense_2", "dense_3", "dense_4"]
+        ws = [(var_dict[f"{self.scope}/{n}/kernel:0"], var_dict[f"{self.scope}/{n}/bias:0"]) for n in names]
+        self.set_weights(ws[:3], ws[3:])
+
+    def upload_reward_head(self, planner, gamma=1.0):
+        planner.set_reward_head(self.reward_weights, float(np.asarray(self.mean_reward)), float(np.asarray(self.std_reward)), gamma)
+
+    def predict(self, unnormalized_state, unnormalized_action):
+        if self.weights is None:
+            raise RuntimeError("NNDynamicsRewardModel has no weights (set_weights / load_vars)")
+        if self._predictor is None:
+            p = Planner(self.obs_dim, self.act_dim, 2, self.size, self.activation, num_paths=1, horizon=1, precision="fp32")
+            p.set_dynamics(self.weights)
+            if self.layer_norm:
+                p.set_layer_norm(self.layer_norm_params)
+            p.set_normalization(*self.normalization6())
+            self.upload_reward_head(p)
+            self._predictor = p
+        return self._predictor.predict_reward(np.asarray(unnormalized_state, np.float64), np.asarray(unnormalized_action, np.float64))

@@ -94,6 +94,30 @@ class Planner:
                 raise ValueError(f"LayerNorm gamma/beta must be [{self.cfg.hidden_size}]")
         self._ck(self._lib.bcmpc_set_layer_norm(self._h, L.ptr_array(gs), L.ptr_array(bs), len(gs), C.c_float(eps)))
 
+    def set_reward_head(self, weights, mean_reward=0.0, std_reward=1.0, gamma=1.0):
+        """Reward head of NNDynamicsRewardModel (dynamics.py:175-178): weights = [(kernel[S,S], bias[S]), (kernel[S,1], bias[1])],
+        or None to go back to cheetah_cost_fn.  The planner then maximises sum_i gamma**i * reward_i (controllers.py:121-158)."""
+        if weights is None:
+            self._ck(self._lib.bcmpc_set_reward_head(self._h, None, None, 0.0, 1.0, 1.0))
+            return
+        Ws = [np.ascontiguousarray(w, np.float32) for w, _ in weights]
+        bs = [np.ascontiguousarray(b, np.float32).reshape(-1) for _, b in weights]
+        S = self.cfg.hidden_size
+        if len(Ws) != 2 or Ws[0].shape != (S, S) or Ws[1].shape != (S, 1) or bs[0].shape != (S,) or bs[1].shape != (1,):
+            raise ValueError(f"reward head must be [({S},{S}), ({S},1)] kernels")
+        self._ck(self._lib.bcmpc_set_reward_head(self._h, L.ptr_array(Ws), L.ptr_array(bs), float(mean_reward),
+                                                 float(std_reward), float(gamma)))
+
+    def predict_reward(self, states, actions):
+        """NNDynamicsRewardModel.predict (dynamics.py:221-238): (next_states [n,D], rewards [n,1])."""
+        states, actions = _f64(states), _f64(actions)
+        n = states.shape[0]
+        if states.shape != (n, self.D) or actions.shape != (n, self.A):
+            raise ValueError(f"predict expects states [n,{self.D}] and actions [n,{self.A}]")
+        out, rew = np.empty_like(states), np.empty(n)
+        self._ck(self._lib.bcmpc_predict_reward(self._h, L.ptr(states), L.ptr(actions), n, L.ptr(out), L.ptr(rew)))
+        return out, rew.reshape(n, 1)
+
     def set_normalization(self, mean_obs, std_obs, mean_action, std_action, mean_deltas, std_deltas):
         a = [_f64(mean_obs, (self.D,)), _f64(std_obs, (self.D,)), _f64(mean_action, (self.A,)),
              _f64(std_action, (self.A,)), _f64(mean_deltas, (self.D,)), _f64(std_deltas, (self.D,))]

@@ -108,6 +108,20 @@ int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* cons
  * proposal network). */
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps);
 
+/* Learned-reward planners: NNDynamicsRewardModel (dynamics.py:121-238) = the dynamics net (n_hidden = 2: shared layer,
+ * delta-head hidden layer, delta output) plus a reward head that branches off the shared layer: W[0] [hidden,hidden]
+ * with the dynamics activation, W[1] [hidden,1] linear.  With a reward head the planner maximises the sum of
+ * gamma^i * (y_r * std_reward + mean_reward) (MPCcontrollerReward.get_action, controllers.py:121-158; gamma = 1 gives
+ * MPCcontrollerPolicyNetReward, :319-363): bcmpc_record.cost is MINUS that sum, index / action its argmax (first index
+ * on ties, like np.argmax).  W == NULL switches back to cheetah_cost_fn.  Call after bcmpc_set_dynamics.
+ * Verification mode only (BCMPC_ERR_UNSUPPORTED with BCMPC_PREC_BF16_FAST). */
+int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward,
+                          double std_reward, double gamma);
+
+/* NNDynamicsRewardModel.predict (dynamics.py:221-238): next_states [n,D] and rewards [n].  HOST buffers. */
+int bcmpc_predict_reward(bcmpc_handle* h, const double* states, const double* actions, int64_t n, double* next_states,
+                         double* rewards);
+
 /* The six members of the normalisation 10-tuple that predict uses (dynamics.py:41,109-113). */
 int bcmpc_set_normalization(bcmpc_handle* h, const double* mean_obs, const double* std_obs,
                             const double* mean_act, const double* std_act,

@@ -17,6 +17,7 @@ What is restated and what it follows (citations into the reference tree):
   per ``distributions.py:79-80``; ``mode = mean`` ``distributions.py:68-69``).
 * ``OracleBC.predict``            - ``behavioral_cloning.py:21-26,44-47``.
 * ``cheetah_cost_fn`` / ``trajectory_cost_fn`` - ``cost_functions.py:9-63``.
+* ``OracleRewardDynamics.predict`` - ``dynamics.py:121-238`` (shared tanh layer, delta head, reward head).
 * ``OracleMPC.get_action``        - ``controllers.py:57-88`` (uniform shooting),
   ``controllers.py:189-237`` (policy proposals) and the legacy
   ``MPCcontroller_BC`` recovered from ``controllers.pyc``.
@@ -151,6 +152,54 @@ class OracleDynamics:
         return s + delta  # :116
 
 
+class OracleRewardDynamics(OracleDynamics):
+    """NNDynamicsRewardModel (dynamics.py:121-238) without TensorFlow: a shared tanh layer, a tanh + linear head that
+    predicts the normalised state delta and a tanh + linear head that predicts the normalised reward (:162-193).
+
+    weights: [(kernel, bias)] x 3 for share / delta-hidden / delta-out (names dense, dense_1, dense_2 in creation order)
+    reward_weights: [(kernel, bias)] x 2 for reward-hidden / reward-out (dense_3, dense_4).
+    normalization must carry mean_reward / std_reward (utils.py:158 order when it is the 10-tuple).
+    layer_norm: [(gamma, beta)] for share and delta-hidden; reward_layer_norm: (gamma, beta) for reward-hidden.
+    predict returns (next_state float64 [K,D], reward float64 [K,1]) like dynamics.py:221-238."""
+
+    def __init__(self, weights, reward_weights, normalization, layer_norm=None, reward_layer_norm=None):
+        super().__init__(weights, normalization, activation="tanh", layer_norm=layer_norm)
+        self.reward_weights = [(np.asarray(w, np.float32), np.asarray(b, np.float32)) for w, b in reward_weights]
+        if isinstance(normalization, dict):
+            self.mean_reward, self.std_reward = normalization["mean_reward"], normalization["std_reward"]
+        else:
+            self.mean_reward, self.std_reward = normalization[4], normalization[5]
+        self.mean_reward = np.float64(self.mean_reward)
+        self.std_reward = np.float64(self.std_reward)
+        self.reward_layer_norm = reward_layer_norm
+
+    def heads(self, x):
+        x = np.asarray(x, np.float32)
+        (w0, b0), (w1, b1), (w2, b2) = self.weights
+        (r1, c1), (r2, c2) = self.reward_weights
+        share = np.tanh(_dense(x, w0, b0)).astype(np.float32)                       # dynamics.py:165 / :181
+        if self.layer_norm is not None:
+            share = _layer_norm(share, *[np.asarray(t, np.float32) for t in self.layer_norm[0]])
+        d = np.tanh(_dense(share, w1, b1)).astype(np.float32)                       # :169 / :183
+        if self.layer_norm is not None:
+            d = _layer_norm(d, *[np.asarray(t, np.float32) for t in self.layer_norm[1]])
+        delta = _dense(d, w2, b2)                                                   # :172 / :184
+        r = np.tanh(_dense(share, r1, c1)).astype(np.float32)                       # :175 / :187
+        if self.reward_layer_norm is not None:
+            r = _layer_norm(r, *[np.asarray(t, np.float32) for t in self.reward_layer_norm])
+        reward = _dense(r, r2, c2)                                                  # :178 / :188
+        return delta, reward
+
+    def predict(self, unnormalized_state, unnormalized_action):
+        s = np.asarray(unnormalized_state)
+        a = np.asarray(unnormalized_action)
+        ns = (s - self.mean_obs) / (self.std_obs + 1e-10)                           # :224
+        na = (a - self.mean_action) / (self.std_action + 1e-10)                     # :225
+        delta, reward = self.heads(np.concatenate([ns.astype(np.float32), na.astype(np.float32)], axis=1))
+        nxt = s + (delta * self.std_deltas + self.mean_deltas)                      # :233-234
+        return nxt, reward * self.std_reward + self.mean_reward                    # :236
+
+
 class OraclePolicy:
     """MlpPolicy 'pol' branch + act (ppo_bc_policy.py:56-60,66-88,174-185)."""
 
@@ -227,7 +276,7 @@ class OracleMPC:
     """
 
     def __init__(self, dyn_model, horizon, num_simulated_paths, cost_fn=cheetah_cost_fn,
-                 proposal="uniform", policy=None, explore=1.0):
+                 proposal="uniform", policy=None, explore=1.0, learned_reward=False, gamma=1.0):
         self.dyn_model = dyn_model
         self.horizon = horizon
         self.num_simulated_paths = num_simulated_paths
@@ -235,6 +284,11 @@ class OracleMPC:
         self.proposal = proposal
         self.policy = policy
         self.explore = explore
+        # learned-reward planners: MPCcontrollerReward (controllers.py:121-158, sum of gamma**i * reward, argmax) and
+        # MPCcontrollerPolicyNetReward (:319-363, plain sum, argmax).  ``costs`` are then MINUS the reward sums, so
+        # that argmin(costs) == argmax(rewards) with the same first-index tie rule.
+        self.learned_reward = learned_reward
+        self.gamma = gamma
 
     def rollout(self, state, inj):
         K, H = self.num_simulated_paths, self.horizon
@@ -243,6 +297,7 @@ class OracleMPC:
         states = np.tile(state, [K, 1])  # controllers.py:63
         states_all = [states]
         actions_all = []
+        rewards_all = []
         for i in range(H):
             if self.proposal == "uniform":
                 actions = inj[i, :, :]  # :70
@@ -256,11 +311,18 @@ class OracleMPC:
                 actions += inj[i, :, :]  # in place: float32 array += float64 draw stays float32
             else:
                 raise ValueError(self.proposal)
-            states = self.dyn_model.predict(states, actions)  # :70 / :210
+            if self.learned_reward:
+                states, reward = self.dyn_model.predict(states, actions)  # :137 / :340
+                rewards_all.append(reward * self.gamma ** i)  # :139 (gamma = 1 reproduces :345)
+            else:
+                states = self.dyn_model.predict(states, actions)  # :70 / :210
             states_all.append(states)
             actions_all.append(actions)
         states_all = np.asarray(states_all)  # :74
         actions_all = np.asarray(actions_all)
+        if self.learned_reward:
+            total = np.reshape(np.sum(np.asarray(rewards_all), axis=0), [-1])  # :151-153
+            return states_all, actions_all, -np.asarray(total, np.float64)
         costs = trajectory_cost_fn(self.cost_fn, states_all[:-1], actions_all, states_all[1:])  # :80
         return states_all, actions_all, np.asarray(costs, np.float64)
 
@@ -318,6 +380,18 @@ def synthetic_problem(seed, hidden=(500, 500), obs_dim=20, act_dim=6, bias_scale
     weights = glorot_mlp(rng, (obs_dim + act_dim, *hidden, obs_dim), bias_scale)
     state = synthetic_state(rng, norm)
     return rng, norm, weights, state
+
+
+def synthetic_reward_problem(seed, hidden=500, obs_dim=20, act_dim=6, bias_scale=0.1):
+    """NNDynamicsRewardModel inputs: shared + delta-head weights (3 layers), reward-head weights (2 layers), and a
+    normalisation dict that also carries mean_reward / std_reward."""
+    rng = np.random.default_rng(seed)
+    norm = synthetic_normalization(obs_dim, act_dim)
+    norm["mean_reward"], norm["std_reward"] = 0.3, 1.7
+    weights = glorot_mlp(rng, (obs_dim + act_dim, hidden, hidden, obs_dim), bias_scale)
+    reward_weights = glorot_mlp(rng, (hidden, hidden, 1), bias_scale)
+    state = synthetic_state(rng, norm)
+    return rng, norm, weights, reward_weights, state
 
 
 def synthetic_policy(rng, obs_dim=20, act_dim=6, hidden=(128, 128), norm=None):

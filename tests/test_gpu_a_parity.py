@@ -109,6 +109,85 @@ def test_layer_norm_dynamics_variant():
         make_pair(17, (S, S), 128, 2, precision="bf16", proposal="policy_mix")[3].set_layer_norm(ln)
 
 
+@pytest.mark.parametrize("proposal,gamma", [("uniform", 0.9), ("uniform", 1.0), ("policy_mix", 1.0)])
+def test_learned_reward_planners(proposal, gamma):
+    """NNDynamicsRewardModel + MPCcontrollerReward / MPCcontrollerPolicyNetReward (dynamics.py:121-238,
+    controllers.py:90-158,289-363): shared tanh layer, delta head, reward head; argmax of the (discounted) reward sum."""
+    from bc_mpc_b200 import Planner
+    K, H, S = 1000, 10, 500
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(29, S)
+    dyn = O.OracleRewardDynamics(weights, rweights, norm)
+    pl = Planner(20, 6, 2, S, "tanh", num_paths=K, horizon=H, precision="fp32", proposal=proposal, explore=0.4)
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], gamma)
+    pol = None
+    if proposal != "uniform":
+        pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
+        pol = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
+        pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+    mpc = O.OracleMPC(dyn, H, K, proposal=proposal, policy=pol, explore=0.4, learned_reward=True, gamma=gamma)
+    inj = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, inj, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, inj)
+    assert scaled_rel_err(so, dbg["states"], state_scale(norm)).max() < TOL
+    assert np.abs(co - dbg["costs"]).max() < 1e-3 * max(1.0, np.abs(dbg["costs"]).max())
+    rec = pl.plan(state, inj=inj)[0]
+    assert rec["index"] == dbg["argmin"]
+    assert np.allclose(rec["action"][:6], act, rtol=1e-5, atol=1e-6)
+    # single-step predict with reward (dynamics.py:221-238)
+    n = 200
+    Sx = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((n, 20))
+    Ax = f32_uniform(rng, (n, 6))
+    nxt, rew = pl.predict_reward(Sx, Ax)
+    wn, wr = dyn.predict(Sx, Ax)
+    assert scaled_rel_err(nxt, wn, state_scale(norm)).max() < 1e-5
+    assert np.abs(rew - wr).max() < 1e-4
+    pl.set_reward_head(None)          # back to cheetah_cost_fn
+    _, _, co2 = pl.rollout_debug(state, inj)
+    assert np.abs(co2 - co).max() > 1e-3
+
+
+def test_learned_reward_controllers_drop_in():
+    """The reference-shaped classes end to end: NNDynamicsRewardModel + MPCcontrollerReward /
+    MPCcontrollerPolicyNetReward with sample_random_actions overridden (controllers.py:119,325)."""
+    from bc_mpc_b200 import controllers, dynamics, policy
+
+    class Space:
+        def __init__(self, n):
+            self.low, self.high, self.shape = -np.ones(n), np.ones(n), (n,)
+
+    class Env:
+        action_space, observation_space = Space(6), Space(20)
+
+    K, H, S = 300, 6, 500
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(31, S)
+    n10 = (norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_reward"],
+           norm["std_reward"], None, None, norm["mean_deltas"], norm["std_deltas"])
+    dm = dynamics.NNDynamicsRewardModel(Env(), n10)
+    dm.set_weights(weights, rweights)
+    od = O.OracleRewardDynamics(weights, rweights, norm)
+    inj = f32_uniform(rng, (H, K, 6))
+    c = controllers.MPCcontrollerReward(Env(), dm, horizon=H, cost_fn=None, num_simulated_paths=K, gamma=0.95)
+    c.sample_random_actions = lambda: inj
+    want = O.OracleMPC(od, H, K, learned_reward=True, gamma=0.95).get_action(state, inj)
+    assert np.allclose(c.get_action(state), want, rtol=1e-5, atol=1e-6)
+    nxt, rew = dm.predict(state[None], inj[0, :1])
+    wn, wr = od.predict(state[None], inj[0, :1])
+    assert rew.shape == (1, 1) and np.abs(rew - wr).max() < 1e-4
+    assert scaled_rel_err(nxt, wn, state_scale(norm)).max() < 1e-5
+
+    pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
+    pol = policy.MlpPolicy(None, Env(), 128, 2)
+    pol.set_weights(pw, logstd, rms_mean, rms_std)
+    pc = controllers.MPCcontrollerPolicyNetReward(Env(), dm, pol, explore=0.3, self_exp=False, horizon=H, cost_fn=None,
+                                                  num_simulated_paths=K, gamma=0.5)
+    pc.sample_random_actions = lambda: inj
+    op = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
+    want = O.OracleMPC(od, H, K, proposal="policy_mix", policy=op, explore=0.3, learned_reward=True, gamma=1.0).get_action(state, inj)
+    assert np.allclose(pc.get_action(state), want, rtol=1e-5, atol=1e-6)
+
+
 def test_threshold_and_tie_cases():
     K, H = 256, 4
     rng, norm, state, pl, mpc = make_pair(11, (64, 64), K, H)

@@ -82,3 +82,39 @@ def test_sample_random_actions_layout(ref):
     c = ctl.MPCcontroller(_Env(), None, horizon=3, cost_fn=None, num_simulated_paths=5)
     a = c.sample_random_actions()
     assert a.shape == (3, 5, 6) and a.dtype == np.float64 and (a >= -1).all() and (a < 1).all()
+
+
+@pytest.mark.parametrize("gamma", [1.0, 0.9])
+def test_learned_reward_controller_matches_reference(ref, gamma):
+    """MPCcontrollerReward (controllers.py:90-158): sum of gamma**i * predicted reward, argmax, first action."""
+    ctl, _ = ref
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(6, 40)
+    dyn = O.OracleRewardDynamics(weights, rweights, norm)
+    H, K = 6, 300
+    actions = rng.uniform(-1, 1, (H, K, 6))
+    c = ctl.MPCcontrollerReward(_Env(), dyn, horizon=H, num_simulated_paths=K, gamma=gamma)
+    c.sample_random_actions = lambda: actions
+    want = c.get_action(state)
+    got, dbg = O.OracleMPC(dyn, H, K, learned_reward=True, gamma=gamma).get_action(state, actions, return_debug=True)
+    assert np.array_equal(want, got)
+    assert dbg["costs"].shape == (K,)
+
+
+def test_learned_reward_policy_controller_matches_reference(ref, capsys):
+    """MPCcontrollerPolicyNetReward (controllers.py:289-363): policy proposals, plain reward sum, argmax."""
+    ctl, _ = ref
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(7, 40)
+    dyn = O.OracleRewardDynamics(weights, rweights, norm)
+    pol = O.OraclePolicy(*O.synthetic_policy(rng, hidden=(16, 16), norm=norm))
+    H, K = 5, 200
+    uni = rng.uniform(-1, 1, (H, K, 6))
+
+    class _Det:      # deterministic branch: act(stochastic=False) is the mean
+        def act(self, ob, stochastic=True):
+            return pol.act(ob, stochastic=False)
+
+    c = ctl.MPCcontrollerPolicyNetReward(_Env(), dyn, _Det(), explore=0.3, self_exp=False, horizon=H, num_simulated_paths=K, gamma=0.5)
+    c.sample_random_actions = lambda: uni
+    want = c.get_action(state)
+    got = O.OracleMPC(dyn, H, K, proposal="policy_mix", policy=pol, explore=0.3, learned_reward=True, gamma=1.0).get_action(state, uni)
+    assert np.allclose(want, got, rtol=0, atol=0)
