@@ -14,7 +14,7 @@ class Config(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("n_hidden", C.c_int32),
                 ("hidden_size", C.c_int32), ("activation", C.c_int32), ("num_paths", C.c_int32),
                 ("horizon", C.c_int32), ("max_states", C.c_int32), ("precision", C.c_int32),
-                ("proposal", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32),
+                ("proposal", C.c_int32), ("device", C.c_int32), ("first_proposal", C.c_int32),
                 ("path_offset", C.c_int64), ("total_paths", C.c_int64), ("explore", C.c_double)]
 
 
@@ -27,7 +27,7 @@ assert RECORD_DTYPE.itemsize == C.sizeof(Record) == 80
 
 ACT_RELU, ACT_TANH = 0, 1
 PREC_FP32_VERIFY, PREC_BF16_FAST = 0, 1
-PROP_UNIFORM, PROP_POLICY_GAUSSIAN, PROP_POLICY_MIX, PROP_NET_PLUS_UNIFORM = 0, 1, 2, 3
+PROP_UNIFORM, PROP_POLICY_GAUSSIAN, PROP_POLICY_MIX, PROP_NET_PLUS_UNIFORM, PROP_POLICY_MEAN = 0, 1, 2, 3, 4
 
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)

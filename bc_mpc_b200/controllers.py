@@ -40,6 +40,7 @@ def _check_cost(cost_fn):
 
 class _GpuShootingController(Controller):
     proposal = "uniform"
+    first_proposal = None       # tree-search planner only: proposal mode of step 0
 
     learned_reward = False      # True: maximise the model's predicted reward instead of minimising cheetah_cost_fn
     gamma = 1.0
@@ -71,15 +72,19 @@ class _GpuShootingController(Controller):
     def _explore(self):
         return 1.0
 
-    def _ensure_planner(self):
+    def _ensure_planner(self, n_states=1):
         dm = self.dyn_model
+        if self._planner is not None and n_states > self._planner.max_states:
+            self._planner.close()        # grow: one handle sized for the largest batch of root states seen so far
+            self._planner = None
         if self._planner is None:
             self._planner = Planner(dm.obs_dim, dm.act_dim, dm.n_layers, dm.size, dm.activation,
-                                    num_paths=self.num_simulated_paths, horizon=self.horizon, max_states=1,
+                                    num_paths=self.num_simulated_paths, horizon=self._planner_horizon(),
+                                    max_states=1 if n_states == 1 else 1 << (n_states - 1).bit_length(),
                                     precision=self.precision, proposal=self.proposal, explore=self._explore(),
-                                    device=self.device)
+                                    device=self.device, first_proposal=self.first_proposal)
             self._planner.set_action_bounds(self.env.action_space.low, self.env.action_space.high)
-            self._dyn_version = None
+            self._dyn_version = self._pol_version = None
         if self._dyn_version != dm.version:     # weights change after every dyn_model.fit (train_mpc_ppo.py:279)
             self._planner.set_dynamics(dm.weights)
             if getattr(dm, "layer_norm", False):
@@ -94,12 +99,29 @@ class _GpuShootingController(Controller):
             self._pol_version = pol.version
         return self._planner
 
+    def _planner_horizon(self):
+        return self.horizon
+
     def _plan(self, state, inj):
         p = self._ensure_planner()
         seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
         rec = p.plan(np.asarray(state, np.float64), inj=inj, seed=seed)[0]
         self.last_record = rec
         return copy.copy(rec["action"][: self.dyn_model.act_dim])   # float64 [A] (controllers.py:85)
+
+    def get_actions(self, states):
+        """Batched get_action: states [B,D] -> actions [B,A], all B plans in ONE launch (B x K paths in flight).  Not
+        in the reference, whose samplers call get_action once per env step (utils.py:115,200); this is what a
+        vectorised sampler over many envs calls (sampling.sample_vectorized).  Randomness: device Philox, counter
+        (path, root state, step), so every root state gets its own K action sequences."""
+        states = np.ascontiguousarray(states, np.float64)
+        if states.ndim != 2:
+            raise ValueError(f"states must be [B, obs_dim], got {states.shape}")
+        p = self._ensure_planner(states.shape[0])
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
+        recs = p.plan(states, seed=seed)
+        self.last_record = recs
+        return recs["action"][:, : self.dyn_model.act_dim].copy()
 
 
 class MPCcontroller(_GpuShootingController):
@@ -177,3 +199,43 @@ class MPCcontrollerPolicyNetReward(MPCcontrollerPolicyNet):
                          num_simulated_paths=num_simulated_paths, precision=precision, device=device)
         self.gamma = 1.0      # not applied by the reference
         self.stored_gamma = gamma
+
+
+class MCTScontrollerPolicyNetReward(_GpuShootingController):
+    """Two-stage search on the learned reward (controllers.py:365-457): num_first_stage_actions candidate first actions
+    (uniform, stochastic policy or deterministic policy), each continued for `horizon` steps under the deterministic
+    policy; score = reward_1 + mean over the rollouts of the summed rewards, argmax; returns the [1,A] action.
+
+    The reference runs random_path_per_action copies of every continuation, but act(stochastic=False) (:433) makes
+    the copies identical, so their mean is the single value; one fused launch of N paths x (horizon + 1) steps with
+    the step-0 proposal switched computes the same scores.  random_path_per_action is kept for the signature."""
+    learned_reward = True
+    proposal = "policy_mean"
+
+    def __init__(self, env, dyn_model, policy_net, explore=1., self_exp=True, horizon=5, cost_fn=None,
+                 num_first_stage_actions=10, random_path_per_action=10, random_first_stage_action=False,
+                 precision="fp32", device=0):
+        self.policy_net, self.self_exp, self.explore = policy_net, self_exp, explore
+        self.num_first_stage_actions, self.random_path_per_action = num_first_stage_actions, random_path_per_action
+        self.random_first_stage_action = random_first_stage_action
+        self.first_proposal = ("uniform" if random_first_stage_action else "policy_gaussian" if self_exp else "policy_mean")
+        self._init_common(env, dyn_model, horizon, cost_fn, num_first_stage_actions, precision, device)
+
+    def _planner_horizon(self):
+        return self.horizon + 1          # the first-stage step plus `horizon` continuation steps (:431)
+
+    def _policy(self):
+        return self.policy_net
+
+    def sample_first_stage(self):
+        """Override to inject the first-stage randomness: [N,A] actions (random_first_stage_action) or N(0,1) noise
+        (self_exp).  None = drawn on the device."""
+        return None
+
+    def get_action(self, state):
+        z = self.sample_first_stage()
+        inj = None
+        if z is not None:
+            inj = np.zeros((self.horizon + 1, self.num_first_stage_actions, self.dyn_model.act_dim))
+            inj[0] = z
+        return self._plan(state, inj)[None, :]        # the reference returns action_1 with its batch axis (:455)

@@ -143,12 +143,15 @@ int inj_kind_of(int proposal) {
   }
 }
 
+int first_proposal_of(const bcmpc_config& c) { return c.first_proposal > 0 ? c.first_proposal - 1 : c.proposal; }
+bool needs_policy(const bcmpc_config& c) { return c.proposal != BCMPC_PROP_UNIFORM || first_proposal_of(c) != BCMPC_PROP_UNIFORM; }
+
 int check_ready(bcmpc_handle* h, bool need_policy) {
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics)");
   if (!h->have_norm) return fail(h, BCMPC_ERR_STATE, "normalisation not set (bcmpc_set_normalization)");
   if (need_policy) {
     if (!h->pol.set) return fail(h, BCMPC_ERR_STATE, "proposal network not set (bcmpc_set_policy)");
-    if (h->cfg.proposal == BCMPC_PROP_POLICY_GAUSSIAN && !h->has_logstd)
+    if ((h->cfg.proposal == BCMPC_PROP_POLICY_GAUSSIAN || first_proposal_of(h->cfg) == BCMPC_PROP_POLICY_GAUSSIAN) && !h->has_logstd)
       return fail(h, BCMPC_ERR_STATE, "POLICY_GAUSSIAN needs logstd in bcmpc_set_policy");
   }
   return BCMPC_OK;
@@ -328,6 +331,8 @@ PlanArgs base_plan_args(bcmpc_handle* h, int B, uint64_t seed) {
   p.D = h->cfg.obs_dim; p.A = h->cfg.act_dim; p.K = h->cfg.num_paths; p.H = h->cfg.horizon; p.B = B;
   p.proposal = h->cfg.proposal;
   p.inj_kind = inj_kind_of(h->cfg.proposal);
+  p.proposal0 = first_proposal_of(h->cfg);
+  p.inj_kind0 = inj_kind_of(p.proposal0);
   p.path_offset = h->cfg.path_offset;
   p.seed = seed;
   return p;
@@ -355,7 +360,8 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   if (c.max_states < 1) return fail(nullptr, BCMPC_ERR_INVALID, "max_states must be >= 1");
   if (c.activation != BCMPC_ACT_RELU && c.activation != BCMPC_ACT_TANH) return fail(nullptr, BCMPC_ERR_INVALID, "unknown activation %d", c.activation);
   if (c.precision != BCMPC_PREC_FP32_VERIFY && c.precision != BCMPC_PREC_BF16_FAST) return fail(nullptr, BCMPC_ERR_INVALID, "unknown precision %d", c.precision);
-  if (c.proposal < BCMPC_PROP_UNIFORM || c.proposal > BCMPC_PROP_NET_PLUS_UNIFORM) return fail(nullptr, BCMPC_ERR_INVALID, "unknown proposal %d", c.proposal);
+  if (c.proposal < BCMPC_PROP_UNIFORM || c.proposal > BCMPC_PROP_POLICY_MEAN) return fail(nullptr, BCMPC_ERR_INVALID, "unknown proposal %d", c.proposal);
+  if (c.first_proposal < 0 || c.first_proposal > 1 + BCMPC_PROP_POLICY_MEAN) return fail(nullptr, BCMPC_ERR_INVALID, "unknown first_proposal %d", c.first_proposal);
   if (c.path_offset < 0 || c.path_offset + c.num_paths > 0xFFFFFFFFLL) return fail(nullptr, BCMPC_ERR_INVALID, "path_offset out of range");
   if (c.precision == BCMPC_PREC_BF16_FAST) {
     std::string why;
@@ -566,7 +572,7 @@ int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states,
                       bcmpc_record* d_out, void* stream) {
   if (!h || !d_states || !d_out) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_states < 1 || n_states > h->cfg.max_states) return fail(h, BCMPC_ERR_INVALID, "n_states %d out of [1,%d]", n_states, h->cfg.max_states);
-  int rc = check_ready(h, h->cfg.proposal != BCMPC_PROP_UNIFORM);
+  int rc = check_ready(h, needs_policy(h->cfg));
   if (rc) return rc;
   CK(h, cudaSetDevice(h->cfg.device));
   PlanArgs p = base_plan_args(h, n_states, seed);
@@ -606,7 +612,7 @@ int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const do
 int bcmpc_rollout_debug(bcmpc_handle* h, const double* state, const double* inj, uint64_t seed, double* states_out,
                         double* actions_out, double* costs_out) {
   if (!h || !state) return fail(h, BCMPC_ERR_INVALID, "null argument");
-  int rc = check_ready(h, h->cfg.proposal != BCMPC_PROP_UNIFORM);
+  int rc = check_ready(h, needs_policy(h->cfg));
   if (rc) return rc;
   CK(h, cudaSetDevice(h->cfg.device));
   const int D = h->cfg.obs_dim, A = h->cfg.act_dim, K = h->cfg.num_paths, H = h->cfg.horizon;
@@ -654,7 +660,7 @@ int bcmpc_predict(bcmpc_handle* h, const double* states, const double* actions, 
   CKC(cudaMemcpy(d_a, actions, sizeof(double) * n * A, cudaMemcpyHostToDevice));
   // one step, every row from its own state with its own action: the predict of dynamics.py:106-119
   PlanArgs p = base_plan_args(h, 1, 0);
-  p.K = (int)n; p.H = 1; p.proposal = BCMPC_PROP_UNIFORM; p.inj_kind = kInjUniformBox;
+  p.K = (int)n; p.H = 1; p.proposal = p.proposal0 = BCMPC_PROP_UNIFORM; p.inj_kind = p.inj_kind0 = kInjUniformBox;
   p.states = d_s; p.inj = d_a; p.states_out = d_o; p.per_row_states = 1;
   rc = run_plan(h, p, nullptr, h->stream, /*force_verify=*/h->cfg.precision != BCMPC_PREC_BF16_FAST);
   if (rc) { cleanup(); return rc; }
@@ -683,7 +689,7 @@ int bcmpc_predict_reward(bcmpc_handle* h, const double* states, const double* ac
   CKC(cudaMemcpy(d_a, actions, sizeof(double) * n * A, cudaMemcpyHostToDevice));
   // one step, every row from its own state with its own action; the step objective is -reward * gamma^0
   PlanArgs p = base_plan_args(h, 1, 0);
-  p.K = (int)n; p.H = 1; p.proposal = BCMPC_PROP_UNIFORM; p.inj_kind = kInjUniformBox;
+  p.K = (int)n; p.H = 1; p.proposal = p.proposal0 = BCMPC_PROP_UNIFORM; p.inj_kind = p.inj_kind0 = kInjUniformBox;
   p.states = d_s; p.inj = d_a; p.states_out = d_o; p.costs_out = d_c; p.per_row_states = 1;
   rc = run_plan(h, p, nullptr, h->stream, /*force_verify=*/1);
   if (rc) { cleanup(); return rc; }
@@ -765,7 +771,7 @@ int bcmpc_sample_injection(bcmpc_handle* h, uint64_t seed, int32_t n_states, dou
   auto cleanup = [&]() { cudaFree(d_o); };
   CKC(cudaMalloc(&d_o, sizeof(double) * rows * A));
   sample_injection_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(
-      h->norm, A, K, H, n_states, inj_kind_of(h->cfg.proposal), seed, h->cfg.path_offset, d_o);
+      h->norm, A, K, H, n_states, inj_kind_of(first_proposal_of(h->cfg)), inj_kind_of(h->cfg.proposal), seed, h->cfg.path_offset, d_o);
   CKC(cudaGetLastError());
   h->launches++;
   CKC(cudaStreamSynchronize(h->stream));

@@ -60,7 +60,7 @@ __global__ void cheetah_cost_kernel(const double* __restrict__ s, const double* 
 }
 
 // Writes the injection tensor [B,H,K,A] exactly as the rollout kernels draw it.
-__global__ void sample_injection_kernel(NormArgs n, int A, int K, int H, int B, int kind, uint64_t seed,
+__global__ void sample_injection_kernel(NormArgs n, int A, int K, int H, int B, int kind0, int kind, uint64_t seed,
                                         int64_t path_offset, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*H*K
   if (i >= (int64_t)B * H * K) return;
@@ -68,7 +68,7 @@ __global__ void sample_injection_kernel(NormArgs n, int A, int K, int H, int B, 
   const int h = (int)((i / K) % H);
   const int b = (int)(i / ((int64_t)K * H));
   float v[kMaxAct];
-  draw_injection(v, A, kind, seed, (uint32_t)(path_offset + k), (uint32_t)b, (uint32_t)h, n.low, n.span);
+  draw_injection(v, A, h == 0 ? kind0 : kind, seed, (uint32_t)(path_offset + k), (uint32_t)b, (uint32_t)h, n.low, n.span);
   for (int j = 0; j < A; ++j) out[i * A + j] = (double)v[j];
 }
 

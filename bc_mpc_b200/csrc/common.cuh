@@ -103,6 +103,7 @@ using Candidate = bcmpc_record;   // {double cost; int64 index (-1 = empty); dou
 struct PlanArgs {
   int D, A, K, H, B;
   int proposal, inj_kind;
+  int proposal0, inj_kind0;   // step 0 (differs from proposal / inj_kind in the tree-search planner only)
   int64_t path_offset;
   uint64_t seed;
   const double* states;       // [B, D] root states  (or [n, D] per-row states in predict mode)

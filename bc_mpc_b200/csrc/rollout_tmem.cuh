@@ -223,6 +223,7 @@ inline bool tm_supported(const bcmpc_config& c, std::string* why) {
   if (c.n_hidden != 2) { *why = "bf16 fast path supports n_hidden == 2 this round"; return false; }
   if (c.hidden_size < 1 || c.hidden_size > 510) { *why = "bf16 fast path supports hidden_size <= 510 this round (TMEM holds the 512-wide padded activations)"; return false; }
   if (c.activation != BCMPC_ACT_RELU) { *why = "bf16 fast path supports relu only"; return false; }
+  if (c.first_proposal != 0 || c.proposal == BCMPC_PROP_POLICY_MEAN) { *why = "bf16 fast path: the tree-search planner (first_proposal, POLICY_MEAN) runs in BCMPC_PREC_FP32_VERIFY only"; return false; }
   return true;
 }
 

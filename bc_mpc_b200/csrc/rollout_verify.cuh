@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(kVerifyThreads) rollout_verify_kernel(const __
   __syncthreads();
 
   for (int h = 0; h < H; ++h) {
+    const int prop = h == 0 ? p.proposal0 : p.proposal;
     // ---- injected randomness of this step (controllers.py:53 / distributions.py:80) ----
     if (p.inj) {
       for (int i = tid; i < M * A; i += kVerifyThreads) {
@@ -181,13 +182,13 @@ __global__ void __launch_bounds__(kVerifyThreads) rollout_verify_kernel(const __
       }
     } else if (tid < M) {
       float v[kMaxAct];
-      draw_injection(v, A, p.inj_kind, p.seed, (uint32_t)(p.path_offset + k_base + tid), (uint32_t)b, (uint32_t)h,
+      draw_injection(v, A, h == 0 ? p.inj_kind0 : p.inj_kind, p.seed, (uint32_t)(p.path_offset + k_base + tid), (uint32_t)b, (uint32_t)h,
                      a.n.low, a.n.span);
       for (int j = 0; j < A; ++j) s_inj[tid * kMaxAct + j] = (double)v[j];
     }
     // ---- proposal network (ppo_bc_policy.py:60,70-72 / behavioral_cloning.py:21-26) ----
     const float* mean = nullptr;
-    if (p.proposal != BCMPC_PROP_UNIFORM) {
+    if (prop != BCMPC_PROP_UNIFORM) {
       const int ip = a.pol.in_pad[0];
       for (int i = tid; i < M * ip; i += kVerifyThreads) {
         const int r = i / ip, d = i % ip;
@@ -203,12 +204,14 @@ __global__ void __launch_bounds__(kVerifyThreads) rollout_verify_kernel(const __
       const int r = i / A, j = i % A;
       const double z = s_inj[r * kMaxAct + j];
       double act;
-      if (p.proposal == BCMPC_PROP_UNIFORM) {
+      if (prop == BCMPC_PROP_UNIFORM) {
         act = z;                                                                   // controllers.py:70
-      } else if (p.proposal == BCMPC_PROP_POLICY_GAUSSIAN) {
+      } else if (prop == BCMPC_PROP_POLICY_GAUSSIAN) {
         act = (double)__fadd_rn(mean[r * ld + j], __fmul_rn(a.pol_std[j], (float)z));   // distributions.py:80
-      } else if (p.proposal == BCMPC_PROP_POLICY_MIX) {
+      } else if (prop == BCMPC_PROP_POLICY_MIX) {
         act = (double)__fmul_rn(a.one_minus_explore, mean[r * ld + j]) + a.explore * z;  // controllers.py:208
+      } else if (prop == BCMPC_PROP_POLICY_MEAN) {
+        act = (double)mean[r * ld + j];                                            // controllers.py:429
       } else {
         act = (double)(float)((double)mean[r * ld + j] + z);   // float32 array += float64 (controllers.pyc)
       }

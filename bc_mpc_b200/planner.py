@@ -6,7 +6,8 @@ import numpy as np
 from . import _lib as L
 
 _PROPOSALS = {"uniform": L.PROP_UNIFORM, "policy_gaussian": L.PROP_POLICY_GAUSSIAN,
-              "policy_mix": L.PROP_POLICY_MIX, "bc_uniform": L.PROP_NET_PLUS_UNIFORM}
+              "policy_mix": L.PROP_POLICY_MIX, "bc_uniform": L.PROP_NET_PLUS_UNIFORM,
+              "policy_mean": L.PROP_POLICY_MEAN}
 _PRECISIONS = {"fp32": L.PREC_FP32_VERIFY, "fp32_verify": L.PREC_FP32_VERIFY,
                "bf16": L.PREC_BF16_FAST, "bf16_fast": L.PREC_BF16_FAST}
 _ACTS = {"relu": L.ACT_RELU, "tanh": L.ACT_TANH}
@@ -36,7 +37,7 @@ class Planner:
 
     def __init__(self, obs_dim=20, act_dim=6, n_hidden=2, hidden_size=500, activation="relu", num_paths=1000,
                  horizon=15, max_states=1, precision="fp32", proposal="uniform", explore=1.0, device=0,
-                 path_offset=0, total_paths=0):
+                 path_offset=0, total_paths=0, first_proposal=None):
         self._h = C.c_void_p()
         self._lib = L.lib()
         cfg = L.Config(obs_dim=obs_dim, act_dim=act_dim, n_hidden=n_hidden, hidden_size=hidden_size,
@@ -44,7 +45,7 @@ class Planner:
                        num_paths=num_paths, horizon=horizon, max_states=max_states,
                        precision=_PRECISIONS[precision] if isinstance(precision, str) else int(precision),
                        proposal=_PROPOSALS[proposal] if isinstance(proposal, str) else int(proposal),
-                       device=device, reserved0=0, path_offset=path_offset, total_paths=total_paths,
+                       device=device, first_proposal=0 if first_proposal is None else 1 + _PROPOSALS[first_proposal], path_offset=path_offset, total_paths=total_paths,
                        explore=float(explore))
         L.check(self._lib.bcmpc_create(C.byref(cfg), C.byref(self._h)))
         self.cfg = cfg

@@ -54,12 +54,14 @@ enum { BCMPC_PREC_FP32_VERIFY = 0, BCMPC_PREC_BF16_FAST = 1 };
  *  P1 POLICY_GAUSSIAN   controllers.py:203          a = mean(s)+exp(logstd)*inj,  inj ~ N(0,1)
  *  P2 POLICY_MIX        controllers.py:205-208      a = (1-e)*mean(s)+e*inj,      inj ~ U[low,high)
  *  P3 NET_PLUS_UNIFORM  controllers.pyc src 120-163 a = net(s)+inj,               inj ~ U[-1,1)
+ *  P4 POLICY_MEAN       controllers.py:429          a = mean(s)  (act(stochastic=False)), no randomness
  */
 enum {
   BCMPC_PROP_UNIFORM = 0,
   BCMPC_PROP_POLICY_GAUSSIAN = 1,
   BCMPC_PROP_POLICY_MIX = 2,
-  BCMPC_PROP_NET_PLUS_UNIFORM = 3
+  BCMPC_PROP_NET_PLUS_UNIFORM = 3,
+  BCMPC_PROP_POLICY_MEAN = 4
 };
 
 /* Replaces the constructor arguments of MPCcontroller / MPCcontrollerPolicyNet
@@ -76,7 +78,9 @@ typedef struct {
   int32_t precision;    /* BCMPC_PREC_*                                             */
   int32_t proposal;     /* BCMPC_PROP_*                                             */
   int32_t device;       /* CUDA device ordinal                                      */
-  int32_t reserved0;
+  int32_t first_proposal; /* 0: every step uses `proposal`.  1 + BCMPC_PROP_*: step 0 uses that mode and steps
+                           * 1..H-1 use `proposal` - the first-stage / rollout split of
+                           * MCTScontrollerPolicyNetReward.get_action (controllers.py:397-457).  Verification mode. */
   int64_t path_offset;  /* global index of this handle's first path (GPU sharding)  */
   int64_t total_paths;  /* global K over all shards (0 -> num_paths)                */
   double explore;       /* e of P2 (MPCcontrollerPolicyNet.explore)                 */

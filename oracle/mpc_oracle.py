@@ -335,6 +335,49 @@ class OracleMPC:
         return action
 
 
+class OracleMCTS:
+    """MCTScontrollerPolicyNetReward.get_action (controllers.py:397-457) with injectable randomness.
+
+    N first-stage actions, each followed by R rollouts of H steps under the DETERMINISTIC policy (:429); the score of a
+    first-stage action is reward_1 + mean over its R rollouts of the summed rewards (:445-450), argmax (:453).
+    first_stage: "uniform" (random_first_stage_action, :409-411; inj = the N sampled actions [N,A]),
+                 "policy_gaussian" (self_exp, :413-414; inj = N(0,1) noise [N,A]),
+                 "policy_mean" (:415-416; no randomness, all N actions are equal).
+    Returns the [1,A] first-stage action like the reference does (:455-457)."""
+
+    def __init__(self, dyn_model, policy, horizon, num_first_stage_actions, random_path_per_action, first_stage):
+        self.dyn_model, self.policy, self.horizon = dyn_model, policy, horizon
+        self.N, self.R, self.first_stage = num_first_stage_actions, random_path_per_action, first_stage
+
+    def get_action(self, state, inj=None, return_debug=False):
+        state_init = np.expand_dims(state, axis=0)  # :402
+        action_1s, reward_1s, states_all_actions = [], [], []
+        for n in range(self.N):  # :405
+            if self.first_stage == "uniform":
+                action_1 = np.expand_dims(inj[n], axis=0)  # :410-411
+            elif self.first_stage == "policy_gaussian":
+                action_1, _ = self.policy.act(state_init, stochastic=True, noise=inj[n:n + 1])  # :414
+            else:
+                action_1, _ = self.policy.act(state_init, stochastic=False)  # :416
+            state_1, reward_1 = self.dyn_model.predict(state_init, action_1)  # :418
+            reward_1s.append(reward_1[0][0])
+            action_1s.append(action_1)
+            states_all_actions.append(np.tile(state_1, [self.R, 1]))  # :424-425
+        states = np.asarray(states_all_actions).reshape((-1, state.shape[0]))  # :427-429
+        rewards_all = []
+        for _ in range(self.horizon):  # :431
+            actions, _ = self.policy.act(states, stochastic=False)  # :433
+            states, reward = self.dyn_model.predict(states, actions)  # :440
+            rewards_all.append(reward)
+        rewards_all = np.sum(np.asarray(rewards_all), axis=0).reshape((self.N, -1))  # :444-447
+        total = np.asarray(reward_1s) + np.mean(rewards_all, axis=1)  # :449-451
+        best = int(np.argmax(total))  # :454
+        if return_debug:
+            return action_1s[best], dict(total=np.asarray(total, np.float64), best=best,
+                                         actions=np.concatenate(action_1s, axis=0))
+        return action_1s[best]
+
+
 # ----------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d) - shared by tests, smoke and bench
 # ----------------------------------------------------------------------------

@@ -103,6 +103,46 @@ def test_controller_host_logic(golden_dir):
     assert pc.proposal == "policy_mix"
 
 
+def test_samplers_host_logic():
+    """sampling.sample mirrors utils.py:91-126; sample_vectorized makes one batched call per time step."""
+    from bc_mpc_b200 import sampling
+
+    class E:
+        def __init__(self, k):
+            self.k, self.t = k, 0
+
+        def reset(self):
+            self.t = 0
+            return np.full(3, float(self.k))
+
+        def step(self, a):
+            self.t += 1
+            return np.full(3, self.k + 0.1 * self.t) + a.sum(), float(self.t), False, {}
+
+    class Ctl:
+        calls = batched = 0
+
+        def get_action(self, s):
+            self.calls += 1
+            return np.array([s[0], -s[0]])
+
+        def get_actions(self, S):
+            self.batched += 1
+            return np.stack([S[:, 0], -S[:, 0]], axis=1)
+
+    c = Ctl()
+    one = sampling.sample(E(2), c, num_paths=3, horizon=4)
+    assert len(one) == 3 and c.calls == 12 and len(one[0]["observations"]) == 4
+    assert np.array_equal(one[0]["next_observations"][0], one[0]["observations"][1])
+    vec = sampling.sample_vectorized([E(k) for k in range(5)], c, horizon=4)
+    assert c.batched == 4 and len(vec) == 5
+    ref = sampling.sample(E(2), c, num_paths=1, horizon=4)[0]
+    for key in ref:
+        assert np.allclose(np.asarray(vec[2][key]), np.asarray(ref[key]))
+    assert sampling.path_cost(lambda s, a, n: float(np.sum(n) - np.sum(s)), vec[1]) == pytest.approx(
+        sum(float(np.sum(n) - np.sum(s)) for s, n in zip(vec[1]["observations"], vec[1]["next_observations"])))
+
+
 def test_shard_bounds():
     from bc_mpc_b200.distributed import shard_bounds
     assert list(shard_bounds(1000, 4)) == [0, 250, 500, 750, 1000]

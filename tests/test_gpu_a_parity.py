@@ -188,6 +188,113 @@ def test_learned_reward_controllers_drop_in():
     assert np.allclose(pc.get_action(state), want, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("first_stage", ["uniform", "policy_gaussian", "policy_mean"])
+def test_tree_search_controller(first_stage):
+    """MCTScontrollerPolicyNetReward.get_action (controllers.py:397-457) as one N x (H+1) launch with the step-0
+    proposal switched; scores and chosen first action vs the oracle restatement (which replays the R copies)."""
+    from bc_mpc_b200 import controllers, dynamics, policy
+
+    class Space:
+        def __init__(self, n):
+            self.low, self.high, self.shape = -np.ones(n), np.ones(n), (n,)
+
+    class Env:
+        action_space, observation_space = Space(6), Space(20)
+
+    H, N, R, S = 5, 64, 4, 500
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(37, S)
+    n10 = (norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_reward"],
+           norm["std_reward"], None, None, norm["mean_deltas"], norm["std_deltas"])
+    dm = dynamics.NNDynamicsRewardModel(Env(), n10)
+    dm.set_weights(weights, rweights)
+    od = O.OracleRewardDynamics(weights, rweights, norm)
+    pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
+    pol = policy.MlpPolicy(None, Env(), 128, 2)
+    pol.set_weights(pw, logstd, rms_mean, rms_std)
+    op = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
+    z = f32_uniform(rng, (N, 6)) if first_stage == "uniform" else rng.standard_normal((N, 6)).astype(np.float32).astype(np.float64)
+    c = controllers.MCTScontrollerPolicyNetReward(Env(), dm, pol, self_exp=first_stage == "policy_gaussian", horizon=H,
+                                                  num_first_stage_actions=N, random_path_per_action=R,
+                                                  random_first_stage_action=first_stage == "uniform")
+    c.sample_first_stage = lambda: z
+    got = c.get_action(state)
+    want, dbg = O.OracleMCTS(od, op, H, N, R, first_stage).get_action(state, z, return_debug=True)
+    assert got.shape == (1, 6)
+    inj = np.zeros((H + 1, N, 6))
+    inj[0] = z
+    _, ao, co = c._planner.rollout_debug(state, inj)
+    assert np.allclose(ao[0], dbg["actions"], rtol=1e-5, atol=1e-6)
+    assert np.abs(-co - dbg["total"]).max() < 1e-3 * max(1.0, np.abs(dbg["total"]).max())
+    if first_stage != "policy_mean":       # with the deterministic first stage all N candidates tie
+        assert c.last_record["index"] == dbg["best"]
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+    # device-drawn first stage: replay the drawn tensor through the oracle
+    c2 = controllers.MCTScontrollerPolicyNetReward(Env(), dm, pol, self_exp=first_stage == "policy_gaussian", horizon=H,
+                                                   num_first_stage_actions=N, random_path_per_action=R,
+                                                   random_first_stage_action=first_stage == "uniform")
+    np.random.seed(5)
+    got2 = c2.get_action(state)
+    np.random.seed(5)
+    seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
+    zd = c2._planner.sample_injection(seed)[0, 0]
+    want2 = O.OracleMCTS(od, op, H, N, R, first_stage).get_action(state, zd)
+    assert np.allclose(got2, want2, rtol=1e-5, atol=1e-6)
+
+
+def test_batched_controller_and_vectorized_sampler():
+    """get_actions(states[B,D]) = B independent plans in one launch (grows the handle on demand); the vectorised
+    sampler drives B model-envs with it.  Every plan is replayed through the oracle with the device-drawn tensor."""
+    from bc_mpc_b200 import controllers, cost_functions, dynamics, sampling
+
+    class Space:
+        def __init__(self, n):
+            self.low, self.high, self.shape = -np.ones(n), np.ones(n), (n,)
+
+    class ModelEnv:            # the learned model as the environment: deterministic, CPU
+        action_space, observation_space = Space(6), Space(20)
+
+        def __init__(self, dyn, s0):
+            self.dyn, self.s0 = dyn, s0
+
+        def reset(self):
+            self.s = self.s0.copy()
+            return self.s
+
+        def step(self, a):
+            self.s = self.dyn.predict(self.s[None], np.asarray(a)[None])[0]
+            return self.s, 0.0, False, {}
+
+    K, H, B = 500, 5, 5
+    rng, norm, weights, state = O.synthetic_problem(41, (64, 64))
+    od = O.OracleDynamics(weights, norm)
+    n10 = (norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], None, None, None, None,
+           norm["mean_deltas"], norm["std_deltas"])
+    dm = dynamics.NNDynamicsModel(ModelEnv, 2, 64, "relu", None, n10)
+    dm.set_weights(weights)
+    c = controllers.MPCcontroller(ModelEnv, dm, horizon=H, cost_fn=cost_functions.cheetah_cost_fn, num_simulated_paths=K)
+    assert c.get_action(state).shape == (6,) and c._planner.max_states == 1
+    S = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((B, 20))
+    np.random.seed(11)
+    acts = c.get_actions(S)
+    assert acts.shape == (B, 6) and c._planner.max_states == 8
+    np.random.seed(11)
+    seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
+    inj = c._planner.sample_injection(seed, n_states=B)
+    for b in range(B):
+        assert np.allclose(acts[b], O.OracleMPC(od, H, K).get_action(S[b], inj[b]), rtol=1e-6, atol=1e-7)
+    envs = [ModelEnv(od, S[b]) for b in range(B)]
+    np.random.seed(12)
+    paths = sampling.sample_vectorized(envs, c, horizon=3)
+    assert len(paths) == B and len(paths[0]["actions"]) == 3
+    np.random.seed(12)
+    for t in range(3):
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
+        inj = c._planner.sample_injection(seed, n_states=B)
+        for b in range(B):
+            want = O.OracleMPC(od, H, K).get_action(paths[b]["observations"][t], inj[b])
+            assert np.allclose(paths[b]["actions"][t], want, rtol=1e-6, atol=1e-7)
+
+
 def test_threshold_and_tie_cases():
     K, H = 256, 4
     rng, norm, state, pl, mpc = make_pair(11, (64, 64), K, H)

@@ -77,6 +77,44 @@ def test_policy_controller_matches_reference(ref):
     assert np.array_equal(want, got)
 
 
+@pytest.mark.parametrize("first_stage", ["uniform", "policy_gaussian", "policy_mean"])
+def test_tree_search_controller_matches_reference(ref, first_stage):
+    """MCTScontrollerPolicyNetReward.get_action (controllers.py:397-457): N first-stage actions, deterministic-policy
+    rollouts, reward_1 + mean rollout reward, argmax."""
+    ctl, _ = ref
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(8, 40)
+    dyn = O.OracleRewardDynamics(weights, rweights, norm)
+    pol = O.OraclePolicy(*O.synthetic_policy(rng, hidden=(16, 16), norm=norm))
+    H, N, R = 4, 23, 3
+    inj = rng.uniform(-1, 1, (N, 6)) if first_stage == "uniform" else rng.standard_normal((N, 6))
+
+    class _Pol:
+        calls = 0
+
+        def act(self, ob, stochastic=True):
+            if stochastic:          # the N first-stage draws come one row at a time (:414)
+                out = pol.act(ob, True, noise=inj[self.calls:self.calls + 1])
+                self.calls += 1
+                return out
+            return pol.act(ob, False)
+
+    class _Space(_Env.action_space.__class__):
+        n = 0
+
+        def sample(self):
+            _Space.n += 1
+            return inj[_Space.n - 1]
+
+    env = _Env()
+    env.action_space = _Space(6)
+    c = ctl.MCTScontrollerPolicyNetReward(env, dyn, _Pol(), self_exp=first_stage == "policy_gaussian", horizon=H,
+                                          num_first_stage_actions=N, random_path_per_action=R,
+                                          random_first_stage_action=first_stage == "uniform")
+    want = c.get_action(state)
+    got = O.OracleMCTS(dyn, pol, H, N, R, first_stage).get_action(state, inj)
+    assert want.shape == (1, 6) and np.array_equal(want, got)
+
+
 def test_sample_random_actions_layout(ref):
     ctl, cf = ref
     c = ctl.MPCcontroller(_Env(), None, horizon=3, cost_fn=None, num_simulated_paths=5)
