@@ -38,6 +38,7 @@ SIGNATURES = {
     "bcmpc_create": (C.c_int, [C.POINTER(Config), _PP]),
     "bcmpc_destroy": (C.c_int, [_P]),
     "bcmpc_set_dynamics": (C.c_int, [_P, _PP, _PP, C.c_int32]),
+    "bcmpc_set_dynamics_device": (C.c_int, [_P, _PP, _PP, C.c_int32, C.c_int32, _P]),
     "bcmpc_set_layer_norm": (C.c_int, [_P, _PP, _PP, C.c_int32, C.c_float]),
     "bcmpc_set_reward_head": (C.c_int, [_P, _PP, _PP, C.c_double, C.c_double, C.c_double]),
     "bcmpc_predict_reward": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),

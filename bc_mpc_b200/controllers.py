@@ -86,9 +86,7 @@ class _GpuShootingController(Controller):
             self._planner.set_action_bounds(self.env.action_space.low, self.env.action_space.high)
             self._dyn_version = self._pol_version = None
         if self._dyn_version != dm.version:     # weights change after every dyn_model.fit (train_mpc_ppo.py:279)
-            self._planner.set_dynamics(dm.weights)
-            if getattr(dm, "layer_norm", False):
-                self._planner.set_layer_norm(dm.layer_norm_params)
+            dm.upload(self._planner)
             self._planner.set_normalization(*dm.normalization6())
             if self.learned_reward:
                 dm.upload_reward_head(self._planner, self.gamma)

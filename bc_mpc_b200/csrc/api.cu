@@ -63,10 +63,11 @@ struct bcmpc_handle {
   tmx::TmHostPlan tmp;
   uint8_t *d_res = nullptr, *d_stream = nullptr, *d_pol = nullptr;
   float* d_lnvec = nullptr;
-  std::vector<float> hW[3], hb[3];            // host copies of the dynamics weights (the fast images are rebuilt when LayerNorm is switched)
-  std::vector<float> ln_gamma[2], ln_beta[2]; // LayerNorm parameters (fast mode)
-  bool ln_on = false;
+  size_t res_cap = 0, stream_cap = 0, lnvec_cap = 0;
+  bool ln_on = false;     // LayerNorm parameters uploaded (ln_bufs / dyn.desc.ln_*), both precision modes
   float ln_eps = 1e-12f;
+  cudaEvent_t ev_weights = nullptr;   // recorded after an asynchronous weight hand-off (bcmpc_set_dynamics_device)
+  bool weights_pending = false;       // plans on other streams wait on ev_weights until it has completed
   unsigned long long* d_trace = nullptr;
   bool tm_ready = false;
   int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
@@ -118,6 +119,54 @@ int upload_mlp(bcmpc_handle* h, DeviceMlp& m, int n_layers, const int* sizes, co
     m.desc.W[l] = dw;
     m.desc.b[l] = db;
   }
+  m.set = true;
+  return BCMPC_OK;
+}
+
+// The dynamics network keeps ONE set of zero-padded float32 device buffers for the lifetime of the handle (its shape is
+// fixed by bcmpc_config), so a weight refresh is a strided copy - from the host or from device memory - on `st`.
+// kind: cudaMemcpyHostToDevice ([in,out] host arrays), cudaMemcpyDeviceToDevice ([in,out] device arrays), or -1 for
+// device arrays in torch.nn.Linear layout [out,in] (transposed by a small kernel).
+int refresh_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int kind, cudaStream_t st) {
+  DeviceMlp& m = h->dyn;
+  const int n_layers = h->cfg.n_hidden + 1;
+  int sizes[kMaxLayers + 1];
+  sizes[0] = h->cfg.obs_dim + h->cfg.act_dim;
+  for (int l = 1; l <= h->cfg.n_hidden; ++l) sizes[l] = h->cfg.hidden_size;
+  sizes[n_layers] = h->cfg.obs_dim;
+  if (m.bufs.empty()) {
+    m.desc = MlpDesc{};
+    m.desc.n_layers = n_layers;
+    for (int l = 0; l < n_layers; ++l) {
+      const int ip = round4(sizes[l]), op = round4(sizes[l + 1]);
+      m.desc.in_dim[l] = sizes[l]; m.desc.out_dim[l] = sizes[l + 1]; m.desc.in_pad[l] = ip; m.desc.out_pad[l] = op;
+      float *dw = nullptr, *db = nullptr;
+      CK(h, cudaMalloc(&dw, (size_t)ip * op * sizeof(float)));
+      m.bufs.push_back(dw);
+      CK(h, cudaMalloc(&db, (size_t)op * sizeof(float)));
+      m.bufs.push_back(db);
+      CK(h, cudaMemsetAsync(dw, 0, (size_t)ip * op * sizeof(float), st));
+      CK(h, cudaMemsetAsync(db, 0, (size_t)op * sizeof(float), st));
+      m.desc.W[l] = dw;
+      m.desc.b[l] = db;
+    }
+  }
+  for (int l = 0; l < n_layers; ++l) {
+    const size_t row = sizeof(float) * sizes[l + 1];
+    if (kind < 0) {
+      const int n = sizes[l] * sizes[l + 1];
+      transpose_in_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(m.desc.W[l]), m.desc.out_pad[l], W[l], sizes[l], sizes[l + 1]);
+      CK(h, cudaGetLastError());
+      h->launches++;
+      CK(h, cudaMemcpyAsync(const_cast<float*>(m.desc.b[l]), b[l], row, cudaMemcpyDeviceToDevice, st));
+    } else {
+      CK(h, cudaMemcpy2DAsync(const_cast<float*>(m.desc.W[l]), sizeof(float) * m.desc.out_pad[l], W[l], row, row, sizes[l], (cudaMemcpyKind)kind, st));
+      CK(h, cudaMemcpyAsync(const_cast<float*>(m.desc.b[l]), b[l], row, (cudaMemcpyKind)kind, st));
+    }
+  }
+  // new weights reset LayerNorm: call bcmpc_set_layer_norm again (the parameters belong to the same checkpoint)
+  for (int l = 0; l < kMaxLayers; ++l) m.desc.ln_gamma[l] = m.desc.ln_beta[l] = nullptr;
+  h->ln_on = false;
   m.set = true;
   return BCMPC_OK;
 }
@@ -199,34 +248,40 @@ int tm_variant(const bcmpc_handle* h) {
   return h->ln_on ? tmx::kVarLayerNorm : tmx::kVarUniform;
 }
 
-// (re)builds the fast-mode weight images from the host copies of the dynamics weights
-int tm_prepare(bcmpc_handle* h) {
+// (re)packs the fast-mode weight images on the device, on stream `st`, from the float32 copies in h->dyn / h->ln_bufs
+int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   const int S = h->cfg.hidden_size;
-  const bool keep_policy = h->tmp.with_policy;
   const tmx::TmHostPlan old = h->tmp;
-  const float* g[2] = {h->ln_gamma[0].data(), h->ln_gamma[1].data()};
-  const float* be[2] = {h->ln_beta[0].data(), h->ln_beta[1].data()};
-  tmx::tm_build(h->hW[0].data(), h->hb[0].data(), h->hW[1].data(), h->hb[1].data(), h->hW[2].data(), h->hb[2].data(), S, h->tm_cg,
-                tm_variant(h), h->ln_on ? g : nullptr, h->ln_on ? be : nullptr, &h->tmp);
-  if (keep_policy) {   // the proposal network survives a dynamics refresh
+  tmx::tm_geometry(S, h->tm_cg, tm_variant(h), &h->tmp);
+  if (old.with_policy) {   // the proposal network survives a dynamics refresh
     h->tmp.with_policy = true; h->tmp.np1 = old.np1; h->tmp.np2 = old.np2; h->tmp.pol = old.pol;
     memcpy(h->tmp.bp1, old.bp1, sizeof old.bp1); memcpy(h->tmp.bp2, old.bp2, sizeof old.bp2); memcpy(h->tmp.bp3, old.bp3, sizeof old.bp3);
   }
   const tmx::TmHostPlan& P = h->tmp;
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
   if (P.lay.nst < 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "weight ring does not fit in shared memory");
-  if (h->d_res) cudaFree(h->d_res);
-  if (h->d_stream) cudaFree(h->d_stream);
-  if (h->d_lnvec) cudaFree(h->d_lnvec);
-  h->d_res = h->d_stream = nullptr; h->d_lnvec = nullptr;
-  CK(h, cudaMalloc(&h->d_res, P.res.size() * 2));
-  CK(h, cudaMalloc(&h->d_stream, P.stream.size() * 2));
-  CK(h, cudaMemcpy(h->d_res, P.res.data(), P.res.size() * 2, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(h->d_stream, P.stream.data(), P.stream.size() * 2, cudaMemcpyHostToDevice));
-  if (P.layer_norm) {
-    CK(h, cudaMalloc(&h->d_lnvec, P.lnvec.size() * sizeof(float)));
-    CK(h, cudaMemcpy(h->d_lnvec, P.lnvec.data(), P.lnvec.size() * sizeof(float), cudaMemcpyHostToDevice));
-  }
+  auto ensure = [&](void** ptr, size_t* cap, size_t need) -> cudaError_t {
+    if (need <= *cap) return cudaSuccess;
+    if (*ptr) cudaFree(*ptr);           // (implicitly waits for every stream of the device)
+    *ptr = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(ptr, need);
+    if (e != cudaSuccess) return e;
+    *cap = need;
+    return cudaMemsetAsync(*ptr, 0, need, st);
+  };
+  CK(h, ensure((void**)&h->d_res, &h->res_cap, P.res_total));
+  CK(h, ensure((void**)&h->d_stream, &h->stream_cap, P.stream_total));
+  if (P.layer_norm) CK(h, ensure((void**)&h->d_lnvec, &h->lnvec_cap, P.lnvec_floats * sizeof(float)));
+  tmx::PackArgs a{};
+  const MlpDesc& d = h->dyn.desc;
+  a.W1 = d.W[0]; a.b1 = d.b[0]; a.W2 = d.W[1]; a.b2 = d.b[1]; a.W3 = d.W[2]; a.b3 = d.b[2];
+  a.ld1 = d.out_pad[0]; a.ld2 = d.out_pad[1]; a.ld3 = d.out_pad[2];
+  if (P.layer_norm) { a.g1 = d.ln_gamma[0]; a.be1 = d.ln_beta[0]; a.g2 = d.ln_gamma[1]; a.be2 = d.ln_beta[1]; }
+  a.S = S; a.s_pad = P.s_pad; a.nc = P.nc; a.cg = P.cg; a.kbs = P.lay.kbs; a.nstg = P.lay.nstg;
+  a.blk_h = P.lay.blk_h; a.blk_o = P.lay.blk_o; a.w1_bytes = P.lay.w1_bytes; a.res_bytes = P.lay.res_bytes; a.stage_bytes = P.lay.stage_bytes;
+  a.res = reinterpret_cast<uint16_t*>(h->d_res); a.stream = reinterpret_cast<uint16_t*>(h->d_stream); a.lnvec = h->d_lnvec;
+  CK(h, tmx::tm_pack(a, st));
+  h->launches += P.layer_norm ? 2 : 1;
   if (!h->trace_path.empty() && !h->d_trace)
     CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots));
   h->tm_ready = true;
@@ -259,7 +314,6 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   if (P.layer_norm) {
     if (pol) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm dynamics with a proposal network run in BCMPC_PREC_FP32_VERIFY only");
     a.lnvec = h->d_lnvec;
-    memcpy(a.u3, P.u3, sizeof a.u3); memcpy(a.c3, P.c3, sizeof a.c3);
     a.ln_inv_n = 1.0f / (float)h->cfg.hidden_size; a.ln_eps = h->ln_eps;
   }
   if (pol) {
@@ -303,6 +357,10 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
     p.cand = h->d_cand;
   } else {
     p.cand = nullptr;
+  }
+  if (h->weights_pending) {     // an asynchronous weight hand-off on another stream: order this plan after it
+    if (cudaEventQuery(h->ev_weights) == cudaSuccess) h->weights_pending = false;
+    else CK(h, cudaStreamWaitEvent(st, h->ev_weights, 0));
   }
   if (h->timing) { CK(h, cudaEventRecord(h->ev0, st)); }
   int rc;
@@ -399,7 +457,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
 int bcmpc_destroy(bcmpc_handle* h) {
   if (!h) return BCMPC_OK;
   cudaSetDevice(h->cfg.device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();
   h->dyn.release();
   h->pol.release();
   h->rew.release();
@@ -410,65 +468,68 @@ int bcmpc_destroy(bcmpc_handle* h) {
   if (h->h_records) cudaFreeHost(h->h_records);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_weights) cudaEventDestroy(h->ev_weights);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return BCMPC_OK;
 }
 
-int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int32_t n_layers) {
+namespace {
+int set_dynamics_common(bcmpc_handle* h, const float* const* W, const float* const* b, int32_t n_layers, int kind, cudaStream_t st) {
   if (!h || !W || !b) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_layers != h->cfg.n_hidden + 1) return fail(h, BCMPC_ERR_INVALID, "n_layers %d != n_hidden+1 = %d", n_layers, h->cfg.n_hidden + 1);
   for (int l = 0; l < n_layers; ++l)
     if (!W[l] || !b[l]) return fail(h, BCMPC_ERR_INVALID, "null weight pointer for layer %d", l);
   CK(h, cudaSetDevice(h->cfg.device));
-  CK(h, cudaStreamSynchronize(h->stream));
-  int sizes[kMaxLayers + 1];
-  sizes[0] = h->cfg.obs_dim + h->cfg.act_dim;
-  for (int l = 1; l <= h->cfg.n_hidden; ++l) sizes[l] = h->cfg.hidden_size;
-  sizes[n_layers] = h->cfg.obs_dim;
-  int rc = upload_mlp(h, h->dyn, n_layers, sizes, W, b);
+  int rc = refresh_dynamics(h, W, b, kind, st);
   if (rc) return rc;
   update_verify_geometry(h);
-  if (h->cfg.precision == BCMPC_PREC_BF16_FAST) {
-    for (int l = 0; l < 3; ++l) {
-      h->hW[l].assign(W[l], W[l] + (size_t)sizes[l] * sizes[l + 1]);
-      h->hb[l].assign(b[l], b[l] + sizes[l + 1]);
-    }
-    h->ln_on = false;      // new weights reset LayerNorm (same rule as the verification path): call bcmpc_set_layer_norm again
-    rc = tm_prepare(h);
-    if (rc) return rc;
-  }
+  if (h->cfg.precision == BCMPC_PREC_BF16_FAST) rc = tm_prepare(h, st);
+  return rc;
+}
+}  // namespace
+
+int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int32_t n_layers) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  int rc = set_dynamics_common(h, W, b, n_layers, cudaMemcpyHostToDevice, h->stream);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));     // the caller may reuse its host arrays; plans on any stream see the new weights
+  return BCMPC_OK;
+}
+
+int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const float* const* db, int32_t n_layers, int32_t layout,
+                              void* stream) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (layout != BCMPC_LAYOUT_IN_OUT && layout != BCMPC_LAYOUT_OUT_IN) return fail(h, BCMPC_ERR_INVALID, "unknown layout %d", layout);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  int rc = set_dynamics_common(h, dW, db, n_layers, layout == BCMPC_LAYOUT_OUT_IN ? -1 : (int)cudaMemcpyDeviceToDevice, st);
+  if (rc) return rc;
+  if (!h->ev_weights) CK(h, cudaEventCreateWithFlags(&h->ev_weights, cudaEventDisableTiming));
+  CK(h, cudaEventRecord(h->ev_weights, st));
+  h->weights_pending = true;
   return BCMPC_OK;
 }
 
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps) {
   if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
-  if (h->cfg.precision == BCMPC_PREC_BF16_FAST) {
-    if (gamma && h->cfg.proposal != BCMPC_PROP_UNIFORM)
-      return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm dynamics with a proposal network run in BCMPC_PREC_FP32_VERIFY only");
-    if (gamma && (!beta || n_hidden != 2)) return fail(h, BCMPC_ERR_INVALID, "fast mode expects gamma and beta for the two hidden layers");
-    CK(h, cudaSetDevice(h->cfg.device));
-    CK(h, cudaStreamSynchronize(h->stream));
-    h->ln_on = gamma != nullptr;
-    h->ln_eps = eps;
-    for (int l = 0; l < 2 && gamma; ++l) {
-      if (!gamma[l] || !beta[l]) return fail(h, BCMPC_ERR_INVALID, "null LayerNorm pointer for layer %d", l);
-      h->ln_gamma[l].assign(gamma[l], gamma[l] + h->cfg.hidden_size);
-      h->ln_beta[l].assign(beta[l], beta[l] + h->cfg.hidden_size);
-    }
-    return tm_prepare(h);
-  }
+  const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
+  if (fast && gamma && h->cfg.proposal != BCMPC_PROP_UNIFORM)
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm dynamics with a proposal network run in BCMPC_PREC_FP32_VERIFY only");
+  if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
+  if (gamma && n_hidden != h->cfg.n_hidden) return fail(h, BCMPC_ERR_INVALID, "n_hidden %d != %d", n_hidden, h->cfg.n_hidden);
+  for (int l = 0; l < n_hidden && gamma; ++l)
+    if (!gamma[l] || !beta[l]) return fail(h, BCMPC_ERR_INVALID, "null LayerNorm pointer for layer %d", l);
   CK(h, cudaSetDevice(h->cfg.device));
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaDeviceSynchronize());      // plans and hand-offs on any stream have finished with the old parameters
   for (float* p : h->ln_bufs) cudaFree(p);
   h->ln_bufs.clear();
   for (int l = 0; l < kMaxLayers; ++l) h->dyn.desc.ln_gamma[l] = h->dyn.desc.ln_beta[l] = nullptr;
-  if (!gamma) return BCMPC_OK;
-  if (!beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
-  if (n_hidden != h->cfg.n_hidden) return fail(h, BCMPC_ERR_INVALID, "n_hidden %d != %d", n_hidden, h->cfg.n_hidden);
-  for (int l = 0; l < n_hidden; ++l) {
-    if (!gamma[l] || !beta[l]) return fail(h, BCMPC_ERR_INVALID, "null LayerNorm pointer for layer %d", l);
+  h->ln_on = gamma != nullptr;
+  h->ln_eps = eps;
+  for (int l = 0; l < n_hidden && gamma; ++l) {
     float *dg = nullptr, *db = nullptr;
     CK(h, cudaMalloc(&dg, sizeof(float) * h->cfg.hidden_size)); h->ln_bufs.push_back(dg);
     CK(h, cudaMalloc(&db, sizeof(float) * h->cfg.hidden_size)); h->ln_bufs.push_back(db);
@@ -478,6 +539,11 @@ int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float
     h->dyn.desc.ln_beta[l] = db;
   }
   h->dyn.desc.ln_eps = eps;
+  if (fast) {
+    int rc = tm_prepare(h, h->stream);
+    if (rc) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
   return BCMPC_OK;
 }
 

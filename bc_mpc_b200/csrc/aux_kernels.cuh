@@ -59,6 +59,14 @@ __global__ void cheetah_cost_kernel(const double* __restrict__ s, const double* 
   out[i] = c;
 }
 
+// dst[i * ld + o] = src[o * in + i]: a torch.nn.Linear weight [out,in] into the padded [in,out] layout of the handle
+__global__ void transpose_in_kernel(float* __restrict__ dst, int ld, const float* __restrict__ src, int in, int out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= in * out) return;
+  const int i = e / out, o = e % out;
+  dst[(size_t)i * ld + o] = src[(size_t)o * in + i];
+}
+
 // Writes the injection tensor [B,H,K,A] exactly as the rollout kernels draw it.
 __global__ void sample_injection_kernel(NormArgs n, int A, int K, int H, int B, int kind0, int kind, uint64_t seed,
                                         int64_t path_offset, double* __restrict__ out) {

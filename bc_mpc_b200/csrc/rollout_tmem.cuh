@@ -144,7 +144,7 @@ constexpr Layout make_layout(int cg, int nc, int var) {
   L.pol_bytes = pol ? 6u * L.blk_h + 2u * L.blk_o : 0u;
   // LayerNorm variant: per-column correction vectors of layer 2 (u2, c2: 2 x 64*nc floats) + per-row statistics
   L.off_ln = (L.off_pol + L.pol_bytes + 1023u) / 1024u * 1024u;
-  L.ln_bytes = ln ? 2u * 64u * nc * 4u + kLnStatsBytes : 0u;
+  L.ln_bytes = ln ? 2u * 64u * nc * 4u + 2u * kOutN * 4u + kLnStatsBytes : 0u;
   L.off_ring = (L.off_ln + L.ln_bytes + 1023u) / 1024u * 1024u;
   L.stage_bytes = L.kbs * L.blk_h;
   L.nst = (int)((kSmemLimit - kMiscBytes - L.off_ring) / L.stage_bytes);
@@ -177,8 +177,7 @@ struct TmArgs {
   float filt_mean[kMaxObs], filt_inv_std[kMaxObs], pol_std[kMaxAct];
   float bp1[kPolMaxHidden], bp2[kPolMaxHidden], bp3[kMaxAct];
   // LayerNorm variant (dynamics.py:68-69): z = rho * acc - rho * mu * u + c per column, rho / mu per row
-  const float* lnvec;            // [u2 (64*nc)][c2 (64*nc)] correction vectors of layer 2
-  float u3[kMaxObs], c3[kMaxObs];   // ... of the output layer
+  const float* lnvec;            // [u2 (64*nc)][c2 (64*nc)] correction vectors of layer 2, [u3 (32)][c3 (32)] of the output layer
   float ln_inv_n, ln_eps;        // 1 / hidden_size, variance epsilon
 };
 // pipeline trace of CTA (0,0), steps 0..3: [2 per L1 pair][2 per L2 chunk][2 per L3 chunk][4 per epilogue chunk][final 8][2 per stage]
@@ -187,14 +186,14 @@ constexpr int kTraceSteps = 4, kTrL1 = 0, kTrL2 = 8, kTrL3 = 24, kTrEpi = 40, kT
 // ---------------------------------------------------------------------------------------------------------
 // host: weight images
 // ---------------------------------------------------------------------------------------------------------
-inline uint16_t f32_to_bf16(float f) {
+__host__ __device__ inline uint16_t f32_to_bf16(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
   if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return (uint16_t)((u >> 16) | 0x40);   // NaN
   u += 0x7FFFu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
-inline float bf16_to_f32(uint16_t h) {
+__host__ __device__ inline float bf16_to_f32(uint16_t h) {
   uint32_t u = (uint32_t)h << 16;
   float f;
   memcpy(&f, &u, 4);
@@ -202,14 +201,13 @@ inline float bf16_to_f32(uint16_t h) {
 }
 
 // byte offset of element (row n, k-column kk < 64) in a K-major SWIZZLE_128B image (8-row groups of 1024 B)
-inline size_t sw128_offset(int n, int kk) {
+__host__ __device__ inline size_t sw128_offset(int n, int kk) {
   return (size_t)(n / 8) * 1024 + (size_t)(n % 8) * 128 + (size_t)(((kk / 8) ^ (n % 8)) * 16) + (size_t)(kk % 8) * 2;
 }
 
 struct TmHostPlan {
-  std::vector<uint16_t> res, stream, pol;
-  std::vector<float> lnvec;      // LayerNorm variant: [u2][c2]
-  float u3[kMaxObs] = {}, c3[kMaxObs] = {};
+  std::vector<uint16_t> pol;
+  size_t res_total = 0, stream_total = 0, lnvec_floats = 0;     // bytes / bytes / floats of the device images
   bool layer_norm = false;
   int cg = 1, s_pad = 0, nc = 0, hidden = 0;
   bool with_policy = false;
@@ -274,18 +272,19 @@ inline void tm_build_policy(const int* sizes, const float* const* W, const float
   P.with_policy = true;
 }
 
-// W[l] are TF kernels [in,out] row-major: W1 [26,S], W2 [S,S], W3 [S,20].
+// Dynamics weight images.  W[l] are TF kernels [in,out] (row stride ld): W1 [26,S], W2 [S,S], W3 [S,20].
 // Bias-in-GEMM: input columns 26,27 of A0 are 1.0; hidden units S and S+1 of both hidden layers are wired to be
 // exactly 1.0 after ReLU; row S / S+1 of the next layer's kernel hold bf16(b) and bf16(b - bf16(b)).
-// ln_gamma / ln_beta: [2][S] LayerNorm parameters of the two hidden layers, or nullptr.  With LayerNorm the kernel
+// ln_gamma / ln_beta: LayerNorm parameters of the two hidden layers, or nullptr.  With LayerNorm the kernel
 // multiplies UN-normalised ReLU outputs r by W' = diag(gamma) W and corrects in the next epilogue:
 //   LN(r) W + b = rho * (r W') - rho * mu * u + c,   u = gamma^T W (column sums of the bf16 W'),  c = beta^T W + b,
 // rho = 1 / sqrt(var(r) + eps) and mu = mean(r) per path.  Biases of layers 2 / 3 live in c, so no "ones" units.
-inline void tm_build(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
-                     int S, int cg, int var, const float* const* ln_gamma, const float* const* ln_beta, TmHostPlan* out) {
+//
+// The images are packed ON THE DEVICE from the float32 copies the handle keeps for the verification kernel, so a
+// refresh after dyn_model.fit (train_mpc_ppo.py:279) is a copy plus two small kernels on the caller's stream whether
+// the new weights come from the host (bcmpc_set_dynamics) or are already device-resident (bcmpc_set_dynamics_device).
+inline void tm_geometry(int S, int cg, int var, TmHostPlan* out) {
   TmHostPlan& P = *out;
-  P = TmHostPlan{};
-  const int in_dim = kD + kA;
   const bool ln = var == kVarLayerNorm;
   P.cg = cg;
   P.hidden = S;
@@ -293,71 +292,97 @@ inline void tm_build(const float* W1, const float* b1, const float* W2, const fl
   P.s_pad = ((ln ? S : S + 2) + 63) / 64 * 64;
   P.nc = P.s_pad / 64;
   P.lay = make_layout(cg, P.nc, var);
-  const int NC = P.nc, NKB = P.nc, kbs = P.lay.kbs;
-  const int rows_h = kChunk / cg, rows_o = kOutN / cg;                 // B rows per CTA (hidden / output tiles)
-  const uint32_t blk_h = P.lay.blk_h, blk_o = P.lay.blk_o, w1_bytes = P.lay.w1_bytes;
-  const uint32_t res_bytes = P.lay.res_bytes, stage_bytes = P.lay.stage_bytes;
+  P.res_total = (size_t)cg * P.lay.res_bytes;
+  P.stream_total = (size_t)P.nc * P.lay.nstg * cg * P.lay.stage_bytes;
+  P.lnvec_floats = ln ? (size_t)2 * P.s_pad + 2 * kOutN : 0;      // [u2][c2][u3][c3]
+}
 
-  auto hi = [](float v) { return f32_to_bf16(v); };
-  auto lo = [](float v) { return f32_to_bf16(v - bf16_to_f32(f32_to_bf16(v))); };
-  const uint16_t one = f32_to_bf16(1.0f);
-  // effective (bias-augmented, zero-padded) kernels as functions
-  auto w1 = [&](int k, int n) -> uint16_t {        // k < 64 (input column), n < s_pad (hidden unit)
-    if (n < S) return k < in_dim ? f32_to_bf16(W1[(size_t)k * S + n]) : k == in_dim ? hi(b1[n]) : k == in_dim + 1 ? lo(b1[n]) : 0;
-    if (!ln && (n == S || n == S + 1)) return k == in_dim ? one : 0;          // the hidden "ones" units: relu(1 * 1) = 1
-    return 0;
-  };
-  auto w2 = [&](int k, int n) -> uint16_t {
-    if (ln) return (n < S && k < S) ? f32_to_bf16(ln_gamma[0][k] * W2[(size_t)k * S + n]) : 0;
-    if (n < S) return k < S ? f32_to_bf16(W2[(size_t)k * S + n]) : k == S ? hi(b2[n]) : k == S + 1 ? lo(b2[n]) : 0;
-    if (n == S || n == S + 1) return k == S ? one : 0;
-    return 0;
-  };
-  auto w3 = [&](int k, int n) -> uint16_t {        // n < 32 (output column)
-    if (n >= kD) return 0;
-    if (ln) return k < S ? f32_to_bf16(ln_gamma[1][k] * W3[(size_t)k * kD + n]) : 0;
-    return k < S ? f32_to_bf16(W3[(size_t)k * kD + n]) : k == S ? hi(b3[n]) : k == S + 1 ? lo(b3[n]) : 0;
-  };
-  if (ln) {
-    P.lnvec.assign((size_t)2 * P.s_pad, 0.f);
-    for (int n = 0; n < S; ++n) {
-      double u = 0.0, c = b2[n];
-      for (int k = 0; k < S; ++k) { u += bf16_to_f32(w2(k, n)); c += (double)ln_beta[0][k] * W2[(size_t)k * S + n]; }
-      P.lnvec[n] = (float)u; P.lnvec[P.s_pad + n] = (float)c;
-    }
-    for (int d = 0; d < kD; ++d) {
-      double u = 0.0, c = b3[d];
-      for (int k = 0; k < S; ++k) { u += bf16_to_f32(w3(k, d)); c += (double)ln_beta[1][k] * W3[(size_t)k * kD + d]; }
-      P.u3[d] = (float)u; P.c3[d] = (float)c;
+struct PackArgs {
+  const float *W1, *b1, *W2, *b2, *W3, *b3;     // device, row strides ld1..ld3
+  const float *g1, *be1, *g2, *be2;             // LayerNorm gamma / beta of hidden layers 1, 2 (nullptr = off)
+  int ld1, ld2, ld3;
+  int S, s_pad, nc, cg, kbs, nstg;
+  uint32_t blk_h, blk_o, w1_bytes, res_bytes, stage_bytes;
+  uint16_t *res, *stream;
+  float* lnvec;
+};
+
+__device__ __forceinline__ uint16_t pk_hi(float v) { return f32_to_bf16(v); }
+__device__ __forceinline__ uint16_t pk_lo(float v) { return f32_to_bf16(__fsub_rn(v, bf16_to_f32(f32_to_bf16(v)))); }
+// effective (bias-augmented, zero-padded) kernels
+__device__ __forceinline__ uint16_t pk_w1(const PackArgs& a, int k, int n) {        // k < 64 (input column), n < s_pad (hidden unit)
+  constexpr int in_dim = kD + kA;
+  const bool ln = a.g1 != nullptr;
+  if (n < a.S) return k < in_dim ? f32_to_bf16(a.W1[(size_t)k * a.ld1 + n]) : k == in_dim ? pk_hi(a.b1[n]) : k == in_dim + 1 ? pk_lo(a.b1[n]) : 0;
+  if (!ln && (n == a.S || n == a.S + 1)) return k == in_dim ? (uint16_t)0x3F80 : 0;   // the hidden "ones" units: relu(1 * 1) = 1
+  return 0;
+}
+__device__ __forceinline__ uint16_t pk_w2(const PackArgs& a, int k, int n) {
+  const int S = a.S;
+  if (a.g1) return (n < S && k < S) ? f32_to_bf16(__fmul_rn(a.g1[k], a.W2[(size_t)k * a.ld2 + n])) : 0;
+  if (n < S) return k < S ? f32_to_bf16(a.W2[(size_t)k * a.ld2 + n]) : k == S ? pk_hi(a.b2[n]) : k == S + 1 ? pk_lo(a.b2[n]) : 0;
+  if (n == S || n == S + 1) return k == S ? (uint16_t)0x3F80 : 0;
+  return 0;
+}
+__device__ __forceinline__ uint16_t pk_w3(const PackArgs& a, int k, int n) {        // n < 32 (output column)
+  const int S = a.S;
+  if (n >= kD) return 0;
+  if (a.g1) return k < S ? f32_to_bf16(__fmul_rn(a.g2[k], a.W3[(size_t)k * a.ld3 + n])) : 0;
+  return k < S ? f32_to_bf16(a.W3[(size_t)k * a.ld3 + n]) : k == S ? pk_hi(a.b3[n]) : k == S + 1 ? pk_lo(a.b3[n]) : 0;
+}
+
+// One thread per element of the three padded kernels (n fastest: coalesced reads of the float32 rows).
+//   resident image, per CTA rank r: [W1 chunk 0..NC-1][W3 k-block 0..NC-1]
+//   streamed image: one slot [CG][stage_bytes] per (chunk, stage), chunk-major = consumption order
+__global__ void pack_images_kernel(PackArgs a) {
+  const int sp = a.s_pad, rows_h = kChunk / a.cg, rows_o = kOutN / a.cg;
+  const int n1 = 64 * sp, n3 = sp * kOutN, n2 = sp * sp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n3 + n2; i += gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int k = i / sp, n = i % sp, c = n / kChunk, j = n % kChunk, r = j / rows_h, ii = j % rows_h;
+      a.res[((size_t)r * a.res_bytes + (size_t)c * a.blk_h + sw128_offset(ii, k)) / 2] = pk_w1(a, k, n);
+    } else if (i < n1 + n3) {
+      const int e = i - n1, k = e / kOutN, n = e % kOutN, r = n / rows_o, ii = n % rows_o;
+      a.res[((size_t)r * a.res_bytes + a.w1_bytes + (size_t)(k / 64) * a.blk_o + sw128_offset(ii, k % 64)) / 2] = pk_w3(a, k, n);
+    } else {
+      const int e = i - n1 - n3, k = e / sp, n = e % sp, c = n / kChunk, j = n % kChunk, r = j / rows_h, ii = j % rows_h;
+      const int kb = k / 64, stg = kb / a.kbs, t = kb % a.kbs;
+      a.stream[((size_t)(c * a.nstg + stg) * a.cg * a.stage_bytes + (size_t)r * a.stage_bytes + (size_t)t * a.blk_h +
+                sw128_offset(ii, k % 64)) / 2] = pk_w2(a, k, n);
     }
   }
+}
 
-  // ---- resident image: per rank [W1 chunk 0..NC-1][W3 k-block 0..NKB-1] ----
-  P.res.assign((size_t)cg * res_bytes / 2, 0);
-  for (int r = 0; r < cg; ++r) {
-    const size_t rb = (size_t)r * res_bytes;
-    for (int c = 0; c < NC; ++c)
-      for (int i = 0; i < rows_h; ++i)
-        for (int k = 0; k < 64; ++k)
-          P.res[(rb + (size_t)c * blk_h + sw128_offset(i, k)) / 2] = w1(k, c * kChunk + r * rows_h + i);
-    for (int kb = 0; kb < NKB; ++kb)
-      for (int i = 0; i < rows_o; ++i)
-        for (int kk = 0; kk < 64; ++kk)
-          P.res[(rb + w1_bytes + (size_t)kb * blk_o + sw128_offset(i, kk)) / 2] = w3(kb * 64 + kk, r * rows_o + i);
-  }
-  // ---- streamed image: one slot [CG][stage_bytes] per (chunk, stage), chunk-major = consumption order ----
-  const int nstg = (NC + kbs - 1) / kbs;
-  P.stream.assign((size_t)NC * nstg * cg * stage_bytes / 2, 0);
-  for (int c = 0; c < NC; ++c)
-    for (int j = 0; j < nstg; ++j) {
-      const size_t off = (size_t)(c * nstg + j) * cg * stage_bytes;
-      for (int r = 0; r < cg; ++r)
-        for (int t = 0; t < kbs && j * kbs + t < NKB; ++t)
-          for (int ii = 0; ii < rows_h; ++ii)
-            for (int kk = 0; kk < 64; ++kk)
-              P.stream[(off + (size_t)r * stage_bytes + (size_t)t * blk_h + sw128_offset(ii, kk)) / 2] =
-                  w2((j * kbs + t) * 64 + kk, c * kChunk + r * rows_h + ii);
+// LayerNorm correction vectors, one warp per column: lnvec = [u2 (s_pad)][c2 (s_pad)][u3 (32)][c3 (32)]
+__global__ void pack_ln_kernel(PackArgs a) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  const int sp = a.s_pad, S = a.S;
+  if (col >= sp + kOutN) return;
+  const bool l3 = col >= sp;
+  const int n = l3 ? col - sp : col;
+  const bool live = l3 ? n < kD : n < S;
+  double u = 0.0, c = 0.0;
+  if (live)
+    for (int k = lane; k < S; k += 32) {
+      if (l3) { u += (double)bf16_to_f32(pk_w3(a, k, n)); c += (double)a.be2[k] * (double)a.W3[(size_t)k * a.ld3 + n]; }
+      else    { u += (double)bf16_to_f32(pk_w2(a, k, n)); c += (double)a.be1[k] * (double)a.W2[(size_t)k * a.ld2 + n]; }
     }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { u += __shfl_xor_sync(0xffffffffu, u, off); c += __shfl_xor_sync(0xffffffffu, c, off); }
+  if (lane == 0) {
+    if (live) c += (double)(l3 ? a.b3[n] : a.b2[n]);
+    float* pu = l3 ? a.lnvec + 2 * sp : a.lnvec;
+    float* pc = l3 ? a.lnvec + 2 * sp + kOutN : a.lnvec + sp;
+    pu[n] = live ? (float)u : 0.f;
+    pc[n] = live ? (float)c : 0.f;
+  }
+}
+
+inline cudaError_t tm_pack(const PackArgs& a, cudaStream_t st) {
+  const int total = 64 * a.s_pad + a.s_pad * kOutN + a.s_pad * a.s_pad;
+  pack_images_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+  if (a.g1) pack_ln_kernel<<<(a.s_pad + kOutN + 7) / 8, 256, 0, st>>>(a);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -494,9 +519,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   }
   if constexpr (LN) {
     float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
-    for (int i = tid; i < 2 * 64 * NC; i += kThreads) s_vec[i] = a.lnvec[i];
+    for (int i = tid; i < 2 * 64 * NC + 2 * kOutN; i += kThreads) s_vec[i] = a.lnvec[i];
     // per-row statistics start at zero: a group without a chunk in some layer never writes its partial
-    for (int i = tid; i < (int)(kLnStatsBytes / 4); i += kThreads) s_vec[2 * 64 * NC + i] = 0.f;
+    for (int i = tid; i < (int)(kLnStatsBytes / 4); i += kThreads) s_vec[2 * 64 * NC + 2 * kOutN + i] = 0.f;
   }
   if (warp == 2) ptx::tmem_alloc_cg<CG>(ptx::smem_u32(s_tmem), kTmemCols);
   ptx::tc_fence_before();
@@ -846,9 +871,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       // ---- LayerNorm variant: statistics of this row's ReLU outputs, correction of the previous layer's statistics ----
       // (each row's chunks are split between the two epilogue groups: partial sums meet in shared memory)
       float ln_sum = 0.f, ln_sq = 0.f, rho = 1.f, rmu = 0.f;
-      [[maybe_unused]] float2* s_stats = reinterpret_cast<float2*>(smem + L.off_ln + 2u * 64u * NC * 4u);   // [layer][group][row]
+      [[maybe_unused]] float2* s_stats = reinterpret_cast<float2*>(smem + L.off_ln + (2u * 64u * NC + 2u * kOutN) * 4u);   // [layer][group][row]
       [[maybe_unused]] const float* s_u2 = reinterpret_cast<const float*>(smem + L.off_ln);
       [[maybe_unused]] const float* s_c2 = s_u2 + 64 * NC;
+      [[maybe_unused]] const float* s_u3 = s_u2 + 2 * 64 * NC;
+      [[maybe_unused]] const float* s_c3 = s_u3 + kOutN;
       // rho = 1 / sqrt(var + eps), rmu = rho * mean of the layer whose partial sums are in s_stats[layer]
       auto ln_row_stats = [&](int layer) {
         const float2 p0 = s_stats[(layer * 2 + 0) * kRows + row], p1 = s_stats[(layer * 2 + 1) * kRows + row];
@@ -987,7 +1014,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if constexpr (LN) {
           ln_row_stats(1);
 #pragma unroll
-          for (int d = 0; d < kD; ++d) v[d] = __float_as_uint(fmaf(rho, __uint_as_float(v[d]), fmaf(-rmu, a.u3[d], a.c3[d])));
+          for (int d = 0; d < kD; ++d) v[d] = __float_as_uint(fmaf(rho, __uint_as_float(v[d]), fmaf(-rmu, s_u3[d], s_c3[d])));
           ln_sum = 0.f; ln_sq = 0.f;
         }
 #pragma unroll

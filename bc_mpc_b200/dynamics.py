@@ -24,6 +24,7 @@ class NNDynamicsModel:
             (self.mean_obs, self.std_obs, self.mean_action, self.std_action, self.mean_reward, self.std_reward,
              self.mean_nxt_state, self.std_nxt_state, self.mean_deltas, self.std_deltas) = normalization  # dynamics.py:41
         self.weights = None
+        self.device_weights = None     # (tensors, layout, stream_ptr) after set_weights_device
         self.layer_norm = layer_norm           # FLAGS.LAYER_NORM of the reference (dynamics.py:68-69)
         self.layer_norm_params = None          # [(gamma, beta)] per hidden layer
         self.version = 0           # bumped on every weight change; controllers re-upload lazily
@@ -33,12 +34,37 @@ class NNDynamicsModel:
     # -- weight hand-off (replaces tf variables / fit) ------------------------------------------------
     def set_weights(self, weights, layer_norm_params=None):
         self.weights = [(np.asarray(w, np.float32), np.asarray(b, np.float32)) for w, b in weights]
+        self.device_weights = None
         if self.layer_norm:
             if layer_norm_params is None:
                 raise ValueError("this model was built with layer_norm=True: pass [(gamma, beta), ...] per hidden layer")
             self.layer_norm_params = [(np.asarray(g, np.float32), np.asarray(b, np.float32)) for g, b in layer_norm_params]
         self.version += 1
         self._predictor = None
+
+    def set_weights_device(self, tensors, layout="out_in", stream_ptr=None):
+        """Hand-off from a trainer that keeps the parameters on the planner's GPU (what replaces sess.run + fit when
+        the dynamics model is trained in PyTorch): tensors = [(W, b), ...] float32 CUDA tensors, layout "out_in"
+        (torch.nn.Linear.weight) or "in_out" (TF kernels).  No host copy is made; controllers and predict() pick the
+        tensors up through Planner.set_dynamics_device on stream_ptr."""
+        if self.layer_norm:
+            raise NotImplementedError("device hand-off of LayerNorm parameters: use set_weights")
+        self.device_weights = (list(tensors), layout, stream_ptr)
+        self.weights = None
+        self.version += 1
+        self._predictor = None
+
+    def upload(self, planner):
+        """Gives `planner` the current dynamics weights (and LayerNorm parameters)."""
+        if self.device_weights is not None:
+            tensors, layout, stream_ptr = self.device_weights
+            planner.set_dynamics_device(tensors, layout=layout, stream_ptr=stream_ptr)
+            return
+        if self.weights is None:
+            raise RuntimeError("NNDynamicsModel has no weights (set_weights / set_weights_device / load_vars)")
+        planner.set_dynamics(self.weights)
+        if self.layer_norm:
+            planner.set_layer_norm(self.layer_norm_params)
 
     def load_vars(self, var_dict):
         """var_dict: {tf variable name: ndarray} as written by logz.pickle_tf_vars (logz.py:78-85)."""
@@ -58,16 +84,12 @@ class NNDynamicsModel:
 
     # -- dynamics.py:106-119 --------------------------------------------------------------------------
     def predict(self, unnormalized_state, unnormalized_action):
-        if self.weights is None:
-            raise RuntimeError("NNDynamicsModel has no weights (set_weights / load_vars)")
         s = np.asarray(unnormalized_state, np.float64)
         a = np.asarray(unnormalized_action, np.float64)
         if self._predictor is None:
             p = Planner(self.obs_dim, self.act_dim, self.n_layers, self.size, self.activation, num_paths=1,
                         horizon=1, precision="fp32")
-            p.set_dynamics(self.weights)
-            if self.layer_norm:
-                p.set_layer_norm(self.layer_norm_params)
+            self.upload(p)
             p.set_normalization(*self.normalization6())
             self._predictor = p
         return self._predictor.predict(s, a)
@@ -105,9 +127,7 @@ class NNDynamicsRewardModel(NNDynamicsModel):
             raise RuntimeError("NNDynamicsRewardModel has no weights (set_weights / load_vars)")
         if self._predictor is None:
             p = Planner(self.obs_dim, self.act_dim, 2, self.size, self.activation, num_paths=1, horizon=1, precision="fp32")
-            p.set_dynamics(self.weights)
-            if self.layer_norm:
-                p.set_layer_norm(self.layer_norm_params)
+            self.upload(p)
             p.set_normalization(*self.normalization6())
             self.upload_reward_head(p)
             self._predictor = p

@@ -82,6 +82,28 @@ class Planner:
                 raise ValueError(f"layer {i}: expected kernel {(sizes[i], sizes[i + 1])}, got {w.shape} / {b.shape}")
         self._ck(self._lib.bcmpc_set_dynamics(self._h, L.ptr_array(Ws), L.ptr_array(bs), len(Ws)))
 
+    def set_dynamics_device(self, weights, layout="in_out", stream_ptr=None):
+        """Weight hand-off without a host round trip (bcmpc_set_dynamics_device): weights = [(W, b), ...] of float32
+        CUDA tensors on this planner's device (anything with data_ptr() / shape / is_contiguous(), e.g. torch
+        parameters), W [in,out] (layout="in_out", TF kernels) or [out,in] (layout="out_in", torch.nn.Linear.weight).
+        Enqueued on stream_ptr (None = the handle's stream); the tensors must stay alive until that stream has run."""
+        sizes = [self.D + self.A] + [self.cfg.hidden_size] * self.cfg.n_hidden + [self.D]
+        if len(weights) != len(sizes) - 1:
+            raise ValueError(f"expected {len(sizes) - 1} layers, got {len(weights)}")
+        if layout not in ("in_out", "out_in"):
+            raise ValueError("layout must be 'in_out' or 'out_in'")
+        for i, (w, b) in enumerate(weights):
+            want = (sizes[i], sizes[i + 1]) if layout == "in_out" else (sizes[i + 1], sizes[i])
+            if tuple(w.shape) != want or tuple(b.shape) != (sizes[i + 1],):
+                raise ValueError(f"layer {i}: expected kernel {want} / bias {(sizes[i + 1],)}, got {tuple(w.shape)} / {tuple(b.shape)}")
+            for t in (w, b):
+                if not t.is_contiguous() or "float32" not in str(t.dtype) or not t.is_cuda:
+                    raise ValueError(f"layer {i}: tensors must be contiguous float32 CUDA tensors")
+        Wp = (C.c_void_p * len(weights))(*[w.data_ptr() for w, _ in weights])
+        bp = (C.c_void_p * len(weights))(*[b.data_ptr() for _, b in weights])
+        self._ck(self._lib.bcmpc_set_dynamics_device(self._h, Wp, bp, len(weights), 0 if layout == "in_out" else 1,
+                                                     _stream(stream_ptr)))
+
     def set_layer_norm(self, params, eps=1e-12):
         """LayerNorm after every hidden activation (dynamics.py:68-69): params = [(gamma[size], beta[size]), ...] per
         hidden layer, or None to switch it off.  Call after set_dynamics (new weights reset it)."""

@@ -155,6 +155,31 @@ def extras():
         "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
         "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
     pl.close()
+    # weight refresh after dyn_model.fit (train_mpc_ppo.py:279): host arrays vs device-resident torch parameters
+    import torch
+    pl = make(4096, 15, "bf16")
+    tens = [(torch.from_numpy(np.ascontiguousarray(w.T)).cuda(), torch.from_numpy(b).cuda()) for w, b in weights]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        pl.set_dynamics(weights)
+        pl.set_dynamics_device(tens, layout="out_in", stream_ptr=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    n = 20
+    t0 = time.perf_counter()
+    for _ in range(n):
+        pl.set_dynamics(weights)
+    t_host = (time.perf_counter() - t0) / n
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(n):
+        pl.set_dynamics_device(tens, layout="out_in", stream_ptr=torch.cuda.current_stream().cuda_stream)
+    e1.record()
+    t_enq = (time.perf_counter() - t0) / n
+    torch.cuda.synchronize()
+    out["weight_refresh_bf16_2x500"] = {"host_arrays_ms": 1e3 * t_host, "device_tensors_enqueue_ms": 1e3 * t_enq,
+                                        "device_tensors_gpu_ms": e0.elapsed_time(e1) / n}
+    pl.close()
     return out
 
 

@@ -104,6 +104,17 @@ int bcmpc_destroy(bcmpc_handle* h);
 /* NNDynamicsModel weights (dynamics.py:54-71).  n_layers = n_hidden + 1; W[i] is [in_i,out_i]. */
 int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int32_t n_layers);
 
+/* The same hand-off for a trainer whose parameters already live on this GPU (the PyTorch successor of
+ * dyn_model.fit, dynamics.py:81-104, train_mpc_ppo.py:279): W[i] / b[i] are DEVICE pointers (float32, contiguous);
+ * layout BCMPC_LAYOUT_IN_OUT = [in_i,out_i] like the TF kernels, BCMPC_LAYOUT_OUT_IN = [out_i,in_i] like
+ * torch.nn.Linear.weight (transposed on the fly).  The copy and the bf16 re-pack of the tensor-core images are enqueued on `stream`
+ * (NULL = the handle's stream) and the call returns without a host round trip; later plans on any stream are ordered
+ * after it.  The caller must not have plans of this handle in flight on OTHER streams while it runs.  Resets
+ * LayerNorm like bcmpc_set_dynamics. */
+enum { BCMPC_LAYOUT_IN_OUT = 0, BCMPC_LAYOUT_OUT_IN = 1 };
+int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const float* const* db, int32_t n_layers,
+                              int32_t layout, void* stream);
+
 /* LayerNorm variant of NNDynamicsModel (dynamics.py:68-69, FLAGS.LAYER_NORM, the default of train_mpc_ppo.py:52):
  * tf.contrib.layers.layer_norm AFTER the activation of every hidden layer - moments over the last axis, centre and
  * scale.  gamma[l], beta[l] are [hidden_size] for hidden layer l (n_hidden of them); eps is the variance epsilon

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+from oracle import mpc_oracle as O
 from tests._util import f32_uniform, make_pair
 
 pytestmark = pytest.mark.gpu
@@ -162,3 +163,72 @@ def test_fast_mode_large_k_properties():
     unsupported = dict(hidden=(500, 500, 500))   # three hidden layers: verification mode only
     with pytest.raises(RuntimeError, match="n_hidden"):
         make_pair(1, unsupported["hidden"], 128, 2, precision="bf16")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_device_weight_handoff_matches_host_upload(precision):
+    """bcmpc_set_dynamics_device (refresh after dyn_model.fit without a host round trip): torch CUDA
+    tensors in TF [in,out] or nn.Linear [out,in] layout give bit-identical plans to the host upload; the hand-off is
+    asynchronous on the trainer's stream and later plans are ordered after it."""
+    import torch
+    from bc_mpc_b200 import Planner
+    K, H, S = 1024, 6, 500
+    rng, norm, weights, state = O.synthetic_problem(51, (S, S))
+    _, _, weights2, _ = O.synthetic_problem(52, (S, S))
+
+    def planner():
+        pl = Planner(20, 6, 2, S, "relu", num_paths=K, horizon=H, precision=precision)
+        pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+        return pl
+
+    host = planner()
+    host.set_dynamics(weights)
+    want1 = host.rollout_debug(state, seed=3)
+    host.set_dynamics(weights2)
+    want2 = host.rollout_debug(state, seed=3)
+    assert not np.array_equal(want1[2], want2[2])
+
+    dev = torch.device("cuda:0")
+    side = torch.cuda.Stream()
+    for layout in ("in_out", "out_in"):
+        def tensors(ws):
+            return [(torch.from_numpy(w if layout == "in_out" else np.ascontiguousarray(w.T)).to(dev), torch.from_numpy(b).to(dev)) for w, b in ws]
+        t1, t2 = tensors(weights), tensors(weights2)
+        torch.cuda.synchronize()
+        pl = planner()
+        pl.set_dynamics_device(t1, layout=layout)
+        got1 = pl.rollout_debug(state, seed=3)
+        with torch.cuda.stream(side):                      # refresh enqueued on the trainer's stream, behind some work
+            junk = torch.randn(4096, 4096, device=dev) @ torch.randn(4096, 4096, device=dev)
+            pl.set_dynamics_device(t2, layout=layout, stream_ptr=side.cuda_stream)
+        got2 = pl.rollout_debug(state, seed=3)             # on the handle's own stream: must wait for the hand-off
+        del junk
+        for a, b in zip(want1, got1):
+            assert np.array_equal(a, b)
+        for a, b in zip(want2, got2):
+            assert np.array_equal(a, b)
+        r_host, r_dev = host.plan(state, seed=5)[0], pl.plan(state, seed=5)[0]
+        assert r_host["index"] == r_dev["index"] and r_host["cost"] == r_dev["cost"]
+    with pytest.raises(ValueError):
+        pl.set_dynamics_device([(w.cpu(), b) for w, b in t1])
+    # through the reference-shaped classes: NNDynamicsModel.set_weights_device -> MPCcontroller
+    from bc_mpc_b200 import controllers, cost_functions, dynamics
+
+    class Space:
+        def __init__(self, n):
+            self.low, self.high, self.shape = -np.ones(n), np.ones(n), (n,)
+
+    class Env:
+        action_space, observation_space = Space(6), Space(20)
+
+    n10 = (norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], None, None, None, None,
+           norm["mean_deltas"], norm["std_deltas"])
+    dm = dynamics.NNDynamicsModel(Env(), 2, S, "relu", None, n10)
+    c = controllers.MPCcontroller(Env(), dm, horizon=H, cost_fn=cost_functions.cheetah_cost_fn, num_simulated_paths=K, precision=precision)
+    for ws, ts in ((weights, t1), (weights2, t2)):       # t1, t2 are in nn.Linear layout after the loop above
+        dm.set_weights_device(ts, layout="out_in")
+        np.random.seed(3)
+        a_dev = c.get_action(state)
+        dm.set_weights(ws)
+        np.random.seed(3)
+        assert np.array_equal(a_dev, c.get_action(state))
