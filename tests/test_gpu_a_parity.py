@@ -87,6 +87,46 @@ def test_config_1_2_verify_mode(seed, K, H):
     assert abs(rec["cost"] - dbg["costs"][dbg["argmin"]]) < 1e-3
 
 
+def test_config_5_three_by_1024_net():
+    """BASELINE.json configs[4]: dynamics MLP 3 x 1024 (verification kernel).  Oracle-size parity, then the
+    size-independent properties at a larger K: device sampling replay, K-sharding with the min-loc reduce."""
+    import time
+    K, H = 512, 6
+    rng, norm, state, pl, mpc = make_pair(5, (1024, 1024, 1024), K, H)
+    actions = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    assert scaled_rel_err(so, dbg["states"], state_scale(norm)).max() < TOL
+    assert np.abs(co - dbg["costs"]).max() < 1e-3
+    rec = pl.plan(state, inj=actions)[0]
+    assert rec["index"] == dbg["argmin"] and np.array_equal(rec["action"][:6], act)
+    # larger K, sharded 4 ways (path_offset / total_paths as on 4 GPUs): the union of the shards is the single plan
+    K2, H2 = 1 << 14, 30
+    w = mpc.dyn_model.weights
+    _, _, _, whole, _ = make_pair(5, (1024, 1024, 1024), K2, H2, weights=w)
+    t0 = time.perf_counter()
+    full = whole.plan(state, seed=77)[0]
+    dt = time.perf_counter() - t0
+    print(f"3x1024 verification kernel: {K2 * H2 / dt:.3e} transitions/s")
+    best = None
+    for g in range(4):
+        _, _, _, shard, _ = make_pair(5, (1024, 1024, 1024), K2 // 4, H2, weights=w, path_offset=g * K2 // 4, total_paths=K2)
+        r = shard.plan(state, seed=77)[0]
+        if best is None or r["cost"] < best["cost"] or (r["cost"] == best["cost"] and r["index"] < best["index"]):
+            best = r
+        shard.close()
+    assert best["index"] == full["index"] and best["cost"] == full["cost"] and np.array_equal(best["action"], full["action"])
+    inj = whole.sample_injection(77)[0]
+    j = int(full["index"])
+    states = np.tile(state, [1, 1])
+    cost = 0.0
+    for h in range(H2):      # replay only the winning path through the oracle
+        nxt = mpc.dyn_model.predict(states, inj[h, j:j + 1])
+        cost += float(O.cheetah_cost_fn(states, inj[h, j:j + 1], nxt)[0])
+        states = nxt
+    assert abs(cost - full["cost"]) < 1e-3 * max(1.0, abs(cost))
+
+
 def test_layer_norm_dynamics_variant():
     """FLAGS.LAYER_NORM = True, the default of train_mpc_ppo.py:52: LayerNorm after every hidden ReLU (dynamics.py:68-69)."""
     K, H, S = 1000, 15, 256
