@@ -244,7 +244,9 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 }
 
 int tm_variant(const bcmpc_handle* h) {
-  if (h->cfg.proposal != BCMPC_PROP_UNIFORM) return tmx::kVarPolicy;
+  const int pol = h->cfg.proposal != BCMPC_PROP_UNIFORM ? tmx::kVarPolicy : 0;
+  if (h->rew.set) return tmx::kVarReward | pol;
+  if (pol) return tmx::kVarPolicy;
   return h->ln_on ? tmx::kVarLayerNorm : tmx::kVarUniform;
 }
 
@@ -259,6 +261,10 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   }
   const tmx::TmHostPlan& P = h->tmp;
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
+  if (P.reward && !tmx::tm_reward_width_supported(P.nc))
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the learned-reward model is built for hidden sizes 193..256 and 449..512 (got %d); use BCMPC_PREC_FP32_VERIFY", S);
+  if (P.reward && h->ln_on)
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm together with the reward head runs in BCMPC_PREC_FP32_VERIFY only");
   if (P.lay.nst < 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "weight ring does not fit in shared memory");
   auto ensure = [&](void** ptr, size_t* cap, size_t need) -> cudaError_t {
     if (need <= *cap) return cudaSuccess;
@@ -271,17 +277,22 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   };
   CK(h, ensure((void**)&h->d_res, &h->res_cap, P.res_total));
   CK(h, ensure((void**)&h->d_stream, &h->stream_cap, P.stream_total));
-  if (P.layer_norm) CK(h, ensure((void**)&h->d_lnvec, &h->lnvec_cap, P.lnvec_floats * sizeof(float)));
+  if (P.lnvec_floats) CK(h, ensure((void**)&h->d_lnvec, &h->lnvec_cap, P.lnvec_floats * sizeof(float)));
   tmx::PackArgs a{};
   const MlpDesc& d = h->dyn.desc;
   a.W1 = d.W[0]; a.b1 = d.b[0]; a.W2 = d.W[1]; a.b2 = d.b[1]; a.W3 = d.W[2]; a.b3 = d.b[2];
   a.ld1 = d.out_pad[0]; a.ld2 = d.out_pad[1]; a.ld3 = d.out_pad[2];
   if (P.layer_norm) { a.g1 = d.ln_gamma[0]; a.be1 = d.ln_beta[0]; a.g2 = d.ln_gamma[1]; a.be2 = d.ln_beta[1]; }
+  if (P.reward) {
+    const MlpDesc& r = h->rew.desc;
+    a.Wr1 = r.W[0]; a.br1 = r.b[0]; a.Wr2 = r.W[1]; a.br2 = r.b[1];
+    a.ldr1 = r.out_pad[0]; a.ldr2 = r.out_pad[1];
+  }
   a.S = S; a.s_pad = P.s_pad; a.nc = P.nc; a.cg = P.cg; a.kbs = P.lay.kbs; a.nstg = P.lay.nstg;
   a.blk_h = P.lay.blk_h; a.blk_o = P.lay.blk_o; a.w1_bytes = P.lay.w1_bytes; a.res_bytes = P.lay.res_bytes; a.stage_bytes = P.lay.stage_bytes;
   a.res = reinterpret_cast<uint16_t*>(h->d_res); a.stream = reinterpret_cast<uint16_t*>(h->d_stream); a.lnvec = h->d_lnvec;
   CK(h, tmx::tm_pack(a, st));
-  h->launches += P.layer_norm ? 2 : 1;
+  h->launches += (P.layer_norm || P.reward) ? 2 : 1;
   if (!h->trace_path.empty() && !h->d_trace)
     CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots));
   h->tm_ready = true;
@@ -309,8 +320,15 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.span[j] = h->norm.span[j];
   }
   const bool pol = p.proposal != BCMPC_PROP_UNIFORM;
-  const int var = pol ? tmx::kVarPolicy : (P.layer_norm ? tmx::kVarLayerNorm : tmx::kVarUniform);
+  const int var = P.reward ? (tmx::kVarReward | (pol ? tmx::kVarPolicy : 0)) : pol ? tmx::kVarPolicy : (P.layer_norm ? tmx::kVarLayerNorm : tmx::kVarUniform);
   a.proposal = p.proposal; a.inj_kind = p.inj_kind;
+  if (h->cfg.activation == BCMPC_ACT_TANH && !P.reward)
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: tanh dynamics are built for the learned-reward model (bcmpc_set_reward_head); a plain tanh NNDynamicsModel runs in BCMPC_PREC_FP32_VERIFY");
+  if (P.reward) {
+    a.lnvec = h->d_lnvec;
+    a.act_tanh = h->cfg.activation == BCMPC_ACT_TANH ? 1 : 0;
+    a.mean_reward = (float)h->mean_reward; a.std_reward = (float)h->std_reward; a.gamma = (float)h->gamma;
+  }
   if (P.layer_norm) {
     if (pol) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm dynamics with a proposal network run in BCMPC_PREC_FP32_VERIFY only");
     a.lnvec = h->d_lnvec;
@@ -550,18 +568,30 @@ int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float
 int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward,
                           double std_reward, double gamma) {
   if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
-  if (h->cfg.precision == BCMPC_PREC_BF16_FAST)
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "learned-reward planners run in BCMPC_PREC_FP32_VERIFY only this round");
+  const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
+  if (fast && !h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the reward head");
   CK(h, cudaSetDevice(h->cfg.device));
-  CK(h, cudaStreamSynchronize(h->stream));
-  if (!W) { h->rew.release(); update_verify_geometry(h); return BCMPC_OK; }
+  CK(h, cudaDeviceSynchronize());
+  if (!W) {
+    h->rew.release();
+    update_verify_geometry(h);
+    if (fast) { int rc = tm_prepare(h, h->stream); if (rc) return rc; CK(h, cudaStreamSynchronize(h->stream)); }
+    return BCMPC_OK;
+  }
   if (!b || !W[0] || !W[1] || !b[0] || !b[1]) return fail(h, BCMPC_ERR_INVALID, "null reward-head pointer");
+  if (fast && h->cfg.activation != BCMPC_ACT_TANH)
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the learned-reward model is built with tanh layers (dynamics.py:162); other activations run in BCMPC_PREC_FP32_VERIFY");
   if (h->cfg.n_hidden != 2) return fail(h, BCMPC_ERR_INVALID, "NNDynamicsRewardModel has a shared layer and one hidden layer per head: n_hidden must be 2");
   const int sizes[3] = {h->cfg.hidden_size, h->cfg.hidden_size, 1};
   int rc = upload_mlp(h, h->rew, 2, sizes, W, b);
   if (rc) return rc;
   h->mean_reward = mean_reward; h->std_reward = std_reward; h->gamma = gamma;
   update_verify_geometry(h);
+  if (fast) {
+    rc = tm_prepare(h, h->stream);
+    if (rc) { h->rew.release(); update_verify_geometry(h); return rc; }
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
   return BCMPC_OK;
 }
 

@@ -64,19 +64,14 @@ __host__ __device__ constexpr int buf_col(int b) { return b < kNumDBuf ? kColD +
 // (2x256 net: 4 buffers).  With a single buffer (hidden = 512) at least the LAST chunk goes elsewhere - to the
 // accumulator buffer of chunk nc-3, drained and without further user in the step - so the step's tail does not wait.
 __host__ __device__ constexpr int a2_buffers(int nc) { return 1 + (256 - 32 * nc) / 32 > 4 ? 4 : 1 + (256 - 32 * nc) / 32; }
-__host__ __device__ constexpr int a2_col(int c, int nc) {
+// (nc = hidden-1 chunks, which decide the free A1 columns; nc2 = hidden-2 chunks)
+__host__ __device__ constexpr int a2_col(int c, int nc, int nc2) {
   const int nb = a2_buffers(nc), b = c % nb;
-  if (nb == 1) return (nc >= 3 && c == nc - 1) ? kColD + kChunk * ((nc - 3) % kNumDBuf) : kColA2;
+  if (nb == 1) return (nc2 >= 3 && c == nc2 - 1) ? kColD + kChunk * ((nc2 - 3) % kNumDBuf) : kColA2;
   return b == 0 ? kColA2 : kColA1 + 32 * nc + 32 * (b - 1);
 }
-// does the epilogue of chunk c have to wait for layer 3 to consume an earlier chunk (and which)?
-__host__ __device__ constexpr int a2_wait_chunk(int c, int nc) {
-  const int nb = a2_buffers(nc);
-  if (nb == 1) return (c == 0 || (nc >= 3 && c == nc - 1)) ? -1 : c - 1;
-  return c >= nb ? c - nb : -1;
-}
 constexpr int kD = 20, kA = 6;
-constexpr int kMaxStages = 16, kMaxChunks = 16;
+constexpr int kMaxStages = 16;
 constexpr int kSmemLimit = 232448;     // 227 KB
 constexpr int kA0Bytes = 128 * 128;
 
@@ -88,20 +83,21 @@ enum : int {
   kEvA0Ready = 0,      // A0 rows of the step are in shared memory                     (epilogue -> L1 issuer)
   kEvD3Full = 1,       // output accumulator complete                                  (L3 issuer -> epilogue)
   kEvA1Ready = 2,      // [8]  hidden-1 k-block c is in TMEM                           (epilogue -> L2 issuers)
-  kEvDFull = 10,       // [16] accumulator of chunk e complete                         (issuer -> epilogue)
-  kEvDEmpty = 26,      // [16] accumulator of chunk e drained into registers           (epilogue -> issuer of the next user)
-  kEvA2Ready = 42,     // [8]  hidden-2 chunk c is in TMEM                             (epilogue -> L3 issuer)
-  kEvA2Empty = 50,     // [8]  layer 3 has consumed hidden-2 chunk c                   (L3 issuer -> epilogue)
+  kEvDFull = 10,       // [24] accumulator of chunk e complete                         (issuer -> epilogue)
+  kEvDEmpty = 34,      // [24] accumulator of chunk e drained into registers           (epilogue -> issuer of the next user)
+  kEvA2Ready = 58,     // [16] hidden-2 chunk c is in TMEM                             (epilogue -> L3 issuer)
+  kEvA2Empty = 74,     // [16] layer 3 has consumed hidden-2 chunk c                   (L3 issuer -> epilogue)
   // proposal network (policy-guided shooting), also once per step each
-  kEvAp0Ready = 58,    // policy input rows are in shared memory                        (epilogue -> issuer)
-  kEvPdFull = 59,      // [4]  policy accumulators: layer-1 chunks 0,1, layer-2 chunks 0,1   (issuer -> epilogue)
-  kEvAp1Ready = 63,    // [2]  policy hidden-1 chunk in TMEM                            (epilogue -> issuer)
-  kEvAp2Ready = 65,    // [2]  policy hidden-2 chunk in TMEM
-  kEvPolFull = 67,     // policy output accumulator complete                            (issuer -> epilogue)
-  kNumEv = 68
+  kEvAp0Ready = 90,    // policy input rows are in shared memory                        (epilogue -> issuer)
+  kEvPdFull = 91,      // [4]  policy accumulators: layer-1 chunks 0,1, layer-2 chunks 0,1   (issuer -> epilogue)
+  kEvAp1Ready = 95,    // [2]  policy hidden-1 chunk in TMEM                            (epilogue -> issuer)
+  kEvAp2Ready = 97,    // [2]  policy hidden-2 chunk in TMEM
+  kEvPolFull = 99,     // policy output accumulator complete                            (issuer -> epilogue)
+  kNumEv = 100
 };
-// misc smem: [w_full 16][w_empty 16][res_full][events 68] x 8 B, tmem ptr, argmin scratch
-constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, kOffTmemPtr = 816, kOffRed = 832, kMiscBytes = 1024;
+constexpr int kMaxChunks1 = 8, kMaxChunks2 = 16;    // hidden-1 chunks; hidden-2 chunks (two heads of 8 in the learned-reward model)
+// misc smem: [w_full 16][w_empty 16][res_full][events 100] x 8 B, tmem ptr, argmin scratch
+constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, kOffTmemPtr = 1072, kOffRed = 1088, kMiscBytes = 1280;
 constexpr int kPolMaxHidden = 128;     // proposal network: two tanh layers of at most 128 units (MlpPolicy hid_size=128, BCnetwork 128/64)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -125,18 +121,22 @@ struct Layout {
   uint32_t blk_h = 0, blk_o = 0, w1_bytes = 0, res_bytes = 0, stage_bytes = 0;
   uint32_t off_a0 = 0, off_res = 0, off_pol = 0, pol_bytes = 0, off_ln = 0, ln_bytes = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
 };
-// kernel variants: uniform shooting, policy-guided shooting, uniform shooting with the LayerNorm dynamics net
-enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2 };
+// kernel variants (bit flags): policy-guided shooting, LayerNorm dynamics net, learned-reward model
+// (NNDynamicsRewardModel, dynamics.py:121-238: shared layer -> state-delta head + reward head, objective = predicted reward)
+enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2, kVarReward = 4, kVarRewardPolicy = 5 };
+__host__ __device__ constexpr int hidden2_chunks(int nc, int var) { return (var & kVarReward) ? 2 * nc : nc; }
+constexpr int kRewardCol = kD;          // output column of the reward head in D3
 constexpr uint32_t kLnStatsBytes = 2 * 2 * kRows * 8;      // [layer][epilogue group][row] (sum, sum of squares)
 constexpr Layout make_layout(int cg, int nc, int var) {
-  const bool pol = var == kVarPolicy, ln = var == kVarLayerNorm;
+  const bool pol = (var & kVarPolicy) != 0, ln = (var & kVarLayerNorm) != 0, rew = (var & kVarReward) != 0;
+  const int nc2 = hidden2_chunks(nc, var);
   Layout L;
   L.kbs = stage_kblocks(cg, nc);
   L.nstg = (nc + L.kbs - 1) / L.kbs;
   L.blk_h = (kChunk / cg) * 128u;                  // bytes of one 64-wide k-block image of a hidden tile, per CTA
   L.blk_o = (kOutN / cg) * 128u;                   // ... of an output tile
   L.w1_bytes = nc * L.blk_h;
-  L.res_bytes = L.w1_bytes + nc * L.blk_o;         // resident: W1 chunks then W3 k-blocks
+  L.res_bytes = L.w1_bytes + nc2 * L.blk_o;        // resident: W1 chunks then W3 k-blocks
   L.off_a0 = 0;
   L.off_res = kA0Bytes;
   L.off_pol = (L.off_res + L.res_bytes + 1023u) / 1024u * 1024u;
@@ -145,6 +145,7 @@ constexpr Layout make_layout(int cg, int nc, int var) {
   // LayerNorm variant: per-column correction vectors of layer 2 (u2, c2: 2 x 64*nc floats) + per-row statistics
   L.off_ln = (L.off_pol + L.pol_bytes + 1023u) / 1024u * 1024u;
   L.ln_bytes = ln ? 2u * 64u * nc * 4u + 2u * kOutN * 4u + kLnStatsBytes : 0u;
+  if (rew) L.ln_bytes = (64u * nc2 + kOutN) * 4u;   // learned-reward model: biases of both heads' hidden layers, then of the outputs
   L.off_ring = (L.off_ln + L.ln_bytes + 1023u) / 1024u * 1024u;
   L.stage_bytes = L.kbs * L.blk_h;
   L.nst = (int)((kSmemLimit - kMiscBytes - L.off_ring) / L.stage_bytes);
@@ -179,6 +180,9 @@ struct TmArgs {
   // LayerNorm variant (dynamics.py:68-69): z = rho * acc - rho * mu * u + c per column, rho / mu per row
   const float* lnvec;            // [u2 (64*nc)][c2 (64*nc)] correction vectors of layer 2, [u3 (32)][c3 (32)] of the output layer
   float ln_inv_n, ln_eps;        // 1 / hidden_size, variance epsilon
+  // learned-reward model: lnvec = [b2 of the delta head (64 * nc)][b2 of the reward head (64 * nc)][b3: 20 deltas, reward, 0...]
+  int act_tanh;                  // hidden activation: 1 = tanh (dynamics.py:162), 0 = ReLU
+  float mean_reward, std_reward, gamma;
 };
 // pipeline trace of CTA (0,0), steps 0..3: [2 per L1 pair][2 per L2 chunk][2 per L3 chunk][4 per epilogue chunk][final 8][2 per stage]
 constexpr int kTraceSteps = 4, kTrL1 = 0, kTrL2 = 8, kTrL3 = 24, kTrEpi = 40, kTrFinal = 104, kTrProd = 112, kTraceSlots = kTrProd + 2 * 64;
@@ -208,8 +212,8 @@ __host__ __device__ inline size_t sw128_offset(int n, int kk) {
 struct TmHostPlan {
   std::vector<uint16_t> pol;
   size_t res_total = 0, stream_total = 0, lnvec_floats = 0;     // bytes / bytes / floats of the device images
-  bool layer_norm = false;
-  int cg = 1, s_pad = 0, nc = 0, hidden = 0;
+  bool layer_norm = false, reward = false;
+  int cg = 1, s_pad = 0, nc = 0, nc2 = 0, hidden = 0;
   bool with_policy = false;
   int np1 = 0, np2 = 0;
   float bp1[kPolMaxHidden] = {}, bp2[kPolMaxHidden] = {}, bp3[kMaxAct] = {};
@@ -220,7 +224,6 @@ inline bool tm_supported(const bcmpc_config& c, std::string* why) {
   if (c.obs_dim != kD || c.act_dim != kA) { *why = "bf16 fast path is specialised for obs_dim=20, act_dim=6 (HalfCheetah)"; return false; }
   if (c.n_hidden != 2) { *why = "bf16 fast path supports n_hidden == 2 this round"; return false; }
   if (c.hidden_size < 1 || c.hidden_size > 510) { *why = "bf16 fast path supports hidden_size <= 510 this round (TMEM holds the 512-wide padded activations)"; return false; }
-  if (c.activation != BCMPC_ACT_RELU) { *why = "bf16 fast path supports relu only"; return false; }
   if (c.first_proposal != 0 || c.proposal == BCMPC_PROP_POLICY_MEAN) { *why = "bf16 fast path: the tree-search planner (first_proposal, POLICY_MEAN) runs in BCMPC_PREC_FP32_VERIFY only"; return false; }
   return true;
 }
@@ -285,22 +288,26 @@ inline void tm_build_policy(const int* sizes, const float* const* W, const float
 // the new weights come from the host (bcmpc_set_dynamics) or are already device-resident (bcmpc_set_dynamics_device).
 inline void tm_geometry(int S, int cg, int var, TmHostPlan* out) {
   TmHostPlan& P = *out;
-  const bool ln = var == kVarLayerNorm;
+  const bool ln = (var & kVarLayerNorm) != 0, rew = (var & kVarReward) != 0;
   P.cg = cg;
   P.hidden = S;
   P.layer_norm = ln;
-  P.s_pad = ((ln ? S : S + 2) + 63) / 64 * 64;
+  P.reward = rew;
+  P.s_pad = (((ln || rew) ? S : S + 2) + 63) / 64 * 64;           // no hidden "ones" units with LayerNorm / the reward model
   P.nc = P.s_pad / 64;
+  P.nc2 = hidden2_chunks(P.nc, var);
   P.lay = make_layout(cg, P.nc, var);
   P.res_total = (size_t)cg * P.lay.res_bytes;
-  P.stream_total = (size_t)P.nc * P.lay.nstg * cg * P.lay.stage_bytes;
+  P.stream_total = (size_t)P.nc2 * P.lay.nstg * cg * P.lay.stage_bytes;
   P.lnvec_floats = ln ? (size_t)2 * P.s_pad + 2 * kOutN : 0;      // [u2][c2][u3][c3]
+  if (rew) P.lnvec_floats = (size_t)64 * P.nc2 + kOutN;           // [b2 delta head][b2 reward head][b3]
 }
 
 struct PackArgs {
   const float *W1, *b1, *W2, *b2, *W3, *b3;     // device, row strides ld1..ld3
   const float *g1, *be1, *g2, *be2;             // LayerNorm gamma / beta of hidden layers 1, 2 (nullptr = off)
-  int ld1, ld2, ld3;
+  const float *Wr1, *br1, *Wr2, *br2;           // reward head [S,S], [S,1] (nullptr = off; learned-reward model)
+  int ld1, ld2, ld3, ldr1, ldr2;
   int S, s_pad, nc, cg, kbs, nstg;
   uint32_t blk_h, blk_o, w1_bytes, res_bytes, stage_bytes;
   uint16_t *res, *stream;
@@ -312,13 +319,18 @@ __device__ __forceinline__ uint16_t pk_lo(float v) { return f32_to_bf16(__fsub_r
 // effective (bias-augmented, zero-padded) kernels
 __device__ __forceinline__ uint16_t pk_w1(const PackArgs& a, int k, int n) {        // k < 64 (input column), n < s_pad (hidden unit)
   constexpr int in_dim = kD + kA;
-  const bool ln = a.g1 != nullptr;
+  const bool ln = a.g1 != nullptr || a.Wr1 != nullptr;      // variants without hidden "ones" units
   if (n < a.S) return k < in_dim ? f32_to_bf16(a.W1[(size_t)k * a.ld1 + n]) : k == in_dim ? pk_hi(a.b1[n]) : k == in_dim + 1 ? pk_lo(a.b1[n]) : 0;
   if (!ln && (n == a.S || n == a.S + 1)) return k == in_dim ? (uint16_t)0x3F80 : 0;   // the hidden "ones" units: relu(1 * 1) = 1
   return 0;
 }
 __device__ __forceinline__ uint16_t pk_w2(const PackArgs& a, int k, int n) {
   const int S = a.S;
+  if (a.Wr1) {        // columns [0, s_pad): state-delta head, [s_pad, 2 s_pad): reward head; biases are added in the epilogue
+    const int nn = n % a.s_pad;
+    if (nn >= S || k >= S) return 0;
+    return f32_to_bf16(n < a.s_pad ? a.W2[(size_t)k * a.ld2 + nn] : a.Wr1[(size_t)k * a.ldr1 + nn]);
+  }
   if (a.g1) return (n < S && k < S) ? f32_to_bf16(__fmul_rn(a.g1[k], a.W2[(size_t)k * a.ld2 + n])) : 0;
   if (n < S) return k < S ? f32_to_bf16(a.W2[(size_t)k * a.ld2 + n]) : k == S ? pk_hi(a.b2[n]) : k == S + 1 ? pk_lo(a.b2[n]) : 0;
   if (n == S || n == S + 1) return k == S ? (uint16_t)0x3F80 : 0;
@@ -326,6 +338,12 @@ __device__ __forceinline__ uint16_t pk_w2(const PackArgs& a, int k, int n) {
 }
 __device__ __forceinline__ uint16_t pk_w3(const PackArgs& a, int k, int n) {        // n < 32 (output column)
   const int S = a.S;
+  if (a.Wr1) {        // rows [0, s_pad): hidden units of the delta head -> columns 0..19; [s_pad, 2 s_pad): reward head -> column 20
+    const int kk = k % a.s_pad;
+    if (kk >= S) return 0;
+    if (k < a.s_pad) return n < kD ? f32_to_bf16(a.W3[(size_t)kk * a.ld3 + n]) : 0;
+    return n == kRewardCol ? f32_to_bf16(a.Wr2[(size_t)kk * a.ldr2]) : 0;
+  }
   if (n >= kD) return 0;
   if (a.g1) return k < S ? f32_to_bf16(__fmul_rn(a.g2[k], a.W3[(size_t)k * a.ld3 + n])) : 0;
   return k < S ? f32_to_bf16(a.W3[(size_t)k * a.ld3 + n]) : k == S ? pk_hi(a.b3[n]) : k == S + 1 ? pk_lo(a.b3[n]) : 0;
@@ -336,7 +354,8 @@ __device__ __forceinline__ uint16_t pk_w3(const PackArgs& a, int k, int n) {    
 //   streamed image: one slot [CG][stage_bytes] per (chunk, stage), chunk-major = consumption order
 __global__ void pack_images_kernel(PackArgs a) {
   const int sp = a.s_pad, rows_h = kChunk / a.cg, rows_o = kOutN / a.cg;
-  const int n1 = 64 * sp, n3 = sp * kOutN, n2 = sp * sp;
+  const int sp2 = a.Wr1 ? 2 * sp : sp;            // width of hidden layer 2 (both heads)
+  const int n1 = 64 * sp, n3 = sp2 * kOutN, n2 = sp * sp2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n3 + n2; i += gridDim.x * blockDim.x) {
     if (i < n1) {
       const int k = i / sp, n = i % sp, c = n / kChunk, j = n % kChunk, r = j / rows_h, ii = j % rows_h;
@@ -345,7 +364,7 @@ __global__ void pack_images_kernel(PackArgs a) {
       const int e = i - n1, k = e / kOutN, n = e % kOutN, r = n / rows_o, ii = n % rows_o;
       a.res[((size_t)r * a.res_bytes + a.w1_bytes + (size_t)(k / 64) * a.blk_o + sw128_offset(ii, k % 64)) / 2] = pk_w3(a, k, n);
     } else {
-      const int e = i - n1 - n3, k = e / sp, n = e % sp, c = n / kChunk, j = n % kChunk, r = j / rows_h, ii = j % rows_h;
+      const int e = i - n1 - n3, k = e / sp2, n = e % sp2, c = n / kChunk, j = n % kChunk, r = j / rows_h, ii = j % rows_h;
       const int kb = k / 64, stg = kb / a.kbs, t = kb % a.kbs;
       a.stream[((size_t)(c * a.nstg + stg) * a.cg * a.stage_bytes + (size_t)r * a.stage_bytes + (size_t)t * a.blk_h +
                 sw128_offset(ii, k % 64)) / 2] = pk_w2(a, k, n);
@@ -378,10 +397,23 @@ __global__ void pack_ln_kernel(PackArgs a) {
   }
 }
 
+// learned-reward model: lnvec = [b2 (s_pad)][br1 (s_pad)][b3 (20), br2, 0 ...]
+__global__ void pack_reward_bias_kernel(PackArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, sp = a.s_pad;
+  if (i >= 2 * sp + kOutN) return;
+  float v = 0.f;
+  if (i < sp) v = i < a.S ? a.b2[i] : 0.f;
+  else if (i < 2 * sp) v = i - sp < a.S ? a.br1[i - sp] : 0.f;
+  else { const int d = i - 2 * sp; v = d < kD ? a.b3[d] : d == kRewardCol ? a.br2[0] : 0.f; }
+  a.lnvec[i] = v;
+}
+
 inline cudaError_t tm_pack(const PackArgs& a, cudaStream_t st) {
-  const int total = 64 * a.s_pad + a.s_pad * kOutN + a.s_pad * a.s_pad;
+  const int sp2 = a.Wr1 ? 2 * a.s_pad : a.s_pad;
+  const int total = 64 * a.s_pad + sp2 * kOutN + a.s_pad * sp2;
   pack_images_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
   if (a.g1) pack_ln_kernel<<<(a.s_pad + kOutN + 7) / 8, 256, 0, st>>>(a);
+  if (a.Wr1) pack_reward_bias_kernel<<<(2 * a.s_pad + kOutN + 255) / 256, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -473,11 +505,12 @@ __device__ __forceinline__ void build_policy_input(const TmArgs& a, uint32_t a0_
 // complete; a single elected lane polling while the others park at the reconvergence barrier costs > 1000).
 template <int CG, int NC, int VAR>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
-  constexpr bool POL = VAR == kVarPolicy, LN = VAR == kVarLayerNorm;
+  constexpr bool POL = (VAR & kVarPolicy) != 0, LN = (VAR & kVarLayerNorm) != 0, REW = (VAR & kVarReward) != 0;
+  constexpr int NC2 = hidden2_chunks(NC, VAR);                // hidden-2 chunks (both heads of the learned-reward model)
+  static_assert(NC <= kMaxChunks1 && NC2 <= kMaxChunks2 && !(LN && REW), "unsupported kernel variant");
   constexpr Layout L = Lay<CG, NC, VAR>::value;
   constexpr int kNstg = L.nstg;                               // weight stages per layer-2 chunk
-  constexpr int kNumStream = NC * kNstg;                      // weight stages per step
-  constexpr int kStagesPerStepR[2] = {((NC + 1) / 2) * kNstg, (NC / 2) * kNstg};   // ... per sub-ring (even / odd chunks)
+  constexpr int kStagesPerStepR[2] = {((NC2 + 1) / 2) * kNstg, (NC2 / 2) * kNstg};   // weight stages per step and sub-ring (even / odd chunks)
   constexpr uint32_t kIdescH = ptx::umma_idesc_bf16(kRows * CG, kChunk), kIdescO = ptx::umma_idesc_bf16(kRows * CG, kOutN);
   static_assert(L.nst_r[0] >= 1 && L.nst_r[1] >= 1, "weight ring too small");
 
@@ -505,17 +538,21 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     ptx::mbar_init(misc + kOffResFull, (CG == 2 && leader) ? 2 : 1);
     ptx::mbar_init(ev + 8u * kEvA0Ready, 4 * CG);
     ptx::mbar_init(ev + 8u * kEvD3Full, 1);
-    for (int i = 0; i < 8; ++i) {
-      ptx::mbar_init(ev + 8u * (kEvA1Ready + i), 4 * CG);
+    for (int i = 0; i < kMaxChunks1; ++i) ptx::mbar_init(ev + 8u * (kEvA1Ready + i), 4 * CG);
+    for (int i = 0; i < kMaxChunks2; ++i) {
       ptx::mbar_init(ev + 8u * (kEvA2Ready + i), 4 * CG);
       ptx::mbar_init(ev + 8u * (kEvA2Empty + i), 1);
     }
-    for (int i = 0; i < kMaxChunks; ++i) { ptx::mbar_init(ev + 8u * (kEvDFull + i), 1); ptx::mbar_init(ev + 8u * (kEvDEmpty + i), 4 * CG); }
+    for (int i = 0; i < kMaxChunks1 + kMaxChunks2; ++i) { ptx::mbar_init(ev + 8u * (kEvDFull + i), 1); ptx::mbar_init(ev + 8u * (kEvDEmpty + i), 4 * CG); }
     ptx::mbar_init(ev + 8u * kEvAp0Ready, 4 * CG);
     for (int i = 0; i < 4; ++i) ptx::mbar_init(ev + 8u * (kEvPdFull + i), 1);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(ev + 8u * (kEvAp1Ready + i), 4 * CG); ptx::mbar_init(ev + 8u * (kEvAp2Ready + i), 4 * CG); }
     ptx::mbar_init(ev + 8u * kEvPolFull, 1);
     ptx::fence_mbar_init();
+  }
+  if constexpr (REW) {      // biases of the two heads: [b2 (64 * NC2)][b3 (32)]
+    float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
+    for (int i = tid; i < 64 * NC2 + kOutN; i += kThreads) s_vec[i] = a.lnvec[i];
   }
   if constexpr (LN) {
     float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
@@ -530,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   // The allocation is the whole TMEM (512 columns), so it starts at lane 0 / column 0; using the literal keeps every
   // TMEM address a compile-time value.
   if (*s_tmem != 0u) { if (tid == 0) printf("bcmpc: unexpected TMEM base 0x%x\n", *s_tmem); __trap(); }
-  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool tracing = !REW && a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;   // (the trace slots are laid out for NC2 == NC)
   const uint32_t hc = a.hint_chain;
 
   // Warps 0-3 run their loops warp-uniformly and elect one lane only for the instructions themselves: every
@@ -554,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     for (int h = 0; h < H; ++h) {
       const uint8_t* src = a.stream + (size_t)rank * L.stage_bytes;
       const bool trp = tracing && h < kTraceSteps;
-      for (int c = 0; c < NC; ++c) {
+      for (int c = 0; c < NC2; ++c) {
         const int r = c & 1;                     // sub-ring: even chunks feed issuer warp 1, odd chunks issuer warp 3
         for (int j = 0; j < kNstg; ++j) {
           const int i = c * kNstg + j;
@@ -667,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           __syncwarp();
         }
         // ---- layer 2: this issuer's chunks, one MMA group per weight stage ----
-        for (uint32_t c = (uint32_t)mine; c < (uint32_t)NC; c += 2) {
+        for (uint32_t c = (uint32_t)mine; c < (uint32_t)NC2; c += 2) {
           const uint32_t gs0 = uh * stages_per_step + (c >> 1) * (uint32_t)kNstg;
           // the chunk's first weight stage landed long ago: take that wait before the ones on the dependency chain
           ptx::mbar_wait(misc + kOffWFull + 8u * (first_mine + gs0 % nst_mine), (gs0 / nst_mine) & 1u);
@@ -716,7 +753,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       __syncwarp();
       uint32_t stage[2] = {0, 0}, phase[2] = {0, 0};
       for (int h = 0; h < H; ++h) {
-        for (int c = 0; c < NC; ++c) {
+        for (int c = 0; c < NC2; ++c) {
           const int r = c & 1;
           for (int j = 0; j < kNstg; ++j) {
             const uint32_t st = (uint32_t)L.first_r[r] + stage[r];
@@ -736,14 +773,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       for (int h = 0; h < H; ++h) {
         const uint32_t uh = (uint32_t)h;
         const bool trw = tracing && h < kTraceSteps;
-        for (uint32_t c = 0; c < (uint32_t)NC; ++c) {
+        for (uint32_t c = 0; c < (uint32_t)NC2; ++c) {
           ptx::mbar_wait(ev + 8u * (kEvA2Ready + c), uh & 1u, hc);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c] = clock64();
             uint32_t acol;
             if constexpr (a2_buffers(NC) == 1) {
-              acol = c == (uint32_t)NC - 1 ? (uint32_t)a2_col(NC - 1, NC) : (uint32_t)kColA2;
+              acol = c == (uint32_t)NC2 - 1 ? (uint32_t)a2_col(NC2 - 1, NC, NC2) : (uint32_t)kColA2;
             } else {
               const uint32_t bsel = c % (uint32_t)a2_buffers(NC);
               acol = bsel == 0 ? (uint32_t)kColA2 : (uint32_t)(kColA1 + 32 * NC) + 32u * (bsel - 1u);
@@ -751,7 +788,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               ptx::umma_ts<CG>(kColD3, acol + ks * 8, w3desc + (uint64_t)(c * (L.blk_o >> 4) + 2u * ks), kIdescO, (c == 0 && ks == 0) ? 0u : 1u);
-            if (c == (uint32_t)NC - 1) ptx::umma_commit_cg<CG>(ev + 8u * kEvD3Full);
+            if (c == (uint32_t)NC2 - 1) ptx::umma_commit_cg<CG>(ev + 8u * kEvD3Full);
             else ptx::umma_commit_cg<CG>(ev + 8u * (kEvA2Empty + c));
             if (trw) a.trace[h * kTraceSlots + kTrL3 + 2 * c + 1] = clock64();
           }
@@ -782,6 +819,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       if (lane == 0) arrive_leader(id);
     };
     float s[kD], z[kA], act[kA], act0[kA], cost = 0.f;
+    [[maybe_unused]] float disc = 1.f;          // gamma ** h of the learned-reward objective
     if (is_final) {
 #pragma unroll
       for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)(p.per_row_states ? kc : b) * kD + d];
@@ -957,6 +995,48 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (lane == 0) arrive_leader(ready_id);
         if (trh) a.trace[h * kTraceSlots + kTrEpi + 4 * e + 3] = clock64();
       };
+      // learned-reward model: the hidden "ones" units that carry the biases of layers 2 / 3 through a ReLU do not
+      // survive a tanh, so those biases are added here (layer 1 keeps its bias in the GEMM: its ones are INPUT columns);
+      // activation = tanh (tanh.approx.bf16x2 on the rounded pair, as in the proposal network) or ReLU
+      [[maybe_unused]] const float* s_b2 = reinterpret_cast<const float*>(smem + L.off_ln);
+      [[maybe_unused]] auto chunk_bias = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, int wait_a2, const float* bias) {
+        uint32_t v0[32], v1[32], w0[16], w1[16];
+        ptx::tmem_ld32(lane_off + col, v0);
+        ptx::tmem_ld32(lane_off + col + 32u, v1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(kEvDEmpty + e);
+        const float4* b4 = reinterpret_cast<const float4*>(bias);
+        auto act2 = [&](float x, float y) {
+          if (a.act_tanh) return ptx::tanh_bf16x2(pack_bf16(x, y));
+          return pack_relu_bf16(x, y);
+        };
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bb = b4[i];
+          w0[2 * i] = act2(__uint_as_float(v0[4 * i]) + bb.x, __uint_as_float(v0[4 * i + 1]) + bb.y);
+          w0[2 * i + 1] = act2(__uint_as_float(v0[4 * i + 2]) + bb.z, __uint_as_float(v0[4 * i + 3]) + bb.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bb = b4[8 + i];
+          w1[2 * i] = act2(__uint_as_float(v1[4 * i]) + bb.x, __uint_as_float(v1[4 * i + 1]) + bb.y);
+          w1[2 * i + 1] = act2(__uint_as_float(v1[4 * i + 2]) + bb.z, __uint_as_float(v1[4 * i + 3]) + bb.w);
+        }
+        if (wait_a2 >= 0) {
+          ptx::mbar_wait(ev + 8u * (kEvA2Empty + wait_a2), uh & 1u, hc);
+          ptx::tc_fence_after();
+        }
+        ptx::tmem_st16(lane_off + dst, w0);
+        ptx::tmem_st16(lane_off + dst + 16u, w1);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(ready_id);
+      };
       // layer 1: the groups take alternate PAIRS of chunks (the pairs the issuer commits together): one combined wait
       for (uint32_t c0 = 2u * (uint32_t)g; c0 < (uint32_t)NC; c0 += 4) {
         const bool two = c0 + 1 < (uint32_t)NC;
@@ -968,6 +1048,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           const uint32_t bsel = c % (uint32_t)kNumDBufL1;
           const uint32_t col = bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2;
           if constexpr (LN) chunk_ln(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, 0, c);
+          else if constexpr (REW) chunk_bias(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, nullptr);
           else chunk(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1);
         }
       }
@@ -977,7 +1058,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       // layer 2: alternate chunks
       bool first_l2 = true;
 #pragma unroll 1
-      for (uint32_t c = (uint32_t)g; c < (uint32_t)NC; c += 2) {
+      for (uint32_t c = (uint32_t)g; c < (uint32_t)NC2; c += 2) {
         ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u, hc);
         ptx::tc_fence_after();
         if constexpr (LN) {
@@ -990,8 +1071,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         uint32_t dst;
         int wait_a2;
         if constexpr (a2_buffers(NC) == 1) {
-          const bool last = NC >= 3 && c == (uint32_t)NC - 1;
-          dst = last ? (uint32_t)a2_col(NC - 1, NC) : (uint32_t)kColA2;
+          const bool last = NC2 >= 3 && c == (uint32_t)NC2 - 1;
+          dst = last ? (uint32_t)a2_col(NC2 - 1, NC, NC2) : (uint32_t)kColA2;
           wait_a2 = (c == 0 || last) ? -1 : (int)c - 1;
         } else {
           const uint32_t bsel = c % (uint32_t)a2_buffers(NC);
@@ -999,6 +1080,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           wait_a2 = c >= (uint32_t)a2_buffers(NC) ? (int)c - a2_buffers(NC) : -1;
         }
         if constexpr (LN) chunk_ln((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, 1, c);
+        else if constexpr (REW) chunk_bias((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, s_b2 + 64u * c);
         else chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2);
       }
 
@@ -1017,12 +1099,24 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           for (int d = 0; d < kD; ++d) v[d] = __float_as_uint(fmaf(rho, __uint_as_float(v[d]), fmaf(-rmu, s_u3[d], s_c3[d])));
           ln_sum = 0.f; ln_sq = 0.f;
         }
+        if constexpr (REW) {
+          const float* s_b3 = s_b2 + 64 * NC2;
+#pragma unroll
+          for (int d = 0; d <= kRewardCol; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) + s_b3[d]);
+        }
 #pragma unroll
         for (int d = 0; d < kD; ++d) delta[d] = fmaf(__uint_as_float(v[d]), a.std_delta[d], a.mean_delta[d]);   // dynamics.py:113
-        if (s[5] >= 0.2f) cost += 10.f;                                      // cost_functions.py:16-26 (pre-step state)
-        if (s[6] >= 0.f) cost += 10.f;
-        if (s[7] >= 0.f) cost += 10.f;
-        cost -= delta[17] * 100.f;                                           // cost_functions.py:28 (/ 0.01)
+        if constexpr (REW) {
+          // controllers.py:137-139 / :340-345: reward = y * std_reward + mean_reward (dynamics.py:236), times gamma ** h;
+          // the planner minimises, so the running "cost" is minus the discounted reward sum
+          cost -= fmaf(__uint_as_float(v[kRewardCol]), a.std_reward, a.mean_reward) * disc;
+          disc *= a.gamma;
+        } else {
+          if (s[5] >= 0.2f) cost += 10.f;                                    // cost_functions.py:16-26 (pre-step state)
+          if (s[6] >= 0.f) cost += 10.f;
+          if (s[7] >= 0.f) cost += 10.f;
+          cost -= delta[17] * 100.f;                                         // cost_functions.py:28 (/ 0.01)
+        }
 #pragma unroll
         for (int d = 0; d < kD; ++d) s[d] += delta[d];                       // dynamics.py:116
         if (p.states_out && valid)
@@ -1104,7 +1198,19 @@ inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t
   }
   return cudaErrorInvalidValue;
 }
+// learned-reward variants: instantiated for 4 and 8 hidden chunks (hidden sizes 193..256 and 449..512; the reference
+// hard-codes 500, dynamics.py:162)
+template <int CG, int VAR>
+inline cudaError_t tm_launch_rew(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  if (nc == 4) return tm_launch_t<CG, 4, VAR>(a, grid, st);
+  // (a single CTA cannot hold the resident images of the 2 x 512 heads AND of a proposal network: tm_prepare reports it)
+  if constexpr (Lay<CG, 8, VAR>::value.nst >= 2) { if (nc == 8) return tm_launch_t<CG, 8, VAR>(a, grid, st); }
+  return cudaErrorInvalidValue;
+}
+inline bool tm_reward_width_supported(int nc) { return nc == 4 || nc == 8; }
 inline cudaError_t tm_launch(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  if (var == kVarReward) return cg == 2 ? tm_launch_rew<2, kVarReward>(nc, a, grid, st) : tm_launch_rew<1, kVarReward>(nc, a, grid, st);
+  if (var == kVarRewardPolicy) return cg == 2 ? tm_launch_rew<2, kVarRewardPolicy>(nc, a, grid, st) : tm_launch_rew<1, kVarRewardPolicy>(nc, a, grid, st);
   if (var == kVarPolicy) return cg == 2 ? tm_launch_cg<2, kVarPolicy>(nc, a, grid, st) : tm_launch_cg<1, kVarPolicy>(nc, a, grid, st);
   if (var == kVarLayerNorm) return cg == 2 ? tm_launch_cg<2, kVarLayerNorm>(nc, a, grid, st) : tm_launch_cg<1, kVarLayerNorm>(nc, a, grid, st);
   return cg == 2 ? tm_launch_cg<2, kVarUniform>(nc, a, grid, st) : tm_launch_cg<1, kVarUniform>(nc, a, grid, st);

@@ -155,6 +155,22 @@ def extras():
         "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
         "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
     pl.close()
+    # learned-reward planner (NNDynamicsRewardModel + MPCcontrollerReward: what run.sh launches), tanh, 26-500-{500-20, 500-1}
+    B, K, H = 32, 4096, 20
+    rrng, rnorm, rw, rrw, _ = O.synthetic_reward_problem(3, 500)
+    pl = Planner(20, 6, 2, 500, "tanh", num_paths=K, horizon=H, max_states=B, precision="bf16")
+    pl.set_dynamics(rw)
+    pl.set_normalization(rnorm["mean_obs"], rnorm["std_obs"], rnorm["mean_action"], rnorm["std_action"], rnorm["mean_deltas"], rnorm["std_deltas"])
+    pl.set_reward_head(rrw, rnorm["mean_reward"], rnorm["std_reward"], 0.99)
+    states = rnorm["mean_obs"] + rnorm["std_obs"] * np.random.default_rng(2).standard_normal((B, 20))
+    pl.enable_timing(True)
+    dt = time_plans(pl, states, 10)
+    k_ms = pl.last_kernel_ms()
+    flop = 2 * (26 * 500 + 2 * 500 * 500 + 500 * 20 + 500)
+    out["learned_reward_tanh_K4096_H20_bf16_x32states"] = {
+        "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
+        "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
+    pl.close()
     # weight refresh after dyn_model.fit (train_mpc_ppo.py:279): host arrays vs device-resident torch parameters
     import torch
     pl = make(4096, 15, "bf16")

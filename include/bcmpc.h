@@ -128,8 +128,10 @@ int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float
  * with the dynamics activation, W[1] [hidden,1] linear.  With a reward head the planner maximises the sum of
  * gamma^i * (y_r * std_reward + mean_reward) (MPCcontrollerReward.get_action, controllers.py:121-158; gamma = 1 gives
  * MPCcontrollerPolicyNetReward, :319-363): bcmpc_record.cost is MINUS that sum, index / action its argmax (first index
- * on ties, like np.argmax).  W == NULL switches back to cheetah_cost_fn.  Call after bcmpc_set_dynamics.
- * Verification mode only (BCMPC_ERR_UNSUPPORTED with BCMPC_PREC_BF16_FAST). */
+ * on ties, like np.argmax).  W == NULL switches back to cheetah_cost_fn.  Call after bcmpc_set_dynamics; the head
+ * persists across later bcmpc_set_dynamics calls.  BCMPC_PREC_BF16_FAST runs it on the tensor cores for the
+ * reference's shape (tanh, hidden size 449..512 or 193..256: both heads form one 2 x hidden wide second layer), with
+ * uniform or policy-guided proposals; other shapes fail with BCMPC_ERR_UNSUPPORTED there and run in verification mode. */
 int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward,
                           double std_reward, double gamma);
 

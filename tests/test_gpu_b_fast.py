@@ -86,6 +86,54 @@ def test_policy_guided_fast_mode_tracks_oracle(proposal, bc, K):
     assert not np.array_equal(r1["action"], r3["action"])
 
 
+@pytest.mark.parametrize("S,proposal,K,gamma", [(500, "uniform", 4096, 0.95), (500, "policy_mix", 1000, 1.0), (256, "uniform", 1000, 1.0)])
+def test_learned_reward_fast_mode_tracks_oracle(S, proposal, K, gamma):
+    """NNDynamicsRewardModel + MPCcontrollerReward / MPCcontrollerPolicyNetReward (dynamics.py:121-238,
+    controllers.py:90-158,289-363) on the tcgen05 path: shared tanh layer, both 500-wide tanh heads as ONE 1024-wide
+    second layer, block-structured output layer (20 deltas + reward), discounted-reward objective in the epilogue."""
+    from bc_mpc_b200 import Planner
+    H = 10
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(33, S)
+    dyn = O.OracleRewardDynamics(weights, rweights, norm)
+    pl = Planner(20, 6, 2, S, "tanh", num_paths=K, horizon=H, precision="bf16", proposal=proposal, explore=0.4)
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    if proposal == "uniform":
+        with pytest.raises(RuntimeError, match="tanh dynamics"):      # a plain tanh NNDynamicsModel has no fast path
+            pl.plan(state, seed=1)
+    if os.environ.get("BCMPC_TC_CG") == "1" and proposal != "uniform" and S > 256:
+        # single-CTA debug mode: one CTA cannot keep the two 512-wide heads AND a proposal network resident
+        with pytest.raises(RuntimeError, match="weight ring"):
+            pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], gamma)
+        return
+    pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], gamma)
+    pol = None
+    if proposal != "uniform":
+        pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
+        pol = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
+        pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+    mpc = O.OracleMPC(dyn, H, K, proposal=proposal, policy=pol, explore=0.4, learned_reward=True, gamma=gamma)
+    inj = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, inj, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, inj)
+    e = _norm_err(so, dbg["states"], norm)
+    one = np.abs(_norm_err(so[1], dbg["states"][1], norm)).max()
+    cstd = dbg["costs"].std()
+    rec = pl.plan(state, inj=inj)[0]
+    regret = (dbg["costs"][rec["index"]] - dbg["costs"].min()) / cstd
+    print(dict(S=S, proposal=proposal, one_step_err_in_delta_std=float(one), max_state_err_in_delta_std=float(np.abs(e).max()),
+               cost_corr=float(np.corrcoef(co, dbg["costs"])[0, 1]), max_cost_err_in_std=float(np.abs(co - dbg["costs"]).max() / cstd),
+               argmin_match=bool(rec["index"] == dbg["argmin"]), regret_in_cost_std=float(regret)))
+    assert one < 0.05 and np.abs(e).max() < 0.3
+    assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
+    assert rec["index"] == int(np.argmin(co)) and np.allclose(rec["action"][:6], ao[0, rec["index"]])
+    assert regret < 0.5
+    r1, r2 = pl.plan(state, seed=5)[0], pl.plan(state, seed=5)[0]
+    assert r1["index"] == r2["index"] and r1["cost"] == r2["cost"]
+    pl.set_dynamics(weights)            # a weight refresh keeps the reward head
+    assert pl.plan(state, seed=5)[0]["cost"] == r1["cost"]
+
+
 @pytest.mark.parametrize("S", [500, 256, 64])
 def test_layer_norm_fast_mode_tracks_oracle(S):
     """FLAGS.LAYER_NORM dynamics (dynamics.py:68-69) on the tcgen05 path: un-normalised activations through the MMAs,
