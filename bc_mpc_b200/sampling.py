@@ -47,6 +47,52 @@ def sample_vectorized(envs, controller, horizon=1000):
     return paths
 
 
+def traj_segment_generator(pi, mpc_controller, mpc_ppo_controller, bc_data_buffer, env, mpc, ppo_mpc, horizon):
+    """utils.py:163-242: one PPO segment of `horizon` env steps.  Every step evaluates the policy (action + value) and,
+    when `mpc`, asks the planner for the action that is actually executed (mpc_ppo_controller if ppo_mpc)."""
+    return traj_segments_vectorized(pi, mpc_ppo_controller if ppo_mpc else mpc_controller, [env], mpc, horizon,
+                                    batched=False)[0]
+
+
+def traj_segments_vectorized(pi, controller, envs, mpc, horizon, batched=True):
+    """len(envs) PPO segments in lock step; with `batched` the planner is called once per time step for all envs
+    (controller.get_actions), otherwise once per env (controller.get_action), exactly like utils.py:200-202."""
+    n = len(envs)
+    ac0 = [e.action_space.sample() for e in envs]           # :165 "not used, just so we have the datatype"
+    obs0 = [e.reset() for e in envs]
+    seg = [{"ob": np.array([obs0[i] for _ in range(horizon)]), "nxt_ob": np.array([obs0[i] for _ in range(horizon)]),
+            "rew": np.zeros(horizon, "float32"), "vpred": np.zeros(horizon, "float32"), "new": np.zeros(horizon, "int32"),
+            "ac": np.array([ac0[i] for _ in range(horizon)])} for i in range(n)]
+    for sg in seg:
+        sg["prevac"], sg["mpcac"] = sg["ac"].copy(), sg["ac"].copy()
+    ob, ac, new = list(obs0), list(ac0), [True] * n
+    ret = [0.0] * n
+    vpred = [0.0] * n
+    for t in range(horizon):
+        prevac = list(ac)
+        for i in range(n):
+            ac[i], vpred[i] = pi.act(ob[i], stochastic=True)                    # :196
+        if mpc:
+            if batched:
+                mpc_ac = list(controller.get_actions(np.asarray(ob, np.float64)))
+            else:
+                mpc_ac = [controller.get_action(ob[i]) for i in range(n)]          # :200-202
+        else:
+            mpc_ac = [np.array(a, copy=True) for a in ac]                          # :204
+        for i, env in enumerate(envs):
+            sg = seg[i]
+            sg["ob"][t], sg["vpred"][t], sg["new"][t] = ob[i], vpred[i], new[i]
+            sg["ac"][t], sg["prevac"][t], sg["mpcac"][t] = ac[i], prevac[i], mpc_ac[i]
+            ob[i], rew, _done, _ = env.step(mpc_ac[i])                             # :213 (episodes are not cut at `done`)
+            new[i] = False
+            sg["nxt_ob"][t], sg["rew"][t] = ob[i], rew
+            ret[i] += rew
+    for i, sg in enumerate(seg):
+        sg["nextvpred"] = vpred[i] * (1 - new[i])                               # :238
+        sg["ep_rets"], sg["ep_lens"] = [ret[i]], [horizon]                         # :226-227
+    return seg
+
+
 def path_cost(cost_fn, path):
     """utils.py:128-130."""
     return trajectory_cost_fn(cost_fn, path["observations"], path["actions"], path["next_observations"])

@@ -42,6 +42,11 @@ def measured_peaks():
     return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
 
 
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6550.0   # fallback: B200_PROFILING.md
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  The sampler runs from
     before the warm-up (nvidia-smi needs a few hundred ms to start); only rows that arrive inside a marked region count."""
@@ -170,6 +175,17 @@ def extras():
     out["learned_reward_tanh_K4096_H20_bf16_x32states"] = {
         "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
         "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
+    pl.close()
+    # stand-alone sampling stage (replay / debugging aid; the planner itself draws in registers): HBM-bound writes,
+    # 6 float64 per (state, step, path) = 48 B per transition
+    pl = make(1 << 17, 20, "bf16", B=4)
+    pl.enable_timing(True)
+    for i in range(3):
+        inj = pl.sample_injection(7 + i, n_states=4)
+    ms = pl.last_kernel_ms()
+    out["sampling_stage_standalone"] = {"bytes_written": int(inj.nbytes), "kernel_ms": ms, "GB_per_s": inj.nbytes / (ms * 1e-3) / 1e9,
+                                        "hbm_peak_GB_per_s": hbm_peak(), "transitions_per_s": inj.size / 6 / (ms * 1e-3)}
+    del inj
     pl.close()
     # weight refresh after dyn_model.fit (train_mpc_ppo.py:279): host arrays vs device-resident torch parameters
     import torch

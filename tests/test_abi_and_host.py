@@ -143,6 +143,57 @@ def test_samplers_host_logic():
         sum(float(np.sum(n) - np.sum(s)) for s, n in zip(vec[1]["observations"], vec[1]["next_observations"])))
 
 
+def test_segment_generators_host_logic():
+    """sampling.traj_segment_generator follows utils.py:163-242; the vectorised form makes one planner call per step."""
+    from bc_mpc_b200 import sampling
+
+    class Space:
+        def sample(self):
+            return np.zeros(2, np.float32)
+
+    class E:
+        action_space = Space()
+
+        def __init__(self, k):
+            self.k, self.t = k, 0
+
+        def reset(self):
+            self.t = 0
+            return np.full(3, float(self.k))
+
+        def step(self, a):
+            self.t += 1
+            return np.full(3, self.k + 0.5 * self.t) + float(np.sum(a)), 1.0 + self.k, False, {}
+
+    class Pi:
+        def act(self, ob, stochastic=True):
+            return np.array([ob[0], 1.0], np.float32), float(ob[0]) * 0.1
+
+    class Ctl:
+        single = batched = 0
+
+        def get_action(self, s):
+            self.single += 1
+            return np.array([0.25 * s[0], 0.0])
+
+        def get_actions(self, S):
+            self.batched += 1
+            return np.stack([0.25 * S[:, 0], np.zeros(len(S))], axis=1)
+
+    c = Ctl()
+    seg = sampling.traj_segment_generator(Pi(), c, None, None, E(2), True, False, 5)
+    assert c.single == 5 and seg["ob"].shape == (5, 3) and seg["new"].tolist() == [1, 0, 0, 0, 0]
+    assert np.allclose(seg["mpcac"][0], [0.5, 0.0]) and np.allclose(seg["ac"][0], [2.0, 1.0])
+    assert np.allclose(seg["prevac"][1], seg["ac"][0]) and np.array_equal(seg["nxt_ob"][:-1], seg["ob"][1:])
+    assert seg["ep_lens"] == [5] and seg["ep_rets"] == [15.0] and seg["nextvpred"] == pytest.approx(float(seg["ob"][4][0]) * 0.1)
+    segs = sampling.traj_segments_vectorized(Pi(), c, [E(k) for k in range(4)], True, 5)
+    assert c.batched == 5 and len(segs) == 4
+    for key in ("ob", "rew", "nxt_ob", "vpred", "new", "ac", "prevac", "mpcac"):
+        assert np.allclose(segs[2][key], seg[key])
+    nompc = sampling.traj_segment_generator(Pi(), c, None, None, E(1), False, False, 3)
+    assert np.allclose(nompc["mpcac"], nompc["ac"])
+
+
 def test_shard_bounds():
     from bc_mpc_b200.distributed import shard_bounds
     assert list(shard_bounds(1000, 4)) == [0, 250, 500, 750, 1000]
