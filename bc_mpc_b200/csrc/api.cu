@@ -13,6 +13,7 @@
 #include "aux_kernels.cuh"
 #include "common.cuh"
 #include "rollout_tmem.cuh"
+#include "weight_pack.cuh"
 #include "rollout_verify.cuh"
 
 using namespace bcmpc;
@@ -246,8 +247,7 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 int tm_variant(const bcmpc_handle* h) {
   const int pol = h->cfg.proposal != BCMPC_PROP_UNIFORM ? tmx::kVarPolicy : 0;
   if (h->rew.set) return tmx::kVarReward | pol;
-  if (pol) return tmx::kVarPolicy;
-  return h->ln_on ? tmx::kVarLayerNorm : tmx::kVarUniform;
+  return pol | (h->ln_on ? tmx::kVarLayerNorm : 0);
 }
 
 // (re)packs the fast-mode weight images on the device, on stream `st`, from the float32 copies in h->dyn / h->ln_bufs
@@ -261,8 +261,8 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   }
   const tmx::TmHostPlan& P = h->tmp;
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
-  if (P.reward && !tmx::tm_reward_width_supported(P.nc))
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the learned-reward model is built for hidden sizes 193..256 and 449..512 (got %d); use BCMPC_PREC_FP32_VERIFY", S);
+  if (!tmx::tm_width_supported(P.nc, tm_variant(h)))
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: this combination (learned-reward model, or LayerNorm with a proposal network) is built for hidden sizes 193..256 and 449..512 (got %d); use BCMPC_PREC_FP32_VERIFY", S);
   if (P.reward && h->ln_on)
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm together with the reward head runs in BCMPC_PREC_FP32_VERIFY only");
   if (P.lay.nst < 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "weight ring does not fit in shared memory");
@@ -320,7 +320,7 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.span[j] = h->norm.span[j];
   }
   const bool pol = p.proposal != BCMPC_PROP_UNIFORM;
-  const int var = P.reward ? (tmx::kVarReward | (pol ? tmx::kVarPolicy : 0)) : pol ? tmx::kVarPolicy : (P.layer_norm ? tmx::kVarLayerNorm : tmx::kVarUniform);
+  const int var = (P.reward ? tmx::kVarReward : 0) | (pol ? tmx::kVarPolicy : 0) | (P.layer_norm ? tmx::kVarLayerNorm : 0);
   a.proposal = p.proposal; a.inj_kind = p.inj_kind;
   if (h->cfg.activation == BCMPC_ACT_TANH && !P.reward)
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: tanh dynamics are built for the learned-reward model (bcmpc_set_reward_head); a plain tanh NNDynamicsModel runs in BCMPC_PREC_FP32_VERIFY");
@@ -330,7 +330,6 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.mean_reward = (float)h->mean_reward; a.std_reward = (float)h->std_reward; a.gamma = (float)h->gamma;
   }
   if (P.layer_norm) {
-    if (pol) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm dynamics with a proposal network run in BCMPC_PREC_FP32_VERIFY only");
     a.lnvec = h->d_lnvec;
     a.ln_inv_n = 1.0f / (float)h->cfg.hidden_size; a.ln_eps = h->ln_eps;
   }
@@ -534,8 +533,6 @@ int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float
   if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
-  if (fast && gamma && h->cfg.proposal != BCMPC_PROP_UNIFORM)
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm dynamics with a proposal network run in BCMPC_PREC_FP32_VERIFY only");
   if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
   if (gamma && n_hidden != h->cfg.n_hidden) return fail(h, BCMPC_ERR_INVALID, "n_hidden %d != %d", n_hidden, h->cfg.n_hidden);
   for (int l = 0; l < n_hidden && gamma; ++l)

@@ -36,7 +36,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity, uin
 }
 // Bounded wait: a protocol bug traps (kills the context) instead of hanging the GPU.  The slow path is out of line so
 // that the dozens of wait sites stay a few instructions each (the rollout kernel is instruction-cache sensitive).
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t hint) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t hint) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity, hint)) {
     if (clock64() - t0 > 6000000000LL) {
@@ -199,7 +199,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   return done != 0;
 }
 // wait on a local mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope)
-__device__ __noinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {

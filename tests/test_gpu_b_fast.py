@@ -161,6 +161,30 @@ def test_layer_norm_fast_mode_tracks_oracle(S):
     assert np.abs(_norm_err(so2, mpc.rollout(state, actions)[0], norm)).max() < 0.25
 
 
+@pytest.mark.parametrize("S,proposal", [(500, "policy_gaussian"), (500, "policy_mix"), (256, "policy_gaussian")])
+def test_layer_norm_with_policy_fast_mode_tracks_oracle(S, proposal):
+    """The reference's default run (train_mpc_ppo.py:52 LAYER_NORM=True with MPCcontrollerPolicyNet) on the tcgen05 path."""
+    K, H = 1000, 15
+    rng, norm, state, pl, mpc = make_pair(27, (S, S), K, H, precision="bf16", proposal=proposal)
+    ln = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(2)]
+    pl.set_layer_norm(ln)
+    mpc.dyn_model.layer_norm = ln
+    inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64) if proposal == "policy_gaussian" else f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, inj, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, inj)
+    e = _norm_err(so, dbg["states"], norm)
+    rec = pl.plan(state, inj=inj)[0]
+    regret = (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std()
+    print(dict(S=S, proposal=proposal, max_state_err_in_delta_std=float(np.abs(e).max()), max_action_err=float(np.abs(ao - dbg["actions"]).max()),
+               cost_corr=float(np.corrcoef(co, dbg["costs"])[0, 1]), argmin_match=bool(rec["index"] == dbg["argmin"]), regret_in_cost_std=float(regret)))
+    assert np.abs(ao[0] - dbg["actions"][0]).max() < 0.03
+    assert np.abs(e).max() < 0.6 and np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
+    assert rec["index"] == int(np.argmin(co)) and regret < 0.5
+    pl.set_layer_norm(None)             # back to the plain policy-guided kernel
+    so2, _, _ = pl.rollout_debug(state, inj)
+    assert np.abs(so2 - so).max() > 1e-3
+
+
 def test_fast_mode_sampling_batching_sharding_are_bit_consistent():
     import torch
     from bc_mpc_b200 import _lib as L
