@@ -40,6 +40,8 @@ struct bcmpc_handle {
   DeviceMlp dyn, pol, rew;       // rew: reward head of NNDynamicsRewardModel (bcmpc_set_reward_head)
   double mean_reward = 0.0, std_reward = 1.0, gamma = 1.0;
   std::vector<float*> ln_bufs;   // LayerNorm gamma/beta of the dynamics net (bcmpc_set_layer_norm)
+  float* rew_ln_buf = nullptr;   // [gamma (hidden)][beta (hidden)] of the reward head's hidden layer (bcmpc_set_reward_layer_norm)
+  bool rew_ln_on = false;
   NormArgs norm{};
   bool have_norm = false, have_bounds = false;
   // proposal network meta
@@ -246,8 +248,7 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 
 int tm_variant(const bcmpc_handle* h) {
   const int pol = h->cfg.proposal != BCMPC_PROP_UNIFORM ? tmx::kVarPolicy : 0;
-  if (h->rew.set) return tmx::kVarReward | pol;
-  return pol | (h->ln_on ? tmx::kVarLayerNorm : 0);
+  return pol | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
 }
 
 // (re)packs the fast-mode weight images on the device, on stream `st`, from the float32 copies in h->dyn / h->ln_bufs
@@ -263,8 +264,11 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
   if (!tmx::tm_width_supported(P.nc, tm_variant(h)))
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: this combination (learned-reward model, or LayerNorm with a proposal network) is built for hidden sizes 193..256 and 449..512 (got %d); use BCMPC_PREC_FP32_VERIFY", S);
-  if (P.reward && h->ln_on)
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: LayerNorm together with the reward head runs in BCMPC_PREC_FP32_VERIFY only");
+  if (P.reward && h->ln_on != h->rew_ln_on) {
+    // between bcmpc_set_layer_norm and bcmpc_set_reward_layer_norm: the images are packed once all three LayerNorms agree
+    h->tm_ready = false;
+    return BCMPC_OK;
+  }
   if (P.lay.nst < 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "weight ring does not fit in shared memory");
   auto ensure = [&](void** ptr, size_t* cap, size_t need) -> cudaError_t {
     if (need <= *cap) return cudaSuccess;
@@ -287,6 +291,7 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
     const MlpDesc& r = h->rew.desc;
     a.Wr1 = r.W[0]; a.br1 = r.b[0]; a.Wr2 = r.W[1]; a.br2 = r.b[1];
     a.ldr1 = r.out_pad[0]; a.ldr2 = r.out_pad[1];
+    if (P.layer_norm) { a.gr = r.ln_gamma[0]; a.ber = r.ln_beta[0]; }
   }
   a.S = S; a.s_pad = P.s_pad; a.nc = P.nc; a.cg = P.cg; a.kbs = P.lay.kbs; a.nstg = P.lay.nstg;
   a.blk_h = P.lay.blk_h; a.blk_o = P.lay.blk_o; a.w1_bytes = P.lay.w1_bytes; a.res_bytes = P.lay.res_bytes; a.stage_bytes = P.lay.stage_bytes;
@@ -300,7 +305,9 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
 }
 
 int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
-  if (!h->tm_ready) return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared (bcmpc_set_dynamics)");
+  if (!h->tm_ready)
+    return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared: set the dynamics weights, and with a reward head either all three LayerNorms "
+                                    "(bcmpc_set_layer_norm + bcmpc_set_reward_layer_norm) or none");
   const tmx::TmHostPlan& P = h->tmp;
   tmx::TmArgs a;
   memset(&a, 0, sizeof a);
@@ -326,6 +333,8 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: tanh dynamics are built for the learned-reward model (bcmpc_set_reward_head); a plain tanh NNDynamicsModel runs in BCMPC_PREC_FP32_VERIFY");
   if (P.reward) {
     a.lnvec = h->d_lnvec;
+    if (P.layer_norm && fabsf(h->rew.desc.ln_eps - h->ln_eps) > 0.f)
+      return fail(h, BCMPC_ERR_INVALID, "bf16 fast path: the three LayerNorms of the reward model must share one epsilon");
     a.act_tanh = h->cfg.activation == BCMPC_ACT_TANH ? 1 : 0;
     a.mean_reward = (float)h->mean_reward; a.std_reward = (float)h->std_reward; a.gamma = (float)h->gamma;
   }
@@ -479,6 +488,7 @@ int bcmpc_destroy(bcmpc_handle* h) {
   h->pol.release();
   h->rew.release();
   for (float* p : h->ln_bufs) cudaFree(p);
+  cudaFree(h->rew_ln_buf);
   cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
   cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_lnvec); cudaFree(h->d_trace);
   if (h->h_states) cudaFreeHost(h->h_states);
@@ -571,6 +581,7 @@ int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* c
   CK(h, cudaDeviceSynchronize());
   if (!W) {
     h->rew.release();
+    h->rew_ln_on = false;
     update_verify_geometry(h);
     if (fast) { int rc = tm_prepare(h, h->stream); if (rc) return rc; CK(h, cudaStreamSynchronize(h->stream)); }
     return BCMPC_OK;
@@ -582,11 +593,38 @@ int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* c
   const int sizes[3] = {h->cfg.hidden_size, h->cfg.hidden_size, 1};
   int rc = upload_mlp(h, h->rew, 2, sizes, W, b);
   if (rc) return rc;
+  h->rew_ln_on = false;        // (upload_mlp cleared the descriptor's LayerNorm pointers)
   h->mean_reward = mean_reward; h->std_reward = std_reward; h->gamma = gamma;
   update_verify_geometry(h);
   if (fast) {
     rc = tm_prepare(h, h->stream);
     if (rc) { h->rew.release(); update_verify_geometry(h); return rc; }
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
+  return BCMPC_OK;
+}
+
+int bcmpc_set_reward_layer_norm(bcmpc_handle* h, const float* gamma, const float* beta, float eps) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (!h->rew.set) return fail(h, BCMPC_ERR_STATE, "reward head not set (bcmpc_set_reward_head)");
+  if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
+  const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaDeviceSynchronize());
+  const size_t n = (size_t)h->cfg.hidden_size;
+  h->rew.desc.ln_gamma[0] = h->rew.desc.ln_beta[0] = nullptr;
+  h->rew_ln_on = gamma != nullptr;
+  if (gamma) {
+    if (!h->rew_ln_buf) CK(h, cudaMalloc(&h->rew_ln_buf, 2 * n * sizeof(float)));
+    CK(h, cudaMemcpy(h->rew_ln_buf, gamma, n * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->rew_ln_buf + n, beta, n * sizeof(float), cudaMemcpyHostToDevice));
+    h->rew.desc.ln_gamma[0] = h->rew_ln_buf;
+    h->rew.desc.ln_beta[0] = h->rew_ln_buf + n;
+    h->rew.desc.ln_eps = eps;
+  }
+  if (fast) {
+    int rc = tm_prepare(h, h->stream);
+    if (rc) return rc;
     CK(h, cudaStreamSynchronize(h->stream));
   }
   return BCMPC_OK;
@@ -845,8 +883,10 @@ int bcmpc_cheetah_cost(bcmpc_handle* h, const double* states, const double* next
   CKC(cudaMalloc(&d_o, sizeof(double) * n));
   CKC(cudaMemcpy(d_s, states, sizeof(double) * n * D, cudaMemcpyHostToDevice));
   CKC(cudaMemcpy(d_n, next_states, sizeof(double) * n * D, cudaMemcpyHostToDevice));
+  if (h->timing) { CKC(cudaEventRecord(h->ev0, h->stream)); }
   cheetah_cost_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_s, d_n, n, D, d_o);
   CKC(cudaGetLastError());
+  if (h->timing) { CKC(cudaEventRecord(h->ev1, h->stream)); h->ev_valid = true; }
   h->launches++;
   CKC(cudaStreamSynchronize(h->stream));
   CKC(cudaMemcpy(out, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost));

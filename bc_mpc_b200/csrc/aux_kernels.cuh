@@ -77,6 +77,13 @@ __global__ void sample_injection_kernel(NormArgs n, int A, int K, int H, int B, 
   const int b = (int)(i / ((int64_t)K * H));
   float v[kMaxAct];
   draw_injection(v, A, h == 0 ? kind0 : kind, seed, (uint32_t)(path_offset + k), (uint32_t)b, (uint32_t)h, n.low, n.span);
+  if (A == 6) {      // HalfCheetah: 48-byte rows, three 16-byte stores
+    double2* o = reinterpret_cast<double2*>(out + i * 6);
+    o[0] = make_double2((double)v[0], (double)v[1]);
+    o[1] = make_double2((double)v[2], (double)v[3]);
+    o[2] = make_double2((double)v[4], (double)v[5]);
+    return;
+  }
   for (int j = 0; j < A; ++j) out[i * A + j] = (double)v[j];
 }
 

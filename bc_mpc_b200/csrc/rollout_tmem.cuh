@@ -126,7 +126,7 @@ struct Layout {
 enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2, kVarReward = 4, kVarRewardPolicy = 5 };
 __host__ __device__ constexpr int hidden2_chunks(int nc, int var) { return (var & kVarReward) ? 2 * nc : nc; }
 constexpr int kRewardCol = kD;          // output column of the reward head in D3
-constexpr uint32_t kLnStatsBytes = 2 * 2 * kRows * 8;      // [layer][epilogue group][row] (sum, sum of squares)
+constexpr uint32_t kLnStatsBytes = 3 * 2 * kRows * 8;      // [layer: hidden 1, hidden 2 (delta head), reward head][epilogue group][row] (sum, sum of squares)
 constexpr Layout make_layout(int cg, int nc, int var) {
   const bool pol = (var & kVarPolicy) != 0, ln = (var & kVarLayerNorm) != 0, rew = (var & kVarReward) != 0;
   const int nc2 = hidden2_chunks(nc, var);
@@ -144,8 +144,9 @@ constexpr Layout make_layout(int cg, int nc, int var) {
   L.pol_bytes = pol ? 6u * L.blk_h + 2u * L.blk_o : 0u;
   // LayerNorm variant: per-column correction vectors of layer 2 (u2, c2: 2 x 64*nc floats) + per-row statistics
   L.off_ln = (L.off_pol + L.pol_bytes + 1023u) / 1024u * 1024u;
-  L.ln_bytes = ln ? 2u * 64u * nc * 4u + 2u * kOutN * 4u + kLnStatsBytes : 0u;
-  if (rew) L.ln_bytes = (64u * nc2 + kOutN) * 4u;   // learned-reward model: biases of both heads' hidden layers, then of the outputs
+  // LayerNorm: [u2 (64 nc2)][c2 (64 nc2)][u3 (32)][c3 (32)] correction vectors + per-row statistics
+  L.ln_bytes = ln ? 2u * 64u * nc2 * 4u + 2u * kOutN * 4u + kLnStatsBytes : 0u;
+  if (rew && !ln) L.ln_bytes = (64u * nc2 + kOutN) * 4u;   // learned-reward model: biases of both heads' hidden layers, then of the outputs
   L.off_ring = (L.off_ln + L.ln_bytes + 1023u) / 1024u * 1024u;
   L.stage_bytes = L.kbs * L.blk_h;
   L.nst = (int)((kSmemLimit - kMiscBytes - L.off_ring) / L.stage_bytes);
@@ -299,8 +300,8 @@ inline void tm_geometry(int S, int cg, int var, TmHostPlan* out) {
   P.lay = make_layout(cg, P.nc, var);
   P.res_total = (size_t)cg * P.lay.res_bytes;
   P.stream_total = (size_t)P.nc2 * P.lay.nstg * cg * P.lay.stage_bytes;
-  P.lnvec_floats = ln ? (size_t)2 * P.s_pad + 2 * kOutN : 0;      // [u2][c2][u3][c3]
-  if (rew) P.lnvec_floats = (size_t)64 * P.nc2 + kOutN;           // [b2 delta head][b2 reward head][b3]
+  P.lnvec_floats = ln ? (size_t)2 * 64 * P.nc2 + 2 * kOutN : 0;   // [u2][c2][u3][c3]
+  if (rew && !ln) P.lnvec_floats = (size_t)64 * P.nc2 + kOutN;    // [b2 delta head][b2 reward head][b3]
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -393,7 +394,7 @@ template <int CG, int NC, int VAR>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
   constexpr bool POL = (VAR & kVarPolicy) != 0, LN = (VAR & kVarLayerNorm) != 0, REW = (VAR & kVarReward) != 0;
   constexpr int NC2 = hidden2_chunks(NC, VAR);                // hidden-2 chunks (both heads of the learned-reward model)
-  static_assert(NC <= kMaxChunks1 && NC2 <= kMaxChunks2 && !(LN && REW), "unsupported kernel variant");
+  static_assert(NC <= kMaxChunks1 && NC2 <= kMaxChunks2, "unsupported kernel variant");
   constexpr Layout L = Lay<CG, NC, VAR>::value;
   constexpr int kNstg = L.nstg;                               // weight stages per layer-2 chunk
   constexpr int kStagesPerStepR[2] = {((NC2 + 1) / 2) * kNstg, (NC2 / 2) * kNstg};   // weight stages per step and sub-ring (even / odd chunks)
@@ -436,15 +437,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     ptx::mbar_init(ev + 8u * kEvPolFull, 1);
     ptx::fence_mbar_init();
   }
-  if constexpr (REW) {      // biases of the two heads: [b2 (64 * NC2)][b3 (32)]
+  if constexpr (REW && !LN) {      // biases of the two heads: [b2 (64 * NC2)][b3 (32)]
     float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
     for (int i = tid; i < 64 * NC2 + kOutN; i += kThreads) s_vec[i] = a.lnvec[i];
   }
   if constexpr (LN) {
     float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
-    for (int i = tid; i < 2 * 64 * NC + 2 * kOutN; i += kThreads) s_vec[i] = a.lnvec[i];
+    for (int i = tid; i < 2 * 64 * NC2 + 2 * kOutN; i += kThreads) s_vec[i] = a.lnvec[i];
     // per-row statistics start at zero: a group without a chunk in some layer never writes its partial
-    for (int i = tid; i < (int)(kLnStatsBytes / 4); i += kThreads) s_vec[2 * 64 * NC + 2 * kOutN + i] = 0.f;
+    for (int i = tid; i < (int)(kLnStatsBytes / 4); i += kThreads) s_vec[2 * 64 * NC2 + 2 * kOutN + i] = 0.f;
   }
   if (warp == 2) ptx::tmem_alloc_cg<CG>(ptx::smem_u32(s_tmem), kTmemCols);
   ptx::tc_fence_before();
@@ -795,10 +796,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       // ---- LayerNorm variant: statistics of this row's ReLU outputs, correction of the previous layer's statistics ----
       // (each row's chunks are split between the two epilogue groups: partial sums meet in shared memory)
       float ln_sum = 0.f, ln_sq = 0.f, rho = 1.f, rmu = 0.f;
-      [[maybe_unused]] float2* s_stats = reinterpret_cast<float2*>(smem + L.off_ln + (2u * 64u * NC + 2u * kOutN) * 4u);   // [layer][group][row]
+      [[maybe_unused]] float2* s_stats = reinterpret_cast<float2*>(smem + L.off_ln + (2u * 64u * NC2 + 2u * kOutN) * 4u);   // [layer][group][row]
       [[maybe_unused]] const float* s_u2 = reinterpret_cast<const float*>(smem + L.off_ln);
-      [[maybe_unused]] const float* s_c2 = s_u2 + 64 * NC;
-      [[maybe_unused]] const float* s_u3 = s_u2 + 2 * 64 * NC;
+      [[maybe_unused]] const float* s_c2 = s_u2 + 64 * NC2;
+      [[maybe_unused]] const float* s_u3 = s_u2 + 2 * 64 * NC2;
       [[maybe_unused]] const float* s_c3 = s_u3 + kOutN;
       // rho = 1 / sqrt(var + eps), rmu = rho * mean of the layer whose partial sums are in s_stats[layer]
       auto ln_row_stats = [&](int layer) {
@@ -808,8 +809,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         rho = rsqrtf(var + a.ln_eps);
         rmu = rho * mean;
       };
-      // one chunk with LayerNorm: layer 0 = hidden 1 (plain ReLU of the accumulator), layer 1 = hidden 2 (corrected)
-      auto chunk_ln = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, int wait_a2, int layer, uint32_t c) {
+      // one chunk with LayerNorm.  corr: apply the correction of the PREVIOUS layer's statistics (hidden 2; hidden 1 is
+      // the plain activation of the accumulator); slot: whose statistics this chunk adds to (0 = hidden 1, 1 = hidden 2 /
+      // delta head, 2 = reward head).  Activation: ReLU, or tanh for the learned-reward model (statistics of the
+      // bf16-rounded values the tensor core will read).
+      auto chunk_ln = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, int wait_a2, bool corr, int slot, uint32_t c) {
         uint32_t v0[32], v1[32], w0[16], w1[16];
         ptx::tmem_ld32(lane_off + col, v0);
         ptx::tmem_ld32(lane_off + col + 32u, v1);
@@ -819,28 +823,41 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (lane == 0) arrive_leader(kEvDEmpty + e);
         const float4* u4 = reinterpret_cast<const float4*>(s_u2 + 64u * c);
         const float4* c4 = reinterpret_cast<const float4*>(s_c2 + 64u * c);
-        auto relu_stat = [&](float acc, float u, float cc) {
-          float zv = layer == 0 ? acc : fmaf(rho, acc, fmaf(-rmu, u, cc));
+        auto pre = [&](float acc, float u, float cc) { return corr ? fmaf(rho, acc, fmaf(-rmu, u, cc)) : acc; };
+        auto relu_stat = [&](float zv) {
           zv = zv < 0.f ? 0.f : zv;
           ln_sum += zv;
           ln_sq = fmaf(zv, zv, ln_sq);
           return zv;
         };
+        // two neighbouring units -> activation -> bf16 pair (+ statistics)
+        auto act_pair = [&](float x, float y) -> uint32_t {
+          if constexpr (REW) {
+            const uint32_t t = ptx::tanh_bf16x2(pack_bf16(x, y));
+            const float lo = __uint_as_float(t << 16), hi = __uint_as_float(t & 0xFFFF0000u);
+            ln_sum += lo + hi;
+            ln_sq = fmaf(lo, lo, fmaf(hi, hi, ln_sq));
+            return t;
+          } else {
+            const float rx = relu_stat(x), ry = relu_stat(y);
+            return pack_bf16(rx, ry);
+          }
+        };
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), cc = uu;
-          if (layer == 1) { uu = u4[i]; cc = c4[i]; }
-          w0[2 * i] = pack_bf16(relu_stat(__uint_as_float(v0[4 * i]), uu.x, cc.x), relu_stat(__uint_as_float(v0[4 * i + 1]), uu.y, cc.y));
-          w0[2 * i + 1] = pack_bf16(relu_stat(__uint_as_float(v0[4 * i + 2]), uu.z, cc.z), relu_stat(__uint_as_float(v0[4 * i + 3]), uu.w, cc.w));
+          if (corr) { uu = u4[i]; cc = c4[i]; }
+          w0[2 * i] = act_pair(pre(__uint_as_float(v0[4 * i]), uu.x, cc.x), pre(__uint_as_float(v0[4 * i + 1]), uu.y, cc.y));
+          w0[2 * i + 1] = act_pair(pre(__uint_as_float(v0[4 * i + 2]), uu.z, cc.z), pre(__uint_as_float(v0[4 * i + 3]), uu.w, cc.w));
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), cc = uu;
-          if (layer == 1) { uu = u4[8 + i]; cc = c4[8 + i]; }
-          w1[2 * i] = pack_bf16(relu_stat(__uint_as_float(v1[4 * i]), uu.x, cc.x), relu_stat(__uint_as_float(v1[4 * i + 1]), uu.y, cc.y));
-          w1[2 * i + 1] = pack_bf16(relu_stat(__uint_as_float(v1[4 * i + 2]), uu.z, cc.z), relu_stat(__uint_as_float(v1[4 * i + 3]), uu.w, cc.w));
+          if (corr) { uu = u4[8 + i]; cc = c4[8 + i]; }
+          w1[2 * i] = act_pair(pre(__uint_as_float(v1[4 * i]), uu.x, cc.x), pre(__uint_as_float(v1[4 * i + 1]), uu.y, cc.y));
+          w1[2 * i + 1] = act_pair(pre(__uint_as_float(v1[4 * i + 2]), uu.z, cc.z), pre(__uint_as_float(v1[4 * i + 3]), uu.w, cc.w));
         }
-        s_stats[(layer * 2 + g) * kRows + row] = make_float2(ln_sum, ln_sq);     // running partial of this group
+        s_stats[(slot * 2 + g) * kRows + row] = make_float2(ln_sum, ln_sq);     // running partial of this group
         __threadfence_block();
         if (wait_a2 >= 0) {
           ptx::mbar_wait(ev + 8u * (kEvA2Empty + wait_a2), uh & 1u, hc);
@@ -933,7 +950,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         for (uint32_t c = c0; c < c0 + (two ? 2u : 1u); ++c) {
           const uint32_t bsel = c % (uint32_t)kNumDBufL1;
           const uint32_t col = bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2;
-          if constexpr (LN) chunk_ln(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, 0, c);
+          if constexpr (LN) chunk_ln(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, false, 0, c);
           else if constexpr (REW) chunk_bias(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, nullptr);
           else chunk(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1);
         }
@@ -943,6 +960,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       if (is_final && h + 1 < H) get_noise(a, b, h + 1, kc, z);
       // layer 2: alternate chunks
       bool first_l2 = true;
+      [[maybe_unused]] bool in_reward_head = false;
 #pragma unroll 1
       for (uint32_t c = (uint32_t)g; c < (uint32_t)NC2; c += 2) {
         ptx::mbar_wait(ev + 8u * (kEvDFull + NC + c), uh & 1u, hc);
@@ -965,7 +983,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           dst = bsel == 0 ? (uint32_t)kColA2 : (uint32_t)(kColA1 + 32 * NC) + 32u * (bsel - 1u);
           wait_a2 = c >= (uint32_t)a2_buffers(NC) ? (int)c - a2_buffers(NC) : -1;
         }
-        if constexpr (LN) chunk_ln((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, 1, c);
+        if constexpr (LN && REW) {
+          if (c >= (uint32_t)NC && !in_reward_head) { ln_sum = 0.f; ln_sq = 0.f; in_reward_head = true; }   // the reward head keeps its own statistics
+        }
+        if constexpr (LN) chunk_ln((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, true,
+                                   (REW && c >= (uint32_t)NC) ? 2 : 1, c);
         else if constexpr (REW) chunk_bias((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, s_b2 + 64u * c);
         else chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2);
       }
@@ -983,9 +1005,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           ln_row_stats(1);
 #pragma unroll
           for (int d = 0; d < kD; ++d) v[d] = __float_as_uint(fmaf(rho, __uint_as_float(v[d]), fmaf(-rmu, s_u3[d], s_c3[d])));
+          if constexpr (REW) {
+            ln_row_stats(2);
+            v[kRewardCol] = __float_as_uint(fmaf(rho, __uint_as_float(v[kRewardCol]), fmaf(-rmu, s_u3[kRewardCol], s_c3[kRewardCol])));
+          }
           ln_sum = 0.f; ln_sq = 0.f;
         }
-        if constexpr (REW) {
+        if constexpr (REW && !LN) {
           const float* s_b3 = s_b2 + 64 * NC2;
 #pragma unroll
           for (int d = 0; d <= kRewardCol; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) + s_b3[d]);
@@ -1102,6 +1128,8 @@ cudaError_t tm_launch_var2(int cg, int nc, const TmArgs& a, dim3 grid, cudaStrea
 cudaError_t tm_launch_var3(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // LayerNorm + proposal network
 cudaError_t tm_launch_var4(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // learned-reward model
 cudaError_t tm_launch_var5(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // ... + proposal network
+cudaError_t tm_launch_var6(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // learned-reward model with LayerNorm
+cudaError_t tm_launch_var7(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // ... + proposal network (what run.sh launches)
 inline cudaError_t tm_launch(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
   switch (var) {
     case 0: return tm_launch_var0(cg, nc, a, grid, st);
@@ -1110,6 +1138,8 @@ inline cudaError_t tm_launch(int cg, int nc, int var, const TmArgs& a, dim3 grid
     case 3: return tm_launch_var3(cg, nc, a, grid, st);
     case 4: return tm_launch_var4(cg, nc, a, grid, st);
     case 5: return tm_launch_var5(cg, nc, a, grid, st);
+    case 6: return tm_launch_var6(cg, nc, a, grid, st);
+    case 7: return tm_launch_var7(cg, nc, a, grid, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -1,0 +1,10 @@
+// tcgen05 rollout kernel, variant 7 (bit flags: 1 = proposal network, 2 = LayerNorm dynamics, 4 = learned-reward model)
+#include "rollout_tmem.cuh"
+
+namespace bcmpc {
+namespace tmx {
+cudaError_t tm_launch_var7(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  return cg == 2 ? tm_launch_48<2, 7>(nc, a, grid, st) : tm_launch_48<1, 7>(nc, a, grid, st);
+}
+}  // namespace tmx
+}  // namespace bcmpc

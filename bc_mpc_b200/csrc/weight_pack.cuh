@@ -10,6 +10,7 @@ struct PackArgs {
   const float *W1, *b1, *W2, *b2, *W3, *b3;     // device, row strides ld1..ld3
   const float *g1, *be1, *g2, *be2;             // LayerNorm gamma / beta of hidden layers 1, 2 (nullptr = off)
   const float *Wr1, *br1, *Wr2, *br2;           // reward head [S,S], [S,1] (nullptr = off; learned-reward model)
+  const float *gr, *ber;                        // LayerNorm gamma / beta of the reward head's hidden layer
   int ld1, ld2, ld3, ldr1, ldr2;
   int S, s_pad, nc, cg, kbs, nstg;
   uint32_t blk_h, blk_o, w1_bytes, res_bytes, stage_bytes;
@@ -27,28 +28,48 @@ __device__ __forceinline__ uint16_t pk_w1(const PackArgs& a, int k, int n) {    
   if (!ln && (n == a.S || n == a.S + 1)) return k == in_dim ? (uint16_t)0x3F80 : 0;   // the hidden "ones" units: relu(1 * 1) = 1
   return 0;
 }
+// Hidden layer 2 and the output layer as seen by the kernel.  Learned-reward model: layer 2 has 2 * s_pad columns
+// (delta head, then reward head) and the output layer 2 * s_pad rows, block-structured: delta-head units feed columns
+// 0..19, reward-head units column 20.  `raw` = the float32 weight, `gamma`/`beta` = the LayerNorm of the INPUT of that
+// weight row, `bias` = the bias of that output column.
+__device__ __forceinline__ bool w2_live(const PackArgs& a, int k, int n) { return k < a.S && (a.Wr1 ? n % a.s_pad : n) < a.S && n < (a.Wr1 ? 2 : 1) * a.s_pad; }
+__device__ __forceinline__ float w2_raw(const PackArgs& a, int k, int n) {
+  if (a.Wr1 && n >= a.s_pad) return a.Wr1[(size_t)k * a.ldr1 + (n - a.s_pad)];
+  return a.W2[(size_t)k * a.ld2 + n];
+}
+__device__ __forceinline__ float w2_bias(const PackArgs& a, int n) { return (a.Wr1 && n >= a.s_pad) ? a.br1[n - a.s_pad] : a.b2[n]; }
+__device__ __forceinline__ bool w3_live(const PackArgs& a, int k, int n) {
+  if (!a.Wr1) return k < a.S && n < kD;
+  if (k % a.s_pad >= a.S || k >= 2 * a.s_pad) return false;
+  return k < a.s_pad ? n < kD : n == kRewardCol;
+}
+__device__ __forceinline__ float w3_raw(const PackArgs& a, int k, int n) {
+  if (a.Wr1 && k >= a.s_pad) return a.Wr2[(size_t)(k - a.s_pad) * a.ldr2];
+  return a.W3[(size_t)k * a.ld3 + n];
+}
+__device__ __forceinline__ float w3_gamma(const PackArgs& a, int k) { return (a.Wr1 && k >= a.s_pad) ? a.gr[k - a.s_pad] : a.g2[k]; }
+__device__ __forceinline__ float w3_beta(const PackArgs& a, int k) { return (a.Wr1 && k >= a.s_pad) ? a.ber[k - a.s_pad] : a.be2[k]; }
+__device__ __forceinline__ float w3_bias(const PackArgs& a, int n) { return (a.Wr1 && n == kRewardCol) ? a.br2[0] : a.b3[n]; }
+
 __device__ __forceinline__ uint16_t pk_w2(const PackArgs& a, int k, int n) {
   const int S = a.S;
-  if (a.Wr1) {        // columns [0, s_pad): state-delta head, [s_pad, 2 s_pad): reward head; biases are added in the epilogue
-    const int nn = n % a.s_pad;
-    if (nn >= S || k >= S) return 0;
-    return f32_to_bf16(n < a.s_pad ? a.W2[(size_t)k * a.ld2 + nn] : a.Wr1[(size_t)k * a.ldr1 + nn]);
+  if (a.g1 || a.Wr1) {         // no bias rows: LayerNorm folds the bias into c, the reward model adds it in the epilogue
+    if (!w2_live(a, k, n)) return 0;
+    const float w = w2_raw(a, k, n);
+    return f32_to_bf16(a.g1 ? __fmul_rn(a.g1[k], w) : w);
   }
-  if (a.g1) return (n < S && k < S) ? f32_to_bf16(__fmul_rn(a.g1[k], a.W2[(size_t)k * a.ld2 + n])) : 0;
   if (n < S) return k < S ? f32_to_bf16(a.W2[(size_t)k * a.ld2 + n]) : k == S ? pk_hi(a.b2[n]) : k == S + 1 ? pk_lo(a.b2[n]) : 0;
   if (n == S || n == S + 1) return k == S ? (uint16_t)0x3F80 : 0;
   return 0;
 }
 __device__ __forceinline__ uint16_t pk_w3(const PackArgs& a, int k, int n) {        // n < 32 (output column)
   const int S = a.S;
-  if (a.Wr1) {        // rows [0, s_pad): hidden units of the delta head -> columns 0..19; [s_pad, 2 s_pad): reward head -> column 20
-    const int kk = k % a.s_pad;
-    if (kk >= S) return 0;
-    if (k < a.s_pad) return n < kD ? f32_to_bf16(a.W3[(size_t)kk * a.ld3 + n]) : 0;
-    return n == kRewardCol ? f32_to_bf16(a.Wr2[(size_t)kk * a.ldr2]) : 0;
+  if (a.g1 || a.Wr1) {
+    if (!w3_live(a, k, n)) return 0;
+    const float w = w3_raw(a, k, n);
+    return f32_to_bf16(a.g1 ? __fmul_rn(w3_gamma(a, k), w) : w);
   }
   if (n >= kD) return 0;
-  if (a.g1) return k < S ? f32_to_bf16(__fmul_rn(a.g2[k], a.W3[(size_t)k * a.ld3 + n])) : 0;
   return k < S ? f32_to_bf16(a.W3[(size_t)k * a.ld3 + n]) : k == S ? pk_hi(a.b3[n]) : k == S + 1 ? pk_lo(a.b3[n]) : 0;
 }
 
@@ -75,26 +96,39 @@ __global__ void pack_images_kernel(PackArgs a) {
   }
 }
 
-// LayerNorm correction vectors, one warp per column: lnvec = [u2 (s_pad)][c2 (s_pad)][u3 (32)][c3 (32)]
+// LayerNorm correction vectors, one warp per column: lnvec = [u2 (sp2)][c2 (sp2)][u3 (32)][c3 (32)], sp2 = width of
+// hidden layer 2:  u = column sum of the bf16 image (gamma folded in), c = beta^T W + bias
 __global__ void pack_ln_kernel(PackArgs a) {
   const int col = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
-  const int sp = a.s_pad, S = a.S;
-  if (col >= sp + kOutN) return;
-  const bool l3 = col >= sp;
-  const int n = l3 ? col - sp : col;
-  const bool live = l3 ? n < kD : n < S;
+  const int sp2 = a.Wr1 ? 2 * a.s_pad : a.s_pad, S = a.S;
+  if (col >= sp2 + kOutN) return;
+  const bool l3 = col >= sp2;
+  const int n = l3 ? col - sp2 : col;
   double u = 0.0, c = 0.0;
-  if (live)
-    for (int k = lane; k < S; k += 32) {
-      if (l3) { u += (double)bf16_to_f32(pk_w3(a, k, n)); c += (double)a.be2[k] * (double)a.W3[(size_t)k * a.ld3 + n]; }
-      else    { u += (double)bf16_to_f32(pk_w2(a, k, n)); c += (double)a.be1[k] * (double)a.W2[(size_t)k * a.ld2 + n]; }
-    }
+  bool live = false;
+  if (l3) {
+    // the rows that feed output column n: the delta head's units for n < 20, the reward head's for n == 20
+    const int k0 = (a.Wr1 && n == kRewardCol) ? a.s_pad : 0;
+    live = w3_live(a, k0, n);
+    if (live)
+      for (int k = k0 + lane; k < k0 + S; k += 32) {
+        u += (double)bf16_to_f32(pk_w3(a, k, n));
+        c += (double)w3_beta(a, k) * (double)w3_raw(a, k, n);
+      }
+  } else {
+    live = w2_live(a, 0, n);
+    if (live)
+      for (int k = lane; k < S; k += 32) {
+        u += (double)bf16_to_f32(pk_w2(a, k, n));
+        c += (double)a.be1[k] * (double)w2_raw(a, k, n);
+      }
+  }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) { u += __shfl_xor_sync(0xffffffffu, u, off); c += __shfl_xor_sync(0xffffffffu, c, off); }
   if (lane == 0) {
-    if (live) c += (double)(l3 ? a.b3[n] : a.b2[n]);
-    float* pu = l3 ? a.lnvec + 2 * sp : a.lnvec;
-    float* pc = l3 ? a.lnvec + 2 * sp + kOutN : a.lnvec + sp;
+    if (live) c += (double)(l3 ? w3_bias(a, n) : w2_bias(a, n));
+    float* pu = l3 ? a.lnvec + 2 * sp2 : a.lnvec;
+    float* pc = l3 ? a.lnvec + 2 * sp2 + kOutN : a.lnvec + sp2;
     pu[n] = live ? (float)u : 0.f;
     pc[n] = live ? (float)c : 0.f;
   }
@@ -115,8 +149,8 @@ inline cudaError_t tm_pack(const PackArgs& a, cudaStream_t st) {
   const int sp2 = a.Wr1 ? 2 * a.s_pad : a.s_pad;
   const int total = 64 * a.s_pad + sp2 * kOutN + a.s_pad * sp2;
   pack_images_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
-  if (a.g1) pack_ln_kernel<<<(a.s_pad + kOutN + 7) / 8, 256, 0, st>>>(a);
-  if (a.Wr1) pack_reward_bias_kernel<<<(2 * a.s_pad + kOutN + 255) / 256, 256, 0, st>>>(a);
+  if (a.g1) pack_ln_kernel<<<(sp2 + kOutN + 7) / 8, 256, 0, st>>>(a);
+  else if (a.Wr1) pack_reward_bias_kernel<<<(2 * a.s_pad + kOutN + 255) / 256, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 

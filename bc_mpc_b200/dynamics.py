@@ -107,20 +107,32 @@ class NNDynamicsRewardModel(NNDynamicsModel):
                          batch_size=batch_size, iterations=iterations, learning_rate=learning_rate, sess=sess,
                          layer_norm=layer_norm)
         self.reward_weights = None
+        self.reward_layer_norm = None
 
-    def set_weights(self, weights, reward_weights, layer_norm_params=None):
+    def set_weights(self, weights, reward_weights, layer_norm_params=None, reward_layer_norm=None):
         """weights: share, delta-hidden, delta-out; reward_weights: reward-hidden, reward-out (TF creation order:
-        dense, dense_1, dense_2, dense_3, dense_4 under scope NNDynamicsModel)."""
+        dense, dense_1, dense_2, dense_3, dense_4 under scope NNDynamicsModel).  With layer_norm=True:
+        layer_norm_params = [(gamma, beta)] of share and delta-hidden, reward_layer_norm = (gamma, beta) of reward-hidden
+        (dynamics.py:165-176)."""
         self.reward_weights = [(np.asarray(w, np.float32), np.asarray(b, np.float32)) for w, b in reward_weights]
+        if self.layer_norm:
+            if reward_layer_norm is None:
+                raise ValueError("this model was built with layer_norm=True: pass reward_layer_norm=(gamma, beta)")
+            self.reward_layer_norm = tuple(np.asarray(t, np.float32) for t in reward_layer_norm)
         super().set_weights(weights, layer_norm_params)
 
     def load_vars(self, var_dict):
         names = ["dense", "dense_1", "dense_2", "dense_3", "dense_4"]
         ws = [(var_dict[f"{self.scope}/{n}/kernel:0"], var_dict[f"{self.scope}/{n}/bias:0"]) for n in names]
-        self.set_weights(ws[:3], ws[3:])
+        ln = None
+        if self.layer_norm:   # creation order: share, delta-hidden, reward-hidden (dynamics.py:165-176) [names from memory]
+            ln = [(var_dict[f"{self.scope}/{n}/gamma:0"], var_dict[f"{self.scope}/{n}/beta:0"])
+                  for n in ("LayerNorm", "LayerNorm_1", "LayerNorm_2")]
+        self.set_weights(ws[:3], ws[3:], ln[:2] if ln else None, ln[2] if ln else None)
 
     def upload_reward_head(self, planner, gamma=1.0):
-        planner.set_reward_head(self.reward_weights, float(np.asarray(self.mean_reward)), float(np.asarray(self.std_reward)), gamma)
+        planner.set_reward_head(self.reward_weights, float(np.asarray(self.mean_reward)), float(np.asarray(self.std_reward)), gamma,
+                                layer_norm=self.reward_layer_norm if self.layer_norm else None)
 
     def predict(self, unnormalized_state, unnormalized_action):
         if self.weights is None:

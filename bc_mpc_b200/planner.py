@@ -117,9 +117,10 @@ class Planner:
                 raise ValueError(f"LayerNorm gamma/beta must be [{self.cfg.hidden_size}]")
         self._ck(self._lib.bcmpc_set_layer_norm(self._h, L.ptr_array(gs), L.ptr_array(bs), len(gs), C.c_float(eps)))
 
-    def set_reward_head(self, weights, mean_reward=0.0, std_reward=1.0, gamma=1.0):
+    def set_reward_head(self, weights, mean_reward=0.0, std_reward=1.0, gamma=1.0, layer_norm=None, eps=1e-12):
         """Reward head of NNDynamicsRewardModel (dynamics.py:175-178): weights = [(kernel[S,S], bias[S]), (kernel[S,1], bias[1])],
-        or None to go back to cheetah_cost_fn.  The planner then maximises sum_i gamma**i * reward_i (controllers.py:121-158)."""
+        or None to go back to cheetah_cost_fn.  The planner then maximises sum_i gamma**i * reward_i (controllers.py:121-158).
+        layer_norm = (gamma[S], beta[S]) of the head's hidden layer when FLAGS.LAYER_NORM (dynamics.py:176)."""
         if weights is None:
             self._ck(self._lib.bcmpc_set_reward_head(self._h, None, None, 0.0, 1.0, 1.0))
             return
@@ -130,6 +131,12 @@ class Planner:
             raise ValueError(f"reward head must be [({S},{S}), ({S},1)] kernels")
         self._ck(self._lib.bcmpc_set_reward_head(self._h, L.ptr_array(Ws), L.ptr_array(bs), float(mean_reward),
                                                  float(std_reward), float(gamma)))
+        if layer_norm is not None:
+            g = np.ascontiguousarray(layer_norm[0], np.float32).reshape(-1)
+            b = np.ascontiguousarray(layer_norm[1], np.float32).reshape(-1)
+            if g.shape != (S,) or b.shape != (S,):
+                raise ValueError(f"reward-head LayerNorm gamma/beta must be [{S}]")
+            self._ck(self._lib.bcmpc_set_reward_layer_norm(self._h, L.ptr(g), L.ptr(b), C.c_float(eps)))
 
     def predict_reward(self, states, actions):
         """NNDynamicsRewardModel.predict (dynamics.py:221-238): (next_states [n,D], rewards [n,1])."""

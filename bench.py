@@ -176,6 +176,24 @@ def extras():
         "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
         "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
     pl.close()
+    # the configuration run.sh launches: LEARN_REWARD + LAYER_NORM (default) + SELFEXP (stochastic policy proposals),
+    # mpc_horizon=30, simulated_paths=400; one env (the reference's loop) and 256 envs in lock step (sample_vectorized)
+    lns = [(np.ones(500, np.float32), np.zeros(500, np.float32))] * 3
+    for tag, B in (("runsh_default_1env", 1), ("runsh_default_256envs", 256)):
+        K, H = 400, 30
+        pl = Planner(20, 6, 2, 500, "tanh", num_paths=K, horizon=H, max_states=B, precision="bf16", proposal="policy_gaussian")
+        pl.set_dynamics(rw)
+        pl.set_layer_norm(lns[:2])
+        pl.set_normalization(rnorm["mean_obs"], rnorm["std_obs"], rnorm["mean_action"], rnorm["std_action"], rnorm["mean_deltas"], rnorm["std_deltas"])
+        pl.set_reward_head(rrw, rnorm["mean_reward"], rnorm["std_reward"], 1.0, layer_norm=lns[2])
+        pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+        st = rnorm["mean_obs"] + rnorm["std_obs"] * np.random.default_rng(3).standard_normal((B, 20))
+        pl.enable_timing(True)
+        dt = time_plans(pl, st, 10)
+        k_ms = pl.last_kernel_ms()
+        out[tag + "_reward_layernorm_selfexp_K400_H30_bf16"] = {"plan_call_ms": 1e3 * dt, "plans_per_s": B / dt, "transitions_per_s_e2e": B * K * H / dt,
+                                                               "kernel_ms": k_ms}
+        pl.close()
     # stand-alone sampling stage (replay / debugging aid; the planner itself draws in registers): HBM-bound writes,
     # 6 float64 per (state, step, path) = 48 B per transition
     pl = make(1 << 17, 20, "bf16", B=4)
@@ -186,6 +204,16 @@ def extras():
     out["sampling_stage_standalone"] = {"bytes_written": int(inj.nbytes), "kernel_ms": ms, "GB_per_s": inj.nbytes / (ms * 1e-3) / 1e9,
                                         "hbm_peak_GB_per_s": hbm_peak(), "transitions_per_s": inj.size / 6 / (ms * 1e-3)}
     del inj
+    # stand-alone cost stage (cheetah_cost_fn over given [n,20] float64 states / next states; in the planner it is fused)
+    n = 1 << 21
+    S0 = np.random.default_rng(4).standard_normal((n, 20))
+    for _ in range(2):
+        pl.cheetah_cost(S0, S0 + 0.01)
+    ms = pl.last_kernel_ms()
+    out["cost_stage_standalone"] = {"rows": n, "kernel_ms": ms, "GB_per_s_arrays": (2 * S0.nbytes + 8 * n) / (ms * 1e-3) / 1e9,
+                                    "GB_per_s_touched_sectors": (3 * 32 + 8) * n / (ms * 1e-3) / 1e9, "hbm_peak_GB_per_s": hbm_peak(),
+                                    "note": "reads 5 of 40 doubles per row: 3 of 10 32-byte sectors"}
+    del S0
     pl.close()
     # weight refresh after dyn_model.fit (train_mpc_ppo.py:279): host arrays vs device-resident torch parameters
     import torch

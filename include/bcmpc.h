@@ -135,6 +135,11 @@ int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float
 int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward,
                           double std_reward, double gamma);
 
+/* LayerNorm after the reward head's hidden layer (dynamics.py:175-176, FLAGS.LAYER_NORM): gamma, beta [hidden], or NULL
+ * to switch it off.  The shared layer and the delta head take theirs from bcmpc_set_layer_norm.  Call after
+ * bcmpc_set_reward_head (a new head resets it). */
+int bcmpc_set_reward_layer_norm(bcmpc_handle* h, const float* gamma, const float* beta, float eps);
+
 /* NNDynamicsRewardModel.predict (dynamics.py:221-238): next_states [n,D] and rewards [n].  HOST buffers. */
 int bcmpc_predict_reward(bcmpc_handle* h, const double* states, const double* actions, int64_t n, double* next_states,
                          double* rewards);

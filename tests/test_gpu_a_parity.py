@@ -149,8 +149,9 @@ def test_layer_norm_dynamics_variant():
         make_pair(17, (64, 64), 128, 2, precision="bf16", proposal="policy_mix")[3].set_layer_norm([(g[:64], b[:64]) for g, b in ln])
 
 
-@pytest.mark.parametrize("proposal,gamma", [("uniform", 0.9), ("uniform", 1.0), ("policy_mix", 1.0)])
-def test_learned_reward_planners(proposal, gamma):
+@pytest.mark.parametrize("proposal,gamma,ln", [("uniform", 0.9, False), ("uniform", 1.0, False), ("policy_mix", 1.0, False),
+                                               ("uniform", 0.9, True), ("policy_gaussian", 1.0, True)])
+def test_learned_reward_planners(proposal, gamma, ln):
     """NNDynamicsRewardModel + MPCcontrollerReward / MPCcontrollerPolicyNetReward (dynamics.py:121-238,
     controllers.py:90-158,289-363): shared tanh layer, delta head, reward head; argmax of the (discounted) reward sum."""
     from bc_mpc_b200 import Planner
@@ -160,14 +161,19 @@ def test_learned_reward_planners(proposal, gamma):
     pl = Planner(20, 6, 2, S, "tanh", num_paths=K, horizon=H, precision="fp32", proposal=proposal, explore=0.4)
     pl.set_dynamics(weights)
     pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
-    pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], gamma)
+    lns = None
+    if ln:        # FLAGS.LAYER_NORM (the default): LayerNorm after the shared layer and after each head's hidden layer
+        lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(3)]
+        dyn = O.OracleRewardDynamics(weights, rweights, norm, layer_norm=lns[:2], reward_layer_norm=lns[2])
+        pl.set_layer_norm(lns[:2])
+    pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], gamma, layer_norm=lns[2] if ln else None)
     pol = None
     if proposal != "uniform":
         pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
         pol = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
         pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
     mpc = O.OracleMPC(dyn, H, K, proposal=proposal, policy=pol, explore=0.4, learned_reward=True, gamma=gamma)
-    inj = f32_uniform(rng, (H, K, 6))
+    inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64) if proposal == "policy_gaussian" else f32_uniform(rng, (H, K, 6))
     act, dbg = mpc.get_action(state, inj, return_debug=True)
     so, ao, co = pl.rollout_debug(state, inj)
     assert scaled_rel_err(so, dbg["states"], state_scale(norm)).max() < TOL

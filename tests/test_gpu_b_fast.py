@@ -86,8 +86,9 @@ def test_policy_guided_fast_mode_tracks_oracle(proposal, bc, K):
     assert not np.array_equal(r1["action"], r3["action"])
 
 
-@pytest.mark.parametrize("S,proposal,K,gamma", [(500, "uniform", 4096, 0.95), (500, "policy_mix", 1000, 1.0), (256, "uniform", 1000, 1.0)])
-def test_learned_reward_fast_mode_tracks_oracle(S, proposal, K, gamma):
+@pytest.mark.parametrize("S,proposal,K,gamma,ln", [(500, "uniform", 4096, 0.95, False), (500, "policy_mix", 1000, 1.0, False), (256, "uniform", 1000, 1.0, False),
+                                                   (500, "uniform", 1000, 0.95, True), (500, "policy_gaussian", 1000, 1.0, True), (256, "policy_mix", 1000, 1.0, True)])
+def test_learned_reward_fast_mode_tracks_oracle(S, proposal, K, gamma, ln):
     """NNDynamicsRewardModel + MPCcontrollerReward / MPCcontrollerPolicyNetReward (dynamics.py:121-238,
     controllers.py:90-158,289-363) on the tcgen05 path: shared tanh layer, both 500-wide tanh heads as ONE 1024-wide
     second layer, block-structured output layer (20 deltas + reward), discounted-reward objective in the epilogue."""
@@ -106,14 +107,19 @@ def test_learned_reward_fast_mode_tracks_oracle(S, proposal, K, gamma):
         with pytest.raises(RuntimeError, match="weight ring"):
             pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], gamma)
         return
-    pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], gamma)
+    lns = None
+    if ln:      # what run.sh launches: LAYER_NORM=True (default), LEARN_REWARD=True, SELFEXP=True
+        lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(3)]
+        dyn = O.OracleRewardDynamics(weights, rweights, norm, layer_norm=lns[:2], reward_layer_norm=lns[2])
+        pl.set_layer_norm(lns[:2])
+    pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], gamma, layer_norm=lns[2] if ln else None)
     pol = None
     if proposal != "uniform":
         pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
         pol = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
         pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
     mpc = O.OracleMPC(dyn, H, K, proposal=proposal, policy=pol, explore=0.4, learned_reward=True, gamma=gamma)
-    inj = f32_uniform(rng, (H, K, 6))
+    inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64) if proposal == "policy_gaussian" else f32_uniform(rng, (H, K, 6))
     act, dbg = mpc.get_action(state, inj, return_debug=True)
     so, ao, co = pl.rollout_debug(state, inj)
     e = _norm_err(so, dbg["states"], norm)
@@ -121,16 +127,20 @@ def test_learned_reward_fast_mode_tracks_oracle(S, proposal, K, gamma):
     cstd = dbg["costs"].std()
     rec = pl.plan(state, inj=inj)[0]
     regret = (dbg["costs"][rec["index"]] - dbg["costs"].min()) / cstd
-    print(dict(S=S, proposal=proposal, one_step_err_in_delta_std=float(one), max_state_err_in_delta_std=float(np.abs(e).max()),
+    print(dict(S=S, proposal=proposal, ln=ln, one_step_err_in_delta_std=float(one), max_state_err_in_delta_std=float(np.abs(e).max()),
                cost_corr=float(np.corrcoef(co, dbg["costs"])[0, 1]), max_cost_err_in_std=float(np.abs(co - dbg["costs"]).max() / cstd),
                argmin_match=bool(rec["index"] == dbg["argmin"]), regret_in_cost_std=float(regret)))
-    assert one < 0.05 and np.abs(e).max() < 0.3
+    assert one < (0.08 if ln else 0.05) and np.abs(e).max() < (0.6 if ln else 0.3)
     assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
     assert rec["index"] == int(np.argmin(co)) and np.allclose(rec["action"][:6], ao[0, rec["index"]])
     assert regret < 0.5
     r1, r2 = pl.plan(state, seed=5)[0], pl.plan(state, seed=5)[0]
     assert r1["index"] == r2["index"] and r1["cost"] == r2["cost"]
-    pl.set_dynamics(weights)            # a weight refresh keeps the reward head
+    pl.set_dynamics(weights)            # a weight refresh keeps the reward head (and resets the dynamics LayerNorm)
+    if ln:
+        with pytest.raises(RuntimeError, match="all three LayerNorms"):
+            pl.plan(state, seed=5)
+        pl.set_layer_norm(lns[:2])
     assert pl.plan(state, seed=5)[0]["cost"] == r1["cost"]
 
 
