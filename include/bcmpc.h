@@ -119,8 +119,9 @@ int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const flo
  * tf.contrib.layers.layer_norm AFTER the activation of every hidden layer - moments over the last axis, centre and
  * scale.  gamma[l], beta[l] are [hidden_size] for hidden layer l (n_hidden of them); eps is the variance epsilon
  * (1e-12 in tf.contrib).  gamma == NULL switches LayerNorm off.  Call it after bcmpc_set_dynamics (new weights reset
- * it).  Both precision modes; BCMPC_PREC_BF16_FAST supports it with uniform shooting only (BCMPC_ERR_UNSUPPORTED with a
- * proposal network). */
+ * it).  Both precision modes; with BCMPC_PREC_BF16_FAST and a proposal network or a reward head it is built for hidden
+ * sizes 193..256 and 449..512 (BCMPC_ERR_UNSUPPORTED otherwise), and a reward head needs bcmpc_set_reward_layer_norm
+ * too (all three LayerNorms or none). */
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps);
 
 /* Learned-reward planners: NNDynamicsRewardModel (dynamics.py:121-238) = the dynamics net (n_hidden = 2: shared layer,
