@@ -467,6 +467,43 @@ def test_edge_shapes_and_errors():
         pl.plan(np.zeros((2, 20)))
 
 
+def test_error_paths_of_the_widened_api():
+    """Every unsupported or mis-ordered request fails loudly with a message; nothing falls back silently."""
+    import ctypes as C
+    from bc_mpc_b200 import Planner, _lib as L
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(3, 40)
+    pl = Planner(20, 6, 2, 40, "tanh", num_paths=8, horizon=2)
+    with pytest.raises(RuntimeError, match="dynamics weights not set"):
+        pl.set_layer_norm([(np.ones(40), np.zeros(40))] * 2)
+    with pytest.raises(RuntimeError, match="reward head not set"):
+        pl.predict_reward(state[None], np.zeros((1, 6)))
+    pl.set_dynamics(weights)
+    with pytest.raises(ValueError, match="reward head must be"):
+        pl.set_reward_head(rweights[:1])
+    with pytest.raises(ValueError, match="LayerNorm gamma/beta"):
+        pl.set_layer_norm([(np.ones(41), np.zeros(41))] * 2)
+    with pytest.raises(RuntimeError, match="n_hidden"):
+        pl.set_layer_norm([(np.ones(40), np.zeros(40))])
+    rc = pl._lib.bcmpc_set_reward_layer_norm(pl._h, None, None, C.c_float(1e-12))
+    assert rc < 0 and b"reward head not set" in pl._lib.bcmpc_last_error(pl._h)
+    with pytest.raises(RuntimeError, match="unknown layout|layout"):
+        L.check(pl._lib.bcmpc_set_dynamics_device(pl._h, (C.c_void_p * 3)(1, 1, 1), (C.c_void_p * 3)(1, 1, 1), 3, 7, None), pl._h)
+    with pytest.raises(RuntimeError, match="tree-search"):                       # tree search: verification mode only
+        Planner(num_paths=4, horizon=2, hidden_size=8, first_proposal="uniform", precision="bf16")
+    three = Planner(20, 6, 3, 40, "relu", num_paths=8, horizon=2)
+    three.set_dynamics(O.synthetic_problem(3, (40, 40, 40))[2])
+    with pytest.raises(RuntimeError, match="n_hidden must be 2"):
+        three.set_reward_head(rweights)
+    with pytest.raises(RuntimeError, match="hidden sizes|hidden size"):          # fast mode: reward model widths 193..256 / 449..512
+        fast = Planner(20, 6, 2, 40, "tanh", num_paths=8, horizon=2, precision="bf16")
+        fast.set_dynamics(weights)
+        fast.set_reward_head(rweights)
+    with pytest.raises(RuntimeError, match="tanh layers"):                       # ... and tanh only
+        fast = Planner(20, 6, 2, 500, "relu", num_paths=8, horizon=2, precision="bf16")
+        fast.set_dynamics(O.synthetic_problem(3, (500, 500))[2])
+        fast.set_reward_head(O.synthetic_reward_problem(3, 500)[3])
+
+
 def test_nan_cost_wins_like_numpy():
     K, H = 64, 2
     rng, norm, state, pl, mpc = make_pair(71, (32, 32), K, H)
