@@ -10,6 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbcmpc.so")
 OBJ = os.path.join(HERE, "_obj")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS += os.environ.get("BCMPC_NVCC_EXTRA", "").split()
 
 
 def sources():

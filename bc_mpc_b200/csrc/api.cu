@@ -459,7 +459,15 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   h->cfg = c;
   if (h->cfg.total_paths <= 0) h->cfg.total_paths = c.path_offset + c.num_paths;
   if (const char* s = getenv("BCMPC_TC_CG")) h->tm_cg = atoi(s) == 2 ? 2 : 1;
-  if (const char* s = getenv("BCMPC_TC_TRACE")) h->trace_path = s;
+  if (const char* s = getenv("BCMPC_TC_TRACE")) {
+#ifdef BCMPC_TRACE
+    h->trace_path = s;
+#else
+    delete h;
+    return fail(nullptr, BCMPC_ERR_UNSUPPORTED, "BCMPC_TC_TRACE is set but this library was built without the pipeline trace: rebuild with "
+                                                "BCMPC_NVCC_EXTRA=-DBCMPC_TRACE python -m bc_mpc_b200._build (developer builds only, ~6%% slower)");
+#endif
+  }
   if (const char* s = getenv("BCMPC_TC_HINT_CHAIN")) h->tm_hint_chain = (uint32_t)strtoul(s, nullptr, 0);
   cudaError_t e = cudaSetDevice(c.device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

@@ -351,15 +351,18 @@ __device__ __forceinline__ void build_input(const TmArgs& a, uint32_t a0_row_add
 
 // the injected randomness of (path, step): the given tensor or a Philox draw.  Uniform shooting: the action itself
 // (controllers.py:53); policy-guided: N(0,1) / U[low,high) / U[-1,1) noise.
+// DBG: the kernel flavour that accepts an injected tensor (and writes the debug outputs); POL: the noise kind depends on
+// the proposal mode at run time - with uniform shooting it is always U[low,high) and the Box-Muller path is not compiled.
+template <bool DBG, bool POL>
 __device__ __forceinline__ void get_noise(const TmArgs& a, int b, int h, int k, float (&z)[kA]) {
   const PlanArgs& p = a.p;
-  if (p.inj) {
+  if (DBG && p.inj) {
     const double* src = p.inj + (((size_t)b * p.H + h) * p.K + k) * kA;
 #pragma unroll
     for (int j = 0; j < kA; ++j) z[j] = (float)src[j];
   } else {
     float v[kMaxAct];
-    draw_injection(v, kA, a.inj_kind, p.seed, (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
+    draw_injection(v, kA, POL ? a.inj_kind : (int)kInjUniformBox, p.seed, (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
 #pragma unroll
     for (int j = 0; j < kA; ++j) z[j] = v[j];
   }
@@ -390,7 +393,11 @@ __device__ __forceinline__ void build_policy_input(const TmArgs& a, uint32_t a0_
 
 // Barrier waits are executed by all 32 lanes of the role warp (measured: ~100 cycles when the phase is already
 // complete; a single elected lane polling while the others park at the reconvergence barrier costs > 1000).
-template <int CG, int NC, int VAR>
+// DBG = true: the flavour used by tests / bcmpc_rollout_debug / bcmpc_predict / injected action tensors - it reads
+// p.inj and writes states_out / actions_out / costs_out.  DBG = false: the production flavour (device-drawn
+// randomness, records only); the same code with those paths compiled out, which is worth ~9 % of the step time
+// (registers, instruction footprint).  BCMPC_TRACE (developer builds, tools/tc_trace.py) adds the pipeline trace.
+template <int CG, int NC, int VAR, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
   constexpr bool POL = (VAR & kVarPolicy) != 0, LN = (VAR & kVarLayerNorm) != 0, REW = (VAR & kVarReward) != 0;
   constexpr int NC2 = hidden2_chunks(NC, VAR);                // hidden-2 chunks (both heads of the learned-reward model)
@@ -454,7 +461,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   // The allocation is the whole TMEM (512 columns), so it starts at lane 0 / column 0; using the literal keeps every
   // TMEM address a compile-time value.
   if (*s_tmem != 0u) { if (tid == 0) printf("bcmpc: unexpected TMEM base 0x%x\n", *s_tmem); __trap(); }
+#ifdef BCMPC_TRACE
   const bool tracing = !REW && a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;   // (the trace slots are laid out for NC2 == NC)
+#else
+  constexpr bool tracing = false;
+#endif
   const uint32_t hc = a.hint_chain;
 
   // Warps 0-3 run their loops warp-uniformly and elect one lane only for the instructions themselves: every
@@ -709,10 +720,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     [[maybe_unused]] float disc = 1.f;          // gamma ** h of the learned-reward objective
     if (is_final) {
 #pragma unroll
-      for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)(p.per_row_states ? kc : b) * kD + d];
-      get_noise(a, b, 0, kc, z);
-      if (p.states_out && valid)
-        for (int d = 0; d < kD; ++d) p.states_out[(size_t)k * kD + d] = (double)s[d];
+      for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)((DBG && p.per_row_states) ? kc : b) * kD + d];
+      get_noise<DBG, POL>(a, b, 0, kc, z);
+      if constexpr (DBG) {
+        if (p.states_out && valid)
+          for (int d = 0; d < kD; ++d) p.states_out[(size_t)k * kD + d] = (double)s[d];
+      }
     }
     for (int h = 0; h < H; ++h) {
       const uint32_t uh = (uint32_t)h;
@@ -787,8 +800,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < kA; ++j) act0[j] = act[j];
         }
-        if (p.actions_out && valid)
-          for (int j = 0; j < kA; ++j) p.actions_out[((size_t)h * p.K + k) * kA + j] = (double)act[j];
+        if constexpr (DBG) {
+          if (p.actions_out && valid)
+            for (int j = 0; j < kA; ++j) p.actions_out[((size_t)h * p.K + k) * kA + j] = (double)act[j];
+        }
         build_input(a, a0_row, row, s, act);
         publish(kEvA0Ready);
         if (trh) a.trace[h * kTraceSlots + kTrFinal + 1] = clock64();
@@ -957,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       }
       // the next step's randomness is drawn between the layer-1 and layer-2 chunks, where these warps have slack (at the
       // top of the step it delays the first layer-1 epilogue, at the bottom the state update)
-      if (is_final && h + 1 < H) get_noise(a, b, h + 1, kc, z);
+      if (is_final && h + 1 < H) get_noise<DBG, POL>(a, b, h + 1, kc, z);
       // layer 2: alternate chunks
       bool first_l2 = true;
       [[maybe_unused]] bool in_reward_head = false;
@@ -1031,13 +1046,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         }
 #pragma unroll
         for (int d = 0; d < kD; ++d) s[d] += delta[d];                       // dynamics.py:116
-        if (p.states_out && valid)
-          for (int d = 0; d < kD; ++d) p.states_out[((size_t)(h + 1) * p.K + k) * kD + d] = (double)s[d];
+        if constexpr (DBG) {
+          if (p.states_out && valid)
+            for (int d = 0; d < kD; ++d) p.states_out[((size_t)(h + 1) * p.K + k) * kD + d] = (double)s[d];
+        }
       }
     }
     if (is_final) {
       // ---- per-tile argmin over the 128 rows (np.argmin order) ----
-      if (p.costs_out && valid) p.costs_out[(size_t)b * p.K + k] = (double)cost;
+      if constexpr (DBG) {
+        if (p.costs_out && valid) p.costs_out[(size_t)b * p.K + k] = (double)cost;
+      }
       double c = (double)cost;
       int64_t idx = valid ? p.path_offset + k : INT64_MAX;
       int src = row;
@@ -1073,11 +1092,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// launch: picks the instantiation for (CTA-group size, hidden chunks)
+// launch: picks the instantiation for (CTA-group size, hidden chunks, variant, flavour)
 // ---------------------------------------------------------------------------------------------------------
-template <int CG, int NC, int VAR>
+template <int CG, int NC, int VAR, bool DBG>
 inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = rollout_tmem_kernel<CG, NC, VAR>;
+  auto kern = rollout_tmem_kernel<CG, NC, VAR, DBG>;
   constexpr Layout L = Lay<CG, NC, VAR>::value;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
@@ -1096,52 +1115,61 @@ inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
-template <int CG, int VAR>
-inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
-  switch (nc) {
-    case 1: return tm_launch_t<CG, 1, VAR>(a, grid, st);
-    case 2: return tm_launch_t<CG, 2, VAR>(a, grid, st);
-    case 3: return tm_launch_t<CG, 3, VAR>(a, grid, st);
-    case 4: return tm_launch_t<CG, 4, VAR>(a, grid, st);
-    case 5: return tm_launch_t<CG, 5, VAR>(a, grid, st);
-    case 6: return tm_launch_t<CG, 6, VAR>(a, grid, st);
-    case 7: return tm_launch_t<CG, 7, VAR>(a, grid, st);
-    case 8: return tm_launch_t<CG, 8, VAR>(a, grid, st);
-  }
-  return cudaErrorInvalidValue;
-}
-// learned-reward and LayerNorm + proposal-network variants: instantiated for 4 and 8 hidden chunks (hidden sizes
-// 193..256 and 449..512; the reference hard-codes 500 for the reward model, dynamics.py:162, and defaults to 500)
-template <int CG, int VAR>
-inline cudaError_t tm_launch_48(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
-  if (nc == 4) return tm_launch_t<CG, 4, VAR>(a, grid, st);
-  // (a single CTA cannot hold the resident images of the 2 x 512 heads AND of a proposal network: tm_prepare reports it)
-  if constexpr (Lay<CG, 8, VAR>::value.nst >= 2) { if (nc == 8) return tm_launch_t<CG, 8, VAR>(a, grid, st); }
-  return cudaErrorInvalidValue;
-}
+// Variants 0..2 (uniform, proposal network, LayerNorm) exist for every width; the combinations - LayerNorm + proposal
+// network and everything with the learned-reward model - for 4 and 8 hidden chunks (hidden sizes 193..256 and
+// 449..512; the reference hard-codes 500 for the reward model, dynamics.py:162, and defaults to 256 / 500 elsewhere).
 inline bool tm_width_supported(int nc, int var) { return var < 3 || nc == 4 || nc == 8; }
+template <int CG, int VAR, bool DBG>
+inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  if constexpr (VAR < 3) {
+    switch (nc) {
+      case 1: return tm_launch_t<CG, 1, VAR, DBG>(a, grid, st);
+      case 2: return tm_launch_t<CG, 2, VAR, DBG>(a, grid, st);
+      case 3: return tm_launch_t<CG, 3, VAR, DBG>(a, grid, st);
+      case 5: return tm_launch_t<CG, 5, VAR, DBG>(a, grid, st);
+      case 6: return tm_launch_t<CG, 6, VAR, DBG>(a, grid, st);
+      case 7: return tm_launch_t<CG, 7, VAR, DBG>(a, grid, st);
+    }
+  }
+  if (nc == 4) return tm_launch_t<CG, 4, VAR, DBG>(a, grid, st);
+  // (a single CTA cannot hold the resident images of the 2 x 512 heads AND of a proposal network: tm_prepare reports it)
+  if constexpr (Lay<CG, 8, VAR>::value.nst >= 2) { if (nc == 8) return tm_launch_t<CG, 8, VAR, DBG>(a, grid, st); }
+  return cudaErrorInvalidValue;
+}
 
-// One translation unit per variant (csrc/tm_var*.cu) so that the ~60 kernel instantiations compile in parallel.
-cudaError_t tm_launch_var0(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // uniform shooting
-cudaError_t tm_launch_var1(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // proposal network
-cudaError_t tm_launch_var2(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // LayerNorm dynamics
-cudaError_t tm_launch_var3(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // LayerNorm + proposal network
-cudaError_t tm_launch_var4(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // learned-reward model
-cudaError_t tm_launch_var5(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // ... + proposal network
-cudaError_t tm_launch_var6(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // learned-reward model with LayerNorm
-cudaError_t tm_launch_var7(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);   // ... + proposal network (what run.sh launches)
-inline cudaError_t tm_launch(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
+// One translation unit per (variant, flavour) - csrc/tm_var*.cu - so that the ~150 kernel instantiations compile in parallel.
+template <int VAR, bool DBG>
+cudaError_t tm_launch_var(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);
+#define BCMPC_TM_DEFINE_VARIANT(VAR, DBG)                                                                        \
+  template <>                                                                                                   \
+  cudaError_t tm_launch_var<VAR, DBG>(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {            \
+    return cg == 2 ? tm_launch_cg<2, VAR, DBG>(nc, a, grid, st) : tm_launch_cg<1, VAR, DBG>(nc, a, grid, st);   \
+  }
+#define BCMPC_TM_DECLARE_VARIANT(VAR)                                                                            \
+  template <> cudaError_t tm_launch_var<VAR, false>(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st); \
+  template <> cudaError_t tm_launch_var<VAR, true>(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);
+BCMPC_TM_DECLARE_VARIANT(0) BCMPC_TM_DECLARE_VARIANT(1) BCMPC_TM_DECLARE_VARIANT(2) BCMPC_TM_DECLARE_VARIANT(3)
+BCMPC_TM_DECLARE_VARIANT(4) BCMPC_TM_DECLARE_VARIANT(5) BCMPC_TM_DECLARE_VARIANT(6) BCMPC_TM_DECLARE_VARIANT(7)
+template <bool DBG>
+inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
   switch (var) {
-    case 0: return tm_launch_var0(cg, nc, a, grid, st);
-    case 1: return tm_launch_var1(cg, nc, a, grid, st);
-    case 2: return tm_launch_var2(cg, nc, a, grid, st);
-    case 3: return tm_launch_var3(cg, nc, a, grid, st);
-    case 4: return tm_launch_var4(cg, nc, a, grid, st);
-    case 5: return tm_launch_var5(cg, nc, a, grid, st);
-    case 6: return tm_launch_var6(cg, nc, a, grid, st);
-    case 7: return tm_launch_var7(cg, nc, a, grid, st);
+    case 0: return tm_launch_var<0, DBG>(cg, nc, a, grid, st);   // uniform shooting
+    case 1: return tm_launch_var<1, DBG>(cg, nc, a, grid, st);   // proposal network
+    case 2: return tm_launch_var<2, DBG>(cg, nc, a, grid, st);   // LayerNorm dynamics
+    case 3: return tm_launch_var<3, DBG>(cg, nc, a, grid, st);   // LayerNorm + proposal network
+    case 4: return tm_launch_var<4, DBG>(cg, nc, a, grid, st);   // learned-reward model
+    case 5: return tm_launch_var<5, DBG>(cg, nc, a, grid, st);   // ... + proposal network
+    case 6: return tm_launch_var<6, DBG>(cg, nc, a, grid, st);   // learned-reward model with LayerNorm
+    case 7: return tm_launch_var<7, DBG>(cg, nc, a, grid, st);   // ... + proposal network (what run.sh launches)
   }
   return cudaErrorInvalidValue;
+}
+// debug flavour iff the call injects randomness, starts every row from its own state or asks for any per-path output
+inline bool tm_needs_debug_flavour(const PlanArgs& p) {
+  return p.inj != nullptr || p.states_out != nullptr || p.actions_out != nullptr || p.costs_out != nullptr || p.per_row_states != 0;
+}
+inline cudaError_t tm_launch(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  return tm_needs_debug_flavour(a.p) ? tm_launch_flavour<true>(cg, nc, var, a, grid, st) : tm_launch_flavour<false>(cg, nc, var, a, grid, st);
 }
 
 }  // namespace tmx

@@ -1,9 +1,9 @@
 // tcgen05 rollout kernel: variant 2 (bit flags: 1 = proposal network, 2 = LayerNorm dynamics, 4 = learned-reward model),
-// production flavour
+// debug flavour (injected randomness, per-path outputs)
 #include "rollout_tmem.cuh"
 
 namespace bcmpc {
 namespace tmx {
-BCMPC_TM_DEFINE_VARIANT(2, false)
+BCMPC_TM_DEFINE_VARIANT(2, true)
 }  // namespace tmx
 }  // namespace bcmpc

@@ -1,6 +1,8 @@
 """Pipeline trace of the tcgen05 rollout kernel (CTA (0,0)): when the MMA warps issued every group, when the epilogue
 groups saw each accumulator chunk, when the per-step state update ran.  Clock = SM cycles (clock64).
-Usage (GPU box): [TRACE_PROPOSAL=policy_gaussian] python tools/tc_trace.py [S]  -> per-step timeline of steps 1 and 2."""
+Usage (GPU box): [TRACE_PROPOSAL=policy_gaussian] python tools/tc_trace.py [S]  -> per-step timeline of steps 1 and 2.
+Needs a developer build of the library: BCMPC_NVCC_EXTRA=-DBCMPC_TRACE python -m bc_mpc_b200._build (the trace code
+costs ~6 % of the step time, so production builds leave it out; rebuild without the flag afterwards)."""
 import os
 import struct
 import sys
