@@ -197,6 +197,40 @@ def test_layer_norm_with_policy_fast_mode_tracks_oracle(S, proposal):
     assert np.abs(so2 - so).max() > 1e-3
 
 
+@pytest.mark.parametrize("variant", ["policy_gaussian", "policy_mix", "bc_uniform", "layer_norm", "layer_norm+policy", "reward", "reward+policy",
+                                     "reward+layer_norm", "reward+layer_norm+policy"])
+def test_production_flavour_equals_debug_flavour(variant):
+    """Every kernel variant has two flavours of the same source: production (device-drawn randomness, records only) and
+    debug (injected tensor, per-path outputs).  A device-sampled plan must equal, bit for bit, the plan replayed from the
+    tensor bcmpc_sample_injection reports for the same seed."""
+    from bc_mpc_b200 import Planner
+    K, H, S, B = 700, 5, 500, 2
+    rew, ln = "reward" in variant, "layer_norm" in variant
+    proposal = variant if variant in ("policy_gaussian", "policy_mix", "bc_uniform") else ("policy_gaussian" if "policy" in variant else "uniform")
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(61, S)
+    if os.environ.get("BCMPC_TC_CG") == "1" and rew and proposal != "uniform":
+        pytest.skip("single-CTA debug mode cannot hold the reward heads and a proposal network")
+    pl = Planner(20, 6, 2, S, "tanh" if rew else "relu", num_paths=K, horizon=H, max_states=B, precision="bf16", proposal=proposal, explore=0.3)
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(3)]
+    if ln:
+        pl.set_layer_norm(lns[:2])
+    if rew:
+        pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], 0.97, layer_norm=lns[2] if ln else None)
+    if proposal == "bc_uniform":
+        pl.set_policy(O.glorot_mlp(rng, (20, 128, 64, 6), 0.05))
+    elif proposal != "uniform":
+        pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
+        pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+    states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((B, 20))
+    prod = pl.plan(states, seed=123)
+    dbg = pl.plan(states, inj=pl.sample_injection(123, B))
+    assert np.array_equal(prod["index"], dbg["index"]) and np.array_equal(prod["cost"], dbg["cost"])
+    assert np.array_equal(prod["action"], dbg["action"])
+    assert not np.array_equal(pl.plan(states, seed=124)["action"], prod["action"])
+
+
 def test_fast_mode_sampling_batching_sharding_are_bit_consistent():
     import torch
     from bc_mpc_b200 import _lib as L
