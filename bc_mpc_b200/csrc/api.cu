@@ -335,7 +335,6 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.lnvec = h->d_lnvec;
     if (P.layer_norm && fabsf(h->rew.desc.ln_eps - h->ln_eps) > 0.f)
       return fail(h, BCMPC_ERR_INVALID, "bf16 fast path: the three LayerNorms of the reward model must share one epsilon");
-    a.act_tanh = h->cfg.activation == BCMPC_ACT_TANH ? 1 : 0;
     a.mean_reward = (float)h->mean_reward; a.std_reward = (float)h->std_reward; a.gamma = (float)h->gamma;
   }
   if (P.layer_norm) {

@@ -182,7 +182,7 @@ struct TmArgs {
   const float* lnvec;            // [u2 (64*nc)][c2 (64*nc)] correction vectors of layer 2, [u3 (32)][c3 (32)] of the output layer
   float ln_inv_n, ln_eps;        // 1 / hidden_size, variance epsilon
   // learned-reward model: lnvec = [b2 of the delta head (64 * nc)][b2 of the reward head (64 * nc)][b3: 20 deltas, reward, 0...]
-  int act_tanh;                  // hidden activation: 1 = tanh (dynamics.py:162), 0 = ReLU
+  // (its hidden activation is tanh, dynamics.py:162; other activations run in verification mode)
   float mean_reward, std_reward, gamma;
 };
 // pipeline trace of CTA (0,0), steps 0..3: [2 per L1 pair][2 per L2 chunk][2 per L3 chunk][4 per epilogue chunk][final 8][2 per stage]
@@ -915,7 +915,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       };
       // learned-reward model: the hidden "ones" units that carry the biases of layers 2 / 3 through a ReLU do not
       // survive a tanh, so those biases are added here (layer 1 keeps its bias in the GEMM: its ones are INPUT columns);
-      // activation = tanh (tanh.approx.bf16x2 on the rounded pair, as in the proposal network) or ReLU
+      // activation = tanh (tanh.approx.bf16x2 on the rounded pair, as in the proposal network)
       [[maybe_unused]] const float* s_b2 = reinterpret_cast<const float*>(smem + L.off_ln);
       [[maybe_unused]] auto chunk_bias = [&](uint32_t e, uint32_t col, uint32_t dst, uint32_t ready_id, int wait_a2, const float* bias) {
         uint32_t v0[32], v1[32], w0[16], w1[16];
@@ -926,10 +926,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         __syncwarp();
         if (lane == 0) arrive_leader(kEvDEmpty + e);
         const float4* b4 = reinterpret_cast<const float4*>(bias);
-        auto act2 = [&](float x, float y) {
-          if (a.act_tanh) return ptx::tanh_bf16x2(pack_bf16(x, y));
-          return pack_relu_bf16(x, y);
-        };
+        auto act2 = [&](float x, float y) { return ptx::tanh_bf16x2(pack_bf16(x, y)); };
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
