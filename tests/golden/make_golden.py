@@ -11,6 +11,11 @@ Files:
   vars_ppo_mpc.npz    the trained dynamics + policy weights of
                       saved_data/ppo-mpc/vars.pkl (data fixture) and a reference-run
                       plan on them
+  mpc_reward.npz      the learned-reward and tree-search planners: MPCcontrollerReward
+                      (controllers.py:90-158), MPCcontrollerPolicyNetReward (:289-363),
+                      MCTScontrollerPolicyNetReward (:365-457) run by the reference on an
+                      oracle NNDynamicsRewardModel (with its three LayerNorms in one case)
+                      (python tests/golden/make_golden.py reward  regenerates only this file)
 """
 import os
 import pickle
@@ -76,7 +81,56 @@ def ref_rollout_costs(dyn, state, actions):
     return allst, costs
 
 
+def reward_and_tree():
+    out = {}
+    seed, S = 11, 64
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(seed, S)
+    lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(3)]
+    pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(32, 32), norm=norm)
+    pol = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
+    H, K, N, R = 5, 120, 40, 3
+    actions = rng.uniform(-1, 1, (H, K, 6)).astype(np.float32).astype(np.float64)
+    eps = rng.standard_normal((H, K, 6)).astype(np.float32)
+    first_uni = rng.uniform(-1, 1, (N, 6)).astype(np.float32).astype(np.float64)
+    first_eps = rng.standard_normal((N, 6)).astype(np.float32)
+    out.update(seed=seed, hidden=S, state=state, actions=actions, eps=eps, first_uni=first_uni, first_eps=first_eps,
+               ln_gamma=np.stack([g for g, _ in lns]), ln_beta=np.stack([b for _, b in lns]), N=N, R=R)
+    for tag, dyn in (("plain", O.OracleRewardDynamics(weights, rweights, norm)),
+                     ("ln", O.OracleRewardDynamics(weights, rweights, norm, layer_norm=lns[:2], reward_layer_norm=lns[2]))):
+        for gamma in (1.0, 0.9):
+            c = ref_controllers.MPCcontrollerReward(FakeEnv(), dyn, horizon=H, num_simulated_paths=K, gamma=gamma)
+            c.sample_random_actions = lambda: actions
+            out[f"{tag}_uniform_g{gamma}_first_action"] = c.get_action(state)
+        # the per-path objective of controllers.py:131-153 re-executed for gamma = 0.9
+        st, tot = np.tile(state, [K, 1]), 0.0
+        for i in range(H):
+            st, r = dyn.predict(st, actions[i])
+            tot = tot + r * 0.9 ** i
+        out[f"{tag}_uniform_g0.9_rewards"] = np.reshape(tot, [-1])
+        c = ref_controllers.MPCcontrollerPolicyNetReward(FakeEnv(), dyn, _InjectedPolicy(pol, eps), explore=0.4, self_exp=False,
+                                                         horizon=H, num_simulated_paths=K, gamma=0.5)
+        c.sample_random_actions = lambda: actions
+        out[f"{tag}_mix_first_action"] = c.get_action(state)
+        c = ref_controllers.MPCcontrollerPolicyNetReward(FakeEnv(), dyn, _InjectedPolicy(pol, eps), explore=0.4, self_exp=True,
+                                                         horizon=H, num_simulated_paths=K)
+        out[f"{tag}_selfexp_first_action"] = c.get_action(state)
+        # tree search: first stage uniform / stochastic policy
+        env = FakeEnv()
+        draws = iter(first_uni)
+        env.action_space.sample = lambda: next(draws)
+        c = ref_controllers.MCTScontrollerPolicyNetReward(env, dyn, _InjectedPolicy(pol, None), horizon=H, num_first_stage_actions=N,
+                                                          random_path_per_action=R, random_first_stage_action=True)
+        out[f"{tag}_tree_uniform_action"] = c.get_action(state)
+        c = ref_controllers.MCTScontrollerPolicyNetReward(FakeEnv(), dyn, _InjectedPolicy(pol, first_eps[:, None, :]), self_exp=True, horizon=H,
+                                                          num_first_stage_actions=N, random_path_per_action=R)
+        out[f"{tag}_tree_selfexp_action"] = c.get_action(state)
+    np.savez_compressed(os.path.join(HERE, "mpc_reward.npz"), **out)
+    print("mpc_reward.npz", os.path.getsize(os.path.join(HERE, "mpc_reward.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "reward":
+        return reward_and_tree()
     # ---- cost KATs -------------------------------------------------
     rng = np.random.default_rng(1234)
     S = rng.standard_normal((64, 20)) * 0.3
@@ -161,6 +215,7 @@ def main():
     fx["plan_costs"] = costs
     fx["plan_states"] = allst
     np.savez_compressed(os.path.join(HERE, "vars_ppo_mpc.npz"), **fx)
+    reward_and_tree()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -149,6 +149,53 @@ def test_layer_norm_dynamics_variant():
         make_pair(17, (64, 64), 128, 2, precision="bf16", proposal="policy_mix")[3].set_layer_norm([(g[:64], b[:64]) for g, b in ln])
 
 
+@pytest.mark.parametrize("tag", ["plain", "ln"])
+def test_golden_reward_and_tree_search_plans(golden_dir, tag):
+    """tests/golden/mpc_reward.npz: first actions chosen by the REFERENCE's MPCcontrollerReward,
+    MPCcontrollerPolicyNetReward and MCTScontrollerPolicyNetReward; the drop-in classes must choose the same."""
+    from bc_mpc_b200 import controllers, dynamics, policy
+    from tests.test_oracle_golden import _reward_fixture
+
+    class Space:
+        def __init__(self, n):
+            self.low, self.high, self.shape = -np.ones(n), np.ones(n), (n,)
+
+    class Env:
+        action_space, observation_space = Space(6), Space(20)
+
+    g, odyn, opol, state = _reward_fixture(golden_dir, tag)
+    S, ln = int(g["hidden"]), tag == "ln"
+    H, K = g["actions"].shape[:2]
+    N, R = int(g["N"]), int(g["R"])
+    n10 = (odyn.mean_obs, odyn.std_obs, odyn.mean_action, odyn.std_action, odyn.mean_reward, odyn.std_reward, None, None,
+           odyn.mean_deltas, odyn.std_deltas)
+    dm = dynamics.NNDynamicsRewardModel(Env(), n10, size=S, layer_norm=ln)
+    lns = [(g["ln_gamma"][i], g["ln_beta"][i]) for i in range(3)]
+    dm.set_weights(odyn.weights, odyn.reward_weights, lns[:2] if ln else None, lns[2] if ln else None)
+    pol = policy.MlpPolicy(None, Env(), 32, 2)
+    pol.set_weights(opol.weights, opol.logstd, opol.rms_mean, opol.rms_std)
+    for gamma in (1.0, 0.9):
+        c = controllers.MPCcontrollerReward(Env(), dm, horizon=H, num_simulated_paths=K, gamma=gamma)
+        c.sample_random_actions = lambda: g["actions"]
+        assert np.array_equal(c.get_action(state), g[f"{tag}_uniform_g{gamma}_first_action"])
+        if gamma == 0.9:
+            _, _, co = c._planner.rollout_debug(state, g["actions"])
+            assert np.abs(-co - g[f"{tag}_uniform_g0.9_rewards"]).max() < 1e-3
+    c = controllers.MPCcontrollerPolicyNetReward(Env(), dm, pol, explore=0.4, self_exp=False, horizon=H, num_simulated_paths=K, gamma=0.5)
+    c.sample_random_actions = lambda: g["actions"]
+    assert np.allclose(c.get_action(state), g[f"{tag}_mix_first_action"], rtol=1e-5, atol=1e-6)
+    c = controllers.MPCcontrollerPolicyNetReward(Env(), dm, pol, explore=0.4, self_exp=True, horizon=H, num_simulated_paths=K)
+    c._ensure_planner()
+    rec = c._planner.plan(state, inj=g["eps"].astype(np.float64))[0]           # the stochastic branch with the reference's own eps
+    assert np.allclose(rec["action"][:6], g[f"{tag}_selfexp_first_action"], rtol=1e-5, atol=1e-6)
+    for mode, z, key in (("uniform", g["first_uni"], "tree_uniform_action"), ("policy_gaussian", g["first_eps"], "tree_selfexp_action")):
+        t = controllers.MCTScontrollerPolicyNetReward(Env(), dm, pol, self_exp=mode == "policy_gaussian", horizon=H, num_first_stage_actions=N,
+                                                      random_path_per_action=R, random_first_stage_action=mode == "uniform")
+        t.sample_first_stage = lambda z=z: np.asarray(z, np.float64)
+        got = t.get_action(state)
+        assert got.shape == (1, 6) and np.allclose(got, g[f"{tag}_{key}"], rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("proposal,gamma,ln", [("uniform", 0.9, False), ("uniform", 1.0, False), ("policy_mix", 1.0, False),
                                                ("uniform", 0.9, True), ("policy_gaussian", 1.0, True)])
 def test_learned_reward_planners(proposal, gamma, ln):

@@ -3,6 +3,7 @@ controllers.py / cost_functions.py (tests/golden/make_golden.py)."""
 import os
 
 import numpy as np
+import pytest
 
 from oracle import mpc_oracle as O
 
@@ -64,6 +65,42 @@ def test_policy_plans(golden_dir):
     a = O.OracleMPC(dyn, H, K, proposal="policy_mix", policy=pol, explore=float(g["explore"])).get_action(
         state, g["uni"])
     assert np.array_equal(a, g["mix_first_action"])
+
+
+def _reward_fixture(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "mpc_reward.npz"))
+    S = int(g["hidden"])
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(int(g["seed"]), S)
+    lns = [(g["ln_gamma"][i], g["ln_beta"][i]) for i in range(3)]
+    for _ in range(3):      # the generator drew the LayerNorm parameters before the policy: keep the stream aligned
+        rng.standard_normal(S), rng.standard_normal(S)
+    pol = O.OraclePolicy(*O.synthetic_policy(rng, hidden=(32, 32), norm=norm))
+    dyn = (O.OracleRewardDynamics(weights, rweights, norm) if tag == "plain" else
+           O.OracleRewardDynamics(weights, rweights, norm, layer_norm=lns[:2], reward_layer_norm=lns[2]))
+    assert np.array_equal(state, g["state"])
+    return g, dyn, pol, state
+
+
+@pytest.mark.parametrize("tag", ["plain", "ln"])
+def test_reward_and_tree_search_plans(golden_dir, tag):
+    """mpc_reward.npz: the reference's MPCcontrollerReward / MPCcontrollerPolicyNetReward / MCTScontrollerPolicyNetReward
+    (controllers.py:90-158, 289-363, 365-457) run on the oracle reward model."""
+    g, dyn, pol, state = _reward_fixture(golden_dir, tag)
+    H, K = g["actions"].shape[:2]
+    N, R = int(g["N"]), int(g["R"])
+    for gamma in (1.0, 0.9):
+        a, dbg = O.OracleMPC(dyn, H, K, learned_reward=True, gamma=gamma).get_action(state, g["actions"], return_debug=True)
+        assert np.array_equal(a, g[f"{tag}_uniform_g{gamma}_first_action"])
+        if gamma == 0.9:
+            assert np.allclose(-dbg["costs"], g[f"{tag}_uniform_g0.9_rewards"], rtol=1e-12, atol=1e-12)
+    a = O.OracleMPC(dyn, H, K, proposal="policy_mix", policy=pol, explore=0.4, learned_reward=True).get_action(state, g["actions"])
+    assert np.array_equal(a, g[f"{tag}_mix_first_action"])
+    a = O.OracleMPC(dyn, H, K, proposal="policy_gaussian", policy=pol, learned_reward=True).get_action(state, g["eps"])
+    assert np.array_equal(a, g[f"{tag}_selfexp_first_action"])
+    a = O.OracleMCTS(dyn, pol, H, N, R, "uniform").get_action(state, g["first_uni"])
+    assert np.array_equal(a, g[f"{tag}_tree_uniform_action"])
+    a = O.OracleMCTS(dyn, pol, H, N, R, "policy_gaussian").get_action(state, g["first_eps"])
+    assert np.array_equal(a, g[f"{tag}_tree_selfexp_action"])
 
 
 def test_trained_weights_plan(golden_dir):
