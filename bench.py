@@ -47,47 +47,91 @@ def hbm_peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6550.0   # fallback: B200_PROFILING.md
 
 
+_NVML_POLLER = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+        nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+while True:
+    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, *[int(bool(r & b)) for b in bits], flush=True)
+    time.sleep(0.01)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  The sampler runs from
-    before the warm-up (nvidia-smi needs a few hundred ms to start); only rows that arrive inside a marked region count."""
+    """SM clock and throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  A helper PROCESS polls NVML
+    every ~10 ms (faster polling measurably slows the host-buffer calls: NVML and the CUDA driver share locks) (nvidia_ml_py: the counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; a thread in
+    this process would take the GIL from the timed host-buffer calls); `nvidia-smi -lms` is the fallback.  Only samples
+    that arrive inside a marked region count."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self.regions, self._t0 = index, [], None, [], None
+        self.index, self.rows, self.proc, self.regions, self._t0, self.source = index, [], None, [], None, None
+        self.log = None        # the poller writes to a file that is parsed after the run: nothing of it runs in this process
 
     def start(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml  # noqa: F401
+            import tempfile
+            self.log = tempfile.NamedTemporaryFile("w+", prefix="bcmpc_clocks_", suffix=".txt", delete=False)
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_POLLER, str(phys)], stdout=self.log,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvml"
         except Exception:
-            self.proc = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={phys}", f"--query-gpu={self.Q}",
+                                              "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi"
+            except Exception:
+                self.proc = None
+        if self.proc is not None and self.source == "nvidia-smi":
+            threading.Thread(target=self._read, daemon=True).start()
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def wait_ready(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < timeout:
+            if self.rows or (self.log is not None and os.path.getsize(self.log.name) > 0):
+                return
+            time.sleep(0.01)
 
     def begin(self):
-        self._t0 = time.perf_counter()
+        self._t0 = time.time()
 
     def end(self):
-        self.regions.append((self._t0, time.perf_counter()))
+        self.regions.append((self._t0, time.time()))
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         time.sleep(0.05)
         self.proc.terminate()
-        inside = [r for t, r in self.rows if any(a - 0.02 <= t <= b + 0.02 for a, b in self.regions)]
+        if self.log is not None:
+            self.proc.wait()
+            for line in open(self.log.name):
+                f = line.split()
+                if len(f) == 7:
+                    self.rows.append((float(f[0]), [f[1], f[2]] + ["Active" if x == "1" else "Not Active" for x in f[3:]]))
+            os.unlink(self.log.name)
+        inside = [r for t, r in self.rows if any(a <= t <= b for a, b in self.regions)]
         rows = inside if inside else [r for _, r in self.rows]
         sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "samples_inside_timed_regions": len(inside)}
+        reasons = sorted({self.NAMES[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "samples_inside_timed_regions": len(inside), "source": self.source}
 
 
 def problem():
@@ -318,8 +362,12 @@ def run_ours(args):
         return sp.plan_device(d_states, B, seed=1000 + i)
 
     def step_e2e(i):
+        if world == 1:
+            # the reference-facing call itself: bcmpc_plan with HOST buffers (numpy in, numpy records out); the library
+            # stages through its pinned buffers, copies host -> device, plans, copies the records back and synchronises
+            return sp.planner.plan(states, seed=2000 + i)
         d_states.copy_(h_states, non_blocking=True)                      # pinned host -> device, every step
-        out = sp.plan_device(d_states, B, seed=2000 + i)
+        out = sp.plan_device(d_states, B, seed=2000 + i)                  # rollout + NCCL all-gather + min-loc
         h_out.copy_(out, non_blocking=True)                               # device -> host read of the winners
         stream.synchronize()
         return h_out
@@ -349,6 +397,8 @@ def run_ours(args):
     for i in range(args.warmup):
         step_resident(i)
         step_e2e(i)
+    if rank == 0:
+        clocks.wait_ready()               # the poller has produced its first sample before the timed regions start
     barrier()
     # ---- resident-input throughput (value) + kernel-only duration for the roofline ----
     pl.enable_timing(True)
