@@ -39,6 +39,7 @@ SIGNATURES = {
     "bcmpc_destroy": (C.c_int, [_P]),
     "bcmpc_set_dynamics": (C.c_int, [_P, _PP, _PP, C.c_int32]),
     "bcmpc_set_dynamics_device": (C.c_int, [_P, _PP, _PP, C.c_int32, C.c_int32, _P]),
+    "bcmpc_set_policy_device": (C.c_int, [_P, C.c_int32, _P, _PP, _PP, C.c_int32, _P, _P, _P, C.c_float, _P]),
     "bcmpc_set_layer_norm": (C.c_int, [_P, _PP, _PP, C.c_int32, C.c_float]),
     "bcmpc_set_reward_head": (C.c_int, [_P, _PP, _PP, C.c_double, C.c_double, C.c_double]),
     "bcmpc_set_reward_layer_norm": (C.c_int, [_P, _P, _P, C.c_float]),

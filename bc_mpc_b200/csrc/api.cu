@@ -65,6 +65,7 @@ struct bcmpc_handle {
   // tcgen05 path (rollout_tmem.cuh)
   tmx::TmHostPlan tmp;
   uint8_t *d_res = nullptr, *d_stream = nullptr, *d_pol = nullptr;
+  float* d_polvec = nullptr;      // biases of the proposal network for the fast kernel
   float* d_lnvec = nullptr;
   size_t res_cap = 0, stream_cap = 0, lnvec_cap = 0;
   bool ln_on = false;     // LayerNorm parameters uploaded (ln_bufs / dyn.desc.ln_*), both precision modes
@@ -126,18 +127,18 @@ int upload_mlp(bcmpc_handle* h, DeviceMlp& m, int n_layers, const int* sizes, co
   return BCMPC_OK;
 }
 
-// The dynamics network keeps ONE set of zero-padded float32 device buffers for the lifetime of the handle (its shape is
-// fixed by bcmpc_config), so a weight refresh is a strided copy - from the host or from device memory - on `st`.
+// Weight refresh into persistent zero-padded float32 device buffers: a strided copy - from the host or from device
+// memory - on `st`; the buffers are (re)allocated only when the layer shapes change (the dynamics shape is fixed by
+// bcmpc_config, a proposal network keeps its shape between PPO / BC updates).
 // kind: cudaMemcpyHostToDevice ([in,out] host arrays), cudaMemcpyDeviceToDevice ([in,out] device arrays), or -1 for
 // device arrays in torch.nn.Linear layout [out,in] (transposed by a small kernel).
-int refresh_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int kind, cudaStream_t st) {
-  DeviceMlp& m = h->dyn;
-  const int n_layers = h->cfg.n_hidden + 1;
-  int sizes[kMaxLayers + 1];
-  sizes[0] = h->cfg.obs_dim + h->cfg.act_dim;
-  for (int l = 1; l <= h->cfg.n_hidden; ++l) sizes[l] = h->cfg.hidden_size;
-  sizes[n_layers] = h->cfg.obs_dim;
-  if (m.bufs.empty()) {
+int refresh_mlp(bcmpc_handle* h, DeviceMlp& m, int n_layers, const int* sizes, const float* const* W, const float* const* b, int kind,
+                cudaStream_t st) {
+  bool same = m.set && m.desc.n_layers == n_layers && (int)m.bufs.size() == 2 * n_layers;
+  for (int l = 0; l < n_layers && same; ++l) same = m.desc.in_dim[l] == sizes[l] && m.desc.out_dim[l] == sizes[l + 1];
+  if (!same) {
+    CK(h, cudaDeviceSynchronize());     // nothing may still read the old buffers
+    m.release();
     m.desc = MlpDesc{};
     m.desc.n_layers = n_layers;
     for (int l = 0; l < n_layers; ++l) {
@@ -167,10 +168,20 @@ int refresh_dynamics(bcmpc_handle* h, const float* const* W, const float* const*
       CK(h, cudaMemcpyAsync(const_cast<float*>(m.desc.b[l]), b[l], row, (cudaMemcpyKind)kind, st));
     }
   }
-  // new weights reset LayerNorm: call bcmpc_set_layer_norm again (the parameters belong to the same checkpoint)
-  for (int l = 0; l < kMaxLayers; ++l) m.desc.ln_gamma[l] = m.desc.ln_beta[l] = nullptr;
-  h->ln_on = false;
+  for (int l = 0; l < kMaxLayers; ++l) m.desc.ln_gamma[l] = m.desc.ln_beta[l] = nullptr;   // LayerNorm parameters belong to one checkpoint
   m.set = true;
+  return BCMPC_OK;
+}
+
+int refresh_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int kind, cudaStream_t st) {
+  const int n_layers = h->cfg.n_hidden + 1;
+  int sizes[kMaxLayers + 1];
+  sizes[0] = h->cfg.obs_dim + h->cfg.act_dim;
+  for (int l = 1; l <= h->cfg.n_hidden; ++l) sizes[l] = h->cfg.hidden_size;
+  sizes[n_layers] = h->cfg.obs_dim;
+  int rc = refresh_mlp(h, h->dyn, n_layers, sizes, W, b, kind, st);
+  if (rc) return rc;
+  h->ln_on = false;     // new weights reset LayerNorm: call bcmpc_set_layer_norm again
   return BCMPC_OK;
 }
 
@@ -256,9 +267,8 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   const int S = h->cfg.hidden_size;
   const tmx::TmHostPlan old = h->tmp;
   tmx::tm_geometry(S, h->tm_cg, tm_variant(h), &h->tmp);
-  if (old.with_policy) {   // the proposal network survives a dynamics refresh
-    h->tmp.with_policy = true; h->tmp.np1 = old.np1; h->tmp.np2 = old.np2; h->tmp.pol = old.pol;
-    memcpy(h->tmp.bp1, old.bp1, sizeof old.bp1); memcpy(h->tmp.bp2, old.bp2, sizeof old.bp2); memcpy(h->tmp.bp3, old.bp3, sizeof old.bp3);
+  if (old.with_policy) {   // the proposal network (its own device images) survives a dynamics refresh
+    h->tmp.with_policy = true; h->tmp.np1 = old.np1; h->tmp.np2 = old.np2;
   }
   const tmx::TmHostPlan& P = h->tmp;
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
@@ -348,7 +358,7 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.explore = (float)h->cfg.explore; a.one_minus_explore = (float)(1.0 - h->cfg.explore);
     for (int d = 0; d < h->cfg.obs_dim; ++d) { a.filt_mean[d] = h->filt_mean[d]; a.filt_inv_std[d] = 1.0f / h->filt_std[d]; }
     for (int j = 0; j < h->cfg.act_dim; ++j) a.pol_std[j] = h->pol_std[j];
-    memcpy(a.bp1, P.bp1, sizeof a.bp1); memcpy(a.bp2, P.bp2, sizeof a.bp2); memcpy(a.bp3, P.bp3, sizeof a.bp3);
+    a.polvec = h->d_polvec;
   }
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
@@ -497,7 +507,7 @@ int bcmpc_destroy(bcmpc_handle* h) {
   for (float* p : h->ln_bufs) cudaFree(p);
   cudaFree(h->rew_ln_buf);
   cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
-  cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_lnvec); cudaFree(h->d_trace);
+  cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_polvec); cudaFree(h->d_lnvec); cudaFree(h->d_trace);
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_records) cudaFreeHost(h->h_records);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -666,19 +676,25 @@ int bcmpc_set_action_bounds(bcmpc_handle* h, const double* low, const double* hi
   return BCMPC_OK;
 }
 
-int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* W,
-                     const float* const* b, const float* logstd, const float* filt_mean, const float* filt_std,
-                     float clip) {
+namespace {
+int set_policy_common(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* W, const float* const* b,
+                      const float* logstd, const float* filt_mean, const float* filt_std, float clip, int kind, cudaStream_t st) {
   if (!h || !sizes || !W || !b) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_layers < 1 || n_layers > kMaxLayers) return fail(h, BCMPC_ERR_INVALID, "n_layers %d out of [1,%d]", n_layers, kMaxLayers);
   if (sizes[0] != h->cfg.obs_dim || sizes[n_layers] != h->cfg.act_dim)
     return fail(h, BCMPC_ERR_INVALID, "policy sizes must start with obs_dim and end with act_dim");
   for (int l = 0; l <= n_layers; ++l)
     if (sizes[l] < 1 || sizes[l] > 1536) return fail(h, BCMPC_ERR_INVALID, "policy layer size %d out of range", sizes[l]);
+  for (int l = 0; l < n_layers; ++l)
+    if (!W[l] || !b[l]) return fail(h, BCMPC_ERR_INVALID, "null weight pointer for policy layer %d", l);
   if ((filt_mean == nullptr) != (filt_std == nullptr)) return fail(h, BCMPC_ERR_INVALID, "filt_mean and filt_std must be given together");
+  const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST && h->cfg.proposal != BCMPC_PROP_UNIFORM;
+  if (fast) {
+    std::string why;
+    if (!tmx::tm_policy_supported(n_layers, sizes, &why)) return fail(h, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
+  }
   CK(h, cudaSetDevice(h->cfg.device));
-  CK(h, cudaStreamSynchronize(h->stream));
-  int rc = upload_mlp(h, h->pol, n_layers, sizes, W, b);
+  int rc = refresh_mlp(h, h->pol, n_layers, sizes, W, b, kind, st);
   if (rc) return rc;
   h->has_filter = filt_mean != nullptr;
   for (int d = 0; d < h->cfg.obs_dim; ++d) {
@@ -689,20 +705,51 @@ int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, co
   h->has_logstd = logstd != nullptr;
   for (int j = 0; j < h->cfg.act_dim; ++j) h->pol_std[j] = logstd ? expf(logstd[j]) : 0.f;   // distributions.py:65
   update_verify_geometry(h);
-  if (h->cfg.precision == BCMPC_PREC_BF16_FAST && h->cfg.proposal != BCMPC_PROP_UNIFORM) {
-    std::string why;
-    if (!tmx::tm_policy_supported(n_layers, sizes, &why)) return fail(h, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
-    if (h->tmp.cg == 0 || h->tmp.lay.blk_h == 0) {   // layout depends only on (pair mode, hidden chunks): fix it now if the dynamics come later
-      h->tmp.cg = h->tm_cg;
-      h->tmp.nc = (h->cfg.hidden_size + 2 + 63) / 64;
-      h->tmp.lay = tmx::make_layout(h->tm_cg, h->tmp.nc, tmx::kVarPolicy);
-    }
-    tmx::tm_build_policy(sizes, W, b, &h->tmp);
-    if (h->d_pol) cudaFree(h->d_pol);
-    h->d_pol = nullptr;
-    CK(h, cudaMalloc(&h->d_pol, h->tmp.pol.size() * 2));
-    CK(h, cudaMemcpy(h->d_pol, h->tmp.pol.data(), h->tmp.pol.size() * 2, cudaMemcpyHostToDevice));
+  if (fast) {
+    // the image layout depends only on the CTA-group size: it can be packed before the dynamics weights arrive
+    const tmx::Layout lay = tmx::make_layout(h->tm_cg, 1, tmx::kVarPolicy);
+    const size_t img_total = (size_t)h->tm_cg * lay.pol_img_bytes;
+    if (!h->d_pol) CK(h, cudaMalloc(&h->d_pol, img_total));
+    if (!h->d_polvec) CK(h, cudaMalloc(&h->d_polvec, tmx::kPolVecFloats * sizeof(float)));
+    tmx::PolicyPackArgs a{};
+    const MlpDesc& d = h->pol.desc;
+    for (int l = 0; l < 3; ++l) { a.W[l] = d.W[l]; a.b[l] = d.b[l]; a.ld[l] = d.out_pad[l]; }
+    a.h1 = sizes[1]; a.h2 = sizes[2]; a.cg = h->tm_cg;
+    a.blk_h = lay.blk_h; a.blk_o = lay.blk_o; a.img_bytes = lay.pol_img_bytes;
+    a.img = reinterpret_cast<uint16_t*>(h->d_pol); a.vec = h->d_polvec;
+    CK(h, tmx::tm_pack_policy(a, st));
+    h->launches++;
+    h->tmp.with_policy = true;
+    h->tmp.np1 = (sizes[1] + 63) / 64; h->tmp.np2 = (sizes[2] + 63) / 64;
   }
+  return BCMPC_OK;
+}
+}  // namespace
+
+int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* W,
+                     const float* const* b, const float* logstd, const float* filt_mean, const float* filt_std,
+                     float clip) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  int rc = set_policy_common(h, n_layers, sizes, W, b, logstd, filt_mean, filt_std, clip, cudaMemcpyHostToDevice, h->stream);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return BCMPC_OK;
+}
+
+int bcmpc_set_policy_device(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* dW, const float* const* db,
+                            int32_t layout, const float* logstd, const float* filt_mean, const float* filt_std, float clip,
+                            void* stream) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (layout != BCMPC_LAYOUT_IN_OUT && layout != BCMPC_LAYOUT_OUT_IN) return fail(h, BCMPC_ERR_INVALID, "unknown layout %d", layout);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  int rc = set_policy_common(h, n_layers, sizes, dW, db, logstd, filt_mean, filt_std, clip,
+                             layout == BCMPC_LAYOUT_OUT_IN ? -1 : (int)cudaMemcpyDeviceToDevice, st);
+  if (rc) return rc;
+  if (!h->ev_weights) CK(h, cudaEventCreateWithFlags(&h->ev_weights, cudaEventDisableTiming));
+  CK(h, cudaEventRecord(h->ev_weights, st));
+  h->weights_pending = true;
   return BCMPC_OK;
 }
 

@@ -99,6 +99,7 @@ constexpr int kMaxChunks1 = 8, kMaxChunks2 = 16;    // hidden-1 chunks; hidden-2
 // misc smem: [w_full 16][w_empty 16][res_full][events 100] x 8 B, tmem ptr, argmin scratch
 constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, kOffTmemPtr = 1072, kOffRed = 1088, kMiscBytes = 1280;
 constexpr int kPolMaxHidden = 128;     // proposal network: two tanh layers of at most 128 units (MlpPolicy hid_size=128, BCnetwork 128/64)
+constexpr int kPolVecFloats = 2 * 128 + 8 + 248;   // [bp1 (128)][bp2 (128)][bp3 (8)], padded to 2 KB
 
 // ---------------------------------------------------------------------------------------------------------
 // The per-step schedule is fixed arithmetic, the same for every step (all accumulators are drained at a step boundary):
@@ -119,6 +120,7 @@ struct Layout {
   int kbs = 0, nstg = 0, nst = 0;
   int nst_r[2] = {0, 0}, first_r[2] = {0, 0};     // the ring is split in two: even layer-2 chunks / odd layer-2 chunks, one per MMA issuer
   uint32_t blk_h = 0, blk_o = 0, w1_bytes = 0, res_bytes = 0, stage_bytes = 0;
+  uint32_t pol_img_bytes = 0;
   uint32_t off_a0 = 0, off_res = 0, off_pol = 0, pol_bytes = 0, off_ln = 0, ln_bytes = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
 };
 // kernel variants (bit flags): policy-guided shooting, LayerNorm dynamics net, learned-reward model
@@ -141,7 +143,8 @@ constexpr Layout make_layout(int cg, int nc, int var) {
   L.off_res = kA0Bytes;
   L.off_pol = (L.off_res + L.res_bytes + 1023u) / 1024u * 1024u;
   // resident proposal network (sized for 128/128 hidden units): [Wp1: 2 chunks][Wp2: 2 chunks x 2 k-blocks][Wp3: 2 k-blocks]
-  L.pol_bytes = pol ? 6u * L.blk_h + 2u * L.blk_o : 0u;
+  L.pol_img_bytes = pol ? 6u * L.blk_h + 2u * L.blk_o : 0u;
+  L.pol_bytes = pol ? L.pol_img_bytes + kPolVecFloats * 4u : 0u;    // + biases of the three layers (float32, from device memory)
   // LayerNorm variant: per-column correction vectors of layer 2 (u2, c2: 2 x 64*nc floats) + per-row statistics
   L.off_ln = (L.off_pol + L.pol_bytes + 1023u) / 1024u * 1024u;
   // LayerNorm: [u2 (64 nc2)][c2 (64 nc2)][u3 (32)][c3 (32)] correction vectors + per-row statistics
@@ -177,7 +180,7 @@ struct TmArgs {
   int proposal, inj_kind, has_filter;
   float clip, explore, one_minus_explore;
   float filt_mean[kMaxObs], filt_inv_std[kMaxObs], pol_std[kMaxAct];
-  float bp1[kPolMaxHidden], bp2[kPolMaxHidden], bp3[kMaxAct];
+  const float* polvec;           // [bp1 (128)][bp2 (128)][bp3 (8)] biases of the proposal network (device; staged into shared memory)
   // LayerNorm variant (dynamics.py:68-69): z = rho * acc - rho * mu * u + c per column, rho / mu per row
   const float* lnvec;            // [u2 (64*nc)][c2 (64*nc)] correction vectors of layer 2, [u3 (32)][c3 (32)] of the output layer
   float ln_inv_n, ln_eps;        // 1 / hidden_size, variance epsilon
@@ -211,13 +214,11 @@ __host__ __device__ inline size_t sw128_offset(int n, int kk) {
 }
 
 struct TmHostPlan {
-  std::vector<uint16_t> pol;
   size_t res_total = 0, stream_total = 0, lnvec_floats = 0;     // bytes / bytes / floats of the device images
   bool layer_norm = false, reward = false;
   int cg = 1, s_pad = 0, nc = 0, nc2 = 0, hidden = 0;
   bool with_policy = false;
   int np1 = 0, np2 = 0;
-  float bp1[kPolMaxHidden] = {}, bp2[kPolMaxHidden] = {}, bp3[kMaxAct] = {};
   Layout lay;
 };
 
@@ -236,46 +237,6 @@ inline bool tm_policy_supported(int n_layers, const int* sizes, std::string* why
   if (sizes[1] < 1 || sizes[1] > kPolMaxHidden || sizes[2] < 1 || sizes[2] > kPolMaxHidden) { *why = "bf16 fast path: proposal network hidden sizes must be <= 128"; return false; }
   return true;
 }
-inline void tm_build_policy(const int* sizes, const float* const* W, const float* const* b, TmHostPlan* plan) {
-  TmHostPlan& P = *plan;
-  const int cg = P.cg, h1 = sizes[1], h2 = sizes[2];
-  P.np1 = (h1 + 63) / 64; P.np2 = (h2 + 63) / 64;
-  const int rows_h = kChunk / cg, rows_o = kOutN / cg;
-  const uint32_t blk_h = P.lay.blk_h, blk_o = P.lay.blk_o, pol_bytes = 6u * blk_h + 2u * blk_o;
-  P.pol.assign((size_t)cg * pol_bytes / 2, 0);
-  for (int r = 0; r < cg; ++r) {
-    const size_t rb = (size_t)r * pol_bytes;
-    for (int j = 0; j < P.np1; ++j)                                  // Wp1 chunk j: [64 units x 64 k (20 used)]
-      for (int i = 0; i < rows_h; ++i) {
-        const int n = j * kChunk + r * rows_h + i;
-        if (n >= h1) continue;
-        for (int k = 0; k < kD; ++k) P.pol[(rb + (size_t)j * blk_h + sw128_offset(i, k)) / 2] = f32_to_bf16(W[0][(size_t)k * h1 + n]);
-      }
-    for (int j = 0; j < P.np2; ++j)                                  // Wp2 chunk j, k-block kb
-      for (int kb = 0; kb < P.np1; ++kb)
-        for (int i = 0; i < rows_h; ++i) {
-          const int n = j * kChunk + r * rows_h + i;
-          if (n >= h2) continue;
-          for (int kk = 0; kk < 64; ++kk) {
-            const int k = kb * 64 + kk;
-            if (k < h1) P.pol[(rb + (size_t)(2 + j * 2 + kb) * blk_h + sw128_offset(i, kk)) / 2] = f32_to_bf16(W[1][(size_t)k * h2 + n]);
-          }
-        }
-    for (int kb = 0; kb < P.np2; ++kb)                               // Wp3 k-block kb: [32 outputs (6 used) x 64 k]
-      for (int i = 0; i < rows_o; ++i) {
-        const int n = r * rows_o + i;
-        if (n >= kA) continue;
-        for (int kk = 0; kk < 64; ++kk) {
-          const int k = kb * 64 + kk;
-          if (k < h2) P.pol[(rb + 6u * blk_h + (size_t)kb * blk_o + sw128_offset(i, kk)) / 2] = f32_to_bf16(W[2][(size_t)k * kA + n]);
-        }
-      }
-  }
-  for (int i = 0; i < kPolMaxHidden; ++i) { P.bp1[i] = i < h1 ? b[0][i] : 0.f; P.bp2[i] = i < h2 ? b[1][i] : 0.f; }
-  for (int i = 0; i < kMaxAct; ++i) P.bp3[i] = i < kA ? b[2][i] : 0.f;
-  P.with_policy = true;
-}
-
 // Dynamics weight images.  W[l] are TF kernels [in,out] (row stride ld): W1 [26,S], W2 [S,S], W3 [S,20].
 // Bias-in-GEMM: input columns 26,27 of A0 are 1.0; hidden units S and S+1 of both hidden layers are wired to be
 // exactly 1.0 after ReLU; row S / S+1 of the next layer's kernel hold bf16(b) and bf16(b - bf16(b)).
@@ -444,6 +405,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     ptx::mbar_init(ev + 8u * kEvPolFull, 1);
     ptx::fence_mbar_init();
   }
+  if constexpr (POL) {
+    float* s_pv = reinterpret_cast<float*>(smem + L.off_pol + L.pol_img_bytes);
+    for (int i = tid; i < 2 * kPolMaxHidden + kMaxAct; i += kThreads) s_pv[i] = a.polvec[i];
+  }
   if constexpr (REW && !LN) {      // biases of the two heads: [b2 (64 * NC2)][b3 (32)]
     float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
     for (int i = tid; i < 64 * NC2 + kOutN; i += kThreads) s_vec[i] = a.lnvec[i];
@@ -475,13 +440,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     // ===================== weight producer (every CTA loads its own half) =====================
     if (ptx::elect_one()) {
       const uint8_t* src = a.res + (size_t)rank * L.res_bytes;
-      ptx::mbar_arrive_expect_tx(misc + kOffResFull, L.res_bytes + L.pol_bytes);
+      ptx::mbar_arrive_expect_tx(misc + kOffResFull, L.res_bytes + L.pol_img_bytes);
       for (uint32_t o = 0; o < L.res_bytes; o += 16384u)
         ptx::bulk_g2s(base + L.off_res + o, src + o, min(16384u, L.res_bytes - o), misc + kOffResFull);
       if constexpr (POL) {
-        const uint8_t* psrc = a.pol + (size_t)rank * L.pol_bytes;
-        for (uint32_t o = 0; o < L.pol_bytes; o += 16384u)
-          ptx::bulk_g2s(base + L.off_pol + o, psrc + o, min(16384u, L.pol_bytes - o), misc + kOffResFull);
+        const uint8_t* psrc = a.pol + (size_t)rank * L.pol_img_bytes;
+        for (uint32_t o = 0; o < L.pol_img_bytes; o += 16384u)
+          ptx::bulk_g2s(base + L.off_pol + o, psrc + o, min(16384u, L.pol_img_bytes - o), misc + kOffResFull);
       }
     }
     __syncwarp();
@@ -750,7 +715,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           ptx::tmem_ld32(lane_off + col, v0);
           ptx::tmem_ld32(lane_off + col + 32u, v1);
           ptx::tmem_ld_wait();
-          auto bias_at = [&](int idx) { if constexpr (layer == 1) return a.bp1[idx]; else return a.bp2[idx]; };
+          const float* s_pv = reinterpret_cast<const float*>(smem + L.off_pol + L.pol_img_bytes) + (layer == 1 ? 0 : kPolMaxHidden);
+          auto bias_at = [&](int idx) { return s_pv[idx]; };
           // bias, round to bf16, then one MUFU.TANH per two units (tanh.approx.bf16x2): the layer is MUFU-bound otherwise
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -783,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           ptx::tc_fence_before();
 #pragma unroll
           for (int j = 0; j < kA; ++j) {
-            const float mean = __uint_as_float(v[j]) + a.bp3[j];
+            const float mean = __uint_as_float(v[j]) + reinterpret_cast<const float*>(smem + L.off_pol + L.pol_img_bytes)[2 * kPolMaxHidden + j];
             if (a.proposal == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
             else if (a.proposal == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
             else act[j] = mean + z[j];                                                                                   // controllers.pyc (BC + U[-1,1))

@@ -171,6 +171,28 @@ class Planner:
         self._ck(self._lib.bcmpc_set_policy(self._h, len(Ws), L.ptr(sizes), L.ptr_array(Ws), L.ptr_array(bs),
                                             L.ptr(ls), L.ptr(fm), L.ptr(fs), float(clip or 0.0)))
 
+    def set_policy_device(self, weights, logstd=None, filt_mean=None, filt_std=None, clip=0.0, layout="in_out", stream_ptr=None):
+        """Proposal-network hand-off without a host round trip (bcmpc_set_policy_device): weights = [(W, b), ...] float32
+        CUDA tensors, W [in,out] (layout="in_out") or [out,in] (layout="out_in", torch.nn.Linear.weight); logstd and the
+        observation-filter statistics are small host arrays.  Enqueued on stream_ptr (None = the handle's stream)."""
+        if layout not in ("in_out", "out_in"):
+            raise ValueError("layout must be 'in_out' or 'out_in'")
+        dims = [(tuple(w.shape) if layout == "in_out" else tuple(w.shape)[::-1]) for w, _ in weights]
+        sizes = np.array([dims[0][0]] + [d[1] for d in dims], np.int32)
+        for i, (w, b) in enumerate(weights):
+            if dims[i] != (sizes[i], sizes[i + 1]) or tuple(b.shape) != (sizes[i + 1],):
+                raise ValueError(f"policy layer {i}: inconsistent shapes {tuple(w.shape)} / {tuple(b.shape)}")
+            for t in (w, b):
+                if not t.is_contiguous() or "float32" not in str(t.dtype) or not t.is_cuda:
+                    raise ValueError(f"policy layer {i}: tensors must be contiguous float32 CUDA tensors")
+        ls = None if logstd is None else np.ascontiguousarray(logstd, np.float32).reshape(-1)
+        fm = None if filt_mean is None else np.ascontiguousarray(filt_mean, np.float32).reshape(-1)
+        fs = None if filt_std is None else np.ascontiguousarray(filt_std, np.float32).reshape(-1)
+        Wp = (C.c_void_p * len(weights))(*[w.data_ptr() for w, _ in weights])
+        bp = (C.c_void_p * len(weights))(*[b.data_ptr() for _, b in weights])
+        self._ck(self._lib.bcmpc_set_policy_device(self._h, len(weights), L.ptr(sizes), Wp, bp, 0 if layout == "in_out" else 1,
+                                                   L.ptr(ls), L.ptr(fm), L.ptr(fs), float(clip or 0.0), _stream(stream_ptr)))
+
     # -- the hot path -----------------------------------------------------------------------------
     def plan(self, states, inj=None, seed=0):
         """get_action for B root states (host buffers).  Returns a structured array [B] of

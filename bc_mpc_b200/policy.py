@@ -22,10 +22,25 @@ class _ProposalNet:
         self.ob_dim = env.observation_space.shape[0]
         self.ac_dim = env.action_space.shape[0]
         self.weights = None
+        self.device_weights = None      # (tensors, layout, stream_ptr) after set_weights_device
         self.version = 0
         self._fwd = None
 
+    def set_weights_device(self, tensors, logstd=None, filt_mean=None, filt_std=None, layout="out_in", stream_ptr=None):
+        """Hand-off from a trainer that keeps the policy parameters on the planner's GPU (PPO / BC updates in PyTorch):
+        tensors = [(W, b), ...] float32 CUDA tensors ("out_in" = torch.nn.Linear.weight, "in_out" = TF kernels); logstd
+        and the observation-filter statistics are small host arrays."""
+        self.device_weights = (list(tensors), layout, stream_ptr)
+        self.weights = None
+        if logstd is not None:
+            self.logstd = np.asarray(logstd, np.float32).reshape(-1)
+        if filt_mean is not None:
+            self.filt_mean, self.filt_std = np.asarray(filt_mean, np.float32), np.asarray(filt_std, np.float32)
+        self.version += 1
+        self._fwd = None
+
     def set_weights(self, weights, logstd=None, filt_mean=None, filt_std=None):
+        self.device_weights = None
         self.weights = [(np.asarray(w, np.float32), np.asarray(b, np.float32)) for w, b in weights]
         if logstd is not None:
             self.logstd = np.asarray(logstd, np.float32).reshape(-1)
@@ -35,11 +50,15 @@ class _ProposalNet:
         self._fwd = None
 
     def upload(self, planner):
+        if self.device_weights is not None:
+            tensors, layout, stream_ptr = self.device_weights
+            planner.set_policy_device(tensors, self.logstd, self.filt_mean, self.filt_std, self.clip, layout=layout, stream_ptr=stream_ptr)
+            return
         planner.set_policy(self.weights, self.logstd, self.filt_mean, self.filt_std, self.clip)
 
     def _forward(self, ob, noise=None):
-        if self.weights is None:
-            raise RuntimeError("proposal network has no weights (set_weights / load_vars)")
+        if self.weights is None and self.device_weights is None:
+            raise RuntimeError("proposal network has no weights (set_weights / set_weights_device / load_vars)")
         if self._fwd is None:
             p = Planner(self.ob_dim, self.ac_dim, 1, 4, num_paths=1, horizon=1)
             self.upload(p)

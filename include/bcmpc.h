@@ -161,6 +161,15 @@ int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, co
                      const float* const* b, const float* logstd, const float* filt_mean,
                      const float* filt_std, float clip);
 
+/* The same hand-off after a PPO / BC update (ppo_bc_policy.py:135-151, train_mpc_ppo.py:355-364) when the trainer's
+ * parameters live on this GPU: dW[i] / db[i] are DEVICE pointers (float32, contiguous, layout as in
+ * bcmpc_set_dynamics_device); copy and re-pack are enqueued on `stream` (NULL = the handle's) and later plans on any
+ * stream are ordered after them.  logstd, filt_mean, filt_std (a few floats the host-side RunningMeanStd / optimiser
+ * own) stay HOST pointers. */
+int bcmpc_set_policy_device(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* dW,
+                            const float* const* db, int32_t layout, const float* logstd, const float* filt_mean,
+                            const float* filt_std, float clip, void* stream);
+
 /* MPCcontroller.get_action / MPCcontrollerPolicyNet.get_action (controllers.py:57-88,189-237)
  * for B root states at once, HOST buffers.  states [B,D]; inj [B,H,K,A] or NULL (NULL = sample
  * on the device with Philox4x32-10 keyed by seed and the global path index).  out [B]. */

@@ -350,3 +350,37 @@ def test_device_weight_handoff_matches_host_upload(precision):
         dm.set_weights(ws)
         np.random.seed(3)
         assert np.array_equal(a_dev, c.get_action(state))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_device_policy_handoff_matches_host_upload(precision):
+    """bcmpc_set_policy_device: the proposal network refreshed from torch CUDA tensors (TF or nn.Linear layout) plans
+    bit-identically to the host upload, also when enqueued on another stream behind other work."""
+    import torch
+    K, H = 512, 5
+    rng, norm, state, host, mpc = make_pair(71, (500, 500), K, H, precision=precision, proposal="policy_gaussian")
+    pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 96), norm=norm)
+    pw2, logstd2, _, _ = O.synthetic_policy(rng, hidden=(128, 96), norm=norm)
+    host.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+    want1 = host.rollout_debug(state, seed=4)
+    host.set_policy(pw2, logstd2, rms_mean, rms_std, clip=5.0)
+    want2 = host.rollout_debug(state, seed=4)
+    assert not np.array_equal(want1[1], want2[1])
+    dev = torch.device("cuda:0")
+    side = torch.cuda.Stream()
+    for layout in ("in_out", "out_in"):
+        def tensors(ws):
+            return [(torch.from_numpy(w if layout == "in_out" else np.ascontiguousarray(w.T)).to(dev), torch.from_numpy(b).to(dev)) for w, b in ws]
+        t1, t2 = tensors(pw), tensors(pw2)
+        torch.cuda.synchronize()
+        _, _, _, pl, _ = make_pair(71, (500, 500), K, H, precision=precision, proposal="policy_gaussian")
+        pl.set_policy_device(t1, logstd, rms_mean, rms_std, clip=5.0, layout=layout)
+        got1 = pl.rollout_debug(state, seed=4)
+        with torch.cuda.stream(side):
+            junk = torch.randn(4096, 4096, device=dev) @ torch.randn(4096, 4096, device=dev)
+            pl.set_policy_device(t2, logstd2, rms_mean, rms_std, clip=5.0, layout=layout, stream_ptr=side.cuda_stream)
+        got2 = pl.rollout_debug(state, seed=4)
+        del junk
+        for a, b in zip(want1 + want2, got1 + got2):
+            assert np.array_equal(a, b)
+        assert pl.plan(state, seed=8)[0]["cost"] == host.plan(state, seed=8)[0]["cost"]
