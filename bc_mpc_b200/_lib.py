@@ -43,6 +43,9 @@ SIGNATURES = {
     "bcmpc_set_layer_norm": (C.c_int, [_P, _PP, _PP, C.c_int32, C.c_float]),
     "bcmpc_set_reward_head": (C.c_int, [_P, _PP, _PP, C.c_double, C.c_double, C.c_double]),
     "bcmpc_set_reward_layer_norm": (C.c_int, [_P, _P, _P, C.c_float]),
+    "bcmpc_set_layer_norm_device": (C.c_int, [_P, _PP, _PP, C.c_int32, C.c_float, _P]),
+    "bcmpc_set_reward_head_device": (C.c_int, [_P, _PP, _PP, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
+    "bcmpc_set_reward_layer_norm_device": (C.c_int, [_P, _P, _P, C.c_float, _P]),
     "bcmpc_predict_reward": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "bcmpc_set_normalization": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "bcmpc_set_action_bounds": (C.c_int, [_P, _P, _P]),

@@ -100,33 +100,6 @@ int fail(bcmpc_handle* h, int code, const char* fmt, ...) {
 
 int round4(int x) { return (x + 3) / 4 * 4; }
 
-// Uploads an MLP as zero-padded [in_pad][out_pad] float32 kernels + [out_pad] biases.
-int upload_mlp(bcmpc_handle* h, DeviceMlp& m, int n_layers, const int* sizes, const float* const* W,
-               const float* const* b) {
-  m.release();
-  m.desc = MlpDesc{};
-  m.desc.n_layers = n_layers;
-  for (int l = 0; l < n_layers; ++l) {
-    const int in = sizes[l], out = sizes[l + 1];
-    const int ip = round4(in), op = round4(out);
-    m.desc.in_dim[l] = in; m.desc.out_dim[l] = out; m.desc.in_pad[l] = ip; m.desc.out_pad[l] = op;
-    std::vector<float> w((size_t)ip * op, 0.f), bb(op, 0.f);
-    for (int i = 0; i < in; ++i) memcpy(&w[(size_t)i * op], W[l] + (size_t)i * out, sizeof(float) * out);
-    memcpy(bb.data(), b[l], sizeof(float) * out);
-    float *dw = nullptr, *db = nullptr;
-    CK(h, cudaMalloc(&dw, w.size() * sizeof(float)));
-    m.bufs.push_back(dw);
-    CK(h, cudaMalloc(&db, bb.size() * sizeof(float)));
-    m.bufs.push_back(db);
-    CK(h, cudaMemcpy(dw, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(db, bb.data(), bb.size() * sizeof(float), cudaMemcpyHostToDevice));
-    m.desc.W[l] = dw;
-    m.desc.b[l] = db;
-  }
-  m.set = true;
-  return BCMPC_OK;
-}
-
 // Weight refresh into persistent zero-padded float32 device buffers: a strided copy - from the host or from device
 // memory - on `st`; the buffers are (re)allocated only when the layer shapes change (the dynamics shape is fixed by
 // bcmpc_config, a proposal network keeps its shape between PPO / BC updates).
@@ -556,8 +529,18 @@ int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const flo
   return BCMPC_OK;
 }
 
-int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps) {
-  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+namespace {
+// host (kind = cudaMemcpyHostToDevice, synchronous) and device (cudaMemcpyDeviceToDevice, enqueued on st) variants share these
+int after_handoff(bcmpc_handle* h, bool device, cudaStream_t st) {
+  if (!device) { CK(h, cudaStreamSynchronize(st)); return BCMPC_OK; }
+  if (!h->ev_weights) CK(h, cudaEventCreateWithFlags(&h->ev_weights, cudaEventDisableTiming));
+  CK(h, cudaEventRecord(h->ev_weights, st));
+  h->weights_pending = true;
+  return BCMPC_OK;
+}
+
+int set_layer_norm_common(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps, bool device,
+                          cudaStream_t st) {
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
   if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
@@ -565,86 +548,120 @@ int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float
   for (int l = 0; l < n_hidden && gamma; ++l)
     if (!gamma[l] || !beta[l]) return fail(h, BCMPC_ERR_INVALID, "null LayerNorm pointer for layer %d", l);
   CK(h, cudaSetDevice(h->cfg.device));
-  CK(h, cudaDeviceSynchronize());      // plans and hand-offs on any stream have finished with the old parameters
-  for (float* p : h->ln_bufs) cudaFree(p);
-  h->ln_bufs.clear();
+  if (!device) CK(h, cudaDeviceSynchronize());      // plans and hand-offs on any stream have finished with the old parameters
+  const size_t n = (size_t)h->cfg.hidden_size;
+  if (gamma && h->ln_bufs.empty())                   // persistent: [gamma, beta] per hidden layer
+    for (int l = 0; l < 2 * h->cfg.n_hidden; ++l) {
+      float* p = nullptr;
+      CK(h, cudaMalloc(&p, sizeof(float) * n));
+      h->ln_bufs.push_back(p);
+    }
   for (int l = 0; l < kMaxLayers; ++l) h->dyn.desc.ln_gamma[l] = h->dyn.desc.ln_beta[l] = nullptr;
   h->ln_on = gamma != nullptr;
   h->ln_eps = eps;
+  const cudaMemcpyKind kind = device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   for (int l = 0; l < n_hidden && gamma; ++l) {
-    float *dg = nullptr, *db = nullptr;
-    CK(h, cudaMalloc(&dg, sizeof(float) * h->cfg.hidden_size)); h->ln_bufs.push_back(dg);
-    CK(h, cudaMalloc(&db, sizeof(float) * h->cfg.hidden_size)); h->ln_bufs.push_back(db);
-    CK(h, cudaMemcpy(dg, gamma[l], sizeof(float) * h->cfg.hidden_size, cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(db, beta[l], sizeof(float) * h->cfg.hidden_size, cudaMemcpyHostToDevice));
-    h->dyn.desc.ln_gamma[l] = dg;
-    h->dyn.desc.ln_beta[l] = db;
+    CK(h, cudaMemcpyAsync(h->ln_bufs[2 * l], gamma[l], sizeof(float) * n, kind, st));
+    CK(h, cudaMemcpyAsync(h->ln_bufs[2 * l + 1], beta[l], sizeof(float) * n, kind, st));
+    h->dyn.desc.ln_gamma[l] = h->ln_bufs[2 * l];
+    h->dyn.desc.ln_beta[l] = h->ln_bufs[2 * l + 1];
   }
   h->dyn.desc.ln_eps = eps;
   if (fast) {
-    int rc = tm_prepare(h, h->stream);
+    int rc = tm_prepare(h, st);
     if (rc) return rc;
-    CK(h, cudaStreamSynchronize(h->stream));
   }
-  return BCMPC_OK;
+  return after_handoff(h, device, st);
 }
 
-int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward,
-                          double std_reward, double gamma) {
-  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+int set_reward_head_common(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward, double std_reward,
+                           double gamma, int kind, bool device, cudaStream_t st) {
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
   if (fast && !h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the reward head");
   CK(h, cudaSetDevice(h->cfg.device));
-  CK(h, cudaDeviceSynchronize());
+  if (!device) CK(h, cudaDeviceSynchronize());
   if (!W) {
+    CK(h, cudaDeviceSynchronize());
     h->rew.release();
     h->rew_ln_on = false;
     update_verify_geometry(h);
-    if (fast) { int rc = tm_prepare(h, h->stream); if (rc) return rc; CK(h, cudaStreamSynchronize(h->stream)); }
-    return BCMPC_OK;
+    if (fast) { int rc = tm_prepare(h, st); if (rc) return rc; }
+    return after_handoff(h, device, st);
   }
   if (!b || !W[0] || !W[1] || !b[0] || !b[1]) return fail(h, BCMPC_ERR_INVALID, "null reward-head pointer");
   if (fast && h->cfg.activation != BCMPC_ACT_TANH)
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the learned-reward model is built with tanh layers (dynamics.py:162); other activations run in BCMPC_PREC_FP32_VERIFY");
   if (h->cfg.n_hidden != 2) return fail(h, BCMPC_ERR_INVALID, "NNDynamicsRewardModel has a shared layer and one hidden layer per head: n_hidden must be 2");
   const int sizes[3] = {h->cfg.hidden_size, h->cfg.hidden_size, 1};
-  int rc = upload_mlp(h, h->rew, 2, sizes, W, b);
+  int rc = refresh_mlp(h, h->rew, 2, sizes, W, b, kind, st);
   if (rc) return rc;
-  h->rew_ln_on = false;        // (upload_mlp cleared the descriptor's LayerNorm pointers)
+  h->rew_ln_on = false;        // (a new head resets its LayerNorm, like new dynamics weights do)
   h->mean_reward = mean_reward; h->std_reward = std_reward; h->gamma = gamma;
   update_verify_geometry(h);
   if (fast) {
-    rc = tm_prepare(h, h->stream);
-    if (rc) { h->rew.release(); update_verify_geometry(h); return rc; }
-    CK(h, cudaStreamSynchronize(h->stream));
+    rc = tm_prepare(h, st);
+    if (rc) { cudaDeviceSynchronize(); h->rew.release(); update_verify_geometry(h); return rc; }
   }
-  return BCMPC_OK;
+  return after_handoff(h, device, st);
 }
 
-int bcmpc_set_reward_layer_norm(bcmpc_handle* h, const float* gamma, const float* beta, float eps) {
-  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+int set_reward_layer_norm_common(bcmpc_handle* h, const float* gamma, const float* beta, float eps, bool device, cudaStream_t st) {
   if (!h->rew.set) return fail(h, BCMPC_ERR_STATE, "reward head not set (bcmpc_set_reward_head)");
   if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
   CK(h, cudaSetDevice(h->cfg.device));
-  CK(h, cudaDeviceSynchronize());
+  if (!device) CK(h, cudaDeviceSynchronize());
   const size_t n = (size_t)h->cfg.hidden_size;
   h->rew.desc.ln_gamma[0] = h->rew.desc.ln_beta[0] = nullptr;
   h->rew_ln_on = gamma != nullptr;
   if (gamma) {
+    const cudaMemcpyKind kind = device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (!h->rew_ln_buf) CK(h, cudaMalloc(&h->rew_ln_buf, 2 * n * sizeof(float)));
-    CK(h, cudaMemcpy(h->rew_ln_buf, gamma, n * sizeof(float), cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(h->rew_ln_buf + n, beta, n * sizeof(float), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpyAsync(h->rew_ln_buf, gamma, n * sizeof(float), kind, st));
+    CK(h, cudaMemcpyAsync(h->rew_ln_buf + n, beta, n * sizeof(float), kind, st));
     h->rew.desc.ln_gamma[0] = h->rew_ln_buf;
     h->rew.desc.ln_beta[0] = h->rew_ln_buf + n;
     h->rew.desc.ln_eps = eps;
   }
   if (fast) {
-    int rc = tm_prepare(h, h->stream);
+    int rc = tm_prepare(h, st);
     if (rc) return rc;
-    CK(h, cudaStreamSynchronize(h->stream));
   }
-  return BCMPC_OK;
+  return after_handoff(h, device, st);
+}
+cudaStream_t pick_stream(bcmpc_handle* h, void* stream) { return stream ? (cudaStream_t)stream : h->stream; }
+}  // namespace
+
+int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  return set_layer_norm_common(h, gamma, beta, n_hidden, eps, false, h->stream);
+}
+int bcmpc_set_layer_norm_device(bcmpc_handle* h, const float* const* d_gamma, const float* const* d_beta, int32_t n_hidden, float eps,
+                                void* stream) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  return set_layer_norm_common(h, d_gamma, d_beta, n_hidden, eps, true, pick_stream(h, stream));
+}
+
+int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward,
+                          double std_reward, double gamma) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  return set_reward_head_common(h, W, b, mean_reward, std_reward, gamma, cudaMemcpyHostToDevice, false, h->stream);
+}
+int bcmpc_set_reward_head_device(bcmpc_handle* h, const float* const* dW, const float* const* db, int32_t layout, double mean_reward,
+                                 double std_reward, double gamma, void* stream) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (layout != BCMPC_LAYOUT_IN_OUT && layout != BCMPC_LAYOUT_OUT_IN) return fail(h, BCMPC_ERR_INVALID, "unknown layout %d", layout);
+  return set_reward_head_common(h, dW, db, mean_reward, std_reward, gamma, layout == BCMPC_LAYOUT_OUT_IN ? -1 : (int)cudaMemcpyDeviceToDevice,
+                                true, pick_stream(h, stream));
+}
+
+int bcmpc_set_reward_layer_norm(bcmpc_handle* h, const float* gamma, const float* beta, float eps) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  return set_reward_layer_norm_common(h, gamma, beta, eps, false, h->stream);
+}
+int bcmpc_set_reward_layer_norm_device(bcmpc_handle* h, const float* d_gamma, const float* d_beta, float eps, void* stream) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  return set_reward_layer_norm_common(h, d_gamma, d_beta, eps, true, pick_stream(h, stream));
 }
 
 int bcmpc_set_normalization(bcmpc_handle* h, const double* mean_obs, const double* std_obs, const double* mean_act,

@@ -42,13 +42,15 @@ class NNDynamicsModel:
         self.version += 1
         self._predictor = None
 
-    def set_weights_device(self, tensors, layout="out_in", stream_ptr=None):
+    def set_weights_device(self, tensors, layout="out_in", stream_ptr=None, layer_norm_tensors=None):
         """Hand-off from a trainer that keeps the parameters on the planner's GPU (what replaces sess.run + fit when
         the dynamics model is trained in PyTorch): tensors = [(W, b), ...] float32 CUDA tensors, layout "out_in"
-        (torch.nn.Linear.weight) or "in_out" (TF kernels).  No host copy is made; controllers and predict() pick the
-        tensors up through Planner.set_dynamics_device on stream_ptr."""
-        if self.layer_norm:
-            raise NotImplementedError("device hand-off of LayerNorm parameters: use set_weights")
+        (torch.nn.Linear.weight) or "in_out" (TF kernels); layer_norm_tensors = [(gamma, beta), ...] CUDA tensors when
+        the model has LayerNorm.  No host copy is made; controllers and predict() pick the tensors up through
+        Planner.set_dynamics_device / set_layer_norm_device on stream_ptr."""
+        if self.layer_norm and layer_norm_tensors is None:
+            raise ValueError("this model was built with layer_norm=True: pass layer_norm_tensors=[(gamma, beta), ...]")
+        self.device_layer_norm = list(layer_norm_tensors) if self.layer_norm else None
         self.device_weights = (list(tensors), layout, stream_ptr)
         self.weights = None
         self.version += 1
@@ -59,6 +61,8 @@ class NNDynamicsModel:
         if self.device_weights is not None:
             tensors, layout, stream_ptr = self.device_weights
             planner.set_dynamics_device(tensors, layout=layout, stream_ptr=stream_ptr)
+            if self.layer_norm:
+                planner.set_layer_norm_device(self.device_layer_norm, stream_ptr=stream_ptr)
             return
         if self.weights is None:
             raise RuntimeError("NNDynamicsModel has no weights (set_weights / set_weights_device / load_vars)")
@@ -130,13 +134,30 @@ class NNDynamicsRewardModel(NNDynamicsModel):
                   for n in ("LayerNorm", "LayerNorm_1", "LayerNorm_2")]
         self.set_weights(ws[:3], ws[3:], ln[:2] if ln else None, ln[2] if ln else None)
 
+    def set_weights_device(self, tensors, reward_tensors, layout="out_in", stream_ptr=None, layer_norm_tensors=None,
+                           reward_layer_norm_tensors=None):
+        """Device hand-off of the whole reward model: tensors = share / delta-hidden / delta-out, reward_tensors =
+        reward-hidden / reward-out [(W, b)] float32 CUDA tensors; with layer_norm=True also the (gamma, beta) tensors of
+        share + delta-hidden (layer_norm_tensors) and of reward-hidden (reward_layer_norm_tensors)."""
+        if self.layer_norm and reward_layer_norm_tensors is None:
+            raise ValueError("this model was built with layer_norm=True: pass reward_layer_norm_tensors=(gamma, beta)")
+        self.device_reward = (list(reward_tensors), reward_layer_norm_tensors if self.layer_norm else None)
+        self.reward_weights = None
+        super().set_weights_device(tensors, layout=layout, stream_ptr=stream_ptr, layer_norm_tensors=layer_norm_tensors)
+
     def upload_reward_head(self, planner, gamma=1.0):
+        if self.device_weights is not None:
+            _, layout, stream_ptr = self.device_weights
+            rt, rln = self.device_reward
+            planner.set_reward_head_device(rt, float(np.asarray(self.mean_reward)), float(np.asarray(self.std_reward)), gamma,
+                                           layer_norm=rln, layout=layout, stream_ptr=stream_ptr)
+            return
         planner.set_reward_head(self.reward_weights, float(np.asarray(self.mean_reward)), float(np.asarray(self.std_reward)), gamma,
                                 layer_norm=self.reward_layer_norm if self.layer_norm else None)
 
     def predict(self, unnormalized_state, unnormalized_action):
-        if self.weights is None:
-            raise RuntimeError("NNDynamicsRewardModel has no weights (set_weights / load_vars)")
+        if self.weights is None and self.device_weights is None:
+            raise RuntimeError("NNDynamicsRewardModel has no weights (set_weights / set_weights_device / load_vars)")
         if self._predictor is None:
             p = Planner(self.obs_dim, self.act_dim, 2, self.size, self.activation, num_paths=1, horizon=1, precision="fp32")
             self.upload(p)

@@ -117,6 +117,40 @@ class Planner:
                 raise ValueError(f"LayerNorm gamma/beta must be [{self.cfg.hidden_size}]")
         self._ck(self._lib.bcmpc_set_layer_norm(self._h, L.ptr_array(gs), L.ptr_array(bs), len(gs), C.c_float(eps)))
 
+    @staticmethod
+    def _check_cuda_f32(t, shape, what):
+        if tuple(t.shape) != tuple(shape) or not t.is_contiguous() or "float32" not in str(t.dtype) or not t.is_cuda:
+            raise ValueError(f"{what}: expected a contiguous float32 CUDA tensor of shape {tuple(shape)}, got {tuple(t.shape)}")
+
+    def set_layer_norm_device(self, params, eps=1e-12, stream_ptr=None):
+        """set_layer_norm with [(gamma, beta), ...] float32 CUDA tensors, enqueued on stream_ptr (bcmpc_set_layer_norm_device)."""
+        S = self.cfg.hidden_size
+        for g, b in params:
+            self._check_cuda_f32(g, (S,), "LayerNorm gamma")
+            self._check_cuda_f32(b, (S,), "LayerNorm beta")
+        gp = (C.c_void_p * len(params))(*[g.data_ptr() for g, _ in params])
+        bp = (C.c_void_p * len(params))(*[b.data_ptr() for _, b in params])
+        self._ck(self._lib.bcmpc_set_layer_norm_device(self._h, gp, bp, len(params), C.c_float(eps), _stream(stream_ptr)))
+
+    def set_reward_head_device(self, weights, mean_reward=0.0, std_reward=1.0, gamma=1.0, layer_norm=None, eps=1e-12, layout="in_out",
+                               stream_ptr=None):
+        """set_reward_head with float32 CUDA tensors ([(W[S,S], b[S]), (W[S,1], b[1])], or [out,in] kernels with
+        layout="out_in"; layer_norm = (gamma, beta) tensors), enqueued on stream_ptr."""
+        S = self.cfg.hidden_size
+        shapes = [(S, S), (S, 1)] if layout == "in_out" else [(S, S), (1, S)]
+        for (w, b), ws, bs in zip(weights, shapes, [(S,), (1,)]):
+            self._check_cuda_f32(w, ws, "reward-head kernel")
+            self._check_cuda_f32(b, bs, "reward-head bias")
+        Wp = (C.c_void_p * 2)(*[w.data_ptr() for w, _ in weights])
+        bp = (C.c_void_p * 2)(*[b.data_ptr() for _, b in weights])
+        self._ck(self._lib.bcmpc_set_reward_head_device(self._h, Wp, bp, 0 if layout == "in_out" else 1, float(mean_reward),
+                                                        float(std_reward), float(gamma), _stream(stream_ptr)))
+        if layer_norm is not None:
+            self._check_cuda_f32(layer_norm[0], (S,), "reward-head LayerNorm gamma")
+            self._check_cuda_f32(layer_norm[1], (S,), "reward-head LayerNorm beta")
+            self._ck(self._lib.bcmpc_set_reward_layer_norm_device(self._h, C.c_void_p(layer_norm[0].data_ptr()),
+                                                                  C.c_void_p(layer_norm[1].data_ptr()), C.c_float(eps), _stream(stream_ptr)))
+
     def set_reward_head(self, weights, mean_reward=0.0, std_reward=1.0, gamma=1.0, layer_norm=None, eps=1e-12):
         """Reward head of NNDynamicsRewardModel (dynamics.py:175-178): weights = [(kernel[S,S], bias[S]), (kernel[S,1], bias[1])],
         or None to go back to cheetah_cost_fn.  The planner then maximises sum_i gamma**i * reward_i (controllers.py:121-158).

@@ -123,6 +123,9 @@ int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const flo
  * sizes 193..256 and 449..512 (BCMPC_ERR_UNSUPPORTED otherwise), and a reward head needs bcmpc_set_reward_layer_norm
  * too (all three LayerNorms or none). */
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps);
+/* ... with DEVICE pointers, enqueued on `stream` (see bcmpc_set_dynamics_device). */
+int bcmpc_set_layer_norm_device(bcmpc_handle* h, const float* const* d_gamma, const float* const* d_beta, int32_t n_hidden,
+                                float eps, void* stream);
 
 /* Learned-reward planners: NNDynamicsRewardModel (dynamics.py:121-238) = the dynamics net (n_hidden = 2: shared layer,
  * delta-head hidden layer, delta output) plus a reward head that branches off the shared layer: W[0] [hidden,hidden]
@@ -140,6 +143,13 @@ int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* c
  * to switch it off.  The shared layer and the delta head take theirs from bcmpc_set_layer_norm.  Call after
  * bcmpc_set_reward_head (a new head resets it). */
 int bcmpc_set_reward_layer_norm(bcmpc_handle* h, const float* gamma, const float* beta, float eps);
+
+/* The reward head and its LayerNorm from DEVICE pointers (layout as in bcmpc_set_dynamics_device), enqueued on `stream`:
+ * together with bcmpc_set_dynamics_device / bcmpc_set_layer_norm_device a PyTorch trainer refreshes the whole
+ * NNDynamicsRewardModel after fit (dynamics.py:195-219) without a host round trip. */
+int bcmpc_set_reward_head_device(bcmpc_handle* h, const float* const* dW, const float* const* db, int32_t layout,
+                                 double mean_reward, double std_reward, double gamma, void* stream);
+int bcmpc_set_reward_layer_norm_device(bcmpc_handle* h, const float* d_gamma, const float* d_beta, float eps, void* stream);
 
 /* NNDynamicsRewardModel.predict (dynamics.py:221-238): next_states [n,D] and rewards [n].  HOST buffers. */
 int bcmpc_predict_reward(bcmpc_handle* h, const double* states, const double* actions, int64_t n, double* next_states,

@@ -384,3 +384,56 @@ def test_device_policy_handoff_matches_host_upload(precision):
         for a, b in zip(want1 + want2, got1 + got2):
             assert np.array_equal(a, b)
         assert pl.plan(state, seed=8)[0]["cost"] == host.plan(state, seed=8)[0]["cost"]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_device_handoff_of_the_whole_reward_model(precision):
+    """dynamics + LayerNorms + reward head + reward LayerNorm + proposal network, all from torch CUDA tensors in nn.Linear
+    layout through the reference-shaped classes, against the host upload of the same parameters (bit-identical plans)."""
+    import torch
+    from bc_mpc_b200 import controllers, dynamics, policy
+
+    class Space:
+        def __init__(self, n):
+            self.low, self.high, self.shape = -np.ones(n), np.ones(n), (n,)
+
+    class Env:
+        action_space, observation_space = Space(6), Space(20)
+
+    K, H, S = 384, 5, 500
+    rng, norm, weights, rweights, state = O.synthetic_reward_problem(81, S)
+    lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(3)]
+    pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
+    n10 = (norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_reward"], norm["std_reward"], None, None,
+           norm["mean_deltas"], norm["std_deltas"])
+    dev = torch.device("cuda:0")
+
+    def lin(ws):       # nn.Linear layout
+        return [(torch.from_numpy(np.ascontiguousarray(w.T)).to(dev), torch.from_numpy(b).to(dev)) for w, b in ws]
+
+    def vec(ps):
+        return [(torch.from_numpy(g).to(dev), torch.from_numpy(b).to(dev)) for g, b in ps]
+
+    def controller(device_side):
+        dm = dynamics.NNDynamicsRewardModel(Env(), n10, size=S, layer_norm=True)
+        pol = policy.MlpPolicy(None, Env(), 128, 2)
+        if device_side:
+            dm.set_weights_device(lin(weights), lin(rweights), layer_norm_tensors=vec(lns[:2]), reward_layer_norm_tensors=vec(lns[2:])[0])
+            pol.set_weights_device(lin(pw), logstd, rms_mean, rms_std)
+        else:
+            dm.set_weights(weights, rweights, lns[:2], lns[2])
+            pol.set_weights(pw, logstd, rms_mean, rms_std)
+        return controllers.MPCcontrollerPolicyNetReward(Env(), dm, pol, self_exp=True, horizon=H, num_simulated_paths=K, precision=precision), dm
+
+    (ch, dmh), (cd, dmd) = controller(False), controller(True)
+    if os.environ.get("BCMPC_TC_CG") == "1" and precision == "bf16":
+        pytest.skip("single-CTA debug mode cannot hold the reward heads and a proposal network")
+    for seed in (1, 2):
+        np.random.seed(seed)
+        a_host = ch.get_action(state)
+        np.random.seed(seed)
+        a_dev = cd.get_action(state)
+        assert np.array_equal(a_host, a_dev) and ch.last_record["cost"] == cd.last_record["cost"]
+    nh, rh = dmh.predict(state[None], np.zeros((1, 6)))
+    nd, rd = dmd.predict(state[None], np.zeros((1, 6)))
+    assert np.array_equal(nh, nd) and np.array_equal(rh, rd)
