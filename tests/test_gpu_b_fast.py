@@ -437,3 +437,17 @@ def test_device_handoff_of_the_whole_reward_model(precision):
     nh, rh = dmh.predict(state[None], np.zeros((1, 6)))
     nd, rd = dmd.predict(state[None], np.zeros((1, 6)))
     assert np.array_equal(nh, nd) and np.array_equal(rh, rd)
+
+
+def test_fast_mode_nan_and_all_equal_costs():
+    """np.argmin semantics in the fast kernel's reductions: the first NaN wins; identical costs -> lowest index."""
+    K, H = 700, 3
+    rng, norm, state, pl, mpc = make_pair(91, (500, 500), K, H, precision="bf16")
+    bad = state.copy()
+    bad[3] = np.nan                                     # every path sees NaN from step 0 on
+    rec = pl.plan(bad, seed=1)[0]
+    assert np.isnan(rec["cost"]) and rec["index"] == 0
+    inj = np.tile(f32_uniform(rng, (H, 1, 6)), (1, K, 1))     # K identical action sequences: a K-way tie
+    rec = pl.plan(state, inj=inj)[0]
+    _, _, co = pl.rollout_debug(state, inj)
+    assert np.all(co == co[0]) and rec["index"] == 0 and rec["cost"] == co[0]
