@@ -204,6 +204,19 @@ def extras():
         "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
         "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
     pl.close()
+    # configs[4]: K = 2**20 x H = 30, MLP 3 x 1024.  Its 1024-wide hidden activations do not fit TMEM next to the
+    # accumulators, so there is no tcgen05 kernel for it yet: it runs on the float32 verification kernel (one plan, ~5 s)
+    rng4, norm4, w4, s4 = O.synthetic_problem(5, (1024, 1024, 1024))
+    pl = Planner(20, 6, 3, 1024, "relu", num_paths=1 << 20, horizon=30, precision="fp32")
+    pl.set_dynamics(w4)
+    pl.set_normalization(norm4["mean_obs"], norm4["std_obs"], norm4["mean_action"], norm4["std_action"], norm4["mean_deltas"], norm4["std_deltas"])
+    t0 = time.perf_counter()
+    pl.plan(s4, seed=1)
+    dt = time.perf_counter() - t0
+    out["configs4_K1048576_H30_3x1024_fp32_verify"] = {"plan_s": dt, "transitions_per_s": (1 << 20) * 30 / dt,
+                                                       "tflops_fp32": (1 << 20) * 30 * 4288512 / dt / 1e12}
+    pl.close()
+    del w4
     # learned-reward planner (NNDynamicsRewardModel + MPCcontrollerReward: what run.sh launches), tanh, 26-500-{500-20, 500-1}
     B, K, H = 32, 4096, 20
     rrng, rnorm, rw, rrw, _ = O.synthetic_reward_problem(3, 500)

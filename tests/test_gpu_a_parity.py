@@ -127,6 +127,41 @@ def test_config_5_three_by_1024_net():
     assert abs(cost - full["cost"]) < 1e-3 * max(1.0, abs(cost))
 
 
+def test_config_5_full_size_properties():
+    """BASELINE.json configs[4] at its full size - K = 2**20 paths x H = 30, MLP 3 x 1024 - through size-independent
+    properties: the union of 8 K-shards (as on 8 GPUs, min-loc over the shard records) is the single-handle plan, and
+    the winning path replayed through the oracle reproduces its cost."""
+    import time
+    K, H = 1 << 20, 30
+    rng, norm, weights, state = O.synthetic_problem(5, (1024, 1024, 1024))
+    dyn = O.OracleDynamics(weights, norm)
+    _, _, _, whole, _ = make_pair(5, (1024, 1024, 1024), K, H, weights=weights)
+    t0 = time.perf_counter()
+    full = whole.plan(state, seed=99)[0]
+    dt = time.perf_counter() - t0
+    print(f"configs[4] full size, verification kernel: {dt:.2f} s per plan, {K * H / dt:.3e} transitions/s")
+    whole.close()
+    best = None
+    for g in range(8):
+        _, _, _, shard, _ = make_pair(5, (1024, 1024, 1024), K // 8, H, weights=weights, path_offset=g * (K // 8), total_paths=K)
+        r = shard.plan(state, seed=99)[0]
+        if g == int(full["index"]) // (K // 8):
+            inj = shard.sample_injection(99)[0]           # [H, K/8, A] of the shard that holds the winner
+            assert r["index"] == full["index"]
+        if best is None or r["cost"] < best["cost"] or (r["cost"] == best["cost"] and r["index"] < best["index"]):
+            best = r
+        shard.close()
+    assert best["index"] == full["index"] and best["cost"] == full["cost"] and np.array_equal(best["action"], full["action"])
+    j = int(full["index"]) % (K // 8)
+    s, cost = state[None], 0.0
+    for h in range(H):
+        nxt = dyn.predict(s, inj[h, j:j + 1])
+        cost += float(O.cheetah_cost_fn(s, inj[h, j:j + 1], nxt)[0])
+        s = nxt
+    assert abs(cost - full["cost"]) < 1e-3 * max(1.0, abs(cost))
+    assert np.array_equal(full["action"][:6], inj[0, j])
+
+
 def test_layer_norm_dynamics_variant():
     """FLAGS.LAYER_NORM = True, the default of train_mpc_ppo.py:52: LayerNorm after every hidden ReLU (dynamics.py:68-69)."""
     K, H, S = 1000, 15, 256
