@@ -27,16 +27,21 @@
 // hidden epilogues are ReLU + convert only.
 //
 // Roles: warp 0 = weight producer; warps 1 and 3 = MMA issuers of the leader CTA (warp 1: the even layer-2 chunks,
-// warp 3: layer 1 and the odd layer-2 chunks - two issuers so that one can wait on barriers while the other keeps the
-// tensor pipe fed; every accumulator is written by one issuer only, so results do not depend on the interleaving);
-// warp 2 = TMEM allocation + layer-3 issuer; in the peer CTA warp 1 forwards "weights landed" to the leader;
-// warps 4-11 = epilogue: two groups of four warps (one warp per TMEM lane quadrant) that take alternate accumulator
-// chunks (layer 1: alternate pairs of chunks), 64 columns per warp and chunk.
-// The step's schedule - which accumulator a chunk uses, what each MMA group waits for and signals - is computed by a
-// constexpr function and unrolled at compile time, so every TMEM column, barrier and descriptor offset is an immediate.
+// warp 3: proposal network, layer 1 and the odd layer-2 chunks - two issuers so that one can wait on barriers while the
+// other keeps the tensor pipe fed; every accumulator is written by one issuer only, so results do not depend on the
+// interleaving); warp 2 = TMEM allocation + layer-3 issuer; in the peer CTA warp 1 forwards "weights landed" to the
+// leader; warps 4-11 = epilogue: two groups of four warps (one warp per TMEM lane quadrant) that take alternate
+// accumulator chunks (layer 1: alternate pairs of chunks), 64 columns per warp and chunk.
+// The step's schedule is fixed arithmetic on the chunk index (see below), so every TMEM column, barrier and descriptor
+// offset is a uniform-register function of a loop counter.
 //
-// Replaces dynamics.py:106-119 + cost_functions.py:10-30,59-63 + controllers.py:53,63-85 for HalfCheetah shapes
-// (D = 20, A = 6), two hidden ReLU layers, S <= 510, uniform shooting (P0).
+// Template parameters: CG (CTAs per tcgen05 group), NC (hidden chunks of 64), VAR (bit flags: 1 = proposal network,
+// 2 = LayerNorm dynamics, 4 = learned-reward model with its two heads as one double-width second layer), DBG (debug
+// flavour: injected randomness, per-path outputs; the production flavour compiles those paths out).
+//
+// Replaces dynamics.py:106-119 (+ :121-238 for the reward model) + cost_functions.py:10-30,59-63 +
+// controllers.py:53,63-85 (+ :189-237, :121-158, :319-363) for HalfCheetah shapes (D = 20, A = 6), two hidden layers,
+// S <= 510.
 #pragma once
 #include <cuda_bf16.h>
 
