@@ -232,7 +232,13 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 
 int tm_variant(const bcmpc_handle* h) {
   const int pol = h->cfg.proposal != BCMPC_PROP_UNIFORM ? tmx::kVarPolicy : 0;
-  return pol | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
+  int var = pol | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
+  // plain ReLU dynamics whose two constant-1 hidden units would need an extra chunk (hidden 63/64, 127/128, 255/256):
+  // biases in the epilogues instead
+  const int S = h->cfg.hidden_size;
+  if ((var & ~tmx::kVarPolicy) == 0 && (S + 2 + 63) / 64 > (S + 63) / 64 && tmx::tm_width_supported((S + 63) / 64, var | tmx::kVarBias))
+    var |= tmx::kVarBias;
+  return var;
 }
 
 // (re)packs the fast-mode weight images on the device, on stream `st`, from the float32 copies in h->dyn / h->ln_bufs
@@ -276,11 +282,12 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
     a.ldr1 = r.out_pad[0]; a.ldr2 = r.out_pad[1];
     if (P.layer_norm) { a.gr = r.ln_gamma[0]; a.ber = r.ln_beta[0]; }
   }
+  a.explicit_bias = P.explicit_bias ? 1 : 0;
   a.S = S; a.s_pad = P.s_pad; a.nc = P.nc; a.cg = P.cg; a.kbs = P.lay.kbs; a.nstg = P.lay.nstg;
   a.blk_h = P.lay.blk_h; a.blk_o = P.lay.blk_o; a.w1_bytes = P.lay.w1_bytes; a.res_bytes = P.lay.res_bytes; a.stage_bytes = P.lay.stage_bytes;
   a.res = reinterpret_cast<uint16_t*>(h->d_res); a.stream = reinterpret_cast<uint16_t*>(h->d_stream); a.lnvec = h->d_lnvec;
   CK(h, tmx::tm_pack(a, st));
-  h->launches += (P.layer_norm || P.reward) ? 2 : 1;
+  h->launches += (P.layer_norm || P.reward || P.explicit_bias) ? 2 : 1;
   if (!h->trace_path.empty() && !h->d_trace)
     CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots));
   h->tm_ready = true;
@@ -310,10 +317,12 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.span[j] = h->norm.span[j];
   }
   const bool pol = p.proposal != BCMPC_PROP_UNIFORM;
-  const int var = (P.reward ? tmx::kVarReward : 0) | (pol ? tmx::kVarPolicy : 0) | (P.layer_norm ? tmx::kVarLayerNorm : 0);
+  const int var = (P.reward ? tmx::kVarReward : 0) | (pol ? tmx::kVarPolicy : 0) | (P.layer_norm ? tmx::kVarLayerNorm : 0) |
+                  (P.explicit_bias ? tmx::kVarBias : 0);
   a.proposal = p.proposal; a.inj_kind = p.inj_kind;
   if (h->cfg.activation == BCMPC_ACT_TANH && !P.reward)
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: tanh dynamics are built for the learned-reward model (bcmpc_set_reward_head); a plain tanh NNDynamicsModel runs in BCMPC_PREC_FP32_VERIFY");
+  if (P.explicit_bias) a.lnvec = h->d_lnvec;
   if (P.reward) {
     a.lnvec = h->d_lnvec;
     if (P.layer_norm && fabsf(h->rew.desc.ln_eps - h->ln_eps) > 0.f)

@@ -130,12 +130,15 @@ struct Layout {
 };
 // kernel variants (bit flags): policy-guided shooting, LayerNorm dynamics net, learned-reward model
 // (NNDynamicsRewardModel, dynamics.py:121-238: shared layer -> state-delta head + reward head, objective = predicted reward)
-enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2, kVarReward = 4, kVarRewardPolicy = 5 };
+// kVarBias: the biases of layers 2 / 3 are added in the epilogues instead of riding in the GEMMs through two constant-1
+// hidden units - chosen when those two units would cost a whole extra 64-wide chunk (hidden sizes 63, 64, 127, 128, 255,
+// 256: the reference's default size is 256, train_mpc_ppo.py:75).  The reward model always works that way (tanh).
+enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2, kVarReward = 4, kVarRewardPolicy = 5, kVarBias = 8 };
 __host__ __device__ constexpr int hidden2_chunks(int nc, int var) { return (var & kVarReward) ? 2 * nc : nc; }
 constexpr int kRewardCol = kD;          // output column of the reward head in D3
 constexpr uint32_t kLnStatsBytes = 3 * 2 * kRows * 8;      // [layer: hidden 1, hidden 2 (delta head), reward head][epilogue group][row] (sum, sum of squares)
 constexpr Layout make_layout(int cg, int nc, int var) {
-  const bool pol = (var & kVarPolicy) != 0, ln = (var & kVarLayerNorm) != 0, rew = (var & kVarReward) != 0;
+  const bool pol = (var & kVarPolicy) != 0, ln = (var & kVarLayerNorm) != 0, rew = (var & (kVarReward | kVarBias)) != 0;
   const int nc2 = hidden2_chunks(nc, var);
   Layout L;
   L.kbs = stage_kblocks(cg, nc);
@@ -220,7 +223,7 @@ __host__ __device__ inline size_t sw128_offset(int n, int kk) {
 
 struct TmHostPlan {
   size_t res_total = 0, stream_total = 0, lnvec_floats = 0;     // bytes / bytes / floats of the device images
-  bool layer_norm = false, reward = false;
+  bool layer_norm = false, reward = false, explicit_bias = false;
   int cg = 1, s_pad = 0, nc = 0, nc2 = 0, hidden = 0;
   bool with_policy = false;
   int np1 = 0, np2 = 0;
@@ -255,19 +258,20 @@ inline bool tm_policy_supported(int n_layers, const int* sizes, std::string* why
 // the new weights come from the host (bcmpc_set_dynamics) or are already device-resident (bcmpc_set_dynamics_device).
 inline void tm_geometry(int S, int cg, int var, TmHostPlan* out) {
   TmHostPlan& P = *out;
-  const bool ln = (var & kVarLayerNorm) != 0, rew = (var & kVarReward) != 0;
+  const bool ln = (var & kVarLayerNorm) != 0, rew = (var & kVarReward) != 0, bias = (var & kVarBias) != 0;
   P.cg = cg;
   P.hidden = S;
   P.layer_norm = ln;
   P.reward = rew;
-  P.s_pad = (((ln || rew) ? S : S + 2) + 63) / 64 * 64;           // no hidden "ones" units with LayerNorm / the reward model
+  P.explicit_bias = bias;
+  P.s_pad = (((ln || rew || bias) ? S : S + 2) + 63) / 64 * 64;   // no hidden "ones" units with LayerNorm / the reward model / explicit biases
   P.nc = P.s_pad / 64;
   P.nc2 = hidden2_chunks(P.nc, var);
   P.lay = make_layout(cg, P.nc, var);
   P.res_total = (size_t)cg * P.lay.res_bytes;
   P.stream_total = (size_t)P.nc2 * P.lay.nstg * cg * P.lay.stage_bytes;
   P.lnvec_floats = ln ? (size_t)2 * 64 * P.nc2 + 2 * kOutN : 0;   // [u2][c2][u3][c3]
-  if (rew && !ln) P.lnvec_floats = (size_t)64 * P.nc2 + kOutN;    // [b2 delta head][b2 reward head][b3]
+  if ((rew || bias) && !ln) P.lnvec_floats = (size_t)64 * P.nc2 + kOutN;    // [b2 (delta head)][b2 reward head][b3]
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -366,6 +370,7 @@ __device__ __forceinline__ void build_policy_input(const TmArgs& a, uint32_t a0_
 template <int CG, int NC, int VAR, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
   constexpr bool POL = (VAR & kVarPolicy) != 0, LN = (VAR & kVarLayerNorm) != 0, REW = (VAR & kVarReward) != 0;
+  constexpr bool BIAS = !LN && (REW || (VAR & kVarBias) != 0);   // biases of layers 2 / 3 added in the epilogues
   constexpr int NC2 = hidden2_chunks(NC, VAR);                // hidden-2 chunks (both heads of the learned-reward model)
   static_assert(NC <= kMaxChunks1 && NC2 <= kMaxChunks2, "unsupported kernel variant");
   constexpr Layout L = Lay<CG, NC, VAR>::value;
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     float* s_pv = reinterpret_cast<float*>(smem + L.off_pol + L.pol_img_bytes);
     for (int i = tid; i < 2 * kPolMaxHidden + kMaxAct; i += kThreads) s_pv[i] = a.polvec[i];
   }
-  if constexpr (REW && !LN) {      // biases of the two heads: [b2 (64 * NC2)][b3 (32)]
+  if constexpr (BIAS) {            // [b2 (64 * NC2: both heads of the reward model)][b3 (32)]
     float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
     for (int i = tid; i < 64 * NC2 + kOutN; i += kThreads) s_vec[i] = a.lnvec[i];
   }
@@ -897,7 +902,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         __syncwarp();
         if (lane == 0) arrive_leader(kEvDEmpty + e);
         const float4* b4 = reinterpret_cast<const float4*>(bias);
-        auto act2 = [&](float x, float y) { return ptx::tanh_bf16x2(pack_bf16(x, y)); };
+        auto act2 = [&](float x, float y) {
+          if constexpr (REW) return ptx::tanh_bf16x2(pack_bf16(x, y));
+          else return pack_relu_bf16(x, y);
+        };
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -934,7 +942,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           const uint32_t bsel = c % (uint32_t)kNumDBufL1;
           const uint32_t col = bsel < (uint32_t)kNumDBuf ? (uint32_t)kColD + (uint32_t)kChunk * bsel : (uint32_t)kColA2;
           if constexpr (LN) chunk_ln(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, false, 0, c);
-          else if constexpr (REW) chunk_bias(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, nullptr);
+          else if constexpr (BIAS) chunk_bias(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1, nullptr);
           else chunk(c, col, (uint32_t)kColA1 + 32u * c, (uint32_t)kEvA1Ready + c, -1);
         }
       }
@@ -971,7 +979,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         }
         if constexpr (LN) chunk_ln((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, true,
                                    (REW && c >= (uint32_t)NC) ? 2 : 1, c);
-        else if constexpr (REW) chunk_bias((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, s_b2 + 64u * c);
+        else if constexpr (BIAS) chunk_bias((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2, s_b2 + 64u * c);
         else chunk((uint32_t)NC + c, (uint32_t)kColD + (uint32_t)kChunk * (c % (uint32_t)kNumDBuf), dst, (uint32_t)kEvA2Ready + c, wait_a2);
       }
 
@@ -994,7 +1002,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           }
           ln_sum = 0.f; ln_sq = 0.f;
         }
-        if constexpr (REW && !LN) {
+        if constexpr (BIAS) {
           const float* s_b3 = s_b2 + 64 * NC2;
 #pragma unroll
           for (int d = 0; d <= kRewardCol; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) + s_b3[d]);
@@ -1086,9 +1094,18 @@ inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
 // Variants 0..2 (uniform, proposal network, LayerNorm) exist for every width; the combinations - LayerNorm + proposal
 // network and everything with the learned-reward model - for 4 and 8 hidden chunks (hidden sizes 193..256 and
 // 449..512; the reference hard-codes 500 for the reward model, dynamics.py:162, and defaults to 256 / 500 elsewhere).
-inline bool tm_width_supported(int nc, int var) { return var < 3 || nc == 4 || nc == 8; }
+inline bool tm_width_supported(int nc, int var) {
+  if (var & kVarBias) return var <= (kVarBias | kVarPolicy) && (nc == 1 || nc == 2 || nc == 4);
+  return var < 3 || nc == 4 || nc == 8;
+}
 template <int CG, int VAR, bool DBG>
 inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  if constexpr ((VAR & kVarBias) != 0) {      // explicit-bias variants: the widths where they save a chunk
+    if (nc == 1) return tm_launch_t<CG, 1, VAR, DBG>(a, grid, st);
+    if (nc == 2) return tm_launch_t<CG, 2, VAR, DBG>(a, grid, st);
+    if (nc == 4) return tm_launch_t<CG, 4, VAR, DBG>(a, grid, st);
+    return cudaErrorInvalidValue;
+  }
   if constexpr (VAR < 3) {
     switch (nc) {
       case 1: return tm_launch_t<CG, 1, VAR, DBG>(a, grid, st);
@@ -1118,6 +1135,7 @@ cudaError_t tm_launch_var(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream
   template <> cudaError_t tm_launch_var<VAR, true>(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);
 BCMPC_TM_DECLARE_VARIANT(0) BCMPC_TM_DECLARE_VARIANT(1) BCMPC_TM_DECLARE_VARIANT(2) BCMPC_TM_DECLARE_VARIANT(3)
 BCMPC_TM_DECLARE_VARIANT(4) BCMPC_TM_DECLARE_VARIANT(5) BCMPC_TM_DECLARE_VARIANT(6) BCMPC_TM_DECLARE_VARIANT(7)
+BCMPC_TM_DECLARE_VARIANT(8) BCMPC_TM_DECLARE_VARIANT(9)
 template <bool DBG>
 inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
   switch (var) {
@@ -1129,6 +1147,8 @@ inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, d
     case 5: return tm_launch_var<5, DBG>(cg, nc, a, grid, st);   // ... + proposal network
     case 6: return tm_launch_var<6, DBG>(cg, nc, a, grid, st);   // learned-reward model with LayerNorm
     case 7: return tm_launch_var<7, DBG>(cg, nc, a, grid, st);   // ... + proposal network (what run.sh launches)
+    case 8: return tm_launch_var<8, DBG>(cg, nc, a, grid, st);   // uniform shooting, explicit biases (hidden 64 / 128 / 256)
+    case 9: return tm_launch_var<9, DBG>(cg, nc, a, grid, st);   // ... + proposal network
   }
   return cudaErrorInvalidValue;
 }

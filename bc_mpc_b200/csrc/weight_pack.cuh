@@ -11,6 +11,7 @@ struct PackArgs {
   const float *g1, *be1, *g2, *be2;             // LayerNorm gamma / beta of hidden layers 1, 2 (nullptr = off)
   const float *Wr1, *br1, *Wr2, *br2;           // reward head [S,S], [S,1] (nullptr = off; learned-reward model)
   const float *gr, *ber;                        // LayerNorm gamma / beta of the reward head's hidden layer
+  int explicit_bias;                            // biases of layers 2 / 3 go to lnvec instead of into the GEMMs (no hidden "ones" units)
   int ld1, ld2, ld3, ldr1, ldr2;
   int S, s_pad, nc, cg, kbs, nstg;
   uint32_t blk_h, blk_o, w1_bytes, res_bytes, stage_bytes;
@@ -23,7 +24,7 @@ __device__ __forceinline__ uint16_t pk_lo(float v) { return f32_to_bf16(__fsub_r
 // effective (bias-augmented, zero-padded) kernels
 __device__ __forceinline__ uint16_t pk_w1(const PackArgs& a, int k, int n) {        // k < 64 (input column), n < s_pad (hidden unit)
   constexpr int in_dim = kD + kA;
-  const bool ln = a.g1 != nullptr || a.Wr1 != nullptr;      // variants without hidden "ones" units
+  const bool ln = a.g1 != nullptr || a.Wr1 != nullptr || a.explicit_bias;      // variants without hidden "ones" units
   if (n < a.S) return k < in_dim ? f32_to_bf16(a.W1[(size_t)k * a.ld1 + n]) : k == in_dim ? pk_hi(a.b1[n]) : k == in_dim + 1 ? pk_lo(a.b1[n]) : 0;
   if (!ln && (n == a.S || n == a.S + 1)) return k == in_dim ? (uint16_t)0x3F80 : 0;   // the hidden "ones" units: relu(1 * 1) = 1
   return 0;
@@ -53,7 +54,7 @@ __device__ __forceinline__ float w3_bias(const PackArgs& a, int n) { return (a.W
 
 __device__ __forceinline__ uint16_t pk_w2(const PackArgs& a, int k, int n) {
   const int S = a.S;
-  if (a.g1 || a.Wr1) {         // no bias rows: LayerNorm folds the bias into c, the reward model adds it in the epilogue
+  if (a.g1 || a.Wr1 || a.explicit_bias) {         // no bias rows: LayerNorm folds the bias into c, the others add it in the epilogue
     if (!w2_live(a, k, n)) return 0;
     const float w = w2_raw(a, k, n);
     return f32_to_bf16(a.g1 ? __fmul_rn(a.g1[k], w) : w);
@@ -64,7 +65,7 @@ __device__ __forceinline__ uint16_t pk_w2(const PackArgs& a, int k, int n) {
 }
 __device__ __forceinline__ uint16_t pk_w3(const PackArgs& a, int k, int n) {        // n < 32 (output column)
   const int S = a.S;
-  if (a.g1 || a.Wr1) {
+  if (a.g1 || a.Wr1 || a.explicit_bias) {
     if (!w3_live(a, k, n)) return 0;
     const float w = w3_raw(a, k, n);
     return f32_to_bf16(a.g1 ? __fmul_rn(w3_gamma(a, k), w) : w);
@@ -134,14 +135,14 @@ __global__ void pack_ln_kernel(PackArgs a) {
   }
 }
 
-// learned-reward model: lnvec = [b2 (s_pad)][br1 (s_pad)][b3 (20), br2, 0 ...]
+// explicit biases: lnvec = [b2 (s_pad)]{[br1 (s_pad)] with the reward model}[b3 (20), {br2,} 0 ...]
 __global__ void pack_reward_bias_kernel(PackArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, sp = a.s_pad;
-  if (i >= 2 * sp + kOutN) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, sp = a.s_pad, sp2 = a.Wr1 ? 2 * sp : sp;
+  if (i >= sp2 + kOutN) return;
   float v = 0.f;
   if (i < sp) v = i < a.S ? a.b2[i] : 0.f;
-  else if (i < 2 * sp) v = i - sp < a.S ? a.br1[i - sp] : 0.f;
-  else { const int d = i - 2 * sp; v = d < kD ? a.b3[d] : d == kRewardCol ? a.br2[0] : 0.f; }
+  else if (i < sp2) v = i - sp < a.S ? a.br1[i - sp] : 0.f;
+  else { const int d = i - sp2; v = d < kD ? a.b3[d] : (a.Wr1 && d == kRewardCol) ? a.br2[0] : 0.f; }
   a.lnvec[i] = v;
 }
 
@@ -197,7 +198,7 @@ inline cudaError_t tm_pack(const PackArgs& a, cudaStream_t st) {
   const int total = 64 * a.s_pad + sp2 * kOutN + a.s_pad * sp2;
   pack_images_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
   if (a.g1) pack_ln_kernel<<<(sp2 + kOutN + 7) / 8, 256, 0, st>>>(a);
-  else if (a.Wr1) pack_reward_bias_kernel<<<(2 * a.s_pad + kOutN + 255) / 256, 256, 0, st>>>(a);
+  else if (a.Wr1 || a.explicit_bias) pack_reward_bias_kernel<<<(sp2 + kOutN + 255) / 256, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
