@@ -1074,11 +1074,13 @@ template <int CG, int NC, int VAR, bool DBG>
 inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
   auto kern = rollout_tmem_kernel<CG, NC, VAR, DBG>;
   constexpr Layout L = Lay<CG, NC, VAR>::value;
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
+  static bool attr_done[64] = {};   // per instantiation and device (a process may own planners on several GPUs)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;

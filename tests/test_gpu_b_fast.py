@@ -451,3 +451,23 @@ def test_fast_mode_nan_and_all_equal_costs():
     rec = pl.plan(state, inj=inj)[0]
     _, _, co = pl.rollout_debug(state, inj)
     assert np.all(co == co[0]) and rec["index"] == 0 and rec["cost"] == co[0]
+
+
+def test_two_devices_in_one_process():
+    """One process, planners on two GPUs (per-device kernel attributes, streams and buffers): identical plans."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from bc_mpc_b200 import Planner
+    rng, norm, weights, state = O.synthetic_problem(13, (500, 500))
+    recs = []
+    for dev in (0, 1, 0):
+        for precision in ("bf16", "fp32"):
+            pl = Planner(20, 6, 2, 500, "relu", num_paths=600, horizon=4, precision=precision, device=dev)
+            pl.set_dynamics(weights)
+            pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+            recs.append((precision, pl.plan(state, seed=3)[0]))
+            pl.close()
+    for precision in ("bf16", "fp32"):
+        same = [r for p, r in recs if p == precision]
+        assert all(r["index"] == same[0]["index"] and r["cost"] == same[0]["cost"] for r in same)
