@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "rollout_tmem.cuh"
 #include "weight_pack.cuh"
+#include "rollout_narrow.cuh"
 #include "rollout_verify.cuh"
 
 using namespace bcmpc;
@@ -74,6 +75,8 @@ struct bcmpc_handle {
   bool weights_pending = false;       // plans on other streams wait on ev_weights until it has completed
   unsigned long long* d_trace = nullptr;
   bool tm_ready = false;
+  bool tm_narrow = false; // the narrow-net kernel (hidden <= 256, uniform shooting, CTA pairs) is in use
+  int tm_narrow_mode = 1; // BCMPC_NARROW=0 keeps hidden <= 256 on rollout_tmem_kernel (rollout_narrow_kernel is the default there)
   int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
   uint32_t tm_hint_chain = 0x989680u;   // BCMPC_TC_HINT_CHAIN: mbarrier try_wait suspend hint (ns) on the per-step dependency chain
   std::string trace_path; // BCMPC_TC_TRACE: dump the pipeline trace of CTA (0,0) after every launch
@@ -230,9 +233,16 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
   return BCMPC_OK;
 }
 
+// the narrow-net kernel: plain ReLU dynamics of at most 256 hidden units, uniform shooting, CTA pairs
+bool narrow_applies(const bcmpc_handle* h) {
+  return h->tm_narrow_mode != 0 && h->tm_cg == 2 && h->cfg.proposal == BCMPC_PROP_UNIFORM && !h->ln_on && !h->rew.set &&
+         h->cfg.hidden_size <= 64 * tmx::kNwMaxChunks;
+}
+
 int tm_variant(const bcmpc_handle* h) {
   const int pol = h->cfg.proposal != BCMPC_PROP_UNIFORM ? tmx::kVarPolicy : 0;
   int var = pol | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
+  if (narrow_applies(h)) return tmx::kVarBias;     // rollout_narrow_kernel: explicit biases for every width it covers
   // plain ReLU dynamics whose two constant-1 hidden units would need an extra chunk (hidden 63/64, 127/128, 255/256):
   // biases in the epilogues instead
   const int S = h->cfg.hidden_size;
@@ -251,7 +261,8 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   }
   const tmx::TmHostPlan& P = h->tmp;
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
-  if (!tmx::tm_width_supported(P.nc, tm_variant(h)))
+  h->tm_narrow = narrow_applies(h);
+  if (!h->tm_narrow && !tmx::tm_width_supported(P.nc, tm_variant(h)))
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: this combination (learned-reward model, or LayerNorm with a proposal network) is built for hidden sizes 193..256 and 449..512 (got %d); use BCMPC_PREC_FP32_VERIFY", S);
   if (P.reward && h->ln_on != h->rew_ln_on) {
     // between bcmpc_set_layer_norm and bcmpc_set_reward_layer_norm: the images are packed once all three LayerNorms agree
@@ -344,7 +355,8 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   }
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
-  CK(h, tmx::tm_launch(h->tm_cg, P.nc, var, a, dim3(p.tiles_per_state, p.B), st));
+  if (h->tm_narrow) CK(h, tmx::nw_launch(P.nc, a, dim3(p.tiles_per_state / 2, p.B), st));
+  else CK(h, tmx::tm_launch(h->tm_cg, P.nc, var, a, dim3(p.tiles_per_state, p.B), st));
   CK(h, cudaGetLastError());
   h->launches++;
   if (h->d_trace) {
@@ -368,6 +380,7 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   const int M = fast ? tmx::kRows : h->vM;
   p.tiles_per_state = (p.K + M - 1) / M;
   if (fast && h->tm_cg == 2) p.tiles_per_state = (p.tiles_per_state + 1) / 2 * 2;   // CTA pairs; a padding tile has no valid row
+  if (fast && h->tm_narrow) p.tiles_per_state = (p.tiles_per_state + 3) / 4 * 4;     // narrow kernel: two tiles per CTA of a pair
   if (d_out) {
     int rc = ensure_cand(h, (size_t)p.B * p.tiles_per_state);
     if (rc) return rc;
@@ -459,6 +472,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
                                                 "BCMPC_NVCC_EXTRA=-DBCMPC_TRACE python -m bc_mpc_b200._build (developer builds only, ~6%% slower)");
 #endif
   }
+  if (const char* s = getenv("BCMPC_NARROW")) h->tm_narrow_mode = atoi(s);
   if (const char* s = getenv("BCMPC_TC_HINT_CHAIN")) h->tm_hint_chain = (uint32_t)strtoul(s, nullptr, 0);
   cudaError_t e = cudaSetDevice(c.device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

@@ -1,0 +1,16 @@
+// Narrow-net tcgen05 rollout kernel (hidden <= 256, two tiles per CTA), debug flavour
+#include "rollout_narrow.cuh"
+
+namespace bcmpc {
+namespace tmx {
+cudaError_t nw_launch_dbg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  switch (nc) {
+    case 1: return nw_launch_t<1, true>(a, grid, st);
+    case 2: return nw_launch_t<2, true>(a, grid, st);
+    case 3: return nw_launch_t<3, true>(a, grid, st);
+    case 4: return nw_launch_t<4, true>(a, grid, st);
+  }
+  return cudaErrorInvalidValue;
+}
+}  // namespace tmx
+}  // namespace bcmpc

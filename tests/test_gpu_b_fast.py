@@ -471,3 +471,47 @@ def test_two_devices_in_one_process():
     for precision in ("bf16", "fp32"):
         same = [r for p, r in recs if p == precision]
         assert all(r["index"] == same[0]["index"] and r["cost"] == same[0]["cost"] for r in same)
+
+
+def _narrow_pair(monkeypatch, mode, seed, S, K, H, **kw):
+    monkeypatch.setenv("BCMPC_NARROW", mode)
+    return make_pair(seed, (S, S), K, H, precision="bf16", **kw)
+
+
+@pytest.mark.parametrize("S", [256, 200, 128, 64, 7])
+def test_narrow_kernel_tracks_oracle_and_matches_the_wide_kernel(monkeypatch, S):
+    """rollout_narrow_kernel (hidden <= 256: two 128-path tiles per CTA, all weights resident) against the oracle, and -
+    where the wide kernel uses the same explicit-bias weight images (hidden 64 / 128 / 256) - bit for bit against it."""
+    if os.environ.get("BCMPC_TC_CG") == "1":
+        pytest.skip("the narrow kernel is a CTA-pair kernel")
+    K, H = 1000, 12
+    rng, norm, state, pl, mpc = _narrow_pair(monkeypatch, "1", 15, S, K, H)
+    actions = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    e = _norm_err(so, dbg["states"], norm)
+    rec = pl.plan(state, inj=actions)[0]
+    regret = (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std()
+    print(dict(S=S, max_state_err_in_delta_std=float(np.abs(e).max()), cost_corr=float(np.corrcoef(co, dbg["costs"])[0, 1]),
+               argmin_match=bool(rec["index"] == dbg["argmin"]), regret=float(regret)))
+    assert np.array_equal(ao, actions) and np.abs(e).max() < 0.3 and np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
+    assert rec["index"] == int(np.argmin(co)) and np.array_equal(rec["action"][:6], actions[0, rec["index"]]) and regret < 0.5
+    # production flavour == debug flavour; batching; ragged K (tile count padded to a multiple of 4)
+    B = 3
+    _, _, _, plb, _ = _narrow_pair(monkeypatch, "1", 15, S, 700, 5, max_states=B)
+    states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((B, 20))
+    prod = plb.plan(states, seed=31)
+    inj = plb.sample_injection(31, B)
+    dbgr = plb.plan(states, inj=inj)
+    assert np.array_equal(prod["index"], dbgr["index"]) and np.array_equal(prod["cost"], dbgr["cost"])
+    for K1 in (1, 129):
+        _, _, _, p1, _ = _narrow_pair(monkeypatch, "1", 15, S, K1, 3)
+        r = p1.plan(state, seed=2)[0]
+        assert 0 <= r["index"] < K1
+    # against the wide kernel
+    _, _, _, wide, _ = _narrow_pair(monkeypatch, "0", 15, S, K, H)
+    sw, _, cw = wide.rollout_debug(state, actions)
+    if S in (64, 128, 256):
+        assert np.array_equal(sw, so) and np.array_equal(cw, co)
+    else:
+        assert np.abs(_norm_err(sw, so, norm)).max() < 0.3
