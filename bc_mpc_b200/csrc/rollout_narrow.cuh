@@ -15,7 +15,8 @@
 //   warps 4-7   epilogue of pipe 0 (one warp per TMEM lane quadrant), warps 8-11 epilogue of pipe 1
 // TMEM, per pipe t (columns 256 t + ...):
 //   [  0,128)  A1  hidden-1 activations (bf16 pairs), A operand of layer 2
-//   [128,192)  D0  accumulator: layer-1 even chunks; every layer-2 chunk, as two independently drained 32-column halves
+//   [128,192)  D0  accumulator: layer-1 even chunks, every layer-2 chunk
+// (Splitting the layer-2 chunks into two independently drained N = 32 halves was tried: +1.5 % at hidden 256, -5 % below.)
 //   [192,256)  X   layer-1 odd chunks; afterwards A2 [192,224) (one hidden-2 chunk) and D3 [224,256) (output layer)
 // Biases: layer 1 through two constant-1 input columns (as in rollout_tmem_kernel); layers 2 / 3 added in the epilogues
 // (the weight images are those of the kVarBias variant, packed by weight_pack.cuh).
@@ -29,10 +30,6 @@ namespace bcmpc {
 namespace tmx {
 
 constexpr int kNwMaxChunks = 4;
-#ifndef BCMPC_NW_HALF_SPLIT
-#define BCMPC_NW_HALF_SPLIT 0
-#endif
-constexpr bool kNwHalfSplit = BCMPC_NW_HALF_SPLIT != 0;   // layer-2 chunks as two independently drained N = 32 halves
 // per-pipe event barriers
 enum : int {
   kNwA0Ready = 0,      // input rows of the step are in shared memory               (epilogue -> issuer)
@@ -40,18 +37,18 @@ enum : int {
   kNwDFull1 = 2,       // [4] layer-1 accumulator of chunk c complete               (issuer -> epilogue)
   kNwDEmpty1 = 6,      // [4] ... drained                                           (epilogue -> issuer)
   kNwA1Ready = 10,     // [4] hidden-1 k-block c stored                              (epilogue -> issuer)
-  kNwDFull2 = 14,      // [8] layer-2 accumulator of chunk c, half hf (index 2c + hf) complete
-  kNwDEmpty2 = 22,     // [8] ... drained
-  kNwA2Ready = 30,     // [4] hidden-2 chunk c stored
-  kNwA2Empty = 34,     // [4] layer 3 has consumed hidden-2 chunk c
-  kNwNumEv = 38
+  kNwDFull2 = 14,      // [4] layer-2 accumulator of chunk c complete
+  kNwDEmpty2 = 18,     // [4] ... drained
+  kNwA2Ready = 22,     // [4] hidden-2 chunk c stored
+  kNwA2Empty = 26,     // [4] layer 3 has consumed hidden-2 chunk c
+  kNwNumEv = 30
 };
 
 struct NwLayout {
   uint32_t blk_h = 0, blk_o = 0, w1_bytes = 0, w3_bytes = 0, w2_bytes = 0;
   uint32_t off_a0 = 0, off_w13 = 0, off_w2 = 0, off_vec = 0, off_misc = 0, smem_bytes = 0;
 };
-constexpr uint32_t kNwMiscBytes = 1024;      // [weights-landed barrier][2 x 38 events] x 8 B, tmem ptr, 2 x argmin scratch
+constexpr uint32_t kNwMiscBytes = 1024;      // [weights-landed barrier][2 x 30 events] x 8 B, tmem ptr, 2 x argmin scratch
 constexpr uint32_t kNwOffEv = 8, kNwOffTmemPtr = 8 + 2 * kNwNumEv * 8, kNwOffRed = 640;
 constexpr NwLayout nw_layout(int nc) {
   NwLayout L;
@@ -104,10 +101,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
         ptx::mbar_init(ev + 8u * (kNwDFull1 + i), 1);
         ptx::mbar_init(ev + 8u * (kNwDEmpty1 + i), 4 * CG);
         ptx::mbar_init(ev + 8u * (kNwA1Ready + i), 4 * CG);
-        ptx::mbar_init(ev + 8u * (kNwDFull2 + 2 * i), 1);
-        ptx::mbar_init(ev + 8u * (kNwDFull2 + 2 * i + 1), 1);
-        ptx::mbar_init(ev + 8u * (kNwDEmpty2 + 2 * i), 4 * CG);
-        ptx::mbar_init(ev + 8u * (kNwDEmpty2 + 2 * i + 1), 4 * CG);
+        ptx::mbar_init(ev + 8u * (kNwDFull2 + i), 1);
+        ptx::mbar_init(ev + 8u * (kNwDEmpty2 + i), 4 * CG);
         ptx::mbar_init(ev + 8u * (kNwA2Ready + i), 4 * CG);
         ptx::mbar_init(ev + 8u * (kNwA2Empty + i), 1);
       }
@@ -169,41 +164,19 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
 #pragma unroll
         for (int c = 0; c <= NC; ++c) {
           if (c < NC) {
-            // The chunk is computed as two N = 32 halves into the two halves of D0: the epilogue drains one half while the
-            // other is in the tensor pipe, and the next chunk's first half can be issued as soon as ITS half is drained -
-            // with one 64-column accumulator per pipe a whole-chunk MMA would wait two hand-offs per chunk.  Half hf takes
-            // 16 of this CTA's 32 weight rows (units 16 hf .. of the CTA's half of the chunk): 2 x 1024-byte row groups.
-            if constexpr (!kNwHalfSplit) {
-              if (c == 0) ptx::mbar_wait(ev + 8u * (kNwA1Ready + NC - 1), par, hc);   // chunks are stored in order: the last implies all
-              else ptx::mbar_wait(ev + 8u * (kNwDEmpty2 + c - 1), par, hc);            // D0 drained
-              ptx::tc_fence_after();
-              if (ptx::elect_one()) {
+            if (c == 0) ptx::mbar_wait(ev + 8u * (kNwA1Ready + NC - 1), par, hc);   // chunks are stored in order: the last implies all
+            else ptx::mbar_wait(ev + 8u * (kNwDEmpty2 + c - 1), par, hc);            // D0 drained
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
 #pragma unroll
-                for (int kb = 0; kb < NC; ++kb)
+              for (int kb = 0; kb < NC; ++kb)
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    ptx::umma_ts<CG>(cD0, cA1 + kb * 32 + ks * 8, w2desc + (uint64_t)((c * NC + kb) * (L.blk_h >> 4) + 2u * ks), kIdescH,
-                                     (kb | ks) ? 1u : 0u);
-                ptx::umma_commit_cg<CG>(ev + 8u * (kNwDFull2 + c));
-              }
-              __syncwarp();
+                for (int ks = 0; ks < 4; ++ks)
+                  ptx::umma_ts<CG>(cD0, cA1 + kb * 32 + ks * 8, w2desc + (uint64_t)((c * NC + kb) * (L.blk_h >> 4) + 2u * ks), kIdescH,
+                                   (kb | ks) ? 1u : 0u);
+              ptx::umma_commit_cg<CG>(ev + 8u * (kNwDFull2 + c));
             }
-#pragma unroll
-            for (int hf = 0; hf < (kNwHalfSplit ? 2 : 0); ++hf) {
-              if (c == 0) { if (hf == 0) ptx::mbar_wait(ev + 8u * (kNwA1Ready + NC - 1), par, hc); }   // chunks are stored in order: the last implies all
-              else ptx::mbar_wait(ev + 8u * (kNwDEmpty2 + 2 * (c - 1) + hf), par, hc);                  // this half of D0 drained
-              ptx::tc_fence_after();
-              if (ptx::elect_one()) {
-#pragma unroll
-                for (int kb = 0; kb < NC; ++kb)
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    ptx::umma_ts<CG>(cD0 + 32u * hf, cA1 + kb * 32 + ks * 8,
-                                     w2desc + (uint64_t)((c * NC + kb) * (L.blk_h >> 4) + hf * (2048u >> 4) + 2u * ks), kIdescO, (kb | ks) ? 1u : 0u);
-                ptx::umma_commit_cg<CG>(ev + 8u * (kNwDFull2 + 2 * c + hf));
-              }
-              __syncwarp();
-            }
+            __syncwarp();
           }
           if (c >= 1) {
             ptx::mbar_wait(ev + 8u * (kNwA2Ready + c - 1), par, hc);
@@ -303,50 +276,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       for (uint32_t c = 0; c < (uint32_t)NC; ++c)
         chunk(par, kNwDFull1 + c, kNwDEmpty1 + c, (c & 1u) ? cX : cD0, cA1 + 32u * c, kNwA1Ready + c, -1, nullptr);
       if (h + 1 < H) get_noise<DBG, false>(a, b, h + 1, kc, z);            // next step's randomness, off the critical path
-      if constexpr (!kNwHalfSplit) {
 #pragma unroll 1
-        for (uint32_t c = 0; c < (uint32_t)NC; ++c)
-          chunk(par, kNwDFull2 + c, kNwDEmpty2 + c, cD0, cX, kNwA2Ready + c, c > 0 ? (int)(kNwA2Empty + c - 1) : -1, s_b2 + 64u * c);
-      }
-#pragma unroll 1
-      for (uint32_t c = 0; c < (kNwHalfSplit ? (uint32_t)NC : 0u); ++c) {
-        // layer-2 chunk c arrives as two 32-column halves: columns 0..15 of half hf = units 16 hf .. of the chunk's first 32
-        // (the leader CTA's weight rows), columns 16..31 = units 32 + 16 hf .. (the peer's)
-        uint32_t va[32], vb[32], w0[16], w1[16];
-        ptx::mbar_wait(ev + 8u * (kNwDFull2 + 2u * c), par, hc);
-        ptx::tc_fence_after();
-        ptx::tmem_ld32(lane_off + cD0, va);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive(kNwDEmpty2 + 2u * c);
-        ptx::mbar_wait(ev + 8u * (kNwDFull2 + 2u * c + 1u), par, hc);
-        ptx::tc_fence_after();
-        ptx::tmem_ld32(lane_off + cD0 + 32u, vb);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive(kNwDEmpty2 + 2u * c + 1u);
-        const float* bias = s_b2 + 64u * c;
-        auto unit = [&](int u) {        // accumulator of unit u (0..63) of the chunk
-          const int first = u < 32 ? 0 : 16, r = u & 31;
-          return __uint_as_float(r < 16 ? va[first + r] : vb[first + r - 16]);
-        };
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w0[i] = pack_relu_bf16(unit(2 * i) + bias[2 * i], unit(2 * i + 1) + bias[2 * i + 1]);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w1[i] = pack_relu_bf16(unit(32 + 2 * i) + bias[32 + 2 * i], unit(32 + 2 * i + 1) + bias[32 + 2 * i + 1]);
-        if (c > 0) {
-          ptx::mbar_wait(ev + 8u * (kNwA2Empty + c - 1u), par, hc);       // layer 3 has consumed the previous hidden-2 chunk
-          ptx::tc_fence_after();
-        }
-        ptx::tmem_st16(lane_off + cX, w0);
-        ptx::tmem_st16(lane_off + cX + 16u, w1);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive(kNwA2Ready + c);
-      }
+      for (uint32_t c = 0; c < (uint32_t)NC; ++c)
+        chunk(par, kNwDFull2 + c, kNwDEmpty2 + c, cD0, cX, kNwA2Ready + c, c > 0 ? (int)(kNwA2Empty + c - 1) : -1, s_b2 + 64u * c);
       ptx::mbar_wait(ev + 8u * kNwD3Full, par, hc);
       ptx::tc_fence_after();
       uint32_t v[32];

@@ -204,6 +204,22 @@ def extras():
         "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
         "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
     pl.close()
+    # the reference's default network size (train_mpc_ppo.py:75 size=256; the shape of saved_data/ppo-mpc/vars.pkl):
+    # hidden <= 256 runs on rollout_narrow_kernel (two tiles per CTA); 37 states x 32 tiles = 296 CTA-pair units = 4 even waves
+    B, K, H = 37, 4096, 20
+    rng2, norm2, w2, _ = O.synthetic_problem(0, (256, 256))
+    pl = Planner(20, 6, 2, 256, "relu", num_paths=K, horizon=H, max_states=B, precision="bf16")
+    pl.set_dynamics(w2)
+    pl.set_normalization(norm2["mean_obs"], norm2["std_obs"], norm2["mean_action"], norm2["std_action"], norm2["mean_deltas"], norm2["std_deltas"])
+    st2 = norm2["mean_obs"] + norm2["std_obs"] * np.random.default_rng(5).standard_normal((B, 20))
+    pl.enable_timing(True)
+    dt = time_plans(pl, st2, 10)
+    k_ms = pl.last_kernel_ms()
+    flop2 = 2 * (26 * 256 + 256 * 256 + 256 * 20)
+    out["net_2x256_K4096_H20_bf16_x37states"] = {
+        "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
+        "tflops_algorithmic": B * K * H * flop2 / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop2}
+    pl.close()
     # configs[4]: K = 2**20 x H = 30, MLP 3 x 1024.  Its 1024-wide hidden activations do not fit TMEM next to the
     # accumulators, so there is no tcgen05 kernel for it yet: it runs on the float32 verification kernel (one plan, ~5 s)
     rng4, norm4, w4, s4 = O.synthetic_problem(5, (1024, 1024, 1024))

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bc_mpc_b200 import Planner  # noqa: E402
 from oracle import mpc_oracle as O  # noqa: E402
 
-B, K, H = 32, 4096, 20
+B, K, H = int(os.environ.get("SWEEP_B", "32")), 4096, 20
 for S in [int(x) for x in os.environ.get("SWEEP_S", "64,128,256,300,384,500").split(",")]:
     rng, norm, weights, state = O.synthetic_problem(0, (S, S))
     pl = Planner(20, 6, 2, S, "relu", num_paths=K, horizon=H, precision="bf16", max_states=B)
