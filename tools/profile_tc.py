@@ -10,8 +10,9 @@ from oracle import mpc_oracle as O  # noqa: E402
 
 B = int(os.environ.get("PROF_B", "32"))
 H = int(os.environ.get("PROF_H", "20"))
-rng, norm, weights, state = O.synthetic_problem(0, (500, 500))
-pl = Planner(20, 6, 2, 500, "relu", num_paths=4096, horizon=H, precision="bf16", max_states=B)
+S = int(os.environ.get("PROF_S", "500"))
+rng, norm, weights, state = O.synthetic_problem(0, (S, S))
+pl = Planner(20, 6, 2, S, "relu", num_paths=4096, horizon=H, precision="bf16", max_states=B)
 pl.set_dynamics(weights)
 pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
 states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((B, 20))
