@@ -51,12 +51,14 @@ struct bcmpc_handle {
   // verify-kernel geometry
   int vM = 32, vld = 0;
   // scratch
+  unsigned int* d_ticket = nullptr;   // [max_states] finished-tile counters of the fused min-loc
   Candidate* d_cand = nullptr;
   size_t cand_cap = 0;
   double* d_states = nullptr;
   bcmpc_record* d_records = nullptr;
   double* h_states = nullptr;        // pinned
-  bcmpc_record* h_records = nullptr; // pinned
+  bcmpc_record* h_records = nullptr; // pinned, mapped into the device address space
+  bcmpc_record* h_records_dev = nullptr;   // its device-side address: small plans write their records straight to the host
   double* d_inj = nullptr;
   size_t inj_cap = 0;
   int64_t launches = 0;
@@ -392,6 +394,11 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
     if (cudaEventQuery(h->ev_weights) == cudaSuccess) h->weights_pending = false;
     else CK(h, cudaStreamWaitEvent(st, h->ev_weights, 0));
   }
+  // few tiles per root state: the rollout kernel's last tile of a state does the min-loc itself (no second launch)
+  // (a latency measure for single plans - the reference plans one state per env step; large batches keep the separate kernel)
+  const bool fused = fast && d_out != nullptr && p.tiles_per_state <= 64 && p.B <= 8;
+  p.out = fused ? d_out : nullptr;
+  p.ticket = h->d_ticket;
   if (h->timing) { CK(h, cudaEventRecord(h->ev0, st)); }
   int rc;
   if (fast) {
@@ -405,7 +412,7 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   }
   if (rc) return rc;
   if (h->timing) { CK(h, cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
-  if (d_out) {
+  if (d_out && !fused) {
     reduce_candidates_kernel<<<p.B, 256, 0, st>>>(h->d_cand, p.tiles_per_state, p.B, 0, d_out);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -481,7 +488,10 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->d_states, sizeof(double) * c.max_states * c.obs_dim);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_records, sizeof(bcmpc_record) * c.max_states);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_states, sizeof(double) * c.max_states * c.obs_dim);
-  if (e == cudaSuccess) e = cudaMallocHost(&h->h_records, sizeof(bcmpc_record) * c.max_states);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_ticket, sizeof(unsigned int) * c.max_states);
+  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int) * c.max_states);
+  if (e == cudaSuccess) e = cudaHostAlloc(&h->h_records, sizeof(bcmpc_record) * c.max_states, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&h->h_records_dev, h->h_records, 0);
   if (e != cudaSuccess) {
     int rc = fail(nullptr, BCMPC_ERR_CUDA, "bcmpc_create: %s", cudaGetErrorString(e));
     bcmpc_destroy(h);
@@ -502,6 +512,7 @@ int bcmpc_destroy(bcmpc_handle* h) {
   h->rew.release();
   for (float* p : h->ln_bufs) cudaFree(p);
   cudaFree(h->rew_ln_buf);
+  cudaFree(h->d_ticket);
   cudaFree(h->d_cand); cudaFree(h->d_states); cudaFree(h->d_records); cudaFree(h->d_inj);
   cudaFree(h->d_res); cudaFree(h->d_stream); cudaFree(h->d_pol); cudaFree(h->d_polvec); cudaFree(h->d_lnvec); cudaFree(h->d_trace);
   if (h->h_states) cudaFreeHost(h->h_states);
@@ -826,9 +837,12 @@ int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const do
     CK(h, cudaMemcpyAsync(h->d_inj, inj, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     d_inj = h->d_inj;
   }
-  int rc = bcmpc_plan_device(h, h->d_states, n_states, d_inj, seed, h->d_records, h->stream);
+  // up to 64 records (5 KB) are written by the min-loc kernel straight into mapped host memory: one copy call and one DMA
+  // round trip less on the single-plan latency path (the reference plans one state per env step)
+  const bool direct = n_states <= 64 && h->h_records_dev != nullptr;
+  int rc = bcmpc_plan_device(h, h->d_states, n_states, d_inj, seed, direct ? h->h_records_dev : h->d_records, h->stream);
   if (rc) return rc;
-  CK(h, cudaMemcpyAsync(h->h_records, h->d_records, sizeof(bcmpc_record) * n_states, cudaMemcpyDeviceToHost, h->stream));
+  if (!direct) CK(h, cudaMemcpyAsync(h->h_records, h->d_records, sizeof(bcmpc_record) * n_states, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   memcpy(out, h->h_records, sizeof(bcmpc_record) * n_states);
   return BCMPC_OK;

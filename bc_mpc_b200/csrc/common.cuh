@@ -115,7 +115,48 @@ struct PlanArgs {
   double* actions_out;        // [H, K, A]
   double* costs_out;          // [B, K]
   int per_row_states;         // predict mode: row k starts from states[k] instead of states[b]
+  // fused per-state min-loc (fast kernels, few tiles per state): the last tile of a root state to finish reduces the
+  // state's candidates itself instead of a second kernel launch
+  bcmpc_record* out;          // [B] winning records, or nullptr = a separate reduce_candidates_kernel follows
+  unsigned int* ticket;       // [B] finished-tile counters, zero between plans
 };
+
+// Called by every lane of the warp that holds a tile's winning row, after that row's lane (writer_lane) has written the
+// tile's candidate.  np.argmin order, same as reduce_candidates_kernel.
+__device__ __forceinline__ void fused_state_minloc(const PlanArgs& p, int b, int lane, int writer_lane) {
+  unsigned int prev = 0;
+  if (lane == writer_lane) {
+    __threadfence();
+    prev = atomicAdd(&p.ticket[b], 1u);
+  }
+  prev = __shfl_sync(0xffffffffu, prev, writer_lane);
+  if (prev != (unsigned int)p.tiles_per_state - 1u) return;
+  __threadfence();
+  const Candidate* cd = p.cand + (size_t)b * p.tiles_per_state;
+  double c = 0.0;
+  long long idx = -1;
+  int src = -1;
+  for (int t = lane; t < p.tiles_per_state; t += 32) {
+    const double cc = __ldcg(&cd[t].cost);
+    const long long ii = __ldcg(reinterpret_cast<const long long*>(&cd[t].index));
+    if (ii >= 0 && (idx < 0 || cand_better(cc, (int64_t)ii, c, (int64_t)idx))) { c = cc; idx = ii; src = t; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double oc = __shfl_xor_sync(0xffffffffu, c, off);
+    const long long oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    const int os = __shfl_xor_sync(0xffffffffu, src, off);
+    if (oi >= 0 && (idx < 0 || cand_better(oc, (int64_t)oi, c, (int64_t)idx))) { c = oc; idx = oi; src = os; }
+  }
+  if (lane == 0) {
+    bcmpc_record r;
+    r.cost = idx < 0 ? 0.0 : c;
+    r.index = idx;
+    for (int j = 0; j < kMaxAct; ++j) r.action[j] = src >= 0 ? __ldcg(&cd[src].action[j]) : 0.0;
+    p.out[b] = r;
+    p.ticket[b] = 0u;
+  }
+}
 
 struct NormArgs {
   double mean_obs[kMaxObs], den_obs[kMaxObs];      // den = std + 1e-10  (dynamics.py:109)

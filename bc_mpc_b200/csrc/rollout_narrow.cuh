@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       for (int j = 0; j < kA; ++j) o.action[j] = (double)act0[j];
       for (int j = kA; j < kMaxAct; ++j) o.action[j] = 0.0;
     }
+    if (p.out && (src >> 5) == q) fused_state_minloc(p, b, lane, src & 31);   // (src is the same in the pipe's 128 threads)
   }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();

@@ -1060,6 +1060,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         for (int j = 0; j < kA; ++j) o.action[j] = (double)act0[j];
         for (int j = kA; j < kMaxAct; ++j) o.action[j] = 0.0;
       }
+      if (p.out && (src >> 5) == q) fused_state_minloc(p, b, lane, src & 31);   // (src is the same in all 128 threads)
     }
   }
   ptx::tc_fence_before();
