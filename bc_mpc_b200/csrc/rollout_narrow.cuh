@@ -61,7 +61,7 @@ constexpr NwLayout nw_layout(int nc) {
   L.off_w13 = 2 * kA0Bytes;                       // [W1 chunks][W3 k-blocks]: the resident image of rollout_tmem_kernel
   L.off_w2 = L.off_w13 + L.w1_bytes + L.w3_bytes; // [chunk c][k-block]: its streamed image, all of it
   L.off_vec = L.off_w2 + L.w2_bytes;              // [b2 (64 nc)][b3 (32)]
-  L.off_misc = (L.off_vec + (64u * nc + kOutN) * 4u + 1023u) / 1024u * 1024u;
+  L.off_misc = (L.off_vec + 2u * (64u * nc + kOutN) * 4u + 1023u) / 1024u * 1024u;   // (LayerNorm: [u2][c2][u3][c3])
   L.smem_bytes = L.off_misc + kNwMiscBytes;
   return L;
 }
@@ -70,7 +70,10 @@ struct NwLay {
   static constexpr NwLayout value = nw_layout(NC);
 };
 
-template <int NC, bool DBG>
+// LN: the LayerNorm variant of the dynamics net (dynamics.py:68-69), same algebra as rollout_tmem_kernel - un-normalised
+// ReLU outputs r through the MMAs with W' = diag(gamma) W, then LN(r) W + b = rho (r W') - rho mu u + c in the next epilogue.
+// Every row is handled by ONE thread for all chunks here, so the statistics never leave its registers.
+template <int NC, bool LN, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __grid_constant__ TmArgs a) {
   constexpr int CG = 2;
   constexpr NwLayout L = NwLay<NC>::value;
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
   }
   {
     float* s_vec = reinterpret_cast<float*>(smem + L.off_vec);
-    for (int i = tid; i < 64 * NC + kOutN; i += kThreads) s_vec[i] = a.lnvec[i];
+    for (int i = tid; i < (LN ? 2 : 1) * (64 * NC + kOutN); i += kThreads) s_vec[i] = a.lnvec[i];
   }
   if (warp == 2) ptx::tmem_alloc_cg<CG>(ptx::smem_u32(s_tmem), kTmemCols);
   ptx::tc_fence_before();
@@ -210,8 +213,21 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
     const int kc = valid ? k : p.K - 1;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t a0_row = base + L.off_a0 + t * (uint32_t)kA0Bytes + (uint32_t)row * 128u;
+    // biases [b2 (64 NC)][b3 (32)], or with LayerNorm the correction vectors [u2][c2][u3][c3]
     const float* s_b2 = reinterpret_cast<const float*>(smem + L.off_vec);
     const float* s_b3 = s_b2 + 64 * NC;
+    [[maybe_unused]] const float* s_u2 = s_b2;
+    [[maybe_unused]] const float* s_c2 = s_b2 + 64 * NC;
+    [[maybe_unused]] const float* s_u3 = s_b2 + 2 * 64 * NC;
+    [[maybe_unused]] const float* s_c3 = s_u3 + kOutN;
+    [[maybe_unused]] float ln_sum = 0.f, ln_sq = 0.f, rho = 1.f, rmu = 0.f;
+    auto ln_finish = [&]() {          // statistics of the layer just completed -> rho = 1 / sqrt(var + eps), rmu = rho * mean
+      const float mean = ln_sum * a.ln_inv_n;
+      const float var = fmaxf(ln_sq * a.ln_inv_n - mean * mean, 0.f);
+      rho = rsqrtf(var + a.ln_eps);
+      rmu = rho * mean;
+      ln_sum = 0.f; ln_sq = 0.f;
+    };
     auto arrive = [&](uint32_t id) { ptx::mbar_arrive_remote(ev_leader + 8u * id); };
     float s[kD], z[kA], act0[kA], cost = 0.f;
 #pragma unroll
@@ -232,20 +248,51 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) arrive(empty_id);
-      const float4* b4 = reinterpret_cast<const float4*>(bias);
+      if constexpr (LN) {
+        // bias == nullptr: hidden 1 (plain ReLU of the accumulator); else hidden 2: bias points at u2 of this chunk, c2 follows
+        const float4* u4 = reinterpret_cast<const float4*>(bias);
+        const float4* c4 = reinterpret_cast<const float4*>(bias + 64 * NC);
+        auto relu_stat = [&](float acc, float u, float cc) {
+          float zv = bias ? fmaf(rho, acc, fmaf(-rmu, u, cc)) : acc;
+          zv = zv < 0.f ? 0.f : zv;
+          ln_sum += zv;
+          ln_sq = fmaf(zv, zv, ln_sq);
+          return zv;
+        };
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) bb = b4[i];
-        w0[2 * i] = pack_relu_bf16(__uint_as_float(v0[4 * i]) + bb.x, __uint_as_float(v0[4 * i + 1]) + bb.y);
-        w0[2 * i + 1] = pack_relu_bf16(__uint_as_float(v0[4 * i + 2]) + bb.z, __uint_as_float(v0[4 * i + 3]) + bb.w);
-      }
+        for (int i = 0; i < 8; ++i) {
+          float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), cc = uu;
+          if (bias) { uu = u4[i]; cc = c4[i]; }
+          const float r0 = relu_stat(__uint_as_float(v0[4 * i]), uu.x, cc.x), r1 = relu_stat(__uint_as_float(v0[4 * i + 1]), uu.y, cc.y);
+          const float r2 = relu_stat(__uint_as_float(v0[4 * i + 2]), uu.z, cc.z), r3 = relu_stat(__uint_as_float(v0[4 * i + 3]), uu.w, cc.w);
+          w0[2 * i] = pack_bf16(r0, r1);
+          w0[2 * i + 1] = pack_bf16(r2, r3);
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) bb = b4[8 + i];
-        w1[2 * i] = pack_relu_bf16(__uint_as_float(v1[4 * i]) + bb.x, __uint_as_float(v1[4 * i + 1]) + bb.y);
-        w1[2 * i + 1] = pack_relu_bf16(__uint_as_float(v1[4 * i + 2]) + bb.z, __uint_as_float(v1[4 * i + 3]) + bb.w);
+        for (int i = 0; i < 8; ++i) {
+          float4 uu = make_float4(0.f, 0.f, 0.f, 0.f), cc = uu;
+          if (bias) { uu = u4[8 + i]; cc = c4[8 + i]; }
+          const float r0 = relu_stat(__uint_as_float(v1[4 * i]), uu.x, cc.x), r1 = relu_stat(__uint_as_float(v1[4 * i + 1]), uu.y, cc.y);
+          const float r2 = relu_stat(__uint_as_float(v1[4 * i + 2]), uu.z, cc.z), r3 = relu_stat(__uint_as_float(v1[4 * i + 3]), uu.w, cc.w);
+          w1[2 * i] = pack_bf16(r0, r1);
+          w1[2 * i + 1] = pack_bf16(r2, r3);
+        }
+      } else {
+        const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bb = b4[i];
+          w0[2 * i] = pack_relu_bf16(__uint_as_float(v0[4 * i]) + bb.x, __uint_as_float(v0[4 * i + 1]) + bb.y);
+          w0[2 * i + 1] = pack_relu_bf16(__uint_as_float(v0[4 * i + 2]) + bb.z, __uint_as_float(v0[4 * i + 3]) + bb.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bb = b4[8 + i];
+          w1[2 * i] = pack_relu_bf16(__uint_as_float(v1[4 * i]) + bb.x, __uint_as_float(v1[4 * i + 1]) + bb.y);
+          w1[2 * i + 1] = pack_relu_bf16(__uint_as_float(v1[4 * i + 2]) + bb.z, __uint_as_float(v1[4 * i + 3]) + bb.w);
+        }
       }
       if (wait_id >= 0) {
         ptx::mbar_wait(ev + 8u * (uint32_t)wait_id, par, hc);       // layer 3 has consumed the previous hidden-2 chunk
@@ -275,10 +322,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
 #pragma unroll 1
       for (uint32_t c = 0; c < (uint32_t)NC; ++c)
         chunk(par, kNwDFull1 + c, kNwDEmpty1 + c, (c & 1u) ? cX : cD0, cA1 + 32u * c, kNwA1Ready + c, -1, nullptr);
+      if constexpr (LN) ln_finish();                                        // statistics of hidden 1
       if (h + 1 < H) get_noise<DBG, false>(a, b, h + 1, kc, z);            // next step's randomness, off the critical path
 #pragma unroll 1
       for (uint32_t c = 0; c < (uint32_t)NC; ++c)
         chunk(par, kNwDFull2 + c, kNwDEmpty2 + c, cD0, cX, kNwA2Ready + c, c > 0 ? (int)(kNwA2Empty + c - 1) : -1, s_b2 + 64u * c);
+      if constexpr (LN) ln_finish();                                        // statistics of hidden 2
       ptx::mbar_wait(ev + 8u * kNwD3Full, par, hc);
       ptx::tc_fence_after();
       uint32_t v[32];
@@ -287,7 +336,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       ptx::tc_fence_before();
       float delta[kD];
 #pragma unroll
-      for (int d = 0; d < kD; ++d) delta[d] = fmaf(__uint_as_float(v[d]) + s_b3[d], a.std_delta[d], a.mean_delta[d]);   // dynamics.py:113
+      for (int d = 0; d < kD; ++d) {
+        const float y = LN ? fmaf(rho, __uint_as_float(v[d]), fmaf(-rmu, s_u3[d], s_c3[d])) : __uint_as_float(v[d]) + s_b3[d];
+        delta[d] = fmaf(y, a.std_delta[d], a.mean_delta[d]);                 // dynamics.py:113
+      }
       if (s[5] >= 0.2f) cost += 10.f;                                      // cost_functions.py:16-26 (pre-step state)
       if (s[6] >= 0.f) cost += 10.f;
       if (s[7] >= 0.f) cost += 10.f;
@@ -338,9 +390,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
   if (warp == 2) ptx::tmem_dealloc_cg<CG>(0u, kTmemCols);
 }
 
-template <int NC, bool DBG>
+template <int NC, bool LN, bool DBG>
 inline cudaError_t nw_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = rollout_narrow_kernel<NC, DBG>;
+  auto kern = rollout_narrow_kernel<NC, LN, DBG>;
   constexpr NwLayout L = NwLay<NC>::value;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes);
   if (e != cudaSuccess) return e;
@@ -356,10 +408,10 @@ inline cudaError_t nw_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 // grid.x = tiles / 2 (two tiles per CTA), tiles a multiple of 4 (two CTAs per pair); one translation unit per flavour
-cudaError_t nw_launch_prod(int nc, const TmArgs& a, dim3 grid, cudaStream_t st);
-cudaError_t nw_launch_dbg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st);
-inline cudaError_t nw_launch(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
-  return tm_needs_debug_flavour(a.p) ? nw_launch_dbg(nc, a, grid, st) : nw_launch_prod(nc, a, grid, st);
+cudaError_t nw_launch_prod(int nc, bool ln, const TmArgs& a, dim3 grid, cudaStream_t st);
+cudaError_t nw_launch_dbg(int nc, bool ln, const TmArgs& a, dim3 grid, cudaStream_t st);
+inline cudaError_t nw_launch(int nc, bool ln, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  return tm_needs_debug_flavour(a.p) ? nw_launch_dbg(nc, ln, a, grid, st) : nw_launch_prod(nc, ln, a, grid, st);
 }
 
 }  // namespace tmx

@@ -515,3 +515,37 @@ def test_narrow_kernel_tracks_oracle_and_matches_the_wide_kernel(monkeypatch, S)
         assert np.array_equal(sw, so) and np.array_equal(cw, co)
     else:
         assert np.abs(_norm_err(sw, so, norm)).max() < 0.3
+
+
+@pytest.mark.parametrize("S", [256, 150, 64])
+def test_narrow_kernel_layer_norm(monkeypatch, S):
+    """LayerNorm dynamics on the narrow-net kernel (per-path statistics stay in the registers of the row's thread):
+    against the oracle, against the wide kernel, production flavour == debug flavour."""
+    if os.environ.get("BCMPC_TC_CG") == "1":
+        pytest.skip("the narrow kernel is a CTA-pair kernel")
+    K, H = 1000, 10
+    ln = None
+
+    def build(mode):
+        nonlocal ln
+        rng, norm, state, pl, mpc = _narrow_pair(monkeypatch, mode, 19, S, K, H)
+        ln = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(2)]
+        pl.set_layer_norm(ln)
+        mpc.dyn_model.layer_norm = ln
+        return rng, norm, state, pl, mpc
+
+    rng, norm, state, pl, mpc = build("1")
+    actions = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    e = _norm_err(so, dbg["states"], norm)
+    rec = pl.plan(state, inj=actions)[0]
+    regret = (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std()
+    print(dict(S=S, max_state_err_in_delta_std=float(np.abs(e).max()), cost_corr=float(np.corrcoef(co, dbg["costs"])[0, 1]), regret=float(regret)))
+    assert np.abs(e).max() < 0.6 and np.corrcoef(co, dbg["costs"])[0, 1] > 0.98 and regret < 0.5
+    prod = pl.plan(state, seed=77)[0]
+    dbgr = pl.plan(state, inj=pl.sample_injection(77)[0])[0]
+    assert prod["index"] == dbgr["index"] and prod["cost"] == dbgr["cost"]
+    _, _, _, wide, _ = build("0")
+    sw, _, cw = wide.rollout_debug(state, actions)
+    assert np.abs(_norm_err(sw, so, norm)).max() < 0.3          # (the two kernels sum the statistics in different orders)
