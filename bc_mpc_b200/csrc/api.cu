@@ -237,14 +237,13 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 
 // the narrow-net kernel: plain ReLU dynamics of at most 256 hidden units, uniform shooting, CTA pairs
 bool narrow_applies(const bcmpc_handle* h) {
-  return h->tm_narrow_mode != 0 && h->tm_cg == 2 && h->cfg.proposal == BCMPC_PROP_UNIFORM && !h->rew.set &&
-         h->cfg.hidden_size <= 64 * tmx::kNwMaxChunks;
+  return h->tm_narrow_mode != 0 && h->tm_cg == 2 && !h->rew.set && h->cfg.hidden_size <= 64 * tmx::kNwMaxChunks;
 }
 
 int tm_variant(const bcmpc_handle* h) {
   const int pol = h->cfg.proposal != BCMPC_PROP_UNIFORM ? tmx::kVarPolicy : 0;
   int var = pol | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
-  if (narrow_applies(h)) return h->ln_on ? tmx::kVarLayerNorm : tmx::kVarBias;     // rollout_narrow_kernel: explicit biases (or LayerNorm vectors)
+  if (narrow_applies(h)) return pol | (h->ln_on ? tmx::kVarLayerNorm : tmx::kVarBias);     // rollout_narrow_kernel: explicit biases (or LayerNorm vectors)
   // plain ReLU dynamics whose two constant-1 hidden units would need an extra chunk (hidden 63/64, 127/128, 255/256):
   // biases in the epilogues instead
   const int S = h->cfg.hidden_size;
@@ -357,7 +356,7 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   }
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
-  if (h->tm_narrow) CK(h, tmx::nw_launch(P.nc, P.layer_norm, a, dim3(p.tiles_per_state / 2, p.B), st));
+  if (h->tm_narrow) CK(h, tmx::nw_launch(P.nc, P.layer_norm, pol, a, dim3(p.tiles_per_state / 2, p.B), st));
   else CK(h, tmx::tm_launch(h->tm_cg, P.nc, var, a, dim3(p.tiles_per_state, p.B), st));
   CK(h, cudaGetLastError());
   h->launches++;

@@ -41,16 +41,22 @@ enum : int {
   kNwDEmpty2 = 18,     // [4] ... drained
   kNwA2Ready = 22,     // [4] hidden-2 chunk c stored
   kNwA2Empty = 26,     // [4] layer 3 has consumed hidden-2 chunk c
-  kNwNumEv = 30
+  // proposal network (policy-guided shooting), once per step each
+  kNwAp0Ready = 30,    // policy input rows in shared memory                        (epilogue -> issuer)
+  kNwPdFull = 31,      // [4] policy accumulators: layer-1 chunks 0,1, layer-2 chunks 0,1
+  kNwAp1Ready = 35,    // [2] policy hidden-1 chunk stored
+  kNwAp2Ready = 37,    // [2] policy hidden-2 chunk stored
+  kNwPolFull = 39,     // policy output accumulator complete
+  kNwNumEv = 40
 };
 
 struct NwLayout {
   uint32_t blk_h = 0, blk_o = 0, w1_bytes = 0, w3_bytes = 0, w2_bytes = 0;
-  uint32_t off_a0 = 0, off_w13 = 0, off_w2 = 0, off_vec = 0, off_misc = 0, smem_bytes = 0;
+  uint32_t off_a0 = 0, off_w13 = 0, off_w2 = 0, off_vec = 0, off_pol = 0, pol_img_bytes = 0, off_misc = 0, smem_bytes = 0;
 };
-constexpr uint32_t kNwMiscBytes = 1024;      // [weights-landed barrier][2 x 30 events] x 8 B, tmem ptr, 2 x argmin scratch
-constexpr uint32_t kNwOffEv = 8, kNwOffTmemPtr = 8 + 2 * kNwNumEv * 8, kNwOffRed = 640;
-constexpr NwLayout nw_layout(int nc) {
+constexpr uint32_t kNwMiscBytes = 1024;      // [weights-landed barrier][2 x 40 events] x 8 B, tmem ptr, 2 x argmin scratch
+constexpr uint32_t kNwOffEv = 8, kNwOffTmemPtr = 8 + 2 * kNwNumEv * 8, kNwOffRed = 704;
+constexpr NwLayout nw_layout(int nc, bool pol = false) {
   NwLayout L;
   L.blk_h = (kChunk / 2) * 128u;
   L.blk_o = (kOutN / 2) * 128u;
@@ -61,22 +67,26 @@ constexpr NwLayout nw_layout(int nc) {
   L.off_w13 = 2 * kA0Bytes;                       // [W1 chunks][W3 k-blocks]: the resident image of rollout_tmem_kernel
   L.off_w2 = L.off_w13 + L.w1_bytes + L.w3_bytes; // [chunk c][k-block]: its streamed image, all of it
   L.off_vec = L.off_w2 + L.w2_bytes;              // [b2 (64 nc)][b3 (32)]
-  L.off_misc = (L.off_vec + 2u * (64u * nc + kOutN) * 4u + 1023u) / 1024u * 1024u;   // (LayerNorm: [u2][c2][u3][c3])
+  L.off_pol = (L.off_vec + 2u * (64u * nc + kOutN) * 4u + 1023u) / 1024u * 1024u;    // (LayerNorm: [u2][c2][u3][c3])
+  L.pol_img_bytes = pol ? 6u * L.blk_h + 2u * L.blk_o : 0u;                           // proposal network images, then its biases
+  L.off_misc = (L.off_pol + (pol ? L.pol_img_bytes + kPolVecFloats * 4u : 0u) + 1023u) / 1024u * 1024u;
   L.smem_bytes = L.off_misc + kNwMiscBytes;
   return L;
 }
-template <int NC>
+template <int NC, bool POL>
 struct NwLay {
-  static constexpr NwLayout value = nw_layout(NC);
+  static constexpr NwLayout value = nw_layout(NC, POL);
 };
 
 // LN: the LayerNorm variant of the dynamics net (dynamics.py:68-69), same algebra as rollout_tmem_kernel - un-normalised
 // ReLU outputs r through the MMAs with W' = diag(gamma) W, then LN(r) W + b = rho (r W') - rho mu u + c in the next epilogue.
 // Every row is handled by ONE thread for all chunks here, so the statistics never leave its registers.
-template <int NC, bool LN, bool DBG>
+// POL: policy-guided shooting - the proposal network (20 -> <=128 tanh -> <=128 tanh -> 6) runs at the top of every step
+// on the pipe's own accumulators, its hidden activations in the (then idle) A1 columns, exactly as in rollout_tmem_kernel.
+template <int NC, bool LN, bool POL, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __grid_constant__ TmArgs a) {
   constexpr int CG = 2;
-  constexpr NwLayout L = NwLay<NC>::value;
+  constexpr NwLayout L = NwLay<NC, POL>::value;
   constexpr uint32_t kIdescH = ptx::umma_idesc_bf16(kRows * CG, kChunk), kIdescO = ptx::umma_idesc_bf16(kRows * CG, kOutN);
   static_assert(NC >= 1 && NC <= kNwMaxChunks && L.smem_bytes <= (uint32_t)kSmemLimit, "narrow kernel: hidden <= 256");
 
@@ -108,13 +118,21 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
         ptx::mbar_init(ev + 8u * (kNwDEmpty2 + i), 4 * CG);
         ptx::mbar_init(ev + 8u * (kNwA2Ready + i), 4 * CG);
         ptx::mbar_init(ev + 8u * (kNwA2Empty + i), 1);
+        ptx::mbar_init(ev + 8u * (kNwPdFull + i), 1);
       }
+      ptx::mbar_init(ev + 8u * kNwAp0Ready, 4 * CG);
+      ptx::mbar_init(ev + 8u * kNwPolFull, 1);
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(ev + 8u * (kNwAp1Ready + i), 4 * CG); ptx::mbar_init(ev + 8u * (kNwAp2Ready + i), 4 * CG); }
     }
     ptx::fence_mbar_init();
   }
   {
     float* s_vec = reinterpret_cast<float*>(smem + L.off_vec);
     for (int i = tid; i < (LN ? 2 : 1) * (64 * NC + kOutN); i += kThreads) s_vec[i] = a.lnvec[i];
+    if constexpr (POL) {
+      float* s_pv = reinterpret_cast<float*>(smem + L.off_pol + L.pol_img_bytes);
+      for (int i = tid; i < 2 * kPolMaxHidden + kMaxAct; i += kThreads) s_pv[i] = a.polvec[i];
+    }
   }
   if (warp == 2) ptx::tmem_alloc_cg<CG>(ptx::smem_u32(s_tmem), kTmemCols);
   ptx::tc_fence_before();
@@ -126,7 +144,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
     // ===================== weights: every CTA loads its own row halves, once =====================
     if (ptx::elect_one()) {
       constexpr uint32_t w13 = L.w1_bytes + L.w3_bytes, stage = NC * L.blk_h;
-      ptx::mbar_arrive_expect_tx(misc, w13 + L.w2_bytes);
+      ptx::mbar_arrive_expect_tx(misc, w13 + L.w2_bytes + L.pol_img_bytes);
+      if constexpr (POL) {
+        const uint8_t* psrc = a.pol + (size_t)rank * L.pol_img_bytes;
+        for (uint32_t o = 0; o < L.pol_img_bytes; o += 16384u) ptx::bulk_g2s(base + L.off_pol + o, psrc + o, min(16384u, L.pol_img_bytes - o), misc);
+      }
       const uint8_t* src = a.res + (size_t)rank * w13;
       for (uint32_t o = 0; o < w13; o += 16384u) ptx::bulk_g2s(base + L.off_w13 + o, src + o, min(16384u, w13 - o), misc);
       for (int c = 0; c < NC; ++c) {           // streamed image of the pair mode: per chunk [rank][NC k-blocks]
@@ -148,6 +170,48 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       const uint64_t w2desc = ptx::umma_desc_sw128(base + L.off_w2);
       for (int h = 0; h < H; ++h) {
         const uint32_t par = (uint32_t)h & 1u;
+        if constexpr (POL) {
+          // ---- proposal network: input (smem) -> tanh layer -> tanh layer -> action means (D3 columns 0..5) ----
+          const uint64_t wpdesc = ptx::umma_desc_sw128(base + L.off_pol);
+          const uint32_t np1 = (uint32_t)a.np1, np2 = (uint32_t)a.np2;
+          ptx::mbar_wait(ev + 8u * kNwAp0Ready, par, hc);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            for (uint32_t j = 0; j < np1; ++j) {
+#pragma unroll
+              for (uint32_t ks = 0; ks < 2; ++ks)
+                ptx::umma_ss<CG>(j ? cX : cD0, a0desc + 2u * ks, wpdesc + (uint64_t)(j * (L.blk_h >> 4) + 2u * ks), kIdescH, ks);
+              ptx::umma_commit_cg<CG>(ev + 8u * (kNwPdFull + j));
+            }
+          }
+          __syncwarp();
+          if (np1 > 1) ptx::mbar_wait2(ev + 8u * kNwAp1Ready, ev + 8u * (kNwAp1Ready + 1), par, hc);
+          else ptx::mbar_wait(ev + 8u * kNwAp1Ready, par, hc);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            for (uint32_t j = 0; j < np2; ++j) {
+              for (uint32_t kb = 0; kb < np1; ++kb)
+#pragma unroll
+                for (uint32_t ks = 0; ks < 4; ++ks)
+                  ptx::umma_ts<CG>(j ? cX : cD0, cA1 + kb * 32u + ks * 8u, wpdesc + (uint64_t)((2u + j * 2u + kb) * (L.blk_h >> 4) + 2u * ks), kIdescH,
+                                   (kb | ks) ? 1u : 0u);
+              ptx::umma_commit_cg<CG>(ev + 8u * (kNwPdFull + 2 + j));
+            }
+          }
+          __syncwarp();
+          if (np2 > 1) ptx::mbar_wait2(ev + 8u * kNwAp2Ready, ev + 8u * (kNwAp2Ready + 1), par, hc);
+          else ptx::mbar_wait(ev + 8u * kNwAp2Ready, par, hc);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            for (uint32_t kb = 0; kb < np2; ++kb)
+#pragma unroll
+              for (uint32_t ks = 0; ks < 4; ++ks)
+                ptx::umma_ts<CG>(cD3, cA1 + 64u + kb * 32u + ks * 8u, wpdesc + (uint64_t)(6u * (L.blk_h >> 4) + kb * (L.blk_o >> 4) + 2u * ks), kIdescO,
+                                 (kb | ks) ? 1u : 0u);
+            ptx::umma_commit_cg<CG>(ev + 8u * kNwPolFull);
+          }
+          __syncwarp();
+        }
         ptx::mbar_wait(ev + 8u * kNwA0Ready, par, hc);
         // ---- layer 1: chunk c into D0 (even) / X (odd); chunks 2, 3 after chunks 0, 1 have been drained ----
 #pragma unroll
@@ -232,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
     float s[kD], z[kA], act0[kA], cost = 0.f;
 #pragma unroll
     for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)((DBG && p.per_row_states) ? kc : b) * kD + d];
-    get_noise<DBG, false>(a, b, 0, kc, z);
+    get_noise<DBG, POL>(a, b, 0, kc, z);
     if constexpr (DBG) {
       if (p.states_out && valid)
         for (int d = 0; d < kD; ++d) p.states_out[(size_t)k * kD + d] = (double)s[d];
@@ -307,15 +371,65 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
     };
     for (int h = 0; h < H; ++h) {
       const uint32_t par = (uint32_t)h & 1u;
+      float act[kA];
+      if constexpr (POL) {
+        // proposal network (ppo_bc_policy.py:60,70-72 / behavioral_cloning.py:21-26) on the tensor cores
+        build_policy_input(a, a0_row, row, s);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) arrive(kNwAp0Ready);
+        const float* s_pv = reinterpret_cast<const float*>(smem + L.off_pol + L.pol_img_bytes);
+        // one 64-unit chunk of a tanh layer: accumulator + bias -> tanh -> bf16 -> TMEM operand of the next policy layer
+        auto pol_chunk = [&](int layer, int j) {
+          const uint32_t col = j ? cX : cD0, dst = cA1 + (layer == 1 ? 0u : 64u) + 32u * (uint32_t)j;
+          const float* bias = s_pv + (layer == 1 ? 0 : kPolMaxHidden) + 64 * j;
+          ptx::mbar_wait(ev + 8u * (uint32_t)(kNwPdFull + (layer - 1) * 2 + j), par, hc);
+          ptx::tc_fence_after();
+          uint32_t v0[32], v1[32], w0[16], w1[16];
+          ptx::tmem_ld32(lane_off + col, v0);
+          ptx::tmem_ld32(lane_off + col + 32u, v1);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            w0[i] = ptx::tanh_bf16x2(pack_bf16(__uint_as_float(v0[2 * i]) + bias[2 * i], __uint_as_float(v0[2 * i + 1]) + bias[2 * i + 1]));
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            w1[i] = ptx::tanh_bf16x2(pack_bf16(__uint_as_float(v1[2 * i]) + bias[32 + 2 * i], __uint_as_float(v1[2 * i + 1]) + bias[32 + 2 * i + 1]));
+          ptx::tmem_st16(lane_off + dst, w0);
+          ptx::tmem_st16(lane_off + dst + 16u, w1);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive((uint32_t)((layer == 1 ? kNwAp1Ready : kNwAp2Ready) + j));
+        };
+        for (int j = 0; j < a.np1; ++j) pol_chunk(1, j);
+        for (int j = 0; j < a.np2; ++j) pol_chunk(2, j);
+        ptx::mbar_wait(ev + 8u * kNwPolFull, par, hc);
+        ptx::tc_fence_after();
+        uint32_t vm[32];
+        ptx::tmem_ld32(lane_off + cD3, vm);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+#pragma unroll
+        for (int j = 0; j < kA; ++j) {
+          const float mean = __uint_as_float(vm[j]) + s_pv[2 * kPolMaxHidden + j];
+          if (a.proposal == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
+          else if (a.proposal == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
+          else act[j] = mean + z[j];                                                                                   // controllers.pyc (BC + U[-1,1))
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kA; ++j) act[j] = z[j];                          // controllers.py:70: the sampled action itself
+      }
       if (h == 0) {
 #pragma unroll
-        for (int j = 0; j < kA; ++j) act0[j] = z[j];
+        for (int j = 0; j < kA; ++j) act0[j] = act[j];
       }
       if constexpr (DBG) {
         if (p.actions_out && valid)
-          for (int j = 0; j < kA; ++j) p.actions_out[((size_t)h * p.K + k) * kA + j] = (double)z[j];
+          for (int j = 0; j < kA; ++j) p.actions_out[((size_t)h * p.K + k) * kA + j] = (double)act[j];
       }
-      build_input(a, a0_row, row, s, z);                                    // controllers.py:70: the sampled action itself
+      build_input(a, a0_row, row, s, act);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) arrive(kNwA0Ready);
@@ -323,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       for (uint32_t c = 0; c < (uint32_t)NC; ++c)
         chunk(par, kNwDFull1 + c, kNwDEmpty1 + c, (c & 1u) ? cX : cD0, cA1 + 32u * c, kNwA1Ready + c, -1, nullptr);
       if constexpr (LN) ln_finish();                                        // statistics of hidden 1
-      if (h + 1 < H) get_noise<DBG, false>(a, b, h + 1, kc, z);            // next step's randomness, off the critical path
+      if (h + 1 < H) get_noise<DBG, POL>(a, b, h + 1, kc, z);              // next step's randomness, off the critical path
 #pragma unroll 1
       for (uint32_t c = 0; c < (uint32_t)NC; ++c)
         chunk(par, kNwDFull2 + c, kNwDEmpty2 + c, cD0, cX, kNwA2Ready + c, c > 0 ? (int)(kNwA2Empty + c - 1) : -1, s_b2 + 64u * c);
@@ -390,10 +504,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
   if (warp == 2) ptx::tmem_dealloc_cg<CG>(0u, kTmemCols);
 }
 
-template <int NC, bool LN, bool DBG>
+template <int NC, bool LN, bool POL, bool DBG>
 inline cudaError_t nw_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = rollout_narrow_kernel<NC, LN, DBG>;
-  constexpr NwLayout L = NwLay<NC>::value;
+  auto kern = rollout_narrow_kernel<NC, LN, POL, DBG>;
+  constexpr NwLayout L = NwLay<NC, POL>::value;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -408,10 +522,10 @@ inline cudaError_t nw_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 // grid.x = tiles / 2 (two tiles per CTA), tiles a multiple of 4 (two CTAs per pair); one translation unit per flavour
-cudaError_t nw_launch_prod(int nc, bool ln, const TmArgs& a, dim3 grid, cudaStream_t st);
-cudaError_t nw_launch_dbg(int nc, bool ln, const TmArgs& a, dim3 grid, cudaStream_t st);
-inline cudaError_t nw_launch(int nc, bool ln, const TmArgs& a, dim3 grid, cudaStream_t st) {
-  return tm_needs_debug_flavour(a.p) ? nw_launch_dbg(nc, ln, a, grid, st) : nw_launch_prod(nc, ln, a, grid, st);
+cudaError_t nw_launch_prod(int nc, bool ln, bool pol, const TmArgs& a, dim3 grid, cudaStream_t st);
+cudaError_t nw_launch_dbg(int nc, bool ln, bool pol, const TmArgs& a, dim3 grid, cudaStream_t st);
+inline cudaError_t nw_launch(int nc, bool ln, bool pol, const TmArgs& a, dim3 grid, cudaStream_t st) {
+  return tm_needs_debug_flavour(a.p) ? nw_launch_dbg(nc, ln, pol, a, grid, st) : nw_launch_prod(nc, ln, pol, a, grid, st);
 }
 
 }  // namespace tmx

@@ -180,8 +180,10 @@ def test_layer_norm_dynamics_variant():
     so2, _, _ = pl.rollout_debug(state, actions)
     assert scaled_rel_err(so2, mpc.rollout(state, actions)[0], state_scale(norm)).max() < TOL
     assert np.abs(so2 - so).max() > 1e-3
-    with pytest.raises(RuntimeError, match="hidden sizes"):   # fast mode: LayerNorm + proposal network is built for 4 / 8 chunks only
-        make_pair(17, (64, 64), 128, 2, precision="bf16", proposal="policy_mix")[3].set_layer_norm([(g[:64], b[:64]) for g, b in ln])
+    # fast mode: LayerNorm + proposal network exists for hidden <= 256 (narrow-net kernel) and 449..512; 320 has no kernel
+    wide_ln = [(np.ones(320, np.float32), np.zeros(320, np.float32))] * 2
+    with pytest.raises(RuntimeError, match="hidden sizes"):
+        make_pair(17, (320, 320), 128, 2, precision="bf16", proposal="policy_mix")[3].set_layer_norm(wide_ln)
 
 
 @pytest.mark.parametrize("tag", ["plain", "ln"])

@@ -549,3 +549,47 @@ def test_narrow_kernel_layer_norm(monkeypatch, S):
     _, _, _, wide, _ = build("0")
     sw, _, cw = wide.rollout_debug(state, actions)
     assert np.abs(_norm_err(sw, so, norm)).max() < 0.3          # (the two kernels sum the statistics in different orders)
+
+
+@pytest.mark.parametrize("S,proposal,ln", [(256, "policy_gaussian", False), (256, "policy_mix", True), (128, "bc_uniform", False),
+                                          (200, "policy_gaussian", True)])
+def test_narrow_kernel_policy_guided(monkeypatch, S, proposal, ln):
+    """Policy-guided shooting (and LayerNorm + policy, the reference's default run at size 256) on the narrow-net kernel:
+    against the oracle, against the wide kernel, production flavour == debug flavour."""
+    if os.environ.get("BCMPC_TC_CG") == "1":
+        pytest.skip("the narrow kernel is a CTA-pair kernel")
+    K, H = 1000, 10
+    lns = None
+
+    def build(mode):
+        nonlocal lns
+        monkeypatch.setenv("BCMPC_NARROW", mode)
+        rng, norm, state, pl, mpc = make_pair(23, (S, S), K, H, precision="bf16", proposal=proposal, bc=proposal == "bc_uniform")
+        if ln:
+            lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(2)]
+            pl.set_layer_norm(lns)
+            mpc.dyn_model.layer_norm = lns
+        return rng, norm, state, pl, mpc
+
+    rng, norm, state, pl, mpc = build("1")
+    inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64) if proposal == "policy_gaussian" else f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, inj, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, inj)
+    e = _norm_err(so, dbg["states"], norm)
+    rec = pl.plan(state, inj=inj)[0]
+    regret = (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std()
+    print(dict(S=S, proposal=proposal, ln=ln, first_action_err=float(np.abs(ao[0] - dbg["actions"][0]).max()),
+               max_state_err_in_delta_std=float(np.abs(e).max()), cost_corr=float(np.corrcoef(co, dbg["costs"])[0, 1]), regret=float(regret)))
+    assert np.abs(ao[0] - dbg["actions"][0]).max() < 0.03
+    assert np.abs(e).max() < 0.6 and np.corrcoef(co, dbg["costs"])[0, 1] > 0.98 and regret < 0.5
+    assert rec["index"] == int(np.argmin(co)) and np.allclose(rec["action"][:6], ao[0, rec["index"]])
+    prod = pl.plan(state, seed=77)[0]
+    dbgr = pl.plan(state, inj=pl.sample_injection(77)[0])[0]
+    assert prod["index"] == dbgr["index"] and prod["cost"] == dbgr["cost"]
+    _, _, _, wide, _ = build("0")
+    sw, aw, cw = wide.rollout_debug(state, inj)
+    assert np.array_equal(aw[0], ao[0])                            # same proposal network images: identical first proposals
+    if S in (128, 256) and not ln:
+        assert np.array_equal(sw, so) and np.array_equal(cw, co)   # ... and identical dynamics images: bit-identical rollouts
+    else:
+        assert np.abs(_norm_err(sw, so, norm)).max() < 0.3
