@@ -267,6 +267,23 @@ def extras():
         out[tag + "_reward_layernorm_selfexp_K400_H30_bf16"] = {"plan_call_ms": 1e3 * dt, "plans_per_s": B / dt, "transitions_per_s_e2e": B * K * H / dt,
                                                                "kernel_ms": k_ms}
         pl.close()
+    # train_mpc_ppo.py's own flag defaults: NNDynamicsModel size=256 with LAYER_NORM, MPCcontrollerPolicyNet with SELFEXP=False,
+    # MPC_EXP=0.5 (deterministic policy mixed with uniform exploration), K=400, H=7 - on the narrow-net kernel (hidden <= 256: two tiles per CTA); one env and 256 envs in lock step
+    rng5, norm5, w5, _ = O.synthetic_problem(0, (256, 256))
+    ln5 = [(np.ones(256, np.float32), np.zeros(256, np.float32))] * 2
+    for tag, B in (("flag_defaults_1env", 1), ("flag_defaults_256envs", 256)):
+        K, H = 400, 7
+        pl = Planner(20, 6, 2, 256, "relu", num_paths=K, horizon=H, max_states=B, precision="bf16", proposal="policy_mix", explore=0.5)
+        pl.set_dynamics(w5)
+        pl.set_layer_norm(ln5)
+        pl.set_normalization(norm5["mean_obs"], norm5["std_obs"], norm5["mean_action"], norm5["std_action"], norm5["mean_deltas"], norm5["std_deltas"])
+        pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+        st = norm5["mean_obs"] + norm5["std_obs"] * np.random.default_rng(3).standard_normal((B, 20))
+        pl.enable_timing(True)
+        dt = time_plans(pl, st, 20)
+        out[tag + "_2x256_layernorm_policy_mix_K400_H7_bf16"] = {"plan_call_ms": 1e3 * dt, "plans_per_s": B / dt, "transitions_per_s_e2e": B * K * H / dt,
+                                                              "kernel_ms": pl.last_kernel_ms()}
+        pl.close()
     # stand-alone sampling stage (replay / debugging aid; the planner itself draws in registers): HBM-bound writes,
     # 6 float64 per (state, step, path) = 48 B per transition
     pl = make(1 << 17, 20, "bf16", B=4)
