@@ -508,6 +508,15 @@ def test_narrow_kernel_tracks_oracle_and_matches_the_wide_kernel(monkeypatch, S)
         _, _, _, p1, _ = _narrow_pair(monkeypatch, "1", 15, S, K1, 3)
         r = p1.plan(state, seed=2)[0]
         assert 0 <= r["index"] < K1
+    # K sharded over three handles (path_offset / total_paths, as on three GPUs): the best shard record is the single plan
+    want = pl.plan(state, seed=5)[0]
+    best = None
+    for lo, hi in ((0, 300), (300, 812), (812, K)):
+        _, _, _, sh, _ = _narrow_pair(monkeypatch, "1", 15, S, hi - lo, H, path_offset=lo, total_paths=K)
+        r = sh.plan(state, seed=5)[0]
+        if best is None or r["cost"] < best["cost"] or (r["cost"] == best["cost"] and r["index"] < best["index"]):
+            best = r
+    assert best["index"] == want["index"] and best["cost"] == want["cost"] and np.array_equal(best["action"], want["action"])
     # against the wide kernel
     _, _, _, wide, _ = _narrow_pair(monkeypatch, "0", 15, S, K, H)
     sw, _, cw = wide.rollout_debug(state, actions)
