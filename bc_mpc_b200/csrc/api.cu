@@ -77,7 +77,10 @@ struct bcmpc_handle {
   bool weights_pending = false;       // plans on other streams wait on ev_weights until it has completed
   unsigned long long* d_trace = nullptr;
   bool tm_ready = false;
-  bool tm_narrow = false; // the narrow-net kernel (hidden <= 256, uniform shooting, CTA pairs) is in use
+  bool tm_narrow = false; // the weight images suit rollout_narrow_kernel (hidden <= 256, CTA pairs, no reward head)
+  bool tm_wide_ok = true; // ... and rollout_tmem_kernel has an instantiation that reads the same images
+  bool tm_use_narrow = false;   // the kernel chosen for the launch in flight (run_plan)
+  int sm_pairs = 74;      // CTA-pair slots of the device (SMs / 2): one wave of rollout_tmem_kernel
   int tm_narrow_mode = 1; // BCMPC_NARROW=0 keeps hidden <= 256 on rollout_tmem_kernel (rollout_narrow_kernel is the default there)
   int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
   uint32_t tm_hint_chain = 0x989680u;   // BCMPC_TC_HINT_CHAIN: mbarrier try_wait suspend hint (ns) on the per-step dependency chain
@@ -263,7 +266,8 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   const tmx::TmHostPlan& P = h->tmp;
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
   h->tm_narrow = narrow_applies(h);
-  if (!h->tm_narrow && !tmx::tm_width_supported(P.nc, tm_variant(h)))
+  h->tm_wide_ok = tmx::tm_width_supported(P.nc, tm_variant(h));
+  if (!h->tm_narrow && !h->tm_wide_ok)
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: this combination (learned-reward model, or LayerNorm with a proposal network) is built for hidden sizes 193..256 and 449..512 (got %d); use BCMPC_PREC_FP32_VERIFY", S);
   if (P.reward && h->ln_on != h->rew_ln_on) {
     // between bcmpc_set_layer_norm and bcmpc_set_reward_layer_norm: the images are packed once all three LayerNorms agree
@@ -356,7 +360,7 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   }
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
-  if (h->tm_narrow) CK(h, tmx::nw_launch(P.nc, P.layer_norm, pol, a, dim3(p.tiles_per_state / 2, p.B), st));
+  if (h->tm_use_narrow) CK(h, tmx::nw_launch(P.nc, P.layer_norm, pol, a, dim3(p.tiles_per_state / 2, p.B), st));
   else CK(h, tmx::tm_launch(h->tm_cg, P.nc, var, a, dim3(p.tiles_per_state, p.B), st));
   CK(h, cudaGetLastError());
   h->launches++;
@@ -381,7 +385,11 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   const int M = fast ? tmx::kRows : h->vM;
   p.tiles_per_state = (p.K + M - 1) / M;
   if (fast && h->tm_cg == 2) p.tiles_per_state = (p.tiles_per_state + 1) / 2 * 2;   // CTA pairs; a padding tile has no valid row
-  if (fast && h->tm_narrow) p.tiles_per_state = (p.tiles_per_state + 3) / 4 * 4;     // narrow kernel: two tiles per CTA of a pair
+  // Hidden <= 256: two kernels read the same weight images.  rollout_narrow_kernel runs two tiles per CTA - ~1.45x the step
+  // time for twice the paths - so it wins as soon as rollout_tmem_kernel would need more than one wave of CTA pairs; a
+  // launch that fits in one wave (the single-state plans of the reference's env loop) is 25-30 % quicker on the wide kernel.
+  h->tm_use_narrow = fast && h->tm_narrow && (!h->tm_wide_ok || (int64_t)p.B * (p.tiles_per_state / 2) > h->sm_pairs);
+  if (h->tm_use_narrow) p.tiles_per_state = (p.tiles_per_state + 3) / 4 * 4;        // two tiles per CTA of a pair
   if (d_out) {
     int rc = ensure_cand(h, (size_t)p.B * p.tiles_per_state);
     if (rc) return rc;
@@ -479,6 +487,11 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
 #endif
   }
   if (const char* s = getenv("BCMPC_NARROW")) h->tm_narrow_mode = atoi(s);
+  {
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess && prop.multiProcessorCount >= 2) h->sm_pairs = prop.multiProcessorCount / 2;
+    if (h->tm_narrow_mode == 2) h->sm_pairs = 0;      // BCMPC_NARROW=2: always the narrow kernel where it applies (tests)
+  }
   if (const char* s = getenv("BCMPC_TC_HINT_CHAIN")) h->tm_hint_chain = (uint32_t)strtoul(s, nullptr, 0);
   cudaError_t e = cudaSetDevice(c.device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

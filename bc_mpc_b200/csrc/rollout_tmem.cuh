@@ -1098,7 +1098,8 @@ inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
 // network and everything with the learned-reward model - for 4 and 8 hidden chunks (hidden sizes 193..256 and
 // 449..512; the reference hard-codes 500 for the reward model, dynamics.py:162, and defaults to 256 / 500 elsewhere).
 inline bool tm_width_supported(int nc, int var) {
-  if (var & kVarBias) return var <= (kVarBias | kVarPolicy) && (nc == 1 || nc == 2 || nc == 4);
+  if (var & kVarBias) return var <= (kVarBias | kVarPolicy) && nc >= 1 && nc <= 4;
+  if (var == (kVarLayerNorm | kVarPolicy)) return (nc >= 1 && nc <= 4) || nc == 8;
   return var < 3 || nc == 4 || nc == 8;
 }
 template <int CG, int VAR, bool DBG>
@@ -1106,8 +1107,14 @@ inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t
   if constexpr ((VAR & kVarBias) != 0) {      // explicit-bias variants: the widths where they save a chunk
     if (nc == 1) return tm_launch_t<CG, 1, VAR, DBG>(a, grid, st);
     if (nc == 2) return tm_launch_t<CG, 2, VAR, DBG>(a, grid, st);
+    if (nc == 3) return tm_launch_t<CG, 3, VAR, DBG>(a, grid, st);
     if (nc == 4) return tm_launch_t<CG, 4, VAR, DBG>(a, grid, st);
     return cudaErrorInvalidValue;
+  }
+  if constexpr (VAR == (kVarLayerNorm | kVarPolicy)) {      // also the narrow widths (shared images with rollout_narrow_kernel)
+    if (nc == 1) return tm_launch_t<CG, 1, VAR, DBG>(a, grid, st);
+    if (nc == 2) return tm_launch_t<CG, 2, VAR, DBG>(a, grid, st);
+    if (nc == 3) return tm_launch_t<CG, 3, VAR, DBG>(a, grid, st);
   }
   if constexpr (VAR < 3) {
     switch (nc) {

@@ -474,6 +474,7 @@ def test_two_devices_in_one_process():
 
 
 def _narrow_pair(monkeypatch, mode, seed, S, K, H, **kw):
+    # BCMPC_NARROW: 0 = wide kernel only, 1 = per launch (narrow when the wide kernel would need more than one wave), 2 = narrow
     monkeypatch.setenv("BCMPC_NARROW", mode)
     return make_pair(seed, (S, S), K, H, precision="bf16", **kw)
 
@@ -485,7 +486,7 @@ def test_narrow_kernel_tracks_oracle_and_matches_the_wide_kernel(monkeypatch, S)
     if os.environ.get("BCMPC_TC_CG") == "1":
         pytest.skip("the narrow kernel is a CTA-pair kernel")
     K, H = 1000, 12
-    rng, norm, state, pl, mpc = _narrow_pair(monkeypatch, "1", 15, S, K, H)
+    rng, norm, state, pl, mpc = _narrow_pair(monkeypatch, "2", 15, S, K, H)
     actions = f32_uniform(rng, (H, K, 6))
     act, dbg = mpc.get_action(state, actions, return_debug=True)
     so, ao, co = pl.rollout_debug(state, actions)
@@ -498,21 +499,21 @@ def test_narrow_kernel_tracks_oracle_and_matches_the_wide_kernel(monkeypatch, S)
     assert rec["index"] == int(np.argmin(co)) and np.array_equal(rec["action"][:6], actions[0, rec["index"]]) and regret < 0.5
     # production flavour == debug flavour; batching; ragged K (tile count padded to a multiple of 4)
     B = 3
-    _, _, _, plb, _ = _narrow_pair(monkeypatch, "1", 15, S, 700, 5, max_states=B)
+    _, _, _, plb, _ = _narrow_pair(monkeypatch, "2", 15, S, 700, 5, max_states=B)
     states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((B, 20))
     prod = plb.plan(states, seed=31)
     inj = plb.sample_injection(31, B)
     dbgr = plb.plan(states, inj=inj)
     assert np.array_equal(prod["index"], dbgr["index"]) and np.array_equal(prod["cost"], dbgr["cost"])
     for K1 in (1, 129):
-        _, _, _, p1, _ = _narrow_pair(monkeypatch, "1", 15, S, K1, 3)
+        _, _, _, p1, _ = _narrow_pair(monkeypatch, "2", 15, S, K1, 3)
         r = p1.plan(state, seed=2)[0]
         assert 0 <= r["index"] < K1
     # K sharded over three handles (path_offset / total_paths, as on three GPUs): the best shard record is the single plan
     want = pl.plan(state, seed=5)[0]
     best = None
     for lo, hi in ((0, 300), (300, 812), (812, K)):
-        _, _, _, sh, _ = _narrow_pair(monkeypatch, "1", 15, S, hi - lo, H, path_offset=lo, total_paths=K)
+        _, _, _, sh, _ = _narrow_pair(monkeypatch, "2", 15, S, hi - lo, H, path_offset=lo, total_paths=K)
         r = sh.plan(state, seed=5)[0]
         if best is None or r["cost"] < best["cost"] or (r["cost"] == best["cost"] and r["index"] < best["index"]):
             best = r
@@ -543,7 +544,7 @@ def test_narrow_kernel_layer_norm(monkeypatch, S):
         mpc.dyn_model.layer_norm = ln
         return rng, norm, state, pl, mpc
 
-    rng, norm, state, pl, mpc = build("1")
+    rng, norm, state, pl, mpc = build("2")
     actions = f32_uniform(rng, (H, K, 6))
     act, dbg = mpc.get_action(state, actions, return_debug=True)
     so, ao, co = pl.rollout_debug(state, actions)
@@ -580,7 +581,7 @@ def test_narrow_kernel_policy_guided(monkeypatch, S, proposal, ln):
             mpc.dyn_model.layer_norm = lns
         return rng, norm, state, pl, mpc
 
-    rng, norm, state, pl, mpc = build("1")
+    rng, norm, state, pl, mpc = build("2")
     inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64) if proposal == "policy_gaussian" else f32_uniform(rng, (H, K, 6))
     act, dbg = mpc.get_action(state, inj, return_debug=True)
     so, ao, co = pl.rollout_debug(state, inj)
