@@ -81,6 +81,7 @@ struct bcmpc_handle {
   bool tm_wide_ok = true; // ... and rollout_tmem_kernel has an instantiation that reads the same images
   bool tm_use_narrow = false;   // the kernel chosen for the launch in flight (run_plan)
   int sm_pairs = 74;      // CTA-pair slots of the device (SMs / 2): one wave of rollout_tmem_kernel
+  int narrow_threshold = 74;   // launches with more CTA-pair units than this go to rollout_narrow_kernel (where it applies)
   int tm_narrow_mode = 1; // BCMPC_NARROW=0 keeps hidden <= 256 on rollout_tmem_kernel (rollout_narrow_kernel is the default there)
   int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
   uint32_t tm_hint_chain = 0x989680u;   // BCMPC_TC_HINT_CHAIN: mbarrier try_wait suspend hint (ns) on the per-step dependency chain
@@ -361,7 +362,13 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
   if (h->tm_use_narrow) CK(h, tmx::nw_launch(P.nc, P.layer_norm, pol, a, dim3(p.tiles_per_state / 2, p.B), st));
-  else CK(h, tmx::tm_launch(h->tm_cg, P.nc, var, a, dim3(p.tiles_per_state, p.B), st));
+  else {
+    // persistent CTAs: at most one wave of CTA groups, each rolling its share of the (root state, tile group) units
+    const int64_t units = (int64_t)p.B * (p.tiles_per_state / h->tm_cg);
+    const int64_t slots = h->tm_cg == 2 ? h->sm_pairs : 2 * h->sm_pairs;
+    const unsigned groups = (unsigned)std::min<int64_t>(units, slots);
+    CK(h, tmx::tm_launch(h->tm_cg, P.nc, var, a, dim3(groups * h->tm_cg, 1), st));
+  }
   CK(h, cudaGetLastError());
   h->launches++;
   if (h->d_trace) {
@@ -388,7 +395,7 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   // Hidden <= 256: two kernels read the same weight images.  rollout_narrow_kernel runs two tiles per CTA - ~1.45x the step
   // time for twice the paths - so it wins as soon as rollout_tmem_kernel would need more than one wave of CTA pairs; a
   // launch that fits in one wave (the single-state plans of the reference's env loop) is 25-30 % quicker on the wide kernel.
-  h->tm_use_narrow = fast && h->tm_narrow && (!h->tm_wide_ok || (int64_t)p.B * (p.tiles_per_state / 2) > h->sm_pairs);
+  h->tm_use_narrow = fast && h->tm_narrow && (!h->tm_wide_ok || (int64_t)p.B * (p.tiles_per_state / 2) > h->narrow_threshold);
   if (h->tm_use_narrow) p.tiles_per_state = (p.tiles_per_state + 3) / 4 * 4;        // two tiles per CTA of a pair
   if (d_out) {
     int rc = ensure_cand(h, (size_t)p.B * p.tiles_per_state);
@@ -490,7 +497,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess && prop.multiProcessorCount >= 2) h->sm_pairs = prop.multiProcessorCount / 2;
-    if (h->tm_narrow_mode == 2) h->sm_pairs = 0;      // BCMPC_NARROW=2: always the narrow kernel where it applies (tests)
+    h->narrow_threshold = h->tm_narrow_mode == 2 ? 0 : h->sm_pairs;      // BCMPC_NARROW=2: always the narrow kernel where it applies (tests)
   }
   if (const char* s = getenv("BCMPC_TC_HINT_CHAIN")) h->tm_hint_chain = (uint32_t)strtoul(s, nullptr, 0);
   cudaError_t e = cudaSetDevice(c.device);

@@ -367,6 +367,8 @@ __device__ __forceinline__ void build_policy_input(const TmArgs& a, uint32_t a0_
 // p.inj and writes states_out / actions_out / costs_out.  DBG = false: the production flavour (device-drawn
 // randomness, records only); the same code with those paths compiled out, which is worth ~9 % of the step time
 // (registers, instruction footprint).  BCMPC_TRACE (developer builds, tools/tc_trace.py) adds the pipeline trace.
+__device__ __forceinline__ int p_tiles_per_state(const TmArgs& a) { return a.p.tiles_per_state; }
+
 template <int CG, int NC, int VAR, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
   constexpr bool POL = (VAR & kVarPolicy) != 0, LN = (VAR & kVarLayerNorm) != 0, REW = (VAR & kVarReward) != 0;
@@ -382,8 +384,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   extern __shared__ __align__(1024) uint8_t smem[];
   const PlanArgs& p = a.p;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, b = blockIdx.y;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  // Persistent CTAs: the grid is at most one wave (one CTA group per SM or SM pair); group `first` rolls the work units
+  // first, first + stride, ... (a unit = the CG tiles of one root state that share an MMA) back to back.  TMEM, the
+  // barriers, the resident weight images and the weight ring live across units - a unit boundary is just another step
+  // boundary - so the ~7 us of per-CTA start-up are paid once per launch instead of once per tile.
+  const int units_per_state = p_tiles_per_state(a) / CG;
+  const int total_units = a.p.B * units_per_state;
+  const int first_unit = (int)blockIdx.x / CG, unit_stride = (int)gridDim.x / CG;
+  const int n_it = first_unit < total_units ? (total_units - first_unit + unit_stride - 1) / unit_stride : 0;
   const bool leader = rank == 0;
   const uint32_t base = ptx::smem_u32(smem);
   const uint32_t misc = base + L.off_misc;
@@ -392,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.off_misc + kOffTmemPtr);
   unsigned char* s_red = smem + L.off_misc + kOffRed;
   const int H = p.H;
+  const int Htot = n_it * H;                 // steps this CTA group runs (all of its work units)
 
   if (tid == 0) {
     if (base & 1023u) { printf("bcmpc: dynamic smem base not 1024-byte aligned\n"); __trap(); }
@@ -437,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   // TMEM address a compile-time value.
   if (*s_tmem != 0u) { if (tid == 0) printf("bcmpc: unexpected TMEM base 0x%x\n", *s_tmem); __trap(); }
 #ifdef BCMPC_TRACE
-  const bool tracing = !REW && a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;   // (the trace slots are laid out for NC2 == NC)
+  const bool tracing = !REW && a.trace != nullptr && blockIdx.x == 0;   // (the trace slots are laid out for NC2 == NC; first work unit only)
 #else
   constexpr bool tracing = false;
 #endif
@@ -461,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     }
     __syncwarp();
     uint32_t stage[2] = {0, 0}, phase[2] = {0, 0};
-    for (int h = 0; h < H; ++h) {
+    for (int h = 0; h < Htot; ++h) {
       const uint8_t* src = a.stream + (size_t)rank * L.stage_bytes;
       const bool trp = tracing && h < kTraceSteps;
       for (int c = 0; c < NC2; ++c) {
@@ -494,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       const uint64_t w1desc = ptx::umma_desc_sw128(base + L.off_res);
       const uint32_t nst_mine = (uint32_t)L.nst_r[mine], first_mine = (uint32_t)L.first_r[mine];
       const uint32_t stages_per_step = (uint32_t)kStagesPerStepR[mine];
-      for (int h = 0; h < H; ++h) {
+      for (int h = 0; h < Htot; ++h) {
         const uint32_t uh = (uint32_t)h, par = uh & 1u;
         const bool trw = tracing && h < kTraceSteps;
         if (mine == 1) {
@@ -625,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       if (ptx::elect_one()) ptx::mbar_arrive_remote(misc_leader + kOffResFull);
       __syncwarp();
       uint32_t stage[2] = {0, 0}, phase[2] = {0, 0};
-      for (int h = 0; h < H; ++h) {
+      for (int h = 0; h < Htot; ++h) {
         for (int c = 0; c < NC2; ++c) {
           const int r = c & 1;
           for (int j = 0; j < kNstg; ++j) {
@@ -643,7 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       // ===================== layer-3 MMA issuer: D3 (+)= A2 x W3[chunk] as the hidden-2 chunks appear =====================
       ptx::mbar_wait(misc + kOffResFull, 0);
       const uint64_t w3desc = ptx::umma_desc_sw128(base + L.off_res + L.w1_bytes);
-      for (int h = 0; h < H; ++h) {
+      for (int h = 0; h < Htot; ++h) {
         const uint32_t uh = (uint32_t)h;
         const bool trw = tracing && h < kTraceSteps;
         for (uint32_t c = 0; c < (uint32_t)NC2; ++c) {
@@ -674,6 +684,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     const int q = warp & 3, g = (warp - 4) >> 2, row = q * 32 + lane;
     const bool is_final = g == 0;
     const bool tr = tracing && q == 0 && lane == 0;
+    for (int it = 0; it < n_it; ++it) {      // ---- one work unit: this CTA's tile of one root state, H steps ----
+    const int unit = first_unit + it * unit_stride;
+    const int b = unit / units_per_state, tile = (unit % units_per_state) * CG + (int)rank;
     const int k = tile * kRows + row;
     const bool valid = k < p.K;
     const int kc = valid ? k : p.K - 1;
@@ -703,8 +716,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       }
     }
     for (int h = 0; h < H; ++h) {
-      const uint32_t uh = (uint32_t)h;
-      const bool trh = tr && h < kTraceSteps;
+      const uint32_t uh = (uint32_t)(it * H + h);           // running step of this CTA: the barriers' phase
+      const bool trh = tr && it == 0 && h < kTraceSteps;
       // ---- the action of this step ----
       if constexpr (POL) {
         // proposal network (ppo_bc_policy.py:60,70-72 / behavioral_cloning.py:21-26) on the tensor cores
@@ -1062,6 +1075,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
       }
       if (p.out && (src >> 5) == q) fused_state_minloc(p, b, lane, src & 31);   // (src is the same in all 128 threads)
     }
+    }      // work units
   }
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
