@@ -361,8 +361,12 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   }
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
-  if (h->tm_use_narrow) CK(h, tmx::nw_launch(P.nc, P.layer_norm, pol, a, dim3(p.tiles_per_state / 2, p.B), st));
-  else {
+  if (h->tm_use_narrow) {
+    const int64_t units = (int64_t)p.B * (p.tiles_per_state / 4);          // persistent CTA pairs, four tiles per unit
+    const unsigned groups = (unsigned)std::min<int64_t>(units, h->sm_pairs);
+    CK(h, tmx::nw_launch(P.nc, P.layer_norm, pol, a, dim3(groups * 2, 1), st));
+  }
+  if (!h->tm_use_narrow) {
     // persistent CTAs: at most one wave of CTA groups, each rolling its share of the (root state, tile group) units
     const int64_t units = (int64_t)p.B * (p.tiles_per_state / h->tm_cg);
     const int64_t slots = h->tm_cg == 2 ? h->sm_pairs : 2 * h->sm_pairs;

@@ -93,7 +93,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
   extern __shared__ __align__(1024) uint8_t smem[];
   const PlanArgs& p = a.p;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y;
+  // persistent CTA pairs (as in rollout_tmem_kernel): pair `first_unit` rolls the units first, first + stride, ...;
+  // a unit = four tiles of one root state (two pipes x two CTAs)
+  const int units_per_state = a.p.tiles_per_state / 4;
+  const int total_units = a.p.B * units_per_state;
+  const int first_unit = (int)blockIdx.x / CG, unit_stride = (int)gridDim.x / CG;
+  const int n_it = first_unit < total_units ? (total_units - first_unit + unit_stride - 1) / unit_stride : 0;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
   const uint32_t base = ptx::smem_u32(smem);
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
   const uint32_t misc_leader = ptx::mapa(misc, 0);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.off_misc + kNwOffTmemPtr);
   const int H = p.H;
+  const int Htot = n_it * H;
   const uint32_t hc = a.hint_chain;
 
   if (tid == 0) {
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       const uint64_t w1desc = ptx::umma_desc_sw128(base + L.off_w13);
       const uint64_t w3desc = ptx::umma_desc_sw128(base + L.off_w13 + L.w1_bytes);
       const uint64_t w2desc = ptx::umma_desc_sw128(base + L.off_w2);
-      for (int h = 0; h < H; ++h) {
+      for (int h = 0; h < Htot; ++h) {
         const uint32_t par = (uint32_t)h & 1u;
         if constexpr (POL) {
           // ---- proposal network: input (smem) -> tanh layer -> tanh layer -> action means (D3 columns 0..5) ----
@@ -271,7 +277,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
     const uint32_t ev = misc + kNwOffEv + t * kNwNumEv * 8u;
     const uint32_t ev_leader = misc_leader + kNwOffEv + t * kNwNumEv * 8u;
     const uint32_t cA1 = 256u * t, cD0 = cA1 + 128u, cX = cA1 + 192u, cD3 = cA1 + 224u;
-    const int tile = 2 * (int)blockIdx.x - (int)rank + 2 * (int)t;        // the pair owns tiles 4 pair + 2 t + rank
+    for (int it = 0; it < n_it; ++it) {      // ---- one work unit ----
+    const int unit = first_unit + it * unit_stride;
+    const int b = unit / units_per_state;
+    const int tile = 4 * (unit % units_per_state) + 2 * (int)t + (int)rank;        // the pair's unit owns tiles 4 u + 2 t + rank
     const int k = tile * kRows + row;
     const bool valid = k < p.K;
     const int kc = valid ? k : p.K - 1;
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       if (lane == 0) arrive(ready_id);
     };
     for (int h = 0; h < H; ++h) {
-      const uint32_t par = (uint32_t)h & 1u;
+      const uint32_t par = (uint32_t)(it * H + h) & 1u;        // running step of this CTA: the barriers' phase
       float act[kA];
       if constexpr (POL) {
         // proposal network (ppo_bc_policy.py:60,70-72 / behavioral_cloning.py:21-26) on the tensor cores
@@ -498,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
       for (int j = kA; j < kMaxAct; ++j) o.action[j] = 0.0;
     }
     if (p.out && (src >> 5) == q) fused_state_minloc(p, b, lane, src & 31);   // (src is the same in the pipe's 128 threads)
+    }      // work units
   }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();
