@@ -30,7 +30,7 @@ K_PATHS, HORIZON, STATES_PER_GPU = 4096, 20, 32
 FLOP_PER_TRANSITION = 2 * (26 * 500 + 500 * 500 + 500 * 20)   # 546 000; padding not credited
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload, from the committed ncu --set full
 # capture (the kernel streams its 0.6 MB of weights from L2; states in, 80-byte records out)
-NCU_DRAM_BYTES_PER_LAUNCH = 696576
+NCU_DRAM_BYTES_PER_LAUNCH = 696832
 NCU_TRAFFIC_SOURCE = "profiles/r1k_ncu_full_rollout_tmem.csv"
 
 
