@@ -1,6 +1,7 @@
 // BF16 fast-mode fused rollout kernel (BCMPC_PREC_BF16_FAST): tcgen05.mma with TMEM-resident activations.
 //
-// One CTA owns 128 paths (one TMEM lane per path) for all H steps.  With CG = 2 two CTAs of a cluster form a
+// One CTA owns 128 paths (one TMEM lane per path) for all H steps, then takes the next 128 (persistent CTAs: the grid is
+// one wave and every CTA group rolls its share of the (root state, tile) units back to back).  With CG = 2 two CTAs of a cluster form a
 // cta_group::2 pair: 256 paths per UMMA (M = 256), every weight tile is fetched once per pair (each CTA loads
 // half of its rows) and read by both tensor cores, which halves the L2 -> SM weight stream per path.
 //
