@@ -1035,7 +1035,7 @@ int bcmpc_sample_injection(bcmpc_handle* h, uint64_t seed, int32_t n_states, dou
   auto cleanup = [&]() { cudaFree(d_o); };
   CKC(cudaMalloc(&d_o, sizeof(double) * rows * A));
   if (h->timing) { CKC(cudaEventRecord(h->ev0, h->stream)); }
-  sample_injection_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(
+  sample_injection_kernel<<<dim3((unsigned)((K + kSampleRows - 1) / kSampleRows), (unsigned)H, (unsigned)(n_states < 65535 ? n_states : 65535)), 256, 0, h->stream>>>(
       h->norm, A, K, H, n_states, inj_kind_of(first_proposal_of(h->cfg)), inj_kind_of(h->cfg.proposal), seed, h->cfg.path_offset, d_o);
   CKC(cudaGetLastError());
   if (h->timing) { CKC(cudaEventRecord(h->ev1, h->stream)); h->ev_valid = true; }

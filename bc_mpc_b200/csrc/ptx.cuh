@@ -77,6 +77,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
                : "memory");
 }
 
+// ---- bulk async copy shared -> global (bulk-group completion) ------------------------------------
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the issuing thread's bulk groups have finished READING shared memory (the buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---- tcgen05 --------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
