@@ -87,7 +87,12 @@ __global__ void __launch_bounds__(256) sample_injection_kernel(NormArgs n, int A
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int k = k0 + r * 256 + threadIdx.x;
-      if (k < K) draw_injection(v[r], A, knd, seed, (uint32_t)(path_offset + k), (uint32_t)b, (uint32_t)h, n.low, n.span);
+      if (k < K) {
+        if (A == 6)   // literal width: the draw's per-element predicates fold away
+          draw_injection(v[r], 6, knd, seed, (uint32_t)(path_offset + k), (uint32_t)b, (uint32_t)h, n.low, n.span);
+        else
+          draw_injection(v[r], A, knd, seed, (uint32_t)(path_offset + k), (uint32_t)b, (uint32_t)h, n.low, n.span);
+      }
     }
     if (A == 6) {
 #pragma unroll
