@@ -302,7 +302,7 @@ def extras():
     ms = pl.last_kernel_ms()
     out["cost_stage_standalone"] = {"rows": n, "kernel_ms": ms, "GB_per_s_arrays": (2 * S0.nbytes + 8 * n) / (ms * 1e-3) / 1e9,
                                     "GB_per_s_touched_sectors": (3 * 32 + 8) * n / (ms * 1e-3) / 1e9, "hbm_peak_GB_per_s": hbm_peak(),
-                                    "note": "reads 5 of 40 doubles per row: 3 of 10 32-byte sectors"}
+                                    "note": "reads 5 of 40 doubles per row (3 of 10 32-byte sectors), but ncu shows DRAM fetching 604 of the 671 MB of arrays at 6.6 TB/s (profiles/r1s_ncu_cost_stage.csv): HBM-bound for the row-major layout"}
     del S0
     pl.close()
     # weight refresh after dyn_model.fit (train_mpc_ppo.py:279): host arrays vs device-resident torch parameters
