@@ -440,11 +440,11 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        clocks.wait_ready()               # the poller has produced its first sample before the warm-up (no idle gap after it)
+    barrier()
     for i in range(args.warmup):
         step_resident(i)
         step_e2e(i)
-    if rank == 0:
-        clocks.wait_ready()               # the poller has produced its first sample before the timed regions start
     barrier()
     # ---- resident-input throughput (value) + kernel-only duration for the roofline ----
     pl.enable_timing(True)
@@ -504,7 +504,8 @@ def run_ours(args):
                              "note": "algorithmic FLOPs only (26-500-500-20); padded tiles (32/512/512/32) are not credited"},
                 "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": B * 20 * 8,
                         "d2h_bytes_per_step": B * 80, "plans_per_s": B * args.steps / (e2e_ms * 1e-3)},
-                "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall}
+                "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall,
+                "step_ms": {"first": ms_list[0], "min": min(ms_list), "median": sorted(ms_list)[len(ms_list) // 2], "max": max(ms_list)}}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         if world == 1 and not args.no_extras:
