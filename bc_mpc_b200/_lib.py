@@ -8,6 +8,7 @@ import numpy as np
 from . import _build
 
 MAX_ACT = 8
+ABI_VERSION = 2      # BCMPC_ABI_VERSION of include/bcmpc.h this binding was written against
 
 
 class Config(C.Structure):
@@ -58,6 +59,7 @@ SIGNATURES = {
     "bcmpc_cheetah_cost": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "bcmpc_sample_injection": (C.c_int, [_P, C.c_uint64, C.c_int32, _P]),
     "bcmpc_reduce_records": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "bcmpc_current_device": (C.c_int, [C.POINTER(C.c_int32)]),
     "bcmpc_kernel_launches": (C.c_int64, [_P]),
     "bcmpc_enable_timing": (C.c_int, [_P, C.c_int32]),
     "bcmpc_last_kernel_ms": (C.c_int, [_P, _P]),
@@ -74,19 +76,30 @@ def lib():
         if _build.stale():
             try:
                 _build.build()
-            except Exception as e:  # no nvcc on the box: use the shipped .so if there is one
+            except Exception as e:  # no nvcc on the box: use the shipped .so if there is one, but say so
                 if not os.path.exists(path):
                     raise ImportError(f"libbcmpc.so is missing and could not be built: {e}") from e
+                import warnings
+                warnings.warn(f"bc_mpc_b200: the CUDA sources are newer than libbcmpc.so and the rebuild failed ({e}); "
+                              "loading the existing library", RuntimeWarning)
         if not os.path.exists(path):
             raise ImportError("libbcmpc.so is missing: run `python -m bc_mpc_b200._build`")
         L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.bcmpc_abi_version() != 1:
-            raise ImportError("libbcmpc.so ABI version mismatch")
+        if L.bcmpc_abi_version() != ABI_VERSION:
+            raise ImportError(f"libbcmpc.so ABI version {L.bcmpc_abi_version()} != {ABI_VERSION} expected by this package: "
+                              "rebuild with `python -m bc_mpc_b200._build`")
         _lib = L
     return _lib
+
+
+def current_device():
+    """The calling thread's current CUDA device (what `device=None` resolves to in the helper planners)."""
+    dev = C.c_int32(0)
+    check(lib().bcmpc_current_device(C.byref(dev)))
+    return int(dev.value)
 
 
 def ptr(a):

@@ -72,6 +72,10 @@ class _GpuShootingController(Controller):
     def _explore(self):
         return 1.0
 
+    def _injects(self):
+        """True when this controller's get_action would inject sample_random_actions() instead of drawing on the device."""
+        return self._sampling_overridden() and self.proposal in ("uniform", "policy_mix")
+
     def _ensure_planner(self, n_states=1):
         dm = self.dyn_model
         if self._planner is not None and n_states > self._planner.max_states:
@@ -117,7 +121,9 @@ class _GpuShootingController(Controller):
             raise ValueError(f"states must be [B, obs_dim], got {states.shape}")
         p = self._ensure_planner(states.shape[0])
         seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
-        recs = p.plan(states, seed=seed)
+        # an overridden sample_random_actions is honoured exactly like in get_action: one [H,K,A] draw per root state
+        inj = np.stack([self.sample_random_actions() for _ in range(states.shape[0])]) if self._injects() else None
+        recs = p.plan(states, inj=inj, seed=seed)
         self.last_record = recs
         return recs["action"][:, : self.dyn_model.act_dim].copy()
 

@@ -3,16 +3,18 @@ rollout kernel's epilogue; these stand-alone entry points (used by the reference
 utils.py:128-130 path_cost) run the same arithmetic on the device through bcmpc_cheetah_cost."""
 import numpy as np
 
+from . import _lib
 from .planner import Planner
 
-_cost_planner = None
+_cost_planners = {}
 
 
 def _planner():
-    global _cost_planner
-    if _cost_planner is None:
-        _cost_planner = Planner(num_paths=1, horizon=1, hidden_size=4, n_hidden=1)
-    return _cost_planner
+    """One helper handle per GPU, on the calling thread's CURRENT device (rank r of a multi-GPU job stays on GPU r)."""
+    dev = _lib.current_device()
+    if dev not in _cost_planners:
+        _cost_planners[dev] = Planner(num_paths=1, horizon=1, hidden_size=4, n_hidden=1, device=dev)
+    return _cost_planners[dev]
 
 
 def cheetah_cost_fn(state, action, next_state):

@@ -107,6 +107,25 @@ int fail(bcmpc_handle* h, int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(h, BCMPC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
 
+
+// Every entry point runs on the handle's device and restores the caller's current device on return (a drop-in must not
+// re-point a torch process's current device: allocations and current streams would silently move to another GPU).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    else if (err == cudaSuccess) prev = -1;          // already current: nothing to restore
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(h)                                                                                        \
+  DeviceGuard dev_guard__((h)->cfg.device);                                                                 \
+  if (dev_guard__.err != cudaSuccess) return fail(h, BCMPC_ERR_CUDA, "cudaSetDevice(%d): %s", (h)->cfg.device, cudaGetErrorString(dev_guard__.err))
+
 int round4(int x) { return (x + 3) / 4 * 4; }
 
 // Weight refresh into persistent zero-padded float32 device buffers: a strided copy - from the host or from device
@@ -438,6 +457,24 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   return BCMPC_OK;
 }
 
+// Asynchronous (device-pointer) weight hand-offs are serialised through ONE event: a hand-off on stream B first waits for
+// the previous hand-off's event (which may have been recorded on another stream A), so the latest record implies every
+// earlier hand-off; plans on any stream wait on it (run_plan), and the handle's own stream - where bcmpc_policy_act,
+// bcmpc_predict and the host uploads run - waits on it right away.
+int begin_handoff(bcmpc_handle* h, bool device, cudaStream_t st) {
+  if (device && h->weights_pending && h->ev_weights) CK(h, cudaStreamWaitEvent(st, h->ev_weights, 0));
+  return BCMPC_OK;
+}
+// host (kind = cudaMemcpyHostToDevice, synchronous) and device (cudaMemcpyDeviceToDevice, enqueued on st) variants share these
+int after_handoff(bcmpc_handle* h, bool device, cudaStream_t st) {
+  if (!device) { CK(h, cudaStreamSynchronize(st)); return BCMPC_OK; }
+  if (!h->ev_weights) CK(h, cudaEventCreateWithFlags(&h->ev_weights, cudaEventDisableTiming));
+  CK(h, cudaEventRecord(h->ev_weights, st));
+  h->weights_pending = true;
+  if (st != h->stream) CK(h, cudaStreamWaitEvent(h->stream, h->ev_weights, 0));
+  return BCMPC_OK;
+}
+
 PlanArgs base_plan_args(bcmpc_handle* h, int B, uint64_t seed) {
   PlanArgs p;
   memset(&p, 0, sizeof p);
@@ -504,7 +541,8 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
     h->narrow_threshold = h->tm_narrow_mode == 2 ? 0 : h->sm_pairs;      // BCMPC_NARROW=2: always the narrow kernel where it applies (tests)
   }
   if (const char* s = getenv("BCMPC_TC_HINT_CHAIN")) h->tm_hint_chain = (uint32_t)strtoul(s, nullptr, 0);
-  cudaError_t e = cudaSetDevice(c.device);
+  DeviceGuard guard(c.device);        // the caller's current device is restored on return
+  cudaError_t e = guard.err;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
@@ -528,7 +566,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
 
 int bcmpc_destroy(bcmpc_handle* h) {
   if (!h) return BCMPC_OK;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaDeviceSynchronize();
   h->dyn.release();
   h->pol.release();
@@ -554,7 +592,7 @@ int set_dynamics_common(bcmpc_handle* h, const float* const* W, const float* con
   if (n_layers != h->cfg.n_hidden + 1) return fail(h, BCMPC_ERR_INVALID, "n_layers %d != n_hidden+1 = %d", n_layers, h->cfg.n_hidden + 1);
   for (int l = 0; l < n_layers; ++l)
     if (!W[l] || !b[l]) return fail(h, BCMPC_ERR_INVALID, "null weight pointer for layer %d", l);
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   int rc = refresh_dynamics(h, W, b, kind, st);
   if (rc) return rc;
   update_verify_geometry(h);
@@ -565,7 +603,7 @@ int set_dynamics_common(bcmpc_handle* h, const float* const* W, const float* con
 
 int bcmpc_set_dynamics(bcmpc_handle* h, const float* const* W, const float* const* b, int32_t n_layers) {
   if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   CK(h, cudaStreamSynchronize(h->stream));
   int rc = set_dynamics_common(h, W, b, n_layers, cudaMemcpyHostToDevice, h->stream);
   if (rc) return rc;
@@ -577,25 +615,16 @@ int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const flo
                               void* stream) {
   if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (layout != BCMPC_LAYOUT_IN_OUT && layout != BCMPC_LAYOUT_OUT_IN) return fail(h, BCMPC_ERR_INVALID, "unknown layout %d", layout);
+  ON_DEVICE(h);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  int rc = set_dynamics_common(h, dW, db, n_layers, layout == BCMPC_LAYOUT_OUT_IN ? -1 : (int)cudaMemcpyDeviceToDevice, st);
+  int rc = begin_handoff(h, true, st);
   if (rc) return rc;
-  if (!h->ev_weights) CK(h, cudaEventCreateWithFlags(&h->ev_weights, cudaEventDisableTiming));
-  CK(h, cudaEventRecord(h->ev_weights, st));
-  h->weights_pending = true;
-  return BCMPC_OK;
+  rc = set_dynamics_common(h, dW, db, n_layers, layout == BCMPC_LAYOUT_OUT_IN ? -1 : (int)cudaMemcpyDeviceToDevice, st);
+  if (rc) return rc;
+  return after_handoff(h, true, st);
 }
 
 namespace {
-// host (kind = cudaMemcpyHostToDevice, synchronous) and device (cudaMemcpyDeviceToDevice, enqueued on st) variants share these
-int after_handoff(bcmpc_handle* h, bool device, cudaStream_t st) {
-  if (!device) { CK(h, cudaStreamSynchronize(st)); return BCMPC_OK; }
-  if (!h->ev_weights) CK(h, cudaEventCreateWithFlags(&h->ev_weights, cudaEventDisableTiming));
-  CK(h, cudaEventRecord(h->ev_weights, st));
-  h->weights_pending = true;
-  return BCMPC_OK;
-}
-
 int set_layer_norm_common(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps, bool device,
                           cudaStream_t st) {
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
@@ -604,8 +633,9 @@ int set_layer_norm_common(bcmpc_handle* h, const float* const* gamma, const floa
   if (gamma && n_hidden != h->cfg.n_hidden) return fail(h, BCMPC_ERR_INVALID, "n_hidden %d != %d", n_hidden, h->cfg.n_hidden);
   for (int l = 0; l < n_hidden && gamma; ++l)
     if (!gamma[l] || !beta[l]) return fail(h, BCMPC_ERR_INVALID, "null LayerNorm pointer for layer %d", l);
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   if (!device) CK(h, cudaDeviceSynchronize());      // plans and hand-offs on any stream have finished with the old parameters
+  { int rc = begin_handoff(h, device, st); if (rc) return rc; }
   const size_t n = (size_t)h->cfg.hidden_size;
   if (gamma && h->ln_bufs.empty())                   // persistent: [gamma, beta] per hidden layer
     for (int l = 0; l < 2 * h->cfg.n_hidden; ++l) {
@@ -635,8 +665,9 @@ int set_reward_head_common(bcmpc_handle* h, const float* const* W, const float* 
                            double gamma, int kind, bool device, cudaStream_t st) {
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
   if (fast && !h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the reward head");
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   if (!device) CK(h, cudaDeviceSynchronize());
+  { int rc = begin_handoff(h, device, st); if (rc) return rc; }
   if (!W) {
     CK(h, cudaDeviceSynchronize());
     h->rew.release();
@@ -666,8 +697,9 @@ int set_reward_layer_norm_common(bcmpc_handle* h, const float* gamma, const floa
   if (!h->rew.set) return fail(h, BCMPC_ERR_STATE, "reward head not set (bcmpc_set_reward_head)");
   if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   if (!device) CK(h, cudaDeviceSynchronize());
+  { int rc = begin_handoff(h, device, st); if (rc) return rc; }
   const size_t n = (size_t)h->cfg.hidden_size;
   h->rew.desc.ln_gamma[0] = h->rew.desc.ln_beta[0] = nullptr;
   h->rew_ln_on = gamma != nullptr;
@@ -767,7 +799,7 @@ int set_policy_common(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, c
     std::string why;
     if (!tmx::tm_policy_supported(n_layers, sizes, &why)) return fail(h, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
   }
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   int rc = refresh_mlp(h, h->pol, n_layers, sizes, W, b, kind, st);
   if (rc) return rc;
   h->has_filter = filt_mean != nullptr;
@@ -804,7 +836,7 @@ int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, co
                      const float* const* b, const float* logstd, const float* filt_mean, const float* filt_std,
                      float clip) {
   if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   CK(h, cudaStreamSynchronize(h->stream));
   int rc = set_policy_common(h, n_layers, sizes, W, b, logstd, filt_mean, filt_std, clip, cudaMemcpyHostToDevice, h->stream);
   if (rc) return rc;
@@ -817,14 +849,14 @@ int bcmpc_set_policy_device(bcmpc_handle* h, int32_t n_layers, const int32_t* si
                             void* stream) {
   if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (layout != BCMPC_LAYOUT_IN_OUT && layout != BCMPC_LAYOUT_OUT_IN) return fail(h, BCMPC_ERR_INVALID, "unknown layout %d", layout);
+  ON_DEVICE(h);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  int rc = set_policy_common(h, n_layers, sizes, dW, db, logstd, filt_mean, filt_std, clip,
-                             layout == BCMPC_LAYOUT_OUT_IN ? -1 : (int)cudaMemcpyDeviceToDevice, st);
+  int rc = begin_handoff(h, true, st);
   if (rc) return rc;
-  if (!h->ev_weights) CK(h, cudaEventCreateWithFlags(&h->ev_weights, cudaEventDisableTiming));
-  CK(h, cudaEventRecord(h->ev_weights, st));
-  h->weights_pending = true;
-  return BCMPC_OK;
+  rc = set_policy_common(h, n_layers, sizes, dW, db, logstd, filt_mean, filt_std, clip,
+                         layout == BCMPC_LAYOUT_OUT_IN ? -1 : (int)cudaMemcpyDeviceToDevice, st);
+  if (rc) return rc;
+  return after_handoff(h, true, st);
 }
 
 int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj, uint64_t seed,
@@ -833,7 +865,8 @@ int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states,
   if (n_states < 1 || n_states > h->cfg.max_states) return fail(h, BCMPC_ERR_INVALID, "n_states %d out of [1,%d]", n_states, h->cfg.max_states);
   int rc = check_ready(h, needs_policy(h->cfg));
   if (rc) return rc;
-  CK(h, cudaSetDevice(h->cfg.device));
+  if (!h->rew.set && h->cfg.obs_dim < 18) return fail(h, BCMPC_ERR_INVALID, "cheetah_cost_fn indexes obs[17]; obs_dim = %d (set a reward head to plan on a learned reward)", h->cfg.obs_dim);
+  ON_DEVICE(h);
   PlanArgs p = base_plan_args(h, n_states, seed);
   p.states = d_states;
   p.inj = d_inj;
@@ -844,7 +877,7 @@ int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const do
                bcmpc_record* out) {
   if (!h || !states || !out) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_states < 1 || n_states > h->cfg.max_states) return fail(h, BCMPC_ERR_INVALID, "n_states %d out of [1,%d]", n_states, h->cfg.max_states);
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   const size_t sbytes = sizeof(double) * n_states * h->cfg.obs_dim;
   memcpy(h->h_states, states, sbytes);
   CK(h, cudaMemcpyAsync(h->d_states, h->h_states, sbytes, cudaMemcpyHostToDevice, h->stream));
@@ -876,7 +909,7 @@ int bcmpc_rollout_debug(bcmpc_handle* h, const double* state, const double* inj,
   if (!h || !state) return fail(h, BCMPC_ERR_INVALID, "null argument");
   int rc = check_ready(h, needs_policy(h->cfg));
   if (rc) return rc;
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   const int D = h->cfg.obs_dim, A = h->cfg.act_dim, K = h->cfg.num_paths, H = h->cfg.horizon;
   double *d_state = nullptr, *d_inj = nullptr, *d_so = nullptr, *d_ao = nullptr, *d_co = nullptr;
   auto cleanup = [&]() { cudaFree(d_state); cudaFree(d_inj); cudaFree(d_so); cudaFree(d_ao); cudaFree(d_co); };
@@ -911,7 +944,7 @@ int bcmpc_predict(bcmpc_handle* h, const double* states, const double* actions, 
   if (n < 1 || n > 0x7FFFFFFF) return fail(h, BCMPC_ERR_INVALID, "row count out of range");
   int rc = check_ready(h, false);
   if (rc) return rc;
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   const int D = h->cfg.obs_dim, A = h->cfg.act_dim;
   double *d_s = nullptr, *d_a = nullptr, *d_o = nullptr;
   auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_a); cudaFree(d_o); };
@@ -939,7 +972,7 @@ int bcmpc_predict_reward(bcmpc_handle* h, const double* states, const double* ac
   if (!h->rew.set) return fail(h, BCMPC_ERR_STATE, "reward head not set (bcmpc_set_reward_head)");
   int rc = check_ready(h, false);
   if (rc) return rc;
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   const int D = h->cfg.obs_dim, A = h->cfg.act_dim;
   double *d_s = nullptr, *d_a = nullptr, *d_o = nullptr, *d_c = nullptr;
   auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_a); cudaFree(d_o); cudaFree(d_c); };
@@ -968,7 +1001,7 @@ int bcmpc_policy_act(bcmpc_handle* h, const double* obs, const float* noise, int
   if (n < 1 || n > 0x7FFFFFFF) return fail(h, BCMPC_ERR_INVALID, "row count out of range");
   if (!h->pol.set) return fail(h, BCMPC_ERR_STATE, "proposal network not set (bcmpc_set_policy)");
   if (noise && !h->has_logstd) return fail(h, BCMPC_ERR_STATE, "stochastic act needs logstd in bcmpc_set_policy");
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   const int D = h->cfg.obs_dim, A = h->cfg.act_dim;
   double* d_obs = nullptr;
   float *d_noise = nullptr, *d_out = nullptr;
@@ -1005,7 +1038,7 @@ int bcmpc_cheetah_cost(bcmpc_handle* h, const double* states, const double* next
   if (!h || !states || !next_states || !out) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n < 1) return fail(h, BCMPC_ERR_INVALID, "row count out of range");
   if (h->cfg.obs_dim < 18) return fail(h, BCMPC_ERR_INVALID, "cheetah_cost_fn indexes obs[17]; obs_dim = %d", h->cfg.obs_dim);
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   const int D = h->cfg.obs_dim;
   double *d_s = nullptr, *d_n = nullptr, *d_o = nullptr;
   auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_n); cudaFree(d_o); };
@@ -1028,7 +1061,7 @@ int bcmpc_cheetah_cost(bcmpc_handle* h, const double* states, const double* next
 int bcmpc_sample_injection(bcmpc_handle* h, uint64_t seed, int32_t n_states, double* out) {
   if (!h || !out) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_states < 1) return fail(h, BCMPC_ERR_INVALID, "n_states must be >= 1");
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   const int A = h->cfg.act_dim, K = h->cfg.num_paths, H = h->cfg.horizon;
   const int64_t rows = (int64_t)n_states * H * K;
   double* d_o = nullptr;
@@ -1051,11 +1084,20 @@ int bcmpc_reduce_records(bcmpc_handle* h, const bcmpc_record* d_gathered, int32_
                          bcmpc_record* d_out, void* stream) {
   if (!h || !d_gathered || !d_out) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_ranks < 1 || n_states < 1) return fail(h, BCMPC_ERR_INVALID, "n_ranks and n_states must be >= 1");
-  CK(h, cudaSetDevice(h->cfg.device));
+  ON_DEVICE(h);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   reduce_candidates_kernel<<<n_states, 256, 0, st>>>(d_gathered, n_ranks, n_states, 1, d_out);
   CK(h, cudaGetLastError());
   h->launches++;
+  return BCMPC_OK;
+}
+
+int bcmpc_current_device(int32_t* device) {
+  if (!device) return fail(nullptr, BCMPC_ERR_INVALID, "null argument");
+  int d = 0;
+  cudaError_t e = cudaGetDevice(&d);
+  if (e != cudaSuccess) return fail(nullptr, BCMPC_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  *device = d;
   return BCMPC_OK;
 }
 

@@ -5,12 +5,13 @@ The reference builds a TF1 graph and trains it with `fit`; training is out of sc
 reference's checkpoint naming (NNDynamicsModel/dense{,_1,_2}/{kernel,bias}:0, logz.py:78-85)."""
 import numpy as np
 
+from . import _lib
 from .planner import Planner
 
 
 class NNDynamicsModel:
     def __init__(self, env, n_layers, size, activation="relu", output_activation=None, normalization=None,
-                 batch_size=None, iterations=None, learning_rate=None, sess=None, precision="fp32", layer_norm=False):
+                 batch_size=None, iterations=None, learning_rate=None, sess=None, precision="fp32", layer_norm=False, device=None):
         if output_activation is not None:
             raise NotImplementedError("output_activation must be None (train_mpc_ppo.py:540)")
         self.env = env
@@ -29,7 +30,20 @@ class NNDynamicsModel:
         self.layer_norm_params = None          # [(gamma, beta)] per hidden layer
         self.version = 0           # bumped on every weight change; controllers re-upload lazily
         self.precision = precision
+        self.device = device       # GPU of the stand-alone predict(); None = the tensors' device after set_weights_device, else the current device
         self._predictor = None
+
+    def _predict_device(self):
+        """Device of the helper planner behind predict(): the explicit one, else where device-resident weights live, else
+        the calling thread's current CUDA device (never a hard-wired 0: on rank r of a multi-GPU job that would create a
+        context on GPU 0 and dereference GPU-r pointers there)."""
+        if self.device is not None:
+            return int(self.device)
+        if self.device_weights is not None:
+            dev = getattr(self.device_weights[0][0][0], "device", None)
+            if getattr(dev, "index", None) is not None:
+                return int(dev.index)
+        return _lib.current_device()
 
     # -- weight hand-off (replaces tf variables / fit) ------------------------------------------------
     def set_weights(self, weights, layer_norm_params=None):
@@ -84,7 +98,11 @@ class NNDynamicsModel:
         return (self.mean_obs, self.std_obs, self.mean_action, self.std_action, self.mean_deltas, self.std_deltas)
 
     def fit(self, data):
-        raise NotImplementedError("training stays in the host framework; call set_weights() after each fit")
+        """dynamics.py:81-104 trains the TF graph.  This package is the INFERENCE side of the planning path only (SURVEY.md
+        section 8: training is out of scope): train in the host framework and hand the new weights over with
+        set_weights() / set_weights_device() after each fit."""
+        raise NotImplementedError("bc_mpc_b200 is inference-only: train in the host framework, then call set_weights() / "
+                                  "set_weights_device() (see INTEGRATION.md)")
 
     # -- dynamics.py:106-119 --------------------------------------------------------------------------
     def predict(self, unnormalized_state, unnormalized_action):
@@ -92,7 +110,7 @@ class NNDynamicsModel:
         a = np.asarray(unnormalized_action, np.float64)
         if self._predictor is None:
             p = Planner(self.obs_dim, self.act_dim, self.n_layers, self.size, self.activation, num_paths=1,
-                        horizon=1, precision="fp32")
+                        horizon=1, precision="fp32", device=self._predict_device())
             self.upload(p)
             p.set_normalization(*self.normalization6())
             self._predictor = p
@@ -106,10 +124,10 @@ class NNDynamicsRewardModel(NNDynamicsModel):
     (build_network, :162); both are parameters here with those defaults."""
 
     def __init__(self, env, normalization, batch_size=None, iterations=None, learning_rate=None, sess=None, size=500,
-                 activation="tanh", layer_norm=False):
+                 activation="tanh", layer_norm=False, device=None):
         super().__init__(env, n_layers=2, size=size, activation=activation, normalization=normalization,
                          batch_size=batch_size, iterations=iterations, learning_rate=learning_rate, sess=sess,
-                         layer_norm=layer_norm)
+                         layer_norm=layer_norm, device=device)
         self.reward_weights = None
         self.reward_layer_norm = None
 
@@ -159,7 +177,8 @@ class NNDynamicsRewardModel(NNDynamicsModel):
         if self.weights is None and self.device_weights is None:
             raise RuntimeError("NNDynamicsRewardModel has no weights (set_weights / set_weights_device / load_vars)")
         if self._predictor is None:
-            p = Planner(self.obs_dim, self.act_dim, 2, self.size, self.activation, num_paths=1, horizon=1, precision="fp32")
+            p = Planner(self.obs_dim, self.act_dim, 2, self.size, self.activation, num_paths=1, horizon=1, precision="fp32",
+                        device=self._predict_device())
             self.upload(p)
             p.set_normalization(*self.normalization6())
             self.upload_reward_head(p)

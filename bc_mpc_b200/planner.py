@@ -22,6 +22,16 @@ def _stream(stream_ptr):
     return C.c_void_p(int(stream_ptr) or _CUDA_STREAM_LEGACY)
 
 
+def _handoff_stream(stream_ptr, tensor):
+    """Stream of a device-pointer weight hand-off.  None = the stream the producer of `tensor` is (by convention) running on:
+    torch's CURRENT stream of the tensor's device, so that the copy is ordered after the optimiser step that wrote the
+    parameters without any synchronize; for non-torch tensors the handle's own stream (the caller synchronises)."""
+    if stream_ptr is None and type(tensor).__module__.split(".")[0] == "torch":
+        import torch
+        stream_ptr = torch.cuda.current_stream(tensor.device).cuda_stream
+    return _stream(stream_ptr)
+
+
 def _f64(a, shape=None):
     a = np.ascontiguousarray(a, dtype=np.float64)
     if shape is not None and tuple(a.shape) != tuple(shape):
@@ -86,7 +96,8 @@ class Planner:
         """Weight hand-off without a host round trip (bcmpc_set_dynamics_device): weights = [(W, b), ...] of float32
         CUDA tensors on this planner's device (anything with data_ptr() / shape / is_contiguous(), e.g. torch
         parameters), W [in,out] (layout="in_out", TF kernels) or [out,in] (layout="out_in", torch.nn.Linear.weight).
-        Enqueued on stream_ptr (None = the handle's stream); the tensors must stay alive until that stream has run."""
+        Enqueued on stream_ptr (None = torch's current stream of the tensors' device, i.e. ordered after the kernels that
+        produced them; the handle's stream for non-torch tensors); the tensors must stay alive until that stream has run."""
         sizes = [self.D + self.A] + [self.cfg.hidden_size] * self.cfg.n_hidden + [self.D]
         if len(weights) != len(sizes) - 1:
             raise ValueError(f"expected {len(sizes) - 1} layers, got {len(weights)}")
@@ -102,7 +113,7 @@ class Planner:
         Wp = (C.c_void_p * len(weights))(*[w.data_ptr() for w, _ in weights])
         bp = (C.c_void_p * len(weights))(*[b.data_ptr() for _, b in weights])
         self._ck(self._lib.bcmpc_set_dynamics_device(self._h, Wp, bp, len(weights), 0 if layout == "in_out" else 1,
-                                                     _stream(stream_ptr)))
+                                                     _handoff_stream(stream_ptr, weights[0][0])))
 
     def set_layer_norm(self, params, eps=1e-12):
         """LayerNorm after every hidden activation (dynamics.py:68-69): params = [(gamma[size], beta[size]), ...] per
@@ -130,7 +141,7 @@ class Planner:
             self._check_cuda_f32(b, (S,), "LayerNorm beta")
         gp = (C.c_void_p * len(params))(*[g.data_ptr() for g, _ in params])
         bp = (C.c_void_p * len(params))(*[b.data_ptr() for _, b in params])
-        self._ck(self._lib.bcmpc_set_layer_norm_device(self._h, gp, bp, len(params), C.c_float(eps), _stream(stream_ptr)))
+        self._ck(self._lib.bcmpc_set_layer_norm_device(self._h, gp, bp, len(params), C.c_float(eps), _handoff_stream(stream_ptr, params[0][0])))
 
     def set_reward_head_device(self, weights, mean_reward=0.0, std_reward=1.0, gamma=1.0, layer_norm=None, eps=1e-12, layout="in_out",
                                stream_ptr=None):
@@ -144,12 +155,12 @@ class Planner:
         Wp = (C.c_void_p * 2)(*[w.data_ptr() for w, _ in weights])
         bp = (C.c_void_p * 2)(*[b.data_ptr() for _, b in weights])
         self._ck(self._lib.bcmpc_set_reward_head_device(self._h, Wp, bp, 0 if layout == "in_out" else 1, float(mean_reward),
-                                                        float(std_reward), float(gamma), _stream(stream_ptr)))
+                                                        float(std_reward), float(gamma), _handoff_stream(stream_ptr, weights[0][0])))
         if layer_norm is not None:
             self._check_cuda_f32(layer_norm[0], (S,), "reward-head LayerNorm gamma")
             self._check_cuda_f32(layer_norm[1], (S,), "reward-head LayerNorm beta")
             self._ck(self._lib.bcmpc_set_reward_layer_norm_device(self._h, C.c_void_p(layer_norm[0].data_ptr()),
-                                                                  C.c_void_p(layer_norm[1].data_ptr()), C.c_float(eps), _stream(stream_ptr)))
+                                                                  C.c_void_p(layer_norm[1].data_ptr()), C.c_float(eps), _handoff_stream(stream_ptr, layer_norm[0])))
 
     def set_reward_head(self, weights, mean_reward=0.0, std_reward=1.0, gamma=1.0, layer_norm=None, eps=1e-12):
         """Reward head of NNDynamicsRewardModel (dynamics.py:175-178): weights = [(kernel[S,S], bias[S]), (kernel[S,1], bias[1])],
@@ -208,7 +219,7 @@ class Planner:
     def set_policy_device(self, weights, logstd=None, filt_mean=None, filt_std=None, clip=0.0, layout="in_out", stream_ptr=None):
         """Proposal-network hand-off without a host round trip (bcmpc_set_policy_device): weights = [(W, b), ...] float32
         CUDA tensors, W [in,out] (layout="in_out") or [out,in] (layout="out_in", torch.nn.Linear.weight); logstd and the
-        observation-filter statistics are small host arrays.  Enqueued on stream_ptr (None = the handle's stream)."""
+        observation-filter statistics are small host arrays.  Enqueued on stream_ptr (None = torch's current stream)."""
         if layout not in ("in_out", "out_in"):
             raise ValueError("layout must be 'in_out' or 'out_in'")
         dims = [(tuple(w.shape) if layout == "in_out" else tuple(w.shape)[::-1]) for w, _ in weights]
@@ -225,7 +236,7 @@ class Planner:
         Wp = (C.c_void_p * len(weights))(*[w.data_ptr() for w, _ in weights])
         bp = (C.c_void_p * len(weights))(*[b.data_ptr() for _, b in weights])
         self._ck(self._lib.bcmpc_set_policy_device(self._h, len(weights), L.ptr(sizes), Wp, bp, 0 if layout == "in_out" else 1,
-                                                   L.ptr(ls), L.ptr(fm), L.ptr(fs), float(clip or 0.0), _stream(stream_ptr)))
+                                                   L.ptr(ls), L.ptr(fm), L.ptr(fs), float(clip or 0.0), _handoff_stream(stream_ptr, weights[0][0])))
 
     # -- the hot path -----------------------------------------------------------------------------
     def plan(self, states, inj=None, seed=0):

@@ -71,7 +71,12 @@ def traj_segments_vectorized(pi, controller, envs, mpc, horizon, batched=True):
     for t in range(horizon):
         prevac = list(ac)
         for i in range(n):
-            ac[i], vpred[i] = pi.act(ob[i], stochastic=True)                    # :196
+            a_i, v_i = pi.act(ob[i], stochastic=True)                             # :196
+            if v_i is None:
+                raise RuntimeError("traj_segment_generator needs pi.act to return vpred (utils.py:196,238): give the policy its "
+                                   "value head (MlpPolicy.set_value_weights, or load_vars with the pi/vf/* variables)")
+            # the reference's act returns [1,A] / [1] for a 1-D observation and stores them by broadcasting (:208-211)
+            ac[i], vpred[i] = np.asarray(a_i).reshape(-1), float(np.asarray(v_i).reshape(-1)[0])
         if mpc:
             if batched:
                 mpc_ac = list(controller.get_actions(np.asarray(ob, np.float64)))

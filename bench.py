@@ -20,6 +20,13 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # The reference arm is a host-core measurement: use every core.  torch.distributed.run exports OMP_NUM_THREADS=1 to its
+    # workers when nproc > 1, and OpenBLAS sizes its pool from the environment when numpy is first imported - so the
+    # thread count is fixed here, before that import, and reported from threadpoolctl in the line.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -57,7 +64,8 @@ bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlo
 mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
 while True:
     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, *[int(bool(r & b)) for b in bits], flush=True)
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, *[int(bool(r & b)) for b in bits],
+          nv.nvmlDeviceGetPowerUsage(h) / 1000.0, flush=True)
     time.sleep(0.01)
 """
 
@@ -122,16 +130,20 @@ class ClockSampler:
             self.proc.wait()
             for line in open(self.log.name):
                 f = line.split()
-                if len(f) == 7:
-                    self.rows.append((float(f[0]), [f[1], f[2]] + ["Active" if x == "1" else "Not Active" for x in f[3:]]))
+                if len(f) == 8:
+                    self.rows.append((float(f[0]), [f[1], f[2]] + ["Active" if x == "1" else "Not Active" for x in f[3:7]] + [f[7]]))
             os.unlink(self.log.name)
         inside = [r for t, r in self.rows if any(a <= t <= b for a, b in self.regions)]
         rows = inside if inside else [r for _, r in self.rows]
         sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = sorted({self.NAMES[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        pw = [float(r[6]) for r in rows if len(r) >= 7]
+        cap = [r for r in rows if len(r) >= 6 and r[5].lower() == "active"]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "samples_inside_timed_regions": len(inside), "source": self.source}
+                "reasons": reasons, "samples": len(sm), "samples_inside_timed_regions": len(inside), "source": self.source,
+                "power_w_median": float(np.median(pw)) if pw else None, "power_w_max": max(pw) if pw else None,
+                "sw_power_cap_share": len(cap) / len(rows) if rows else None}
 
 
 def problem():
@@ -154,8 +166,8 @@ def cpu_baseline(budget_s=12.0):
         mpc.get_action(state, rng.uniform(-1, 1, (H, K, 6)))   # controllers.py:53 sampling included
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": n * K * H / dt, "unit": "transitions/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{n} plans of configs[0] (1 state x K=1000 x H=15, numpy float32 BLAS predict, all host threads), "
+    return {"value": n * K * H / dt, "unit": "transitions/s", "cores": blas_threads(), "kind": "port",
+            "sample": f"{n} plans of configs[0] (1 state x K=1000 x H=15, numpy float32 BLAS predict, {blas_threads()} BLAS threads on {os.cpu_count()} host cores), "
                       f"{dt:.1f} s; plans/s = {n / dt:.2f}; TF-less restatement = optimistic stand-in for the TF CPU path"}
 
 
@@ -333,12 +345,24 @@ def extras():
     return out
 
 
+def blas_threads():
+    """Threads the BLAS behind numpy will actually use (threadpoolctl), not the core count."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(d["num_threads"]) for d in threadpool_info() if d.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return 1
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; TensorFlow is not installable here) on
-    this arm's config, each step a bounded sample: 1 root state x K=4096 x H=20."""
+    """--impl reference: the reference's CPU algorithm (oracle port; TensorFlow is not installable here) on the host
+    cores, each step a bounded sample of this arm's workload: 1 root state x K=4096 x H=20 (the workload is 32*N such
+    states per step; the rate in transitions/s is comparable, the work per step is not - the line's config says so)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = blas_threads()
     O, rng, norm, weights = problem()
     dyn = O.OracleDynamics(weights, norm)
     mpc = O.OracleMPC(dyn, HORIZON, K_PATHS)
@@ -350,13 +374,20 @@ def run_reference(args):
         mpc.get_action(state, rng.uniform(-1, 1, (HORIZON, K_PATHS, 6)))
     dt = time.perf_counter() - t0
     val = args.steps * K_PATHS * HORIZON / dt
-    sample = "each step = 1 root state x K=4096 x H=20 of the workload (81 920 transitions), oracle port, all host threads"
+    sample = (f"each step = 1 root state x K={K_PATHS} x H={HORIZON} of the workload ({K_PATHS * HORIZON} transitions), oracle port "
+              f"(reference controllers.py / cost_functions.py logic + numpy float32 BLAS predict), {threads} BLAS threads on "
+              f"{os.cpu_count()} host cores (OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS')})")
+    cfg = workload_config(args.gpus)
+    cfg.update({"states": 1, "states_of_the_workload": STATES_PER_GPU * args.gpus,
+                "precision": "float32 MLP / float64 normalise, state carry and cost (dynamics.py:106-119)",
+                "parallelism": f"host CPU, {threads} BLAS threads", "l2": "n/a (host)",
+                "sample": "1 of the workload's root states per step"})
     line = {"impl": "reference", "metric": "dynamics transitions/s (HalfCheetah random-shooting MPC)", "value": val,
             "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "plans_per_s": args.steps / dt,
-            "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": val, "unit": "transitions/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "config": cfg,
+            "cpu_baseline": {"value": val, "unit": "transitions/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -482,6 +513,41 @@ def run_ours(args):
     e2e_ms, _, _ = timed(step_e2e, args.steps, True)
     clocks.end()
     clk = clocks.stop() if rank == 0 else None
+    # ---- sustained leg: seconds of back-to-back batched plans (no L2 flush, no host synchronisation inside), clocks and
+    # power sampled inside it; quoted against the sustained cuBLAS figure of MEASURED_PEAKS.json ----
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(50, int(args.sustain_s * 1.15 / (total_ms / args.steps * 1e-3)))
+        sclk = ClockSampler(local)
+        if rank == 0:
+            sclk.start()
+            sclk.wait_ready()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sclk.begin()
+        e0.record(stream)
+        for i in range(n_sus):
+            step_resident(5000 + i)
+        e1.record(stream)
+        barrier()
+        sclk.end()
+        sus_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sus_ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            sus_s = float(sus_ms.item()) * 1e-3
+            c = sclk.stop()
+            p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            sus_peak = float(json.load(open(p)).get("bf16_tflops_sustained", 1408.5)) if os.path.exists(p) else 1400.0
+            tr_s = B * K_PATHS * HORIZON * n_sus / sus_s
+            tf = tr_s / world * FLOP_PER_TRANSITION / 1e12
+            sustained = {"seconds": sus_s, "steps": n_sus, "transitions_per_s": tr_s, "ms_per_step": 1e3 * sus_s / n_sus,
+                         "tflops_algorithmic_per_gpu": tf, "peak_sustained_tflops": sus_peak, "frac_sustained": tf / sus_peak,
+                         "frac_burst": tf / measured_peaks()[0], "sm_mhz_median": c.get("sm_mhz"), "sm_mhz_min": c.get("sm_min_mhz"),
+                         "power_w_median": c.get("power_w_median"), "power_w_max": c.get("power_w_max"),
+                         "sw_power_cap_share": c.get("sw_power_cap_share"), "reasons": c.get("reasons"), "clock_samples": c.get("samples"),
+                         "note": "back-to-back batched plans on one stream, weights L2-resident, device time from one CUDA event pair "
+                                 "around the whole run (max over ranks); the rollout kernel is > 99 % of each step"}
 
     transitions_per_step = B * K_PATHS * HORIZON                          # all ranks together
     value = transitions_per_step * args.steps / (total_ms * 1e-3)
@@ -504,7 +570,7 @@ def run_ours(args):
                              "note": "algorithmic FLOPs only (26-500-500-20); padded tiles (32/512/512/32) are not credited"},
                 "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": B * 20 * 8,
                         "d2h_bytes_per_step": B * 80, "plans_per_s": B * args.steps / (e2e_ms * 1e-3)},
-                "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall,
+                "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "sustained": sustained,
                 "step_ms": {"first": ms_list[0], "min": min(ms_list), "median": sorted(ms_list)[len(ms_list) // 2], "max": max(ms_list)}}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
@@ -527,6 +593,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="seconds of the sustained leg (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BCMPC_ABI_VERSION 1
+#define BCMPC_ABI_VERSION 2   /* bumped whenever bcmpc_config, bcmpc_record or a signature changes */
 #define BCMPC_MAX_ACT 8      /* action dims carried in a record (HalfCheetah: 6) */
 #define BCMPC_MAX_OBS 32     /* observation dims supported (HalfCheetah: 20)      */
 #define BCMPC_MAX_LAYERS 5   /* dense layers per MLP, output layer included        */
@@ -212,6 +212,11 @@ int bcmpc_sample_injection(bcmpc_handle* h, uint64_t seed, int32_t n_states, dou
  * index on ties, NaN wins (np.argmin, controllers.py:82).  DEVICE buffers, asynchronous. */
 int bcmpc_reduce_records(bcmpc_handle* h, const bcmpc_record* d_gathered, int32_t n_ranks,
                          int32_t n_states, bcmpc_record* d_out, void* stream);
+
+/* The calling thread's current CUDA device: what the Python mirror's helper planners (NNDynamicsModel.predict,
+ * MlpPolicy.act, cheetah_cost_fn) use when no device is given - never a hard-wired device 0.  Every other entry
+ * point runs on its handle's device and RESTORES the caller's current device before it returns. */
+int bcmpc_current_device(int32_t* device);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t bcmpc_kernel_launches(const bcmpc_handle* h);
