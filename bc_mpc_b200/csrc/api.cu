@@ -15,6 +15,8 @@
 #include "rollout_tmem.cuh"
 #include "weight_pack.cuh"
 #include "rollout_narrow.cuh"
+#include "rollout_deep.cuh"
+#include "deep_pack.cuh"
 #include "rollout_verify.cuh"
 
 using namespace bcmpc;
@@ -83,6 +85,9 @@ struct bcmpc_handle {
   int sm_pairs = 74;      // CTA-pair slots of the device (SMs / 2): one wave of rollout_tmem_kernel
   int narrow_threshold = 74;   // launches with more CTA-pair units than this go to rollout_narrow_kernel (where it applies)
   int tm_narrow_mode = 1; // BCMPC_NARROW=0 keeps hidden <= 256 on rollout_tmem_kernel (rollout_narrow_kernel is the default there)
+  bool deep = false;      // the cluster-split kernel (rollout_deep.cuh): n_hidden != 2 or hidden_size > 510
+  int deep_nch = 0;       // 64-unit chunks per K-half
+  int deep_clusters = 0;  // co-resident clusters of four (cudaOccupancyMaxActiveClusters, cached after the first launch)
   int tm_cg = 2;          // BCMPC_TC_CG: CTAs per tcgen05 group (2 = CTA pairs, the default; 1 = single CTAs)
   uint32_t tm_hint_chain = 0x989680u;   // BCMPC_TC_HINT_CHAIN: mbarrier try_wait suspend hint (ns) on the per-step dependency chain
   std::string trace_path; // BCMPC_TC_TRACE: dump the pipeline trace of CTA (0,0) after every launch
@@ -276,7 +281,65 @@ int tm_variant(const bcmpc_handle* h) {
 }
 
 // (re)packs the fast-mode weight images on the device, on stream `st`, from the float32 copies in h->dyn / h->ln_bufs
+// cluster-split kernel: (re)pack its weight image [4 ranks][stages per step][16 KB] and bias vector on the device
+int deep_prepare(bcmpc_handle* h, cudaStream_t st) {
+  const int S = h->cfg.hidden_size, L = h->cfg.n_hidden;
+  const int nch = (S + 127) / 128;
+  h->deep_nch = nch;
+  const size_t img = (size_t)dpx::kCluster * dpx::stages_per_step(nch, L) * dpx::kStageBytes;
+  const size_t vec = ((size_t)(L - 1) * 128 * nch + 32) * sizeof(float);
+  auto ensure = [&](void** ptr, size_t* cap, size_t need) -> cudaError_t {
+    if (need <= *cap) return cudaSuccess;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(ptr, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+  };
+  CK(h, ensure((void**)&h->d_stream, &h->stream_cap, img));
+  CK(h, ensure((void**)&h->d_lnvec, &h->lnvec_cap, vec));
+  dpx::PackArgs a{};
+  const MlpDesc& d = h->dyn.desc;
+  for (int l = 0; l <= L; ++l) { a.W[l] = d.W[l]; a.b[l] = d.b[l]; a.ld[l] = d.out_pad[l]; }
+  a.L = L; a.S = S; a.nch = nch;
+  a.stream = reinterpret_cast<uint16_t*>(h->d_stream); a.vec = h->d_lnvec;
+  CK(h, dpx::deep_pack(a, st));
+  h->launches++;
+  h->tm_ready = true;
+  return BCMPC_OK;
+}
+
+int launch_deep(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
+  if (!h->tm_ready) return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared: set the dynamics weights first");
+  if (h->ln_on) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) has no LayerNorm variant; use BCMPC_PREC_FP32_VERIFY");
+  dpx::DeepArgs a;
+  memset(&a, 0, sizeof a);
+  a.t.p = p;
+  a.t.stream = h->d_stream; a.t.lnvec = h->d_lnvec;
+  a.t.hint_chain = h->tm_hint_chain;
+  for (int d = 0; d < h->cfg.obs_dim; ++d) {
+    a.t.mean_obs[d] = (float)h->norm.mean_obs[d];
+    a.t.inv_den_obs[d] = (float)(1.0 / h->norm.den_obs[d]);
+    a.t.mean_delta[d] = (float)h->norm.mean_delta[d];
+    a.t.std_delta[d] = (float)h->norm.std_delta[d];
+  }
+  for (int j = 0; j < h->cfg.act_dim; ++j) {
+    a.t.mean_act[j] = (float)h->norm.mean_act[j];
+    a.t.inv_den_act[j] = (float)(1.0 / h->norm.den_act[j]);
+    a.t.low[j] = h->norm.low[j];
+    a.t.span[j] = h->norm.span[j];
+  }
+  a.t.proposal = p.proposal; a.t.inj_kind = p.inj_kind;
+  a.n_hidden = h->cfg.n_hidden; a.s_half = 64 * h->deep_nch;
+  const int64_t units = (int64_t)p.B * (p.tiles_per_state / 2);
+  CK(h, dpx::deep_launch(h->deep_nch, a, h->deep_clusters, units, st, &h->deep_clusters));
+  CK(h, cudaGetLastError());
+  h->launches++;
+  return BCMPC_OK;
+}
+
 int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
+  if (h->deep) return deep_prepare(h, st);
   const int S = h->cfg.hidden_size;
   const tmx::TmHostPlan old = h->tmp;
   tmx::tm_geometry(S, h->tm_cg, tm_variant(h), &h->tmp);
@@ -331,6 +394,7 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
 }
 
 int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
+  if (h->deep) return launch_deep(h, p, st);
   if (!h->tm_ready)
     return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared: set the dynamics weights, and with a reward head either all three LayerNorms "
                                     "(bcmpc_set_layer_norm + bcmpc_set_reward_layer_norm) or none");
@@ -414,11 +478,11 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST && !force_verify;
   const int M = fast ? tmx::kRows : h->vM;
   p.tiles_per_state = (p.K + M - 1) / M;
-  if (fast && h->tm_cg == 2) p.tiles_per_state = (p.tiles_per_state + 1) / 2 * 2;   // CTA pairs; a padding tile has no valid row
+  if (fast && (h->tm_cg == 2 || h->deep)) p.tiles_per_state = (p.tiles_per_state + 1) / 2 * 2;   // CTA pairs; a padding tile has no valid row
   // Hidden <= 256: two kernels read the same weight images.  rollout_narrow_kernel runs two tiles per CTA - ~1.45x the step
   // time for twice the paths - so it wins as soon as rollout_tmem_kernel would need more than one wave of CTA pairs; a
   // launch that fits in one wave (the single-state plans of the reference's env loop) is 25-30 % quicker on the wide kernel.
-  h->tm_use_narrow = fast && h->tm_narrow && (!h->tm_wide_ok || (int64_t)p.B * (p.tiles_per_state / 2) > h->narrow_threshold);
+  h->tm_use_narrow = fast && !h->deep && h->tm_narrow && (!h->tm_wide_ok || (int64_t)p.B * (p.tiles_per_state / 2) > h->narrow_threshold);
   if (h->tm_use_narrow) p.tiles_per_state = (p.tiles_per_state + 3) / 4 * 4;        // two tiles per CTA of a pair
   if (d_out) {
     int rc = ensure_cand(h, (size_t)p.B * p.tiles_per_state);
@@ -513,9 +577,12 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   if (c.proposal < BCMPC_PROP_UNIFORM || c.proposal > BCMPC_PROP_POLICY_MEAN) return fail(nullptr, BCMPC_ERR_INVALID, "unknown proposal %d", c.proposal);
   if (c.first_proposal < 0 || c.first_proposal > 1 + BCMPC_PROP_POLICY_MEAN) return fail(nullptr, BCMPC_ERR_INVALID, "unknown first_proposal %d", c.first_proposal);
   if (c.path_offset < 0 || c.path_offset + c.num_paths > 0xFFFFFFFFLL) return fail(nullptr, BCMPC_ERR_INVALID, "path_offset out of range");
+  // bf16 fast mode: two hidden layers of up to 510 units run on rollout_tmem_kernel / rollout_narrow_kernel, everything
+  // wider or deeper (up to 4 x 1024) on the cluster-split rollout_deep_kernel
+  const bool want_deep = c.precision == BCMPC_PREC_BF16_FAST && (c.n_hidden != 2 || c.hidden_size > 510);
   if (c.precision == BCMPC_PREC_BF16_FAST) {
     std::string why;
-    if (!tmx::tm_supported(c, &why)) return fail(nullptr, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
+    if (want_deep ? !dpx::deep_supported(c, &why) : !tmx::tm_supported(c, &why)) return fail(nullptr, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -523,6 +590,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   if (c.device < 0 || c.device >= ndev) return fail(nullptr, BCMPC_ERR_INVALID, "device %d out of [0,%d)", c.device, ndev);
   bcmpc_handle* h = new bcmpc_handle();
   h->cfg = c;
+  h->deep = want_deep;
   if (h->cfg.total_paths <= 0) h->cfg.total_paths = c.path_offset + c.num_paths;
   if (const char* s = getenv("BCMPC_TC_CG")) h->tm_cg = atoi(s) == 2 ? 2 : 1;
   if (const char* s = getenv("BCMPC_TC_TRACE")) {
@@ -629,6 +697,7 @@ int set_layer_norm_common(bcmpc_handle* h, const float* const* gamma, const floa
                           cudaStream_t st) {
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
+  if (fast && h->deep && gamma) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) has no LayerNorm variant; use BCMPC_PREC_FP32_VERIFY");
   if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
   if (gamma && n_hidden != h->cfg.n_hidden) return fail(h, BCMPC_ERR_INVALID, "n_hidden %d != %d", n_hidden, h->cfg.n_hidden);
   for (int l = 0; l < n_hidden && gamma; ++l)
@@ -677,6 +746,7 @@ int set_reward_head_common(bcmpc_handle* h, const float* const* W, const float* 
     return after_handoff(h, device, st);
   }
   if (!b || !W[0] || !W[1] || !b[0] || !b[1]) return fail(h, BCMPC_ERR_INVALID, "null reward-head pointer");
+  if (fast && h->deep) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the learned-reward model runs on rollout_tmem_kernel (n_hidden = 2, hidden_size <= 510)");
   if (fast && h->cfg.activation != BCMPC_ACT_TANH)
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the learned-reward model is built with tanh layers (dynamics.py:162); other activations run in BCMPC_PREC_FP32_VERIFY");
   if (h->cfg.n_hidden != 2) return fail(h, BCMPC_ERR_INVALID, "NNDynamicsRewardModel has a shared layer and one hidden layer per head: n_hidden must be 2");

@@ -1,0 +1,85 @@
+// Device-side packing of the cluster-split kernel's weight image (rollout_deep.cuh).  Included by api.cu only.
+#pragma once
+#include "rollout_deep.cuh"
+
+namespace bcmpc {
+namespace dpx {
+
+// ---------------------------------------------------------------------------------------------------------
+// weight image, packed on the device from the float32 copies the handle keeps (dynamics.py:54-71 layer stack):
+//   per cluster rank r = 2 p + q, per step the stages in consumption order (see the schedule above); a tile is the UMMA B
+//   operand of one (output chunk, k-block): this CTA's half of the chunk's rows (q) x 64 k, K-major SWIZZLE_128B.
+//   Layer 1 carries its bias in the GEMM (input columns 26 / 27 are 1: rows 26 / 27 hold bf16(b), bf16(b - bf16(b))).
+// bias vector: [layer 2 (128 nch)] ... [layer L (128 nch)][output (32)]
+// ---------------------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* W[BCMPC_MAX_LAYERS];
+  const float* b[BCMPC_MAX_LAYERS];
+  int ld[BCMPC_MAX_LAYERS];
+  int L, S, nch;
+  uint16_t* stream;
+  float* vec;
+};
+
+__global__ void pack_deep_kernel(PackArgs a) {
+  const int nch = a.nch, spu = stages_per_use(nch), L = a.L, S = a.S;
+  const int nstg = stages_per_step(nch, L);
+  const size_t per_rank = (size_t)nstg * (kStageBytes / 2);
+  const size_t total = (size_t)kCluster * per_rank;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / per_rank), p = r >> 1, q = r & 1;
+    const size_t er = e % per_rank;
+    const int s = (int)(er / (kStageBytes / 2));
+    const uint32_t off = (uint32_t)(er % (kStageBytes / 2)) * 2u;        // byte offset in the stage
+    uint16_t v = 0;
+    auto untile = [](uint32_t o, int& n_local, int& kk) {                // inverse of sw128_offset within a tile
+      const int g = (int)(o / 1024u), rr = (int)((o % 1024u) / 128u), c16 = (int)((o % 128u) / 16u) ^ rr, e2 = (int)((o % 16u) / 2u);
+      n_local = g * 8 + rr;
+      kk = c16 * 8 + e2;
+    };
+    if (s < spu) {                                                        // ---- layer 1: tiles of own chunks 4 s + t ----
+      const int t = (int)(off / kTileH), c = 4 * s + t;
+      int nl, kk;
+      untile(off % kTileH, nl, kk);
+      const int n = (p * nch + c) * 64 + q * 32 + nl;
+      if (c < nch && n < S) {
+        constexpr int in_dim = kD + kA;
+        if (kk < in_dim) v = tmx::f32_to_bf16(a.W[0][(size_t)kk * a.ld[0] + n]);
+        else if (kk == in_dim) v = tmx::f32_to_bf16(a.b[0][n]);
+        else if (kk == in_dim + 1) v = tmx::f32_to_bf16(__fsub_rn(a.b[0][n], tmx::bf16_to_f32(tmx::f32_to_bf16(a.b[0][n]))));
+      }
+    } else if (s < nstg - 1) {                                            // ---- hidden layers 2..L ----
+      const int s2 = s - spu, per_layer = 2 * nch * spu;
+      const int l = 1 + s2 / per_layer;                                   // weight index (W[l]: hidden l -> hidden l+1)
+      const int rem = s2 % per_layer, use = rem / spu, sg = rem % spu;
+      const int i = use >> 1, own = use & 1;
+      const int gc = (own ? p : 1 - p) * nch + i;                         // global output chunk
+      const int t = (int)(off / kTileH), kb = 4 * sg + t;
+      int nl, kk;
+      untile(off % kTileH, nl, kk);
+      const int k = (p * nch + kb) * 64 + kk, n = gc * 64 + q * 32 + nl;
+      if (kb < nch && k < S && n < S) v = tmx::f32_to_bf16(a.W[l][(size_t)k * a.ld[l] + n]);
+    } else {                                                              // ---- output layer ----
+      const int kb = (int)(off / kTileO);
+      int nl, kk;
+      untile(off % kTileO, nl, kk);
+      const int k = (p * nch + kb) * 64 + kk, n = q * 16 + nl;
+      if (kb < nch && k < S && n < kD) v = tmx::f32_to_bf16(a.W[L][(size_t)k * a.ld[L] + n]);
+    }
+    a.stream[e] = v;
+  }
+  const int sp2 = 2 * nch * 64, nvec = (L - 1) * sp2 + 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < (L - 1) * sp2) { const int l = 1 + i / sp2, n = i % sp2; v = n < S ? a.b[l][n] : 0.f; }
+    else { const int d = i - (L - 1) * sp2; v = d < kD ? a.b[L][d] : 0.f; }
+    a.vec[i] = v;
+  }
+}
+inline cudaError_t deep_pack(const PackArgs& a, cudaStream_t st) {
+  pack_deep_kernel<<<592, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace dpx
+}  // namespace bcmpc

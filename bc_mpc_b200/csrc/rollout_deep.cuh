@@ -1,0 +1,593 @@
+// BF16 fast-mode rollout kernel for WIDE / DEEP dynamics nets: L >= 2 hidden layers of up to 1024 units (BASELINE.json
+// configs[4]: 26 -> 1024 -> 1024 -> 1024 -> 20, K = 2^20 paths x H = 30), uniform shooting, ReLU.
+//
+// Why a third kernel: the hidden activations of a 128-path tile at width 1024 are 256 KB in bf16 - all of TMEM - and a
+// layer needs its whole input alive until its last output chunk, i.e. input + output = 512 KB per 128 paths, more than
+// TMEM (256 KB) + shared memory (227 KB) of one SM.  So the HIDDEN DIMENSION IS SPLIT OVER A CLUSTER OF FOUR CTAs:
+//
+//   cluster rank r = 2 p + q     p = K-half (hidden units [512 p, 512 p + 512)), q = row half (128 of the unit's 256 paths)
+//   CTAs (2p, 2p+1) form a cta_group::2 pair: M = 256 MMAs over the 256 paths, every weight tile fetched once per pair
+//   CTA r keeps ITS K-half of every hidden activation of ITS 128 paths on chip and computes, for every output chunk of a
+//   layer, the PARTIAL sum over its K-half.  Output chunks are owned by the pair whose K-half they belong to: the other
+//   pair's fp32 partial travels through distributed shared memory (CTA r <-> r ^ 2: same paths, other K-half) and the
+//   owner adds it to its own accumulator before bias / ReLU / bf16.  Layer 1 needs no exchange (K = 28 inputs, every
+//   pair computes its own half of the units); the output layer exchanges its 20-column partial both ways, so both pairs
+//   carry identical fp32 states (a + b == b + a) and build their own layer-1 input.
+//
+// Per CTA (NCH = 64-unit chunks per K-half; 8 at width 1024):
+//   TMEM   [0, 32 NCH)            activation "X" (hidden 1, 3, ...): bf16 pairs, A operand from TMEM
+//          [32 NCH, 32 NCH+32 NT) the first NT k-blocks of activation "Y" (hidden 2, 4, ...)
+//          2 x 64 columns          fp32 accumulators (ping-pong); the output layer uses 32 columns of one
+//   smem   A0 (input tile, 16 KB), the last NCH - NT k-blocks of Y as K-major SWIZZLE_128B tiles (A operand from smem),
+//          2 x 32 KB receive slots for the partner's partials, a ring of 16 KB weight stages, the hidden biases
+//   registers (epilogue group 0): state, cost, first action of the path that owns the TMEM lane
+// Activations alternate between X and Y, so a layer's output never overwrites its input.  No activation, state or
+// per-step cost touches HBM; weights stream from L2 (1 MB per pair and hidden layer at width 1024 - the same bytes per
+// FLOP as rollout_tmem_kernel).
+//
+// Schedule of one step (every CTA; "use" = one accumulator buffer's life, buffers alternate):
+//   layer 1      NCH uses: D = A0 x W1[:, own chunk c]                       -> ReLU -> X block c
+//   layer l>=2   2 NCH uses in the order F0 O0 F1 O1 ...: Fi = partial of the partner's chunk i (sent), Oi = partial of own
+//                chunk i (+ the partner's Fi + bias -> ReLU -> block i of the layer's output)
+//   output       1 use: partial of the 20 deltas (exchanged both ways)     -> denormalise, cost, state update, next input
+// Roles (384 threads): warp 0 weight producer; warp 1 MMA issuer (leader CTA of the pair) / "weights landed" forwarder
+// (peer CTA); warp 2 TMEM allocation; warps 4-7 epilogue group 0 (layer-1 even chunks, F sends, output + state), warps
+// 8-11 group 1 (layer-1 odd chunks, O finalisation).  Accumulator buffer g belongs to group g.
+//
+// Replaces dynamics.py:54-71,106-119 (any n_layers / size up to 1024) + cost_functions.py:10-30,59-63 +
+// controllers.py:53,63-85 for HalfCheetah shapes (D = 20, A = 6).
+#pragma once
+#include "rollout_tmem.cuh"
+
+namespace bcmpc {
+namespace dpx {
+
+using tmx::kA;
+using tmx::kD;
+using tmx::kRows;
+using tmx::kThreads;
+
+constexpr int kCluster = 4;
+constexpr int kMaxNch = 8;                      // hidden <= 1024
+constexpr int kMaxHidden = BCMPC_MAX_LAYERS - 1;  // hidden layers (the handle accepts n_hidden + 1 <= BCMPC_MAX_LAYERS)
+constexpr uint32_t kStageBytes = 16384;         // one weight stage: four (64-unit chunk x 64-wide k-block) tiles of this CTA's row half
+constexpr uint32_t kTileH = 4096, kTileO = 2048;   // hidden tile (32 rows x 128 B), output tile (16 rows x 128 B)
+constexpr uint32_t kRecvBytes = 32768;          // one receive slot: 128 rows x 64 fp32
+constexpr uint32_t kA0Bytes = 128 * 128;
+constexpr uint32_t kBlockBytes = 128 * 128;     // one 64-unit k-block of an activation as an smem A tile
+
+__host__ __device__ constexpr int stages_per_use(int nch) { return (nch + 3) / 4; }
+__host__ __device__ constexpr int tmem_y_blocks(int nch) { return nch < 12 - nch ? nch : 12 - nch; }   // NT: Y k-blocks that fit in TMEM next to X and 2 accumulators
+__host__ __device__ constexpr int stages_per_step(int nch, int L) { return stages_per_use(nch) * (1 + (L - 1) * 2 * nch) + 1; }
+
+// misc smem: barriers then scratch
+enum : uint32_t {
+  kBarWFull = 0,        // [8] weight stage landed                  (producer / peer forwarder -> issuer)
+  kBarWEmpty = 64,      // [8] weight stage consumed                (issuer commit -> producer)
+  kBarA0Ready = 128,    // input rows of the step in smem           (group 0 of both CTAs -> issuer)
+  kBarActReady = 136,   // [8] k-block kb of the current layer's output stored (both CTAs -> issuer)
+  kBarAccFull = 200,    // [2] accumulator complete                 (issuer commit -> epilogue of both CTAs)
+  kBarAccEmpty = 216,   // [2] accumulator drained                  (epilogue of both CTAs -> issuer)
+  kBarRecvFull = 232,   // [2] the partner's partial is in my receive slot      (partner's sender threads -> my receiver)
+  kBarRecvEmpty = 248,  // [2] the partner has read ITS receive slot (I may overwrite it)   (partner's receiver threads -> my sender)
+  kOffTmemPtr = 264,
+  kOffRed = 272,        // argmin scratch (128 B)
+  kMiscBytes = 512
+};
+constexpr int kMaxStages = 8;
+
+struct Layout {
+  int nch = 0, L = 0, nt = 0, ns = 0, spu = 0, nst = 0;
+  uint32_t off_a0 = 0, off_y = 0, off_recv = 0, off_vec = 0, vec_bytes = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
+  uint32_t col_x = 0, col_y = 0, col_acc = 0;
+};
+constexpr Layout make_layout(int nch, int max_hidden) {
+  Layout Y;
+  Y.nch = nch; Y.L = max_hidden;
+  Y.nt = tmem_y_blocks(nch); Y.ns = nch - Y.nt; Y.spu = stages_per_use(nch);
+  Y.col_x = 0; Y.col_y = 32u * nch; Y.col_acc = 32u * nch + 32u * Y.nt;
+  Y.off_a0 = 0;
+  Y.off_y = kA0Bytes;
+  Y.off_recv = Y.off_y + Y.ns * kBlockBytes;
+  Y.off_ring = Y.off_recv + 2 * kRecvBytes;
+  // [hidden biases of layers 2..L: own K-half, 64 nch floats each][output bias 32] after the ring (sized for max_hidden layers)
+  Y.vec_bytes = ((uint32_t)(max_hidden - 1) * 64u * nch + 32u) * 4u;
+  const uint32_t fixed = Y.off_ring + ((Y.vec_bytes + 1023u) / 1024u * 1024u) + kMiscBytes;
+  Y.nst = (int)((tmx::kSmemLimit - fixed) / kStageBytes);
+  if (Y.nst > kMaxStages) Y.nst = kMaxStages;
+  Y.off_vec = Y.off_ring + Y.nst * kStageBytes;
+  Y.off_misc = Y.off_vec + (Y.vec_bytes + 1023u) / 1024u * 1024u;
+  Y.smem_bytes = Y.off_misc + kMiscBytes;
+  return Y;
+}
+template <int NCH>
+struct Lay {
+  static constexpr Layout value = make_layout(NCH, kMaxHidden);
+};
+
+struct DeepArgs {
+  tmx::TmArgs t;          // plan arguments, normalisation, hint; t.stream = weight image [4 ranks][stages_per_step][16 KB]; t.lnvec = bias vector
+  int n_hidden;           // L
+  int s_half;             // 64 * NCH: units per K-half (padded)
+};
+
+inline bool deep_supported(const bcmpc_config& c, std::string* why) {
+  if (c.obs_dim != kD || c.act_dim != kA) { *why = "bf16 fast path is specialised for obs_dim=20, act_dim=6 (HalfCheetah)"; return false; }
+  if (c.n_hidden < 2 || c.n_hidden > kMaxHidden) { *why = "bf16 fast path (cluster-split kernel) supports 2..4 hidden layers"; return false; }
+  if (c.hidden_size < 1 || c.hidden_size > 64 * 2 * kMaxNch) { *why = "bf16 fast path supports hidden_size <= 1024"; return false; }
+  if (c.activation != BCMPC_ACT_RELU) { *why = "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) is built for ReLU dynamics"; return false; }
+  if (c.proposal != BCMPC_PROP_UNIFORM || c.first_proposal != 0) { *why = "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) runs uniform shooting; policy-guided proposals run in BCMPC_PREC_FP32_VERIFY there"; return false; }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {      // arrive at `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// TMEM -> registers: this warp's 32 lanes x 32 columns - reuse ptx::tmem_ld32
+
+template <int NCH, bool DBG>
+__global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_constant__ DeepArgs da) {
+  constexpr Layout Y = Lay<NCH>::value;
+  constexpr int NT = Y.nt, SPU = Y.spu, NST = Y.nst;
+  constexpr uint32_t kIdescH = ptx::umma_idesc_bf16(2 * kRows, 64), kIdescO = ptx::umma_idesc_bf16(2 * kRows, 32);
+  static_assert(NCH >= 1 && NCH <= kMaxNch && NST >= 2 && Y.col_acc + 128u <= 512u, "unsupported width");
+  const tmx::TmArgs& a = da.t;
+  const PlanArgs& p = a.p;
+  const int L = da.n_hidden;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t khalf = rank >> 1, qrow = rank & 1u;
+  const bool leader = qrow == 0;
+  const uint32_t base = ptx::smem_u32(smem);
+  const uint32_t misc = base + Y.off_misc;
+  const uint32_t misc_leader = ptx::mapa(misc, rank & ~1u);        // barriers the pair's issuer waits on
+  const uint32_t base_partner = ptx::mapa(base, rank ^ 2u);        // same paths, other K-half
+  const uint32_t misc_partner = base_partner + Y.off_misc;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + Y.off_misc + kOffTmemPtr);
+  // persistent clusters: cluster `first_unit` rolls the units first, first + stride, ...; a unit = 256 paths of one root state
+  const int units_per_state = p.tiles_per_state / 2;
+  const int total_units = p.B * units_per_state;
+  const int first_unit = (int)blockIdx.x / kCluster, unit_stride = (int)gridDim.x / kCluster;
+  const int n_it = first_unit < total_units ? (total_units - first_unit + unit_stride - 1) / unit_stride : 0;
+  const int H = p.H, Htot = n_it * H;
+  const uint32_t hc = a.hint_chain;
+  const int stages_step = SPU * (1 + (L - 1) * 2 * NCH) + 1;
+  const uint32_t xs_step = (uint32_t)(L - 1) * NCH + 1u;           // exchanges per step
+
+  if (tid == 0) {
+    if (base & 1023u) { printf("bcmpc: dynamic smem base not 1024-byte aligned\n"); __trap(); }
+    for (int i = 0; i < kMaxStages; ++i) {
+      ptx::mbar_init(misc + kBarWFull + 8u * i, leader ? 2 : 1);   // leader: own producer + the peer's "my half has landed"
+      ptx::mbar_init(misc + kBarWEmpty + 8u * i, 1);
+    }
+    ptx::mbar_init(misc + kBarA0Ready, 8);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(misc + kBarActReady + 8u * i, 8);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(misc + kBarAccFull + 8u * i, 1);
+      ptx::mbar_init(misc + kBarAccEmpty + 8u * i, 8);
+      ptx::mbar_init(misc + kBarRecvFull + 8u * i, 128);
+      ptx::mbar_init(misc + kBarRecvEmpty + 8u * i, 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  {   // biases: own K-half of every hidden layer >= 2, then the output bias
+    float* s_vec = reinterpret_cast<float*>(smem + Y.off_vec);
+    const int sh = 64 * NCH;
+    for (int i = tid; i < (L - 1) * sh; i += kThreads) s_vec[i] = a.lnvec[(size_t)(i / sh) * (2 * sh) + khalf * sh + (i % sh)];
+    for (int i = tid; i < 32; i += kThreads) s_vec[(L - 1) * sh + i] = a.lnvec[(size_t)(L - 1) * 2 * sh + i];
+  }
+  if (warp == 2) ptx::tmem_alloc_cg<2>(ptx::smem_u32(s_tmem), 512);
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  if (*s_tmem != 0u) { if (tid == 0) printf("bcmpc: unexpected TMEM base 0x%x\n", *s_tmem); __trap(); }
+
+  if (warp == 0) {
+    // ===================== weight producer: every CTA streams its own row halves =====================
+    uint32_t ws = 0;
+    for (int h = 0; h < Htot; ++h) {
+      const uint8_t* src = a.stream + (size_t)rank * stages_step * kStageBytes;
+      for (int s = 0; s < stages_step; ++s) {
+        // bytes of the stage: layer-1 / hidden stages hold up to four 4 KB tiles, the output stage NCH 2 KB tiles
+        uint32_t bytes;
+        if (s == stages_step - 1) bytes = NCH * kTileO;
+        else { const int sg = s < SPU ? s : (s - SPU) % SPU; bytes = (uint32_t)(NCH - 4 * sg < 4 ? NCH - 4 * sg : 4) * kTileH; }
+        const uint32_t stage = ws % NST, ph = (ws / NST) & 1u;
+        ptx::mbar_wait(misc + kBarWEmpty + 8u * stage, ph ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(misc + kBarWFull + 8u * stage, bytes);
+          ptx::bulk_g2s(base + Y.off_ring + stage * kStageBytes, src, bytes, misc + kBarWFull + 8u * stage);
+        }
+        __syncwarp();
+        src += kStageBytes;
+        ++ws;
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer of the pair =====================
+      const uint16_t pair_mask = (uint16_t)(3u << (2u * khalf));
+      const uint64_t a0desc = ptx::umma_desc_sw128(base + Y.off_a0);
+      // Accumulator buffer g belongs to epilogue group g (layer-1 chunk c -> group c & 1, F -> 0, O -> 1, output -> 0), so
+      // every phase of a buffer's full / empty barriers is seen by the same waiters in order (a waiter that skips phases can
+      // mistake "not yet started" for "already complete": the parity bit has only two states).
+      uint32_t nu0 = 0, nu1 = 0, ws = 0, lo = 0;      // uses of buffer 0 / 1, weight stages, layer outputs consumed so far
+      auto acc_wait = [&](uint32_t g) {              // the buffer's previous use has been drained
+        ptx::mbar_wait(misc + kBarAccEmpty + 8u * g, ((g ? nu1 : nu0) & 1u) ^ 1u, hc);
+      };
+      auto acc_done = [&](uint32_t g) { if (g) ++nu1; else ++nu0; };
+      for (int h = 0; h < Htot; ++h) {
+        // ---- layer 1: own chunks, K = 32 (2 k-steps), A from smem ----
+        ptx::mbar_wait(misc + kBarA0Ready, (uint32_t)h & 1u, hc);
+        for (int j = 0; j < SPU; ++j) {
+          const uint32_t stage = ws % NST;
+          ptx::mbar_wait(misc + kBarWFull + 8u * stage, (ws / NST) & 1u);
+          const uint64_t bdesc = ptx::umma_desc_sw128(base + Y.off_ring + stage * kStageBytes);
+          for (int t = 0; t < 4 && 4 * j + t < NCH; ++t) {
+            const uint32_t g = (uint32_t)(4 * j + t) & 1u;
+            acc_wait(g);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t d = Y.col_acc + 64u * g;
+#pragma unroll
+              for (uint32_t ks = 0; ks < 2; ++ks)
+                ptx::umma_ss<2>(d, a0desc + 2u * ks, bdesc + (uint64_t)((uint32_t)t * (kTileH >> 4) + 2u * ks), kIdescH, ks);
+              umma_commit_pair(misc + kBarAccFull + 8u * g, pair_mask);
+            }
+            __syncwarp();
+            acc_done(g);
+          }
+          if (ptx::elect_one()) umma_commit_pair(misc + kBarWEmpty + 8u * stage, pair_mask);
+          __syncwarp();
+          ++ws;
+        }
+        // ---- hidden layers 2..L and the output layer (l == L + 1): A = this CTA's K-half of the previous activation ----
+        for (int l = 2; l <= L + 1; ++l) {
+          const bool in_y = ((l - 1) & 1) == 0;          // hidden 2, 4 live in the Y region (TMEM + smem), 1, 3, 5 in X
+          const bool outl = l == L + 1;
+          const uint32_t par_in = lo & 1u;
+          const int n_use = outl ? 1 : 2 * NCH;
+          for (int i = 0; i < n_use; ++i) {
+            const uint32_t g = outl ? 0u : (uint32_t)i & 1u;       // F (even) -> group 0, O (odd) -> group 1, output -> group 0
+            acc_wait(g);
+            const uint32_t d = Y.col_acc + 64u * g;
+            for (int sg = 0; sg < (outl ? 1 : SPU); ++sg) {
+              const uint32_t stage = ws % NST;
+              ptx::mbar_wait(misc + kBarWFull + 8u * stage, (ws / NST) & 1u);
+              const uint64_t bdesc = ptx::umma_desc_sw128(base + Y.off_ring + stage * kStageBytes);
+              const int nt = outl ? NCH : (NCH - 4 * sg < 4 ? NCH - 4 * sg : 4);
+              const uint32_t idesc = outl ? kIdescO : kIdescH, tile16 = (outl ? kTileO : kTileH) >> 4;
+              // the four k-steps of k-block kb (tile t of the stage): A from TMEM, or from smem for the tail of a Y activation
+              auto issue_kb = [&](int t) {
+                const int kb = 4 * sg + t;
+                const uint64_t bt = bdesc + (uint64_t)((uint32_t)t * tile16);
+                if (in_y && kb >= NT) {
+                  const uint64_t ad = ptx::umma_desc_sw128(base + Y.off_y + (uint32_t)(kb - NT) * kBlockBytes);
+#pragma unroll
+                  for (uint32_t ks = 0; ks < 4; ++ks) ptx::umma_ss<2>(d, ad + 2u * ks, bt + 2u * ks, idesc, (kb | (int)ks) ? 1u : 0u);
+                } else {
+                  const uint32_t ac = (in_y ? Y.col_y : Y.col_x) + 32u * (uint32_t)kb;
+#pragma unroll
+                  for (uint32_t ks = 0; ks < 4; ++ks) ptx::umma_ts<2>(d, ac + 8u * ks, bt + 2u * ks, idesc, (kb | (int)ks) ? 1u : 0u);
+                }
+              };
+              if (i == 0) {
+                // first use of the layer: k-block by k-block behind the epilogues that store its input
+                for (int t = 0; t < nt; ++t) {
+                  ptx::mbar_wait(misc + kBarActReady + 8u * (uint32_t)(4 * sg + t), par_in, hc);
+                  ptx::tc_fence_after();
+                  if (ptx::elect_one()) issue_kb(t);
+                  __syncwarp();
+                }
+              } else {
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+#pragma unroll
+                  for (int t = 0; t < 4; ++t)
+                    if (t < nt) issue_kb(t);
+                }
+                __syncwarp();
+              }
+              if (ptx::elect_one()) umma_commit_pair(misc + kBarWEmpty + 8u * stage, pair_mask);
+              __syncwarp();
+              ++ws;
+            }
+            if (ptx::elect_one()) umma_commit_pair(misc + kBarAccFull + 8u * g, pair_mask);
+            __syncwarp();
+            acc_done(g);
+          }
+          ++lo;
+        }
+      }
+    } else {
+      // ===================== peer CTA: tell the leader when this CTA's weight halves have landed =====================
+      uint32_t ws = 0;
+      for (int h = 0; h < Htot; ++h)
+        for (int s = 0; s < stages_step; ++s) {
+          const uint32_t stage = ws % NST;
+          ptx::mbar_wait(misc + kBarWFull + 8u * stage, (ws / NST) & 1u);
+          if (ptx::elect_one()) ptx::mbar_arrive_remote(misc_leader + kBarWFull + 8u * stage);
+          __syncwarp();
+          ++ws;
+        }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: group g drains accumulator buffer g =====================
+    const int q = warp & 3, g = (warp - 4) >> 2, row = q * 32 + lane;
+    const bool is_final = g == 0;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t a0_row = base + Y.off_a0 + (uint32_t)row * 128u;
+    const float* s_vec = reinterpret_cast<const float*>(smem + Y.off_vec);
+    unsigned char* s_red = smem + Y.off_misc + kOffRed;
+    uint32_t nuse = 0;               // uses of THIS group's accumulator buffer (buffer g) so far
+    uint32_t step = 0;               // running step of this CTA
+    auto arrive_leader = [&](uint32_t bar) { ptx::mbar_arrive_remote(misc_leader + bar); };
+    // this group's next accumulator -> registers (64 or 32 columns), then release the buffer
+    auto drain = [&](uint32_t (&v0)[32], uint32_t (&v1)[32], bool both) {
+      ptx::mbar_wait(misc + kBarAccFull + 8u * (uint32_t)g, nuse & 1u, hc);
+      ++nuse;
+      ptx::tc_fence_after();
+      const uint32_t col = Y.col_acc + 64u * (uint32_t)g;
+      ptx::tmem_ld32(lane_off + col, v0);
+      if (both) ptx::tmem_ld32(lane_off + col + 32u, v1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_leader(kBarAccEmpty + 8u * (uint32_t)g);
+    };
+    // 64 activations of this row (bf16 pairs w0 | w1) -> k-block kb of the X or Y activation, then tell the issuer
+    auto store_block = [&](bool to_y, uint32_t kb, const uint32_t (&w0)[16], const uint32_t (&w1)[16]) {
+      if (to_y && kb >= (uint32_t)NT) {
+        const uint32_t rb = base + Y.off_y + (kb - (uint32_t)NT) * kBlockBytes + (uint32_t)row * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t addr = rb + (uint32_t)(((c ^ (row & 7)) << 4));
+          const uint32_t* w = c < 4 ? &w0[4 * c] : &w1[4 * (c - 4)];
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        }
+        ptx::fence_proxy_async_smem();
+      } else {
+        const uint32_t dst = (to_y ? Y.col_y : Y.col_x) + 32u * kb;
+        ptx::tmem_st16(lane_off + dst, w0);
+        ptx::tmem_st16(lane_off + dst + 16u, w1);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+      }
+      __syncwarp();
+      if (lane == 0) arrive_leader(kBarActReady + 8u * kb);
+    };
+    for (int it = 0; it < n_it; ++it) {      // ---- one work unit: this CTA's 128 paths of one root state, H steps ----
+      const int unit = first_unit + it * unit_stride;
+      const int b = unit / units_per_state, tile = (unit % units_per_state) * 2 + (int)qrow;
+      const int k = tile * kRows + row;
+      const bool valid = k < p.K;
+      const int kc = valid ? k : p.K - 1;
+      const bool writer = khalf == 0;                              // both K-halves carry the state; one reports
+      float s[kD], z[kA], act0[kA], cost = 0.f;
+      if (is_final) {
+#pragma unroll
+        for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)((DBG && p.per_row_states) ? kc : b) * kD + d];
+        tmx::get_noise<DBG, false>(a, b, 0, kc, z);
+        if constexpr (DBG) {
+          if (writer && p.states_out && valid)
+            for (int d = 0; d < kD; ++d) p.states_out[(size_t)k * kD + d] = (double)s[d];
+        }
+      }
+      for (int h = 0; h < H; ++h, ++step) {
+        const uint32_t xbase = step * xs_step;                    // exchange index of the step's first exchanged chunk
+        if (is_final) {
+          if (h == 0) {
+#pragma unroll
+            for (int j = 0; j < kA; ++j) act0[j] = z[j];
+          }
+          if constexpr (DBG) {
+            if (writer && p.actions_out && valid)
+              for (int j = 0; j < kA; ++j) p.actions_out[((size_t)h * p.K + k) * kA + j] = (double)z[j];
+          }
+          tmx::build_input(a, a0_row, row, s, z);                  // controllers.py:70: the sampled action itself
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) arrive_leader(kBarA0Ready);
+        }
+        // ---- layer 1: chunk c -> X block c (bias rides in the GEMM) ----
+#pragma unroll 1
+        for (uint32_t c = (uint32_t)g; c < (uint32_t)NCH; c += 2) {
+          uint32_t v0[32], v1[32], w0[16], w1[16];
+          drain(v0, v1, true);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w0[i] = tmx::pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w1[i] = tmx::pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          store_block(false, c, w0, w1);
+        }
+        // the next step's randomness, drawn where group 0 has slack
+        if (is_final && h + 1 < H) tmx::get_noise<DBG, false>(a, b, h + 1, kc, z);
+        // ---- hidden layers 2..L ----
+        for (int l = 2; l <= L; ++l) {
+          const bool to_y = (l & 1) == 0;
+          const float* bias_l = s_vec + (l - 2) * 64 * NCH;
+#pragma unroll 1
+          for (uint32_t i = 0; i < (uint32_t)NCH; ++i) {
+            const uint32_t x = xbase + (uint32_t)(l - 2) * NCH + i, slot = x & 1u, xph = (x >> 1) & 1u;
+            if (g == 0) {
+              // F: my partial of the PARTNER's chunk i -> the partner's receive slot
+              uint32_t v0[32], v1[32];
+              drain(v0, v1, true);
+              ptx::mbar_wait_cluster(misc + kBarRecvEmpty + 8u * slot, xph ^ 1u);      // the partner has read the slot's previous content
+              const uint32_t dst = base_partner + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) st_cluster_v4(dst + (uint32_t)j * 2048u, v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) st_cluster_v4(dst + (uint32_t)(8 + j) * 2048u, v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]);
+              ptx::mbar_arrive_cluster(misc_partner + kBarRecvFull + 8u * slot);       // release at cluster scope, one arrive per thread
+            } else {
+              // O: own chunk i = my partial + the partner's + bias -> ReLU -> block i of this layer's output
+              uint32_t v0[32], v1[32], w0[16], w1[16];
+              drain(v0, v1, true);
+              ptx::mbar_wait_cluster(misc + kBarRecvFull + 8u * slot, xph);
+              const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+              const float4* b4 = reinterpret_cast<const float4*>(bias_l + 64u * i);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = ld_shared_v4(src + (uint32_t)j * 2048u), bb = b4[j];
+                w0[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v0[4 * j]) + r.x + bb.x, __uint_as_float(v0[4 * j + 1]) + r.y + bb.y);
+                w0[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v0[4 * j + 2]) + r.z + bb.z, __uint_as_float(v0[4 * j + 3]) + r.w + bb.w);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = ld_shared_v4(src + (uint32_t)(8 + j) * 2048u), bb = b4[8 + j];
+                w1[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v1[4 * j]) + r.x + bb.x, __uint_as_float(v1[4 * j + 1]) + r.y + bb.y);
+                w1[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v1[4 * j + 2]) + r.z + bb.z, __uint_as_float(v1[4 * j + 3]) + r.w + bb.w);
+              }
+              ptx::mbar_arrive_cluster(misc_partner + kBarRecvEmpty + 8u * slot);      // my slot may be overwritten (release: after my loads)
+              store_block(to_y, i, w0, w1);
+            }
+          }
+        }
+        // ---- output layer: the two K-half partials of the 20 deltas are exchanged both ways ----
+        if (is_final) {
+          const uint32_t x = xbase + (uint32_t)(L - 1) * NCH, slot = x & 1u, xph = (x >> 1) & 1u;
+          uint32_t v[32], dummy[32];
+          drain(v, dummy, false);
+          ptx::mbar_wait_cluster(misc + kBarRecvEmpty + 8u * slot, xph ^ 1u);
+          const uint32_t dst = base_partner + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st_cluster_v4(dst + (uint32_t)j * 2048u, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          ptx::mbar_arrive_cluster(misc_partner + kBarRecvFull + 8u * slot);
+          ptx::mbar_wait_cluster(misc + kBarRecvFull + 8u * slot, xph);
+          const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+          const float* b3 = s_vec + (L - 1) * 64 * NCH;
+          float y[kD];
+#pragma unroll
+          for (int j = 0; j < kD / 4; ++j) {
+            const float4 r = ld_shared_v4(src + (uint32_t)j * 2048u);
+            y[4 * j] = (__uint_as_float(v[4 * j]) + r.x) + b3[4 * j];
+            y[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + r.y) + b3[4 * j + 1];
+            y[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + r.z) + b3[4 * j + 2];
+            y[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + r.w) + b3[4 * j + 3];
+          }
+          ptx::mbar_arrive_cluster(misc_partner + kBarRecvEmpty + 8u * slot);
+          float delta[kD];
+#pragma unroll
+          for (int d = 0; d < kD; ++d) delta[d] = fmaf(y[d], a.std_delta[d], a.mean_delta[d]);   // dynamics.py:113
+          if (s[5] >= 0.2f) cost += 10.f;                                    // cost_functions.py:16-26 (pre-step state)
+          if (s[6] >= 0.f) cost += 10.f;
+          if (s[7] >= 0.f) cost += 10.f;
+          cost -= delta[17] * 100.f;                                         // cost_functions.py:28 (/ 0.01)
+#pragma unroll
+          for (int d = 0; d < kD; ++d) s[d] += delta[d];                     // dynamics.py:116
+          if constexpr (DBG) {
+            if (writer && p.states_out && valid)
+              for (int d = 0; d < kD; ++d) p.states_out[((size_t)(h + 1) * p.K + k) * kD + d] = (double)s[d];
+          }
+        }
+      }
+      if (is_final) {
+        // ---- per-tile argmin over the 128 rows (np.argmin order); reported by the K-half-0 CTAs ----
+        if constexpr (DBG) {
+          if (writer && p.costs_out && valid) p.costs_out[(size_t)b * p.K + k] = (double)cost;
+        }
+        double c = (double)cost;
+        int64_t idx = valid ? p.path_offset + k : INT64_MAX;
+        int src = row;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double oc = __shfl_xor_sync(0xffffffffu, c, off);
+          const int64_t oi = __shfl_xor_sync(0xffffffffu, idx, off);
+          const int os = __shfl_xor_sync(0xffffffffu, src, off);
+          if (oi != INT64_MAX && (idx == INT64_MAX || cand_better(oc, oi, c, idx))) { c = oc; idx = oi; src = os; }
+        }
+        double* r_cost = reinterpret_cast<double*>(s_red);
+        int64_t* r_idx = reinterpret_cast<int64_t*>(s_red + 32);
+        int* r_src = reinterpret_cast<int*>(s_red + 64);
+        ptx::named_bar_sync(1, 128);                                         // the previous unit's readers are done with s_red
+        if (lane == 0) { r_cost[q] = c; r_idx[q] = idx; r_src[q] = src; }
+        ptx::named_bar_sync(1, 128);
+        c = r_cost[0]; idx = r_idx[0]; src = r_src[0];
+#pragma unroll
+        for (int i = 1; i < 4; ++i)
+          if (r_idx[i] != INT64_MAX && (idx == INT64_MAX || cand_better(r_cost[i], r_idx[i], c, idx))) { c = r_cost[i]; idx = r_idx[i]; src = r_src[i]; }
+        if (writer) {
+          if (row == src && p.cand) {
+            Candidate& o = p.cand[(size_t)b * p.tiles_per_state + tile];
+            o.cost = c;
+            o.index = idx == INT64_MAX ? -1 : idx;
+#pragma unroll
+            for (int j = 0; j < kA; ++j) o.action[j] = (double)act0[j];
+            for (int j = kA; j < kMaxAct; ++j) o.action[j] = 0.0;
+          }
+          if (p.out && (src >> 5) == q) fused_state_minloc(p, b, lane, src & 31);
+        }
+      }
+    }      // work units
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 2) ptx::tmem_dealloc_cg<2>(0u, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch
+// ---------------------------------------------------------------------------------------------------------
+template <int NCH, bool DBG>
+inline cudaError_t deep_launch_t(const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+  auto kern = rollout_deep_kernel<NCH, DBG>;
+  constexpr Layout Y = Lay<NCH>::value;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y.smem_bytes);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Y.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = max_clusters;
+  if (n <= 0) {          // clusters of four that can be co-resident (GPC granularity: fewer than SMs / 4 on most parts)
+    cfg.gridDim = dim3(kCluster * 64);
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 32; }
+  }
+  if (clusters_out) *clusters_out = n;
+  const int64_t g = units < n ? units : n;
+  cfg.gridDim = dim3((unsigned)(g * kCluster));
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+cudaError_t deep_launch_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+cudaError_t deep_launch_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+inline cudaError_t deep_launch(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+  return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_dbg(nch, a, max_clusters, units, st, clusters_out)
+                                             : deep_launch_prod(nch, a, max_clusters, units, st, clusters_out);
+}
+#define BCMPC_DEEP_DEFINE(NAME, DBG)                                                                                        \
+  cudaError_t NAME(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {      \
+    switch (nch) {                                                                                                          \
+      case 1: return deep_launch_t<1, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+      case 2: return deep_launch_t<2, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+      case 3: return deep_launch_t<3, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+      case 4: return deep_launch_t<4, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+      case 5: return deep_launch_t<5, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+      case 6: return deep_launch_t<6, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+      case 7: return deep_launch_t<7, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+      case 8: return deep_launch_t<8, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+    }                                                                                                                       \
+    return cudaErrorInvalidValue;                                                                                           \
+  }
+
+}  // namespace dpx
+}  // namespace bcmpc

@@ -278,9 +278,10 @@ def test_fast_mode_large_k_properties():
     assert np.array_equal(inj1[0, 0], rec["action"][:6])
     _, _, c = mpc1.rollout(state, inj1)
     assert abs(c[0] - rec["cost"]) < 0.25 * abs(c[0]) + 5.0
-    unsupported = dict(hidden=(500, 500, 500))   # three hidden layers: verification mode only
-    with pytest.raises(RuntimeError, match="n_hidden"):
-        make_pair(1, unsupported["hidden"], 128, 2, precision="bf16")
+    # five hidden layers: beyond every fast kernel (the cluster-split kernel takes 2..4), verification mode only
+    from bc_mpc_b200 import Planner as P
+    with pytest.raises(RuntimeError, match="n_hidden|hidden layers"):
+        P(20, 6, 5, 64, "relu", num_paths=128, horizon=2, precision="bf16")
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
