@@ -127,8 +127,13 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) { 
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+// 16 bytes into another CTA's shared memory; the store itself reports its bytes to the destination's mbarrier
+// (st.async, SASS STAS): the sender needs no fence and no separate "data has landed" arrive - a release.cluster arrive per
+// thread behind 16 remote stores cost the sending group half of its time (MEMBAR + ERRBAR waiting for the store acks).
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t bar, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(x),
+               "r"(y), "r"(z), "r"(w), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
@@ -179,8 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(misc + kBarAccFull + 8u * i, 1);
       ptx::mbar_init(misc + kBarAccEmpty + 8u * i, 8);
-      ptx::mbar_init(misc + kBarRecvFull + 8u * i, 128);
-      ptx::mbar_init(misc + kBarRecvEmpty + 8u * i, 128);
+      ptx::mbar_init(misc + kBarRecvFull + 8u * i, 1);        // the receiver's arming arrive (+ the bytes of the partner's st.async)
+      ptx::mbar_init(misc + kBarRecvEmpty + 8u * i, 4);       // one arrive per receiving warp
     }
     ptx::fence_mbar_init();
   }
@@ -427,18 +432,20 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
               // F: my partial of the PARTNER's chunk i -> the partner's receive slot
               uint32_t v0[32], v1[32];
               drain(v0, v1, true);
-              ptx::mbar_wait_cluster(misc + kBarRecvEmpty + 8u * slot, xph ^ 1u);      // the partner has read the slot's previous content
+              ptx::mbar_wait(misc + kBarRecvEmpty + 8u * slot, xph ^ 1u, hc);          // the partner has read the slot's previous content
               const uint32_t dst = base_partner + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+              const uint32_t rbar = misc_partner + kBarRecvFull + 8u * slot;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) st_cluster_v4(dst + (uint32_t)j * 2048u, v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+              for (int j = 0; j < 8; ++j) st_async_v4(dst + (uint32_t)j * 2048u, rbar, v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) st_cluster_v4(dst + (uint32_t)(8 + j) * 2048u, v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]);
-              ptx::mbar_arrive_cluster(misc_partner + kBarRecvFull + 8u * slot);       // release at cluster scope, one arrive per thread
+              for (int j = 0; j < 8; ++j) st_async_v4(dst + (uint32_t)(8 + j) * 2048u, rbar, v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]);
             } else {
               // O: own chunk i = my partial + the partner's + bias -> ReLU -> block i of this layer's output
               uint32_t v0[32], v1[32], w0[16], w1[16];
+              if (warp == 8 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * slot, kRecvBytes);   // arm: 32 KB will arrive
+              __syncwarp();
               drain(v0, v1, true);
-              ptx::mbar_wait_cluster(misc + kBarRecvFull + 8u * slot, xph);
+              ptx::mbar_wait_cluster(misc + kBarRecvFull + 8u * slot, xph);           // (acquire at cluster scope: the bytes came from another CTA)
               const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
               const float4* b4 = reinterpret_cast<const float4*>(bias_l + 64u * i);
 #pragma unroll
@@ -453,7 +460,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
                 w1[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v1[4 * j]) + r.x + bb.x, __uint_as_float(v1[4 * j + 1]) + r.y + bb.y);
                 w1[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v1[4 * j + 2]) + r.z + bb.z, __uint_as_float(v1[4 * j + 3]) + r.w + bb.w);
               }
-              ptx::mbar_arrive_cluster(misc_partner + kBarRecvEmpty + 8u * slot);      // my slot may be overwritten (release: after my loads)
+              __syncwarp();                                                           // every lane's loads are in its registers (and used)
+              if (lane == 0) ptx::mbar_arrive_remote(misc_partner + kBarRecvEmpty + 8u * slot);   // my slot may be overwritten
               store_block(to_y, i, w0, w1);
             }
           }
@@ -463,11 +471,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           const uint32_t x = xbase + (uint32_t)(L - 1) * NCH, slot = x & 1u, xph = (x >> 1) & 1u;
           uint32_t v[32], dummy[32];
           drain(v, dummy, false);
-          ptx::mbar_wait_cluster(misc + kBarRecvEmpty + 8u * slot, xph ^ 1u);
+          // arm the receive barrier only now: the output accumulator is complete, so every hidden exchange of the step -
+          // in particular the slot's previous one, which the OTHER group waited for - has been consumed
+          if (warp == 4 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * slot, 5u * 2048u);   // 20 columns will arrive
+          __syncwarp();
+          ptx::mbar_wait(misc + kBarRecvEmpty + 8u * slot, xph ^ 1u, hc);
           const uint32_t dst = base_partner + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+          const uint32_t rbar = misc_partner + kBarRecvFull + 8u * slot;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) st_cluster_v4(dst + (uint32_t)j * 2048u, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          ptx::mbar_arrive_cluster(misc_partner + kBarRecvFull + 8u * slot);
+          for (int j = 0; j < kD / 4; ++j) st_async_v4(dst + (uint32_t)j * 2048u, rbar, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           ptx::mbar_wait_cluster(misc + kBarRecvFull + 8u * slot, xph);
           const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
           const float* b3 = s_vec + (L - 1) * 64 * NCH;
@@ -480,7 +492,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
             y[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + r.z) + b3[4 * j + 2];
             y[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + r.w) + b3[4 * j + 3];
           }
-          ptx::mbar_arrive_cluster(misc_partner + kBarRecvEmpty + 8u * slot);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_remote(misc_partner + kBarRecvEmpty + 8u * slot);
           float delta[kD];
 #pragma unroll
           for (int d = 0; d < kD; ++d) delta[d] = fmaf(y[d], a.std_delta[d], a.mean_delta[d]);   // dynamics.py:113

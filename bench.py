@@ -232,8 +232,8 @@ def extras():
         "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
         "tflops_algorithmic": B * K * H * flop2 / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop2}
     pl.close()
-    # configs[4]: K = 2**20 x H = 30, MLP 3 x 1024.  Its 1024-wide hidden activations do not fit TMEM next to the
-    # accumulators, so there is no tcgen05 kernel for it yet: it runs on the float32 verification kernel (one plan, ~5 s)
+    # configs[4] (K = 2**20 x H = 30, MLP 3 x 1024) on the float32 verification kernel, for comparison with the tensor-core line
+    # `configs4` of the contract line (cluster-split tcgen05 kernel, rollout_deep.cuh): one plan, ~5 s
     rng4, norm4, w4, s4 = O.synthetic_problem(5, (1024, 1024, 1024))
     pl = Planner(20, 6, 3, 1024, "relu", num_paths=1 << 20, horizon=30, precision="fp32")
     pl.set_dynamics(w4)
@@ -353,6 +353,61 @@ def blas_threads():
         return max(n) if n else 1
     except Exception:
         return 1
+
+
+CONFIGS4_K, CONFIGS4_H, CONFIGS4_HIDDEN = 1 << 20, 30, (1024, 1024, 1024)
+CONFIGS4_FLOP = 2 * (26 * 1024 + 2 * 1024 * 1024 + 1024 * 20)      # 4 288 512 per transition
+
+
+def configs4_leg(torch, dist, world, rank, local, n_plans=6):
+    """BASELINE.json configs[4] - the scaling-sweep config: ONE root state, K = 2**20 paths x H = 30, dynamics MLP 3 x 1024,
+    K sharded over the ranks (strong scaling), NCCL all-gather of one 80-byte record per rank + min-loc.  Runs on the
+    cluster-split tcgen05 kernel (rollout_deep.cuh).  Device time per plan from CUDA events, max over ranks."""
+    from bc_mpc_b200.distributed import ShardedPlanner
+    from oracle import mpc_oracle as O      # synthetic inputs only
+    rng, norm, weights, state = O.synthetic_problem(5, CONFIGS4_HIDDEN)
+    sp = ShardedPlanner(CONFIGS4_K, CONFIGS4_H, rank=rank, world_size=world, device=local, obs_dim=20, act_dim=6, n_hidden=3,
+                        hidden_size=1024, activation="relu", max_states=1, precision="bf16", proposal="uniform")
+    pl = sp.planner
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    pl.set_action_bounds(-np.ones(6), np.ones(6))
+    d_state = torch.from_numpy(state[None]).cuda()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(2):
+        sp.plan_device(d_state, 1, seed=10 + i)
+    barrier()
+    pl.enable_timing(True)
+    evs, kms = [], []
+    for i in range(n_plans):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = sp.plan_device(d_state, 1, seed=100 + i)
+        e1.record(stream)
+        evs.append((e0, e1))
+        torch.cuda.synchronize()
+        kms.append(pl.last_kernel_ms())
+    barrier()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs), sum(kms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    plan_ms, kernel_ms = float(ms[0].item()) / n_plans, float(ms[1].item()) / n_plans
+    rec = np.frombuffer(out.cpu().numpy().tobytes(), dtype=[("cost", "<f8"), ("index", "<i8"), ("action", "<f8", (8,))])[0]
+    pl.close()
+    tr = CONFIGS4_K * CONFIGS4_H
+    peak, _ = measured_peaks()
+    tf_gpu = tr / world * CONFIGS4_FLOP / (kernel_ms * 1e-3) / 1e12
+    return {"workload": f"BASELINE.json configs[4]: 1 root state x K=2^20 x H=30, MLP 26-1024-1024-1024-20 ReLU, bf16 fast mode, K sharded over {world} GPU(s)",
+            "scaling": "strong", "n_gpus": world, "plans": n_plans, "plan_ms": plan_ms, "plans_per_s": 1e3 / plan_ms,
+            "transitions_per_s": tr / (plan_ms * 1e-3), "kernel_ms_max_over_ranks": kernel_ms,
+            "tflops_algorithmic_per_gpu": tf_gpu, "frac_of_burst_peak": tf_gpu / peak, "flop_per_transition": CONFIGS4_FLOP,
+            "kernel": "bcmpc::dpx::rollout_deep_kernel<8>", "winner_index": int(rec["index"]), "winner_cost": float(rec["cost"])}
 
 
 def run_reference(args):
@@ -549,6 +604,14 @@ def run_ours(args):
                          "note": "back-to-back batched plans on one stream, weights L2-resident, device time from one CUDA event pair "
                                  "around the whole run (max over ranks); the rollout kernel is > 99 % of each step"}
 
+    sp.planner.close()
+    del flush
+    configs4 = None
+    if not args.no_configs4:
+        try:
+            configs4 = configs4_leg(torch, dist, world, rank, local)
+        except Exception as e:      # never breaks the contract line
+            configs4 = {"error": repr(e)}
     transitions_per_step = B * K_PATHS * HORIZON                          # all ranks together
     value = transitions_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = transitions_per_step * args.steps / (e2e_ms * 1e-3)
@@ -570,7 +633,7 @@ def run_ours(args):
                              "note": "algorithmic FLOPs only (26-500-500-20); padded tiles (32/512/512/32) are not credited"},
                 "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": B * 20 * 8,
                         "d2h_bytes_per_step": B * 80, "plans_per_s": B * args.steps / (e2e_ms * 1e-3)},
-                "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "sustained": sustained,
+                "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "sustained": sustained, "configs4": configs4,
                 "step_ms": {"first": ms_list[0], "min": min(ms_list), "median": sorted(ms_list)[len(ms_list) // 2], "max": max(ms_list)}}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
@@ -593,6 +656,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-configs4", action="store_true", help="skip the BASELINE.json configs[4] leg (3 x 1024 net, K = 2^20 x H = 30)")
     ap.add_argument("--sustain-s", type=float, default=3.0, help="seconds of the sustained leg (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

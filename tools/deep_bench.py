@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Times the cluster-split tcgen05 kernel (rollout_deep.cuh) on BASELINE.json configs[4] or a scaled-down variant:
+  python tools/deep_bench.py [--K 1048576] [--H 30] [--hidden 1024,1024,1024] [--plans 5]
+Prints one JSON line (kernel ms from the handle's CUDA events, TFLOP/s on the algorithmic FLOPs)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--K", type=int, default=1 << 20)
+    ap.add_argument("--H", type=int, default=30)
+    ap.add_argument("--hidden", default="1024,1024,1024")
+    ap.add_argument("--plans", type=int, default=5)
+    ap.add_argument("--states", type=int, default=1)
+    args = ap.parse_args()
+    from bc_mpc_b200 import Planner
+    from oracle import mpc_oracle as O      # synthetic inputs only
+    hidden = tuple(int(x) for x in args.hidden.split(","))
+    rng, norm, weights, state = O.synthetic_problem(5, hidden)
+    pl = Planner(20, 6, len(hidden), hidden[0], "relu", num_paths=args.K, horizon=args.H, max_states=args.states, precision="bf16")
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((args.states, 20))
+    pl.enable_timing(True)
+    ms = []
+    for i in range(args.plans + 1):
+        pl.plan(states, seed=i)
+        ms.append(pl.last_kernel_ms())
+    ms = ms[1:]
+    flop = 2 * sum(a * b for a, b in zip((26,) + hidden, hidden + (20,)))
+    tr = args.states * args.K * args.H
+    k = float(np.median(ms))
+    print(json.dumps({"hidden": hidden, "K": args.K, "H": args.H, "states": args.states, "kernel_ms_median": k, "kernel_ms_min": min(ms),
+                      "transitions_per_s": tr / (k * 1e-3), "tflops_algorithmic": tr * flop / (k * 1e-3) / 1e12,
+                      "flop_per_transition": flop}))
+
+
+if __name__ == "__main__":
+    main()
