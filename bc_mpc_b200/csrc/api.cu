@@ -305,6 +305,7 @@ int deep_prepare(bcmpc_handle* h, cudaStream_t st) {
   a.stream = reinterpret_cast<uint16_t*>(h->d_stream); a.vec = h->d_lnvec;
   CK(h, dpx::deep_pack(a, st));
   h->launches++;
+  if (!h->trace_path.empty() && !h->d_trace) CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * dpx::kTraceWords));
   h->tm_ready = true;
   return BCMPC_OK;
 }
@@ -332,9 +333,22 @@ int launch_deep(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   a.t.proposal = p.proposal; a.t.inj_kind = p.inj_kind;
   a.n_hidden = h->cfg.n_hidden; a.s_half = 64 * h->deep_nch;
   const int64_t units = (int64_t)p.B * (p.tiles_per_state / 2);
+  a.t.trace = h->d_trace;
+  if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * dpx::kTraceWords, st));
   CK(h, dpx::deep_launch(h->deep_nch, a, h->deep_clusters, units, st, &h->deep_clusters));
   CK(h, cudaGetLastError());
   h->launches++;
+  if (h->d_trace) {
+    CK(h, cudaStreamSynchronize(st));
+    std::vector<unsigned long long> t((size_t)dpx::kTraceWords);
+    CK(h, cudaMemcpy(t.data(), h->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(h->trace_path.c_str(), "wb")) {
+      const int hdr[6] = {dpx::kTrSteps, dpx::kTrRoles, dpx::kTrUses, dpx::kTrStamps, h->deep_nch, h->cfg.n_hidden};
+      fwrite(hdr, sizeof hdr, 1, f);
+      fwrite(t.data(), sizeof(unsigned long long), t.size(), f);
+      fclose(f);
+    }
+  }
   return BCMPC_OK;
 }
 

@@ -37,7 +37,8 @@ __global__ void pack_deep_kernel(PackArgs a) {
       n_local = g * 8 + rr;
       kk = c16 * 8 + e2;
     };
-    if (s < spu) {                                                        // ---- layer 1: tiles of own chunks 4 s + t ----
+    const int l1s = spu;
+    if (s < l1s) {                                                        // ---- layer 1: tiles of own chunks 4 s + t ----
       const int t = (int)(off / kTileH), c = 4 * s + t;
       int nl, kk;
       untile(off % kTileH, nl, kk);
@@ -48,8 +49,8 @@ __global__ void pack_deep_kernel(PackArgs a) {
         else if (kk == in_dim) v = tmx::f32_to_bf16(a.b[0][n]);
         else if (kk == in_dim + 1) v = tmx::f32_to_bf16(__fsub_rn(a.b[0][n], tmx::bf16_to_f32(tmx::f32_to_bf16(a.b[0][n]))));
       }
-    } else if (s < nstg - 1) {                                            // ---- hidden layers 2..L ----
-      const int s2 = s - spu, per_layer = 2 * nch * spu;
+    } else if (s < nstg - spu) {                                          // ---- hidden layers 2..L ----
+      const int s2 = s - l1s, per_layer = 2 * nch * spu;
       const int l = 1 + s2 / per_layer;                                   // weight index (W[l]: hidden l -> hidden l+1)
       const int rem = s2 % per_layer, use = rem / spu, sg = rem % spu;
       const int i = use >> 1, own = use & 1;
@@ -59,12 +60,12 @@ __global__ void pack_deep_kernel(PackArgs a) {
       untile(off % kTileH, nl, kk);
       const int k = (p * nch + kb) * 64 + kk, n = gc * 64 + q * 32 + nl;
       if (kb < nch && k < S && n < S) v = tmx::f32_to_bf16(a.W[l][(size_t)k * a.ld[l] + n]);
-    } else {                                                              // ---- output layer ----
-      const int kb = (int)(off / kTileO);
+    } else {                                                              // ---- output layer: stage sg = k-blocks 4 sg .. 4 sg + 3 ----
+      const int sg = s - (nstg - spu), t = (int)(off / kTileO), kb = 4 * sg + t;
       int nl, kk;
       untile(off % kTileO, nl, kk);
       const int k = (p * nch + kb) * 64 + kk, n = q * 16 + nl;
-      if (kb < nch && k < S && n < kD) v = tmx::f32_to_bf16(a.W[L][(size_t)k * a.ld[L] + n]);
+      if (t < 4 && kb < nch && k < S && n < kD) v = tmx::f32_to_bf16(a.W[L][(size_t)k * a.ld[L] + n]);
     }
     a.stream[e] = v;
   }

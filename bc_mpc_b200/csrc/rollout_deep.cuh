@@ -52,13 +52,15 @@ constexpr int kMaxNch = 8;                      // hidden <= 1024
 constexpr int kMaxHidden = BCMPC_MAX_LAYERS - 1;  // hidden layers (the handle accepts n_hidden + 1 <= BCMPC_MAX_LAYERS)
 constexpr uint32_t kStageBytes = 16384;         // one weight stage: four (64-unit chunk x 64-wide k-block) tiles of this CTA's row half
 constexpr uint32_t kTileH = 4096, kTileO = 2048;   // hidden tile (32 rows x 128 B), output tile (16 rows x 128 B)
-constexpr uint32_t kRecvBytes = 32768;          // one receive slot: 128 rows x 64 fp32
+constexpr uint32_t kRecvBytes = 16384;          // one receive slot: 128 rows x 32 fp32 - HALF a chunk per message (two 32 KB slots cost the weight ring two stages)
 constexpr uint32_t kA0Bytes = 128 * 128;
 constexpr uint32_t kBlockBytes = 128 * 128;     // one 64-unit k-block of an activation as an smem A tile
 
 __host__ __device__ constexpr int stages_per_use(int nch) { return (nch + 3) / 4; }
+constexpr int kNumAcc = 2;                      // accumulator buffers (64 columns each): buffer g belongs to epilogue group g
 __host__ __device__ constexpr int tmem_y_blocks(int nch) { return nch < 12 - nch ? nch : 12 - nch; }   // NT: Y k-blocks that fit in TMEM next to X and 2 accumulators
-__host__ __device__ constexpr int stages_per_step(int nch, int L) { return stages_per_use(nch) * (1 + (L - 1) * 2 * nch) + 1; }
+// weight stages of one step: layer 1, 2 nch uses per hidden layer >= 2, the output layer - stages_per_use each
+__host__ __device__ constexpr int stages_per_step(int nch, int L) { return stages_per_use(nch) * ((L - 1) * 2 * nch + 2); }
 
 // misc smem: barriers then scratch
 enum : uint32_t {
@@ -67,17 +69,19 @@ enum : uint32_t {
   kBarA0Ready = 128,    // input rows of the step in smem           (group 0 of both CTAs -> issuer)
   kBarActReady = 136,   // [8] k-block kb of the current layer's output stored (both CTAs -> issuer)
   kBarAccFull = 200,    // [2] accumulator complete                 (issuer commit -> epilogue of both CTAs)
-  kBarAccEmpty = 216,   // [2] accumulator drained                  (epilogue of both CTAs -> issuer)
-  kBarRecvFull = 232,   // [2] the partner's partial is in my receive slot      (partner's sender threads -> my receiver)
-  kBarRecvEmpty = 248,  // [2] the partner has read ITS receive slot (I may overwrite it)   (partner's receiver threads -> my sender)
-  kOffTmemPtr = 264,
-  kOffRed = 272,        // argmin scratch (128 B)
+  kBarAccEmpty = 224,   // [2] accumulator drained                  (epilogue of both CTAs -> issuer)
+  kBarRecvFull = 248,   // [2] the partner's partial is in my receive slot      (partner's st.async bytes + my arming arrive)
+  kBarRecvEmpty = 264,  // [2] the partner has read ITS receive slot (I may overwrite it)   (partner's receiver warps -> my sender)
+  kBarSig = 280,        // [2] issue token of issuer warp w: the other issuer has issued its use     (issuer -> issuer)
+  kOffTmemPtr = 304,
+  kOffRed = 320,        // argmin scratch (128 B)
   kMiscBytes = 512
 };
 constexpr int kMaxStages = 8;
 
 struct Layout {
   int nch = 0, L = 0, nt = 0, ns = 0, spu = 0, nst = 0;
+  int nst_r[2] = {0, 0}, first_r[2] = {0, 0};     // the ring is split in two: one sub-ring per MMA issuer
   uint32_t off_a0 = 0, off_y = 0, off_recv = 0, off_vec = 0, vec_bytes = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
   uint32_t col_x = 0, col_y = 0, col_acc = 0;
 };
@@ -95,6 +99,8 @@ constexpr Layout make_layout(int nch, int max_hidden) {
   const uint32_t fixed = Y.off_ring + ((Y.vec_bytes + 1023u) / 1024u * 1024u) + kMiscBytes;
   Y.nst = (int)((tmx::kSmemLimit - fixed) / kStageBytes);
   if (Y.nst > kMaxStages) Y.nst = kMaxStages;
+  Y.nst_r[0] = (Y.nst + 1) / 2; Y.nst_r[1] = Y.nst / 2;      // one sub-ring per issuer warp
+  Y.first_r[0] = 0; Y.first_r[1] = Y.nst_r[0];
   Y.off_vec = Y.off_ring + Y.nst * kStageBytes;
   Y.off_misc = Y.off_vec + (Y.vec_bytes + 1023u) / 1024u * 1024u;
   Y.smem_bytes = Y.off_misc + kMiscBytes;
@@ -110,6 +116,18 @@ struct DeepArgs {
   int n_hidden;           // L
   int s_half;             // 64 * NCH: units per K-half (padded)
 };
+
+// pipeline trace of CTA 0 (developer builds, -DBCMPC_TRACE; tools/deep_trace.py): [step (4)][role: issuer warp 1, group 0, group 1, issuer warp 3][use (64)][stamp (8)]
+constexpr int kTrSteps = 4, kTrRoles = 4, kTrUses = 64, kTrStamps = 8, kTraceWords = kTrSteps * kTrRoles * kTrUses * kTrStamps;
+#ifdef BCMPC_TRACE
+#define BCMPC_DTRACE(tr, tstep, role, use, k)                                                                               \
+  do {                                                                                                                      \
+    if ((tr) != nullptr && blockIdx.x == 0 && (tstep) < (uint32_t)kTrSteps)                                                 \
+      (tr)[(((tstep) * kTrRoles + (role)) * kTrUses + (use)) * kTrStamps + (k)] = (unsigned long long)clock64();           \
+  } while (0)
+#else
+#define BCMPC_DTRACE(tr, tstep, role, use, k) do { } while (0)
+#endif
 
 inline bool deep_supported(const bcmpc_config& c, std::string* why) {
   if (c.obs_dim != kD || c.act_dim != kA) { *why = "bf16 fast path is specialised for obs_dim=20, act_dim=6 (HalfCheetah)"; return false; }
@@ -147,7 +165,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
   constexpr Layout Y = Lay<NCH>::value;
   constexpr int NT = Y.nt, SPU = Y.spu, NST = Y.nst;
   constexpr uint32_t kIdescH = ptx::umma_idesc_bf16(2 * kRows, 64), kIdescO = ptx::umma_idesc_bf16(2 * kRows, 32);
-  static_assert(NCH >= 1 && NCH <= kMaxNch && NST >= 2 && Y.col_acc + 128u <= 512u, "unsupported width");
+  static_assert(Y.nst_r[0] >= SPU && Y.nst_r[1] >= SPU, "weight ring too small");
+  static_assert(NCH >= 1 && NCH <= kMaxNch && NST >= 2 && NST <= kMaxStages && Y.col_acc + 64u * kNumAcc <= 512u, "unsupported width");
   const tmx::TmArgs& a = da.t;
   const PlanArgs& p = a.p;
   const int L = da.n_hidden;
@@ -170,8 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
   const int n_it = first_unit < total_units ? (total_units - first_unit + unit_stride - 1) / unit_stride : 0;
   const int H = p.H, Htot = n_it * H;
   const uint32_t hc = a.hint_chain;
-  const int stages_step = SPU * (1 + (L - 1) * 2 * NCH) + 1;
-  const uint32_t xs_step = (uint32_t)(L - 1) * NCH + 1u;           // exchanges per step
+  const int stages_step = stages_per_step(NCH, L);
+  const uint32_t xs_step = (uint32_t)(L - 1) * NCH * 2u + 1u;      // exchanged messages per step: two halves per hidden chunk + the output partial
 
   if (tid == 0) {
     if (base & 1023u) { printf("bcmpc: dynamic smem base not 1024-byte aligned\n"); __trap(); }
@@ -181,9 +200,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
     }
     ptx::mbar_init(misc + kBarA0Ready, 8);
     for (int i = 0; i < 8; ++i) ptx::mbar_init(misc + kBarActReady + 8u * i, 8);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kNumAcc; ++i) {
       ptx::mbar_init(misc + kBarAccFull + 8u * i, 1);
       ptx::mbar_init(misc + kBarAccEmpty + 8u * i, 8);
+      ptx::mbar_init(misc + kBarSig + 8u * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(misc + kBarRecvFull + 8u * i, 1);        // the receiver's arming arrive (+ the bytes of the partner's st.async)
       ptx::mbar_init(misc + kBarRecvEmpty + 8u * i, 4);       // one arrive per receiving warp
     }
@@ -201,133 +223,193 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
   ptx::tc_fence_after();
   if (*s_tmem != 0u) { if (tid == 0) printf("bcmpc: unexpected TMEM base 0x%x\n", *s_tmem); __trap(); }
 
+  // Weight stages of one step, in consumption order: [layer 1: SPU stages of up to four chunk tiles] [layers 2..L: F0, O0, F1,
+  // O1, ... SPU stages of four k-blocks each] [output: SPU stages].  TWO ISSUER WARPS: warp 1 issues layer 1, every F use and
+  // the output layer (weight sub-ring 0), warp 3 every O use (sub-ring 1).  A UTCHMMA issue is paced by the tensor pipe (32
+  // cycles per M=256,N=64 MMA), but every mbarrier wait / tcgen05.commit around it costs the issuing warp 100-250 cycles with
+  // the pipe idle (measured with one issuer: 1560-1780 cycles per 32-MMA use against 1024 on the pipe).  With two warps
+  // the waits of one (accumulator drained, weight stages landed, layer input stored) run while the other issues; a token
+  // passed back and forth (mbarrier hand-off, given away just before the commits) keeps them taking turns instead of
+  // interleaving, so consecutive uses finish one after the other and the three accumulator buffers cover the drains.
+  // Every accumulator is written by one warp only: results do not depend on how the two streams interleave.
   if (warp == 0) {
     // ===================== weight producer: every CTA streams its own row halves =====================
-    uint32_t ws = 0;
+    uint32_t wsr[2] = {0, 0};
+    auto fill = [&](int r, const uint8_t* src, uint32_t bytes) {
+      const uint32_t n = wsr[r]++, stage = (uint32_t)Y.first_r[r] + n % (uint32_t)Y.nst_r[r], ph = (n / (uint32_t)Y.nst_r[r]) & 1u;
+      ptx::mbar_wait(misc + kBarWEmpty + 8u * stage, ph ^ 1u);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(misc + kBarWFull + 8u * stage, bytes);
+        ptx::bulk_g2s(base + Y.off_ring + stage * kStageBytes, src, bytes, misc + kBarWFull + 8u * stage);
+      }
+      __syncwarp();
+    };
     for (int h = 0; h < Htot; ++h) {
       const uint8_t* src = a.stream + (size_t)rank * stages_step * kStageBytes;
-      for (int s = 0; s < stages_step; ++s) {
-        // bytes of the stage: layer-1 / hidden stages hold up to four 4 KB tiles, the output stage NCH 2 KB tiles
-        uint32_t bytes;
-        if (s == stages_step - 1) bytes = NCH * kTileO;
-        else { const int sg = s < SPU ? s : (s - SPU) % SPU; bytes = (uint32_t)(NCH - 4 * sg < 4 ? NCH - 4 * sg : 4) * kTileH; }
-        const uint32_t stage = ws % NST, ph = (ws / NST) & 1u;
-        ptx::mbar_wait(misc + kBarWEmpty + 8u * stage, ph ^ 1u);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(misc + kBarWFull + 8u * stage, bytes);
-          ptx::bulk_g2s(base + Y.off_ring + stage * kStageBytes, src, bytes, misc + kBarWFull + 8u * stage);
-        }
-        __syncwarp();
-        src += kStageBytes;
-        ++ws;
-      }
+      for (int sg = 0; sg < SPU; ++sg, src += kStageBytes) fill(0, src, (uint32_t)(NCH - 4 * sg < 4 ? NCH - 4 * sg : 4) * kTileH);
+      for (int l = 2; l <= L; ++l)
+        for (int i = 0; i < 2 * NCH; ++i)
+          for (int sg = 0; sg < SPU; ++sg, src += kStageBytes) fill(i & 1, src, (uint32_t)(NCH - 4 * sg < 4 ? NCH - 4 * sg : 4) * kTileH);
+      for (int sg = 0; sg < SPU; ++sg, src += kStageBytes) fill(0, src, (uint32_t)(NCH - 4 * sg < 4 ? NCH - 4 * sg : 4) * kTileO);
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 3) {
+    const uint32_t w = warp == 1 ? 0u : 1u;            // issuer 0: layer 1, F uses, output; issuer 1: O uses
+    const uint32_t nst_g = (uint32_t)Y.nst_r[w], first_g = (uint32_t)Y.first_r[w];
     if (leader) {
-      // ===================== MMA issuer of the pair =====================
+      // ===================== MMA issuers of the pair =====================
+      // Accumulator buffer g belongs to epilogue group g (layer-1 chunk c -> c & 1, F -> 0, O -> 1, output -> 0), so every phase
+      // of a buffer's "full" barrier is seen by the same waiters in order (a waiter that skips phases can mistake "not yet
+      // started" for "already complete": the parity bit has only two states).  Two buffers are enough because the two
+      // issuers take turns: use n + 2 is issued ~2048 cycles after use n, whose life - issue, 1024 cycles on the pipe, the
+      // drain with its two mbarrier hops (~650) - is over by then; the TMEM columns a third buffer would take keep two more
+      // k-blocks of the Y activation out of shared memory, which buys the weight ring two more stages.
       const uint16_t pair_mask = (uint16_t)(3u << (2u * khalf));
       const uint64_t a0desc = ptx::umma_desc_sw128(base + Y.off_a0);
-      // Accumulator buffer g belongs to epilogue group g (layer-1 chunk c -> group c & 1, F -> 0, O -> 1, output -> 0), so
-      // every phase of a buffer's full / empty barriers is seen by the same waiters in order (a waiter that skips phases can
-      // mistake "not yet started" for "already complete": the parity bit has only two states).
-      uint32_t nu0 = 0, nu1 = 0, ws = 0, lo = 0;      // uses of buffer 0 / 1, weight stages, layer outputs consumed so far
-      auto acc_wait = [&](uint32_t g) {              // the buffer's previous use has been drained
-        ptx::mbar_wait(misc + kBarAccEmpty + 8u * g, ((g ? nu1 : nu0) & 1u) ^ 1u, hc);
-      };
-      auto acc_done = [&](uint32_t g) { if (g) ++nu1; else ++nu0; };
-      for (int h = 0; h < Htot; ++h) {
-        // ---- layer 1: own chunks, K = 32 (2 k-steps), A from smem ----
-        ptx::mbar_wait(misc + kBarA0Ready, (uint32_t)h & 1u, hc);
-        for (int j = 0; j < SPU; ++j) {
-          const uint32_t stage = ws % NST;
-          ptx::mbar_wait(misc + kBarWFull + 8u * stage, (ws / NST) & 1u);
-          const uint64_t bdesc = ptx::umma_desc_sw128(base + Y.off_ring + stage * kStageBytes);
-          for (int t = 0; t < 4 && 4 * j + t < NCH; ++t) {
-            const uint32_t g = (uint32_t)(4 * j + t) & 1u;
-            acc_wait(g);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint32_t d = Y.col_acc + 64u * g;
+      uint32_t ws = 0, lo = 0, ntok = 0;    // weight stages of this warp's sub-ring, layer outputs consumed, tokens received so far
+      // uses of buffer 0 / 1 per step, and so far at the start of the step
+      constexpr uint32_t kL1b[2] = {(NCH + 1) / 2, NCH / 2};
+      const uint32_t cb[2] = {kL1b[0] + (uint32_t)(L - 1) * NCH + 1u, kL1b[1] + (uint32_t)(L - 1) * NCH};
+      uint32_t nb[2] = {0, 0};
+      const uint32_t tok_mine = misc + kBarSig + 8u * w, tok_other = misc + kBarSig + 8u * (w ^ 1u);
+      for (int h = 0; h < Htot; ++h, nb[0] += cb[0], nb[1] += cb[1]) {
+        // ---- layer 1 (issuer 0): own chunks, K = 32 (2 k-steps), A from smem ----
+        if (w == 0) {
+          ptx::mbar_wait(misc + kBarA0Ready, (uint32_t)h & 1u, hc);
+          for (int j = 0; j < SPU; ++j) {
+            const uint32_t stage = first_g + ws % nst_g;
+            ptx::mbar_wait(misc + kBarWFull + 8u * stage, (ws / nst_g) & 1u);
+            const uint64_t bdesc = ptx::umma_desc_sw128(base + Y.off_ring + stage * kStageBytes);
+            for (int t = 0; t < 4 && 4 * j + t < NCH; ++t) {
+              const uint32_t c = (uint32_t)(4 * j + t), b = c & 1u, n = nb[b] + (c >> 1);      // the n-th use of buffer b
+              if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, 0, 4 * j + t, 0);
+              ptx::mbar_wait(misc + kBarAccEmpty + 8u * b, (n & 1u) ^ 1u, hc);      // the buffer's previous use has been drained
+              ptx::tc_fence_after();
+              if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, 0, 4 * j + t, 1);
+              if (ptx::elect_one()) {
+                const uint32_t d = Y.col_acc + 64u * b;
 #pragma unroll
-              for (uint32_t ks = 0; ks < 2; ++ks)
-                ptx::umma_ss<2>(d, a0desc + 2u * ks, bdesc + (uint64_t)((uint32_t)t * (kTileH >> 4) + 2u * ks), kIdescH, ks);
-              umma_commit_pair(misc + kBarAccFull + 8u * g, pair_mask);
+                for (uint32_t ks = 0; ks < 2; ++ks)
+                  ptx::umma_ss<2>(d, a0desc + 2u * ks, bdesc + (uint64_t)((uint32_t)t * (kTileH >> 4) + 2u * ks), kIdescH, ks);
+                umma_commit_pair(misc + kBarAccFull + 8u * b, pair_mask);
+              }
+              __syncwarp();
             }
+            if (ptx::elect_one()) umma_commit_pair(misc + kBarWEmpty + 8u * stage, pair_mask);
             __syncwarp();
-            acc_done(g);
+            ++ws;
           }
-          if (ptx::elect_one()) umma_commit_pair(misc + kBarWEmpty + 8u * stage, pair_mask);
-          __syncwarp();
-          ++ws;
         }
         // ---- hidden layers 2..L and the output layer (l == L + 1): A = this CTA's K-half of the previous activation ----
-        for (int l = 2; l <= L + 1; ++l) {
-          const bool in_y = ((l - 1) & 1) == 0;          // hidden 2, 4 live in the Y region (TMEM + smem), 1, 3, 5 in X
+        for (int l = 2; l <= L + 1; ++l, ++lo) {
+          const bool in_y = ((l - 1) & 1) == 0;          // hidden 2, 4 live in the Y region (TMEM + smem), 1, 3 in X
           const bool outl = l == L + 1;
           const uint32_t par_in = lo & 1u;
-          const int n_use = outl ? 1 : 2 * NCH;
-          for (int i = 0; i < n_use; ++i) {
-            const uint32_t g = outl ? 0u : (uint32_t)i & 1u;       // F (even) -> group 0, O (odd) -> group 1, output -> group 0
-            acc_wait(g);
-            const uint32_t d = Y.col_acc + 64u * g;
-            for (int sg = 0; sg < (outl ? 1 : SPU); ++sg) {
-              const uint32_t stage = ws % NST;
-              ptx::mbar_wait(misc + kBarWFull + 8u * stage, (ws / NST) & 1u);
-              const uint64_t bdesc = ptx::umma_desc_sw128(base + Y.off_ring + stage * kStageBytes);
-              const int nt = outl ? NCH : (NCH - 4 * sg < 4 ? NCH - 4 * sg : 4);
-              const uint32_t idesc = outl ? kIdescO : kIdescH, tile16 = (outl ? kTileO : kTileH) >> 4;
-              // the four k-steps of k-block kb (tile t of the stage): A from TMEM, or from smem for the tail of a Y activation
-              auto issue_kb = [&](int t) {
-                const int kb = 4 * sg + t;
-                const uint64_t bt = bdesc + (uint64_t)((uint32_t)t * tile16);
-                if (in_y && kb >= NT) {
-                  const uint64_t ad = ptx::umma_desc_sw128(base + Y.off_y + (uint32_t)(kb - NT) * kBlockBytes);
+          if (outl && w == 1) {
+            // no output use for issuer 1, but it must still SEE this phase of every k-block's barrier
+            for (uint32_t kb = 0; kb < (uint32_t)NCH; ++kb) ptx::mbar_wait(misc + kBarActReady + 8u * kb, par_in, hc);
+            continue;
+          }
+          const uint32_t idesc = outl ? kIdescO : kIdescH, tile16 = (outl ? kTileO : kTileH) >> 4;
+          for (int i = 0; i < (outl ? 1 : NCH); ++i) {
+            const uint32_t j = (uint32_t)NCH + (uint32_t)(l - 2) * 2u * NCH + 2u * (uint32_t)i + (outl ? 0u : w);   // index of the use within the step
+            const uint32_t b = outl ? 0u : w, d = Y.col_acc + 64u * b;
+            const uint32_t n = nb[b] + (outl ? cb[0] - 1u : kL1b[b] + (uint32_t)(l - 2) * NCH + (uint32_t)i);      // the n-th use of buffer b
+            const bool first = i == 0;                            // first use of the layer (the output layer's only one)
+            const bool after_own = w == 0 && first && l == 2;     // issuer 0's F0 of layer 2 follows its own layer-1 uses: no token
+            if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 0);
+            // ---- what this use depends on, waited for while the other issuer feeds the pipe ----
+            // (first use of a layer: the first pair of input k-blocks before the accumulator, so that this wait never runs
+            // ahead of the OTHER issuer's last use of the buffer - a layer-1 chunk - see the note on phases above)
+            // Layer 2's first uses wait for ALL of hidden 1: the previous use of buffer 1 is a layer-1 chunk issued by the OTHER
+            // warp, and only "every layer-1 chunk is stored" says that it has been drained; later layers follow this warp's own
+            // use of the buffer and start on the first pair of k-blocks.
+            const int kb_first = first ? (l == 2 ? NCH : (NCH >= 2 ? 2 : 1)) : 0;      // input k-blocks waited for before the first MMA
+            for (int kb = 0; kb < kb_first; kb += 2) {
+              if (kb + 1 < kb_first) ptx::mbar_wait2(misc + kBarActReady + 8u * (uint32_t)kb, misc + kBarActReady + 8u * (uint32_t)(kb + 1), par_in, hc);
+              else ptx::mbar_wait(misc + kBarActReady + 8u * (uint32_t)kb, par_in, hc);
+            }
+            ptx::mbar_wait(misc + kBarAccEmpty + 8u * b, (n & 1u) ^ 1u, hc);        // the buffer's previous use has been drained
+            if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 3);
+            uint32_t stage[SPU];
 #pragma unroll
-                  for (uint32_t ks = 0; ks < 4; ++ks) ptx::umma_ss<2>(d, ad + 2u * ks, bt + 2u * ks, idesc, (kb | (int)ks) ? 1u : 0u);
-                } else {
-                  const uint32_t ac = (in_y ? Y.col_y : Y.col_x) + 32u * (uint32_t)kb;
+            for (int sg = 0; sg < SPU; ++sg) {
+              stage[sg] = first_g + (ws + (uint32_t)sg) % nst_g;
+              ptx::mbar_wait(misc + kBarWFull + 8u * stage[sg], ((ws + (uint32_t)sg) / nst_g) & 1u);
+            }
+            if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 4);
+            // the four k-steps of k-block kb: A from TMEM, or from smem for the tail of a Y activation; B = tile kb % 4 of stage kb / 4
+            auto issue_kb = [&](int kb) {
+              const uint64_t bt = ptx::umma_desc_sw128(base + Y.off_ring + stage[kb >> 2] * kStageBytes) + (uint64_t)((uint32_t)(kb & 3) * tile16);
+              if (in_y && kb >= NT) {
+                const uint64_t ad = ptx::umma_desc_sw128(base + Y.off_y + (uint32_t)(kb - NT) * kBlockBytes);
 #pragma unroll
-                  for (uint32_t ks = 0; ks < 4; ++ks) ptx::umma_ts<2>(d, ac + 8u * ks, bt + 2u * ks, idesc, (kb | (int)ks) ? 1u : 0u);
-                }
-              };
-              if (i == 0) {
-                // first use of the layer: k-block by k-block behind the epilogues that store its input
-                for (int t = 0; t < nt; ++t) {
-                  ptx::mbar_wait(misc + kBarActReady + 8u * (uint32_t)(4 * sg + t), par_in, hc);
-                  ptx::tc_fence_after();
-                  if (ptx::elect_one()) issue_kb(t);
-                  __syncwarp();
-                }
+                for (uint32_t ks = 0; ks < 4; ++ks) ptx::umma_ss<2>(d, ad + 2u * ks, bt + 2u * ks, idesc, (kb | (int)ks) ? 1u : 0u);
               } else {
+                const uint32_t ac = (in_y ? Y.col_y : Y.col_x) + 32u * (uint32_t)kb;
+#pragma unroll
+                for (uint32_t ks = 0; ks < 4; ++ks) ptx::umma_ts<2>(d, ac + 8u * ks, bt + 2u * ks, idesc, (kb | (int)ks) ? 1u : 0u);
+              }
+            };
+            if (first) {
+              // k-block pairs as the epilogues of the previous layer store them: both issuers run this concurrently (F0 and
+              // O0, or the output layer alone), so most of the layer's first uses is done when its last input block lands
+              if (w == 0 && !after_own) { ptx::mbar_wait(tok_mine, ntok & 1u, hc); ++ntok; }      // (issuer 1's last O use is issued)
+              if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 1);
+              for (int kb = 0; kb < NCH; kb += 2) {
+                if (kb >= kb_first) {
+                  if (kb + 1 < NCH) ptx::mbar_wait2(misc + kBarActReady + 8u * (uint32_t)kb, misc + kBarActReady + 8u * (uint32_t)(kb + 1), par_in, hc);
+                  else ptx::mbar_wait(misc + kBarActReady + 8u * (uint32_t)kb, par_in, hc);
+                }
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-#pragma unroll
-                  for (int t = 0; t < 4; ++t)
-                    if (t < nt) issue_kb(t);
+                  issue_kb(kb);
+                  if (kb + 1 < NCH) issue_kb(kb + 1);
                 }
                 __syncwarp();
               }
-              if (ptx::elect_one()) umma_commit_pair(misc + kBarWEmpty + 8u * stage, pair_mask);
+              if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 5);
+              if (ptx::elect_one()) {
+                if (!outl) ptx::mbar_arrive(tok_other);
+#pragma unroll
+                for (int sg = 0; sg < SPU; ++sg) umma_commit_pair(misc + kBarWEmpty + 8u * stage[sg], pair_mask);
+                umma_commit_pair(misc + kBarAccFull + 8u * b, pair_mask);
+              }
               __syncwarp();
-              ++ws;
+              if (w == 1) { ptx::mbar_wait(tok_mine, ntok & 1u, hc); ++ntok; }      // (consume F0's token: the counts stay in step)
+            } else {
+              // ---- the token: the other issuer has issued its use ----
+              ptx::mbar_wait(tok_mine, ntok & 1u, hc);
+              ++ntok;
+              ptx::tc_fence_after();
+              if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 1);
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int sg = 0; sg < SPU; ++sg) {
+#pragma unroll
+                  for (int t = 0; t < 4; ++t)
+                    if (4 * sg + t < NCH) issue_kb(4 * sg + t);
+                  if (sg == SPU - 1) ptx::mbar_arrive(tok_other);       // all MMAs of the use are issued: the other issuer's turn
+                  umma_commit_pair(misc + kBarWEmpty + 8u * stage[sg], pair_mask);
+                }
+                umma_commit_pair(misc + kBarAccFull + 8u * b, pair_mask);
+              }
+              __syncwarp();
             }
-            if (ptx::elect_one()) umma_commit_pair(misc + kBarAccFull + 8u * g, pair_mask);
-            __syncwarp();
-            acc_done(g);
+            ws += SPU;
+            if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 2);
           }
-          ++lo;
         }
       }
     } else {
-      // ===================== peer CTA: tell the leader when this CTA's weight halves have landed =====================
+      // ===================== peer CTA: tell the leader when this CTA's weight halves (of this warp's sub-ring) have landed ====
+      const int per_step = w == 0 ? SPU * (2 + (L - 1) * NCH) : SPU * (L - 1) * NCH;
       uint32_t ws = 0;
       for (int h = 0; h < Htot; ++h)
-        for (int s = 0; s < stages_step; ++s) {
-          const uint32_t stage = ws % NST;
-          ptx::mbar_wait(misc + kBarWFull + 8u * stage, (ws / NST) & 1u);
+        for (int s = 0; s < per_step; ++s, ++ws) {
+          const uint32_t stage = first_g + ws % nst_g;
+          ptx::mbar_wait(misc + kBarWFull + 8u * stage, (ws / nst_g) & 1u);
           if (ptx::elect_one()) ptx::mbar_arrive_remote(misc_leader + kBarWFull + 8u * stage);
           __syncwarp();
-          ++ws;
         }
     }
   } else if (warp >= 4) {
@@ -338,21 +420,23 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
     const uint32_t a0_row = base + Y.off_a0 + (uint32_t)row * 128u;
     const float* s_vec = reinterpret_cast<const float*>(smem + Y.off_vec);
     unsigned char* s_red = smem + Y.off_misc + kOffRed;
+    [[maybe_unused]] const bool tr = (warp == 4 || warp == 8) && lane == 0;
     uint32_t nuse = 0;               // uses of THIS group's accumulator buffer (buffer g) so far
     uint32_t step = 0;               // running step of this CTA
     auto arrive_leader = [&](uint32_t bar) { ptx::mbar_arrive_remote(misc_leader + bar); };
     // this group's next accumulator -> registers (64 or 32 columns), then release the buffer
     auto drain = [&](uint32_t (&v0)[32], uint32_t (&v1)[32], bool both) {
-      ptx::mbar_wait(misc + kBarAccFull + 8u * (uint32_t)g, nuse & 1u, hc);
+      const uint32_t ab = (uint32_t)g;
+      ptx::mbar_wait(misc + kBarAccFull + 8u * ab, nuse & 1u, hc);
       ++nuse;
       ptx::tc_fence_after();
-      const uint32_t col = Y.col_acc + 64u * (uint32_t)g;
+      const uint32_t col = Y.col_acc + 64u * ab;
       ptx::tmem_ld32(lane_off + col, v0);
       if (both) ptx::tmem_ld32(lane_off + col + 32u, v1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) arrive_leader(kBarAccEmpty + 8u * (uint32_t)g);
+      if (lane == 0) arrive_leader(kBarAccEmpty + 8u * ab);
     };
     // 64 activations of this row (bf16 pairs w0 | w1) -> k-block kb of the X or Y activation, then tell the issuer
     auto store_block = [&](bool to_y, uint32_t kb, const uint32_t (&w0)[16], const uint32_t (&w1)[16]) {
@@ -407,17 +491,21 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) arrive_leader(kBarA0Ready);
+          if (tr) BCMPC_DTRACE(a.trace, step, 1, 0, 7);
         }
         // ---- layer 1: chunk c -> X block c (bias rides in the GEMM) ----
 #pragma unroll 1
         for (uint32_t c = (uint32_t)g; c < (uint32_t)NCH; c += 2) {
           uint32_t v0[32], v1[32], w0[16], w1[16];
+          if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, c, 0);
           drain(v0, v1, true);
+          if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, c, 1);
 #pragma unroll
           for (int i = 0; i < 16; ++i) w0[i] = tmx::pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
 #pragma unroll
           for (int i = 0; i < 16; ++i) w1[i] = tmx::pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
           store_block(false, c, w0, w1);
+          if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, c, 4);
         }
         // the next step's randomness, drawn where group 0 has slack
         if (is_final && h + 1 < H) tmx::get_noise<DBG, false>(a, b, h + 1, kc, z);
@@ -427,50 +515,73 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           const float* bias_l = s_vec + (l - 2) * 64 * NCH;
 #pragma unroll 1
           for (uint32_t i = 0; i < (uint32_t)NCH; ++i) {
-            const uint32_t x = xbase + (uint32_t)(l - 2) * NCH + i, slot = x & 1u, xph = (x >> 1) & 1u;
+            // two messages per chunk (columns 0..31, 32..63): message x uses receive slot x & 1, phase (x >> 1) & 1
+            const uint32_t x0 = xbase + ((uint32_t)(l - 2) * NCH + i) * 2u;
+            [[maybe_unused]] const uint32_t tuse = (uint32_t)NCH + (uint32_t)(l - 2) * 2u * NCH + 2u * i + (uint32_t)g;
+            if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, tuse, 0);
             if (g == 0) {
-              // F: my partial of the PARTNER's chunk i -> the partner's receive slot
+              // F: my partial of the PARTNER's chunk i -> the partner's receive slots
               uint32_t v0[32], v1[32];
               drain(v0, v1, true);
-              ptx::mbar_wait(misc + kBarRecvEmpty + 8u * slot, xph ^ 1u, hc);          // the partner has read the slot's previous content
-              const uint32_t dst = base_partner + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
-              const uint32_t rbar = misc_partner + kBarRecvFull + 8u * slot;
+              if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 1);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) st_async_v4(dst + (uint32_t)j * 2048u, rbar, v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+              for (uint32_t hf = 0; hf < 2; ++hf) {
+                const uint32_t x = x0 + hf, slot = x & 1u, xph = (x >> 1) & 1u;
+                ptx::mbar_wait(misc + kBarRecvEmpty + 8u * slot, xph ^ 1u, hc);        // the partner has read the slot's previous content
+                if (tr && hf == 0) BCMPC_DTRACE(a.trace, step, 1, tuse, 2);
+                const uint32_t dst = base_partner + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+                const uint32_t rbar = misc_partner + kBarRecvFull + 8u * slot;
+                const uint32_t(&v)[32] = hf ? v1 : v0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) st_async_v4(dst + (uint32_t)(8 + j) * 2048u, rbar, v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]);
+                for (int j = 0; j < 8; ++j) st_async_v4(dst + (uint32_t)j * 2048u, rbar, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+              if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 3);
             } else {
               // O: own chunk i = my partial + the partner's + bias -> ReLU -> block i of this layer's output
               uint32_t v0[32], v1[32], w0[16], w1[16];
-              if (warp == 8 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * slot, kRecvBytes);   // arm: 32 KB will arrive
-              __syncwarp();
               drain(v0, v1, true);
-              ptx::mbar_wait_cluster(misc + kBarRecvFull + 8u * slot, xph);           // (acquire at cluster scope: the bytes came from another CTA)
-              const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+              // arm both halves (16 KB each will arrive) only now: this accumulator exists, so the layer's input does, so the
+              // previous step's output exchange - the last message the OTHER group armed on one of these slots - is complete
+              if (warp == 8 && ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * (x0 & 1u), kRecvBytes);
+                ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * ((x0 + 1u) & 1u), kRecvBytes);
+              }
+              __syncwarp();
+              if (tr) BCMPC_DTRACE(a.trace, step, 2, tuse, 1);
               const float4* b4 = reinterpret_cast<const float4*>(bias_l + 64u * i);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = ld_shared_v4(src + (uint32_t)j * 2048u), bb = b4[j];
-                w0[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v0[4 * j]) + r.x + bb.x, __uint_as_float(v0[4 * j + 1]) + r.y + bb.y);
-                w0[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v0[4 * j + 2]) + r.z + bb.z, __uint_as_float(v0[4 * j + 3]) + r.w + bb.w);
-              }
+              for (uint32_t hf = 0; hf < 2; ++hf) {
+                const uint32_t x = x0 + hf, slot = x & 1u, xph = (x >> 1) & 1u;
+                // (a CTA-scope acquire like every consumer of TMA-written shared memory uses: a cluster-scope acquire costs ~370
+                // cycles per wait for an L1 invalidation that shared memory does not need)
+                ptx::mbar_wait(misc + kBarRecvFull + 8u * slot, xph, hc);
+                if (tr && hf == 0) BCMPC_DTRACE(a.trace, step, 2, tuse, 2);
+                const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
+                const uint32_t(&v)[32] = hf ? v1 : v0;
+                uint32_t(&w)[16] = hf ? w1 : w0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = ld_shared_v4(src + (uint32_t)(8 + j) * 2048u), bb = b4[8 + j];
-                w1[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v1[4 * j]) + r.x + bb.x, __uint_as_float(v1[4 * j + 1]) + r.y + bb.y);
-                w1[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v1[4 * j + 2]) + r.z + bb.z, __uint_as_float(v1[4 * j + 3]) + r.w + bb.w);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 r = ld_shared_v4(src + (uint32_t)j * 2048u), bb = b4[8 * hf + j];
+                  w[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v[4 * j]) + r.x + bb.x, __uint_as_float(v[4 * j + 1]) + r.y + bb.y);
+                  w[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v[4 * j + 2]) + r.z + bb.z, __uint_as_float(v[4 * j + 3]) + r.w + bb.w);
+                }
+                __syncwarp();                                                         // every lane's loads are in its registers (and used)
+                if (lane == 0) ptx::mbar_arrive_remote(misc_partner + kBarRecvEmpty + 8u * slot);   // my slot may be overwritten
               }
-              __syncwarp();                                                           // every lane's loads are in its registers (and used)
-              if (lane == 0) ptx::mbar_arrive_remote(misc_partner + kBarRecvEmpty + 8u * slot);   // my slot may be overwritten
+              if (tr) BCMPC_DTRACE(a.trace, step, 2, tuse, 3);
               store_block(to_y, i, w0, w1);
+              if (tr) BCMPC_DTRACE(a.trace, step, 2, tuse, 4);
             }
           }
         }
         // ---- output layer: the two K-half partials of the 20 deltas are exchanged both ways ----
         if (is_final) {
-          const uint32_t x = xbase + (uint32_t)(L - 1) * NCH, slot = x & 1u, xph = (x >> 1) & 1u;
+          const uint32_t x = xbase + (uint32_t)(L - 1) * NCH * 2u, slot = x & 1u, xph = (x >> 1) & 1u;
           uint32_t v[32], dummy[32];
+          [[maybe_unused]] const uint32_t tuse = (uint32_t)NCH + (uint32_t)(L - 1) * 2u * NCH;
+          if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 0);
           drain(v, dummy, false);
+          if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 1);
           // arm the receive barrier only now: the output accumulator is complete, so every hidden exchange of the step -
           // in particular the slot's previous one, which the OTHER group waited for - has been consumed
           if (warp == 4 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * slot, 5u * 2048u);   // 20 columns will arrive
@@ -480,7 +591,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           const uint32_t rbar = misc_partner + kBarRecvFull + 8u * slot;
 #pragma unroll
           for (int j = 0; j < kD / 4; ++j) st_async_v4(dst + (uint32_t)j * 2048u, rbar, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          ptx::mbar_wait_cluster(misc + kBarRecvFull + 8u * slot, xph);
+          if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 3);
+          ptx::mbar_wait(misc + kBarRecvFull + 8u * slot, xph, hc);
+          if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 4);
           const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
           const float* b3 = s_vec + (L - 1) * 64 * NCH;
           float y[kD];
@@ -507,6 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
             if (writer && p.states_out && valid)
               for (int d = 0; d < kD; ++d) p.states_out[((size_t)(h + 1) * p.K + k) * kD + d] = (double)s[d];
           }
+          if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 5);
         }
       }
       if (is_final) {
