@@ -269,7 +269,7 @@ bool narrow_applies(const bcmpc_handle* h) {
 }
 
 int tm_variant(const bcmpc_handle* h) {
-  const int pol = h->cfg.proposal != BCMPC_PROP_UNIFORM ? tmx::kVarPolicy : 0;
+  const int pol = needs_policy(h->cfg) ? tmx::kVarPolicy : 0;
   int var = pol | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
   if (narrow_applies(h)) return pol | (h->ln_on ? tmx::kVarLayerNorm : tmx::kVarBias);     // rollout_narrow_kernel: explicit biases (or LayerNorm vectors)
   // plain ReLU dynamics whose two constant-1 hidden units would need an extra chunk (hidden 63/64, 127/128, 255/256):
@@ -430,10 +430,11 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.low[j] = h->norm.low[j];
     a.span[j] = h->norm.span[j];
   }
-  const bool pol = p.proposal != BCMPC_PROP_UNIFORM;
+  const bool pol = p.proposal != BCMPC_PROP_UNIFORM || p.proposal0 != BCMPC_PROP_UNIFORM;
   const int var = (P.reward ? tmx::kVarReward : 0) | (pol ? tmx::kVarPolicy : 0) | (P.layer_norm ? tmx::kVarLayerNorm : 0) |
                   (P.explicit_bias ? tmx::kVarBias : 0);
   a.proposal = p.proposal; a.inj_kind = p.inj_kind;
+  a.proposal0 = p.proposal0; a.inj_kind0 = p.inj_kind0;
   if (h->cfg.activation == BCMPC_ACT_TANH && !P.reward)
     return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: tanh dynamics are built for the learned-reward model (bcmpc_set_reward_head); a plain tanh NNDynamicsModel runs in BCMPC_PREC_FP32_VERIFY");
   if (P.explicit_bias) a.lnvec = h->d_lnvec;
@@ -878,7 +879,7 @@ int set_policy_common(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, c
   for (int l = 0; l < n_layers; ++l)
     if (!W[l] || !b[l]) return fail(h, BCMPC_ERR_INVALID, "null weight pointer for policy layer %d", l);
   if ((filt_mean == nullptr) != (filt_std == nullptr)) return fail(h, BCMPC_ERR_INVALID, "filt_mean and filt_std must be given together");
-  const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST && h->cfg.proposal != BCMPC_PROP_UNIFORM;
+  const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST && needs_policy(h->cfg);
   if (fast) {
     std::string why;
     if (!tmx::tm_policy_supported(n_layers, sizes, &why)) return fail(h, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());

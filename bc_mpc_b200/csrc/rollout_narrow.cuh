@@ -422,9 +422,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_narrow_kernel(const __gri
 #pragma unroll
         for (int j = 0; j < kA; ++j) {
           const float mean = __uint_as_float(vm[j]) + s_pv[2 * kPolMaxHidden + j];
-          if (a.proposal == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
-          else if (a.proposal == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
-          else act[j] = mean + z[j];                                                                                   // controllers.pyc (BC + U[-1,1))
+          const int prop = h == 0 ? a.proposal0 : a.proposal;           // (the tree-search planner switches the mode after its first stage)
+          if (prop == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
+          else if (prop == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
+          else if (prop == BCMPC_PROP_POLICY_MEAN) act[j] = mean;                                                // controllers.py:429,433
+          else if (prop == BCMPC_PROP_UNIFORM) act[j] = z[j];                                                    // controllers.py:411 (random first stage)
+          else act[j] = mean + z[j];                                                                             // controllers.pyc (BC + U[-1,1))
         }
       } else {
 #pragma unroll

@@ -187,6 +187,7 @@ struct TmArgs {
   const uint8_t* pol;            // resident image [CG][pol_bytes]
   int np1, np2;                  // 64-unit chunks of the two hidden layers
   int proposal, inj_kind, has_filter;
+  int proposal0, inj_kind0;      // step 0 (the first stage of the tree-search planner, controllers.py:397-457; else = proposal / inj_kind)
   float clip, explore, one_minus_explore;
   float filt_mean[kMaxObs], filt_inv_std[kMaxObs], pol_std[kMaxAct];
   const float* polvec;           // [bp1 (128)][bp2 (128)][bp3 (8)] biases of the proposal network (device; staged into shared memory)
@@ -235,7 +236,6 @@ inline bool tm_supported(const bcmpc_config& c, std::string* why) {
   if (c.obs_dim != kD || c.act_dim != kA) { *why = "bf16 fast path is specialised for obs_dim=20, act_dim=6 (HalfCheetah)"; return false; }
   if (c.n_hidden != 2) { *why = "bf16 fast path supports n_hidden == 2 this round"; return false; }
   if (c.hidden_size < 1 || c.hidden_size > 510) { *why = "bf16 fast path supports hidden_size <= 510 this round (TMEM holds the 512-wide padded activations)"; return false; }
-  if (c.first_proposal != 0 || c.proposal == BCMPC_PROP_POLICY_MEAN) { *why = "bf16 fast path: the tree-search planner (first_proposal, POLICY_MEAN) runs in BCMPC_PREC_FP32_VERIFY only"; return false; }
   return true;
 }
 
@@ -333,7 +333,7 @@ __device__ __forceinline__ void get_noise(const TmArgs& a, int b, int h, int k, 
     for (int j = 0; j < kA; ++j) z[j] = (float)src[j];
   } else {
     float v[kMaxAct];
-    draw_injection(v, kA, POL ? a.inj_kind : (int)kInjUniformBox, p.seed, (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
+    draw_injection(v, kA, POL ? (h == 0 ? a.inj_kind0 : a.inj_kind) : (int)kInjUniformBox, p.seed, (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
 #pragma unroll
     for (int j = 0; j < kA; ++j) z[j] = v[j];
   }
@@ -774,9 +774,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < kA; ++j) {
             const float mean = __uint_as_float(v[j]) + reinterpret_cast<const float*>(smem + L.off_pol + L.pol_img_bytes)[2 * kPolMaxHidden + j];
-            if (a.proposal == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
-            else if (a.proposal == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
-            else act[j] = mean + z[j];                                                                                   // controllers.pyc (BC + U[-1,1))
+            const int prop = h == 0 ? a.proposal0 : a.proposal;           // (the tree-search planner switches the mode after its first stage)
+            if (prop == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
+            else if (prop == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
+            else if (prop == BCMPC_PROP_POLICY_MEAN) act[j] = mean;                                                // controllers.py:429,433
+            else if (prop == BCMPC_PROP_UNIFORM) act[j] = z[j];                                                    // controllers.py:411 (random first stage)
+            else act[j] = mean + z[j];                                                                             // controllers.pyc (BC + U[-1,1))
           }
         }
       } else {

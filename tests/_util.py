@@ -53,3 +53,24 @@ def scaled_rel_err(got, ref, scale):
 def f32_uniform(rng, shape):
     """U[-1,1) draws that are exactly representable in float32 (so every precision mode sees the same numbers)"""
     return rng.uniform(-1, 1, shape).astype(np.float32).astype(np.float64)
+
+
+def check_winner_replay(rec, one_bf16, oracle_mpc, state, inj1, norm, worst_sigma=1.0):
+    """Full-size property check of a bf16 plan whose K is far beyond what the oracle rolls in seconds: replay ONLY the
+    winning path (its device-drawn action sequence `inj1` [H,1,A]) through (i) a one-path bf16 planner - must reproduce
+    the recorded cost bit for bit - and (ii) the oracle: the bf16 trajectory stays within `worst_sigma` delta-sigmas of
+    the oracle's at every step (the metric of the trajectory-tracking tests), and the cost difference is exactly what
+    that drift explains: cost = sum of threshold penalties - (x17[H] - x17[0]) / 0.01 (cost_functions.py:16-28 summed over
+    the steps), so |cost_bf16 - cost_oracle| <= 100 * |x17[H] error| + 10 * (threshold decisions that differ)."""
+    so, ao, co = one_bf16.rollout_debug(state, inj1)
+    assert co[0] == rec["cost"], (co[0], rec["cost"])
+    ref_s, _, ref_c = oracle_mpc.rollout(state, inj1)
+    sd = np.where(norm["std_deltas"] > 0, norm["std_deltas"], 1.0)
+    e = np.abs((so - ref_s) / sd)
+    assert e.max() < worst_sigma, e.max()
+    flips = 0
+    for d, thr in ((5, 0.2), (6, 0.0), (7, 0.0)):
+        flips += int(np.sum((so[:-1, 0, d] >= thr) != (ref_s[:-1, 0, d] >= thr)))
+    bound = 100.0 * abs(so[-1, 0, 17] - ref_s[-1, 0, 17]) + 10.0 * flips + 1e-2 * max(1.0, abs(ref_c[0]))
+    assert abs(co[0] - ref_c[0]) <= bound, (co[0], ref_c[0], bound, flips)
+    return float(e.max()), float(abs(co[0] - ref_c[0])), flips

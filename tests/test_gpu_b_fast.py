@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import mpc_oracle as O
-from tests._util import f32_uniform, make_pair
+from tests._util import check_winner_replay, f32_uniform, make_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -271,13 +271,12 @@ def test_fast_mode_large_k_properties():
     rng, norm, state, pl, mpc = make_pair(13, (500, 500), K, H, precision="bf16")
     rec = pl.plan(state, seed=42)[0]
     assert 0 <= rec["index"] < K
-    # re-roll only the winning path through the ORACLE with the action sequence the device drew
-    from bc_mpc_b200 import Planner
-    _, _, _, one, mpc1 = make_pair(13, (500, 500), 1, H, precision="fp32", path_offset=int(rec["index"]), total_paths=K)
+    # replay only the winning path - its device-drawn action sequence - through a one-path bf16 planner (bit-exact cost) and
+    # through the ORACLE (trajectory within one delta-sigma, cost difference explained by the drift of x17 / threshold flips)
+    _, _, _, one, mpc1 = make_pair(13, (500, 500), 1, H, precision="bf16", path_offset=int(rec["index"]), total_paths=K)
     inj1 = one.sample_injection(42)[0]
     assert np.array_equal(inj1[0, 0], rec["action"][:6])
-    _, _, c = mpc1.rollout(state, inj1)
-    assert abs(c[0] - rec["cost"]) < 0.25 * abs(c[0]) + 5.0
+    print("winner replay (worst delta-sigma, |cost diff|, threshold flips):", check_winner_replay(rec, one, mpc1, state, inj1, norm))
     # five hidden layers: beyond every fast kernel (the cluster-split kernel takes 2..4), verification mode only
     from bc_mpc_b200 import Planner as P
     with pytest.raises(RuntimeError, match="n_hidden|hidden layers"):
