@@ -265,17 +265,20 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 
 // the narrow-net kernel: plain ReLU dynamics of at most 256 hidden units, uniform shooting, CTA pairs
 bool narrow_applies(const bcmpc_handle* h) {
-  return h->tm_narrow_mode != 0 && h->tm_cg == 2 && !h->rew.set && h->cfg.hidden_size <= 64 * tmx::kNwMaxChunks;
+  return h->tm_narrow_mode != 0 && h->tm_cg == 2 && !h->rew.set && h->cfg.activation == BCMPC_ACT_RELU &&
+         h->cfg.hidden_size <= 64 * tmx::kNwMaxChunks;
 }
 
 int tm_variant(const bcmpc_handle* h) {
   const int pol = needs_policy(h->cfg) ? tmx::kVarPolicy : 0;
   int var = pol | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
   if (narrow_applies(h)) return pol | (h->ln_on ? tmx::kVarLayerNorm : tmx::kVarBias);     // rollout_narrow_kernel: explicit biases (or LayerNorm vectors)
+  // a plain tanh NNDynamicsModel (the reference builder's default activation, dynamics.py:60): biases in the epilogues
+  if (h->cfg.activation == BCMPC_ACT_TANH && !h->rew.set) return pol | tmx::kVarBias | tmx::kVarTanh | (h->ln_on ? tmx::kVarLayerNorm : 0);
   // plain ReLU dynamics whose two constant-1 hidden units would need an extra chunk (hidden 63/64, 127/128, 255/256):
   // biases in the epilogues instead
   const int S = h->cfg.hidden_size;
-  if ((var & ~tmx::kVarPolicy) == 0 && (S + 2 + 63) / 64 > (S + 63) / 64 && tmx::tm_width_supported((S + 63) / 64, var | tmx::kVarBias))
+  if ((var & ~tmx::kVarPolicy) == 0 && (S + 2 + 63) / 64 > (S + 63) / 64 && tmx::tm_width_supported(h->tm_cg, (S + 63) / 64, var | tmx::kVarBias))
     var |= tmx::kVarBias;
   return var;
 }
@@ -363,9 +366,16 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   const tmx::TmHostPlan& P = h->tmp;
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
   h->tm_narrow = narrow_applies(h);
-  h->tm_wide_ok = tmx::tm_width_supported(P.nc, tm_variant(h));
-  if (!h->tm_narrow && !h->tm_wide_ok)
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: this combination (learned-reward model, or LayerNorm with a proposal network) is built for hidden sizes 193..256 and 449..512 (got %d); use BCMPC_PREC_FP32_VERIFY", S);
+  h->tm_wide_ok = tmx::tm_width_supported(h->tm_cg, P.nc, tm_variant(h));
+  if (h->cfg.activation == BCMPC_ACT_TANH && !h->rew.set && h->ln_on) {
+    // tanh + LayerNorm exists for the learned-reward model only: its head may still follow (bcmpc_set_reward_head comes after
+    // bcmpc_set_layer_norm); a plan before that fails in launch_tm
+    h->tm_ready = false;
+    return BCMPC_OK;
+  }
+  if (!h->tm_narrow && !h->tm_wide_ok) {
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: no tensor-core variant for this combination at hidden size %d with BCMPC_TC_CG=%d (single-CTA developer mode: the learned-reward model and LayerNorm + proposal network are built for hidden 193..256 and 449..512, no plain tanh); use BCMPC_PREC_FP32_VERIFY", S, h->tm_cg);
+  }
   if (P.reward && h->ln_on != h->rew_ln_on) {
     // between bcmpc_set_layer_norm and bcmpc_set_reward_layer_norm: the images are packed once all three LayerNorms agree
     h->tm_ready = false;
@@ -409,9 +419,13 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
 
 int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   if (h->deep) return launch_deep(h, p, st);
-  if (!h->tm_ready)
+  if (!h->tm_ready) {
+    if (h->cfg.activation == BCMPC_ACT_TANH && !h->rew.set && h->ln_on)
+      return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: a plain tanh NNDynamicsModel with LayerNorm has no tensor-core variant (ReLU + LayerNorm and the "
+                                            "tanh learned-reward model + LayerNorm do); use BCMPC_PREC_FP32_VERIFY");
     return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared: set the dynamics weights, and with a reward head either all three LayerNorms "
                                     "(bcmpc_set_layer_norm + bcmpc_set_reward_layer_norm) or none");
+  }
   const tmx::TmHostPlan& P = h->tmp;
   tmx::TmArgs a;
   memset(&a, 0, sizeof a);
@@ -431,12 +445,11 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.span[j] = h->norm.span[j];
   }
   const bool pol = p.proposal != BCMPC_PROP_UNIFORM || p.proposal0 != BCMPC_PROP_UNIFORM;
+  const bool plain_tanh = h->cfg.activation == BCMPC_ACT_TANH && !P.reward;
   const int var = (P.reward ? tmx::kVarReward : 0) | (pol ? tmx::kVarPolicy : 0) | (P.layer_norm ? tmx::kVarLayerNorm : 0) |
-                  (P.explicit_bias ? tmx::kVarBias : 0);
+                  (P.explicit_bias ? tmx::kVarBias : 0) | (plain_tanh ? tmx::kVarTanh : 0);
   a.proposal = p.proposal; a.inj_kind = p.inj_kind;
   a.proposal0 = p.proposal0; a.inj_kind0 = p.inj_kind0;
-  if (h->cfg.activation == BCMPC_ACT_TANH && !P.reward)
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: tanh dynamics are built for the learned-reward model (bcmpc_set_reward_head); a plain tanh NNDynamicsModel runs in BCMPC_PREC_FP32_VERIFY");
   if (P.explicit_bias) a.lnvec = h->d_lnvec;
   if (P.reward) {
     a.lnvec = h->d_lnvec;

@@ -134,7 +134,9 @@ struct Layout {
 // kVarBias: the biases of layers 2 / 3 are added in the epilogues instead of riding in the GEMMs through two constant-1
 // hidden units - chosen when those two units would cost a whole extra 64-wide chunk (hidden sizes 63, 64, 127, 128, 255,
 // 256: the reference's default size is 256, train_mpc_ppo.py:75).  The reward model always works that way (tanh).
-enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2, kVarReward = 4, kVarRewardPolicy = 5, kVarBias = 8 };
+// kVarTanh: a plain NNDynamicsModel with tanh hidden layers (the builder default of the reference, dynamics.py:60); always with
+// kVarBias (a tanh does not preserve the constant-1 hidden units that carry the biases of layers 2 / 3 through a ReLU).
+enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2, kVarReward = 4, kVarRewardPolicy = 5, kVarBias = 8, kVarTanh = 16 };
 __host__ __device__ constexpr int hidden2_chunks(int nc, int var) { return (var & kVarReward) ? 2 * nc : nc; }
 constexpr int kRewardCol = kD;          // output column of the reward head in D3
 constexpr uint32_t kLnStatsBytes = 3 * 2 * kRows * 8;      // [layer: hidden 1, hidden 2 (delta head), reward head][epilogue group][row] (sum, sum of squares)
@@ -234,8 +236,8 @@ struct TmHostPlan {
 
 inline bool tm_supported(const bcmpc_config& c, std::string* why) {
   if (c.obs_dim != kD || c.act_dim != kA) { *why = "bf16 fast path is specialised for obs_dim=20, act_dim=6 (HalfCheetah)"; return false; }
-  if (c.n_hidden != 2) { *why = "bf16 fast path supports n_hidden == 2 this round"; return false; }
-  if (c.hidden_size < 1 || c.hidden_size > 510) { *why = "bf16 fast path supports hidden_size <= 510 this round (TMEM holds the 512-wide padded activations)"; return false; }
+  if (c.n_hidden != 2) { *why = "rollout_tmem_kernel is built for n_hidden == 2"; return false; }
+  if (c.hidden_size < 1 || c.hidden_size > 510) { *why = "rollout_tmem_kernel holds hidden_size <= 510 (TMEM keeps the 512-wide padded activations)"; return false; }
   return true;
 }
 
@@ -374,6 +376,8 @@ template <int CG, int NC, int VAR, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_constant__ TmArgs a) {
   constexpr bool POL = (VAR & kVarPolicy) != 0, LN = (VAR & kVarLayerNorm) != 0, REW = (VAR & kVarReward) != 0;
   constexpr bool BIAS = !LN && (REW || (VAR & kVarBias) != 0);   // biases of layers 2 / 3 added in the epilogues
+  constexpr bool TANH = REW || (VAR & kVarTanh) != 0;            // hidden activation (the learned-reward model is tanh, dynamics.py:162)
+  static_assert(!(VAR & kVarTanh) || (BIAS && !REW), "the plain tanh variant uses explicit biases");
   constexpr int NC2 = hidden2_chunks(NC, VAR);                // hidden-2 chunks (both heads of the learned-reward model)
   static_assert(NC <= kMaxChunks1 && NC2 <= kMaxChunks2, "unsupported kernel variant");
   constexpr Layout L = Lay<CG, NC, VAR>::value;
@@ -920,7 +924,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (lane == 0) arrive_leader(kEvDEmpty + e);
         const float4* b4 = reinterpret_cast<const float4*>(bias);
         auto act2 = [&](float x, float y) {
-          if constexpr (REW) return ptx::tanh_bf16x2(pack_bf16(x, y));
+          if constexpr (TANH) return ptx::tanh_bf16x2(pack_bf16(x, y));
           else return pack_relu_bf16(x, y);
         };
 #pragma unroll
@@ -1112,41 +1116,38 @@ inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
-// Variants 0..2 (uniform, proposal network, LayerNorm) exist for every width; the combinations - LayerNorm + proposal
-// network and everything with the learned-reward model - for 4 and 8 hidden chunks (hidden sizes 193..256 and
-// 449..512; the reference hard-codes 500 for the reward model, dynamics.py:162, and defaults to 256 / 500 elsewhere).
-inline bool tm_width_supported(int nc, int var) {
-  if (var & kVarBias) return var <= (kVarBias | kVarPolicy) && nc >= 1 && nc <= 4;
-  if (var == (kVarLayerNorm | kVarPolicy)) return (nc >= 1 && nc <= 4) || nc == 8;
+// CTA pairs (the default): every variant at every width (1..8 hidden chunks), except the explicit-bias ReLU variants, which
+// exist only where they save a chunk (hidden 63/64, 127/128, 191/192, 255/256).  Single CTAs (BCMPC_TC_CG=1, a developer
+// mode): variants 0..2 everywhere, the combinations at 4 and 8 chunks, no plain-tanh variant.
+inline bool tm_width_supported(int cg, int nc, int var) {
+  if (nc < 1 || nc > 8) return false;
+  if (var & kVarTanh) return cg == 2 && (var & ~kVarPolicy) == (kVarBias | kVarTanh);
+  if (var & kVarBias) return var <= (kVarBias | kVarPolicy) && nc <= 4;
+  if (cg == 2) return var >= 0 && var < 8;
+  if (var == (kVarLayerNorm | kVarPolicy)) return nc <= 4 || nc == 8;
   return var < 3 || nc == 4 || nc == 8;
+}
+template <int CG, int NC, int VAR, bool DBG>
+inline cudaError_t tm_launch_fit(const TmArgs& a, dim3 grid, cudaStream_t st) {
+  // (a CTA that cannot hold the resident images next to a two-stage weight ring has no instantiation: tm_prepare reports it)
+  if constexpr (Lay<CG, NC, VAR>::value.nst >= 2) return tm_launch_t<CG, NC, VAR, DBG>(a, grid, st);
+  return cudaErrorInvalidValue;
 }
 template <int CG, int VAR, bool DBG>
 inline cudaError_t tm_launch_cg(int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {
-  if constexpr ((VAR & kVarBias) != 0) {      // explicit-bias variants: the widths where they save a chunk
-    if (nc == 1) return tm_launch_t<CG, 1, VAR, DBG>(a, grid, st);
-    if (nc == 2) return tm_launch_t<CG, 2, VAR, DBG>(a, grid, st);
-    if (nc == 3) return tm_launch_t<CG, 3, VAR, DBG>(a, grid, st);
-    if (nc == 4) return tm_launch_t<CG, 4, VAR, DBG>(a, grid, st);
-    return cudaErrorInvalidValue;
+  if (!tm_width_supported(CG, nc, VAR)) return cudaErrorInvalidValue;
+  constexpr bool all = CG == 2 || VAR < 3;              // every width is instantiated
+  constexpr bool narrow = (VAR & kVarBias) && !(VAR & kVarTanh);   // only 1..4 chunks
+  if (nc == 1) { if constexpr (all || narrow || VAR == 3) return tm_launch_fit<CG, 1, VAR, DBG>(a, grid, st); }
+  if (nc == 2) { if constexpr (all || narrow || VAR == 3) return tm_launch_fit<CG, 2, VAR, DBG>(a, grid, st); }
+  if (nc == 3) { if constexpr (all || narrow || VAR == 3) return tm_launch_fit<CG, 3, VAR, DBG>(a, grid, st); }
+  if (nc == 4) return tm_launch_fit<CG, 4, VAR, DBG>(a, grid, st);
+  if constexpr (!narrow) {
+    if (nc == 5) { if constexpr (all) return tm_launch_fit<CG, 5, VAR, DBG>(a, grid, st); }
+    if (nc == 6) { if constexpr (all) return tm_launch_fit<CG, 6, VAR, DBG>(a, grid, st); }
+    if (nc == 7) { if constexpr (all) return tm_launch_fit<CG, 7, VAR, DBG>(a, grid, st); }
+    if (nc == 8) return tm_launch_fit<CG, 8, VAR, DBG>(a, grid, st);
   }
-  if constexpr (VAR == (kVarLayerNorm | kVarPolicy)) {      // also the narrow widths (shared images with rollout_narrow_kernel)
-    if (nc == 1) return tm_launch_t<CG, 1, VAR, DBG>(a, grid, st);
-    if (nc == 2) return tm_launch_t<CG, 2, VAR, DBG>(a, grid, st);
-    if (nc == 3) return tm_launch_t<CG, 3, VAR, DBG>(a, grid, st);
-  }
-  if constexpr (VAR < 3) {
-    switch (nc) {
-      case 1: return tm_launch_t<CG, 1, VAR, DBG>(a, grid, st);
-      case 2: return tm_launch_t<CG, 2, VAR, DBG>(a, grid, st);
-      case 3: return tm_launch_t<CG, 3, VAR, DBG>(a, grid, st);
-      case 5: return tm_launch_t<CG, 5, VAR, DBG>(a, grid, st);
-      case 6: return tm_launch_t<CG, 6, VAR, DBG>(a, grid, st);
-      case 7: return tm_launch_t<CG, 7, VAR, DBG>(a, grid, st);
-    }
-  }
-  if (nc == 4) return tm_launch_t<CG, 4, VAR, DBG>(a, grid, st);
-  // (a single CTA cannot hold the resident images of the 2 x 512 heads AND of a proposal network: tm_prepare reports it)
-  if constexpr (Lay<CG, 8, VAR>::value.nst >= 2) { if (nc == 8) return tm_launch_t<CG, 8, VAR, DBG>(a, grid, st); }
   return cudaErrorInvalidValue;
 }
 
@@ -1156,14 +1157,16 @@ cudaError_t tm_launch_var(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream
 #define BCMPC_TM_DEFINE_VARIANT(VAR, DBG)                                                                        \
   template <>                                                                                                   \
   cudaError_t tm_launch_var<VAR, DBG>(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {            \
-    return cg == 2 ? tm_launch_cg<2, VAR, DBG>(nc, a, grid, st) : tm_launch_cg<1, VAR, DBG>(nc, a, grid, st);   \
+    if (cg == 2) return tm_launch_cg<2, VAR, DBG>(nc, a, grid, st);                                             \
+    if constexpr (((VAR) & kVarTanh) == 0) return tm_launch_cg<1, VAR, DBG>(nc, a, grid, st);                   \
+    return cudaErrorInvalidValue;                                                                               \
   }
 #define BCMPC_TM_DECLARE_VARIANT(VAR)                                                                            \
   template <> cudaError_t tm_launch_var<VAR, false>(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st); \
   template <> cudaError_t tm_launch_var<VAR, true>(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st);
 BCMPC_TM_DECLARE_VARIANT(0) BCMPC_TM_DECLARE_VARIANT(1) BCMPC_TM_DECLARE_VARIANT(2) BCMPC_TM_DECLARE_VARIANT(3)
 BCMPC_TM_DECLARE_VARIANT(4) BCMPC_TM_DECLARE_VARIANT(5) BCMPC_TM_DECLARE_VARIANT(6) BCMPC_TM_DECLARE_VARIANT(7)
-BCMPC_TM_DECLARE_VARIANT(8) BCMPC_TM_DECLARE_VARIANT(9)
+BCMPC_TM_DECLARE_VARIANT(8) BCMPC_TM_DECLARE_VARIANT(9) BCMPC_TM_DECLARE_VARIANT(24) BCMPC_TM_DECLARE_VARIANT(25)
 template <bool DBG>
 inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
   switch (var) {
@@ -1177,6 +1180,8 @@ inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, d
     case 7: return tm_launch_var<7, DBG>(cg, nc, a, grid, st);   // ... + proposal network (what run.sh launches)
     case 8: return tm_launch_var<8, DBG>(cg, nc, a, grid, st);   // uniform shooting, explicit biases (hidden 64 / 128 / 256)
     case 9: return tm_launch_var<9, DBG>(cg, nc, a, grid, st);   // ... + proposal network
+    case 24: return tm_launch_var<24, DBG>(cg, nc, a, grid, st); // plain tanh dynamics (explicit biases)
+    case 25: return tm_launch_var<25, DBG>(cg, nc, a, grid, st); // ... + proposal network
   }
   return cudaErrorInvalidValue;
 }

@@ -102,8 +102,7 @@ def test_learned_reward_fast_mode_tracks_oracle(S, proposal, K, gamma, ln):
     pl.set_dynamics(weights)
     pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
     if proposal == "uniform":
-        with pytest.raises(RuntimeError, match="tanh dynamics"):      # a plain tanh NNDynamicsModel has no fast path
-            pl.plan(state, seed=1)
+        pl.plan(state, seed=1)          # (a plain tanh NNDynamicsModel has its own tensor-core variant: test_gpu_f_fast_holes.py)
     if os.environ.get("BCMPC_TC_CG") == "1" and proposal != "uniform" and S > 256:
         # single-CTA debug mode: one CTA cannot keep the two 512-wide heads AND a proposal network resident
         with pytest.raises(RuntimeError, match="weight ring"):
