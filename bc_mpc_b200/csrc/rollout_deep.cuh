@@ -559,11 +559,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
                 const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
                 const uint32_t(&v)[32] = hf ? v1 : v0;
                 uint32_t(&w)[16] = hf ? w1 : w0;
+                float4 r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = ld_shared_v4(src + (uint32_t)j * 2048u);      // all eight loads in flight before the first use
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float4 r = ld_shared_v4(src + (uint32_t)j * 2048u), bb = b4[8 * hf + j];
-                  w[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v[4 * j]) + r.x + bb.x, __uint_as_float(v[4 * j + 1]) + r.y + bb.y);
-                  w[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v[4 * j + 2]) + r.z + bb.z, __uint_as_float(v[4 * j + 3]) + r.w + bb.w);
+                  const float4 bb = b4[8 * hf + j];
+                  w[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v[4 * j]) + r[j].x + bb.x, __uint_as_float(v[4 * j + 1]) + r[j].y + bb.y);
+                  w[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v[4 * j + 2]) + r[j].z + bb.z, __uint_as_float(v[4 * j + 3]) + r[j].w + bb.w);
                 }
                 __syncwarp();                                                         // every lane's loads are in its registers (and used)
                 if (lane == 0) ptx::mbar_arrive_remote(misc_partner + kBarRecvEmpty + 8u * slot);   // my slot may be overwritten
