@@ -8,7 +8,7 @@ import numpy as np
 from . import _build
 
 MAX_ACT = 8
-ABI_VERSION = 2      # BCMPC_ABI_VERSION of include/bcmpc.h this binding was written against
+ABI_VERSION = 3      # BCMPC_ABI_VERSION of include/bcmpc.h this binding was written against
 
 
 class Config(C.Structure):
@@ -60,6 +60,8 @@ SIGNATURES = {
     "bcmpc_sample_injection": (C.c_int, [_P, C.c_uint64, C.c_int32, _P]),
     "bcmpc_reduce_records": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "bcmpc_current_device": (C.c_int, [C.POINTER(C.c_int32)]),
+    "bcmpc_peer_exchange_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "bcmpc_set_peer_exchange": (C.c_int, [_P, C.c_int32, C.c_int32, _PP]),
     "bcmpc_kernel_launches": (C.c_int64, [_P]),
     "bcmpc_enable_timing": (C.c_int, [_P, C.c_int32]),
     "bcmpc_last_kernel_ms": (C.c_int, [_P, _P]),

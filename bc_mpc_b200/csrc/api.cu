@@ -85,6 +85,7 @@ struct bcmpc_handle {
   int sm_pairs = 74;      // CTA-pair slots of the device (SMs / 2): one wave of rollout_tmem_kernel
   int narrow_threshold = 74;   // launches with more CTA-pair units than this go to rollout_narrow_kernel (where it applies)
   int tm_narrow_mode = 1; // BCMPC_NARROW=0 keeps hidden <= 256 on rollout_tmem_kernel (rollout_narrow_kernel is the default there)
+  PeerExchangeArgs peer{};     // bcmpc_set_peer_exchange: world == 0 means off
   bool deep = false;      // the cluster-split kernel (rollout_deep.cuh): n_hidden != 2 or hidden_size > 510
   int deep_nch = 0;       // 64-unit chunks per K-half
   int deep_clusters = 0;  // co-resident clusters of four (cudaOccupancyMaxActiveClusters, cached after the first launch)
@@ -525,7 +526,8 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   }
   // few tiles per root state: the rollout kernel's last tile of a state does the min-loc itself (no second launch)
   // (a latency measure for single plans - the reference plans one state per env step; large batches keep the separate kernel)
-  const bool fused = fast && d_out != nullptr && p.tiles_per_state <= 64 && p.B <= 8;
+  const bool exchange = h->peer.world > 0 && d_out != nullptr;     // collective plan: winners over all ranks through peer memory
+  const bool fused = fast && d_out != nullptr && p.tiles_per_state <= 64 && p.B <= 8 && !exchange;
   p.out = fused ? d_out : nullptr;
   p.ticket = h->d_ticket;
   if (h->timing) { CK(h, cudaEventRecord(h->ev0, st)); }
@@ -541,7 +543,12 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   }
   if (rc) return rc;
   if (h->timing) { CK(h, cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
-  if (d_out && !fused) {
+  if (exchange) {
+    h->peer.epoch++;
+    peer_exchange_kernel<<<h->peer.world, 256, 0, st>>>(h->peer, h->d_cand, p.tiles_per_state, p.B, d_out);
+    CK(h, cudaGetLastError());
+    h->launches++;
+  } else if (d_out && !fused) {
     reduce_candidates_kernel<<<p.B, 256, 0, st>>>(h->d_cand, p.tiles_per_state, p.B, 0, d_out);
     CK(h, cudaGetLastError());
     h->launches++;
@@ -1196,6 +1203,26 @@ int bcmpc_current_device(int32_t* device) {
   cudaError_t e = cudaGetDevice(&d);
   if (e != cudaSuccess) return fail(nullptr, BCMPC_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
   *device = d;
+  return BCMPC_OK;
+}
+
+int64_t bcmpc_peer_exchange_bytes(int32_t world, int32_t max_states) {
+  if (world < 1 || world > kMaxPeers || max_states < 1) return -1;
+  return (int64_t)peer_exchange_bytes(world, max_states);
+}
+
+int bcmpc_set_peer_exchange(bcmpc_handle* h, int32_t world, int32_t rank, void* const* peer_bufs) {
+  if (!h) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  if (!peer_bufs) { h->peer = PeerExchangeArgs{}; return BCMPC_OK; }
+  if (world < 1 || world > kMaxPeers) return fail(h, BCMPC_ERR_INVALID, "world %d out of [1,%d]", world, kMaxPeers);
+  if (rank < 0 || rank >= world) return fail(h, BCMPC_ERR_INVALID, "rank %d out of [0,%d)", rank, world);
+  PeerExchangeArgs x{};
+  for (int r = 0; r < world; ++r) {
+    if (!peer_bufs[r]) return fail(h, BCMPC_ERR_INVALID, "null peer buffer for rank %d", r);
+    x.buf[r] = static_cast<unsigned char*>(peer_bufs[r]);
+  }
+  x.world = world; x.rank = rank; x.max_states = h->cfg.max_states; x.epoch = 0;
+  h->peer = x;
   return BCMPC_OK;
 }
 

@@ -46,6 +46,89 @@ __global__ void __launch_bounds__(256) reduce_candidates_kernel(const Candidate*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cross-GPU min-loc over NVLink peer memory: the one exchange step of a sharded plan as ONE kernel
+// per rank instead of reduce kernel + ncclAllGather + reduce kernel.
+//   every rank owns a peer-mapped buffer  [2 slots][world][max_states] records  + flags [2 slots][world] (uint32)
+//   block p of rank r: per-state min-loc of rank r's tile candidates (recomputed by every block: a few tiles per state) ->
+//                      plain stores into PEER p's buffer[slot][r][*] over NVLink -> __threadfence_system ->
+//                      release store of the epoch number into peer p's flag[slot][r]
+//   block 0 of rank r: acquire-polls its OWN flags [slot][0..world) for the epoch, then reduces its own buffer[slot] over
+//                      the ranks (lowest GLOBAL index on ties: np.argmin order, identical on every rank) -> out
+// slot = epoch & 1: a rank can be at most one exchange ahead of a peer (it needs every peer's records of exchange e to
+// finish e), so two slots are enough and nothing is ever reset.  Every rank of the group must launch it (a collective).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerExchangeArgs {
+  unsigned char* buf[kMaxPeers];     // base of every rank's exchange buffer (peer-mapped device pointers; [rank] is local)
+  int world, rank, max_states;
+  uint32_t epoch;                    // 1, 2, 3, ... (flags start at 0)
+};
+__host__ __device__ inline size_t peer_exchange_bytes(int world, int max_states) {
+  return (size_t)2 * world * max_states * sizeof(bcmpc_record) + 2 * kMaxPeers * sizeof(uint32_t);
+}
+__global__ void __launch_bounds__(256) peer_exchange_kernel(PeerExchangeArgs x, const Candidate* __restrict__ cand, int tiles_per_state,
+                                                            int n_states, bcmpc_record* __restrict__ out) {
+  const uint32_t slot = x.epoch & 1u;
+  const size_t rec_bytes = (size_t)2 * x.world * x.max_states * sizeof(bcmpc_record);
+  const int peer = blockIdx.x;
+  // ---- my records -> peer `peer` ----
+  bcmpc_record* dst = reinterpret_cast<bcmpc_record*>(x.buf[peer]) + ((size_t)slot * x.world + x.rank) * x.max_states;
+  for (int b = threadIdx.x; b < n_states; b += blockDim.x) {
+    const Candidate* cd = cand + (size_t)b * tiles_per_state;
+    double c = 0.0;
+    long long idx = -1;
+    int src = -1;
+    for (int t = 0; t < tiles_per_state; ++t) {
+      const long long ii = cd[t].index;
+      if (ii >= 0 && (idx < 0 || cand_better(cd[t].cost, (int64_t)ii, c, (int64_t)idx))) { c = cd[t].cost; idx = ii; src = t; }
+    }
+    bcmpc_record r;
+    r.cost = idx < 0 ? 0.0 : c;
+    r.index = idx;
+    for (int j = 0; j < kMaxAct; ++j) r.action[j] = src >= 0 ? cd[src].action[j] : 0.0;
+    dst[b] = r;                                          // st.global on a peer-mapped pointer: travels over NVLink
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* flag = reinterpret_cast<uint32_t*>(x.buf[peer] + rec_bytes) + slot * kMaxPeers + x.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(x.epoch) : "memory");
+  }
+  if (blockIdx.x != 0) return;
+  // ---- block 0: wait for every rank's records of this exchange, then the G-way min-loc ----
+  if ((int)threadIdx.x < x.world) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(x.buf[x.rank] + rec_bytes) + slot * kMaxPeers + threadIdx.x;
+    const long long t0 = clock64();
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (v != x.epoch && clock64() - t0 > 20000000000LL) {
+        printf("bcmpc: peer exchange timed out (rank %d waiting for rank %d, epoch %u, flag %u)\n", x.rank, (int)threadIdx.x, x.epoch, v);
+        __trap();
+      }
+    } while (v != x.epoch);
+  }
+  __syncthreads();
+  const bcmpc_record* mine = reinterpret_cast<const bcmpc_record*>(x.buf[x.rank]) + (size_t)slot * x.world * x.max_states;
+  for (int b = threadIdx.x; b < n_states; b += blockDim.x) {
+    double c = 0.0;
+    long long idx = -1;
+    int src = -1;
+    for (int g = 0; g < x.world; ++g) {
+      const volatile bcmpc_record* r = mine + (size_t)g * x.max_states + b;
+      const long long ii = r->index;
+      const double cc = r->cost;
+      if (ii >= 0 && (idx < 0 || cand_better(cc, (int64_t)ii, c, (int64_t)idx))) { c = cc; idx = ii; src = g; }
+    }
+    bcmpc_record r;
+    r.cost = idx < 0 ? 0.0 : c;
+    r.index = idx;
+    for (int j = 0; j < kMaxAct; ++j) r.action[j] = src >= 0 ? ((const volatile bcmpc_record*)(mine + (size_t)src * x.max_states + b))->action[j] : 0.0;
+    out[b] = r;
+  }
+}
+
 // cheetah_cost_fn batched branch (cost_functions.py:10-30), float64.
 __global__ void cheetah_cost_kernel(const double* __restrict__ s, const double* __restrict__ ns, int64_t n, int D,
                                     double* __restrict__ out) {

@@ -302,6 +302,19 @@ class Planner:
         self._ck(self._lib.bcmpc_sample_injection(self._h, C.c_uint64(seed), n_states, L.ptr(out)))
         return out
 
+    def peer_exchange_bytes(self, world):
+        return int(self._lib.bcmpc_peer_exchange_bytes(world, self.max_states))
+
+    def set_peer_exchange(self, world, rank, peer_ptrs):
+        """Makes every later plan_device a collective over `world` handles: winners over ALL ranks' paths, exchanged through
+        NVLink peer memory (bcmpc_set_peer_exchange).  peer_ptrs[r] = rank r's exchange buffer as this process sees it
+        (zero-filled, peer_exchange_bytes(world) each); None switches it off."""
+        if peer_ptrs is None:
+            self._ck(self._lib.bcmpc_set_peer_exchange(self._h, 0, 0, None))
+            return
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._ck(self._lib.bcmpc_set_peer_exchange(self._h, world, rank, arr))
+
     def reduce_records_device(self, d_gathered_ptr, n_ranks, n_states, d_out_ptr, stream_ptr=None):
         self._ck(self._lib.bcmpc_reduce_records(self._h, C.c_void_p(d_gathered_ptr), n_ranks, n_states,
                                                 C.c_void_p(d_out_ptr), _stream(stream_ptr)))

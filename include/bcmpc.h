@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BCMPC_ABI_VERSION 2   /* bumped whenever bcmpc_config, bcmpc_record or a signature changes */
+#define BCMPC_ABI_VERSION 3   /* bumped whenever bcmpc_config, bcmpc_record or a signature changes */
 #define BCMPC_MAX_ACT 8      /* action dims carried in a record (HalfCheetah: 6) */
 #define BCMPC_MAX_OBS 32     /* observation dims supported (HalfCheetah: 20)      */
 #define BCMPC_MAX_LAYERS 5   /* dense layers per MLP, output layer included        */
@@ -217,6 +217,17 @@ int bcmpc_reduce_records(bcmpc_handle* h, const bcmpc_record* d_gathered, int32_
  * MlpPolicy.act, cheetah_cost_fn) use when no device is given - never a hard-wired device 0.  Every other entry
  * point runs on its handle's device and RESTORES the caller's current device before it returns. */
 int bcmpc_current_device(int32_t* device);
+
+/* Cross-GPU min-loc through NVLink peer memory instead of ncclAllGather + bcmpc_reduce_records (the
+ * one exchange step of a sharded plan).  peer_bufs[r] is rank r's exchange buffer as THIS process sees it (peer-mapped
+ * device pointers, e.g. the buffer_ptrs of a torch symmetric-memory rendezvous; peer_bufs[rank] is local), each of
+ * bcmpc_peer_exchange_bytes(world, max_states) bytes and zero-filled once before the first plan.  After this call every
+ * bcmpc_plan_device of the handle is a COLLECTIVE over the `world` handles of the group: one rollout launch plus one
+ * exchange kernel that stores this rank's per-state winners into every peer's buffer, flags them, waits for the peers'
+ * and reduces (lowest global index on ties, np.argmin, controllers.py:82) - d_out holds the GLOBAL winners, identical
+ * on every rank.  peer_bufs == NULL switches back to the local result.  world <= 16. */
+int64_t bcmpc_peer_exchange_bytes(int32_t world, int32_t max_states);
+int bcmpc_set_peer_exchange(bcmpc_handle* h, int32_t world, int32_t rank, void* const* peer_bufs);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t bcmpc_kernel_launches(const bcmpc_handle* h);

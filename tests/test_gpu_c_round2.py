@@ -205,3 +205,22 @@ def test_get_actions_honours_an_overridden_sampler_and_plan_rejects_small_obs():
     small.set_normalization(np.zeros(10), np.ones(10), np.zeros(2), np.ones(2), np.zeros(10), np.ones(10))
     with pytest.raises(RuntimeError, match="obs\\[17\\]"):
         small.plan(np.zeros(10))
+
+
+def test_peer_exchange_matches_nccl_all_gather():
+    """The NVLink peer-store record exchange (bcmpc_set_peer_exchange, one kernel after the rollout) against ncclAllGather +
+    min-loc and against a single handle over all paths: bit-identical winners on every rank (2 GPUs, torchrun)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29547", os.path.join(root, "tools", "multi_gpu_check.py")], cwd=root, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
+    assert json.loads(line)["identical_on_all_ranks"] is True
