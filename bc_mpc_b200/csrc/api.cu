@@ -15,6 +15,7 @@
 #include "rollout_tmem.cuh"
 #include "weight_pack.cuh"
 #include "rollout_narrow.cuh"
+#include "rollout_duo.cuh"
 #include "rollout_deep.cuh"
 #include "deep_pack.cuh"
 #include "rollout_verify.cuh"
@@ -82,6 +83,8 @@ struct bcmpc_handle {
   bool tm_narrow = false; // the weight images suit rollout_narrow_kernel (hidden <= 256, CTA pairs, no reward head)
   bool tm_wide_ok = true; // ... and rollout_tmem_kernel has an instantiation that reads the same images
   bool tm_use_narrow = false;   // the kernel chosen for the launch in flight (run_plan)
+  bool tm_use_duo = false;      // ... rollout_duo_kernel (two tiles per CTA taking turns on one hidden-1 buffer: hidden 257..510, more than one wave)
+  int duo_mode = 0;             // BCMPC_DUO: 0 = never (default: measured 3-5 % slower than rollout_tmem_kernel), 1 = when the launch has more CTA-pair units than the device has SM pairs, 2 = always where it applies
   int sm_pairs = 74;      // CTA-pair slots of the device (SMs / 2): one wave of rollout_tmem_kernel
   int narrow_threshold = 74;   // launches with more CTA-pair units than this go to rollout_narrow_kernel (where it applies)
   int tm_narrow_mode = 1; // BCMPC_NARROW=0 keeps hidden <= 256 on rollout_tmem_kernel (rollout_narrow_kernel is the default there)
@@ -268,6 +271,16 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 bool narrow_applies(const bcmpc_handle* h) {
   return h->tm_narrow_mode != 0 && h->tm_cg == 2 && !h->rew.set && h->cfg.activation == BCMPC_ACT_RELU &&
          h->cfg.hidden_size <= 64 * tmx::kNwMaxChunks;
+}
+
+// the two-tiles-per-CTA kernel for wide nets: plain dynamics net (ReLU with the biases in the GEMMs, or tanh), uniform shooting, CTA pairs
+bool duo_applies(const bcmpc_handle* h, const PlanArgs& p) {
+  const tmx::TmHostPlan& P = h->tmp;
+  if (h->duo_mode == 0 || h->tm_cg != 2 || !h->tm_ready || P.layer_norm || P.reward) return false;
+  if (p.proposal != BCMPC_PROP_UNIFORM || p.proposal0 != BCMPC_PROP_UNIFORM) return false;
+  const bool plain_tanh = h->cfg.activation == BCMPC_ACT_TANH;
+  const int var = (P.explicit_bias ? tmx::kVarBias : 0) | (plain_tanh ? tmx::kVarTanh : 0);
+  return tmx::du_supported(P.nc, var);
 }
 
 int tm_variant(const bcmpc_handle* h) {
@@ -478,7 +491,11 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     const unsigned groups = (unsigned)std::min<int64_t>(units, h->sm_pairs);
     CK(h, tmx::nw_launch(P.nc, P.layer_norm, pol, a, dim3(groups * 2, 1), st));
   }
-  if (!h->tm_use_narrow) {
+  if (h->tm_use_duo) {
+    const int64_t units = (int64_t)p.B * (p.tiles_per_state / 2);          // persistent CTA pairs; each pair's units alternate between its two pipes
+    const unsigned groups = (unsigned)std::min<int64_t>(units, h->sm_pairs);
+    CK(h, tmx::du_launch(P.nc, var, a, dim3(groups * 2, 1), st));
+  } else if (!h->tm_use_narrow) {
     // persistent CTAs: at most one wave of CTA groups, each rolling its share of the (root state, tile group) units
     const int64_t units = (int64_t)p.B * (p.tiles_per_state / h->tm_cg);
     const int64_t slots = h->tm_cg == 2 ? h->sm_pairs : 2 * h->sm_pairs;
@@ -491,7 +508,14 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     CK(h, cudaStreamSynchronize(st));
     std::vector<unsigned long long> t((size_t)tmx::kTraceSteps * tmx::kTraceSlots);
     CK(h, cudaMemcpy(t.data(), h->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    if (FILE* f = fopen(h->trace_path.c_str(), "wb")) {
+    if (h->tm_use_duo) {
+      if (FILE* f = fopen(h->trace_path.c_str(), "wb")) {
+        const int hdr[10] = {-2, tmx::kDuTrSteps, tmx::kDuTrSlots, P.nc, 0, 0, 0, 0, 0, 0};
+        fwrite(hdr, sizeof hdr, 1, f);
+        fwrite(t.data(), sizeof(unsigned long long), t.size(), f);
+        fclose(f);
+      }
+    } else if (FILE* f = fopen(h->trace_path.c_str(), "wb")) {
       const int hdr[10] = {tmx::kTraceSteps, tmx::kTraceSlots, P.nc, P.lay.nstg, tmx::kTrL1, tmx::kTrL2, tmx::kTrL3, tmx::kTrEpi,
                            tmx::kTrFinal, tmx::kTrProd};
       fwrite(hdr, sizeof hdr, 1, f);
@@ -513,6 +537,10 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   // launch that fits in one wave (the single-state plans of the reference's env loop) is 25-30 % quicker on the wide kernel.
   h->tm_use_narrow = fast && !h->deep && h->tm_narrow && (!h->tm_wide_ok || (int64_t)p.B * (p.tiles_per_state / 2) > h->narrow_threshold);
   if (h->tm_use_narrow) p.tiles_per_state = (p.tiles_per_state + 3) / 4 * 4;        // two tiles per CTA of a pair
+  // Hidden 257..510, uniform shooting: with more than one wave of CTA-pair units every pair rolls two tiles that take turns on
+  // the hidden-1 buffer (rollout_duo_kernel: the idle stretches of one tile's step are the other's layer 2); same weight images
+  h->tm_use_duo = fast && !h->deep && !h->tm_use_narrow && duo_applies(h, p) &&
+                  (h->duo_mode == 2 || (int64_t)p.B * (p.tiles_per_state / 2) > h->sm_pairs);
   if (d_out) {
     int rc = ensure_cand(h, (size_t)p.B * p.tiles_per_state);
     if (rc) return rc;
@@ -638,6 +666,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
 #endif
   }
   if (const char* s = getenv("BCMPC_NARROW")) h->tm_narrow_mode = atoi(s);
+  if (const char* s = getenv("BCMPC_DUO")) h->duo_mode = atoi(s);
   {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess && prop.multiProcessorCount >= 2) h->sm_pairs = prop.multiProcessorCount / 2;
