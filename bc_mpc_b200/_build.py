@@ -13,15 +13,16 @@ LIB = os.path.join(HERE, "libbcmpc.so")
 OBJ = os.path.join(HERE, "_obj")
 NVCC_BASE = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 NVCC_EXTRA = os.environ.get("BCMPC_NVCC_EXTRA", "").split()
-# -lineinfo (ncu source pages) on the production kernels; the debug-flavour translation units (tests / bcmpc_rollout_debug
-# only, never profiled) go without it: the shipped library is pushed to the GPU box on every run (98 MB -> ~55 MB).
-# BCMPC_LINEINFO=all / none overrides.
+# -lineinfo (ncu source pages) on the translation units whose kernels are profiled - the C ABI, the bench workload's kernel
+# (variant 0), the policy-guided one (variant 1), the narrow-net, cluster-split and two-tile kernels; the other variants and
+# every debug flavour (tests / bcmpc_rollout_debug only) go without it: line tables triple an object's size and the library is
+# pushed to the GPU box on every run (100 MB -> ~65 MB).  BCMPC_LINEINFO=all / none overrides.
 LINEINFO = os.environ.get("BCMPC_LINEINFO", "production")
+LINEINFO_TUS = {"api.cu", "tm_var0.cu", "tm_var1.cu", "tm_narrow.cu", "tm_deep.cu", "tm_duo.cu"}
 
 
 def nvcc_flags(src):
-    dbg = os.path.basename(src).endswith("_dbg.cu")
-    li = LINEINFO == "all" or (LINEINFO == "production" and not dbg)
+    li = LINEINFO == "all" or (LINEINFO == "production" and os.path.basename(src) in LINEINFO_TUS)
     return NVCC_BASE + (["-lineinfo"] if li else []) + NVCC_EXTRA
 
 
@@ -56,7 +57,7 @@ def obj_of(src):
 
 
 def flags_stamp():
-    return " ".join(NVCC_BASE + NVCC_EXTRA + [LINEINFO])
+    return " ".join(NVCC_BASE + NVCC_EXTRA + [LINEINFO] + sorted(LINEINFO_TUS))
 
 
 def obj_stale(src):

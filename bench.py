@@ -569,6 +569,14 @@ def run_ours(args):
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     total_ms = float(tot.item())
     pl.enable_timing(False)
+    # per rank: the rollout kernel alone and the whole step - at N > 1 the step of the job is the slowest GPU's (kernel-time spread
+    # between the GPUs of a box is what the scaling efficiency loses; the record exchange itself is a few microseconds)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([float(np.mean(kernel_ms)), sum(ms_list) / len(ms_list)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"kernel_ms": [float(t[0].item()) for t in allr], "step_ms": [float(t[1].item()) for t in allr]}
     # ---- end-to-end through the host-buffer path ----
     clocks.begin()
     e2e_ms, _, _ = timed(step_e2e, args.steps, True)
@@ -639,7 +647,7 @@ def run_ours(args):
                              "note": "algorithmic FLOPs only (26-500-500-20); padded tiles (32/512/512/32) are not credited"},
                 "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": B * 20 * 8,
                         "d2h_bytes_per_step": B * 80, "plans_per_s": B * args.steps / (e2e_ms * 1e-3)},
-                "record_exchange": getattr(sp, "exchange", None) if world > 1 else None,
+                "record_exchange": getattr(sp, "exchange", None) if world > 1 else None, "per_rank": per_rank,
                 "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": wall, "sustained": sustained, "configs4": configs4,
                 "step_ms": {"first": ms_list[0], "min": min(ms_list), "median": sorted(ms_list)[len(ms_list) // 2], "max": max(ms_list)}}
         if world == 1 and not args.no_cpu_baseline:

@@ -20,7 +20,7 @@ NAMES = {0: "L1 first issue", 1: "L1 last issue", 2: "L2 first issue", 3: "L2 la
 def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 500
     rng, norm, weights, state = O.synthetic_problem(0, (S, S))
-    pl = Planner(20, 6, 2, S, "relu", num_paths=128 * 2 * 74 * 2, horizon=8, precision="bf16")     # two units per CTA pair: both pipes
+    pl = Planner(20, 6, 2, S, "relu", num_paths=128 * 2 * 74 * int(os.environ.get("DUO_TRACE_UNITS", "2")), horizon=8, precision="bf16")     # two units per CTA pair: both pipes
     pl.set_dynamics(weights)
     pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
     for i in range(3):
