@@ -71,6 +71,8 @@ struct bcmpc_handle {
   // tcgen05 path (rollout_tmem.cuh)
   tmx::TmHostPlan tmp;
   uint8_t *d_res = nullptr, *d_stream = nullptr, *d_pol = nullptr;
+  size_t pol_cap = 0;
+  bool pol_wide = false;          // the proposal network has more than 128 units in a hidden layer: kVarPolWide kernel variants
   float* d_polvec = nullptr;      // biases of the proposal network for the fast kernel
   float* d_lnvec = nullptr;
   size_t res_cap = 0, stream_cap = 0, lnvec_cap = 0;
@@ -269,6 +271,7 @@ int ensure_cand(bcmpc_handle* h, size_t n) {
 
 // the narrow-net kernel: plain ReLU dynamics of at most 256 hidden units, uniform shooting, CTA pairs
 bool narrow_applies(const bcmpc_handle* h) {
+  if (h->pol_wide && needs_policy(h->cfg)) return false;        // wide proposal networks run on rollout_tmem_kernel only
   return h->tm_narrow_mode != 0 && h->tm_cg == 2 && !h->rew.set && h->cfg.activation == BCMPC_ACT_RELU &&
          h->cfg.hidden_size <= 64 * tmx::kNwMaxChunks;
 }
@@ -285,14 +288,15 @@ bool duo_applies(const bcmpc_handle* h, const PlanArgs& p) {
 
 int tm_variant(const bcmpc_handle* h) {
   const int pol = needs_policy(h->cfg) ? tmx::kVarPolicy : 0;
-  int var = pol | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
+  const int wide = (pol && h->pol_wide) ? tmx::kVarPolWide : 0;
+  int var = pol | wide | (h->ln_on ? tmx::kVarLayerNorm : 0) | (h->rew.set ? tmx::kVarReward : 0);
   if (narrow_applies(h)) return pol | (h->ln_on ? tmx::kVarLayerNorm : tmx::kVarBias);     // rollout_narrow_kernel: explicit biases (or LayerNorm vectors)
   // a plain tanh NNDynamicsModel (the reference builder's default activation, dynamics.py:60): biases in the epilogues
-  if (h->cfg.activation == BCMPC_ACT_TANH && !h->rew.set) return pol | tmx::kVarBias | tmx::kVarTanh | (h->ln_on ? tmx::kVarLayerNorm : 0);
+  if (h->cfg.activation == BCMPC_ACT_TANH && !h->rew.set) return pol | wide | tmx::kVarBias | tmx::kVarTanh | (h->ln_on ? tmx::kVarLayerNorm : 0);
   // plain ReLU dynamics whose two constant-1 hidden units would need an extra chunk (hidden 63/64, 127/128, 255/256):
   // biases in the epilogues instead
   const int S = h->cfg.hidden_size;
-  if ((var & ~tmx::kVarPolicy) == 0 && (S + 2 + 63) / 64 > (S + 63) / 64 && tmx::tm_width_supported(h->tm_cg, (S + 63) / 64, var | tmx::kVarBias))
+  if (!wide && (var & ~tmx::kVarPolicy) == 0 && (S + 2 + 63) / 64 > (S + 63) / 64 && tmx::tm_width_supported(h->tm_cg, (S + 63) / 64, var | tmx::kVarBias))
     var |= tmx::kVarBias;
   return var;
 }
@@ -352,7 +356,7 @@ int launch_deep(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   const int64_t units = (int64_t)p.B * (p.tiles_per_state / 2);
   a.t.trace = h->d_trace;
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * dpx::kTraceWords, st));
-  CK(h, dpx::deep_launch(h->deep_nch, a, h->deep_clusters, units, st, &h->deep_clusters));
+  CK(h, dpx::deep_launch(h->deep_nch, h->cfg.activation == BCMPC_ACT_TANH, a, h->deep_clusters, units, st, &h->deep_clusters));
   CK(h, cudaGetLastError());
   h->launches++;
   if (h->d_trace) {
@@ -461,7 +465,10 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   const bool pol = p.proposal != BCMPC_PROP_UNIFORM || p.proposal0 != BCMPC_PROP_UNIFORM;
   const bool plain_tanh = h->cfg.activation == BCMPC_ACT_TANH && !P.reward;
   const int var = (P.reward ? tmx::kVarReward : 0) | (pol ? tmx::kVarPolicy : 0) | (P.layer_norm ? tmx::kVarLayerNorm : 0) |
-                  (P.explicit_bias ? tmx::kVarBias : 0) | (plain_tanh ? tmx::kVarTanh : 0);
+                  (P.explicit_bias ? tmx::kVarBias : 0) | (plain_tanh ? tmx::kVarTanh : 0) | ((pol && h->pol_wide) ? tmx::kVarPolWide : 0);
+  // (the streamed dynamics image is packed for the variant's stage size: set_policy re-packs it when the network's class changes)
+  if (tmx::make_layout(h->tm_cg, P.nc, var).kbs != P.lay.kbs)
+    return fail(h, BCMPC_ERR_STATE, "bf16 fast path: the weight images were packed for another kernel variant (set the proposal network before planning)");
   a.proposal = p.proposal; a.inj_kind = p.inj_kind;
   a.proposal0 = p.proposal0; a.inj_kind0 = p.inj_kind0;
   if (P.explicit_bias) a.lnvec = h->d_lnvec;
@@ -947,20 +954,32 @@ int set_policy_common(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, c
   update_verify_geometry(h);
   if (fast) {
     // the image layout depends only on the CTA-group size: it can be packed before the dynamics weights arrive
-    const tmx::Layout lay = tmx::make_layout(h->tm_cg, 1, tmx::kVarPolicy);
+    const bool wide = tmx::tm_policy_is_wide(sizes);
+    if (wide && h->tm_cg != 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: proposal networks wider than 128 units need CTA pairs (BCMPC_TC_CG=2, the default)");
+    const int pvar = tmx::kVarPolicy | (wide ? tmx::kVarPolWide : 0);
+    const tmx::Layout lay = tmx::make_layout(h->tm_cg, 1, pvar);
     const size_t img_total = (size_t)h->tm_cg * lay.pol_img_bytes;
-    if (!h->d_pol) CK(h, cudaMalloc(&h->d_pol, img_total));
-    if (!h->d_polvec) CK(h, cudaMalloc(&h->d_polvec, tmx::kPolVecFloats * sizeof(float)));
+    if (img_total > h->pol_cap) {
+      if (h->d_pol) { CK(h, cudaDeviceSynchronize()); CK(h, cudaFree(h->d_pol)); h->d_pol = nullptr; h->pol_cap = 0; }
+      CK(h, cudaMalloc(&h->d_pol, img_total));
+      h->pol_cap = img_total;
+    }
+    if (!h->d_polvec) CK(h, cudaMalloc(&h->d_polvec, tmx::kPolWideVecFloats * sizeof(float)));
     tmx::PolicyPackArgs a{};
     const MlpDesc& d = h->pol.desc;
     for (int l = 0; l < 3; ++l) { a.W[l] = d.W[l]; a.b[l] = d.b[l]; a.ld[l] = d.out_pad[l]; }
-    a.h1 = sizes[1]; a.h2 = sizes[2]; a.cg = h->tm_cg;
+    a.h1 = sizes[1]; a.h2 = sizes[2]; a.cg = h->tm_cg; a.pn = tmx::pol_chunks(pvar);
     a.blk_h = lay.blk_h; a.blk_o = lay.blk_o; a.img_bytes = lay.pol_img_bytes;
     a.img = reinterpret_cast<uint16_t*>(h->d_pol); a.vec = h->d_polvec;
     CK(h, tmx::tm_pack_policy(a, st));
     h->launches++;
     h->tmp.with_policy = true;
     h->tmp.np1 = (sizes[1] + 63) / 64; h->tmp.np2 = (sizes[2] + 63) / 64;
+    if (wide != h->pol_wide) {
+      // the network changed class: another kernel variant, whose weight ring has another stage size - re-pack the dynamics images
+      h->pol_wide = wide;
+      if (h->dyn.set) { rc = tm_prepare(h, st); if (rc) return rc; }
+    }
   }
   return BCMPC_OK;
 }

@@ -1,5 +1,5 @@
 // BF16 fast-mode rollout kernel for WIDE / DEEP dynamics nets: L >= 2 hidden layers of up to 1024 units (BASELINE.json
-// configs[4]: 26 -> 1024 -> 1024 -> 1024 -> 20, K = 2^20 paths x H = 30), uniform shooting, ReLU.
+// configs[4]: 26 -> 1024 -> 1024 -> 1024 -> 20, K = 2^20 paths x H = 30), uniform shooting, ReLU or tanh.
 //
 // Why a third kernel: the hidden activations of a 128-path tile at width 1024 are 256 KB in bf16 - all of TMEM - and a
 // layer needs its whole input alive until its last output chunk, i.e. input + output = 512 KB per 128 paths, more than
@@ -133,7 +133,6 @@ inline bool deep_supported(const bcmpc_config& c, std::string* why) {
   if (c.obs_dim != kD || c.act_dim != kA) { *why = "bf16 fast path is specialised for obs_dim=20, act_dim=6 (HalfCheetah)"; return false; }
   if (c.n_hidden < 2 || c.n_hidden > kMaxHidden) { *why = "bf16 fast path (cluster-split kernel) supports 2..4 hidden layers"; return false; }
   if (c.hidden_size < 1 || c.hidden_size > 64 * 2 * kMaxNch) { *why = "bf16 fast path supports hidden_size <= 1024"; return false; }
-  if (c.activation != BCMPC_ACT_RELU) { *why = "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) is built for ReLU dynamics"; return false; }
   if (c.proposal != BCMPC_PROP_UNIFORM || c.first_proposal != 0) { *why = "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) runs uniform shooting; policy-guided proposals run in BCMPC_PREC_FP32_VERIFY there"; return false; }
   return true;
 }
@@ -160,8 +159,14 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
 }
 // TMEM -> registers: this warp's 32 lanes x 32 columns - reuse ptx::tmem_ld32
 
-template <int NCH, bool DBG>
+// TANH: hidden activation tanh (the reference builder's default, dynamics.py:60; tanh.approx.bf16x2 on the rounded pair, like
+// rollout_tmem_kernel's kVarTanh) instead of ReLU - the biases of layers >= 2 are explicit here anyway, layer 1's ride in the GEMM.
+template <int NCH, bool DBG, bool TANH>
 __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_constant__ DeepArgs da) {
+  auto act2 = [](float x, float y) -> uint32_t {
+    if constexpr (TANH) return ptx::tanh_bf16x2(tmx::pack_bf16(x, y));
+    else return tmx::pack_relu_bf16(x, y);
+  };
   constexpr Layout Y = Lay<NCH>::value;
   constexpr int NT = Y.nt, SPU = Y.spu, NST = Y.nst;
   constexpr uint32_t kIdescH = ptx::umma_idesc_bf16(2 * kRows, 64), kIdescO = ptx::umma_idesc_bf16(2 * kRows, 32);
@@ -501,9 +506,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           drain(v0, v1, true);
           if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, c, 1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w0[i] = tmx::pack_relu_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+          for (int i = 0; i < 16; ++i) w0[i] = act2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w1[i] = tmx::pack_relu_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          for (int i = 0; i < 16; ++i) w1[i] = act2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
           store_block(false, c, w0, w1);
           if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, c, 4);
         }
@@ -565,8 +570,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float4 bb = b4[8 * hf + j];
-                  w[2 * j] = tmx::pack_relu_bf16(__uint_as_float(v[4 * j]) + r[j].x + bb.x, __uint_as_float(v[4 * j + 1]) + r[j].y + bb.y);
-                  w[2 * j + 1] = tmx::pack_relu_bf16(__uint_as_float(v[4 * j + 2]) + r[j].z + bb.z, __uint_as_float(v[4 * j + 3]) + r[j].w + bb.w);
+                  w[2 * j] = act2(__uint_as_float(v[4 * j]) + r[j].x + bb.x, __uint_as_float(v[4 * j + 1]) + r[j].y + bb.y);
+                  w[2 * j + 1] = act2(__uint_as_float(v[4 * j + 2]) + r[j].z + bb.z, __uint_as_float(v[4 * j + 3]) + r[j].w + bb.w);
                 }
                 __syncwarp();                                                         // every lane's loads are in its registers (and used)
                 if (lane == 0) ptx::mbar_arrive_remote(misc_partner + kBarRecvEmpty + 8u * slot);   // my slot may be overwritten
@@ -673,9 +678,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------------------
-template <int NCH, bool DBG>
+template <int NCH, bool DBG, bool TANH>
 inline cudaError_t deep_launch_t(const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
-  auto kern = rollout_deep_kernel<NCH, DBG>;
+  auto kern = rollout_deep_kernel<NCH, DBG, TANH>;
   constexpr Layout Y = Lay<NCH>::value;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y.smem_bytes);
   if (e != cudaSuccess) return e;
@@ -700,21 +705,26 @@ inline cudaError_t deep_launch_t(const DeepArgs& a, int max_clusters, int64_t un
 }
 cudaError_t deep_launch_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
-inline cudaError_t deep_launch(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+cudaError_t deep_launch_tanh_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+cudaError_t deep_launch_tanh_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+inline cudaError_t deep_launch(int nch, bool tanh_act, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+  if (tanh_act)
+    return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_tanh_dbg(nch, a, max_clusters, units, st, clusters_out)
+                                               : deep_launch_tanh_prod(nch, a, max_clusters, units, st, clusters_out);
   return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_dbg(nch, a, max_clusters, units, st, clusters_out)
                                              : deep_launch_prod(nch, a, max_clusters, units, st, clusters_out);
 }
-#define BCMPC_DEEP_DEFINE(NAME, DBG)                                                                                        \
+#define BCMPC_DEEP_DEFINE(NAME, DBG, TANH)                                                                                        \
   cudaError_t NAME(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {      \
     switch (nch) {                                                                                                          \
-      case 1: return deep_launch_t<1, DBG>(a, max_clusters, units, st, clusters_out);                                       \
-      case 2: return deep_launch_t<2, DBG>(a, max_clusters, units, st, clusters_out);                                       \
-      case 3: return deep_launch_t<3, DBG>(a, max_clusters, units, st, clusters_out);                                       \
-      case 4: return deep_launch_t<4, DBG>(a, max_clusters, units, st, clusters_out);                                       \
-      case 5: return deep_launch_t<5, DBG>(a, max_clusters, units, st, clusters_out);                                       \
-      case 6: return deep_launch_t<6, DBG>(a, max_clusters, units, st, clusters_out);                                       \
-      case 7: return deep_launch_t<7, DBG>(a, max_clusters, units, st, clusters_out);                                       \
-      case 8: return deep_launch_t<8, DBG>(a, max_clusters, units, st, clusters_out);                                       \
+      case 1: return deep_launch_t<1, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
+      case 2: return deep_launch_t<2, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
+      case 3: return deep_launch_t<3, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
+      case 4: return deep_launch_t<4, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
+      case 5: return deep_launch_t<5, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
+      case 6: return deep_launch_t<6, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
+      case 7: return deep_launch_t<7, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
+      case 8: return deep_launch_t<8, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
     }                                                                                                                       \
     return cudaErrorInvalidValue;                                                                                           \
   }

@@ -95,17 +95,22 @@ enum : int {
   kEvA2Empty = 74,     // [16] layer 3 has consumed hidden-2 chunk c                   (L3 issuer -> epilogue)
   // proposal network (policy-guided shooting), also once per step each
   kEvAp0Ready = 90,    // policy input rows are in shared memory                        (epilogue -> issuer)
-  kEvPdFull = 91,      // [4]  policy accumulators: layer-1 chunks 0,1, layer-2 chunks 0,1   (issuer -> epilogue)
-  kEvAp1Ready = 95,    // [2]  policy hidden-1 chunk in TMEM                            (epilogue -> issuer)
-  kEvAp2Ready = 97,    // [2]  policy hidden-2 chunk in TMEM
-  kEvPolFull = 99,     // policy output accumulator complete                            (issuer -> epilogue)
-  kNumEv = 100
+  kEvPdFull = 91,      // [8]  policy accumulators: layer-1 chunks 0..3, layer-2 chunks 0..3 (issuer -> epilogue)
+  kEvAp1Ready = 99,    // [4]  policy hidden-1 chunk in TMEM                            (epilogue -> issuer)
+  kEvAp2Ready = 103,   // [4]  policy hidden-2 chunk in TMEM
+  kEvPolFull = 107,    // policy output accumulator complete                            (issuer -> epilogue)
+  kNumEv = 108
 };
 constexpr int kMaxChunks1 = 8, kMaxChunks2 = 16;    // hidden-1 chunks; hidden-2 chunks (two heads of 8 in the learned-reward model)
-// misc smem: [w_full 16][w_empty 16][res_full][events 100] x 8 B, tmem ptr, argmin scratch
-constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, kOffTmemPtr = 1072, kOffRed = 1088, kMiscBytes = 1280;
-constexpr int kPolMaxHidden = 128;     // proposal network: two tanh layers of at most 128 units (MlpPolicy hid_size=128, BCnetwork 128/64)
+// misc smem: [w_full 16][w_empty 16][res_full][events 108] x 8 B, tmem ptr, argmin scratch
+constexpr int kOffWFull = 0, kOffWEmpty = 128, kOffResFull = 256, kOffEv = 264, kOffTmemPtr = 1136, kOffRed = 1152, kMiscBytes = 1280;
+static_assert(kOffEv + 8 * kNumEv <= kOffTmemPtr && kOffRed + 80 <= kMiscBytes, "misc shared-memory map");
+constexpr int kPolMaxHidden = 128;     // proposal network: two tanh layers of at most 128 units (MlpPolicy hid_size=128, BCnetwork 128/64) ...
 constexpr int kPolVecFloats = 2 * 128 + 8 + 248;   // [bp1 (128)][bp2 (128)][bp3 (8)], padded to 2 KB
+// ... or, in the kVarPolWide variants, of at most 256 units (MlpPolicy(hid_size=256), various_train/train_mpc_ppo_r.py:142):
+// four 64-unit chunks per hidden layer, an 88 KB resident image per CTA, quarter-chunk weight stages for the dynamics net
+constexpr int kPolWideHidden = 256;
+constexpr int kPolWideVecFloats = 2 * 256 + 8 + 248;   // [bp1 (256)][bp2 (256)][bp3 (8)], padded to 3 KB
 
 // ---------------------------------------------------------------------------------------------------------
 // The per-step schedule is fixed arithmetic, the same for every step (all accumulators are drained at a step boundary):
@@ -119,7 +124,8 @@ constexpr int kPolVecFloats = 2 * 128 + 8 + 248;   // [bp1 (128)][bp2 (128)][bp3
 // ---------------------------------------------------------------------------------------------------------
 // k-blocks per streamed weight stage: a whole chunk of W2 per stage for a CTA pair (32 KB per CTA at NC = 8), a
 // quarter chunk for a single CTA (16 KB; the ring must hold several stages next to the resident W1 / W3)
-constexpr int stage_kblocks(int cg, int nc) { return cg == 2 ? nc : (nc + 3) / 4; }
+// (a CTA pair that also holds a wide proposal network has ~70 KB left for the ring: quarter chunks there as well)
+constexpr int stage_kblocks(int cg, int nc, bool pol_wide = false) { return (cg == 2 && !pol_wide) ? nc : (nc + 3) / 4; }
 
 // shared-memory map, a function of (CTA-group size, hidden chunks) only: the kernel uses it as compile-time constants
 struct Layout {
@@ -136,7 +142,12 @@ struct Layout {
 // 256: the reference's default size is 256, train_mpc_ppo.py:75).  The reward model always works that way (tanh).
 // kVarTanh: a plain NNDynamicsModel with tanh hidden layers (the builder default of the reference, dynamics.py:60); always with
 // kVarBias (a tanh does not preserve the constant-1 hidden units that carry the biases of layers 2 / 3 through a ReLU).
-enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2, kVarReward = 4, kVarRewardPolicy = 5, kVarBias = 8, kVarTanh = 16 };
+// kVarPolWide: the proposal network has up to 256 units per hidden layer (always with kVarPolicy; CTA pairs only).
+enum : int { kVarUniform = 0, kVarPolicy = 1, kVarLayerNorm = 2, kVarReward = 4, kVarRewardPolicy = 5, kVarBias = 8, kVarTanh = 16, kVarPolWide = 32 };
+// 64-unit chunks a hidden layer of the proposal network may have (= the image's chunk stride), its widest layer, its bias vector
+__host__ __device__ constexpr int pol_chunks(int var) { return (var & kVarPolWide) ? 4 : 2; }
+__host__ __device__ constexpr int pol_max_hidden(int var) { return (var & kVarPolWide) ? kPolWideHidden : kPolMaxHidden; }
+__host__ __device__ constexpr int pol_vec_floats(int var) { return (var & kVarPolWide) ? kPolWideVecFloats : kPolVecFloats; }
 __host__ __device__ constexpr int hidden2_chunks(int nc, int var) { return (var & kVarReward) ? 2 * nc : nc; }
 constexpr int kRewardCol = kD;          // output column of the reward head in D3
 constexpr uint32_t kLnStatsBytes = 3 * 2 * kRows * 8;      // [layer: hidden 1, hidden 2 (delta head), reward head][epilogue group][row] (sum, sum of squares)
@@ -144,7 +155,7 @@ constexpr Layout make_layout(int cg, int nc, int var) {
   const bool pol = (var & kVarPolicy) != 0, ln = (var & kVarLayerNorm) != 0, rew = (var & (kVarReward | kVarBias)) != 0;
   const int nc2 = hidden2_chunks(nc, var);
   Layout L;
-  L.kbs = stage_kblocks(cg, nc);
+  L.kbs = stage_kblocks(cg, nc, (var & kVarPolWide) != 0);
   L.nstg = (nc + L.kbs - 1) / L.kbs;
   L.blk_h = (kChunk / cg) * 128u;                  // bytes of one 64-wide k-block image of a hidden tile, per CTA
   L.blk_o = (kOutN / cg) * 128u;                   // ... of an output tile
@@ -153,9 +164,11 @@ constexpr Layout make_layout(int cg, int nc, int var) {
   L.off_a0 = 0;
   L.off_res = kA0Bytes;
   L.off_pol = (L.off_res + L.res_bytes + 1023u) / 1024u * 1024u;
-  // resident proposal network (sized for 128/128 hidden units): [Wp1: 2 chunks][Wp2: 2 chunks x 2 k-blocks][Wp3: 2 k-blocks]
-  L.pol_img_bytes = pol ? 6u * L.blk_h + 2u * L.blk_o : 0u;
-  L.pol_bytes = pol ? L.pol_img_bytes + kPolVecFloats * 4u : 0u;    // + biases of the three layers (float32, from device memory)
+  // resident proposal network (sized for PN = 2 chunks = 128 hidden units per layer, or PN = 4 = 256 in the kVarPolWide
+  // variants): [Wp1: PN chunks][Wp2: PN chunks x PN k-blocks][Wp3: PN k-blocks]
+  const uint32_t pn = (uint32_t)pol_chunks(var);
+  L.pol_img_bytes = pol ? (pn + pn * pn) * L.blk_h + pn * L.blk_o : 0u;
+  L.pol_bytes = pol ? L.pol_img_bytes + pol_vec_floats(var) * 4u : 0u;    // + biases of the three layers (float32, from device memory)
   // LayerNorm variant: per-column correction vectors of layer 2 (u2, c2: 2 x 64*nc floats) + per-row statistics
   L.off_ln = (L.off_pol + L.pol_bytes + 1023u) / 1024u * 1024u;
   // LayerNorm: [u2 (64 nc2)][c2 (64 nc2)][u3 (32)][c3 (32)] correction vectors + per-row statistics
@@ -241,13 +254,15 @@ inline bool tm_supported(const bcmpc_config& c, std::string* why) {
   return true;
 }
 
-// Proposal network for the fast path: sizes = {20, h1, h2, 6}, tanh hidden layers, h1, h2 <= 128.  W[l] are [in,out].
+// Proposal network for the fast path: sizes = {20, h1, h2, 6}, tanh hidden layers, h1, h2 <= 256 (more than 128 units in
+// either layer selects the kVarPolWide kernel variants).  W[l] are [in,out].
 inline bool tm_policy_supported(int n_layers, const int* sizes, std::string* why) {
   if (n_layers != 3) { *why = "bf16 fast path supports proposal networks with two hidden layers"; return false; }
   if (sizes[0] != kD || sizes[3] != kA) { *why = "bf16 fast path: proposal network must map 20 observations to 6 actions"; return false; }
-  if (sizes[1] < 1 || sizes[1] > kPolMaxHidden || sizes[2] < 1 || sizes[2] > kPolMaxHidden) { *why = "bf16 fast path: proposal network hidden sizes must be <= 128"; return false; }
+  if (sizes[1] < 1 || sizes[1] > kPolWideHidden || sizes[2] < 1 || sizes[2] > kPolWideHidden) { *why = "bf16 fast path: proposal network hidden sizes must be <= 256"; return false; }
   return true;
 }
+inline bool tm_policy_is_wide(const int* sizes) { return sizes[1] > kPolMaxHidden || sizes[2] > kPolMaxHidden; }
 // Dynamics weight images.  W[l] are TF kernels [in,out] (row stride ld): W1 [26,S], W2 [S,S], W3 [S,20].
 // Bias-in-GEMM: input columns 26,27 of A0 are 1.0; hidden units S and S+1 of both hidden layers are wired to be
 // exactly 1.0 after ReLU; row S / S+1 of the next layer's kernel hold bf16(b) and bf16(b - bf16(b)).
@@ -380,6 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   static_assert(!(VAR & kVarTanh) || (BIAS && !REW), "the plain tanh variant uses explicit biases");
   constexpr int NC2 = hidden2_chunks(NC, VAR);                // hidden-2 chunks (both heads of the learned-reward model)
   static_assert(NC <= kMaxChunks1 && NC2 <= kMaxChunks2, "unsupported kernel variant");
+  static_assert(!(VAR & kVarPolWide) || (POL && CG == 2), "the wide proposal network exists for CTA pairs only");
+  constexpr int PN = pol_chunks(VAR), PH = pol_max_hidden(VAR);   // proposal network: chunk slots per hidden layer, widest layer
   constexpr Layout L = Lay<CG, NC, VAR>::value;
   constexpr int kNstg = L.nstg;                               // weight stages per layer-2 chunk
   constexpr int kStagesPerStepR[2] = {((NC2 + 1) / 2) * kNstg, (NC2 / 2) * kNstg};   // weight stages per step and sub-ring (even / odd chunks)
@@ -425,14 +442,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     }
     for (int i = 0; i < kMaxChunks1 + kMaxChunks2; ++i) { ptx::mbar_init(ev + 8u * (kEvDFull + i), 1); ptx::mbar_init(ev + 8u * (kEvDEmpty + i), 4 * CG); }
     ptx::mbar_init(ev + 8u * kEvAp0Ready, 4 * CG);
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(ev + 8u * (kEvPdFull + i), 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(ev + 8u * (kEvAp1Ready + i), 4 * CG); ptx::mbar_init(ev + 8u * (kEvAp2Ready + i), 4 * CG); }
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(ev + 8u * (kEvPdFull + i), 1);
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(ev + 8u * (kEvAp1Ready + i), 4 * CG); ptx::mbar_init(ev + 8u * (kEvAp2Ready + i), 4 * CG); }
     ptx::mbar_init(ev + 8u * kEvPolFull, 1);
     ptx::fence_mbar_init();
   }
   if constexpr (POL) {
     float* s_pv = reinterpret_cast<float*>(smem + L.off_pol + L.pol_img_bytes);
-    for (int i = tid; i < 2 * kPolMaxHidden + kMaxAct; i += kThreads) s_pv[i] = a.polvec[i];
+    for (int i = tid; i < 2 * PH + kMaxAct; i += kThreads) s_pv[i] = a.polvec[i];
   }
   if constexpr (BIAS) {            // [b2 (64 * NC2: both heads of the reward model)][b3 (32)]
     float* s_vec = reinterpret_cast<float*>(smem + L.off_ln);
@@ -515,15 +532,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         if (mine == 1) {
           if constexpr (POL) {
             // ---- proposal network: policy input (smem) -> tanh layer -> tanh layer -> action means (D3 columns 0..5) ----
-            // Accumulators: layer-1 chunks in buffers 0,1; layer-2 chunks in buffers 2,0 (every policy accumulator has
-            // been drained before the barrier that lets its buffer's next user start completes).
+            // Accumulators: layer-1 chunks in buffers 0,1 (2,3: wide network); layer-2 chunks in buffers 2,0 (1,3) (every policy
+            // accumulator has been drained before the barrier that lets its buffer's next user start completes; buffer 3 =
+            // [448,512) overlaps the output accumulator D3, which is written only after all of hidden 2 has been stored).
             const uint64_t wpdesc = ptx::umma_desc_sw128(base + L.off_pol);
             const uint32_t np1 = (uint32_t)a.np1, np2 = (uint32_t)a.np2;
             ptx::mbar_wait(ev + 8u * kEvAp0Ready, par, hc);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               for (uint32_t j = 0; j < np1; ++j) {
-                const uint32_t d = j ? (uint32_t)buf_col(1) : (uint32_t)buf_col(0);
+                const uint32_t d = PN == 2 ? (j ? (uint32_t)buf_col(1) : (uint32_t)buf_col(0)) : (j < 3u ? (uint32_t)kColD + (uint32_t)kChunk * j : (uint32_t)kColA2);
 #pragma unroll
                 for (uint32_t ks = 0; ks < 2; ++ks)
                   ptx::umma_ss<CG>(d, a0desc + 2u * ks, wpdesc + (uint64_t)(j * (L.blk_h >> 4) + 2u * ks), kIdescH, ks);
@@ -533,28 +551,37 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
             __syncwarp();
             if (np1 > 1) ptx::mbar_wait2(ev + 8u * kEvAp1Ready, ev + 8u * (kEvAp1Ready + 1), par, hc);
             else ptx::mbar_wait(ev + 8u * kEvAp1Ready, par, hc);
+            if constexpr (PN > 2) {
+              if (np1 > 3) ptx::mbar_wait2(ev + 8u * (kEvAp1Ready + 2), ev + 8u * (kEvAp1Ready + 3), par, hc);
+              else if (np1 > 2) ptx::mbar_wait(ev + 8u * (kEvAp1Ready + 2), par, hc);
+            }
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               for (uint32_t j = 0; j < np2; ++j) {
-                const uint32_t d = j ? (uint32_t)buf_col(0) : (uint32_t)buf_col(2);
+                // buffers 2, 0 (, 1, 3)
+                const uint32_t d = PN == 2 ? (j ? (uint32_t)buf_col(0) : (uint32_t)buf_col(2)) : (j < 3u ? (uint32_t)kColD + (uint32_t)kChunk * ((j + 2u) % 3u) : (uint32_t)kColA2);
                 for (uint32_t kb = 0; kb < np1; ++kb)
 #pragma unroll
                   for (uint32_t ks = 0; ks < 4; ++ks)
-                    ptx::umma_ts<CG>(d, kColA1 + kb * 32u + ks * 8u, wpdesc + (uint64_t)((2u + j * 2u + kb) * (L.blk_h >> 4) + 2u * ks), kIdescH,
+                    ptx::umma_ts<CG>(d, kColA1 + kb * 32u + ks * 8u, wpdesc + (uint64_t)(((uint32_t)PN + j * (uint32_t)PN + kb) * (L.blk_h >> 4) + 2u * ks), kIdescH,
                                      (kb | ks) ? 1u : 0u);
-                ptx::umma_commit_cg<CG>(ev + 8u * (kEvPdFull + 2 + j));
+                ptx::umma_commit_cg<CG>(ev + 8u * (kEvPdFull + PN + j));
               }
             }
             __syncwarp();
             if (np2 > 1) ptx::mbar_wait2(ev + 8u * kEvAp2Ready, ev + 8u * (kEvAp2Ready + 1), par, hc);
             else ptx::mbar_wait(ev + 8u * kEvAp2Ready, par, hc);
+            if constexpr (PN > 2) {
+              if (np2 > 3) ptx::mbar_wait2(ev + 8u * (kEvAp2Ready + 2), ev + 8u * (kEvAp2Ready + 3), par, hc);
+              else if (np2 > 2) ptx::mbar_wait(ev + 8u * (kEvAp2Ready + 2), par, hc);
+            }
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               for (uint32_t kb = 0; kb < np2; ++kb)
 #pragma unroll
                 for (uint32_t ks = 0; ks < 4; ++ks)
-                  ptx::umma_ts<CG>(kColD3, kColA1 + 64u + kb * 32u + ks * 8u,
-                                   wpdesc + (uint64_t)(6u * (L.blk_h >> 4) + kb * (L.blk_o >> 4) + 2u * ks), kIdescO, (kb | ks) ? 1u : 0u);
+                  ptx::umma_ts<CG>(kColD3, kColA1 + 32u * (uint32_t)PN + kb * 32u + ks * 8u,
+                                   wpdesc + (uint64_t)((uint32_t)(PN + PN * PN) * (L.blk_h >> 4) + kb * (L.blk_o >> 4) + 2u * ks), kIdescO, (kb | ks) ? 1u : 0u);
               ptx::umma_commit_cg<CG>(ev + 8u * kEvPolFull);
             }
             __syncwarp();
@@ -734,16 +761,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         // one 64-unit chunk of a tanh layer: accumulator + bias -> tanh -> bf16 -> TMEM operand of the next policy layer
         auto pol_chunk = [&](auto lc, auto jc) {
           constexpr int layer = decltype(lc)::value, j = decltype(jc)::value;
-          constexpr uint32_t col = layer == 1 ? (uint32_t)buf_col(j) : (j == 0 ? (uint32_t)buf_col(2) : (uint32_t)buf_col(0));
-          constexpr uint32_t dst = kColA1 + (layer == 1 ? 0u : 64u) + 32u * j;
-          ptx::mbar_wait(ev + 8u * (kEvPdFull + (layer - 1) * 2 + j), uh & 1u, hc);
+          constexpr uint32_t col = layer == 1 ? (uint32_t)buf_col(j) : (j < 3 ? (uint32_t)buf_col((j + 2) % 3) : (uint32_t)buf_col(3));
+          constexpr uint32_t dst = kColA1 + (layer == 1 ? 0u : 32u * PN) + 32u * j;
+          ptx::mbar_wait(ev + 8u * (kEvPdFull + (layer - 1) * PN + j), uh & 1u, hc);
           ptx::tc_fence_after();
           if (trh) a.trace[h * kTraceSlots + kTrFinal + 1 + 2 * layer] = clock64();
           uint32_t v0[32], v1[32], w0[16], w1[16];
           ptx::tmem_ld32(lane_off + col, v0);
           ptx::tmem_ld32(lane_off + col + 32u, v1);
           ptx::tmem_ld_wait();
-          const float* s_pv = reinterpret_cast<const float*>(smem + L.off_pol + L.pol_img_bytes) + (layer == 1 ? 0 : kPolMaxHidden);
+          const float* s_pv = reinterpret_cast<const float*>(smem + L.off_pol + L.pol_img_bytes) + (layer == 1 ? 0 : PH);
           auto bias_at = [&](int idx) { return s_pv[idx]; };
           // bias, round to bf16, then one MUFU.TANH per two units (tanh.approx.bf16x2): the layer is MUFU-bound otherwise
 #pragma unroll
@@ -765,8 +792,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         // group g takes chunk g of both hidden layers
         if (g == 0) pol_chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
         else if (a.np1 > 1) pol_chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+        if constexpr (PN > 2) {      // wide network: group g also takes chunk 2 + g
+          if (g == 0) { if (a.np1 > 2) pol_chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{}); }
+          else if (a.np1 > 3) pol_chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, 3>{});
+        }
         if (g == 0) pol_chunk(std::integral_constant<int, 2>{}, std::integral_constant<int, 0>{});
         else if (a.np2 > 1) pol_chunk(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{});
+        if constexpr (PN > 2) {
+          if (g == 0) { if (a.np2 > 2) pol_chunk(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}); }
+          else if (a.np2 > 3) pol_chunk(std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{});
+        }
         if (is_final) {
           ptx::mbar_wait(ev + 8u * kEvPolFull, uh & 1u, hc);
           ptx::tc_fence_after();
@@ -777,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
           ptx::tc_fence_before();
 #pragma unroll
           for (int j = 0; j < kA; ++j) {
-            const float mean = __uint_as_float(v[j]) + reinterpret_cast<const float*>(smem + L.off_pol + L.pol_img_bytes)[2 * kPolMaxHidden + j];
+            const float mean = __uint_as_float(v[j]) + reinterpret_cast<const float*>(smem + L.off_pol + L.pol_img_bytes)[2 * PH + j];
             const int prop = h == 0 ? a.proposal0 : a.proposal;           // (the tree-search planner switches the mode after its first stage)
             if (prop == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
             else if (prop == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
@@ -1121,6 +1156,10 @@ inline cudaError_t tm_launch_t(const TmArgs& a, dim3 grid, cudaStream_t st) {
 // mode): variants 0..2 everywhere, the combinations at 4 and 8 chunks, no plain-tanh variant.
 inline bool tm_width_supported(int cg, int nc, int var) {
   if (nc < 1 || nc > 8) return false;
+  if (var & kVarPolWide) {      // wide proposal network: CTA pairs; ReLU (biases in the GEMMs), LayerNorm, the reward model, plain tanh
+    const int base = var & ~kVarPolWide;
+    return cg == 2 && (base == 1 || base == 3 || base == 5 || base == 7 || base == (kVarPolicy | kVarBias | kVarTanh));
+  }
   if (var & kVarTanh) return cg == 2 && (var & ~kVarPolicy) == (kVarBias | kVarTanh);
   if (var & kVarBias) return var <= (kVarBias | kVarPolicy) && nc <= 4;
   if (cg == 2) return var >= 0 && var < 8;
@@ -1158,7 +1197,7 @@ cudaError_t tm_launch_var(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream
   template <>                                                                                                   \
   cudaError_t tm_launch_var<VAR, DBG>(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream_t st) {            \
     if (cg == 2) return tm_launch_cg<2, VAR, DBG>(nc, a, grid, st);                                             \
-    if constexpr (((VAR) & kVarTanh) == 0) return tm_launch_cg<1, VAR, DBG>(nc, a, grid, st);                   \
+    if constexpr (((VAR) & (kVarTanh | kVarPolWide)) == 0) return tm_launch_cg<1, VAR, DBG>(nc, a, grid, st);   \
     return cudaErrorInvalidValue;                                                                               \
   }
 #define BCMPC_TM_DECLARE_VARIANT(VAR)                                                                            \
@@ -1167,6 +1206,7 @@ cudaError_t tm_launch_var(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream
 BCMPC_TM_DECLARE_VARIANT(0) BCMPC_TM_DECLARE_VARIANT(1) BCMPC_TM_DECLARE_VARIANT(2) BCMPC_TM_DECLARE_VARIANT(3)
 BCMPC_TM_DECLARE_VARIANT(4) BCMPC_TM_DECLARE_VARIANT(5) BCMPC_TM_DECLARE_VARIANT(6) BCMPC_TM_DECLARE_VARIANT(7)
 BCMPC_TM_DECLARE_VARIANT(8) BCMPC_TM_DECLARE_VARIANT(9) BCMPC_TM_DECLARE_VARIANT(24) BCMPC_TM_DECLARE_VARIANT(25)
+BCMPC_TM_DECLARE_VARIANT(33) BCMPC_TM_DECLARE_VARIANT(35) BCMPC_TM_DECLARE_VARIANT(37) BCMPC_TM_DECLARE_VARIANT(39) BCMPC_TM_DECLARE_VARIANT(57)
 template <bool DBG>
 inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
   switch (var) {
@@ -1182,6 +1222,12 @@ inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, d
     case 9: return tm_launch_var<9, DBG>(cg, nc, a, grid, st);   // ... + proposal network
     case 24: return tm_launch_var<24, DBG>(cg, nc, a, grid, st); // plain tanh dynamics (explicit biases)
     case 25: return tm_launch_var<25, DBG>(cg, nc, a, grid, st); // ... + proposal network
+    // proposal networks of up to 256 units per hidden layer (kVarPolWide)
+    case 33: return tm_launch_var<33, DBG>(cg, nc, a, grid, st); // ReLU dynamics
+    case 35: return tm_launch_var<35, DBG>(cg, nc, a, grid, st); // LayerNorm dynamics
+    case 37: return tm_launch_var<37, DBG>(cg, nc, a, grid, st); // learned-reward model (train_mpc_ppo_r.py:142 runs this pair)
+    case 39: return tm_launch_var<39, DBG>(cg, nc, a, grid, st); // learned-reward model with LayerNorm
+    case 57: return tm_launch_var<57, DBG>(cg, nc, a, grid, st); // plain tanh dynamics
   }
   return cudaErrorInvalidValue;
 }

@@ -3,6 +3,6 @@
 
 namespace bcmpc {
 namespace dpx {
-BCMPC_DEEP_DEFINE(deep_launch_prod, false)
+BCMPC_DEEP_DEFINE(deep_launch_prod, false, false)
 }  // namespace dpx
 }  // namespace bcmpc

@@ -146,14 +146,15 @@ __global__ void pack_reward_bias_kernel(PackArgs a) {
   a.lnvec[i] = v;
 }
 
-// Proposal network for the fast path: sizes = {20, h1, h2, 6}, tanh hidden layers, h1, h2 <= 128.  W[l] are [in,out]
-// with row stride ld[l] (device).  Image per CTA rank r (zero-filled by the caller first):
-//   [Wp1 chunk 0,1: 64 units x 64 k (20 used)][Wp2 chunk j x k-block kb][Wp3 k-block 0,1: 32 outputs (6 used) x 64 k]
-// and the bias vector polvec = [bp1 (128)][bp2 (128)][bp3 (8)].
+// Proposal network for the fast path: sizes = {20, h1, h2, 6}, tanh hidden layers, h1, h2 <= 64 pn (pn = 2 chunk slots per
+// layer, or 4 for the kVarPolWide variants).  W[l] are [in,out] with row stride ld[l] (device).  Image per CTA rank r
+// (zero-filled by the caller first):
+//   [Wp1 chunk 0..pn-1: 64 units x 64 k (20 used)][Wp2 chunk j x k-block kb (pn x pn)][Wp3 k-block 0..pn-1: 32 outputs (6 used) x 64 k]
+// and the bias vector polvec = [bp1 (64 pn)][bp2 (64 pn)][bp3 (8)].
 struct PolicyPackArgs {
   const float *W[3], *b[3];
   int ld[3];
-  int h1, h2, cg;
+  int h1, h2, cg, pn;
   uint32_t blk_h, blk_o, img_bytes;
   uint16_t* img;
   float* vec;
@@ -167,20 +168,20 @@ __global__ void pack_policy_kernel(PolicyPackArgs a) {
       a.img[((size_t)r * a.img_bytes + (size_t)j * a.blk_h + sw128_offset(ii, k)) / 2] = f32_to_bf16(a.W[0][(size_t)k * a.ld[0] + n]);
     } else if (i < n1 + n2) {
       const int e = i - n1, k = e / a.h2, n = e % a.h2, j = n / kChunk, r = (n % kChunk) / rows_h, ii = (n % kChunk) % rows_h;
-      a.img[((size_t)r * a.img_bytes + (size_t)(2 + j * 2 + k / 64) * a.blk_h + sw128_offset(ii, k % 64)) / 2] =
+      a.img[((size_t)r * a.img_bytes + (size_t)(a.pn + j * a.pn + k / 64) * a.blk_h + sw128_offset(ii, k % 64)) / 2] =
           f32_to_bf16(a.W[1][(size_t)k * a.ld[1] + n]);
     } else {
       const int e = i - n1 - n2, k = e / kA, n = e % kA, r = n / rows_o, ii = n % rows_o;
-      a.img[((size_t)r * a.img_bytes + 6u * a.blk_h + (size_t)(k / 64) * a.blk_o + sw128_offset(ii, k % 64)) / 2] =
+      a.img[((size_t)r * a.img_bytes + (size_t)(a.pn + a.pn * a.pn) * a.blk_h + (size_t)(k / 64) * a.blk_o + sw128_offset(ii, k % 64)) / 2] =
           f32_to_bf16(a.W[2][(size_t)k * a.ld[2] + n]);
     }
   }
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < 2 * kPolMaxHidden + kMaxAct) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, ph = 64 * a.pn;
+  if (t < 2 * ph + kMaxAct) {
     float v = 0.f;
-    if (t < kPolMaxHidden) v = t < a.h1 ? a.b[0][t] : 0.f;
-    else if (t < 2 * kPolMaxHidden) v = t - kPolMaxHidden < a.h2 ? a.b[1][t - kPolMaxHidden] : 0.f;
-    else v = t - 2 * kPolMaxHidden < kA ? a.b[2][t - 2 * kPolMaxHidden] : 0.f;
+    if (t < ph) v = t < a.h1 ? a.b[0][t] : 0.f;
+    else if (t < 2 * ph) v = t - ph < a.h2 ? a.b[1][t - ph] : 0.f;
+    else v = t - 2 * ph < kA ? a.b[2][t - 2 * ph] : 0.f;
     a.vec[t] = v;
   }
 }
@@ -188,7 +189,8 @@ inline cudaError_t tm_pack_policy(const PolicyPackArgs& a, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(a.img, 0, (size_t)a.cg * a.img_bytes, st);
   if (e != cudaSuccess) return e;
   const int total = kD * a.h1 + a.h1 * a.h2 + a.h2 * kA;
-  const int threads = total > 2 * kPolMaxHidden + kMaxAct ? total : 2 * kPolMaxHidden + kMaxAct;   // the first 264 threads also write the bias vector
+  const int nvec = 2 * 64 * a.pn + kMaxAct;
+  const int threads = total > nvec ? total : nvec;   // the first threads also write the bias vector
   pack_policy_kernel<<<(threads + 255) / 256, 256, 0, st>>>(a);
   return cudaGetLastError();
 }

@@ -216,6 +216,19 @@ def extras():
         "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
         "tflops_algorithmic": B * K * H * flop / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop}
     pl.close()
+    # the same plan with MlpPolicy(hid_size=256) (various_train/train_mpc_ppo_r.py:142): the kVarPolWide kernel variant -
+    # an 88 KB resident proposal network per CTA, quarter-chunk weight stages for the dynamics net
+    pw_w, logstd_w, rms_mean_w, rms_std_w = O.synthetic_policy(np.random.default_rng(4), hidden=(256, 256), norm=norm)
+    pl = make(K, H, "bf16", "policy_gaussian", B)
+    pl.set_policy(pw_w, logstd_w, rms_mean_w, rms_std_w, clip=5.0)
+    pl.enable_timing(True)
+    dt = time_plans(pl, states, 10)
+    k_ms = pl.last_kernel_ms()
+    flop_w = FLOP_PER_TRANSITION + 2 * (20 * 256 + 256 * 256 + 256 * 6)
+    out["configs3_policy_gaussian_hid256_K8192_H15_bf16_x16states"] = {
+        "transitions_per_s_e2e": B * K * H / dt, "transitions_per_s_kernel": B * K * H / (k_ms * 1e-3), "kernel_ms": k_ms,
+        "tflops_algorithmic": B * K * H * flop_w / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop_w}
+    pl.close()
     # the reference's default network size (train_mpc_ppo.py:75 size=256; the shape of saved_data/ppo-mpc/vars.pkl):
     # hidden <= 256 runs on rollout_narrow_kernel (two tiles per CTA); 37 states x 32 tiles = 296 CTA-pair units = 4 even waves
     B, K, H = 37, 4096, 20

@@ -147,8 +147,8 @@ def test_deep_full_size_properties():
 
 def test_deep_rejects_what_it_does_not_implement():
     from bc_mpc_b200 import Planner
-    with pytest.raises(RuntimeError, match="ReLU"):
-        Planner(20, 6, 3, 1024, "tanh", num_paths=256, horizon=2, precision="bf16")
+    with pytest.raises(RuntimeError, match="2..4 hidden layers"):
+        Planner(20, 6, 1, 1024, "relu", num_paths=256, horizon=2, precision="bf16")
     with pytest.raises(RuntimeError, match="uniform shooting"):
         Planner(20, 6, 3, 1024, "relu", num_paths=256, horizon=2, precision="bf16", proposal="policy_mix")
     rng, norm, weights, state = O.synthetic_problem(5, (600, 600))
@@ -156,3 +156,35 @@ def test_deep_rejects_what_it_does_not_implement():
     pl.set_dynamics(weights)
     with pytest.raises(RuntimeError, match="LayerNorm"):
         pl.set_layer_norm([(np.ones(600, np.float32), np.zeros(600, np.float32))] * 2)
+
+
+@pytest.mark.parametrize("hidden", [(1024, 1024, 1024), (600, 600), (300, 300, 300, 300)])
+def test_deep_tanh_dynamics(hidden):
+    """tanh hidden layers - the reference builder's default activation (dynamics.py:60) - on the cluster-split kernel:
+    same schedule, tanh.approx.bf16x2 in the layer-1 and owner epilogues instead of ReLU."""
+    from bc_mpc_b200 import Planner
+    K, H = 1000, 5
+    rng, norm, weights, state = O.synthetic_problem(43, hidden)
+    dyn = O.OracleDynamics(weights, norm, activation="tanh")
+    mpc = O.OracleMPC(dyn, H, K)
+    pl = Planner(20, 6, len(hidden), hidden[0], "tanh", num_paths=K, horizon=H, precision="bf16")
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    actions = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    e = _norm_err(so, dbg["states"], norm)
+    assert np.abs(e[1]).max() < 0.1 and np.abs(e).max() < 1.0, (np.abs(e[1]).max(), np.abs(e).max())
+    assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
+    rec = pl.plan(state, inj=actions)[0]
+    assert rec["index"] == int(np.argmin(co)) and rec["cost"] == co[rec["index"]]
+    assert (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std() < 0.5
+    prod = pl.plan(state, seed=11)[0]
+    again = pl.plan(state, inj=pl.sample_injection(11)[0])[0]
+    assert prod["index"] == again["index"] and prod["cost"] == again["cost"]
+    # and it is not the ReLU network
+    pr = Planner(20, 6, len(hidden), hidden[0], "relu", num_paths=K, horizon=H, precision="bf16")
+    pr.set_dynamics(weights)
+    pr.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    assert np.abs(pr.rollout_debug(state, actions)[0] - so).max() > 1e-3
+    pl.close(); pr.close()
