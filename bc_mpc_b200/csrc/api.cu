@@ -649,7 +649,14 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   if (c.path_offset < 0 || c.path_offset + c.num_paths > 0xFFFFFFFFLL) return fail(nullptr, BCMPC_ERR_INVALID, "path_offset out of range");
   // bf16 fast mode: two hidden layers of up to 510 units run on rollout_tmem_kernel / rollout_narrow_kernel, everything
   // wider or deeper (up to 4 x 1024) on the cluster-split rollout_deep_kernel
-  const bool want_deep = c.precision == BCMPC_PREC_BF16_FAST && (c.n_hidden != 2 || c.hidden_size > 510);
+  // (BCMPC_DEEP=1, a developer switch: also run two hidden layers of <= 510 units on the cluster-split kernel where it applies -
+  // half the layer-2 work per SM and step, the latency experiment of DESIGN.md section 7)
+  bool force_deep = false;
+  if (const char* s = getenv("BCMPC_DEEP")) {
+    std::string why;
+    force_deep = atoi(s) == 1 && c.precision == BCMPC_PREC_BF16_FAST && dpx::deep_supported(c, &why);
+  }
+  const bool want_deep = c.precision == BCMPC_PREC_BF16_FAST && (c.n_hidden != 2 || c.hidden_size > 510 || force_deep);
   if (c.precision == BCMPC_PREC_BF16_FAST) {
     std::string why;
     if (want_deep ? !dpx::deep_supported(c, &why) : !tmx::tm_supported(c, &why)) return fail(nullptr, BCMPC_ERR_UNSUPPORTED, "%s", why.c_str());
@@ -954,7 +961,9 @@ int set_policy_common(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, c
   update_verify_geometry(h);
   if (fast) {
     // the image layout depends only on the CTA-group size: it can be packed before the dynamics weights arrive
-    const bool wide = tmx::tm_policy_is_wide(sizes);
+    // (BCMPC_POL_WIDE=1, a developer switch: run a <= 128-unit network on the wide variants - their cost is the smaller weight ring)
+    const char* force_wide = getenv("BCMPC_POL_WIDE");
+    const bool wide = tmx::tm_policy_is_wide(sizes) || (force_wide && atoi(force_wide) == 1 && h->tm_cg == 2);
     if (wide && h->tm_cg != 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: proposal networks wider than 128 units need CTA pairs (BCMPC_TC_CG=2, the default)");
     const int pvar = tmx::kVarPolicy | (wide ? tmx::kVarPolWide : 0);
     const tmx::Layout lay = tmx::make_layout(h->tm_cg, 1, pvar);

@@ -119,9 +119,10 @@ int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const flo
  * tf.contrib.layers.layer_norm AFTER the activation of every hidden layer - moments over the last axis, centre and
  * scale.  gamma[l], beta[l] are [hidden_size] for hidden layer l (n_hidden of them); eps is the variance epsilon
  * (1e-12 in tf.contrib).  gamma == NULL switches LayerNorm off.  Call it after bcmpc_set_dynamics (new weights reset
- * it).  Both precision modes; with BCMPC_PREC_BF16_FAST and a proposal network or a reward head it is built for hidden
- * sizes 193..256 and 449..512 (BCMPC_ERR_UNSUPPORTED otherwise), and a reward head needs bcmpc_set_reward_layer_norm
- * too (all three LayerNorms or none). */
+ * it).  Both precision modes; with BCMPC_PREC_BF16_FAST: ReLU dynamics of two hidden layers (<= 510 units; also together
+ * with a proposal network) and the tanh learned-reward model, where a reward head needs bcmpc_set_reward_layer_norm too
+ * (all three LayerNorms or none); a plain tanh net with LayerNorm and the cluster-split kernel (n_hidden > 2 or
+ * hidden_size > 510) fail with BCMPC_ERR_UNSUPPORTED there. */
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps);
 /* ... with DEVICE pointers, enqueued on `stream` (see bcmpc_set_dynamics_device). */
 int bcmpc_set_layer_norm_device(bcmpc_handle* h, const float* const* d_gamma, const float* const* d_beta, int32_t n_hidden,
@@ -134,8 +135,9 @@ int bcmpc_set_layer_norm_device(bcmpc_handle* h, const float* const* d_gamma, co
  * MPCcontrollerPolicyNetReward, :319-363): bcmpc_record.cost is MINUS that sum, index / action its argmax (first index
  * on ties, like np.argmax).  W == NULL switches back to cheetah_cost_fn.  Call after bcmpc_set_dynamics; the head
  * persists across later bcmpc_set_dynamics calls.  BCMPC_PREC_BF16_FAST runs it on the tensor cores for the
- * reference's shape (tanh, hidden size 449..512 or 193..256: both heads form one 2 x hidden wide second layer), with
- * uniform or policy-guided proposals; other shapes fail with BCMPC_ERR_UNSUPPORTED there and run in verification mode. */
+ * reference's activation (tanh, dynamics.py:162) at every hidden size <= 510 (both heads form one 2 x hidden wide second
+ * layer), with uniform or policy-guided proposals; ReLU heads fail with BCMPC_ERR_UNSUPPORTED there and run in
+ * verification mode. */
 int bcmpc_set_reward_head(bcmpc_handle* h, const float* const* W, const float* const* b, double mean_reward,
                           double std_reward, double gamma);
 
@@ -166,7 +168,10 @@ int bcmpc_set_action_bounds(bcmpc_handle* h, const double* low, const double* hi
 /* Proposal network: MlpPolicy 'pol' branch (ppo_bc_policy.py:60,70-72,79) or BCnetwork
  * (behavioral_cloning.py:21-26).  sizes has n_layers+1 entries (sizes[0] = D, last = A); hidden
  * layers are tanh, the last is linear.  logstd [A] may be NULL (P2/P3).  filt_mean/filt_std [D]
- * (RunningMeanStd mean/std as float32) may be NULL = no filter; clip <= 0 = no clipping. */
+ * (RunningMeanStd mean/std as float32) may be NULL = no filter; clip <= 0 = no clipping.
+ * BCMPC_PREC_BF16_FAST: two hidden layers of at most 256 units (MlpPolicy hid_size 128 / 256, BCnetwork 128 / 64); a network
+ * with more than 128 units in a layer runs on kernel variants with a smaller weight ring, and switching between the two
+ * classes re-packs the dynamics images.  Wider / deeper networks: BCMPC_ERR_UNSUPPORTED (verification mode takes any). */
 int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* W,
                      const float* const* b, const float* logstd, const float* filt_mean,
                      const float* filt_std, float clip);

@@ -10,6 +10,7 @@ from bc_mpc_b200 import Planner  # noqa: E402
 from oracle import mpc_oracle as O  # noqa: E402
 
 rng, norm, weights, state = O.synthetic_problem(0, (500, 500))
+print("BCMPC_DEEP =", os.environ.get("BCMPC_DEEP"))
 for K, H in ((1000, 15), (1000, 1), (4096, 15)):
     pl = Planner(20, 6, 2, 500, "relu", num_paths=K, horizon=H, precision="bf16")
     pl.set_dynamics(weights)
