@@ -15,19 +15,28 @@ rng = np.random.default_rng(int(os.environ.get("STRESS_SEED", "1")))
 t0, n, by_kind = time.time(), 0, {}
 while time.time() - t0 < budget:
     S = int(rng.choice([7, 64, 100, 128, 200, 256, 300, 384, 500, 510]))
-    kind = str(rng.choice(["uniform", "policy_gaussian", "policy_mix", "bc_uniform", "ln", "ln+policy", "reward", "reward+ln+policy"]))
-    rew, ln = "reward" in kind, "ln" in kind
+    kind = str(rng.choice(["uniform", "policy_gaussian", "policy_mix", "bc_uniform", "ln", "ln+policy", "reward", "reward+ln+policy", "reward+policy",
+                           "tanh", "tanh+policy", "deep", "deep+tanh"]))
+    rew, ln, deep = "reward" in kind, "ln" in kind, "deep" in kind
+    act = "tanh" if (rew or "tanh" in kind) else "relu"
     if rew:
-        S = int(rng.choice([256, 500]))
-    if kind == "ln+policy" and not (S <= 256 or 449 <= S <= 512):
-        S = 256
+        S = int(rng.choice([100, 256, 330, 500]))
+    hidden = (S, S)
+    if deep:      # the cluster-split kernel: more than two hidden layers or more than 510 units
+        S = int(rng.choice([100, 300, 600, 768, 1024]))
+        hidden = (S,) * int(rng.integers(3 if S <= 510 else 2, 5))
     prop = kind if kind in ("policy_gaussian", "policy_mix", "bc_uniform") else ("policy_gaussian" if "policy" in kind else "uniform")
     K, H, B = int(rng.integers(1, 3000)), int(rng.integers(1, 12)), int(rng.integers(1, 5))
     if rng.random() < 0.15:
         K, B = int(rng.integers(3000, 20000)), int(rng.integers(4, 40))       # multi-wave launches (narrow-net kernel where it applies)
-    prng, norm, weights, rweights, state = O.synthetic_reward_problem(int(rng.integers(1 << 30)), S)
+    if deep:
+        K = min(K, 4000)
+        prng, norm, weights, state = O.synthetic_problem(int(rng.integers(1 << 30)), hidden)
+        rweights = None
+    else:
+        prng, norm, weights, rweights, state = O.synthetic_reward_problem(int(rng.integers(1 << 30)), S)
     try:
-        pl = Planner(20, 6, 2, S, "tanh" if rew else "relu", num_paths=K, horizon=H, max_states=B, precision="bf16", proposal=prop, explore=0.3)
+        pl = Planner(20, 6, len(hidden), S, act, num_paths=K, horizon=H, max_states=B, precision="bf16", proposal=prop, explore=0.3)
         pl.set_dynamics(weights)
         pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
         lns = [(1.0 + 0.1 * prng.standard_normal(S).astype(np.float32), 0.1 * prng.standard_normal(S).astype(np.float32)) for _ in range(3)]
@@ -38,7 +47,7 @@ while time.time() - t0 < budget:
         if prop == "bc_uniform":
             pl.set_policy(O.glorot_mlp(prng, (20, 128, 64, 6), 0.05))
         elif prop != "uniform":
-            pw, logstd, rms_mean, rms_std = O.synthetic_policy(prng, hidden=(int(rng.choice([32, 64, 128])), int(rng.choice([48, 128]))), norm=norm)
+            pw, logstd, rms_mean, rms_std = O.synthetic_policy(prng, hidden=(int(rng.choice([32, 64, 128, 129, 200, 256])), int(rng.choice([48, 128, 192, 256]))), norm=norm)
             pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
     except RuntimeError as e:            # combinations without a kernel in this mode (e.g. BCMPC_TC_CG=1: reward heads + policy)
         if "weight ring" in str(e) or "hidden sizes" in str(e):
