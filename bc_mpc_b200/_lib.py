@@ -8,7 +8,7 @@ import numpy as np
 from . import _build
 
 MAX_ACT = 8
-ABI_VERSION = 3      # BCMPC_ABI_VERSION of include/bcmpc.h this binding was written against
+ABI_VERSION = 4      # BCMPC_ABI_VERSION of include/bcmpc.h this binding was written against
 
 
 class Config(C.Structure):
@@ -53,6 +53,7 @@ SIGNATURES = {
     "bcmpc_set_policy": (C.c_int, [_P, C.c_int32, _P, _PP, _PP, _P, _P, _P, C.c_float]),
     "bcmpc_plan": (C.c_int, [_P, _P, C.c_int32, _P, C.c_uint64, _P]),
     "bcmpc_plan_device": (C.c_int, [_P, _P, C.c_int32, _P, C.c_uint64, _P, _P]),
+    "bcmpc_plan_device_seeded": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),
     "bcmpc_rollout_debug": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P, _P]),
     "bcmpc_predict": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "bcmpc_policy_act": (C.c_int, [_P, _P, _P, C.c_int64, _P]),

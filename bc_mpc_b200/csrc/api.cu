@@ -579,6 +579,10 @@ int run_plan(bcmpc_handle* h, PlanArgs p, bcmpc_record* d_out, cudaStream_t st, 
   if (rc) return rc;
   if (h->timing) { CK(h, cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
   if (exchange) {
+    // the exchange epoch is a launch argument that must advance with every plan: a captured graph would replay a stale one
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+      return fail(h, BCMPC_ERR_UNSUPPORTED, "a plan with the NVLink peer-store exchange cannot be captured into a CUDA graph (use BCMPC_EXCHANGE=nccl or capture per-rank plans)");
     h->peer.epoch++;
     peer_exchange_kernel<<<h->peer.world, 256, 0, st>>>(h->peer, h->d_cand, p.tiles_per_state, p.B, d_out);
     CK(h, cudaGetLastError());
@@ -1021,8 +1025,9 @@ int bcmpc_set_policy_device(bcmpc_handle* h, int32_t n_layers, const int32_t* si
   return after_handoff(h, true, st);
 }
 
-int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj, uint64_t seed,
-                      bcmpc_record* d_out, void* stream) {
+namespace {
+int plan_device_common(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj, uint64_t seed,
+                       const uint64_t* d_seed, bcmpc_record* d_out, void* stream) {
   if (!h || !d_states || !d_out) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_states < 1 || n_states > h->cfg.max_states) return fail(h, BCMPC_ERR_INVALID, "n_states %d out of [1,%d]", n_states, h->cfg.max_states);
   int rc = check_ready(h, needs_policy(h->cfg));
@@ -1030,9 +1035,22 @@ int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states,
   if (!h->rew.set && h->cfg.obs_dim < 18) return fail(h, BCMPC_ERR_INVALID, "cheetah_cost_fn indexes obs[17]; obs_dim = %d (set a reward head to plan on a learned reward)", h->cfg.obs_dim);
   ON_DEVICE(h);
   PlanArgs p = base_plan_args(h, n_states, seed);
+  p.seed_ptr = reinterpret_cast<const unsigned long long*>(d_seed);
   p.states = d_states;
   p.inj = d_inj;
   return run_plan(h, p, d_out, stream ? (cudaStream_t)stream : h->stream, 0);
+}
+}  // namespace
+
+int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj, uint64_t seed,
+                      bcmpc_record* d_out, void* stream) {
+  return plan_device_common(h, d_states, n_states, d_inj, seed, nullptr, d_out, stream);
+}
+
+int bcmpc_plan_device_seeded(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj,
+                             const uint64_t* d_seed, bcmpc_record* d_out, void* stream) {
+  if (!d_seed) return fail(h, BCMPC_ERR_INVALID, "null argument");
+  return plan_device_common(h, d_states, n_states, d_inj, 0, d_seed, d_out, stream);
 }
 
 int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const double* inj, uint64_t seed,

@@ -106,6 +106,7 @@ struct PlanArgs {
   int proposal0, inj_kind0;   // step 0 (differs from proposal / inj_kind in the tree-search planner only)
   int64_t path_offset;
   uint64_t seed;
+  const unsigned long long* seed_ptr;   // device-resident seed (bcmpc_plan_device_seeded: a captured CUDA graph replays with new draws), or nullptr = `seed`
   const double* states;       // [B, D] root states  (or [n, D] per-row states in predict mode)
   const double* inj;          // [B, H, K, A] or nullptr
   Candidate* cand;            // [B, tiles_per_state]
@@ -120,6 +121,9 @@ struct PlanArgs {
   bcmpc_record* out;          // [B] winning records, or nullptr = a separate reduce_candidates_kernel follows
   unsigned int* ticket;       // [B] finished-tile counters, zero between plans
 };
+
+// the plan's Philox key: the launch argument, or the device scalar a captured graph reads at replay time
+__device__ __forceinline__ uint64_t plan_seed(const PlanArgs& p) { return p.seed_ptr ? (uint64_t)__ldg(p.seed_ptr) : p.seed; }
 
 // Called by every lane of the warp that holds a tile's winning row, after that row's lane (writer_lane) has written the
 // tile's candidate.  np.argmin order, same as reduce_candidates_kernel.

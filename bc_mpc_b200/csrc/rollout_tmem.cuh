@@ -350,7 +350,7 @@ __device__ __forceinline__ void get_noise(const TmArgs& a, int b, int h, int k, 
     for (int j = 0; j < kA; ++j) z[j] = (float)src[j];
   } else {
     float v[kMaxAct];
-    draw_injection(v, kA, POL ? (h == 0 ? a.inj_kind0 : a.inj_kind) : (int)kInjUniformBox, p.seed, (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
+    draw_injection(v, kA, POL ? (h == 0 ? a.inj_kind0 : a.inj_kind) : (int)kInjUniformBox, plan_seed(p), (uint32_t)(p.path_offset + k), (uint32_t)b, (uint32_t)h, a.low, a.span);
 #pragma unroll
     for (int j = 0; j < kA; ++j) z[j] = v[j];
   }

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kVerifyThreads) rollout_verify_kernel(const __
       }
     } else if (tid < M) {
       float v[kMaxAct];
-      draw_injection(v, A, h == 0 ? p.inj_kind0 : p.inj_kind, p.seed, (uint32_t)(p.path_offset + k_base + tid), (uint32_t)b, (uint32_t)h,
+      draw_injection(v, A, h == 0 ? p.inj_kind0 : p.inj_kind, plan_seed(p), (uint32_t)(p.path_offset + k_base + tid), (uint32_t)b, (uint32_t)h,
                      a.n.low, a.n.span);
       for (int j = 0; j < A; ++j) s_inj[tid * kMaxAct + j] = (double)v[j];
     }

@@ -254,10 +254,17 @@ class Planner:
         self._ck(self._lib.bcmpc_plan(self._h, L.ptr(states), B, L.ptr(inj), C.c_uint64(seed), L.ptr(out)))
         return out
 
-    def plan_device(self, d_states_ptr, n_states, d_out_ptr, seed=0, d_inj_ptr=None, stream_ptr=None):
+    def plan_device(self, d_states_ptr, n_states, d_out_ptr, seed=0, d_inj_ptr=None, stream_ptr=None, d_seed_ptr=None):
         """Asynchronous launch on device buffers (raw pointers, e.g. torch.Tensor.data_ptr()).
         stream_ptr: None = the handle's own stream; an integer cudaStream_t otherwise (0, torch's default
-        stream, is passed as cudaStreamLegacy so that it is not mistaken for "none")."""
+        stream, is passed as cudaStreamLegacy so that it is not mistaken for "none").
+        d_seed_ptr: device address of a uint64 / int64 scalar that holds the Philox key (bcmpc_plan_device_seeded) - the
+        launch can then be captured into a CUDA graph and replayed with new draws; `seed` is ignored."""
+        if d_seed_ptr is not None:
+            self._ck(self._lib.bcmpc_plan_device_seeded(self._h, C.c_void_p(d_states_ptr), n_states,
+                                                        C.c_void_p(d_inj_ptr) if d_inj_ptr else None, C.c_void_p(d_seed_ptr),
+                                                        C.c_void_p(d_out_ptr), _stream(stream_ptr)))
+            return
         self._ck(self._lib.bcmpc_plan_device(self._h, C.c_void_p(d_states_ptr), n_states,
                                              C.c_void_p(d_inj_ptr) if d_inj_ptr else None, C.c_uint64(seed),
                                              C.c_void_p(d_out_ptr), _stream(stream_ptr)))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BCMPC_ABI_VERSION 3   /* bumped whenever bcmpc_config, bcmpc_record or a signature changes */
+#define BCMPC_ABI_VERSION 4   /* bumped whenever bcmpc_config, bcmpc_record or a signature changes */
 #define BCMPC_MAX_ACT 8      /* action dims carried in a record (HalfCheetah: 6) */
 #define BCMPC_MAX_OBS 32     /* observation dims supported (HalfCheetah: 20)      */
 #define BCMPC_MAX_LAYERS 5   /* dense layers per MLP, output layer included        */
@@ -194,6 +194,15 @@ int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const do
 /* Same, DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = the handle's own). */
 int bcmpc_plan_device(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj,
                       uint64_t seed, bcmpc_record* d_out, void* stream);
+
+/* Same, with the Philox key read from DEVICE memory (*d_seed) when the kernels run instead of being a launch argument.
+ * The call makes no host round trip and is capturable (cudaStreamBeginCapture / torch.cuda.graph; make one un-captured
+ * call first: the first launch of a kernel sets its attributes): the vectorised env loop of utils.py:193-213 - policy /
+ * env step / plan per time step - becomes one graph, and every replay draws new action sequences once the caller has
+ * advanced *d_seed (e.g. a one-element tensor incremented inside the same graph).  Same results as bcmpc_plan_device
+ * with seed = *d_seed. */
+int bcmpc_plan_device_seeded(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj,
+                             const uint64_t* d_seed, bcmpc_record* d_out, void* stream);
 
 /* Verification only: one root state, every path's states [H+1,K,D] (controllers.py:74), actions
  * [H,K,A] and trajectory costs [K] (controllers.py:80).  Any output may be NULL.  HOST buffers. */

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.bcmpc_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.bcmpc_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header():
