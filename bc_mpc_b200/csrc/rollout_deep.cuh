@@ -53,6 +53,19 @@ constexpr int kMaxHidden = BCMPC_MAX_LAYERS - 1;  // hidden layers (the handle a
 constexpr uint32_t kStageBytes = 16384;         // one weight stage: four (64-unit chunk x 64-wide k-block) tiles of this CTA's row half
 constexpr uint32_t kTileH = 4096, kTileO = 2048;   // hidden tile (32 rows x 128 B), output tile (16 rows x 128 B)
 constexpr uint32_t kRecvBytes = 16384;          // one receive slot: 128 rows x 32 fp32 - HALF a chunk per message (two 32 KB slots cost the weight ring two stages)
+// The hidden layers' partials cross the cluster as 24-bit floats (sign, exponent, 15 mantissa bits, round to nearest): four
+// values in three words, 12 instead of 16 st.async per thread and use.  The exchange needs 16 B/clk per SM and direction to
+// keep the tensor pipe busy and the SM-to-SM network delivers 17.5 (tools/micro/dsmem_bw.cu): with 25 % fewer bytes the steady
+// state is the pipe's.  The rounding (2^-16 of the PARTNER's partial; the own partial stays fp32) is 2^8 times finer than the bf16
+// rounding of the activation that follows.  The output layer's 20-column exchange stays fp32 (both K-halves must carry
+// bit-identical states).  -DBCMPC_DEEP_FP32_EXCHANGE restores the fp32 partials (A/B, tools/deep_bench.py).
+#ifdef BCMPC_DEEP_FP32_EXCHANGE
+constexpr bool kPack24 = false;
+#else
+constexpr bool kPack24 = true;
+#endif
+constexpr uint32_t kMsgV4 = kPack24 ? 6 : 8;            // 16-byte stores per thread and half-chunk message (32 values)
+constexpr uint32_t kMsgBytes = kMsgV4 * 2048u;         // bytes of one hidden-layer message (128 rows)
 constexpr uint32_t kA0Bytes = 128 * 128;
 constexpr uint32_t kBlockBytes = 128 * 128;     // one 64-unit k-block of an activation as an smem A tile
 
@@ -152,6 +165,19 @@ __device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t bar, uint32_
                "r"(y), "r"(z), "r"(w), "r"(bar)
                : "memory");
 }
+// four fp32 bit patterns -> three words of 24-bit floats (round to nearest; Inf / NaN survive), and back (low byte zero)
+__device__ __forceinline__ void pack24(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+  a += 0x80u; b += 0x80u; c += 0x80u; d += 0x80u;
+  w0 = __byte_perm(a, b, 0x3217);          // [a3 a2 a1 | b3]
+  w1 = __byte_perm(b, c, 0x2176);          // [b2 b1 | c3 c2]
+  w2 = __byte_perm(c, d, 0x1765);          // [c1 | d3 d2 d1]
+}
+__device__ __forceinline__ void unpack24(uint32_t w0, uint32_t w1, uint32_t w2, float& a, float& b, float& c, float& d) {
+  a = __uint_as_float(w0 & 0xFFFFFF00u);
+  b = __uint_as_float(__byte_perm(w0, w1, 0x0764) & 0xFFFFFF00u);      // [b3 = w0.0, b2 = w1.3, b1 = w1.2, -]
+  c = __uint_as_float(__byte_perm(w1, w2, 0x1074) & 0xFFFFFF00u);      // [c3 = w1.1, c2 = w1.0, c1 = w2.3, -]
+  d = __uint_as_float(w2 << 8);
+}
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -239,6 +265,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
   // Every accumulator is written by one warp only: results do not depend on how the two streams interleave.
   if (warp == 0) {
     // ===================== weight producer: every CTA streams its own row halves =====================
+    // (ONE producer walking the stages in consumption order.  A producer warp per sub-ring - no head-of-line blocking on the
+    // other sub-ring's "stage empty" barrier - was measured and is slower, 51 550 vs 49 920 cycles per step: the stream is
+    // bound by L2 -> SM bandwidth, weights 5.1 TB/s + exchange ~2 TB/s over 132 SMs, not by when the requests are issued.)
     uint32_t wsr[2] = {0, 0};
     auto fill = [&](int r, const uint8_t* src, uint32_t bytes) {
       const uint32_t n = wsr[r]++, stage = (uint32_t)Y.first_r[r] + n % (uint32_t)Y.nst_r[r], ph = (n / (uint32_t)Y.nst_r[r]) & 1u;
@@ -537,8 +566,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
                 const uint32_t dst = base_partner + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
                 const uint32_t rbar = misc_partner + kBarRecvFull + 8u * slot;
                 const uint32_t(&v)[32] = hf ? v1 : v0;
+                if constexpr (kPack24) {
+                  uint32_t w[24];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) st_async_v4(dst + (uint32_t)j * 2048u, rbar, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                  for (int j = 0; j < 8; ++j) pack24(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], w[3 * j], w[3 * j + 1], w[3 * j + 2]);
+#pragma unroll
+                  for (int j = 0; j < 6; ++j) st_async_v4(dst + (uint32_t)j * 2048u, rbar, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) st_async_v4(dst + (uint32_t)j * 2048u, rbar, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
               }
               if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 3);
             } else {
@@ -548,8 +585,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
               // arm both halves (16 KB each will arrive) only now: this accumulator exists, so the layer's input does, so the
               // previous step's output exchange - the last message the OTHER group armed on one of these slots - is complete
               if (warp == 8 && ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * (x0 & 1u), kRecvBytes);
-                ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * ((x0 + 1u) & 1u), kRecvBytes);
+                ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * (x0 & 1u), kMsgBytes);
+                ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * ((x0 + 1u) & 1u), kMsgBytes);
               }
               __syncwarp();
               if (tr) BCMPC_DTRACE(a.trace, step, 2, tuse, 1);
@@ -565,8 +602,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
                 const uint32_t(&v)[32] = hf ? v1 : v0;
                 uint32_t(&w)[16] = hf ? w1 : w0;
                 float4 r[8];
+                if constexpr (kPack24) {
+                  float4 q[6];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] = ld_shared_v4(src + (uint32_t)j * 2048u);      // all eight loads in flight before the first use
+                  for (int j = 0; j < 6; ++j) q[j] = ld_shared_v4(src + (uint32_t)j * 2048u);    // all six loads in flight before the first use
+                  const uint32_t* qw = reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) unpack24(qw[3 * j], qw[3 * j + 1], qw[3 * j + 2], r[j].x, r[j].y, r[j].z, r[j].w);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) r[j] = ld_shared_v4(src + (uint32_t)j * 2048u);    // all eight loads in flight before the first use
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float4 bb = b4[8 * hf + j];
