@@ -75,8 +75,8 @@ def lib():
     """Loads (building first if the sources are newer) libbcmpc.so."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if _build.stale():
+        path = os.environ.get("BCMPC_LIB") or _build.LIB        # (BCMPC_LIB: a developer A/B build, tools/ab_deep.sh)
+        if path == _build.LIB and _build.stale():
             try:
                 _build.build()
             except Exception as e:  # no nvcc on the box: use the shipped .so if there is one, but say so

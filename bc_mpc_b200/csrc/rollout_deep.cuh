@@ -52,7 +52,8 @@ constexpr int kMaxNch = 8;                      // hidden <= 1024
 constexpr int kMaxHidden = BCMPC_MAX_LAYERS - 1;  // hidden layers (the handle accepts n_hidden + 1 <= BCMPC_MAX_LAYERS)
 constexpr uint32_t kStageBytes = 16384;         // one weight stage: four (64-unit chunk x 64-wide k-block) tiles of this CTA's row half
 constexpr uint32_t kTileH = 4096, kTileO = 2048;   // hidden tile (32 rows x 128 B), output tile (16 rows x 128 B)
-constexpr uint32_t kRecvBytes = 16384;          // one receive slot: 128 rows x 32 fp32 - HALF a chunk per message (two 32 KB slots cost the weight ring two stages)
+// one receive slot: HALF a chunk per message, 128 rows x 32 values (two whole-chunk slots cost the weight ring two stages); with
+// 24-bit partials 12 KB - the two slots then leave room for a SEVENTH weight stage (the output layer's 10 KB message fits too)
 // The hidden layers' partials cross the cluster as 24-bit floats (sign, exponent, 15 mantissa bits, round to nearest): four
 // values in three words, 12 instead of 16 st.async per thread and use.  The exchange needs 16 B/clk per SM and direction to
 // keep the tensor pipe busy and the SM-to-SM network delivers 17.5 (tools/micro/dsmem_bw.cu): with 25 % fewer bytes the steady
@@ -66,6 +67,7 @@ constexpr bool kPack24 = true;
 #endif
 constexpr uint32_t kMsgV4 = kPack24 ? 6 : 8;            // 16-byte stores per thread and half-chunk message (32 values)
 constexpr uint32_t kMsgBytes = kMsgV4 * 2048u;         // bytes of one hidden-layer message (128 rows)
+constexpr uint32_t kRecvBytes = kMsgBytes;
 constexpr uint32_t kA0Bytes = 128 * 128;
 constexpr uint32_t kBlockBytes = 128 * 128;     // one 64-unit k-block of an activation as an smem A tile
 
@@ -90,7 +92,14 @@ enum : uint32_t {
   kOffRed = 320,        // argmin scratch (128 B)
   kMiscBytes = 512
 };
-constexpr int kMaxStages = 8;
+#ifndef BCMPC_DEEP_STAGES
+#define BCMPC_DEEP_STAGES 7
+#endif
+constexpr int kMaxStages = BCMPC_DEEP_STAGES;      // (a seventh stage fits since the 24-bit exchange shrank the receive slots: A/B in tools/ab_deep.sh)
+#ifndef BCMPC_DEEP_WEIGHTS_FIRST
+#define BCMPC_DEEP_WEIGHTS_FIRST 1
+#endif
+constexpr bool kWeightsFirst = BCMPC_DEEP_WEIGHTS_FIRST != 0;   // issuer: wait for the weight stages before the accumulator's "drained" barrier
 
 struct Layout {
   int nch = 0, L = 0, nt = 0, ns = 0, spu = 0, nst = 0;
@@ -112,7 +121,11 @@ constexpr Layout make_layout(int nch, int max_hidden) {
   const uint32_t fixed = Y.off_ring + ((Y.vec_bytes + 1023u) / 1024u * 1024u) + kMiscBytes;
   Y.nst = (int)((tmx::kSmemLimit - fixed) / kStageBytes);
   if (Y.nst > kMaxStages) Y.nst = kMaxStages;
-  Y.nst_r[0] = (Y.nst + 1) / 2; Y.nst_r[1] = Y.nst / 2;      // one sub-ring per issuer warp
+#ifdef BCMPC_DEEP_ODD_TO_F
+  Y.nst_r[0] = (Y.nst + 1) / 2; Y.nst_r[1] = Y.nst / 2;
+#else
+  Y.nst_r[0] = Y.nst / 2; Y.nst_r[1] = (Y.nst + 1) / 2;      // one sub-ring per issuer warp (an odd stage goes to the O issuer's)
+#endif
   Y.first_r[0] = 0; Y.first_r[1] = Y.nst_r[0];
   Y.off_vec = Y.off_ring + Y.nst * kStageBytes;
   Y.off_misc = Y.off_vec + (Y.vec_bytes + 1023u) / 1024u * 1024u;
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
 
   if (tid == 0) {
     if (base & 1023u) { printf("bcmpc: dynamic smem base not 1024-byte aligned\n"); __trap(); }
-    for (int i = 0; i < kMaxStages; ++i) {
+    for (int i = 0; i < 8; ++i) {
       ptx::mbar_init(misc + kBarWFull + 8u * i, leader ? 2 : 1);   // leader: own producer + the peer's "my half has landed"
       ptx::mbar_init(misc + kBarWEmpty + 8u * i, 1);
     }
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           }
           const uint32_t idesc = outl ? kIdescO : kIdescH, tile16 = (outl ? kTileO : kTileH) >> 4;
           for (int i = 0; i < (outl ? 1 : NCH); ++i) {
-            const uint32_t j = (uint32_t)NCH + (uint32_t)(l - 2) * 2u * NCH + 2u * (uint32_t)i + (outl ? 0u : w);   // index of the use within the step
+            [[maybe_unused]] const uint32_t j = (uint32_t)NCH + (uint32_t)(l - 2) * 2u * NCH + 2u * (uint32_t)i + (outl ? 0u : w);   // index of the use within the step
             const uint32_t b = outl ? 0u : w, d = Y.col_acc + 64u * b;
             const uint32_t n = nb[b] + (outl ? cb[0] - 1u : kL1b[b] + (uint32_t)(l - 2) * NCH + (uint32_t)i);      // the n-th use of buffer b
             const bool first = i == 0;                            // first use of the layer (the output layer's only one)
@@ -358,19 +371,26 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
             // warp, and only "every layer-1 chunk is stored" says that it has been drained; later layers follow this warp's own
             // use of the buffer and start on the first pair of k-blocks.
             const int kb_first = first ? (l == 2 ? NCH : (NCH >= 2 ? 2 : 1)) : 0;      // input k-blocks waited for before the first MMA
+            // The weight stages first: they were requested a whole use ago and have normally landed, but even a wait on a
+            // completed phase costs ~165 cycles - taken here, they overlap the drain of the accumulator's previous use instead of
+            // sitting behind it on the chain that paces the kernel (issue -> 1024 cycles of MMAs -> commit -> drain -> "empty"
+            // -> issue of the buffer's next use: 2450 cycles per F/O pair before this reordering, the pipe needs 2048).
+            uint32_t stage[SPU];
+#pragma unroll
+            for (int sg = 0; sg < SPU; ++sg) stage[sg] = first_g + (ws + (uint32_t)sg) % nst_g;
+            auto wait_weights = [&]() {
+#pragma unroll
+              for (int sg = 0; sg < SPU; ++sg) ptx::mbar_wait(misc + kBarWFull + 8u * stage[sg], ((ws + (uint32_t)sg) / nst_g) & 1u);
+              if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 4);
+            };
+            if constexpr (kWeightsFirst) wait_weights();
             for (int kb = 0; kb < kb_first; kb += 2) {
               if (kb + 1 < kb_first) ptx::mbar_wait2(misc + kBarActReady + 8u * (uint32_t)kb, misc + kBarActReady + 8u * (uint32_t)(kb + 1), par_in, hc);
               else ptx::mbar_wait(misc + kBarActReady + 8u * (uint32_t)kb, par_in, hc);
             }
             ptx::mbar_wait(misc + kBarAccEmpty + 8u * b, (n & 1u) ^ 1u, hc);        // the buffer's previous use has been drained
             if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 3);
-            uint32_t stage[SPU];
-#pragma unroll
-            for (int sg = 0; sg < SPU; ++sg) {
-              stage[sg] = first_g + (ws + (uint32_t)sg) % nst_g;
-              ptx::mbar_wait(misc + kBarWFull + 8u * stage[sg], ((ws + (uint32_t)sg) / nst_g) & 1u);
-            }
-            if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 4);
+            if constexpr (!kWeightsFirst) wait_weights();
             // the four k-steps of k-block kb: A from TMEM, or from smem for the tail of a Y activation; B = tile kb % 4 of stage kb / 4
             auto issue_kb = [&](int kb) {
               const uint64_t bt = ptx::umma_desc_sw128(base + Y.off_ring + stage[kb >> 2] * kStageBytes) + (uint64_t)((uint32_t)(kb & 3) * tile16);
