@@ -5,7 +5,8 @@ plans/s, HalfCheetah).
 Workload (config.workload): the per-GPU share of BASELINE.json configs[2] - 32*N concurrent synthetic root
 states x K=4096 paths x H=20, MLP 26->500->500->20 ReLU, cheetah cost, uniform shooting sampled on the
 device, bf16 fast mode; the K paths of every state are sharded over the N ranks (512*8/N ... K/N per rank)
-and each plan ends with one NCCL all-gather of 80-byte records + a min-loc kernel.  N=8 is configs[2] itself.
+and each plan ends with one exchange of 80-byte records (NVLink peer stores; NCCL all-gather + min-loc kernel as fallback).
+N=8 is configs[2] itself.
 A "step" is one batched plan.  `value` = transitions/s with inputs resident in HBM; `e2e` = the same
 through the host-buffer C-ABI call (pinned-host -> device copy of the states and device -> host read of the
 winning records inside the timed region).
@@ -37,8 +38,8 @@ K_PATHS, HORIZON, STATES_PER_GPU = 4096, 20, 32
 FLOP_PER_TRANSITION = 2 * (26 * 500 + 500 * 500 + 500 * 20)   # 546 000; padding not credited
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload, from the committed ncu --set full
 # capture (the kernel streams its 0.6 MB of weights from L2; states in, 80-byte records out)
-NCU_DRAM_BYTES_PER_LAUNCH = 696832
-NCU_TRAFFIC_SOURCE = "profiles/r1k_ncu_full_rollout_tmem.csv"
+NCU_DRAM_BYTES_PER_LAUNCH = 697600
+NCU_TRAFFIC_SOURCE = "profiles/r2zj_ncu_full_rollout_tmem.csv"
 
 
 def measured_peaks():
