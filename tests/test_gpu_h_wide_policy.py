@@ -128,3 +128,40 @@ def test_proposal_network_wider_than_256_is_rejected_in_fast_mode():
     with pytest.raises(RuntimeError, match="<= 256"):
         pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
     pl.close()
+
+
+def test_wide_proposal_network_device_handoff_and_class_switch_on_a_side_stream():
+    """bcmpc_set_policy_device with a 256-unit network: the hand-off (torch CUDA tensors, nn.Linear layout) that switches the
+    planner from a 128-unit to a 256-unit network re-packs the dynamics images on the CALLER's stream, behind other work,
+    and plans bit-identically to the host upload."""
+    import torch
+    from tests._util import make_pair
+    K, H = 512, 5
+    rng, norm, state, host, mpc = make_pair(71, (500, 500), K, H, precision="bf16", proposal="policy_gaussian")
+    wide = O.synthetic_policy(rng, hidden=(256, 200), norm=norm)
+    narrow = O.synthetic_policy(rng, hidden=(128, 96), norm=norm)
+    host.set_policy(*wide, clip=5.0)
+    want_wide = host.rollout_debug(state, seed=4)
+    host.set_policy(*narrow, clip=5.0)
+    want_narrow = host.rollout_debug(state, seed=4)
+    assert not np.array_equal(want_wide[1], want_narrow[1])
+    dev = torch.device("cuda:0")
+    side = torch.cuda.Stream()
+
+    def tensors(ws):
+        return [(torch.from_numpy(np.ascontiguousarray(w.T)).to(dev), torch.from_numpy(b).to(dev)) for w, b in ws]
+    tw, tn = tensors(wide[0]), tensors(narrow[0])
+    torch.cuda.synchronize()
+    _, _, _, pl, _ = make_pair(71, (500, 500), K, H, precision="bf16", proposal="policy_gaussian")      # starts with a 128-unit network
+    with torch.cuda.stream(side):
+        junk = torch.randn(4096, 4096, device=dev) @ torch.randn(4096, 4096, device=dev)
+        pl.set_policy_device(tw, wide[1], wide[2], wide[3], clip=5.0, layout="out_in", stream_ptr=side.cuda_stream)
+    got_wide = pl.rollout_debug(state, seed=4)
+    with torch.cuda.stream(side):
+        junk = junk @ junk
+        pl.set_policy_device(tn, narrow[1], narrow[2], narrow[3], clip=5.0, layout="out_in", stream_ptr=side.cuda_stream)
+    got_narrow = pl.rollout_debug(state, seed=4)
+    del junk
+    for a, b in zip(want_wide + want_narrow, got_wide + got_narrow):
+        assert np.array_equal(a, b)
+    pl.close(); host.close()
