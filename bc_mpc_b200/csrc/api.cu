@@ -308,7 +308,7 @@ int deep_prepare(bcmpc_handle* h, cudaStream_t st) {
   const int nch = (S + 127) / 128;
   h->deep_nch = nch;
   const size_t img = (size_t)dpx::kCluster * dpx::stages_per_step(nch, L) * dpx::kStageBytes;
-  const size_t vec = ((size_t)(L - 1) * 128 * nch + 32) * sizeof(float);
+  const size_t vec = (h->ln_on ? (size_t)(L - 1) * 2 * 128 * nch + 64 : (size_t)(L - 1) * 128 * nch + 32) * sizeof(float);   // LayerNorm: [u][c] per layer
   auto ensure = [&](void** ptr, size_t* cap, size_t need) -> cudaError_t {
     if (need <= *cap) return cudaSuccess;
     if (*ptr) cudaFree(*ptr);
@@ -322,10 +322,12 @@ int deep_prepare(bcmpc_handle* h, cudaStream_t st) {
   dpx::PackArgs a{};
   const MlpDesc& d = h->dyn.desc;
   for (int l = 0; l <= L; ++l) { a.W[l] = d.W[l]; a.b[l] = d.b[l]; a.ld[l] = d.out_pad[l]; }
+  if (h->ln_on)
+    for (int l = 0; l < L; ++l) { a.g[l] = d.ln_gamma[l]; a.be[l] = d.ln_beta[l]; }
   a.L = L; a.S = S; a.nch = nch;
   a.stream = reinterpret_cast<uint16_t*>(h->d_stream); a.vec = h->d_lnvec;
   CK(h, dpx::deep_pack(a, st));
-  h->launches++;
+  h->launches += h->ln_on ? 2 : 1;
   if (!h->trace_path.empty() && !h->d_trace) CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * dpx::kTraceWords));
   h->tm_ready = true;
   return BCMPC_OK;
@@ -333,7 +335,8 @@ int deep_prepare(bcmpc_handle* h, cudaStream_t st) {
 
 int launch_deep(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   if (!h->tm_ready) return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared: set the dynamics weights first");
-  if (h->ln_on) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) has no LayerNorm variant; use BCMPC_PREC_FP32_VERIFY");
+  if (h->ln_on && h->cfg.activation != BCMPC_ACT_RELU)
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) has a LayerNorm variant for ReLU dynamics only; use BCMPC_PREC_FP32_VERIFY");
   dpx::DeepArgs a;
   memset(&a, 0, sizeof a);
   a.t.p = p;
@@ -353,10 +356,11 @@ int launch_deep(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   }
   a.t.proposal = p.proposal; a.t.inj_kind = p.inj_kind;
   a.n_hidden = h->cfg.n_hidden; a.s_half = 64 * h->deep_nch;
+  if (h->ln_on) { a.t.ln_inv_n = 1.0f / (float)h->cfg.hidden_size; a.t.ln_eps = h->ln_eps; }
   const int64_t units = (int64_t)p.B * (p.tiles_per_state / 2);
   a.t.trace = h->d_trace;
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * dpx::kTraceWords, st));
-  CK(h, dpx::deep_launch(h->deep_nch, h->cfg.activation == BCMPC_ACT_TANH, a, h->deep_clusters, units, st, &h->deep_clusters));
+  CK(h, dpx::deep_launch(h->deep_nch, h->cfg.activation == BCMPC_ACT_TANH, h->ln_on, a, h->deep_clusters, units, st, &h->deep_clusters));
   CK(h, cudaGetLastError());
   h->launches++;
   if (h->d_trace) {
@@ -779,7 +783,8 @@ int set_layer_norm_common(bcmpc_handle* h, const float* const* gamma, const floa
                           cudaStream_t st) {
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
-  if (fast && h->deep && gamma) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) has no LayerNorm variant; use BCMPC_PREC_FP32_VERIFY");
+  if (fast && h->deep && gamma && h->cfg.activation != BCMPC_ACT_RELU)
+    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) has a LayerNorm variant for ReLU dynamics only; use BCMPC_PREC_FP32_VERIFY");
   if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
   if (gamma && n_hidden != h->cfg.n_hidden) return fail(h, BCMPC_ERR_INVALID, "n_hidden %d != %d", n_hidden, h->cfg.n_hidden);
   for (int l = 0; l < n_hidden && gamma; ++l)

@@ -11,10 +11,16 @@ namespace dpx {
 //   operand of one (output chunk, k-block): this CTA's half of the chunk's rows (q) x 64 k, K-major SWIZZLE_128B.
 //   Layer 1 carries its bias in the GEMM (input columns 26 / 27 are 1: rows 26 / 27 hold bf16(b), bf16(b - bf16(b))).
 // bias vector: [layer 2 (128 nch)] ... [layer L (128 nch)][output (32)]
+// LayerNorm (g / be = gamma / beta of hidden layer j at index j - 1, dynamics.py:68-69): the kernels of layers >= 2 and of the
+// output layer are packed as W' = diag(gamma) W, and the vector holds, per layer, the corrections of
+//   LN(r) W + b = rho (r W') - rho mu u + c :   [u (128 nch)][c (128 nch)] ... [u3 (32)][c3 (32)],
+// u = column sums of the bf16-rounded W' (what the tensor core multiplies), c = beta^T W + b.
 // ---------------------------------------------------------------------------------------------------------
 struct PackArgs {
   const float* W[BCMPC_MAX_LAYERS];
   const float* b[BCMPC_MAX_LAYERS];
+  const float* g[BCMPC_MAX_LAYERS];     // LayerNorm gamma / beta of hidden layer j at [j - 1], or all nullptr
+  const float* be[BCMPC_MAX_LAYERS];
   int ld[BCMPC_MAX_LAYERS];
   int L, S, nch;
   uint16_t* stream;
@@ -59,16 +65,17 @@ __global__ void pack_deep_kernel(PackArgs a) {
       int nl, kk;
       untile(off % kTileH, nl, kk);
       const int k = (p * nch + kb) * 64 + kk, n = gc * 64 + q * 32 + nl;
-      if (kb < nch && k < S && n < S) v = tmx::f32_to_bf16(a.W[l][(size_t)k * a.ld[l] + n]);
+      if (kb < nch && k < S && n < S) v = tmx::f32_to_bf16(a.g[0] ? a.g[l - 1][k] * a.W[l][(size_t)k * a.ld[l] + n] : a.W[l][(size_t)k * a.ld[l] + n]);
     } else {                                                              // ---- output layer: stage sg = k-blocks 4 sg .. 4 sg + 3 ----
       const int sg = s - (nstg - spu), t = (int)(off / kTileO), kb = 4 * sg + t;
       int nl, kk;
       untile(off % kTileO, nl, kk);
       const int k = (p * nch + kb) * 64 + kk, n = q * 16 + nl;
-      if (t < 4 && kb < nch && k < S && n < kD) v = tmx::f32_to_bf16(a.W[L][(size_t)k * a.ld[L] + n]);
+      if (t < 4 && kb < nch && k < S && n < kD) v = tmx::f32_to_bf16(a.g[0] ? a.g[L - 1][k] * a.W[L][(size_t)k * a.ld[L] + n] : a.W[L][(size_t)k * a.ld[L] + n]);
     }
     a.stream[e] = v;
   }
+  if (a.g[0]) return;                                   // LayerNorm: pack_deep_ln_kernel writes the vector
   const int sp2 = 2 * nch * 64, nvec = (L - 1) * sp2 + 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -77,8 +84,38 @@ __global__ void pack_deep_kernel(PackArgs a) {
     a.vec[i] = v;
   }
 }
+// LayerNorm correction vectors: one warp per (weight index l = 1..L, output column n)
+__global__ void pack_deep_ln_kernel(PackArgs a) {
+  const int L = a.L, S = a.S, sp2 = 2 * a.nch * 64;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int total = (L - 1) * sp2 + 32;
+  if (warp >= total) return;
+  const bool outl = warp >= (L - 1) * sp2;
+  const int l = outl ? L : 1 + warp / sp2, n = outl ? warp - (L - 1) * sp2 : warp % sp2;
+  const bool live = outl ? n < kD : n < S;
+  double u = 0.0, c = 0.0;
+  if (live)
+    for (int k = lane; k < S; k += 32) {
+      const float w = a.W[l][(size_t)k * a.ld[l] + n];
+      u += (double)tmx::bf16_to_f32(tmx::f32_to_bf16(a.g[l - 1][k] * w));
+      c += (double)a.be[l - 1][k] * (double)w;
+    }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { u += __shfl_xor_sync(0xffffffffu, u, off); c += __shfl_xor_sync(0xffffffffu, c, off); }
+  if (lane == 0) {
+    if (live) c += (double)a.b[l][n];
+    float* pu = outl ? a.vec + (size_t)(L - 1) * 2 * sp2 : a.vec + (size_t)(l - 1) * 2 * sp2;
+    float* pc = outl ? pu + 32 : pu + sp2;
+    pu[n] = live ? (float)u : 0.f;
+    pc[n] = live ? (float)c : 0.f;
+  }
+}
 inline cudaError_t deep_pack(const PackArgs& a, cudaStream_t st) {
   pack_deep_kernel<<<592, 256, 0, st>>>(a);
+  if (a.g[0]) {
+    const int warps = (a.L - 1) * 2 * a.nch * 64 + 32;
+    pack_deep_ln_kernel<<<(warps + 7) / 8, 256, 0, st>>>(a);
+  }
   return cudaGetLastError();
 }
 

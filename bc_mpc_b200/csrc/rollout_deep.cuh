@@ -88,10 +88,18 @@ enum : uint32_t {
   kBarRecvFull = 248,   // [2] the partner's partial is in my receive slot      (partner's st.async bytes + my arming arrive)
   kBarRecvEmpty = 264,  // [2] the partner has read ITS receive slot (I may overwrite it)   (partner's receiver warps -> my sender)
   kBarSig = 280,        // [2] issue token of issuer warp w: the other issuer has issued its use     (issuer -> issuer)
-  kOffTmemPtr = 304,
-  kOffRed = 320,        // argmin scratch (128 B)
+  // LayerNorm variant: per-row statistics of a hidden layer are spread over the two K-halves (and, for hidden 1, over both epilogue groups)
+  kBarStat = 296,       // [4] the PARTNER's partial sums of hidden layer l (index l - 1) are in my shared memory  (partner's st.async bytes + my arming arrive)
+  kBarStatLoc = 328,    // [2] [0] group 0's hidden-1 partial is in shared memory (-> group 1);  [1] group 1's last-hidden partial (-> group 0)
+  kOffTmemPtr = 344,
+  kOffRed = 352,        // argmin scratch (128 B)
   kMiscBytes = 512
 };
+// LayerNorm: (sum, sum of squares) per path.  Remote slots (the partner CTA's partials): [0], [1] hidden 1 of the partner's group 0 / 1,
+// [2 + (l & 1)] hidden layer l >= 2; then the local slots [group] (this CTA's partials for its other group).  Hidden 1 has slots
+// of its own because a group without a layer-1 chunk (NCH = 1: group 1) sends its (zero) partial of the NEXT step as soon as its
+// last O use is done - before the other group has read the last layer's statistics of THIS step.
+constexpr uint32_t kStatBytes = (4u + 2u) * 128u * 8u;
 #ifndef BCMPC_DEEP_STAGES
 #define BCMPC_DEEP_STAGES 7
 #endif
@@ -104,10 +112,10 @@ constexpr bool kWeightsFirst = BCMPC_DEEP_WEIGHTS_FIRST != 0;   // issuer: wait 
 struct Layout {
   int nch = 0, L = 0, nt = 0, ns = 0, spu = 0, nst = 0;
   int nst_r[2] = {0, 0}, first_r[2] = {0, 0};     // the ring is split in two: one sub-ring per MMA issuer
-  uint32_t off_a0 = 0, off_y = 0, off_recv = 0, off_vec = 0, vec_bytes = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
+  uint32_t off_a0 = 0, off_y = 0, off_recv = 0, off_vec = 0, vec_bytes = 0, off_stat = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
   uint32_t col_x = 0, col_y = 0, col_acc = 0;
 };
-constexpr Layout make_layout(int nch, int max_hidden) {
+constexpr Layout make_layout(int nch, int max_hidden, bool ln = false) {
   Layout Y;
   Y.nch = nch; Y.L = max_hidden;
   Y.nt = tmem_y_blocks(nch); Y.ns = nch - Y.nt; Y.spu = stages_per_use(nch);
@@ -117,7 +125,8 @@ constexpr Layout make_layout(int nch, int max_hidden) {
   Y.off_recv = Y.off_y + Y.ns * kBlockBytes;
   Y.off_ring = Y.off_recv + 2 * kRecvBytes;
   // [hidden biases of layers 2..L: own K-half, 64 nch floats each][output bias 32] after the ring (sized for max_hidden layers)
-  Y.vec_bytes = ((uint32_t)(max_hidden - 1) * 64u * nch + 32u) * 4u;
+  // (LayerNorm variant: correction vectors u, c instead of the bias - twice the floats - and the statistics slots)
+  Y.vec_bytes = ln ? ((uint32_t)(max_hidden - 1) * 2u * 64u * nch + 64u) * 4u + kStatBytes : ((uint32_t)(max_hidden - 1) * 64u * nch + 32u) * 4u;
   const uint32_t fixed = Y.off_ring + ((Y.vec_bytes + 1023u) / 1024u * 1024u) + kMiscBytes;
   Y.nst = (int)((tmx::kSmemLimit - fixed) / kStageBytes);
   if (Y.nst > kMaxStages) Y.nst = kMaxStages;
@@ -128,13 +137,14 @@ constexpr Layout make_layout(int nch, int max_hidden) {
 #endif
   Y.first_r[0] = 0; Y.first_r[1] = Y.nst_r[0];
   Y.off_vec = Y.off_ring + Y.nst * kStageBytes;
+  Y.off_stat = Y.off_vec + (ln ? ((uint32_t)(max_hidden - 1) * 2u * 64u * nch + 64u) * 4u : 0u);      // (8-byte aligned: a multiple of 256 bytes)
   Y.off_misc = Y.off_vec + (Y.vec_bytes + 1023u) / 1024u * 1024u;
   Y.smem_bytes = Y.off_misc + kMiscBytes;
   return Y;
 }
-template <int NCH>
+template <int NCH, bool LN = false>
 struct Lay {
-  static constexpr Layout value = make_layout(NCH, kMaxHidden);
+  static constexpr Layout value = make_layout(NCH, kMaxHidden, LN);
 };
 
 struct DeepArgs {
@@ -200,13 +210,19 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
 
 // TANH: hidden activation tanh (the reference builder's default, dynamics.py:60; tanh.approx.bf16x2 on the rounded pair, like
 // rollout_tmem_kernel's kVarTanh) instead of ReLU - the biases of layers >= 2 are explicit here anyway, layer 1's ride in the GEMM.
-template <int NCH, bool DBG, bool TANH>
+// LN: LayerNorm after every hidden activation (dynamics.py:68-69, FLAGS.LAYER_NORM - the reference's default): like
+// rollout_tmem_kernel the tensor cores multiply the UN-normalised ReLU outputs r by W' = diag(gamma) W and the owner's epilogue
+// applies  LN(r) W + b = rho (r W') - rho mu u + c  (u = column sums of the bf16 W', c = beta^T W + b; rho, mu per path).  A path's
+// hidden units are spread over the two K-halves, so every CTA keeps the partial (sum, sum of squares) of ITS units and the two
+// partner CTAs exchange them (8 bytes per path and layer, st.async) while the next layer's MMAs run.
+template <int NCH, bool DBG, bool TANH, bool LN>
 __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_constant__ DeepArgs da) {
+  static_assert(!(LN && TANH), "the LayerNorm variant of the cluster-split kernel is built for ReLU dynamics");
   auto act2 = [](float x, float y) -> uint32_t {
     if constexpr (TANH) return ptx::tanh_bf16x2(tmx::pack_bf16(x, y));
     else return tmx::pack_relu_bf16(x, y);
   };
-  constexpr Layout Y = Lay<NCH>::value;
+  constexpr Layout Y = Lay<NCH, LN>::value;
   constexpr int NT = Y.nt, SPU = Y.spu, NST = Y.nst;
   constexpr uint32_t kIdescH = ptx::umma_idesc_bf16(2 * kRows, 64), kIdescO = ptx::umma_idesc_bf16(2 * kRows, 32);
   static_assert(Y.nst_r[0] >= SPU && Y.nst_r[1] >= SPU, "weight ring too small");
@@ -253,9 +269,29 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
       ptx::mbar_init(misc + kBarRecvFull + 8u * i, 1);        // the receiver's arming arrive (+ the bytes of the partner's st.async)
       ptx::mbar_init(misc + kBarRecvEmpty + 8u * i, 4);       // one arrive per receiving warp
     }
+    if constexpr (LN) {
+      for (int i = 0; i < 4; ++i) ptx::mbar_init(misc + kBarStat + 8u * i, 1);
+      for (int i = 0; i < 2; ++i) ptx::mbar_init(misc + kBarStatLoc + 8u * i, 4);
+    }
     ptx::fence_mbar_init();
+    if constexpr (LN) {
+      // armed for the first step (nothing can arrive before the cluster barrier below): hidden 1 gets both groups' partials of the
+      // partner (2 x 1 KB), every later layer one group's; each consumer re-arms its barrier right after it has waited on it
+      if (n_it > 0) {
+        ptx::mbar_arrive_expect_tx(misc + kBarStat, 2048u);
+        for (int l = 2; l <= L; ++l) ptx::mbar_arrive_expect_tx(misc + kBarStat + 8u * (uint32_t)(l - 1), 1024u);
+      }
+    }
   }
-  {   // biases: own K-half of every hidden layer >= 2, then the output bias
+  if constexpr (LN) {   // per hidden layer >= 2: [u (own K-half)][c (own K-half)], then [u3 (32)][c3 (32)] of the output layer
+    float* s_vec = reinterpret_cast<float*>(smem + Y.off_vec);
+    const int sh = 64 * NCH;
+    for (int i = tid; i < (L - 1) * 2 * sh; i += kThreads) {
+      const int layer = i / (2 * sh), part = (i % (2 * sh)) / sh, jj = i % sh;
+      s_vec[i] = a.lnvec[(size_t)layer * (4 * sh) + (size_t)part * (2 * sh) + khalf * sh + jj];
+    }
+    for (int i = tid; i < 64; i += kThreads) s_vec[(L - 1) * 2 * sh + i] = a.lnvec[(size_t)(L - 1) * 4 * sh + i];
+  } else {   // biases: own K-half of every hidden layer >= 2, then the output bias
     float* s_vec = reinterpret_cast<float*>(smem + Y.off_vec);
     const int sh = 64 * NCH;
     for (int i = tid; i < (L - 1) * sh; i += kThreads) s_vec[i] = a.lnvec[(size_t)(i / sh) * (2 * sh) + khalf * sh + (i % sh)];
@@ -513,6 +549,38 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
       __syncwarp();
       if (lane == 0) arrive_leader(kBarActReady + 8u * kb);
     };
+    // ---- LayerNorm variant: per-row statistics ----
+    [[maybe_unused]] float ln_s1 = 0.f, ln_s2 = 0.f;            // this thread's partial (sum, sum of squares) of the layer being produced
+    [[maybe_unused]] float rho = 1.f, rmu = 0.f;                // 1 / sqrt(var + eps), rho * mean of the layer being consumed
+    [[maybe_unused]] float2* s_rem = reinterpret_cast<float2*>(smem + Y.off_stat);               // [slot (4)][row]: the partner's partials
+    [[maybe_unused]] float2* s_loc = reinterpret_cast<float2*>(smem + Y.off_stat) + 4 * 128;       // [group][row]: this CTA's partials
+    // two neighbouring units: ReLU, statistics of the fp32 values, bf16 pair
+    [[maybe_unused]] auto relu_stat2 = [&](float x, float y) -> uint32_t {
+      x = x < 0.f ? 0.f : x;
+      y = y < 0.f ? 0.f : y;
+      ln_s1 += x + y;
+      ln_s2 = fmaf(x, x, fmaf(y, y, ln_s2));
+      return tmx::pack_bf16(x, y);
+    };
+    // this thread's partial of hidden layer l -> the partner CTA's slot (8 bytes, reported to its barrier of layer l)
+    [[maybe_unused]] auto send_stats = [&](int l) {
+      const uint32_t dst = base_partner + Y.off_stat + (uint32_t)(((l == 1 ? g : 2 + (l & 1)) * 128 + row) * 8);
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dst), "r"(__float_as_uint(ln_s1)),
+                   "r"(__float_as_uint(ln_s2)), "r"(misc_partner + kBarStat + 8u * (uint32_t)(l - 1))
+                   : "memory");
+    };
+    // ... -> this CTA's slot [group], for the other epilogue group
+    [[maybe_unused]] auto publish_local = [&](uint32_t which) {
+      s_loc[g * 128 + row] = make_float2(ln_s1, ln_s2);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(misc + kBarStatLoc + 8u * which);      // (release: the slot writes of this warp are visible to the waiter)
+    };
+    [[maybe_unused]] auto set_row_stats = [&](float t1, float t2) {
+      const float mean = t1 * a.ln_inv_n;
+      const float var = fmaxf(t2 * a.ln_inv_n - mean * mean, 0.f);
+      rho = rsqrtf(var + a.ln_eps);
+      rmu = rho * mean;
+    };
     for (int it = 0; it < n_it; ++it) {      // ---- one work unit: this CTA's 128 paths of one root state, H steps ----
       const int unit = first_unit + it * unit_stride;
       const int b = unit / units_per_state, tile = (unit % units_per_state) * 2 + (int)qrow;
@@ -554,12 +622,27 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, c, 0);
           drain(v0, v1, true);
           if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, c, 1);
+          if constexpr (LN) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w0[i] = act2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+            for (int i = 0; i < 16; ++i) w0[i] = relu_stat2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w1[i] = act2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+            for (int i = 0; i < 16; ++i) w1[i] = relu_stat2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w0[i] = act2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w1[i] = act2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          }
           store_block(false, c, w0, w1);
           if (tr) BCMPC_DTRACE(a.trace, step, 1 + g, c, 4);
+        }
+        [[maybe_unused]] float own1 = 0.f, own2 = 0.f;            // group 1: its own partial of the layer whose statistics it needs next
+        if constexpr (LN) {
+          // hidden 1 is converted by BOTH groups: each sends its partial to the partner CTA; group 0's also goes to group 1
+          send_stats(1);
+          if (g == 0) publish_local(0);
+          else { own1 = ln_s1; own2 = ln_s2; }
+          ln_s1 = 0.f; ln_s2 = 0.f;
         }
         // the next step's randomness, drawn where group 0 has slack
         if (is_final && h + 1 < H) tmx::get_noise<DBG, false>(a, b, h + 1, kc, z);
@@ -610,7 +693,29 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
               }
               __syncwarp();
               if (tr) BCMPC_DTRACE(a.trace, step, 2, tuse, 1);
-              const float4* b4 = reinterpret_cast<const float4*>(bias_l + 64u * i);
+              [[maybe_unused]] const float4* b4 = reinterpret_cast<const float4*>(bias_l + 64u * i);
+              if constexpr (LN) {
+                if (i == 0) {
+                  // statistics of hidden layer l - 1, whose LayerNorm output this layer consumes: own partial + (hidden 1: group 0's) +
+                  // the partner CTA's.  The waits sit behind this use's drain, i.e. ~1000 cycles of MMAs after the partials were sent.
+                  // ((mine) + (theirs): the partner CTA adds the same two numbers the other way round - identical statistics)
+                  const int lp = l - 1;
+                  float m1 = own1, m2 = own2;
+                  if (lp == 1) {
+                    ptx::mbar_wait(misc + kBarStatLoc, step & 1u, hc);
+                    const float2 o = s_loc[row];
+                    m1 += o.x; m2 += o.y;
+                  }
+                  ptx::mbar_wait(misc + kBarStat + 8u * (uint32_t)(lp - 1), step & 1u, hc);
+                  if (warp == 8 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(misc + kBarStat + 8u * (uint32_t)(lp - 1), lp == 1 ? 2048u : 1024u);   // next step's
+                  __syncwarp();
+                  float2 th = s_rem[(lp == 1 ? 1 : 2 + (lp & 1)) * 128 + row];
+                  if (lp == 1) { const float2 r0 = s_rem[row]; th.x += r0.x; th.y += r0.y; }
+                  set_row_stats(m1 + th.x, m2 + th.y);
+                }
+              }
+              [[maybe_unused]] const float4* u4 = reinterpret_cast<const float4*>(s_vec + (l - 2) * 2 * 64 * NCH + 64u * i);
+              [[maybe_unused]] const float4* c4 = reinterpret_cast<const float4*>(s_vec + (l - 2) * 2 * 64 * NCH + 64 * NCH + 64u * i);
 #pragma unroll
               for (uint32_t hf = 0; hf < 2; ++hf) {
                 const uint32_t x = x0 + hf, slot = x & 1u, xph = (x >> 1) & 1u;
@@ -633,11 +738,21 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
 #pragma unroll
                   for (int j = 0; j < 8; ++j) r[j] = ld_shared_v4(src + (uint32_t)j * 2048u);    // all eight loads in flight before the first use
                 }
+                if constexpr (LN) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 bb = b4[8 * hf + j];
-                  w[2 * j] = act2(__uint_as_float(v[4 * j]) + r[j].x + bb.x, __uint_as_float(v[4 * j + 1]) + r[j].y + bb.y);
-                  w[2 * j + 1] = act2(__uint_as_float(v[4 * j + 2]) + r[j].z + bb.z, __uint_as_float(v[4 * j + 3]) + r[j].w + bb.w);
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 uu = u4[8 * hf + j], cc = c4[8 * hf + j];
+                    auto pre = [&](uint32_t acc, float part, float u, float c) { return fmaf(rho, __uint_as_float(acc) + part, fmaf(-rmu, u, c)); };
+                    w[2 * j] = relu_stat2(pre(v[4 * j], r[j].x, uu.x, cc.x), pre(v[4 * j + 1], r[j].y, uu.y, cc.y));
+                    w[2 * j + 1] = relu_stat2(pre(v[4 * j + 2], r[j].z, uu.z, cc.z), pre(v[4 * j + 3], r[j].w, uu.w, cc.w));
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 bb = b4[8 * hf + j];
+                    w[2 * j] = act2(__uint_as_float(v[4 * j]) + r[j].x + bb.x, __uint_as_float(v[4 * j + 1]) + r[j].y + bb.y);
+                    w[2 * j + 1] = act2(__uint_as_float(v[4 * j + 2]) + r[j].z + bb.z, __uint_as_float(v[4 * j + 3]) + r[j].w + bb.w);
+                  }
                 }
                 __syncwarp();                                                         // every lane's loads are in its registers (and used)
                 if (lane == 0) ptx::mbar_arrive_remote(misc_partner + kBarRecvEmpty + 8u * slot);   // my slot may be overwritten
@@ -645,6 +760,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
               if (tr) BCMPC_DTRACE(a.trace, step, 2, tuse, 3);
               store_block(to_y, i, w0, w1);
               if (tr) BCMPC_DTRACE(a.trace, step, 2, tuse, 4);
+              if constexpr (LN) {
+                if (i == (uint32_t)NCH - 1) {      // this CTA's units of hidden layer l are complete
+                  send_stats(l);
+                  if (l == L) publish_local(1);    // the output layer is finalised by group 0
+                  own1 = ln_s1; own2 = ln_s2;
+                  ln_s1 = 0.f; ln_s2 = 0.f;
+                }
+              }
             }
           }
         }
@@ -656,6 +779,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 0);
           drain(v, dummy, false);
           if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 1);
+          if constexpr (LN) {
+            // statistics of the last hidden layer: group 1's partial of this CTA + the partner CTA's.  Read BEFORE this CTA's output
+            // partial is sent: the partner starts its next step only after that message, and its next statistics may land in the same slot.
+            ptx::mbar_wait(misc + kBarStatLoc + 8u, step & 1u, hc);
+            ptx::mbar_wait(misc + kBarStat + 8u * (uint32_t)(L - 1), step & 1u, hc);
+            if (warp == 4 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(misc + kBarStat + 8u * (uint32_t)(L - 1), 1024u);   // next step's
+            __syncwarp();
+            const float2 mine = s_loc[128 + row], th = s_rem[(2 + (L & 1)) * 128 + row];
+            set_row_stats(mine.x + th.x, mine.y + th.y);
+          }
           // arm the receive barrier only now: the output accumulator is complete, so every hidden exchange of the step -
           // in particular the slot's previous one, which the OTHER group waited for - has been consumed
           if (warp == 4 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(misc + kBarRecvFull + 8u * slot, 5u * 2048u);   // 20 columns will arrive
@@ -669,15 +802,23 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           ptx::mbar_wait(misc + kBarRecvFull + 8u * slot, xph, hc);
           if (tr) BCMPC_DTRACE(a.trace, step, 1, tuse, 4);
           const uint32_t src = base + Y.off_recv + slot * kRecvBytes + (uint32_t)row * 16u;
-          const float* b3 = s_vec + (L - 1) * 64 * NCH;
+          const float* b3 = s_vec + (LN ? (L - 1) * 2 * 64 * NCH : (L - 1) * 64 * NCH);      // LN: [u3 (32)][c3 (32)]
           float y[kD];
 #pragma unroll
           for (int j = 0; j < kD / 4; ++j) {
             const float4 r = ld_shared_v4(src + (uint32_t)j * 2048u);
-            y[4 * j] = (__uint_as_float(v[4 * j]) + r.x) + b3[4 * j];
-            y[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + r.y) + b3[4 * j + 1];
-            y[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + r.z) + b3[4 * j + 2];
-            y[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + r.w) + b3[4 * j + 3];
+            if constexpr (LN) {
+              auto fin = [&](uint32_t acc, float part, int d) { return fmaf(rho, __uint_as_float(acc) + part, fmaf(-rmu, b3[d], b3[32 + d])); };
+              y[4 * j] = fin(v[4 * j], r.x, 4 * j);
+              y[4 * j + 1] = fin(v[4 * j + 1], r.y, 4 * j + 1);
+              y[4 * j + 2] = fin(v[4 * j + 2], r.z, 4 * j + 2);
+              y[4 * j + 3] = fin(v[4 * j + 3], r.w, 4 * j + 3);
+            } else {
+              y[4 * j] = (__uint_as_float(v[4 * j]) + r.x) + b3[4 * j];
+              y[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + r.y) + b3[4 * j + 1];
+              y[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + r.z) + b3[4 * j + 2];
+              y[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + r.w) + b3[4 * j + 3];
+            }
           }
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_remote(misc_partner + kBarRecvEmpty + 8u * slot);
@@ -744,10 +885,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------------------
-template <int NCH, bool DBG, bool TANH>
+template <int NCH, bool DBG, bool TANH, bool LN = false>
 inline cudaError_t deep_launch_t(const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
-  auto kern = rollout_deep_kernel<NCH, DBG, TANH>;
-  constexpr Layout Y = Lay<NCH>::value;
+  auto kern = rollout_deep_kernel<NCH, DBG, TANH, LN>;
+  constexpr Layout Y = Lay<NCH, LN>::value;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y.smem_bytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -773,24 +914,32 @@ cudaError_t deep_launch_prod(int nch, const DeepArgs& a, int max_clusters, int64
 cudaError_t deep_launch_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_tanh_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_tanh_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
-inline cudaError_t deep_launch(int nch, bool tanh_act, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+cudaError_t deep_launch_ln_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+cudaError_t deep_launch_ln_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+inline cudaError_t deep_launch(int nch, bool tanh_act, bool layer_norm, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+  if (layer_norm) {
+    if (tanh_act) return cudaErrorInvalidValue;
+    return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_ln_dbg(nch, a, max_clusters, units, st, clusters_out)
+                                               : deep_launch_ln_prod(nch, a, max_clusters, units, st, clusters_out);
+  }
   if (tanh_act)
     return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_tanh_dbg(nch, a, max_clusters, units, st, clusters_out)
                                                : deep_launch_tanh_prod(nch, a, max_clusters, units, st, clusters_out);
   return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_dbg(nch, a, max_clusters, units, st, clusters_out)
                                              : deep_launch_prod(nch, a, max_clusters, units, st, clusters_out);
 }
-#define BCMPC_DEEP_DEFINE(NAME, DBG, TANH)                                                                                        \
+#define BCMPC_DEEP_DEFINE(NAME, DBG, TANH) BCMPC_DEEP_DEFINE_LN(NAME, DBG, TANH, false)
+#define BCMPC_DEEP_DEFINE_LN(NAME, DBG, TANH, LN)                                                                                        \
   cudaError_t NAME(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {      \
     switch (nch) {                                                                                                          \
-      case 1: return deep_launch_t<1, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
-      case 2: return deep_launch_t<2, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
-      case 3: return deep_launch_t<3, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
-      case 4: return deep_launch_t<4, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
-      case 5: return deep_launch_t<5, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
-      case 6: return deep_launch_t<6, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
-      case 7: return deep_launch_t<7, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
-      case 8: return deep_launch_t<8, DBG, TANH>(a, max_clusters, units, st, clusters_out);                                 \
+      case 1: return deep_launch_t<1, DBG, TANH, LN>(a, max_clusters, units, st, clusters_out);                                 \
+      case 2: return deep_launch_t<2, DBG, TANH, LN>(a, max_clusters, units, st, clusters_out);                                 \
+      case 3: return deep_launch_t<3, DBG, TANH, LN>(a, max_clusters, units, st, clusters_out);                                 \
+      case 4: return deep_launch_t<4, DBG, TANH, LN>(a, max_clusters, units, st, clusters_out);                                 \
+      case 5: return deep_launch_t<5, DBG, TANH, LN>(a, max_clusters, units, st, clusters_out);                                 \
+      case 6: return deep_launch_t<6, DBG, TANH, LN>(a, max_clusters, units, st, clusters_out);                                 \
+      case 7: return deep_launch_t<7, DBG, TANH, LN>(a, max_clusters, units, st, clusters_out);                                 \
+      case 8: return deep_launch_t<8, DBG, TANH, LN>(a, max_clusters, units, st, clusters_out);                                 \
     }                                                                                                                       \
     return cudaErrorInvalidValue;                                                                                           \
   }

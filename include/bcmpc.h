@@ -121,8 +121,8 @@ int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const flo
  * (1e-12 in tf.contrib).  gamma == NULL switches LayerNorm off.  Call it after bcmpc_set_dynamics (new weights reset
  * it).  Both precision modes; with BCMPC_PREC_BF16_FAST: ReLU dynamics of two hidden layers (<= 510 units; also together
  * with a proposal network) and the tanh learned-reward model, where a reward head needs bcmpc_set_reward_layer_norm too
- * (all three LayerNorms or none); a plain tanh net with LayerNorm and the cluster-split kernel (n_hidden > 2 or
- * hidden_size > 510) fail with BCMPC_ERR_UNSUPPORTED there. */
+ * (all three LayerNorms or none), also on the cluster-split kernel (n_hidden > 2 or hidden_size > 510, ReLU); a plain tanh
+ * net with LayerNorm fails with BCMPC_ERR_UNSUPPORTED there. */
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps);
 /* ... with DEVICE pointers, enqueued on `stream` (see bcmpc_set_dynamics_device). */
 int bcmpc_set_layer_norm_device(bcmpc_handle* h, const float* const* d_gamma, const float* const* d_beta, int32_t n_hidden,

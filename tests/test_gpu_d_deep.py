@@ -152,9 +152,9 @@ def test_deep_rejects_what_it_does_not_implement():
     with pytest.raises(RuntimeError, match="uniform shooting"):
         Planner(20, 6, 3, 1024, "relu", num_paths=256, horizon=2, precision="bf16", proposal="policy_mix")
     rng, norm, weights, state = O.synthetic_problem(5, (600, 600))
-    pl = Planner(20, 6, 2, 600, "relu", num_paths=256, horizon=2, precision="bf16")
+    pl = Planner(20, 6, 2, 600, "tanh", num_paths=256, horizon=2, precision="bf16")
     pl.set_dynamics(weights)
-    with pytest.raises(RuntimeError, match="LayerNorm"):
+    with pytest.raises(RuntimeError, match="LayerNorm variant for ReLU"):
         pl.set_layer_norm([(np.ones(600, np.float32), np.zeros(600, np.float32))] * 2)
 
 
@@ -188,3 +188,72 @@ def test_deep_tanh_dynamics(hidden):
     pr.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
     assert np.abs(pr.rollout_debug(state, actions)[0] - so).max() > 1e-3
     pl.close(); pr.close()
+
+
+@pytest.mark.parametrize("hidden", [(1024, 1024, 1024), (600, 600), (300, 300, 300, 300), (100, 100, 100), (768, 768)])
+def test_deep_layer_norm_dynamics(hidden):
+    """FLAGS.LAYER_NORM (the reference's default, dynamics.py:68-69) with more than two hidden layers or more than 510 units:
+    the cluster-split kernel multiplies un-normalised ReLU outputs by diag(gamma) W and corrects in the owner's epilogue; a
+    path's statistics are summed over both K-halves (8 bytes per path and layer through distributed shared memory)."""
+    from bc_mpc_b200 import Planner
+    K, H, S = 1000, 5, hidden[0]
+    rng, norm, weights, state = O.synthetic_problem(47, hidden)
+    lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in hidden]
+    dyn = O.OracleDynamics(weights, norm, layer_norm=lns)
+    mpc = O.OracleMPC(dyn, H, K)
+    pl = Planner(20, 6, len(hidden), S, "relu", num_paths=K, horizon=H, precision="bf16")
+    pl.set_dynamics(weights)
+    pl.set_layer_norm(lns)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    actions = f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, actions, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, actions)
+    e = _norm_err(so, dbg["states"], norm)
+    print("LayerNorm", hidden, "one-step err", np.abs(e[1]).max(), "max err", np.abs(e).max())
+    assert np.abs(e[1]).max() < 0.15 and np.abs(e).max() < 1.0, (np.abs(e[1]).max(), np.abs(e).max())
+    assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
+    rec = pl.plan(state, inj=actions)[0]
+    assert rec["index"] == int(np.argmin(co)) and rec["cost"] == co[rec["index"]]
+    assert (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std() < 0.5
+    # production flavour == debug flavour, several work units per cluster, and determinism
+    prod = pl.plan(state, seed=11)[0]
+    again = pl.plan(state, inj=pl.sample_injection(11)[0])[0]
+    assert prod["index"] == again["index"] and prod["cost"] == again["cost"]
+    assert pl.plan(state, seed=11)[0]["cost"] == prod["cost"]
+    # switching LayerNorm off again gives the plain network back
+    pl.set_layer_norm(None)
+    plain = pl.rollout_debug(state, actions)[0]
+    ref_plain = O.OracleMPC(O.OracleDynamics(weights, norm), H, K).rollout(state, actions)[0]
+    assert np.abs(_norm_err(plain, ref_plain, norm)).max() < 1.0 and np.abs(plain - so).max() > 1e-3
+    pl.close()
+
+
+def test_deep_layer_norm_many_units_and_batched_states():
+    """More work units than clusters (barrier phases carry across units) and several root states: batched == one by one."""
+    from bc_mpc_b200 import Planner
+    hidden, K, H, B = (1024, 1024, 1024), 256 * 70, 3, 2
+    S = hidden[0]
+    rng, norm, weights, state = O.synthetic_problem(48, hidden)
+    lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in hidden]
+    pl = Planner(20, 6, 3, S, "relu", num_paths=K, horizon=H, max_states=B, precision="bf16")
+    pl.set_dynamics(weights)
+    pl.set_layer_norm(lns)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((B, 20))
+    both = pl.plan(states, seed=5)
+    # (the Philox counter includes the root-state index, so a single-state plan replays state 0 only)
+    one = pl.plan(states[:1], seed=5)
+    assert both["index"][0] == one["index"][0] and both["cost"][0] == one["cost"][0]
+    assert np.array_equal(pl.plan(states, seed=5)["cost"], both["cost"])
+    # the winner's cost replayed through the oracle on the drawn actions
+    inj = pl.sample_injection(5, B)
+    dyn = O.OracleDynamics(weights, norm, layer_norm=lns)
+    j = int(both["index"][1])
+    s = states[1:2].copy()
+    cost = 0.0
+    for h in range(H):
+        nxt = dyn.predict(s, inj[1, h, j:j + 1])
+        cost += float(O.cheetah_cost_fn(s, inj[1, h, j:j + 1], nxt)[0])
+        s = nxt
+    assert abs(cost - both["cost"][1]) < 0.05 * abs(cost) + 5.0, (cost, both["cost"][1])
+    pl.close()

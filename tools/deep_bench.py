@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--hidden", default="1024,1024,1024")
     ap.add_argument("--plans", type=int, default=5)
     ap.add_argument("--states", type=int, default=1)
+    ap.add_argument("--ln", action="store_true", help="LayerNorm after every hidden activation (FLAGS.LAYER_NORM)")
     args = ap.parse_args()
     from bc_mpc_b200 import Planner
     from oracle import mpc_oracle as O      # synthetic inputs only
@@ -26,6 +27,9 @@ def main():
     rng, norm, weights, state = O.synthetic_problem(5, hidden)
     pl = Planner(20, 6, len(hidden), hidden[0], "relu", num_paths=args.K, horizon=args.H, max_states=args.states, precision="bf16")
     pl.set_dynamics(weights)
+    if args.ln:
+        S = hidden[0]
+        pl.set_layer_norm([(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in hidden])
     pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
     states = norm["mean_obs"] + norm["std_obs"] * rng.standard_normal((args.states, 20))
     pl.enable_timing(True)

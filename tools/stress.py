@@ -16,7 +16,7 @@ t0, n, by_kind = time.time(), 0, {}
 while time.time() - t0 < budget:
     S = int(rng.choice([7, 64, 100, 128, 200, 256, 300, 384, 500, 510]))
     kind = str(rng.choice(["uniform", "policy_gaussian", "policy_mix", "bc_uniform", "ln", "ln+policy", "reward", "reward+ln+policy", "reward+policy",
-                           "tanh", "tanh+policy", "deep", "deep+tanh"]))
+                           "tanh", "tanh+policy", "deep", "deep+tanh", "deep+ln"]))
     rew, ln, deep = "reward" in kind, "ln" in kind, "deep" in kind
     act = "tanh" if (rew or "tanh" in kind) else "relu"
     if rew:
@@ -39,9 +39,9 @@ while time.time() - t0 < budget:
         pl = Planner(20, 6, len(hidden), S, act, num_paths=K, horizon=H, max_states=B, precision="bf16", proposal=prop, explore=0.3)
         pl.set_dynamics(weights)
         pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
-        lns = [(1.0 + 0.1 * prng.standard_normal(S).astype(np.float32), 0.1 * prng.standard_normal(S).astype(np.float32)) for _ in range(3)]
+        lns = [(1.0 + 0.1 * prng.standard_normal(S).astype(np.float32), 0.1 * prng.standard_normal(S).astype(np.float32)) for _ in range(max(3, len(hidden)))]
         if ln:
-            pl.set_layer_norm(lns[:2])
+            pl.set_layer_norm(lns[:len(hidden)])
         if rew:
             pl.set_reward_head(rweights, norm["mean_reward"], norm["std_reward"], 0.97, layer_norm=lns[2] if ln else None)
         if prop == "bc_uniform":
