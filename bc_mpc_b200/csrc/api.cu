@@ -335,8 +335,6 @@ int deep_prepare(bcmpc_handle* h, cudaStream_t st) {
 
 int launch_deep(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   if (!h->tm_ready) return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared: set the dynamics weights first");
-  if (h->ln_on && h->cfg.activation != BCMPC_ACT_RELU)
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) has a LayerNorm variant for ReLU dynamics only; use BCMPC_PREC_FP32_VERIFY");
   dpx::DeepArgs a;
   memset(&a, 0, sizeof a);
   a.t.p = p;
@@ -389,9 +387,10 @@ int tm_prepare(bcmpc_handle* h, cudaStream_t st) {
   if (P.nc < 1 || P.nc > 8) return fail(h, BCMPC_ERR_UNSUPPORTED, "hidden width %d does not fit the TMEM-resident kernel", S);
   h->tm_narrow = narrow_applies(h);
   h->tm_wide_ok = tmx::tm_width_supported(h->tm_cg, P.nc, tm_variant(h));
-  if (h->cfg.activation == BCMPC_ACT_TANH && !h->rew.set && h->ln_on) {
-    // tanh + LayerNorm exists for the learned-reward model only: its head may still follow (bcmpc_set_reward_head comes after
-    // bcmpc_set_layer_norm); a plan before that fails in launch_tm
+  if (h->cfg.activation == BCMPC_ACT_TANH && !h->rew.set && h->ln_on && !h->tm_wide_ok) {
+    // plain tanh + LayerNorm has no instantiation in this mode (single-CTA developer mode, or a 256-unit proposal network), but the
+    // learned-reward model might: its head may still follow (bcmpc_set_reward_head comes after bcmpc_set_layer_norm); a plan
+    // before that fails in launch_tm
     h->tm_ready = false;
     return BCMPC_OK;
   }
@@ -443,8 +442,8 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   if (h->deep) return launch_deep(h, p, st);
   if (!h->tm_ready) {
     if (h->cfg.activation == BCMPC_ACT_TANH && !h->rew.set && h->ln_on)
-      return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: a plain tanh NNDynamicsModel with LayerNorm has no tensor-core variant (ReLU + LayerNorm and the "
-                                            "tanh learned-reward model + LayerNorm do); use BCMPC_PREC_FP32_VERIFY");
+      return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: a plain tanh NNDynamicsModel with LayerNorm has no tensor-core variant in this mode (BCMPC_TC_CG=1, or "
+                                            "together with a proposal network of more than 128 units); use BCMPC_PREC_FP32_VERIFY");
     return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared: set the dynamics weights, and with a reward head either all three LayerNorms "
                                     "(bcmpc_set_layer_norm + bcmpc_set_reward_layer_norm) or none");
   }
@@ -783,8 +782,6 @@ int set_layer_norm_common(bcmpc_handle* h, const float* const* gamma, const floa
                           cudaStream_t st) {
   if (!h->dyn.set) return fail(h, BCMPC_ERR_STATE, "dynamics weights not set (bcmpc_set_dynamics) - set them before the LayerNorm parameters");
   const bool fast = h->cfg.precision == BCMPC_PREC_BF16_FAST;
-  if (fast && h->deep && gamma && h->cfg.activation != BCMPC_ACT_RELU)
-    return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) has a LayerNorm variant for ReLU dynamics only; use BCMPC_PREC_FP32_VERIFY");
   if (gamma && !beta) return fail(h, BCMPC_ERR_INVALID, "gamma and beta must be given together");
   if (gamma && n_hidden != h->cfg.n_hidden) return fail(h, BCMPC_ERR_INVALID, "n_hidden %d != %d", n_hidden, h->cfg.n_hidden);
   for (int l = 0; l < n_hidden && gamma; ++l)

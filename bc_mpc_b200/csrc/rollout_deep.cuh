@@ -217,7 +217,6 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
 // partner CTAs exchange them (8 bytes per path and layer, st.async) while the next layer's MMAs run.
 template <int NCH, bool DBG, bool TANH, bool LN>
 __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_constant__ DeepArgs da) {
-  static_assert(!(LN && TANH), "the LayerNorm variant of the cluster-split kernel is built for ReLU dynamics");
   auto act2 = [](float x, float y) -> uint32_t {
     if constexpr (TANH) return ptx::tanh_bf16x2(tmx::pack_bf16(x, y));
     else return tmx::pack_relu_bf16(x, y);
@@ -554,13 +553,22 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
     [[maybe_unused]] float rho = 1.f, rmu = 0.f;                // 1 / sqrt(var + eps), rho * mean of the layer being consumed
     [[maybe_unused]] float2* s_rem = reinterpret_cast<float2*>(smem + Y.off_stat);               // [slot (4)][row]: the partner's partials
     [[maybe_unused]] float2* s_loc = reinterpret_cast<float2*>(smem + Y.off_stat) + 4 * 128;       // [group][row]: this CTA's partials
-    // two neighbouring units: ReLU, statistics of the fp32 values, bf16 pair
+    // two neighbouring units: activation, statistics (ReLU: of the fp32 values; tanh: of the bf16-rounded values the tensor core
+    // will read, as in rollout_tmem_kernel), bf16 pair
     [[maybe_unused]] auto relu_stat2 = [&](float x, float y) -> uint32_t {
-      x = x < 0.f ? 0.f : x;
-      y = y < 0.f ? 0.f : y;
-      ln_s1 += x + y;
-      ln_s2 = fmaf(x, x, fmaf(y, y, ln_s2));
-      return tmx::pack_bf16(x, y);
+      if constexpr (TANH) {
+        const uint32_t t = ptx::tanh_bf16x2(tmx::pack_bf16(x, y));
+        const float lo = __uint_as_float(t << 16), hi = __uint_as_float(t & 0xFFFF0000u);
+        ln_s1 += lo + hi;
+        ln_s2 = fmaf(lo, lo, fmaf(hi, hi, ln_s2));
+        return t;
+      } else {
+        x = x < 0.f ? 0.f : x;
+        y = y < 0.f ? 0.f : y;
+        ln_s1 += x + y;
+        ln_s2 = fmaf(x, x, fmaf(y, y, ln_s2));
+        return tmx::pack_bf16(x, y);
+      }
     };
     // this thread's partial of hidden layer l -> the partner CTA's slot (8 bytes, reported to its barrier of layer l)
     [[maybe_unused]] auto send_stats = [&](int l) {
@@ -916,9 +924,13 @@ cudaError_t deep_launch_tanh_prod(int nch, const DeepArgs& a, int max_clusters, 
 cudaError_t deep_launch_tanh_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_ln_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_ln_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+cudaError_t deep_launch_ln_tanh_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+cudaError_t deep_launch_ln_tanh_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 inline cudaError_t deep_launch(int nch, bool tanh_act, bool layer_norm, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+  if (layer_norm && tanh_act)
+    return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_ln_tanh_dbg(nch, a, max_clusters, units, st, clusters_out)
+                                               : deep_launch_ln_tanh_prod(nch, a, max_clusters, units, st, clusters_out);
   if (layer_norm) {
-    if (tanh_act) return cudaErrorInvalidValue;
     return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_ln_dbg(nch, a, max_clusters, units, st, clusters_out)
                                                : deep_launch_ln_prod(nch, a, max_clusters, units, st, clusters_out);
   }

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
   constexpr bool POL = (VAR & kVarPolicy) != 0, LN = (VAR & kVarLayerNorm) != 0, REW = (VAR & kVarReward) != 0;
   constexpr bool BIAS = !LN && (REW || (VAR & kVarBias) != 0);   // biases of layers 2 / 3 added in the epilogues
   constexpr bool TANH = REW || (VAR & kVarTanh) != 0;            // hidden activation (the learned-reward model is tanh, dynamics.py:162)
-  static_assert(!(VAR & kVarTanh) || (BIAS && !REW), "the plain tanh variant uses explicit biases");
+  static_assert(!(VAR & kVarTanh) || ((BIAS || LN) && !REW), "the plain tanh variant uses explicit biases (or the LayerNorm correction vectors)");
   constexpr int NC2 = hidden2_chunks(NC, VAR);                // hidden-2 chunks (both heads of the learned-reward model)
   static_assert(NC <= kMaxChunks1 && NC2 <= kMaxChunks2, "unsupported kernel variant");
   static_assert(!(VAR & kVarPolWide) || (POL && CG == 2), "the wide proposal network exists for CTA pairs only");
@@ -883,7 +883,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
         };
         // two neighbouring units -> activation -> bf16 pair (+ statistics)
         auto act_pair = [&](float x, float y) -> uint32_t {
-          if constexpr (REW) {
+          if constexpr (TANH) {
             const uint32_t t = ptx::tanh_bf16x2(pack_bf16(x, y));
             const float lo = __uint_as_float(t << 16), hi = __uint_as_float(t & 0xFFFF0000u);
             ln_sum += lo + hi;
@@ -1164,7 +1164,7 @@ inline bool tm_width_supported(int cg, int nc, int var) {
     const int base = var & ~kVarPolWide;
     return cg == 2 && (base == 1 || base == 3 || base == 5 || base == 7 || base == (kVarPolicy | kVarBias | kVarTanh));
   }
-  if (var & kVarTanh) return cg == 2 && (var & ~kVarPolicy) == (kVarBias | kVarTanh);
+  if (var & kVarTanh) return cg == 2 && (var & ~(kVarPolicy | kVarLayerNorm)) == (kVarBias | kVarTanh);      // plain tanh net, with or without LayerNorm
   if (var & kVarBias) return var <= (kVarBias | kVarPolicy) && nc <= 4;
   if (cg == 2) return var >= 0 && var < 8;
   if (var == (kVarLayerNorm | kVarPolicy)) return nc <= 4 || nc == 8;
@@ -1210,6 +1210,7 @@ cudaError_t tm_launch_var(int cg, int nc, const TmArgs& a, dim3 grid, cudaStream
 BCMPC_TM_DECLARE_VARIANT(0) BCMPC_TM_DECLARE_VARIANT(1) BCMPC_TM_DECLARE_VARIANT(2) BCMPC_TM_DECLARE_VARIANT(3)
 BCMPC_TM_DECLARE_VARIANT(4) BCMPC_TM_DECLARE_VARIANT(5) BCMPC_TM_DECLARE_VARIANT(6) BCMPC_TM_DECLARE_VARIANT(7)
 BCMPC_TM_DECLARE_VARIANT(8) BCMPC_TM_DECLARE_VARIANT(9) BCMPC_TM_DECLARE_VARIANT(24) BCMPC_TM_DECLARE_VARIANT(25)
+BCMPC_TM_DECLARE_VARIANT(26) BCMPC_TM_DECLARE_VARIANT(27)
 BCMPC_TM_DECLARE_VARIANT(33) BCMPC_TM_DECLARE_VARIANT(35) BCMPC_TM_DECLARE_VARIANT(37) BCMPC_TM_DECLARE_VARIANT(39) BCMPC_TM_DECLARE_VARIANT(57)
 template <bool DBG>
 inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, dim3 grid, cudaStream_t st) {
@@ -1226,6 +1227,8 @@ inline cudaError_t tm_launch_flavour(int cg, int nc, int var, const TmArgs& a, d
     case 9: return tm_launch_var<9, DBG>(cg, nc, a, grid, st);   // ... + proposal network
     case 24: return tm_launch_var<24, DBG>(cg, nc, a, grid, st); // plain tanh dynamics (explicit biases)
     case 25: return tm_launch_var<25, DBG>(cg, nc, a, grid, st); // ... + proposal network
+    case 26: return tm_launch_var<26, DBG>(cg, nc, a, grid, st); // plain tanh dynamics with LayerNorm (the builder default activation + FLAGS.LAYER_NORM)
+    case 27: return tm_launch_var<27, DBG>(cg, nc, a, grid, st); // ... + proposal network
     // proposal networks of up to 256 units per hidden layer (kVarPolWide)
     case 33: return tm_launch_var<33, DBG>(cg, nc, a, grid, st); // ReLU dynamics
     case 35: return tm_launch_var<35, DBG>(cg, nc, a, grid, st); // LayerNorm dynamics

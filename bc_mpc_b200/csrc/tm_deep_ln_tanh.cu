@@ -1,0 +1,8 @@
+// Cluster-split tcgen05 rollout kernel, tanh dynamics with LayerNorm (the reference builder's default activation + FLAGS.LAYER_NORM), production flavour
+#include "rollout_deep.cuh"
+
+namespace bcmpc {
+namespace dpx {
+BCMPC_DEEP_DEFINE_LN(deep_launch_ln_tanh_prod, false, true, true)
+}  // namespace dpx
+}  // namespace bcmpc

@@ -119,10 +119,10 @@ int bcmpc_set_dynamics_device(bcmpc_handle* h, const float* const* dW, const flo
  * tf.contrib.layers.layer_norm AFTER the activation of every hidden layer - moments over the last axis, centre and
  * scale.  gamma[l], beta[l] are [hidden_size] for hidden layer l (n_hidden of them); eps is the variance epsilon
  * (1e-12 in tf.contrib).  gamma == NULL switches LayerNorm off.  Call it after bcmpc_set_dynamics (new weights reset
- * it).  Both precision modes; with BCMPC_PREC_BF16_FAST: ReLU dynamics of two hidden layers (<= 510 units; also together
- * with a proposal network) and the tanh learned-reward model, where a reward head needs bcmpc_set_reward_layer_norm too
- * (all three LayerNorms or none), also on the cluster-split kernel (n_hidden > 2 or hidden_size > 510, ReLU); a plain tanh
- * net with LayerNorm fails with BCMPC_ERR_UNSUPPORTED there. */
+ * it).  Both precision modes; with BCMPC_PREC_BF16_FAST: ReLU or tanh dynamics of two hidden layers (<= 510 units; also
+ * together with a proposal network of <= 128 units, ReLU: <= 256) and the tanh learned-reward model, where a reward head needs
+ * bcmpc_set_reward_layer_norm too (all three LayerNorms or none), and the cluster-split kernel (n_hidden > 2 or
+ * hidden_size > 510; ReLU or tanh). */
 int bcmpc_set_layer_norm(bcmpc_handle* h, const float* const* gamma, const float* const* beta, int32_t n_hidden, float eps);
 /* ... with DEVICE pointers, enqueued on `stream` (see bcmpc_set_dynamics_device). */
 int bcmpc_set_layer_norm_device(bcmpc_handle* h, const float* const* d_gamma, const float* const* d_beta, int32_t n_hidden,

@@ -152,10 +152,10 @@ def test_deep_rejects_what_it_does_not_implement():
     with pytest.raises(RuntimeError, match="uniform shooting"):
         Planner(20, 6, 3, 1024, "relu", num_paths=256, horizon=2, precision="bf16", proposal="policy_mix")
     rng, norm, weights, state = O.synthetic_problem(5, (600, 600))
-    pl = Planner(20, 6, 2, 600, "tanh", num_paths=256, horizon=2, precision="bf16")
+    pl = Planner(20, 6, 2, 600, "relu", num_paths=256, horizon=2, precision="bf16")
     pl.set_dynamics(weights)
-    with pytest.raises(RuntimeError, match="LayerNorm variant for ReLU"):
-        pl.set_layer_norm([(np.ones(600, np.float32), np.zeros(600, np.float32))] * 2)
+    with pytest.raises(RuntimeError, match="n_hidden"):
+        pl.set_layer_norm([(np.ones(600, np.float32), np.zeros(600, np.float32))] * 3)
 
 
 @pytest.mark.parametrize("hidden", [(1024, 1024, 1024), (600, 600), (300, 300, 300, 300)])
@@ -190,8 +190,9 @@ def test_deep_tanh_dynamics(hidden):
     pl.close(); pr.close()
 
 
+@pytest.mark.parametrize("activation", ["relu", "tanh"])
 @pytest.mark.parametrize("hidden", [(1024, 1024, 1024), (600, 600), (300, 300, 300, 300), (100, 100, 100), (768, 768)])
-def test_deep_layer_norm_dynamics(hidden):
+def test_deep_layer_norm_dynamics(hidden, activation):
     """FLAGS.LAYER_NORM (the reference's default, dynamics.py:68-69) with more than two hidden layers or more than 510 units:
     the cluster-split kernel multiplies un-normalised ReLU outputs by diag(gamma) W and corrects in the owner's epilogue; a
     path's statistics are summed over both K-halves (8 bytes per path and layer through distributed shared memory)."""
@@ -199,9 +200,9 @@ def test_deep_layer_norm_dynamics(hidden):
     K, H, S = 1000, 5, hidden[0]
     rng, norm, weights, state = O.synthetic_problem(47, hidden)
     lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in hidden]
-    dyn = O.OracleDynamics(weights, norm, layer_norm=lns)
+    dyn = O.OracleDynamics(weights, norm, activation=activation, layer_norm=lns)
     mpc = O.OracleMPC(dyn, H, K)
-    pl = Planner(20, 6, len(hidden), S, "relu", num_paths=K, horizon=H, precision="bf16")
+    pl = Planner(20, 6, len(hidden), S, activation, num_paths=K, horizon=H, precision="bf16")
     pl.set_dynamics(weights)
     pl.set_layer_norm(lns)
     pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
@@ -209,7 +210,7 @@ def test_deep_layer_norm_dynamics(hidden):
     act, dbg = mpc.get_action(state, actions, return_debug=True)
     so, ao, co = pl.rollout_debug(state, actions)
     e = _norm_err(so, dbg["states"], norm)
-    print("LayerNorm", hidden, "one-step err", np.abs(e[1]).max(), "max err", np.abs(e).max())
+    print("LayerNorm", hidden, activation, "one-step err", np.abs(e[1]).max(), "max err", np.abs(e).max())
     assert np.abs(e[1]).max() < 0.15 and np.abs(e).max() < 1.0, (np.abs(e[1]).max(), np.abs(e).max())
     assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
     rec = pl.plan(state, inj=actions)[0]
@@ -223,7 +224,7 @@ def test_deep_layer_norm_dynamics(hidden):
     # switching LayerNorm off again gives the plain network back
     pl.set_layer_norm(None)
     plain = pl.rollout_debug(state, actions)[0]
-    ref_plain = O.OracleMPC(O.OracleDynamics(weights, norm), H, K).rollout(state, actions)[0]
+    ref_plain = O.OracleMPC(O.OracleDynamics(weights, norm, activation=activation), H, K).rollout(state, actions)[0]
     assert np.abs(_norm_err(plain, ref_plain, norm)).max() < 1.0 and np.abs(plain - so).max() > 1e-3
     pl.close()
 

@@ -102,9 +102,21 @@ def test_plain_tanh_dynamics_fast_mode(S, proposal):
     prod = pl.plan(state, seed=11)[0]
     again = pl.plan(state, inj=pl.sample_injection(11)[0])[0]
     assert prod["index"] == again["index"] and prod["cost"] == again["cost"]
-    pl.set_layer_norm([(np.ones(S, np.float32), np.zeros(S, np.float32))] * 2)      # (accepted: a reward head may follow)
-    with pytest.raises(RuntimeError, match="plain tanh NNDynamicsModel with LayerNorm"):
-        pl.plan(state, seed=1)
+    # the same net with LayerNorm after every tanh (the builder default activation + FLAGS.LAYER_NORM): variants 26 / 27
+    lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in range(2)]
+    pl.set_layer_norm(lns)
+    mpc_ln = O.OracleMPC(O.OracleDynamics(weights, norm, activation="tanh", layer_norm=lns), H, K, proposal=proposal, policy=pol, explore=0.4)
+    act, dbg = mpc_ln.get_action(state, inj, return_debug=True)
+    so_ln, ao, co = pl.rollout_debug(state, inj)
+    e = _norm_err(so_ln, dbg["states"], norm)
+    assert np.abs(e[1]).max() < 0.15 and np.abs(e).max() < 1.0, (np.abs(e[1]).max(), np.abs(e).max())
+    assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98 and np.abs(so_ln - so).max() > 1e-3
+    rec = pl.plan(state, inj=inj)[0]
+    assert rec["index"] == int(np.argmin(co))
+    assert (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std() < 0.5
+    prod = pl.plan(state, seed=11)[0]
+    again = pl.plan(state, inj=pl.sample_injection(11)[0])[0]
+    assert prod["index"] == again["index"] and prod["cost"] == again["cost"]
 
 
 @pytest.mark.parametrize("S,proposal,ln", [(100, "uniform", False), (320, "policy_mix", False), (400, "uniform", True), (448, "policy_gaussian", True),

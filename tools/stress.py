@@ -16,7 +16,7 @@ t0, n, by_kind = time.time(), 0, {}
 while time.time() - t0 < budget:
     S = int(rng.choice([7, 64, 100, 128, 200, 256, 300, 384, 500, 510]))
     kind = str(rng.choice(["uniform", "policy_gaussian", "policy_mix", "bc_uniform", "ln", "ln+policy", "reward", "reward+ln+policy", "reward+policy",
-                           "tanh", "tanh+policy", "deep", "deep+tanh", "deep+ln"]))
+                           "tanh", "tanh+policy", "tanh+ln", "deep", "deep+tanh", "deep+ln", "deep+tanh+ln"]))
     rew, ln, deep = "reward" in kind, "ln" in kind, "deep" in kind
     act = "tanh" if (rew or "tanh" in kind) else "relu"
     if rew:
