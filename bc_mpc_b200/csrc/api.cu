@@ -333,6 +333,19 @@ int deep_prepare(bcmpc_handle* h, cudaStream_t st) {
   return BCMPC_OK;
 }
 
+// proposal-network arguments of the fast kernels (policy-guided shooting)
+int fill_policy_args(bcmpc_handle* h, tmx::TmArgs& a) {
+  const tmx::TmHostPlan& P = h->tmp;
+  if (!P.with_policy || !h->d_pol) return fail(h, BCMPC_ERR_STATE, "proposal network not set (bcmpc_set_policy)");
+  a.pol = h->d_pol; a.np1 = P.np1; a.np2 = P.np2;
+  a.has_filter = h->has_filter ? 1 : 0; a.clip = h->clip;
+  a.explore = (float)h->cfg.explore; a.one_minus_explore = (float)(1.0 - h->cfg.explore);
+  for (int d = 0; d < h->cfg.obs_dim; ++d) { a.filt_mean[d] = h->filt_mean[d]; a.filt_inv_std[d] = 1.0f / h->filt_std[d]; }
+  for (int j = 0; j < h->cfg.act_dim; ++j) a.pol_std[j] = h->pol_std[j];
+  a.polvec = h->d_polvec;
+  return BCMPC_OK;
+}
+
 int launch_deep(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
   if (!h->tm_ready) return fail(h, BCMPC_ERR_STATE, "bf16 fast path not prepared: set the dynamics weights first");
   dpx::DeepArgs a;
@@ -353,12 +366,19 @@ int launch_deep(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.t.span[j] = h->norm.span[j];
   }
   a.t.proposal = p.proposal; a.t.inj_kind = p.inj_kind;
+  a.t.proposal0 = p.proposal0; a.t.inj_kind0 = p.inj_kind0;
+  const bool pol = p.proposal != BCMPC_PROP_UNIFORM || p.proposal0 != BCMPC_PROP_UNIFORM;
+  if (pol) {
+    if (h->pol_wide) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel holds proposal networks of at most 128 units per hidden layer");
+    int rc = fill_policy_args(h, a.t);
+    if (rc) return rc;
+  }
   a.n_hidden = h->cfg.n_hidden; a.s_half = 64 * h->deep_nch;
   if (h->ln_on) { a.t.ln_inv_n = 1.0f / (float)h->cfg.hidden_size; a.t.ln_eps = h->ln_eps; }
   const int64_t units = (int64_t)p.B * (p.tiles_per_state / 2);
   a.t.trace = h->d_trace;
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * dpx::kTraceWords, st));
-  CK(h, dpx::deep_launch(h->deep_nch, h->cfg.activation == BCMPC_ACT_TANH, h->ln_on, a, h->deep_clusters, units, st, &h->deep_clusters));
+  CK(h, dpx::deep_launch(h->deep_nch, h->cfg.activation == BCMPC_ACT_TANH, h->ln_on, pol, a, h->deep_clusters, units, st, &h->deep_clusters));
   CK(h, cudaGetLastError());
   h->launches++;
   if (h->d_trace) {
@@ -485,15 +505,7 @@ int launch_tm(bcmpc_handle* h, const PlanArgs& p, cudaStream_t st) {
     a.lnvec = h->d_lnvec;
     a.ln_inv_n = 1.0f / (float)h->cfg.hidden_size; a.ln_eps = h->ln_eps;
   }
-  if (pol) {
-    if (!P.with_policy || !h->d_pol) return fail(h, BCMPC_ERR_STATE, "proposal network not set (bcmpc_set_policy)");
-    a.pol = h->d_pol; a.np1 = P.np1; a.np2 = P.np2;
-    a.has_filter = h->has_filter ? 1 : 0; a.clip = h->clip;
-    a.explore = (float)h->cfg.explore; a.one_minus_explore = (float)(1.0 - h->cfg.explore);
-    for (int d = 0; d < h->cfg.obs_dim; ++d) { a.filt_mean[d] = h->filt_mean[d]; a.filt_inv_std[d] = 1.0f / h->filt_std[d]; }
-    for (int j = 0; j < h->cfg.act_dim; ++j) a.pol_std[j] = h->pol_std[j];
-    a.polvec = h->d_polvec;
-  }
+  if (pol) { int rc = fill_policy_args(h, a); if (rc) return rc; }
   if (h->d_trace) CK(h, cudaMemsetAsync(h->d_trace, 0, sizeof(unsigned long long) * tmx::kTraceSteps * tmx::kTraceSlots, st));
   // tiles_per_state is even when tm_cg == 2 (run_plan pads it)
   if (h->tm_use_narrow) {
@@ -677,6 +689,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   h->deep = want_deep;
   if (h->cfg.total_paths <= 0) h->cfg.total_paths = c.path_offset + c.num_paths;
   if (const char* s = getenv("BCMPC_TC_CG")) h->tm_cg = atoi(s) == 2 ? 2 : 1;
+  if (h->deep) h->tm_cg = 2;          // the cluster-split kernel always works in CTA pairs (its proposal-network image is the pair geometry)
   if (const char* s = getenv("BCMPC_TC_TRACE")) {
 #ifdef BCMPC_TRACE
     h->trace_path = s;
@@ -971,6 +984,7 @@ int set_policy_common(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, c
     const char* force_wide = getenv("BCMPC_POL_WIDE");
     const bool wide = tmx::tm_policy_is_wide(sizes) || (force_wide && atoi(force_wide) == 1 && h->tm_cg == 2);
     if (wide && h->tm_cg != 2) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: proposal networks wider than 128 units need CTA pairs (BCMPC_TC_CG=2, the default)");
+    if (wide && h->deep) return fail(h, BCMPC_ERR_UNSUPPORTED, "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) holds proposal networks of at most 128 units per hidden layer");
     const int pvar = tmx::kVarPolicy | (wide ? tmx::kVarPolWide : 0);
     const tmx::Layout lay = tmx::make_layout(h->tm_cg, 1, pvar);
     const size_t img_total = (size_t)h->tm_cg * lay.pol_img_bytes;

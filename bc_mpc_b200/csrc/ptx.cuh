@@ -40,8 +40,12 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity, hint)) {
     if (clock64() - t0 > 6000000000LL) {
-      printf("bcmpc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
-             parity);
+      // (one line per warp, and a second of grace before the trap so that the other stuck warps of the kernel report as well:
+      // a deadlock is diagnosed from the SET of barriers being waited for)
+      if ((threadIdx.x & 31) == 0)
+        printf("bcmpc: mbarrier wait timed out (block %d warp %d bar offset 0x%x parity %u)\n", blockIdx.x, threadIdx.x >> 5, bar & 0xFFFFu, parity);
+      const long long t1 = clock64();
+      while (clock64() - t1 < 2000000000LL) __nanosleep(1000);
       __trap();
     }
   }

@@ -1,5 +1,6 @@
 // BF16 fast-mode rollout kernel for WIDE / DEEP dynamics nets: L >= 2 hidden layers of up to 1024 units (BASELINE.json
-// configs[4]: 26 -> 1024 -> 1024 -> 1024 -> 20, K = 2^20 paths x H = 30), uniform shooting, ReLU or tanh.
+// configs[4]: 26 -> 1024 -> 1024 -> 1024 -> 20, K = 2^20 paths x H = 30), ReLU or tanh, with or without LayerNorm; uniform
+// shooting at every width, policy-guided shooting (template flag POL) for ReLU nets of 129..640 units.
 //
 // Why a third kernel: the hidden activations of a 128-path tile at width 1024 are 256 KB in bf16 - all of TMEM - and a
 // layer needs its whole input alive until its last output chunk, i.e. input + output = 512 KB per 128 paths, more than
@@ -87,14 +88,27 @@ enum : uint32_t {
   kBarAccEmpty = 224,   // [2] accumulator drained                  (epilogue of both CTAs -> issuer)
   kBarRecvFull = 248,   // [2] the partner's partial is in my receive slot      (partner's st.async bytes + my arming arrive)
   kBarRecvEmpty = 264,  // [2] the partner has read ITS receive slot (I may overwrite it)   (partner's receiver warps -> my sender)
-  kBarSig = 280,        // [2] issue token of issuer warp w: the other issuer has issued its use     (issuer -> issuer)
+  //      280..295        (free)
   // LayerNorm variant: per-row statistics of a hidden layer are spread over the two K-halves (and, for hidden 1, over both epilogue groups)
   kBarStat = 296,       // [4] the PARTNER's partial sums of hidden layer l (index l - 1) are in my shared memory  (partner's st.async bytes + my arming arrive)
   kBarStatLoc = 328,    // [2] [0] group 0's hidden-1 partial is in shared memory (-> group 1);  [1] group 1's last-hidden partial (-> group 0)
-  kOffTmemPtr = 344,
-  kOffRed = 352,        // argmin scratch (128 B)
-  kMiscBytes = 512
+  // proposal network (policy-guided shooting), each once per step
+  kBarPolIn = 344,      // the policy input rows are in shared memory          (group 0 of both CTAs -> issuer)
+  kBarPdFull = 352,     // [4] policy accumulators: layer-1 chunks 0, 1, layer-2 chunks 0, 1   (issuer commit -> epilogue of both CTAs)
+  kBarAp1 = 384,        // [2] policy hidden-1 chunk j stored                  (group j of both CTAs -> issuer)
+  kBarAp2 = 400,        // [2] policy hidden-2 chunk j stored
+  kBarPolFull = 416,    // the action means are complete                       (issuer commit -> group 0 of both CTAs)
+  kOffTmemPtr = 424,
+  kOffRed = 432,        // argmin scratch (80 B)
+  // [2][2] issue tokens of issuer warp w: the other issuer has issued its use (issuer -> issuer).  Token k of a warp goes to barrier
+  // [w][k & 1]: a warp can be TWO tokens ahead of the other's waits (the first use of a layer is issued without a token and arrives
+  // before the wait that consumes the previous one has run), and two arrivals on one single-count barrier would skip a phase - the
+  // waiter then sits on a parity that never completes (seen as a hang under policy-guided shooting at 2 chunks per K-half).
+  kBarSig = 512,
+  kMiscBytes = 576
 };
+constexpr uint32_t kPolImgBytes = 6u * 4096u + 2u * 2048u;      // resident proposal network per CTA: [Wp1: 2 chunks][Wp2: 2 x 2][Wp3: 2 k-blocks] (tm_pack_policy, CTA-pair geometry)
+constexpr uint32_t kPolBytes = kPolImgBytes + tmx::kPolVecFloats * 4u;
 // LayerNorm: (sum, sum of squares) per path.  Remote slots (the partner CTA's partials): [0], [1] hidden 1 of the partner's group 0 / 1,
 // [2 + (l & 1)] hidden layer l >= 2; then the local slots [group] (this CTA's partials for its other group).  Hidden 1 has slots
 // of its own because a group without a layer-1 chunk (NCH = 1: group 1) sends its (zero) partial of the NEXT step as soon as its
@@ -112,10 +126,10 @@ constexpr bool kWeightsFirst = BCMPC_DEEP_WEIGHTS_FIRST != 0;   // issuer: wait 
 struct Layout {
   int nch = 0, L = 0, nt = 0, ns = 0, spu = 0, nst = 0;
   int nst_r[2] = {0, 0}, first_r[2] = {0, 0};     // the ring is split in two: one sub-ring per MMA issuer
-  uint32_t off_a0 = 0, off_y = 0, off_recv = 0, off_vec = 0, vec_bytes = 0, off_stat = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
+  uint32_t off_a0 = 0, off_y = 0, off_recv = 0, off_pol = 0, off_vec = 0, vec_bytes = 0, off_stat = 0, off_ring = 0, off_misc = 0, smem_bytes = 0;
   uint32_t col_x = 0, col_y = 0, col_acc = 0;
 };
-constexpr Layout make_layout(int nch, int max_hidden, bool ln = false) {
+constexpr Layout make_layout(int nch, int max_hidden, bool ln = false, bool pol = false) {
   Layout Y;
   Y.nch = nch; Y.L = max_hidden;
   Y.nt = tmem_y_blocks(nch); Y.ns = nch - Y.nt; Y.spu = stages_per_use(nch);
@@ -123,7 +137,8 @@ constexpr Layout make_layout(int nch, int max_hidden, bool ln = false) {
   Y.off_a0 = 0;
   Y.off_y = kA0Bytes;
   Y.off_recv = Y.off_y + Y.ns * kBlockBytes;
-  Y.off_ring = Y.off_recv + 2 * kRecvBytes;
+  Y.off_pol = Y.off_recv + 2 * kRecvBytes;                      // (1024-byte aligned: UMMA tiles)
+  Y.off_ring = Y.off_pol + (pol ? kPolBytes : 0u);
   // [hidden biases of layers 2..L: own K-half, 64 nch floats each][output bias 32] after the ring (sized for max_hidden layers)
   // (LayerNorm variant: correction vectors u, c instead of the bias - twice the floats - and the statistics slots)
   Y.vec_bytes = ln ? ((uint32_t)(max_hidden - 1) * 2u * 64u * nch + 64u) * 4u + kStatBytes : ((uint32_t)(max_hidden - 1) * 64u * nch + 32u) * 4u;
@@ -142,9 +157,9 @@ constexpr Layout make_layout(int nch, int max_hidden, bool ln = false) {
   Y.smem_bytes = Y.off_misc + kMiscBytes;
   return Y;
 }
-template <int NCH, bool LN = false>
+template <int NCH, bool LN = false, bool POL = false>
 struct Lay {
-  static constexpr Layout value = make_layout(NCH, kMaxHidden, LN);
+  static constexpr Layout value = make_layout(NCH, kMaxHidden, LN, POL);
 };
 
 struct DeepArgs {
@@ -169,7 +184,13 @@ inline bool deep_supported(const bcmpc_config& c, std::string* why) {
   if (c.obs_dim != kD || c.act_dim != kA) { *why = "bf16 fast path is specialised for obs_dim=20, act_dim=6 (HalfCheetah)"; return false; }
   if (c.n_hidden < 2 || c.n_hidden > kMaxHidden) { *why = "bf16 fast path (cluster-split kernel) supports 2..4 hidden layers"; return false; }
   if (c.hidden_size < 1 || c.hidden_size > 64 * 2 * kMaxNch) { *why = "bf16 fast path supports hidden_size <= 1024"; return false; }
-  if (c.proposal != BCMPC_PROP_UNIFORM || c.first_proposal != 0) { *why = "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) runs uniform shooting; policy-guided proposals run in BCMPC_PREC_FP32_VERIFY there"; return false; }
+  if (c.proposal != BCMPC_PROP_UNIFORM || c.first_proposal != 0) {
+    const int nch = (c.hidden_size + 127) / 128;
+    if (nch < 2 || nch > 5 || c.activation != BCMPC_ACT_RELU) {
+      *why = "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) runs policy-guided proposals for ReLU nets of 129..640 hidden units; other shapes run them in BCMPC_PREC_FP32_VERIFY";
+      return false;
+    }
+  }
   return true;
 }
 
@@ -215,13 +236,19 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
 // applies  LN(r) W + b = rho (r W') - rho mu u + c  (u = column sums of the bf16 W', c = beta^T W + b; rho, mu per path).  A path's
 // hidden units are spread over the two K-halves, so every CTA keeps the partial (sum, sum of squares) of ITS units and the two
 // partner CTAs exchange them (8 bytes per path and layer, st.async) while the next layer's MMAs run.
-template <int NCH, bool DBG, bool TANH, bool LN>
+// POL: policy-guided shooting (controllers.py:189-237 / the legacy BC planners) on nets of 2..5 chunks per K-half (hidden 129..640,
+// i.e. three- and four-layer nets of the reference's widths): the proposal phase of rollout_tmem_kernel at the top of every step -
+// observation filter -> two tanh layers (<= 128 units) -> action means -> noise mixing - with the proposal network resident in
+// every CTA (both K-half pairs compute the same actions from their bit-identical states), its accumulators in the two regular
+// buffers and its hidden activations in the (then dead) activation columns [0, 128).
+template <int NCH, bool DBG, bool TANH, bool LN, bool POL = false>
 __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_constant__ DeepArgs da) {
+  static_assert(!POL || (NCH >= 2 && 32 * NCH + 32 * tmem_y_blocks(NCH) >= 128), "the proposal network needs 128 activation columns in TMEM");
   auto act2 = [](float x, float y) -> uint32_t {
     if constexpr (TANH) return ptx::tanh_bf16x2(tmx::pack_bf16(x, y));
     else return tmx::pack_relu_bf16(x, y);
   };
-  constexpr Layout Y = Lay<NCH, LN>::value;
+  constexpr Layout Y = Lay<NCH, LN, POL>::value;
   constexpr int NT = Y.nt, SPU = Y.spu, NST = Y.nst;
   constexpr uint32_t kIdescH = ptx::umma_idesc_bf16(2 * kRows, 64), kIdescO = ptx::umma_idesc_bf16(2 * kRows, 32);
   static_assert(Y.nst_r[0] >= SPU && Y.nst_r[1] >= SPU, "weight ring too small");
@@ -262,8 +289,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
     for (int i = 0; i < kNumAcc; ++i) {
       ptx::mbar_init(misc + kBarAccFull + 8u * i, 1);
       ptx::mbar_init(misc + kBarAccEmpty + 8u * i, 8);
-      ptx::mbar_init(misc + kBarSig + 8u * i, 1);
     }
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(misc + kBarSig + 8u * i, 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(misc + kBarRecvFull + 8u * i, 1);        // the receiver's arming arrive (+ the bytes of the partner's st.async)
       ptx::mbar_init(misc + kBarRecvEmpty + 8u * i, 4);       // one arrive per receiving warp
@@ -271,6 +298,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
     if constexpr (LN) {
       for (int i = 0; i < 4; ++i) ptx::mbar_init(misc + kBarStat + 8u * i, 1);
       for (int i = 0; i < 2; ++i) ptx::mbar_init(misc + kBarStatLoc + 8u * i, 4);
+    }
+    if constexpr (POL) {
+      ptx::mbar_init(misc + kBarPolIn, 8);
+      for (int i = 0; i < 4; ++i) ptx::mbar_init(misc + kBarPdFull + 8u * i, 1);
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(misc + kBarAp1 + 8u * i, 8); ptx::mbar_init(misc + kBarAp2 + 8u * i, 8); }
+      ptx::mbar_init(misc + kBarPolFull, 1);
     }
     ptx::fence_mbar_init();
     if constexpr (LN) {
@@ -281,6 +314,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
         for (int l = 2; l <= L; ++l) ptx::mbar_arrive_expect_tx(misc + kBarStat + 8u * (uint32_t)(l - 1), 1024u);
       }
     }
+  }
+  if constexpr (POL) {  // resident proposal network: this CTA's row half of every tile, then the three bias vectors
+    const uint4* src = reinterpret_cast<const uint4*>(a.pol + (size_t)qrow * kPolImgBytes);
+    uint4* dst = reinterpret_cast<uint4*>(smem + Y.off_pol);
+    for (int i = tid; i < (int)(kPolImgBytes / 16u); i += kThreads) dst[i] = src[i];
+    float* s_pv = reinterpret_cast<float*>(smem + Y.off_pol + kPolImgBytes);
+    for (int i = tid; i < 2 * tmx::kPolMaxHidden + kMaxAct; i += kThreads) s_pv[i] = a.polvec[i];
+    ptx::fence_proxy_async_smem();      // the tensor cores read the tiles through the async proxy (after the cluster barrier below)
   }
   if constexpr (LN) {   // per hidden layer >= 2: [u (own K-half)][c (own K-half)], then [u3 (32)][c3 (32)] of the output layer
     float* s_vec = reinterpret_cast<float*>(smem + Y.off_vec);
@@ -347,13 +388,61 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
       // k-blocks of the Y activation out of shared memory, which buys the weight ring two more stages.
       const uint16_t pair_mask = (uint16_t)(3u << (2u * khalf));
       const uint64_t a0desc = ptx::umma_desc_sw128(base + Y.off_a0);
-      uint32_t ws = 0, lo = 0, ntok = 0;    // weight stages of this warp's sub-ring, layer outputs consumed, tokens received so far
+      uint32_t ws = 0, lo = 0, ntok = 0, nsent = 0;    // weight stages of this warp's sub-ring, layer outputs consumed, tokens received / given so far
       // uses of buffer 0 / 1 per step, and so far at the start of the step
       constexpr uint32_t kL1b[2] = {(NCH + 1) / 2, NCH / 2};
       const uint32_t cb[2] = {kL1b[0] + (uint32_t)(L - 1) * NCH + 1u, kL1b[1] + (uint32_t)(L - 1) * NCH};
       uint32_t nb[2] = {0, 0};
-      const uint32_t tok_mine = misc + kBarSig + 8u * w, tok_other = misc + kBarSig + 8u * (w ^ 1u);
+      auto tok_wait = [&]() {      // the next token for this warp
+        ptx::mbar_wait(misc + kBarSig + 8u * (2u * w + (ntok & 1u)), (ntok >> 1) & 1u, hc);
+        ++ntok;
+      };
+      auto tok_other = [&]() -> uint32_t { return misc + kBarSig + 8u * (2u * (w ^ 1u) + (nsent & 1u)); };      // where this warp's next token goes
       for (int h = 0; h < Htot; ++h, nb[0] += cb[0], nb[1] += cb[1]) {
+        if constexpr (POL) {
+          if (w == 0) {
+            // ---- proposal network (issuer 0): policy input (smem) -> tanh layer -> tanh layer -> action means, as in rollout_tmem_kernel.
+            // Accumulators: chunk j of both hidden layers in buffer j, the means in the first 32 columns of buffer 0; every one of them
+            // has been drained before the barrier that lets its buffer's next user start completes.
+            const uint64_t wpdesc = ptx::umma_desc_sw128(base + Y.off_pol);
+            const uint32_t np1 = (uint32_t)a.np1, np2 = (uint32_t)a.np2, par = (uint32_t)h & 1u;
+            ptx::mbar_wait(misc + kBarPolIn, par, hc);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              for (uint32_t j = 0; j < np1; ++j) {
+#pragma unroll
+                for (uint32_t ks = 0; ks < 2; ++ks)
+                  ptx::umma_ss<2>(Y.col_acc + 64u * j, a0desc + 2u * ks, wpdesc + (uint64_t)(j * (kTileH >> 4) + 2u * ks), kIdescH, ks);
+                umma_commit_pair(misc + kBarPdFull + 8u * j, pair_mask);
+              }
+            }
+            __syncwarp();
+            for (uint32_t j = 0; j < np1; ++j) ptx::mbar_wait(misc + kBarAp1 + 8u * j, par, hc);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              for (uint32_t j = 0; j < np2; ++j) {
+                for (uint32_t kb = 0; kb < np1; ++kb)
+#pragma unroll
+                  for (uint32_t ks = 0; ks < 4; ++ks)
+                    ptx::umma_ts<2>(Y.col_acc + 64u * j, kb * 32u + ks * 8u, wpdesc + (uint64_t)((2u + j * 2u + kb) * (kTileH >> 4) + 2u * ks), kIdescH,
+                                    (kb | ks) ? 1u : 0u);
+                umma_commit_pair(misc + kBarPdFull + 8u * (2u + j), pair_mask);
+              }
+            }
+            __syncwarp();
+            for (uint32_t j = 0; j < np2; ++j) ptx::mbar_wait(misc + kBarAp2 + 8u * j, par, hc);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              for (uint32_t kb = 0; kb < np2; ++kb)
+#pragma unroll
+                for (uint32_t ks = 0; ks < 4; ++ks)
+                  ptx::umma_ts<2>(Y.col_acc, 64u + kb * 32u + ks * 8u, wpdesc + (uint64_t)(6u * (kTileH >> 4) + kb * (kTileO >> 4) + 2u * ks), kIdescO,
+                                  (kb | ks) ? 1u : 0u);
+              umma_commit_pair(misc + kBarPolFull, pair_mask);
+            }
+            __syncwarp();
+          }
+        }
         // ---- layer 1 (issuer 0): own chunks, K = 32 (2 k-steps), A from smem ----
         if (w == 0) {
           ptx::mbar_wait(misc + kBarA0Ready, (uint32_t)h & 1u, hc);
@@ -442,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
             if (first) {
               // k-block pairs as the epilogues of the previous layer store them: both issuers run this concurrently (F0 and
               // O0, or the output layer alone), so most of the layer's first uses is done when its last input block lands
-              if (w == 0 && !after_own) { ptx::mbar_wait(tok_mine, ntok & 1u, hc); ++ntok; }      // (issuer 1's last O use is issued)
+              if (w == 0 && !after_own) tok_wait();      // (issuer 1's last O use is issued)
               if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 1);
               for (int kb = 0; kb < NCH; kb += 2) {
                 if (kb >= kb_first) {
@@ -458,17 +547,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
               }
               if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 5);
               if (ptx::elect_one()) {
-                if (!outl) ptx::mbar_arrive(tok_other);
+                if (!outl) ptx::mbar_arrive(tok_other());
 #pragma unroll
                 for (int sg = 0; sg < SPU; ++sg) umma_commit_pair(misc + kBarWEmpty + 8u * stage[sg], pair_mask);
                 umma_commit_pair(misc + kBarAccFull + 8u * b, pair_mask);
               }
               __syncwarp();
-              if (w == 1) { ptx::mbar_wait(tok_mine, ntok & 1u, hc); ++ntok; }      // (consume F0's token: the counts stay in step)
+              if (!outl) ++nsent;
+              if (w == 1) tok_wait();      // (consume F0's token: the counts stay in step)
             } else {
               // ---- the token: the other issuer has issued its use ----
-              ptx::mbar_wait(tok_mine, ntok & 1u, hc);
-              ++ntok;
+              tok_wait();
               ptx::tc_fence_after();
               if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 1);
               if (ptx::elect_one()) {
@@ -477,12 +566,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
 #pragma unroll
                   for (int t = 0; t < 4; ++t)
                     if (4 * sg + t < NCH) issue_kb(4 * sg + t);
-                  if (sg == SPU - 1) ptx::mbar_arrive(tok_other);       // all MMAs of the use are issued: the other issuer's turn
+                  if (sg == SPU - 1) ptx::mbar_arrive(tok_other());       // all MMAs of the use are issued: the other issuer's turn
                   umma_commit_pair(misc + kBarWEmpty + 8u * stage[sg], pair_mask);
                 }
                 umma_commit_pair(misc + kBarAccFull + 8u * b, pair_mask);
               }
               __syncwarp();
+              ++nsent;
             }
             ws += SPU;
             if (lane == 0) BCMPC_DTRACE(a.trace, (uint32_t)h, w ? 3 : 0, j, 2);
@@ -600,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
       if (is_final) {
 #pragma unroll
         for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)((DBG && p.per_row_states) ? kc : b) * kD + d];
-        tmx::get_noise<DBG, false>(a, b, 0, kc, z);
+        tmx::get_noise<DBG, POL>(a, b, 0, kc, z);
         if constexpr (DBG) {
           if (writer && p.states_out && valid)
             for (int d = 0; d < kD; ++d) p.states_out[(size_t)k * kD + d] = (double)s[d];
@@ -608,16 +698,82 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
       }
       for (int h = 0; h < H; ++h, ++step) {
         const uint32_t xbase = step * xs_step;                    // exchange index of the step's first exchanged chunk
+        [[maybe_unused]] float act[kA];
+        if constexpr (POL) {
+          // ---- the action of this step: proposal network on the tensor cores (ppo_bc_policy.py:60,70-72 / behavioral_cloning.py:21-26) ----
+          if (is_final) {
+            tmx::build_policy_input(a, a0_row, row, s);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) arrive_leader(kBarPolIn);
+          }
+          const float* s_pv = reinterpret_cast<const float*>(smem + Y.off_pol + kPolImgBytes);
+          // chunk g of a tanh layer: accumulator + bias -> tanh -> bf16 -> TMEM operand of the next policy layer
+          auto pol_chunk = [&](int layer) {
+            const uint32_t j = (uint32_t)g;
+            ptx::mbar_wait(misc + kBarPdFull + 8u * ((uint32_t)(layer - 1) * 2u + j), step & 1u, hc);
+            ptx::tc_fence_after();
+            uint32_t v0[32], v1[32], w0[16], w1[16];
+            ptx::tmem_ld32(lane_off + Y.col_acc + 64u * j, v0);
+            ptx::tmem_ld32(lane_off + Y.col_acc + 64u * j + 32u, v1);
+            ptx::tmem_ld_wait();
+            const float4* b4 = reinterpret_cast<const float4*>(s_pv + (layer == 1 ? 0 : tmx::kPolMaxHidden) + 64 * j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = b4[i];
+              w0[2 * i] = ptx::tanh_bf16x2(tmx::pack_bf16(__uint_as_float(v0[4 * i]) + bb.x, __uint_as_float(v0[4 * i + 1]) + bb.y));
+              w0[2 * i + 1] = ptx::tanh_bf16x2(tmx::pack_bf16(__uint_as_float(v0[4 * i + 2]) + bb.z, __uint_as_float(v0[4 * i + 3]) + bb.w));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = b4[8 + i];
+              w1[2 * i] = ptx::tanh_bf16x2(tmx::pack_bf16(__uint_as_float(v1[4 * i]) + bb.x, __uint_as_float(v1[4 * i + 1]) + bb.y));
+              w1[2 * i + 1] = ptx::tanh_bf16x2(tmx::pack_bf16(__uint_as_float(v1[4 * i + 2]) + bb.z, __uint_as_float(v1[4 * i + 3]) + bb.w));
+            }
+            const uint32_t dst = (layer == 1 ? 0u : 64u) + 32u * j;
+            ptx::tmem_st16(lane_off + dst, w0);
+            ptx::tmem_st16(lane_off + dst + 16u, w1);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_leader((layer == 1 ? kBarAp1 : kBarAp2) + 8u * j);
+          };
+          if (g < a.np1) pol_chunk(1);
+          if (g < a.np2) pol_chunk(2);
+          if (is_final) {
+            ptx::mbar_wait(misc + kBarPolFull, step & 1u, hc);
+            ptx::tc_fence_after();
+            uint32_t v[32];
+            ptx::tmem_ld32(lane_off + Y.col_acc, v);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+#pragma unroll
+            for (int j = 0; j < kA; ++j) {
+              const float mean = __uint_as_float(v[j]) + s_pv[2 * tmx::kPolMaxHidden + j];
+              const int prop = h == 0 ? a.proposal0 : a.proposal;           // (the tree-search planner switches the mode after its first stage)
+              if (prop == BCMPC_PROP_POLICY_GAUSSIAN) act[j] = fmaf(a.pol_std[j], z[j], mean);                        // distributions.py:80
+              else if (prop == BCMPC_PROP_POLICY_MIX) act[j] = fmaf(a.one_minus_explore, mean, a.explore * z[j]);   // controllers.py:208
+              else if (prop == BCMPC_PROP_POLICY_MEAN) act[j] = mean;                                                // controllers.py:429,433
+              else if (prop == BCMPC_PROP_UNIFORM) act[j] = z[j];                                                    // controllers.py:411 (random first stage)
+              else act[j] = mean + z[j];                                                                             // controllers.pyc (BC + U[-1,1))
+            }
+          }
+        } else {
+          if (is_final) {
+#pragma unroll
+            for (int j = 0; j < kA; ++j) act[j] = z[j];              // controllers.py:70: the sampled action itself
+          }
+        }
         if (is_final) {
           if (h == 0) {
 #pragma unroll
-            for (int j = 0; j < kA; ++j) act0[j] = z[j];
+            for (int j = 0; j < kA; ++j) act0[j] = act[j];
           }
           if constexpr (DBG) {
             if (writer && p.actions_out && valid)
-              for (int j = 0; j < kA; ++j) p.actions_out[((size_t)h * p.K + k) * kA + j] = (double)z[j];
+              for (int j = 0; j < kA; ++j) p.actions_out[((size_t)h * p.K + k) * kA + j] = (double)act[j];
           }
-          tmx::build_input(a, a0_row, row, s, z);                  // controllers.py:70: the sampled action itself
+          tmx::build_input(a, a0_row, row, s, act);
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) arrive_leader(kBarA0Ready);
@@ -653,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
           ln_s1 = 0.f; ln_s2 = 0.f;
         }
         // the next step's randomness, drawn where group 0 has slack
-        if (is_final && h + 1 < H) tmx::get_noise<DBG, false>(a, b, h + 1, kc, z);
+        if (is_final && h + 1 < H) tmx::get_noise<DBG, POL>(a, b, h + 1, kc, z);
         // ---- hidden layers 2..L ----
         for (int l = 2; l <= L; ++l) {
           const bool to_y = (l & 1) == 0;
@@ -893,10 +1049,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------------------
-template <int NCH, bool DBG, bool TANH, bool LN = false>
+template <int NCH, bool DBG, bool TANH, bool LN = false, bool POL = false>
 inline cudaError_t deep_launch_t(const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
-  auto kern = rollout_deep_kernel<NCH, DBG, TANH, LN>;
-  constexpr Layout Y = Lay<NCH, LN>::value;
+  auto kern = rollout_deep_kernel<NCH, DBG, TANH, LN, POL>;
+  constexpr Layout Y = Lay<NCH, LN, POL>::value;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y.smem_bytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -926,7 +1082,16 @@ cudaError_t deep_launch_ln_prod(int nch, const DeepArgs& a, int max_clusters, in
 cudaError_t deep_launch_ln_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_ln_tanh_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_ln_tanh_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
-inline cudaError_t deep_launch(int nch, bool tanh_act, bool layer_norm, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+// policy-guided shooting: ReLU nets of 2..5 chunks per K-half (hidden 129..640), with or without LayerNorm
+constexpr int kPolMinNch = 2, kPolMaxNch = 5;
+cudaError_t deep_launch_pol_prod(int nch, bool ln, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+cudaError_t deep_launch_pol_dbg(int nch, bool ln, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+inline cudaError_t deep_launch(int nch, bool tanh_act, bool layer_norm, bool policy, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
+  if (policy) {
+    if (tanh_act || nch < kPolMinNch || nch > kPolMaxNch) return cudaErrorInvalidValue;
+    return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_pol_dbg(nch, layer_norm, a, max_clusters, units, st, clusters_out)
+                                               : deep_launch_pol_prod(nch, layer_norm, a, max_clusters, units, st, clusters_out);
+  }
   if (layer_norm && tanh_act)
     return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_ln_tanh_dbg(nch, a, max_clusters, units, st, clusters_out)
                                                : deep_launch_ln_tanh_prod(nch, a, max_clusters, units, st, clusters_out);
@@ -940,6 +1105,20 @@ inline cudaError_t deep_launch(int nch, bool tanh_act, bool layer_norm, const De
   return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_dbg(nch, a, max_clusters, units, st, clusters_out)
                                              : deep_launch_prod(nch, a, max_clusters, units, st, clusters_out);
 }
+#define BCMPC_DEEP_DEFINE_POL(NAME, DBG)                                                                                        \
+  cudaError_t NAME(int nch, bool ln, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) { \
+    switch (nch) {                                                                                                              \
+      case 2: return ln ? deep_launch_t<2, DBG, false, true, true>(a, max_clusters, units, st, clusters_out)                    \
+                        : deep_launch_t<2, DBG, false, false, true>(a, max_clusters, units, st, clusters_out);                  \
+      case 3: return ln ? deep_launch_t<3, DBG, false, true, true>(a, max_clusters, units, st, clusters_out)                    \
+                        : deep_launch_t<3, DBG, false, false, true>(a, max_clusters, units, st, clusters_out);                  \
+      case 4: return ln ? deep_launch_t<4, DBG, false, true, true>(a, max_clusters, units, st, clusters_out)                    \
+                        : deep_launch_t<4, DBG, false, false, true>(a, max_clusters, units, st, clusters_out);                  \
+      case 5: return ln ? deep_launch_t<5, DBG, false, true, true>(a, max_clusters, units, st, clusters_out)                    \
+                        : deep_launch_t<5, DBG, false, false, true>(a, max_clusters, units, st, clusters_out);                  \
+    }                                                                                                                           \
+    return cudaErrorInvalidValue;                                                                                               \
+  }
 #define BCMPC_DEEP_DEFINE(NAME, DBG, TANH) BCMPC_DEEP_DEFINE_LN(NAME, DBG, TANH, false)
 #define BCMPC_DEEP_DEFINE_LN(NAME, DBG, TANH, LN)                                                                                        \
   cudaError_t NAME(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {      \

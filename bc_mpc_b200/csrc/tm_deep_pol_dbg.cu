@@ -1,0 +1,8 @@
+// Cluster-split tcgen05 rollout kernel with the proposal network (policy-guided shooting on nets of more than two hidden layers), debug flavour
+#include "rollout_deep.cuh"
+
+namespace bcmpc {
+namespace dpx {
+BCMPC_DEEP_DEFINE_POL(deep_launch_pol_dbg, true)
+}  // namespace dpx
+}  // namespace bcmpc

@@ -149,8 +149,6 @@ def test_deep_rejects_what_it_does_not_implement():
     from bc_mpc_b200 import Planner
     with pytest.raises(RuntimeError, match="2..4 hidden layers"):
         Planner(20, 6, 1, 1024, "relu", num_paths=256, horizon=2, precision="bf16")
-    with pytest.raises(RuntimeError, match="uniform shooting"):
-        Planner(20, 6, 3, 1024, "relu", num_paths=256, horizon=2, precision="bf16", proposal="policy_mix")
     rng, norm, weights, state = O.synthetic_problem(5, (600, 600))
     pl = Planner(20, 6, 2, 600, "relu", num_paths=256, horizon=2, precision="bf16")
     pl.set_dynamics(weights)
@@ -257,4 +255,63 @@ def test_deep_layer_norm_many_units_and_batched_states():
         cost += float(O.cheetah_cost_fn(s, inj[1, h, j:j + 1], nxt)[0])
         s = nxt
     assert abs(cost - both["cost"][1]) < 0.05 * abs(cost) + 5.0, (cost, both["cost"][1])
+    pl.close()
+
+
+@pytest.mark.parametrize("hidden,proposal,ln", [((500, 500, 500), "policy_gaussian", False), ((256, 256, 256), "policy_mix", True),
+                                                ((600, 600), "policy_mix", False), ((320, 320, 320, 320), "bc_uniform", False),
+                                                ((640, 640, 640), "policy_gaussian", True)])
+def test_deep_policy_guided(hidden, proposal, ln):
+    """Policy-guided shooting (controllers.py:189-237, the legacy BC planner) on nets with more than two hidden layers (or 511..640
+    units): the proposal phase of rollout_tmem_kernel at the top of every step of the cluster-split kernel, both K-half pairs
+    computing the same actions from their bit-identical states."""
+    from bc_mpc_b200 import Planner
+    K, H, S = 1000, 5, hidden[0]
+    rng, norm, weights, state = O.synthetic_problem(49, hidden)
+    lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in hidden] if ln else None
+    dyn = O.OracleDynamics(weights, norm, layer_norm=lns)
+    pl = Planner(20, 6, len(hidden), S, "relu", num_paths=K, horizon=H, precision="bf16", proposal=proposal, explore=0.4)
+    pl.set_dynamics(weights)
+    if ln:
+        pl.set_layer_norm(lns)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    pl.set_action_bounds(-np.ones(6), np.ones(6))
+    if proposal == "bc_uniform":
+        pw = O.glorot_mlp(rng, (20, 128, 64, 6), 0.05)
+        pol = O.OracleBC(pw)
+        pl.set_policy(pw)
+    else:
+        pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 96), norm=norm)
+        pol = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
+        pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+    mpc = O.OracleMPC(dyn, H, K, proposal=proposal, policy=pol, explore=0.4)
+    inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64) if proposal == "policy_gaussian" else f32_uniform(rng, (H, K, 6))
+    act, dbg = mpc.get_action(state, inj, return_debug=True)
+    so, ao, co = pl.rollout_debug(state, inj)
+    assert np.abs(ao[0] - dbg["actions"][0]).max() < 0.03           # first proposals: same state, bf16 policy net
+    e = _norm_err(so, dbg["states"], norm)
+    print("deep policy", hidden, proposal, ln, "one-step", np.abs(e[1]).max(), "max", np.abs(e).max())
+    assert np.abs(e[1]).max() < 0.15 and np.abs(e).max() < 1.0, (np.abs(e[1]).max(), np.abs(e).max())
+    assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
+    rec = pl.plan(state, inj=inj)[0]
+    assert rec["index"] == int(np.argmin(co)) and np.allclose(rec["action"][:6], ao[0, rec["index"]])
+    assert (dbg["costs"][rec["index"]] - dbg["costs"].min()) / dbg["costs"].std() < 0.5
+    prod = pl.plan(state, seed=11)[0]
+    again = pl.plan(state, inj=pl.sample_injection(11)[0])[0]
+    assert prod["index"] == again["index"] and prod["cost"] == again["cost"] and np.array_equal(prod["action"], again["action"])
+    assert not np.array_equal(pl.plan(state, seed=12)[0]["action"], prod["action"])
+    pl.close()
+
+
+def test_deep_policy_guided_shapes_outside_the_fast_mode():
+    from bc_mpc_b200 import Planner
+    with pytest.raises(RuntimeError, match="129..640"):
+        Planner(20, 6, 3, 1024, "relu", num_paths=256, horizon=2, precision="bf16", proposal="policy_mix")
+    with pytest.raises(RuntimeError, match="129..640"):
+        Planner(20, 6, 3, 400, "tanh", num_paths=256, horizon=2, precision="bf16", proposal="policy_mix")
+    rng, norm, weights, state = O.synthetic_problem(5, (400, 400, 400))
+    pl = Planner(20, 6, 3, 400, "relu", num_paths=256, horizon=2, precision="bf16", proposal="policy_mix")
+    pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(256, 64), norm=norm)
+    with pytest.raises(RuntimeError, match="at most 128 units"):
+        pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
     pl.close()

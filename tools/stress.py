@@ -16,7 +16,7 @@ t0, n, by_kind = time.time(), 0, {}
 while time.time() - t0 < budget:
     S = int(rng.choice([7, 64, 100, 128, 200, 256, 300, 384, 500, 510]))
     kind = str(rng.choice(["uniform", "policy_gaussian", "policy_mix", "bc_uniform", "ln", "ln+policy", "reward", "reward+ln+policy", "reward+policy",
-                           "tanh", "tanh+policy", "tanh+ln", "deep", "deep+tanh", "deep+ln", "deep+tanh+ln"]))
+                           "tanh", "tanh+policy", "tanh+ln", "deep", "deep+tanh", "deep+ln", "deep+tanh+ln", "deep+policy", "deep+ln+policy"]))
     rew, ln, deep = "reward" in kind, "ln" in kind, "deep" in kind
     act = "tanh" if (rew or "tanh" in kind) else "relu"
     if rew:
@@ -24,6 +24,8 @@ while time.time() - t0 < budget:
     hidden = (S, S)
     if deep:      # the cluster-split kernel: more than two hidden layers or more than 510 units
         S = int(rng.choice([100, 300, 600, 768, 1024]))
+        if "policy" in kind:      # the cluster-split kernel holds a proposal network next to 2..5 chunks per K-half
+            S = int(rng.choice([200, 300, 500, 600, 640]))
         hidden = (S,) * int(rng.integers(3 if S <= 510 else 2, 5))
     prop = kind if kind in ("policy_gaussian", "policy_mix", "bc_uniform") else ("policy_gaussian" if "policy" in kind else "uniform")
     K, H, B = int(rng.integers(1, 3000)), int(rng.integers(1, 12)), int(rng.integers(1, 5))
@@ -47,7 +49,7 @@ while time.time() - t0 < budget:
         if prop == "bc_uniform":
             pl.set_policy(O.glorot_mlp(prng, (20, 128, 64, 6), 0.05))
         elif prop != "uniform":
-            pw, logstd, rms_mean, rms_std = O.synthetic_policy(prng, hidden=(int(rng.choice([32, 64, 128, 129, 200, 256])), int(rng.choice([48, 128, 192, 256]))), norm=norm)
+            pw, logstd, rms_mean, rms_std = O.synthetic_policy(prng, hidden=((int(rng.choice([32, 64, 128])), int(rng.choice([48, 128]))) if deep else (int(rng.choice([32, 64, 128, 129, 200, 256])), int(rng.choice([48, 128, 192, 256])))), norm=norm)
             pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
     except RuntimeError as e:            # combinations without a kernel in this mode (e.g. BCMPC_TC_CG=1: reward heads + policy)
         if "weight ring" in str(e) or "hidden sizes" in str(e):
@@ -55,7 +57,11 @@ while time.time() - t0 < budget:
         raise
     states = norm["mean_obs"] + norm["std_obs"] * prng.standard_normal((B, 20))
     seed = int(rng.integers(1 << 40))
-    a, b = pl.plan(states, seed=seed), pl.plan(states, seed=seed)
+    try:
+        a, b = pl.plan(states, seed=seed), pl.plan(states, seed=seed)
+    except RuntimeError:
+        print("FAILED configuration:", dict(kind=kind, hidden=hidden, K=K, H=H, B=B, seed=seed), flush=True)
+        raise
     assert np.array_equal(a["index"], b["index"]) and np.array_equal(a["cost"], b["cost"], equal_nan=True), ("not deterministic", kind, S, K, H, B)
     if K * H * B <= 400000:
         c = pl.plan(states, inj=pl.sample_injection(seed, B))
