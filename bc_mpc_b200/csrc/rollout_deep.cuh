@@ -1,6 +1,6 @@
 // BF16 fast-mode rollout kernel for WIDE / DEEP dynamics nets: L >= 2 hidden layers of up to 1024 units (BASELINE.json
 // configs[4]: 26 -> 1024 -> 1024 -> 1024 -> 20, K = 2^20 paths x H = 30), ReLU or tanh, with or without LayerNorm; uniform
-// shooting at every width, policy-guided shooting (template flag POL) for ReLU nets of 129..640 units.
+// shooting at every width, policy-guided shooting (template flag POL) at 129..1024 units.
 //
 // Why a third kernel: the hidden activations of a 128-path tile at width 1024 are 256 KB in bf16 - all of TMEM - and a
 // layer needs its whole input alive until its last output chunk, i.e. input + output = 512 KB per 128 paths, more than
@@ -185,9 +185,8 @@ inline bool deep_supported(const bcmpc_config& c, std::string* why) {
   if (c.n_hidden < 2 || c.n_hidden > kMaxHidden) { *why = "bf16 fast path (cluster-split kernel) supports 2..4 hidden layers"; return false; }
   if (c.hidden_size < 1 || c.hidden_size > 64 * 2 * kMaxNch) { *why = "bf16 fast path supports hidden_size <= 1024"; return false; }
   if (c.proposal != BCMPC_PROP_UNIFORM || c.first_proposal != 0) {
-    const int nch = (c.hidden_size + 127) / 128;
-    if (nch < 2 || nch > 5 || c.activation != BCMPC_ACT_RELU) {
-      *why = "bf16 fast path: the cluster-split kernel (n_hidden > 2 or hidden_size > 510) runs policy-guided proposals for ReLU nets of 129..640 hidden units; other shapes run them in BCMPC_PREC_FP32_VERIFY";
+    if ((c.hidden_size + 127) / 128 < 2) {      // (the proposal network's activations take 128 TMEM columns of the dynamics net's)
+      *why = "bf16 fast path: the cluster-split kernel (n_hidden > 2) runs policy-guided proposals for nets of 129..1024 hidden units; narrower ones run them in BCMPC_PREC_FP32_VERIFY";
       return false;
     }
   }
@@ -236,8 +235,8 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
 // applies  LN(r) W + b = rho (r W') - rho mu u + c  (u = column sums of the bf16 W', c = beta^T W + b; rho, mu per path).  A path's
 // hidden units are spread over the two K-halves, so every CTA keeps the partial (sum, sum of squares) of ITS units and the two
 // partner CTAs exchange them (8 bytes per path and layer, st.async) while the next layer's MMAs run.
-// POL: policy-guided shooting (controllers.py:189-237 / the legacy BC planners) on nets of 2..5 chunks per K-half (hidden 129..640,
-// i.e. three- and four-layer nets of the reference's widths): the proposal phase of rollout_tmem_kernel at the top of every step -
+// POL: policy-guided shooting (controllers.py:189-237 / the legacy BC planners) on nets of 2..8 chunks per K-half (hidden 129..1024):
+// the proposal phase of rollout_tmem_kernel at the top of every step -
 // observation filter -> two tanh layers (<= 128 units) -> action means -> noise mixing - with the proposal network resident in
 // every CTA (both K-half pairs compute the same actions from their bit-identical states), its accumulators in the two regular
 // buffers and its hidden activations in the (then dead) activation columns [0, 128).
@@ -1082,13 +1081,18 @@ cudaError_t deep_launch_ln_prod(int nch, const DeepArgs& a, int max_clusters, in
 cudaError_t deep_launch_ln_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_ln_tanh_prod(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_ln_tanh_dbg(int nch, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
-// policy-guided shooting: ReLU nets of 2..5 chunks per K-half (hidden 129..640), with or without LayerNorm
-constexpr int kPolMinNch = 2, kPolMaxNch = 5;
+// policy-guided shooting: 2..8 chunks per K-half (hidden 129..1024), ReLU or tanh, with or without LayerNorm
+constexpr int kPolMinNch = 2, kPolMaxNch = kMaxNch;
 cudaError_t deep_launch_pol_prod(int nch, bool ln, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 cudaError_t deep_launch_pol_dbg(int nch, bool ln, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+cudaError_t deep_launch_pol_tanh_prod(int nch, bool ln, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
+cudaError_t deep_launch_pol_tanh_dbg(int nch, bool ln, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out);
 inline cudaError_t deep_launch(int nch, bool tanh_act, bool layer_norm, bool policy, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) {
   if (policy) {
-    if (tanh_act || nch < kPolMinNch || nch > kPolMaxNch) return cudaErrorInvalidValue;
+    if (nch < kPolMinNch || nch > kPolMaxNch) return cudaErrorInvalidValue;
+    if (tanh_act)
+      return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_pol_tanh_dbg(nch, layer_norm, a, max_clusters, units, st, clusters_out)
+                                                 : deep_launch_pol_tanh_prod(nch, layer_norm, a, max_clusters, units, st, clusters_out);
     return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_pol_dbg(nch, layer_norm, a, max_clusters, units, st, clusters_out)
                                                : deep_launch_pol_prod(nch, layer_norm, a, max_clusters, units, st, clusters_out);
   }
@@ -1105,17 +1109,23 @@ inline cudaError_t deep_launch(int nch, bool tanh_act, bool layer_norm, bool pol
   return tmx::tm_needs_debug_flavour(a.t.p) ? deep_launch_dbg(nch, a, max_clusters, units, st, clusters_out)
                                              : deep_launch_prod(nch, a, max_clusters, units, st, clusters_out);
 }
-#define BCMPC_DEEP_DEFINE_POL(NAME, DBG)                                                                                        \
+#define BCMPC_DEEP_DEFINE_POL(NAME, DBG, TANH)                                                                                  \
   cudaError_t NAME(int nch, bool ln, const DeepArgs& a, int max_clusters, int64_t units, cudaStream_t st, int* clusters_out) { \
     switch (nch) {                                                                                                              \
-      case 2: return ln ? deep_launch_t<2, DBG, false, true, true>(a, max_clusters, units, st, clusters_out)                    \
-                        : deep_launch_t<2, DBG, false, false, true>(a, max_clusters, units, st, clusters_out);                  \
-      case 3: return ln ? deep_launch_t<3, DBG, false, true, true>(a, max_clusters, units, st, clusters_out)                    \
-                        : deep_launch_t<3, DBG, false, false, true>(a, max_clusters, units, st, clusters_out);                  \
-      case 4: return ln ? deep_launch_t<4, DBG, false, true, true>(a, max_clusters, units, st, clusters_out)                    \
-                        : deep_launch_t<4, DBG, false, false, true>(a, max_clusters, units, st, clusters_out);                  \
-      case 5: return ln ? deep_launch_t<5, DBG, false, true, true>(a, max_clusters, units, st, clusters_out)                    \
-                        : deep_launch_t<5, DBG, false, false, true>(a, max_clusters, units, st, clusters_out);                  \
+      case 2: return ln ? deep_launch_t<2, DBG, TANH, true, true>(a, max_clusters, units, st, clusters_out)                     \
+                        : deep_launch_t<2, DBG, TANH, false, true>(a, max_clusters, units, st, clusters_out);                   \
+      case 3: return ln ? deep_launch_t<3, DBG, TANH, true, true>(a, max_clusters, units, st, clusters_out)                     \
+                        : deep_launch_t<3, DBG, TANH, false, true>(a, max_clusters, units, st, clusters_out);                   \
+      case 4: return ln ? deep_launch_t<4, DBG, TANH, true, true>(a, max_clusters, units, st, clusters_out)                     \
+                        : deep_launch_t<4, DBG, TANH, false, true>(a, max_clusters, units, st, clusters_out);                   \
+      case 5: return ln ? deep_launch_t<5, DBG, TANH, true, true>(a, max_clusters, units, st, clusters_out)                     \
+                        : deep_launch_t<5, DBG, TANH, false, true>(a, max_clusters, units, st, clusters_out);                   \
+      case 6: return ln ? deep_launch_t<6, DBG, TANH, true, true>(a, max_clusters, units, st, clusters_out)                     \
+                        : deep_launch_t<6, DBG, TANH, false, true>(a, max_clusters, units, st, clusters_out);                   \
+      case 7: return ln ? deep_launch_t<7, DBG, TANH, true, true>(a, max_clusters, units, st, clusters_out)                     \
+                        : deep_launch_t<7, DBG, TANH, false, true>(a, max_clusters, units, st, clusters_out);                   \
+      case 8: return ln ? deep_launch_t<8, DBG, TANH, true, true>(a, max_clusters, units, st, clusters_out)                     \
+                        : deep_launch_t<8, DBG, TANH, false, true>(a, max_clusters, units, st, clusters_out);                   \
     }                                                                                                                           \
     return cudaErrorInvalidValue;                                                                                               \
   }

@@ -3,6 +3,6 @@
 
 namespace bcmpc {
 namespace dpx {
-BCMPC_DEEP_DEFINE_POL(deep_launch_pol_prod, false)
+BCMPC_DEEP_DEFINE_POL(deep_launch_pol_prod, false, false)
 }  // namespace dpx
 }  // namespace bcmpc

@@ -3,6 +3,6 @@
 
 namespace bcmpc {
 namespace dpx {
-BCMPC_DEEP_DEFINE_POL(deep_launch_pol_dbg, true)
+BCMPC_DEEP_DEFINE_POL(deep_launch_pol_dbg, true, false)
 }  // namespace dpx
 }  // namespace bcmpc

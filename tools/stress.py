@@ -16,7 +16,7 @@ t0, n, by_kind = time.time(), 0, {}
 while time.time() - t0 < budget:
     S = int(rng.choice([7, 64, 100, 128, 200, 256, 300, 384, 500, 510]))
     kind = str(rng.choice(["uniform", "policy_gaussian", "policy_mix", "bc_uniform", "ln", "ln+policy", "reward", "reward+ln+policy", "reward+policy",
-                           "tanh", "tanh+policy", "tanh+ln", "deep", "deep+tanh", "deep+ln", "deep+tanh+ln", "deep+policy", "deep+ln+policy"]))
+                           "tanh", "tanh+policy", "tanh+ln", "deep", "deep+tanh", "deep+ln", "deep+tanh+ln", "deep+policy", "deep+ln+policy", "deep+tanh+policy", "deep+tanh+ln+policy"]))
     rew, ln, deep = "reward" in kind, "ln" in kind, "deep" in kind
     act = "tanh" if (rew or "tanh" in kind) else "relu"
     if rew:
@@ -24,8 +24,8 @@ while time.time() - t0 < budget:
     hidden = (S, S)
     if deep:      # the cluster-split kernel: more than two hidden layers or more than 510 units
         S = int(rng.choice([100, 300, 600, 768, 1024]))
-        if "policy" in kind:      # the cluster-split kernel holds a proposal network next to 2..5 chunks per K-half
-            S = int(rng.choice([200, 300, 500, 600, 640]))
+        if "policy" in kind:      # the proposal network's activations take 128 TMEM columns: at least 2 chunks per K-half
+            S = int(rng.choice([200, 300, 500, 600, 768, 1024]))
         hidden = (S,) * int(rng.integers(3 if S <= 510 else 2, 5))
     prop = kind if kind in ("policy_gaussian", "policy_mix", "bc_uniform") else ("policy_gaussian" if "policy" in kind else "uniform")
     K, H, B = int(rng.integers(1, 3000)), int(rng.integers(1, 12)), int(rng.integers(1, 5))
