@@ -258,6 +258,20 @@ def extras():
     out["configs4_K1048576_H30_3x1024_fp32_verify"] = {"plan_s": dt, "transitions_per_s": (1 << 20) * 30 / dt,
                                                        "tflops_fp32": (1 << 20) * 30 * 4288512 / dt / 1e12}
     pl.close()
+    # ... and the same net under policy-guided shooting (train_mpc_ppo.py --n_layers 3 --size 1024 with its MlpPolicy(hid_size=128)):
+    # the proposal network resident in every CTA of the cluster-split kernel
+    pl = Planner(20, 6, 3, 1024, "relu", num_paths=1 << 20, horizon=30, precision="bf16", proposal="policy_gaussian")
+    pl.set_dynamics(w4)
+    pl.set_normalization(norm4["mean_obs"], norm4["std_obs"], norm4["mean_action"], norm4["std_action"], norm4["mean_deltas"], norm4["std_deltas"])
+    pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+    pl.enable_timing(True)
+    dt = time_plans(pl, s4, 4)
+    k_ms = pl.last_kernel_ms()
+    flop4 = 4288512 + 2 * (20 * 128 + 128 * 128 + 128 * 6)
+    out["net_3x1024_policy_gaussian_K1048576_H30_bf16"] = {
+        "plan_ms": 1e3 * dt, "kernel_ms": k_ms, "transitions_per_s_e2e": (1 << 20) * 30 / dt,
+        "tflops_algorithmic": (1 << 20) * 30 * flop4 / (k_ms * 1e-3) / 1e12, "flop_per_transition": flop4}
+    pl.close()
     del w4
     # learned-reward planner (NNDynamicsRewardModel + MPCcontrollerReward: what run.sh launches), tanh, 26-500-{500-20, 500-1}
     B, K, H = 32, 4096, 20

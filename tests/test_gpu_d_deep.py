@@ -316,3 +316,45 @@ def test_deep_policy_guided_shapes_outside_the_fast_mode():
     with pytest.raises(RuntimeError, match="at most 128 units"):
         pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
     pl.close()
+
+
+@pytest.mark.parametrize("hidden,first_stage", [((300, 300, 300), "uniform"), ((768, 768), "policy_gaussian")])
+def test_deep_two_stage_proposals(hidden, first_stage):
+    """The tree-search planner's proposal schedule (controllers.py:409-416,429: a random or stochastic first-stage action, then
+    the deterministic policy) on the cluster-split kernel: first_proposal switches the mode after step 0."""
+    from bc_mpc_b200 import Planner
+    K, H, S = 777, 5, hidden[0]
+    rng, norm, weights, state = O.synthetic_problem(53, hidden)
+    dyn = O.OracleDynamics(weights, norm)
+    pw, logstd, rms_mean, rms_std = O.synthetic_policy(rng, hidden=(128, 128), norm=norm)
+    pol = O.OraclePolicy(pw, logstd, rms_mean, rms_std)
+    pl = Planner(20, 6, len(hidden), S, "relu", num_paths=K, horizon=H, precision="bf16", proposal="policy_mean", first_proposal=first_stage)
+    pl.set_dynamics(weights)
+    pl.set_normalization(norm["mean_obs"], norm["std_obs"], norm["mean_action"], norm["std_action"], norm["mean_deltas"], norm["std_deltas"])
+    pl.set_policy(pw, logstd, rms_mean, rms_std, clip=5.0)
+    z = f32_uniform(rng, (K, 6)) if first_stage == "uniform" else rng.standard_normal((K, 6)).astype(np.float32).astype(np.float64)
+    inj = np.zeros((H, K, 6))
+    inj[0] = z
+    # the oracle, step by step
+    s, states, acts = np.tile(state, [K, 1]), [], []
+    for h in range(H):
+        a = z if (h == 0 and first_stage == "uniform") else pol.act(s, stochastic=(h == 0), noise=z)[0]
+        states.append(s)
+        acts.append(np.asarray(a, np.float64))
+        s = dyn.predict(s, a)
+    states.append(s)
+    states, acts = np.asarray(states), np.asarray(acts)
+    costs = O.trajectory_cost_fn(O.cheetah_cost_fn, states[:-1], acts, states[1:])
+    so, ao, co = pl.rollout_debug(state, inj)
+    assert np.abs(ao[0] - acts[0]).max() < (1e-6 if first_stage == "uniform" else 0.03)
+    assert np.abs(ao[1:] - acts[1:]).max() < 0.05                        # deterministic policy on (almost) the same states
+    e = _norm_err(so, states, norm)
+    assert np.abs(e[1]).max() < 0.15 and np.abs(e).max() < 1.0, (np.abs(e[1]).max(), np.abs(e).max())
+    assert np.corrcoef(co, costs)[0, 1] > 0.98
+    rec = pl.plan(state, inj=inj)[0]
+    assert rec["index"] == int(np.argmin(co)) and np.allclose(rec["action"][:6], ao[0, rec["index"]])
+    assert (costs[rec["index"]] - costs.min()) / costs.std() < 0.5
+    prod = pl.plan(state, seed=3)[0]
+    again = pl.plan(state, inj=pl.sample_injection(3)[0])[0]
+    assert prod["index"] == again["index"] and prod["cost"] == again["cost"] and np.array_equal(prod["action"], again["action"])
+    pl.close()
