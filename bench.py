@@ -38,8 +38,8 @@ K_PATHS, HORIZON, STATES_PER_GPU = 4096, 20, 32
 FLOP_PER_TRANSITION = 2 * (26 * 500 + 500 * 500 + 500 * 20)   # 546 000; padding not credited
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload, from the committed ncu --set full
 # capture (the kernel streams its 0.6 MB of weights from L2; states in, 80-byte records out)
-NCU_DRAM_BYTES_PER_LAUNCH = 697600
-NCU_TRAFFIC_SOURCE = "profiles/r2zj_ncu_full_rollout_tmem.csv"
+NCU_DRAM_BYTES_PER_LAUNCH = 697088     # dram__bytes_read.sum + dram__bytes_write.sum of rollout_tmem_kernel, one ncu --set full capture
+NCU_TRAFFIC_SOURCE = "profiles/r2zm_ncu_full_rollout_tmem.csv"
 
 
 def measured_peaks():
