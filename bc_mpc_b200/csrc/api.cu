@@ -66,6 +66,7 @@ struct bcmpc_handle {
   size_t inj_cap = 0;
   int64_t launches = 0;
   bool timing = false;
+  bool inline_state_ok = true;      // BCMPC_INLINE_STATE=0: single plans copy their root state like batched ones
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   // tcgen05 path (rollout_tmem.cuh)
@@ -689,6 +690,7 @@ int bcmpc_create(const bcmpc_config* cfg, bcmpc_handle** out) {
   h->deep = want_deep;
   if (h->cfg.total_paths <= 0) h->cfg.total_paths = c.path_offset + c.num_paths;
   if (const char* s = getenv("BCMPC_TC_CG")) h->tm_cg = atoi(s) == 2 ? 2 : 1;
+  if (const char* s = getenv("BCMPC_INLINE_STATE")) h->inline_state_ok = atoi(s) != 0;
   if (h->deep) h->tm_cg = 2;          // the cluster-split kernel always works in CTA pairs (its proposal-network image is the pair geometry)
   if (const char* s = getenv("BCMPC_TC_TRACE")) {
 #ifdef BCMPC_TRACE
@@ -1043,7 +1045,7 @@ int bcmpc_set_policy_device(bcmpc_handle* h, int32_t n_layers, const int32_t* si
 
 namespace {
 int plan_device_common(bcmpc_handle* h, const double* d_states, int32_t n_states, const double* d_inj, uint64_t seed,
-                       const uint64_t* d_seed, bcmpc_record* d_out, void* stream) {
+                       const uint64_t* d_seed, bcmpc_record* d_out, void* stream, const double* host_state = nullptr) {
   if (!h || !d_states || !d_out) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_states < 1 || n_states > h->cfg.max_states) return fail(h, BCMPC_ERR_INVALID, "n_states %d out of [1,%d]", n_states, h->cfg.max_states);
   int rc = check_ready(h, needs_policy(h->cfg));
@@ -1054,6 +1056,10 @@ int plan_device_common(bcmpc_handle* h, const double* d_states, int32_t n_states
   p.seed_ptr = reinterpret_cast<const unsigned long long*>(d_seed);
   p.states = d_states;
   p.inj = d_inj;
+  if (host_state) {      // one root state in the launch arguments (bcmpc_plan with n_states == 1)
+    p.inline_state = 1;
+    for (int d = 0; d < h->cfg.obs_dim; ++d) p.state0[d] = host_state[d];
+  }
   return run_plan(h, p, d_out, stream ? (cudaStream_t)stream : h->stream, 0);
 }
 }  // namespace
@@ -1074,9 +1080,13 @@ int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const do
   if (!h || !states || !out) return fail(h, BCMPC_ERR_INVALID, "null argument");
   if (n_states < 1 || n_states > h->cfg.max_states) return fail(h, BCMPC_ERR_INVALID, "n_states %d out of [1,%d]", n_states, h->cfg.max_states);
   ON_DEVICE(h);
-  const size_t sbytes = sizeof(double) * n_states * h->cfg.obs_dim;
-  memcpy(h->h_states, states, sbytes);
-  CK(h, cudaMemcpyAsync(h->d_states, h->h_states, sbytes, cudaMemcpyHostToDevice, h->stream));
+  // a single plan carries its root state in the launch arguments (BCMPC_INLINE_STATE=0 restores the copy: A/B in tools/latency_breakdown.py)
+  const bool inline_state = n_states == 1 && h->inline_state_ok;
+  if (!inline_state) {
+    const size_t sbytes = sizeof(double) * n_states * h->cfg.obs_dim;
+    memcpy(h->h_states, states, sbytes);
+    CK(h, cudaMemcpyAsync(h->d_states, h->h_states, sbytes, cudaMemcpyHostToDevice, h->stream));
+  }
   const double* d_inj = nullptr;
   if (inj) {
     const size_t n = (size_t)n_states * h->cfg.horizon * h->cfg.num_paths * h->cfg.act_dim;
@@ -1092,7 +1102,8 @@ int bcmpc_plan(bcmpc_handle* h, const double* states, int32_t n_states, const do
   // up to 64 records (5 KB) are written by the min-loc kernel straight into mapped host memory: one copy call and one DMA
   // round trip less on the single-plan latency path (the reference plans one state per env step)
   const bool direct = n_states <= 64 && h->h_records_dev != nullptr;
-  int rc = bcmpc_plan_device(h, h->d_states, n_states, d_inj, seed, direct ? h->h_records_dev : h->d_records, h->stream);
+  int rc = plan_device_common(h, h->d_states, n_states, d_inj, seed, nullptr, direct ? h->h_records_dev : h->d_records, h->stream,
+                              inline_state ? states : nullptr);
   if (rc) return rc;
   if (!direct) CK(h, cudaMemcpyAsync(h->h_records, h->d_records, sizeof(bcmpc_record) * n_states, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));

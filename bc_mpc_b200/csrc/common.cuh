@@ -120,7 +120,16 @@ struct PlanArgs {
   // state's candidates itself instead of a second kernel launch
   bcmpc_record* out;          // [B] winning records, or nullptr = a separate reduce_candidates_kernel follows
   unsigned int* ticket;       // [B] finished-tile counters, zero between plans
+  // single host-buffer plans (the reference's env loop, utils.py:200): the root state rides in the launch arguments - no
+  // host-to-device copy ahead of the kernel (one API call and one DMA round trip less per plan; `states` is not read then)
+  int inline_state;
+  double state0[kMaxObs];
 };
+
+// entry d of the root state of row `row` ([B, D] states, or the state in the launch arguments)
+__device__ __forceinline__ double root_state(const PlanArgs& p, size_t row, int D, int d) {
+  return p.inline_state ? p.state0[d] : p.states[row * (size_t)D + d];
+}
 
 // the plan's Philox key: the launch argument, or the device scalar a captured graph reads at replay time
 __device__ __forceinline__ uint64_t plan_seed(const PlanArgs& p) { return p.seed_ptr ? (uint64_t)__ldg(p.seed_ptr) : p.seed; }

@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_deep_kernel(const __grid_
       float s[kD], z[kA], act0[kA], cost = 0.f;
       if (is_final) {
 #pragma unroll
-        for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)((DBG && p.per_row_states) ? kc : b) * kD + d];
+        for (int d = 0; d < kD; ++d) s[d] = (float)root_state(p, (size_t)((DBG && p.per_row_states) ? kc : b), kD, d);
         tmx::get_noise<DBG, POL>(a, b, 0, kc, z);
         if constexpr (DBG) {
           if (writer && p.states_out && valid)

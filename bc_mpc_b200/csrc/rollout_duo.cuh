@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_duo_kernel(const __grid_c
       const int kc = valid ? k : p.K - 1;
       float s[kD], z[kA], act0[kA], cost = 0.f;
 #pragma unroll
-      for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)((DBG && p.per_row_states) ? kc : b) * kD + d];
+      for (int d = 0; d < kD; ++d) s[d] = (float)root_state(p, (size_t)((DBG && p.per_row_states) ? kc : b), kD, d);
       get_noise<DBG, false>(a, b, 0, kc, z);
       if constexpr (DBG) {
         if (p.states_out && valid)

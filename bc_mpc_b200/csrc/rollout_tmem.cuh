@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tmem_kernel(const __grid_
     [[maybe_unused]] float disc = 1.f;          // gamma ** h of the learned-reward objective
     if (is_final) {
 #pragma unroll
-      for (int d = 0; d < kD; ++d) s[d] = (float)p.states[(size_t)((DBG && p.per_row_states) ? kc : b) * kD + d];
+      for (int d = 0; d < kD; ++d) s[d] = (float)root_state(p, (size_t)((DBG && p.per_row_states) ? kc : b), kD, d);
       get_noise<DBG, POL>(a, b, 0, kc, z);
       if constexpr (DBG) {
         if (p.states_out && valid)

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kVerifyThreads) rollout_verify_kernel(const __
   for (int i = tid; i < M * D; i += kVerifyThreads) {
     const int r = i / D, d = i % D;
     const int k = min(k_base + r, K - 1);
-    s_state[r * kMaxObs + d] = p.per_row_states ? p.states[(size_t)k * D + d] : p.states[(size_t)b * D + d];
+    s_state[r * kMaxObs + d] = root_state(p, (size_t)(p.per_row_states ? k : b), D, d);
     if (p.states_out && k_base + r < K) p.states_out[(size_t)(k_base + r) * D + d] = s_state[r * kMaxObs + d];
   }
   if (tid < M) s_cost[tid] = 0.0;
