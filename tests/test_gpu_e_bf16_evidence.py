@@ -98,6 +98,27 @@ def test_bf16_agreement_configs3_over_24_seeds():
     assert report["max_regret_in_cost_std"] < 0.5 and report["argmin_agreement"] >= 0.75
 
 
+def test_bf16_agreement_deep_policy_over_12_seeds():
+    """Policy-guided shooting on a three-layer net (train_mpc_ppo.py --n_layers 3 with its proposal network): the cluster-split
+    kernel's POL flavour against the float32 oracle, K = 2048 x H = 15, 3 x 500 dynamics, 12 seeded problems."""
+    K, H, n = 2048, 15, 12
+    rows = []
+    for seed in range(n):
+        rng, norm, state, pl, mpc = make_pair(300 + seed, (500, 500, 500), K, H, precision="bf16", proposal="policy_gaussian")
+        inj = rng.standard_normal((H, K, 6)).astype(np.float32).astype(np.float64)
+        rows.append(_agreement(pl, mpc, [state], [inj], norm))
+        pl.close()
+    report = {"config": "policy_gaussian proposals, K=2048 x H=15, MLP 26-500-500-500-20 (cluster-split kernel, POL), policy 20-128-128-6", "seeds": n,
+              "argmin_agreement": float(np.mean([r["argmin_agreement"] for r in rows])),
+              "max_regret_in_cost_std": max(r["max_regret_in_cost_std"] for r in rows),
+              "mean_regret_in_cost_std": float(np.mean([r["mean_regret_in_cost_std"] for r in rows])),
+              "worst_state_err_in_delta_std": max(r["worst_state_err_in_delta_std"] for r in rows),
+              "min_cost_correlation": min(r["min_cost_correlation"] for r in rows),
+              "min_runner_up_margin_in_cost_std": min(r["min_runner_up_margin_in_cost_std"] for r in rows)}
+    _dump("r2_bf16_agreement_deep_policy.json", report)
+    assert report["max_regret_in_cost_std"] < 0.5 and report["argmin_agreement"] >= 0.75
+
+
 def test_fp32_strict_per_step_error_report():
     """The fp32 verification mode against the oracle with NO relaxation: per BASELINE config and seed, the worst
     entry-relative error |got - ref| / |ref| (i) of one predict step fed the oracle's own trajectory state, at EVERY step,
