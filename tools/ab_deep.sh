@@ -1,6 +1,6 @@
 #!/bin/bash
 # Same-box A/B of compile-time variants of the cluster-split kernel: builds bc_mpc_b200/_ab/lib_<name>.so for every
-# "name:flags" argument from the objects of the regular build (only the tm_deep*.cu translation units are recompiled).
+# "name:flags" argument from the objects of the regular build (only the tm_deep*.cu translation units - all of them - are recompiled).
 #   tools/ab_deep.sh base: fp32x:-DBCMPC_DEEP_FP32_EXCHANGE st7:-DBCMPC_DEEP_STAGES=7
 # then, on the GPU box:  for l in bc_mpc_b200/_ab/lib_*.so; do BCMPC_LIB=$l python tools/deep_bench.py; done
 set -e
@@ -9,7 +9,7 @@ mkdir -p _ab
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"; [ "$flags" = "$spec" ] && flags=""
   dir=_ab/obj_$name; mkdir -p $dir
-  for f in tm_deep tm_deep_dbg tm_deep_tanh tm_deep_tanh_dbg; do
+  for f in $(ls csrc/tm_deep*.cu | xargs -n1 basename | sed 's/\.cu$//'); do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC $flags -c -o $dir/$f.o csrc/$f.cu &
   done
   wait
