@@ -258,13 +258,13 @@ def test_deep_layer_norm_many_units_and_batched_states():
     pl.close()
 
 
-@pytest.mark.parametrize("hidden,proposal,ln,act", [((500, 500, 500), "policy_gaussian", False, "relu"), ((256, 256, 256), "policy_mix", True, "relu"),
+@pytest.mark.parametrize("hidden,proposal,ln,activation", [((500, 500, 500), "policy_gaussian", False, "relu"), ((256, 256, 256), "policy_mix", True, "relu"),
                                                     ((600, 600), "policy_mix", False, "relu"), ((320, 320, 320, 320), "bc_uniform", False, "relu"),
                                                     ((640, 640, 640), "policy_gaussian", True, "relu"), ((200, 200, 200), "policy_gaussian", False, "relu"),
                                                     ((1024, 1024, 1024), "policy_gaussian", False, "relu"), ((1024, 1024, 1024), "policy_mix", True, "relu"),
                                                     ((768, 768), "bc_uniform", True, "tanh"), ((400, 400, 400), "policy_mix", False, "tanh"),
                                                     ((896, 896, 896, 896), "policy_gaussian", False, "tanh")])
-def test_deep_policy_guided(hidden, proposal, ln, act):
+def test_deep_policy_guided(hidden, proposal, ln, activation):
     """Policy-guided shooting (controllers.py:189-237, the legacy BC planner) on nets with more than two hidden layers (or 511..640
     units): the proposal phase of rollout_tmem_kernel at the top of every step of the cluster-split kernel, both K-half pairs
     computing the same actions from their bit-identical states."""
@@ -272,8 +272,8 @@ def test_deep_policy_guided(hidden, proposal, ln, act):
     K, H, S = 1000, 5, hidden[0]
     rng, norm, weights, state = O.synthetic_problem(49, hidden)
     lns = [(1.0 + 0.1 * rng.standard_normal(S).astype(np.float32), 0.1 * rng.standard_normal(S).astype(np.float32)) for _ in hidden] if ln else None
-    dyn = O.OracleDynamics(weights, norm, layer_norm=lns, activation=act)
-    pl = Planner(20, 6, len(hidden), S, act, num_paths=K, horizon=H, precision="bf16", proposal=proposal, explore=0.4)
+    dyn = O.OracleDynamics(weights, norm, layer_norm=lns, activation=activation)
+    pl = Planner(20, 6, len(hidden), S, activation, num_paths=K, horizon=H, precision="bf16", proposal=proposal, explore=0.4)
     pl.set_dynamics(weights)
     if ln:
         pl.set_layer_norm(lns)
@@ -293,7 +293,7 @@ def test_deep_policy_guided(hidden, proposal, ln, act):
     so, ao, co = pl.rollout_debug(state, inj)
     assert np.abs(ao[0] - dbg["actions"][0]).max() < 0.03           # first proposals: same state, bf16 policy net
     e = _norm_err(so, dbg["states"], norm)
-    print("deep policy", hidden, proposal, ln, act, "one-step", np.abs(e[1]).max(), "max", np.abs(e).max())
+    print("deep policy", hidden, proposal, ln, activation, "one-step", np.abs(e[1]).max(), "max", np.abs(e).max())
     assert np.abs(e[1]).max() < 0.15 and np.abs(e).max() < 1.0, (np.abs(e[1]).max(), np.abs(e).max())
     assert np.corrcoef(co, dbg["costs"])[0, 1] > 0.98
     rec = pl.plan(state, inj=inj)[0]
