@@ -171,7 +171,9 @@ int bcmpc_set_action_bounds(bcmpc_handle* h, const double* low, const double* hi
  * (RunningMeanStd mean/std as float32) may be NULL = no filter; clip <= 0 = no clipping.
  * BCMPC_PREC_BF16_FAST: two hidden layers of at most 256 units (MlpPolicy hid_size 128 / 256, BCnetwork 128 / 64); a network
  * with more than 128 units in a layer runs on kernel variants with a smaller weight ring, and switching between the two
- * classes re-packs the dynamics images.  Wider / deeper networks: BCMPC_ERR_UNSUPPORTED (verification mode takes any). */
+ * classes re-packs the dynamics images; next to a dynamics net on the cluster-split kernel (n_hidden > 2 or hidden_size > 510,
+ * which runs policy-guided shooting at 129..1024 hidden units) at most 128 units per layer.  Wider / deeper networks:
+ * BCMPC_ERR_UNSUPPORTED (verification mode takes any). */
 int bcmpc_set_policy(bcmpc_handle* h, int32_t n_layers, const int32_t* sizes, const float* const* W,
                      const float* const* b, const float* logstd, const float* filt_mean,
                      const float* filt_std, float clip);
