@@ -107,6 +107,8 @@ enum : uint32_t {
   kBarSig = 512,
   kMiscBytes = 576
 };
+static_assert(kBarPolFull + 8u <= kOffTmemPtr && kOffTmemPtr + 8u <= kOffRed && kOffRed + 80u <= kBarSig && kBarSig + 4u * 8u <= kMiscBytes,
+              "misc shared memory: barriers and scratch overlap");
 constexpr uint32_t kPolImgBytes = 6u * 4096u + 2u * 2048u;      // resident proposal network per CTA: [Wp1: 2 chunks][Wp2: 2 x 2][Wp3: 2 k-blocks] (tm_pack_policy, CTA-pair geometry)
 constexpr uint32_t kPolBytes = kPolImgBytes + tmx::kPolVecFloats * 4u;
 // LayerNorm: (sum, sum of squares) per path.  Remote slots (the partner CTA's partials): [0], [1] hidden 1 of the partner's group 0 / 1,
